@@ -1,0 +1,182 @@
+/*
+ * rgbdslam_b200.h -- C ABI of the B200-native RGB-D SLAM front-end hot path.
+ *
+ * Drop-in boundary for felixendres/rgbdslam_v2.  The
+ * reference has no FFI layer; its hot path is reached through C++ member calls
+ * (Node ctor, Node::matchNodePair, bruteForceSearchORB,
+ * GraphManager::optimizeGraph).  Every entry point below cites the reference
+ * interface it replaces (paths relative to the reference tree).  The C++ shim
+ * classes in include/rgbdslam_b200/ (Node, MatchingResult, LoadedEdge3D ...)
+ * keep those call sites compiling unchanged and forward to this ABI.
+ *
+ * Conventions
+ *  - plain C: pointers + sizes, POD structs, no exceptions, no torch types.
+ *  - every function returns 0 on success, non-zero on error;
+ *    rgbdslam_b200_last_error() returns a thread-local message.
+ *  - caller owns all host buffers.  Device memory is owned by the library
+ *    (node handles, workspaces) unless a function name ends in _device, in
+ *    which case the pointers are device pointers owned by the caller.
+ *  - there is NO CPU fallback: without a CUDA device every compute call fails
+ *    with RGBDSLAM_B200_ERR_CUDA.
+ */
+#ifndef RGBDSLAM_B200_H
+#define RGBDSLAM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RGBDSLAM_B200_OK 0
+#define RGBDSLAM_B200_ERR_ARG 1
+#define RGBDSLAM_B200_ERR_CUDA 2
+#define RGBDSLAM_B200_ERR_STATE 3
+#define RGBDSLAM_B200_ERR_NCCL 4
+
+#define RGBDSLAM_B200_MAX_MATCHES_CAP 512 /* hard upper bound for params.max_matches */
+
+/* Layout-compatible with cv::KeyPoint (7 x 4 B): node.h:167 feature_locations_2d_. */
+typedef struct rgbdslam_b200_keypoint {
+  float x, y;     /* pt */
+  float size;     /* 31 * 1.2^octave for ORB */
+  float angle;    /* degrees */
+  float response; /* Harris response */
+  int32_t octave;
+  int32_t class_id;
+} rgbdslam_b200_keypoint;
+
+/* Layout-compatible with cv::DMatch (4 x 4 B): matching_result.h:35-36. */
+typedef struct rgbdslam_b200_dmatch {
+  int32_t queryIdx; /* index into the newer node's features   */
+  int32_t trainIdx; /* index into the older node's features   */
+  int32_t imgIdx;   /* always -1 (cv::DMatch default)         */
+  float distance;   /* hd/256 + jitter (node.cpp:573)         */
+} rgbdslam_b200_dmatch;
+
+/*
+ * Hot-path parameters = the ParameterServer defaults the path reads
+ * (src/parameter_server.cpp).
+ */
+typedef struct rgbdslam_b200_params {
+  int32_t max_keypoints;        /* 600   parameter_server.cpp:83  */
+  int32_t min_matches;          /* 20    :85                      */
+  int32_t max_matches;          /* 300   :86  (<= MAX_MATCHES_CAP) */
+  int32_t ransac_iterations;    /* 200   :101                     */
+  double max_dist_for_inliers;  /* 3.0   :100 (Mahalanobis)       */
+  double sigma_depth;           /* 0.01  :46                      */
+  /*
+   * depth_covariance() in misc2.h:30-35 caches its FIRST result in a function
+   * static: cov_z is the constant (sigma_depth*z0^2)^2 of the first depth it
+   * ever sees.  depth_cov_z0 > 0 : use this z0 (deterministic emulation).
+   * depth_cov_z0 == 0 : latch z0 like the reference does -- from the first
+   * scored match of the first pair of the first match_pairs call.
+   * depth_cov_z0 < 0 : per-point covariance (sigma*z^2)^2 (quirk switched off).
+   */
+  double depth_cov_z0;
+  double depth_scaling_factor;  /* 1.0   :34                      */
+  int32_t detector_grid_resolution; /* 3 :87                      */
+  int32_t adjuster_max_iterations;  /* 5 :89                      */
+  double min_translation_meter; /* 0     :98                      */
+  double min_rotation_degree;   /* 0     :99                      */
+  double max_translation_meter; /* 1e10  :96                      */
+  double max_rotation_degree;   /* 360   :97                      */
+  double nn_distance_ratio;     /* 0.95  :160 (SIFT path)         */
+  int32_t use_root_sift;        /* 1     :92                      */
+  int32_t reserved_[7];
+} rgbdslam_b200_params;
+
+/*
+ * One frame pair = MatchingResult (matching_result.h:24-46) + LoadedEdge3D
+ * (edge.h:24-32) without the two std::vector<cv::DMatch>, which are returned in
+ * separate arrays (params.max_matches entries per pair).
+ */
+typedef struct rgbdslam_b200_pair_result {
+  int32_t id1, id2;        /* edge.id1 = older id, edge.id2 = newer id; -1,-1 = no transformation (node.cpp:1420) */
+  int32_t n_all_matches;   /* all_matches.size()   after keepStrongestMatches */
+  int32_t n_inliers;       /* inlier_matches.size() */
+  float rmse;              /* MatchingResult::rmse (Mahalanobis RMS of the inliers) */
+  int32_t valid_iterations;/* RANSAC iterations that produced a refined model (node.cpp:1170) */
+  float ransac_trafo[16];  /* Eigen::Matrix4f, column-major; maps newer-frame points into the older frame */
+  double info_scale;       /* edge.informationMatrix = I6 * info_scale, = n_inliers / rmse^2 (node.cpp:1335) */
+  int32_t used_identity;   /* 1 if the identity last-resort hypothesis was taken (node.cpp:1192-1215) */
+  int32_t reserved_;
+} rgbdslam_b200_pair_result;
+
+/* ---- library state ------------------------------------------------------- */
+
+/* Fill *p with the reference defaults (parameter_server.cpp:22-173). */
+void rgbdslam_b200_default_params(rgbdslam_b200_params* p);
+
+/* Select CUDA device + parameters.  Replaces ParameterServer::instance() for this path. */
+int rgbdslam_b200_init(int device, const rgbdslam_b200_params* p);
+int rgbdslam_b200_shutdown(void);
+
+/* Run all subsequent work on this cudaStream_t (NULL = the library's own stream). */
+int rgbdslam_b200_set_stream(void* cuda_stream);
+/* Block until all work queued by the library has finished. */
+int rgbdslam_b200_synchronize(void);
+
+const char* rgbdslam_b200_last_error(void);
+/* Number of kernels launched by this library since init (for bench gpu_launches). */
+int64_t rgbdslam_b200_launch_count(void);
+/* The z0 currently latched for depth_covariance (0 if not latched yet). */
+double rgbdslam_b200_depth_cov_z0(void);
+
+/* ---- brute-force ORB search ----------------------------------------------
+ * == bruteForceSearchORB (src/features.cpp:168-182) applied to nq query rows,
+ * i.e. the loop node.cpp:567-575 without the hd>=128 filter.  Quirk kept: only
+ * train rows [0, nt-2] are examined (features.cpp:174); lowest index wins ties;
+ * nt <= 1 gives hd = 257, idx = -1.  q/t are host buffers of nq*4 / nt*4 uint64. */
+int rgbdslam_b200_brute_force_orb(const uint64_t* q, int nq, const uint64_t* t, int nt,
+                                  int32_t* idx, int32_t* hd);
+
+/* ---- nodes ---------------------------------------------------------------
+ * A node handle owns the device copy of what Node keeps per frame
+ * (node.h:167-174): descriptors (N x 32 B), 3-D points (N x Vector4f). */
+
+/* Upload precomputed ORB features (host buffers).  desc: n*32 B, xyz1: n*4 float. */
+int rgbdslam_b200_node_create_from_features(int32_t id, const uint8_t* desc, const float* xyz1, int n,
+                                            uint64_t* node_handle);
+int rgbdslam_b200_node_num_features(uint64_t node_handle, int* n);
+/* Download (any pointer may be NULL). */
+int rgbdslam_b200_node_download(uint64_t node_handle, uint8_t* desc, float* xyz1);
+/* == Node::~Node (node.cpp:371). */
+int rgbdslam_b200_node_destroy(uint64_t node_handle);
+
+/* ---- frame-pair matching --------------------------------------------------
+ * == Node::matchNodePair (node.cpp:1305-1429) for npairs independent pairs
+ * (the QtConcurrent::blockingMapped fan-out of graph_manager.cpp:548 as one
+ * batched launch): featureMatching ORB branch (node.cpp:561-576,674) ->
+ * getRelativeTransformationTo (node.cpp:1074-1277) -> edge (node.cpp:1335-1339).
+ * The reference draws from global rand(); this ABI takes an explicit seed and
+ * uses a counter-based generator keyed by (seed, pair_index[, hypothesis]).
+ * pair_index = first_pair_index + position in the batch, so sharded callers
+ * reproduce the single-call results.
+ * all_matches / inlier_matches: npairs * params.max_matches entries (may be NULL). */
+int rgbdslam_b200_match_pairs(const uint64_t* newer, const uint64_t* older, int npairs,
+                              uint64_t seed, int64_t first_pair_index,
+                              rgbdslam_b200_pair_result* results,
+                              rgbdslam_b200_dmatch* all_matches,
+                              rgbdslam_b200_dmatch* inlier_matches);
+
+/* Same, but the nodes are given as host feature buffers (upload inside the call):
+ * desc_* : concatenated descriptors, xyz_* : concatenated points; n_*[i] features
+ * of pair i.  This is the "host buffers in, host results out" path used for the
+ * end-to-end measurement. */
+int rgbdslam_b200_match_pairs_host(const uint8_t* desc_newer, const float* xyz_newer, const int32_t* n_newer,
+                                   const uint8_t* desc_older, const float* xyz_older, const int32_t* n_older,
+                                   const int32_t* id_newer, const int32_t* id_older, int npairs,
+                                   uint64_t seed, int64_t first_pair_index,
+                                   rgbdslam_b200_pair_result* results,
+                                   rgbdslam_b200_dmatch* all_matches,
+                                   rgbdslam_b200_dmatch* inlier_matches);
+
+/* Timing hook: CUDA-event duration (ms) of the dominant kernel (Hamming match)
+ * and of the whole device part of the last match_pairs* call. */
+int rgbdslam_b200_last_timing(float* hamming_ms, float* total_device_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RGBDSLAM_B200_H */

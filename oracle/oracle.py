@@ -1,0 +1,150 @@
+"""ctypes wrapper of the C oracle (oracle/liboracle.so) -- TEST INFRASTRUCTURE, not product code.
+
+Only tests/, bench.py (cpu_baseline / --impl reference) and __graft_entry__.smoke() import this.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+
+DMATCH_DTYPE = np.dtype([("queryIdx", "<i4"), ("trainIdx", "<i4"), ("imgIdx", "<i4"), ("distance", "<f4")])
+RESULT_DTYPE = np.dtype([
+    ("id1", "<i4"), ("id2", "<i4"), ("n_all_matches", "<i4"), ("n_inliers", "<i4"), ("rmse", "<f4"),
+    ("valid_iterations", "<i4"), ("ransac_trafo", "<f4", (16,)), ("info_scale", "<f8"), ("used_identity", "<i4"),
+    ("real_iterations", "<i4"),
+])
+
+
+class OParams(C.Structure):
+    _fields_ = [("min_matches", C.c_int32), ("max_matches", C.c_int32), ("ransac_iterations", C.c_int32),
+                ("pad_", C.c_int32), ("max_dist_for_inliers", C.c_double), ("sigma_depth", C.c_double),
+                ("depth_cov_z0", C.c_double)]
+
+
+def build(force: bool = False) -> Path:
+    out = HERE / "liboracle.so"
+    srcs = sorted(HERE.glob("*.c"))
+    if force or not out.exists() or out.stat().st_mtime < max(s.stat().st_mtime for s in srcs + [HERE / "Makefile"]):
+        subprocess.run(["make", "-C", str(HERE), "all"], check=True, capture_output=True)
+    return out
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(str(build()))
+        _lib.oracle_rand31.restype = C.c_uint32
+        _lib.oracle_rand31.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32]
+        _lib.oracle_match_distance.restype = C.c_float
+        _lib.oracle_match_distance.argtypes = [C.c_int, C.c_uint32]
+        _lib.oracle_error_function2.restype = C.c_double
+    return _lib
+
+
+def ref_lib():
+    """The reference's own bruteForceSearchORB, compiled from /root/reference (None if not built)."""
+    p = HERE / "_ref" / "libref_features.so"
+    if not p.exists():
+        return None
+    return C.CDLL(str(p))
+
+
+def make_params(min_matches=20, max_matches=300, ransac_iterations=200, max_dist_for_inliers=3.0, sigma_depth=0.01,
+                depth_cov_z0=-1.0) -> OParams:
+    return OParams(min_matches, max_matches, ransac_iterations, 0, max_dist_for_inliers, sigma_depth, depth_cov_z0)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def brute_force_orb(q: np.ndarray, t: np.ndarray):
+    q = np.ascontiguousarray(q, np.uint8).reshape(-1, 32)
+    t = np.ascontiguousarray(t, np.uint8).reshape(-1, 32)
+    idx = np.empty(len(q), np.int32)
+    hd = np.empty(len(q), np.int32)
+    lib().oracle_brute_force_orb_batch(_p(q), C.c_int(len(q)), _p(t), C.c_int(len(t)), _p(idx), _p(hd))
+    return hd, idx
+
+
+def ref_brute_force_orb(q: np.ndarray, t: np.ndarray):
+    """Calls the REFERENCE function int bruteForceSearchORB(const uint64_t*, const uint64_t*, const unsigned&, int&)."""
+    rl = ref_lib()
+    fn = getattr(rl, "_Z19bruteForceSearchORBPKmS0_RKjRi")
+    fn.restype = C.c_int
+    q = np.ascontiguousarray(q, np.uint8).reshape(-1, 32)
+    t = np.ascontiguousarray(t, np.uint8).reshape(-1, 32)
+    idx = np.empty(len(q), np.int32)
+    hd = np.empty(len(q), np.int32)
+    size = C.c_uint(len(t))
+    for i in range(len(q)):
+        r = C.c_int(-7)
+        hd[i] = fn(C.c_void_p(q[i].ctypes.data), _p(t), C.byref(size), C.byref(r))
+        idx[i] = r.value
+    return hd, idx
+
+
+def feature_matching_orb(q, t, max_matches, seed, pair):
+    q = np.ascontiguousarray(q, np.uint8).reshape(-1, 32)
+    t = np.ascontiguousarray(t, np.uint8).reshape(-1, 32)
+    out = np.zeros(max(len(q), 1), DMATCH_DTYPE)
+    fn = lib().oracle_feature_matching_orb
+    fn.restype = C.c_int
+    n = fn(_p(q), C.c_int(len(q)), _p(t), C.c_int(len(t)), C.c_int(max_matches), C.c_uint64(seed), C.c_uint64(pair), _p(out))
+    return out[:n]
+
+
+def match_pairs(params: OParams, desc_newer, xyz_newer, n_newer, desc_older, xyz_older, n_older, id_newer=None,
+                id_older=None, seed=0, first_pair_index=0, threads=1, want_matches=True):
+    n_newer = np.ascontiguousarray(n_newer, np.int32)
+    n_older = np.ascontiguousarray(n_older, np.int32)
+    npairs = len(n_newer)
+    res = np.zeros(npairs, RESULT_DTYPE)
+    allm = np.zeros((npairs, params.max_matches), DMATCH_DTYPE) if want_matches else None
+    inl = np.zeros((npairs, params.max_matches), DMATCH_DTYPE) if want_matches else None
+    idn = None if id_newer is None else np.ascontiguousarray(id_newer, np.int32)
+    ido = None if id_older is None else np.ascontiguousarray(id_older, np.int32)
+    d1 = np.ascontiguousarray(desc_newer, np.uint8)
+    x1 = np.ascontiguousarray(xyz_newer, np.float32)
+    d2 = np.ascontiguousarray(desc_older, np.uint8)
+    x2 = np.ascontiguousarray(xyz_older, np.float32)
+    lib().oracle_match_pairs(C.byref(params), _p(d1), _p(x1), _p(n_newer), _p(d2), _p(x2), _p(n_older), _p(idn), _p(ido),
+                             C.c_int(npairs), C.c_uint64(seed), C.c_int64(first_pair_index), _p(res), _p(allm), _p(inl),
+                             C.c_int(threads))
+    return res, allm, inl
+
+
+def get_transform_from_matches(xyz_newer, xyz_older, matches):
+    x1 = np.ascontiguousarray(xyz_newer, np.float32)
+    x2 = np.ascontiguousarray(xyz_older, np.float32)
+    m = np.ascontiguousarray(matches)
+    T = np.zeros(16, np.float32)
+    lib().oracle_get_transform_from_matches(_p(x1), _p(x2), _p(m), None, C.c_int(len(m)), _p(T))
+    return T.reshape(4, 4).T.copy()  # column-major -> numpy row/col
+
+
+def error_function2(params: OParams, x1, x2, T4x4):
+    a = np.ascontiguousarray(x1, np.float32)
+    b = np.ascontiguousarray(x2, np.float32)
+    Tc = np.ascontiguousarray(np.asarray(T4x4, np.float64).T.reshape(-1))  # column-major
+    return lib().oracle_error_function2(C.byref(params), _p(a), _p(b), _p(Tc))
+
+
+def first_depth_z0(params: OParams, allm_row, n_all, xyz_newer, xyz_older):
+    """z of the first correspondence errorFunction2 would see for this pair (misc2.h:30-35 latch emulation)."""
+    if n_all <= params.min_matches:
+        return 0.0
+    for m in allm_row[:n_all]:
+        zf, zt = xyz_newer[m["queryIdx"], 2], xyz_older[m["trainIdx"], 2]
+        if zf == 0 or zt == 0 or np.isnan(zf) or np.isnan(zt):
+            continue
+        return float(zf)
+    return 0.0

@@ -1,0 +1,253 @@
+"""ctypes binding of include/rgbdslam_b200.h + a small host-side mirror of the reference interface.
+
+Only plumbing lives here.  Every compute call goes through the C ABI into the CUDA library; if the
+library cannot be loaded the import of this module still works (so CPU-only tests can inspect the
+header), but any attempt to use it raises :class:`LibraryMissingError` -- there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+
+from .build import library_path
+
+MAX_MATCHES_CAP = 512
+
+
+class LibraryMissingError(RuntimeError):
+    pass
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+class KeyPoint(C.Structure):  # == cv::KeyPoint
+    _fields_ = [("x", C.c_float), ("y", C.c_float), ("size", C.c_float), ("angle", C.c_float),
+                ("response", C.c_float), ("octave", C.c_int32), ("class_id", C.c_int32)]
+
+
+class DMatch(C.Structure):  # == cv::DMatch
+    _fields_ = [("queryIdx", C.c_int32), ("trainIdx", C.c_int32), ("imgIdx", C.c_int32), ("distance", C.c_float)]
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("max_keypoints", C.c_int32), ("min_matches", C.c_int32), ("max_matches", C.c_int32),
+        ("ransac_iterations", C.c_int32), ("max_dist_for_inliers", C.c_double), ("sigma_depth", C.c_double),
+        ("depth_cov_z0", C.c_double), ("depth_scaling_factor", C.c_double),
+        ("detector_grid_resolution", C.c_int32), ("adjuster_max_iterations", C.c_int32),
+        ("min_translation_meter", C.c_double), ("min_rotation_degree", C.c_double),
+        ("max_translation_meter", C.c_double), ("max_rotation_degree", C.c_double),
+        ("nn_distance_ratio", C.c_double), ("use_root_sift", C.c_int32), ("reserved_", C.c_int32 * 7),
+    ]
+
+
+class PairResult(C.Structure):
+    _fields_ = [
+        ("id1", C.c_int32), ("id2", C.c_int32), ("n_all_matches", C.c_int32), ("n_inliers", C.c_int32),
+        ("rmse", C.c_float), ("valid_iterations", C.c_int32), ("ransac_trafo", C.c_float * 16),
+        ("info_scale", C.c_double), ("used_identity", C.c_int32), ("reserved_", C.c_int32),
+    ]
+
+
+DMATCH_DTYPE = np.dtype([("queryIdx", "<i4"), ("trainIdx", "<i4"), ("imgIdx", "<i4"), ("distance", "<f4")])
+KEYPOINT_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                           ("octave", "<i4"), ("class_id", "<i4")])
+PAIR_RESULT_DTYPE = np.dtype([
+    ("id1", "<i4"), ("id2", "<i4"), ("n_all_matches", "<i4"), ("n_inliers", "<i4"), ("rmse", "<f4"),
+    ("valid_iterations", "<i4"), ("ransac_trafo", "<f4", (16,)), ("info_scale", "<f8"), ("used_identity", "<i4"),
+    ("reserved_", "<i4"),
+])
+assert PAIR_RESULT_DTYPE.itemsize == C.sizeof(PairResult) == 104
+assert DMATCH_DTYPE.itemsize == C.sizeof(DMatch) == 16
+assert KEYPOINT_DTYPE.itemsize == C.sizeof(KeyPoint) == 28
+
+_lib = None
+
+
+def header_path() -> Path:
+    return Path(__file__).resolve().parent.parent / "include" / "rgbdslam_b200.h"
+
+
+def declared_symbols() -> list[str]:
+    """All function names declared in include/*.h (used by the CPU-only export test)."""
+    names = []
+    for h in sorted(header_path().parent.glob("*.h")):
+        txt = re.sub(r"/\*.*?\*/", "", h.read_text(), flags=re.S)
+        names += re.findall(r"\b(rgbdslam_b200_[a-z0-9_]+)\s*\(", txt)
+    return sorted(set(names))
+
+
+def load_library(path: str | Path | None = None) -> C.CDLL:
+    """dlopen the CUDA library and set up prototypes.  Raises LibraryMissingError if it is absent."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = Path(path) if path else library_path()
+    if not p.exists():
+        raise LibraryMissingError(
+            f"{p} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  rgbdslam_v2_b200 has no CPU fallback.")
+    lib = C.CDLL(str(p))
+    u64, i64, i32p = C.c_uint64, C.c_int64, C.POINTER(C.c_int32)
+    vp = C.c_void_p
+    lib.rgbdslam_b200_default_params.argtypes = [C.POINTER(Params)]
+    lib.rgbdslam_b200_default_params.restype = None
+    lib.rgbdslam_b200_init.argtypes = [C.c_int, C.POINTER(Params)]
+    lib.rgbdslam_b200_shutdown.argtypes = []
+    lib.rgbdslam_b200_set_stream.argtypes = [vp]
+    lib.rgbdslam_b200_synchronize.argtypes = []
+    lib.rgbdslam_b200_last_error.argtypes = []
+    lib.rgbdslam_b200_last_error.restype = C.c_char_p
+    lib.rgbdslam_b200_launch_count.argtypes = []
+    lib.rgbdslam_b200_launch_count.restype = i64
+    lib.rgbdslam_b200_depth_cov_z0.argtypes = []
+    lib.rgbdslam_b200_depth_cov_z0.restype = C.c_double
+    lib.rgbdslam_b200_brute_force_orb.argtypes = [vp, C.c_int, vp, C.c_int, vp, vp]
+    lib.rgbdslam_b200_node_create_from_features.argtypes = [C.c_int32, vp, vp, C.c_int, C.POINTER(u64)]
+    lib.rgbdslam_b200_node_num_features.argtypes = [u64, C.POINTER(C.c_int)]
+    lib.rgbdslam_b200_node_download.argtypes = [u64, vp, vp]
+    lib.rgbdslam_b200_node_destroy.argtypes = [u64]
+    lib.rgbdslam_b200_match_pairs.argtypes = [vp, vp, C.c_int, u64, i64, vp, vp, vp]
+    lib.rgbdslam_b200_match_pairs_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, u64, i64, vp, vp, vp]
+    lib.rgbdslam_b200_last_timing.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    for name in declared_symbols():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+        if fn.restype is C.c_int and name not in ("rgbdslam_b200_default_params",):
+            fn.restype = C.c_int
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def default_params() -> Params:
+    p = Params()
+    load_library().rgbdslam_b200_default_params(C.byref(p))
+    return p
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        assert a.flags.c_contiguous
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):  # torch tensor (pinned host memory for the e2e path)
+        assert a.is_contiguous()
+        return a.data_ptr()
+    raise TypeError(type(a))
+
+
+class Frontend:
+    """Host-side mirror of the reference's front-end interface for this path.
+
+    ``Frontend.match_node_pairs`` == ``Node::matchNodePair`` (node.cpp:1305) for a batch of pairs,
+    ``Frontend.brute_force_search_orb`` == ``bruteForceSearchORB`` (features.cpp:168) per query row.
+    """
+
+    def __init__(self, device: int = 0, params: Params | None = None):
+        self.lib = load_library()
+        self.params = params if params is not None else default_params()
+        self._check(self.lib.rgbdslam_b200_init(device, C.byref(self.params)))
+        self._nodes: list[int] = []
+
+    # -- helpers -----------------------------------------------------------
+    def _check(self, rc: int):
+        if rc != 0:
+            raise B200Error(f"rgbdslam_b200 error {rc}: {self.lib.rgbdslam_b200_last_error().decode()}")
+
+    def set_stream(self, stream_ptr: int | None):
+        self._check(self.lib.rgbdslam_b200_set_stream(stream_ptr))
+
+    def synchronize(self):
+        self._check(self.lib.rgbdslam_b200_synchronize())
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.rgbdslam_b200_launch_count())
+
+    @property
+    def depth_cov_z0(self) -> float:
+        return float(self.lib.rgbdslam_b200_depth_cov_z0())
+
+    def last_timing(self) -> tuple[float, float]:
+        a, b = C.c_float(), C.c_float()
+        self._check(self.lib.rgbdslam_b200_last_timing(C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    # -- bruteForceSearchORB ------------------------------------------------
+    def brute_force_search_orb(self, q: np.ndarray, t: np.ndarray):
+        q = np.ascontiguousarray(q, dtype=np.uint8).reshape(-1, 32)
+        t = np.ascontiguousarray(t, dtype=np.uint8).reshape(-1, 32)
+        idx = np.empty(len(q), np.int32)
+        hd = np.empty(len(q), np.int32)
+        self._check(self.lib.rgbdslam_b200_brute_force_orb(_ptr(q), len(q), _ptr(t), len(t), _ptr(idx), _ptr(hd)))
+        return hd, idx
+
+    # -- nodes ----------------------------------------------------------------
+    def node_from_features(self, node_id: int, desc: np.ndarray, xyz1: np.ndarray) -> int:
+        desc = np.ascontiguousarray(desc, dtype=np.uint8).reshape(-1, 32)
+        xyz1 = np.ascontiguousarray(xyz1, dtype=np.float32).reshape(-1, 4)
+        assert len(desc) == len(xyz1)
+        h = C.c_uint64()
+        self._check(self.lib.rgbdslam_b200_node_create_from_features(node_id, _ptr(desc), _ptr(xyz1), len(desc), C.byref(h)))
+        self._nodes.append(h.value)
+        return h.value
+
+    def node_num_features(self, h: int) -> int:
+        n = C.c_int()
+        self._check(self.lib.rgbdslam_b200_node_num_features(h, C.byref(n)))
+        return n.value
+
+    def node_download(self, h: int):
+        n = self.node_num_features(h)
+        desc = np.empty((n, 32), np.uint8)
+        xyz = np.empty((n, 4), np.float32)
+        self._check(self.lib.rgbdslam_b200_node_download(h, _ptr(desc), _ptr(xyz)))
+        return desc, xyz
+
+    def node_destroy(self, h: int):
+        self._check(self.lib.rgbdslam_b200_node_destroy(h))
+        if h in self._nodes:
+            self._nodes.remove(h)
+
+    # -- matchNodePair ----------------------------------------------------------
+    def _alloc_out(self, npairs, want_matches):
+        res = np.zeros(npairs, PAIR_RESULT_DTYPE)
+        mm = self.params.max_matches
+        allm = np.zeros((npairs, mm), DMATCH_DTYPE) if want_matches else None
+        inl = np.zeros((npairs, mm), DMATCH_DTYPE) if want_matches else None
+        return res, allm, inl
+
+    def match_node_pairs(self, newer: list[int], older: list[int], seed: int = 0, first_pair_index: int = 0,
+                         want_matches: bool = True, out=None):
+        npairs = len(newer)
+        a = np.asarray(newer, dtype=np.uint64)
+        b = np.asarray(older, dtype=np.uint64)
+        res, allm, inl = out if out is not None else self._alloc_out(npairs, want_matches)
+        self._check(self.lib.rgbdslam_b200_match_pairs(_ptr(a), _ptr(b), npairs, seed, first_pair_index,
+                                                       _ptr(res), _ptr(allm), _ptr(inl)))
+        return res, allm, inl
+
+    def match_pairs_host(self, desc_newer, xyz_newer, n_newer, desc_older, xyz_older, n_older, id_newer=None,
+                         id_older=None, seed: int = 0, first_pair_index: int = 0, want_matches: bool = True, out=None):
+        """Host feature buffers in (numpy or pinned torch tensors), host results out."""
+        n_newer = np.ascontiguousarray(n_newer, dtype=np.int32)
+        n_older = np.ascontiguousarray(n_older, dtype=np.int32)
+        npairs = len(n_newer)
+        idn = None if id_newer is None else np.ascontiguousarray(id_newer, dtype=np.int32)
+        ido = None if id_older is None else np.ascontiguousarray(id_older, dtype=np.int32)
+        res, allm, inl = out if out is not None else self._alloc_out(npairs, want_matches)
+        self._check(self.lib.rgbdslam_b200_match_pairs_host(
+            _ptr(desc_newer), _ptr(xyz_newer), _ptr(n_newer), _ptr(desc_older), _ptr(xyz_older), _ptr(n_older),
+            _ptr(idn), _ptr(ido), npairs, seed, first_pair_index, _ptr(res), _ptr(allm), _ptr(inl)))
+        return res, allm, inl
+
+    def close(self):
+        for h in list(self._nodes):
+            self.lib.rgbdslam_b200_node_destroy(h)
+        self._nodes.clear()

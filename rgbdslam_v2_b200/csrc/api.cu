@@ -1,0 +1,564 @@
+// api.cu -- the extern "C" boundary declared in include/rgbdslam_b200.h.
+// Host-side orchestration only: device memory, streams, workspaces, launches.  There is no CPU
+// compute path in this file: every entry point that computes anything requires a CUDA device.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+#include "state.h"
+
+namespace rb200 {
+
+static thread_local std::string t_last_error;
+State g_state;
+
+void set_error(const std::string& s) { t_last_error = s; }
+
+int cuda_fail(cudaError_t e, const char* what) {
+  char buf[512];
+  snprintf(buf, sizeof(buf), "CUDA error in %s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+  set_error(buf);
+  return RGBDSLAM_B200_ERR_CUDA;
+}
+
+int DevBuf::ensure(size_t bytes) {
+  if (bytes <= cap) return 0;
+  if (ptr) cudaFree(ptr);
+  ptr = nullptr;
+  cap = 0;
+  size_t want = bytes + bytes / 4 + 256;
+  cudaError_t e = cudaMalloc(&ptr, want);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(workspace)");
+  cap = want;
+  return 0;
+}
+void DevBuf::release() {
+  if (ptr) cudaFree(ptr);
+  ptr = nullptr;
+  cap = 0;
+}
+int PinBuf::ensure(size_t bytes) {
+  if (bytes <= cap) return 0;
+  if (ptr) cudaFreeHost(ptr);
+  ptr = nullptr;
+  cap = 0;
+  size_t want = bytes + bytes / 4 + 256;
+  cudaError_t e = cudaMallocHost(&ptr, want);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMallocHost(staging)");
+  cap = want;
+  return 0;
+}
+void PinBuf::release() {
+  if (ptr) cudaFreeHost(ptr);
+  ptr = nullptr;
+  cap = 0;
+}
+
+static void make_dev_params(const rgbdslam_b200_params& p, double z0, DevParams& d) {
+  d.min_matches = p.min_matches;
+  d.max_matches = p.max_matches;
+  d.ransac_iterations = p.ransac_iterations;
+  d.pad_ = 0;
+  d.max_dist_m = (float)p.max_dist_for_inliers;              // node.cpp:1105 (const float max_dist_m)
+  d.sq_max_dist = (double)(d.max_dist_m * d.max_dist_m);     // node.cpp:1152 (float product promoted)
+  d.sigma_depth = p.sigma_depth;
+  if (p.depth_cov_z0 < 0) {
+    d.cov_z_const = -1.0;
+  } else {
+    const double sd = p.sigma_depth * z0 * z0;  // misc2.h:20-35, first-call static cache
+    d.cov_z_const = sd * sd;
+  }
+  // misc.cpp:702-709
+  const double cam_angle_x = 58.0 / 180.0 * M_PI, cam_angle_y = 45.0 / 180.0 * M_PI;
+  const double rsx = 3 * tan(cam_angle_x / 640), rsy = 3 * tan(cam_angle_y / 480);
+  d.raster_cov_x = rsx * rsx;
+  d.raster_cov_y = rsy * rsy;
+}
+
+int check_inited() {
+  if (!g_state.inited) {
+    set_error("rgbdslam_b200_init() has not been called");
+    return RGBDSLAM_B200_ERR_STATE;
+  }
+  cudaError_t e = cudaSetDevice(g_state.device);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+  return 0;
+}
+
+static int push_dev_params() {
+  State& s = g_state;
+  make_dev_params(s.params, s.z0, s.dp);
+  cudaError_t e = set_dev_params(s.dp, s.stream);
+  if (e != cudaSuccess) return cuda_fail(e, "set_dev_params");
+  // the constant upload reads s.dp asynchronously from pageable memory -> staged by the runtime; safe.
+  return 0;
+}
+
+// Hamming stage dispatcher (counts the launch).
+static cudaError_t launch_hamming(const PairDesc* d_pairs, const PairDesc* h_pairs, int npairs, int max_nq, int2* best,
+                                  int stride, cudaStream_t st) {
+  (void)h_pairs;
+  g_state.launches += 1;
+  return launch_hamming_simt(d_pairs, npairs, max_nq, best, stride, st);
+}
+
+// Core of match_pairs*: h_pairs (device pointers inside) -> results on the host.
+static int run_pairs(const std::vector<PairDesc>& h_pairs, uint64_t seed, int64_t first_pair,
+                     rgbdslam_b200_pair_result* results, rgbdslam_b200_dmatch* all_matches,
+                     rgbdslam_b200_dmatch* inlier_matches) {
+  State& s = g_state;
+  const int npairs = (int)h_pairs.size();
+  if (npairs == 0) return 0;
+  int max_nq = 0;
+  for (const PairDesc& pd : h_pairs) {
+    if (pd.nq > kMaxFeatures || pd.nt > kMaxFeatures) {
+      set_error("node has more than 4096 features");
+      return RGBDSLAM_B200_ERR_ARG;
+    }
+    max_nq = pd.nq > max_nq ? pd.nq : max_nq;
+  }
+  const int stride = (max_nq + 127) / 128 * 128 + 128;
+  const int maxM = s.params.max_matches;
+  const int H = s.params.ransac_iterations;
+  int rc;
+  if ((rc = s.d_pairs.ensure(sizeof(PairDesc) * npairs))) return rc;
+  if ((rc = s.h_pairs.ensure(sizeof(PairDesc) * npairs))) return rc;
+  if ((rc = s.d_best.ensure(sizeof(int2) * (size_t)npairs * stride))) return rc;
+  if ((rc = s.d_matches.ensure(sizeof(rgbdslam_b200_dmatch) * (size_t)npairs * maxM))) return rc;
+  if ((rc = s.d_inliers.ensure(sizeof(rgbdslam_b200_dmatch) * (size_t)npairs * maxM))) return rc;
+  if ((rc = s.d_mfrom.ensure(sizeof(float4) * (size_t)npairs * maxM))) return rc;
+  if ((rc = s.d_mto.ensure(sizeof(float4) * (size_t)npairs * maxM))) return rc;
+  if ((rc = s.d_nall.ensure(sizeof(int32_t) * npairs))) return rc;
+  if ((rc = s.d_hyp.ensure(sizeof(HypResult) * (size_t)npairs * (H > 0 ? H : 1)))) return rc;
+  if ((rc = s.d_results.ensure(sizeof(rgbdslam_b200_pair_result) * npairs))) return rc;
+
+  cudaStream_t st = s.stream;
+  cudaError_t e;
+  memcpy(s.h_pairs.ptr, h_pairs.data(), sizeof(PairDesc) * npairs);
+  e = cudaMemcpyAsync(s.d_pairs.ptr, s.h_pairs.ptr, sizeof(PairDesc) * npairs, cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) return cuda_fail(e, "upload pair table");
+  const PairDesc* d_pairs = (const PairDesc*)s.d_pairs.ptr;
+
+  cudaEventRecord(s.ev[0], st);
+  e = launch_hamming(d_pairs, h_pairs.data(), npairs, max_nq, (int2*)s.d_best.ptr, stride, st);
+  if (e != cudaSuccess) return cuda_fail(e, "hamming kernel");
+  cudaEventRecord(s.ev[1], st);
+  e = launch_select_matches(d_pairs, npairs, (const int2*)s.d_best.ptr, stride, seed, first_pair,
+                            (rgbdslam_b200_dmatch*)s.d_matches.ptr, (float4*)s.d_mfrom.ptr, (float4*)s.d_mto.ptr,
+                            (int32_t*)s.d_nall.ptr, max_nq, st);
+  if (e != cudaSuccess) return cuda_fail(e, "select_matches kernel");
+  s.launches += 1;
+
+  if (s.params.depth_cov_z0 == 0.0 && s.z0 == 0.0) {
+    // Emulate the function-static of depth_covariance (misc2.h:30-35): latch the z of the first
+    // correspondence errorFunction2 would see -- first pair that reaches RANSAC, first sorted match with
+    // non-zero, non-NaN depth on both sides (node.cpp:994, misc.cpp:711-716).
+    std::vector<int32_t> nall(npairs);
+    e = cudaMemcpyAsync(nall.data(), s.d_nall.ptr, sizeof(int32_t) * npairs, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return cuda_fail(e, "z0 latch (n_all)");
+    for (int p = 0; p < npairs && s.z0 == 0.0; p++) {
+      if (nall[p] <= s.params.min_matches) continue;
+      std::vector<float4> f(nall[p]), t(nall[p]);
+      cudaMemcpyAsync(f.data(), (float4*)s.d_mfrom.ptr + (size_t)p * maxM, sizeof(float4) * nall[p],
+                      cudaMemcpyDeviceToHost, st);
+      cudaMemcpyAsync(t.data(), (float4*)s.d_mto.ptr + (size_t)p * maxM, sizeof(float4) * nall[p],
+                      cudaMemcpyDeviceToHost, st);
+      e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) return cuda_fail(e, "z0 latch (points)");
+      for (int i = 0; i < nall[p]; i++) {
+        if (f[i].z == 0.f || t[i].z == 0.f) continue;
+        if (std::isnan(f[i].z) || std::isnan(t[i].z)) continue;
+        s.z0 = (double)f[i].z;
+        break;
+      }
+    }
+    if (s.z0 != 0.0 && (rc = push_dev_params())) return rc;
+  }
+
+  e = launch_ransac_hypotheses(npairs, H, maxM, seed, first_pair, (const float4*)s.d_mfrom.ptr,
+                               (const float4*)s.d_mto.ptr, (const int32_t*)s.d_nall.ptr, (HypResult*)s.d_hyp.ptr, st);
+  if (e != cudaSuccess) return cuda_fail(e, "ransac_hyp kernel");
+  e = launch_ransac_select(d_pairs, npairs, H, maxM, (const float4*)s.d_mfrom.ptr, (const float4*)s.d_mto.ptr,
+                           (const int32_t*)s.d_nall.ptr, (const rgbdslam_b200_dmatch*)s.d_matches.ptr,
+                           (const HypResult*)s.d_hyp.ptr, (rgbdslam_b200_pair_result*)s.d_results.ptr,
+                           (rgbdslam_b200_dmatch*)s.d_inliers.ptr, st);
+  if (e != cudaSuccess) return cuda_fail(e, "ransac_select kernel");
+  s.launches += 2;
+  cudaEventRecord(s.ev[2], st);
+
+  if (results) {
+    e = cudaMemcpyAsync(results, s.d_results.ptr, sizeof(rgbdslam_b200_pair_result) * npairs, cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) return cuda_fail(e, "download results");
+  }
+  if (all_matches) {
+    e = cudaMemcpyAsync(all_matches, s.d_matches.ptr, sizeof(rgbdslam_b200_dmatch) * (size_t)npairs * maxM,
+                        cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) return cuda_fail(e, "download all_matches");
+  }
+  if (inlier_matches) {
+    e = cudaMemcpyAsync(inlier_matches, s.d_inliers.ptr, sizeof(rgbdslam_b200_dmatch) * (size_t)npairs * maxM,
+                        cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) return cuda_fail(e, "download inlier_matches");
+  }
+  e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return cuda_fail(e, "match_pairs synchronize");
+  s.timing_valid = true;
+  return 0;
+}
+
+}  // namespace rb200
+
+using namespace rb200;
+
+extern "C" {
+
+void rgbdslam_b200_default_params(rgbdslam_b200_params* p) {
+  if (!p) return;
+  memset(p, 0, sizeof(*p));
+  p->max_keypoints = 600;
+  p->min_matches = 20;
+  p->max_matches = 300;
+  p->ransac_iterations = 200;
+  p->max_dist_for_inliers = 3.0;
+  p->sigma_depth = 0.01;
+  p->depth_cov_z0 = 0.0;
+  p->depth_scaling_factor = 1.0;
+  p->detector_grid_resolution = 3;
+  p->adjuster_max_iterations = 5;
+  p->min_translation_meter = 0.0;
+  p->min_rotation_degree = 0.0;
+  p->max_translation_meter = 1e10;
+  p->max_rotation_degree = 360.0;
+  p->nn_distance_ratio = 0.95;
+  p->use_root_sift = 1;
+}
+
+const char* rgbdslam_b200_last_error(void) { return t_last_error.c_str(); }
+
+int rgbdslam_b200_init(int device, const rgbdslam_b200_params* p) {
+  std::lock_guard<std::mutex> lk(g_state.mu);
+  State& s = g_state;
+  rgbdslam_b200_params prm;
+  if (p) prm = *p;
+  else rgbdslam_b200_default_params(&prm);
+  if (prm.max_matches < 1 || prm.max_matches > RGBDSLAM_B200_MAX_MATCHES_CAP || prm.min_matches < 0 ||
+      prm.ransac_iterations < 0 || prm.ransac_iterations > 100000) {
+    set_error("invalid parameters (max_matches must be in [1,512], ransac_iterations in [0,100000])");
+    return RGBDSLAM_B200_ERR_ARG;
+  }
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount (no CUDA device: this library has no CPU fallback)");
+  if (device < 0 || device >= count) {
+    set_error("device index out of range");
+    return RGBDSLAM_B200_ERR_ARG;
+  }
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceProperties");
+  if (prop.major != 10) {
+    set_error(std::string("this build targets sm_100a (B200); device is ") + prop.name);
+    return RGBDSLAM_B200_ERR_CUDA;
+  }
+  if (!s.inited) {
+    e = cudaStreamCreateWithFlags(&s.own_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
+    for (int i = 0; i < 4; i++) {
+      e = cudaEventCreate(&s.ev[i]);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
+    }
+    s.stream = s.own_stream;
+    s.launches = 0;
+  }
+  s.device = device;
+  s.sm_count = prop.multiProcessorCount;
+  s.params = prm;
+  s.z0 = prm.depth_cov_z0 > 0 ? prm.depth_cov_z0 : 0.0;
+  s.inited = true;
+  s.timing_valid = false;
+  int rc = push_dev_params();
+  if (rc) return rc;
+  e = cudaStreamSynchronize(s.stream);
+  if (e != cudaSuccess) return cuda_fail(e, "init synchronize");
+  return 0;
+}
+
+int rgbdslam_b200_shutdown(void) {
+  std::lock_guard<std::mutex> lk(g_state.mu);
+  State& s = g_state;
+  if (!s.inited) return 0;
+  cudaSetDevice(s.device);
+  cudaDeviceSynchronize();
+  s.release_workspaces();
+  for (int i = 0; i < 4; i++) cudaEventDestroy(s.ev[i]);
+  cudaStreamDestroy(s.own_stream);
+  s.inited = false;
+  return 0;
+}
+
+int rgbdslam_b200_set_stream(void* cuda_stream) {
+  std::lock_guard<std::mutex> lk(g_state.mu);
+  int rc = check_inited();
+  if (rc) return rc;
+  g_state.stream = cuda_stream ? (cudaStream_t)cuda_stream : g_state.own_stream;
+  return push_dev_params();  // constant memory is per-context, but keep ordering on the new stream
+}
+
+int rgbdslam_b200_synchronize(void) {
+  std::lock_guard<std::mutex> lk(g_state.mu);
+  int rc = check_inited();
+  if (rc) return rc;
+  cudaError_t e = cudaStreamSynchronize(g_state.stream);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaStreamSynchronize");
+  return 0;
+}
+
+int64_t rgbdslam_b200_launch_count(void) { return g_state.launches; }
+double rgbdslam_b200_depth_cov_z0(void) { return g_state.z0; }
+
+int rgbdslam_b200_last_timing(float* hamming_ms, float* total_device_ms) {
+  std::lock_guard<std::mutex> lk(g_state.mu);
+  int rc = check_inited();
+  if (rc) return rc;
+  if (!g_state.timing_valid) {
+    set_error("no match_pairs call has completed yet");
+    return RGBDSLAM_B200_ERR_STATE;
+  }
+  float a = 0, b = 0;
+  cudaError_t e = cudaEventElapsedTime(&a, g_state.ev[0], g_state.ev[1]);
+  if (e == cudaSuccess) e = cudaEventElapsedTime(&b, g_state.ev[0], g_state.ev[2]);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaEventElapsedTime");
+  if (hamming_ms) *hamming_ms = a;
+  if (total_device_ms) *total_device_ms = b;
+  return 0;
+}
+
+int rgbdslam_b200_brute_force_orb(const uint64_t* q, int nq, const uint64_t* t, int nt, int32_t* idx, int32_t* hd) {
+  std::lock_guard<std::mutex> lk(g_state.mu);
+  int rc = check_inited();
+  if (rc) return rc;
+  if (nq < 0 || nt < 0 || (nq > 0 && (!q || !idx || !hd)) || (nt > 0 && !t)) {
+    set_error("brute_force_orb: bad arguments");
+    return RGBDSLAM_B200_ERR_ARG;
+  }
+  if (nq == 0) return 0;
+  if (nq > kMaxFeatures || nt > kMaxFeatures) {
+    set_error("brute_force_orb: more than 4096 descriptors");
+    return RGBDSLAM_B200_ERR_ARG;
+  }
+  State& s = g_state;
+  const int stride = (nq + 127) / 128 * 128 + 128;
+  if ((rc = s.d_feat_a.ensure(32 * (size_t)nq))) return rc;
+  if ((rc = s.d_feat_b.ensure(32 * (size_t)(nt > 0 ? nt : 1)))) return rc;
+  if ((rc = s.d_best.ensure(sizeof(int2) * (size_t)stride))) return rc;
+  if ((rc = s.d_pairs.ensure(sizeof(PairDesc)))) return rc;
+  if ((rc = s.h_pairs.ensure(sizeof(PairDesc)))) return rc;
+  cudaStream_t st = s.stream;
+  cudaError_t e = cudaMemcpyAsync(s.d_feat_a.ptr, q, 32 * (size_t)nq, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && nt > 0) e = cudaMemcpyAsync(s.d_feat_b.ptr, t, 32 * (size_t)nt, cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) return cuda_fail(e, "brute_force_orb upload");
+  PairDesc pd;
+  pd.q_desc = (const uint32_t*)s.d_feat_a.ptr;
+  pd.t_desc = (const uint32_t*)s.d_feat_b.ptr;
+  pd.q_xyz = nullptr;
+  pd.t_xyz = nullptr;
+  pd.nq = nq;
+  pd.nt = nt;
+  pd.id_q = pd.id_t = 0;
+  memcpy(s.h_pairs.ptr, &pd, sizeof(pd));
+  e = cudaMemcpyAsync(s.d_pairs.ptr, s.h_pairs.ptr, sizeof(pd), cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) return cuda_fail(e, "brute_force_orb pair upload");
+  e = launch_hamming((const PairDesc*)s.d_pairs.ptr, &pd, 1, nq, (int2*)s.d_best.ptr, stride, st);
+  if (e != cudaSuccess) return cuda_fail(e, "hamming kernel");
+  std::vector<int2> h(nq);
+  e = cudaMemcpyAsync(h.data(), s.d_best.ptr, sizeof(int2) * nq, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return cuda_fail(e, "brute_force_orb download");
+  for (int i = 0; i < nq; i++) {
+    hd[i] = h[i].x;
+    idx[i] = h[i].y;
+  }
+  return 0;
+}
+
+int rgbdslam_b200_node_create_from_features(int32_t id, const uint8_t* desc, const float* xyz1, int n,
+                                            uint64_t* node_handle) {
+  std::lock_guard<std::mutex> lk(g_state.mu);
+  int rc = check_inited();
+  if (rc) return rc;
+  if (!node_handle || n < 0 || n > kMaxFeatures || (n > 0 && (!desc || !xyz1))) {
+    set_error("node_create_from_features: bad arguments (0 <= n <= 4096)");
+    return RGBDSLAM_B200_ERR_ARG;
+  }
+  NodeDev* nd = new NodeDev();
+  nd->magic = NodeDev::kMagic;
+  nd->id = id;
+  nd->n = n;
+  const size_t nalloc = (size_t)(n > 0 ? n : 1);
+  cudaError_t e = cudaMalloc(&nd->desc, 32 * nalloc);
+  if (e == cudaSuccess) e = cudaMalloc(&nd->xyz, 16 * nalloc);
+  if (e != cudaSuccess) {
+    if (nd->desc) cudaFree(nd->desc);
+    delete nd;
+    return cuda_fail(e, "cudaMalloc(node)");
+  }
+  if (n > 0) {
+    cudaStream_t st = g_state.stream;
+    e = cudaMemcpyAsync(nd->desc, desc, 32 * (size_t)n, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(nd->xyz, xyz1, 16 * (size_t)n, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+      cudaFree(nd->desc);
+      cudaFree(nd->xyz);
+      delete nd;
+      return cuda_fail(e, "node upload");
+    }
+  }
+  *node_handle = (uint64_t)(uintptr_t)nd;
+  return 0;
+}
+
+static NodeDev* get_node(uint64_t h) {
+  NodeDev* nd = (NodeDev*)(uintptr_t)h;
+  if (!nd || nd->magic != NodeDev::kMagic) {
+    set_error("invalid node handle");
+    return nullptr;
+  }
+  return nd;
+}
+
+int rgbdslam_b200_node_num_features(uint64_t node_handle, int* n) {
+  NodeDev* nd = get_node(node_handle);
+  if (!nd || !n) return RGBDSLAM_B200_ERR_ARG;
+  *n = nd->n;
+  return 0;
+}
+
+int rgbdslam_b200_node_download(uint64_t node_handle, uint8_t* desc, float* xyz1) {
+  std::lock_guard<std::mutex> lk(g_state.mu);
+  int rc = check_inited();
+  if (rc) return rc;
+  NodeDev* nd = get_node(node_handle);
+  if (!nd) return RGBDSLAM_B200_ERR_ARG;
+  if (nd->n == 0) return 0;
+  cudaStream_t st = g_state.stream;
+  cudaError_t e = cudaSuccess;
+  if (desc) e = cudaMemcpyAsync(desc, nd->desc, 32 * (size_t)nd->n, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && xyz1) e = cudaMemcpyAsync(xyz1, nd->xyz, 16 * (size_t)nd->n, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return cuda_fail(e, "node download");
+  return 0;
+}
+
+int rgbdslam_b200_node_destroy(uint64_t node_handle) {
+  std::lock_guard<std::mutex> lk(g_state.mu);
+  NodeDev* nd = get_node(node_handle);
+  if (!nd) return RGBDSLAM_B200_ERR_ARG;
+  if (g_state.inited) {
+    cudaSetDevice(g_state.device);
+    cudaStreamSynchronize(g_state.stream);
+  }
+  nd->magic = 0;
+  if (nd->desc) cudaFree(nd->desc);
+  if (nd->xyz) cudaFree(nd->xyz);
+  if (nd->desc_i8) cudaFree(nd->desc_i8);
+  delete nd;
+  return 0;
+}
+
+int rgbdslam_b200_match_pairs(const uint64_t* newer, const uint64_t* older, int npairs, uint64_t seed,
+                              int64_t first_pair_index, rgbdslam_b200_pair_result* results,
+                              rgbdslam_b200_dmatch* all_matches, rgbdslam_b200_dmatch* inlier_matches) {
+  std::lock_guard<std::mutex> lk(g_state.mu);
+  int rc = check_inited();
+  if (rc) return rc;
+  if (npairs < 0 || (npairs > 0 && (!newer || !older || !results))) {
+    set_error("match_pairs: bad arguments");
+    return RGBDSLAM_B200_ERR_ARG;
+  }
+  std::vector<PairDesc> pairs(npairs);
+  for (int i = 0; i < npairs; i++) {
+    NodeDev* a = get_node(newer[i]);
+    NodeDev* b = get_node(older[i]);
+    if (!a || !b) return RGBDSLAM_B200_ERR_ARG;
+    pairs[i].q_desc = (const uint32_t*)a->desc;
+    pairs[i].t_desc = (const uint32_t*)b->desc;
+    pairs[i].q_xyz = (const float4*)a->xyz;
+    pairs[i].t_xyz = (const float4*)b->xyz;
+    pairs[i].nq = a->n;
+    pairs[i].nt = b->n;
+    pairs[i].id_q = a->id;
+    pairs[i].id_t = b->id;
+  }
+  return run_pairs(pairs, seed, first_pair_index, results, all_matches, inlier_matches);
+}
+
+int rgbdslam_b200_match_pairs_host(const uint8_t* desc_newer, const float* xyz_newer, const int32_t* n_newer,
+                                   const uint8_t* desc_older, const float* xyz_older, const int32_t* n_older,
+                                   const int32_t* id_newer, const int32_t* id_older, int npairs, uint64_t seed,
+                                   int64_t first_pair_index, rgbdslam_b200_pair_result* results,
+                                   rgbdslam_b200_dmatch* all_matches, rgbdslam_b200_dmatch* inlier_matches) {
+  std::lock_guard<std::mutex> lk(g_state.mu);
+  int rc = check_inited();
+  if (rc) return rc;
+  if (npairs < 0 || (npairs > 0 && (!n_newer || !n_older || !results))) {
+    set_error("match_pairs_host: bad arguments");
+    return RGBDSLAM_B200_ERR_ARG;
+  }
+  if (npairs == 0) return 0;
+  State& s = g_state;
+  size_t tot_n = 0, tot_o = 0;
+  for (int i = 0; i < npairs; i++) {
+    if (n_newer[i] < 0 || n_older[i] < 0 || n_newer[i] > kMaxFeatures || n_older[i] > kMaxFeatures) {
+      set_error("match_pairs_host: feature count out of range [0,4096]");
+      return RGBDSLAM_B200_ERR_ARG;
+    }
+    tot_n += n_newer[i];
+    tot_o += n_older[i];
+  }
+  if ((tot_n && (!desc_newer || !xyz_newer)) || (tot_o && (!desc_older || !xyz_older))) {
+    set_error("match_pairs_host: null feature buffer");
+    return RGBDSLAM_B200_ERR_ARG;
+  }
+  if ((rc = s.d_feat_a.ensure(32 * (tot_n + 1)))) return rc;
+  if ((rc = s.d_feat_b.ensure(32 * (tot_o + 1)))) return rc;
+  if ((rc = s.d_xyz_a.ensure(16 * (tot_n + 1)))) return rc;
+  if ((rc = s.d_xyz_b.ensure(16 * (tot_o + 1)))) return rc;
+  cudaStream_t st = s.stream;
+  cudaError_t e = cudaSuccess;
+  if (tot_n) {
+    e = cudaMemcpyAsync(s.d_feat_a.ptr, desc_newer, 32 * tot_n, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(s.d_xyz_a.ptr, xyz_newer, 16 * tot_n, cudaMemcpyHostToDevice, st);
+  }
+  if (e == cudaSuccess && tot_o) {
+    e = cudaMemcpyAsync(s.d_feat_b.ptr, desc_older, 32 * tot_o, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(s.d_xyz_b.ptr, xyz_older, 16 * tot_o, cudaMemcpyHostToDevice, st);
+  }
+  if (e != cudaSuccess) return cuda_fail(e, "match_pairs_host upload");
+  std::vector<PairDesc> pairs(npairs);
+  size_t on = 0, oo = 0;
+  for (int i = 0; i < npairs; i++) {
+    pairs[i].q_desc = (const uint32_t*)((const uint8_t*)s.d_feat_a.ptr + 32 * on);
+    pairs[i].t_desc = (const uint32_t*)((const uint8_t*)s.d_feat_b.ptr + 32 * oo);
+    pairs[i].q_xyz = (const float4*)s.d_xyz_a.ptr + on;
+    pairs[i].t_xyz = (const float4*)s.d_xyz_b.ptr + oo;
+    pairs[i].nq = n_newer[i];
+    pairs[i].nt = n_older[i];
+    pairs[i].id_q = id_newer ? id_newer[i] : i;
+    pairs[i].id_t = id_older ? id_older[i] : i;
+    on += n_newer[i];
+    oo += n_older[i];
+  }
+  return run_pairs(pairs, seed, first_pair_index, results, all_matches, inlier_matches);
+}
+
+}  // extern "C"

@@ -1,0 +1,620 @@
+// frontend_kernels.cu -- sm_100a kernels of the frame-pair hot path:
+//   hamming_simt_kernel    : bruteForceSearchORB (features.cpp:168-182) for every query row of every pair
+//   select_matches_kernel  : hd<128 filter, jitter distance, sort, keepStrongestMatches (node.cpp:572-573,674,1127)
+//   ransac_hyp_kernel      : one warp per RANSAC hypothesis (node.cpp:1130-1169) -- sample 4, weighted Kabsch
+//                            (transformation_estimation_euclidean.cpp:7-61), Mahalanobis scoring
+//                            (node.cpp:968-1020, misc.cpp:697-770) with __ballot_sync inlier masks, <=19 refits
+//   ransac_select_kernel   : sequential replay of the best-hypothesis bookkeeping incl. the n+=10 / break
+//                            shortcuts (node.cpp:1170-1216), identity last resort, edge (node.cpp:1335-1339)
+#include "kernels.h"
+
+namespace rb200 {
+
+__constant__ DevParams c_params;
+
+cudaError_t set_dev_params(const DevParams& p, cudaStream_t stream) {
+  return cudaMemcpyToSymbolAsync(c_params, &p, sizeof(DevParams), 0, cudaMemcpyHostToDevice, stream);
+}
+
+// =====================================================================================================
+// Hamming brute force, SIMT popcount version.
+// One thread per query descriptor (8 x u32 in registers), train descriptors staged through shared
+// memory in tiles and read as broadcast LDS.128.  Reference semantics kept bit-exactly:
+//   - only train rows [0, nt-2] are examined (loop bound `i < size-1`, features.cpp:174)
+//   - strict `<` while scanning upwards => lowest index wins ties (features.cpp:176)
+//   - no candidate => (257, -1) (features.cpp:172-173)
+constexpr int kHamQ = 128;  // queries per CTA
+constexpr int kHamT = 128;  // train rows per smem tile
+
+__global__ void __launch_bounds__(kHamQ) hamming_simt_kernel(const PairDesc* __restrict__ pairs,
+                                                             int2* __restrict__ best, int stride) {
+  const PairDesc pd = pairs[blockIdx.y];
+  const int q0 = blockIdx.x * kHamQ;
+  if (q0 >= pd.nq) return;
+  __shared__ uint4 tile[kHamT * 2];
+  const int qi = q0 + threadIdx.x;
+  const bool qvalid = qi < pd.nq;
+  uint4 qa = make_uint4(0, 0, 0, 0), qb = qa;
+  if (qvalid) {
+    const uint4* qp = reinterpret_cast<const uint4*>(pd.q_desc) + 2 * (size_t)qi;
+    qa = __ldg(qp);
+    qb = __ldg(qp + 1);
+  }
+  int best_hd = 257, best_idx = -1;
+  const int nsearch = pd.nt - 1;
+  const uint4* tp = reinterpret_cast<const uint4*>(pd.t_desc);
+  for (int t0 = 0; t0 < nsearch; t0 += kHamT) {
+    const int cnt = min(kHamT, nsearch - t0);
+    __syncthreads();
+    for (int k = threadIdx.x; k < 2 * cnt; k += kHamQ) tile[k] = __ldg(tp + 2 * (size_t)t0 + k);
+    __syncthreads();
+#pragma unroll 4
+    for (int j = 0; j < cnt; j++) {
+      const uint4 a = tile[2 * j], b = tile[2 * j + 1];
+      const int d = (__popc(qa.x ^ a.x) + __popc(qa.y ^ a.y)) + (__popc(qa.z ^ a.z) + __popc(qa.w ^ a.w)) +
+                    (__popc(qb.x ^ b.x) + __popc(qb.y ^ b.y)) + (__popc(qb.z ^ b.z) + __popc(qb.w ^ b.w));
+      if (d < best_hd) {
+        best_hd = d;
+        best_idx = t0 + j;
+      }
+    }
+  }
+  if (qvalid) best[(size_t)blockIdx.y * stride + qi] = make_int2(best_hd, best_idx);
+}
+
+cudaError_t launch_hamming_simt(const PairDesc* pairs, int npairs, int max_nq, int2* best, int stride,
+                                cudaStream_t stream) {
+  if (npairs <= 0 || max_nq <= 0) return cudaSuccess;
+  dim3 grid((max_nq + kHamQ - 1) / kHamQ, npairs);
+  hamming_simt_kernel<<<grid, kHamQ, 0, stream>>>(pairs, best, stride);
+  return cudaGetLastError();
+}
+
+// =====================================================================================================
+// Match selection.  distance = hd/256.0 + (float)rand()/(1000.0*RAND_MAX) (node.cpp:573) with rand()
+// replaced by rand31(pair key, stream 0, queryIdx); keepStrongestMatches + std::sort == ascending sort by
+// (distance, queryIdx) and truncation to max_matches.  One CTA per pair, bitonic sort in shared memory.
+constexpr int kSelThreads = 512;
+
+__device__ __forceinline__ float match_distance(int hd, uint32_t r31) {
+  const double d = __dadd_rn(__ddiv_rn((double)hd, 256.0), __ddiv_rn((double)(float)r31, 1000.0 * 2147483647.0));
+  return __double2float_rn(d);
+}
+
+__global__ void __launch_bounds__(kSelThreads)
+    select_matches_kernel(const PairDesc* __restrict__ pairs, const int2* __restrict__ best, int stride, uint64_t seed,
+                          int64_t first_pair, rgbdslam_b200_dmatch* __restrict__ matches, float4* __restrict__ mfrom,
+                          float4* __restrict__ mto, int32_t* __restrict__ n_all) {
+  __shared__ unsigned long long keys[kMaxFeatures];
+  __shared__ int s_count;
+  const int p = blockIdx.x;
+  const PairDesc pd = pairs[p];
+  const int nq = min(pd.nq, kMaxFeatures);
+  int N = 2;
+  while (N < nq) N <<= 1;
+  const uint64_t key = pair_key(seed, (uint64_t)(first_pair + p));
+  const int2* bp = best + (size_t)p * stride;
+  if (threadIdx.x == 0) s_count = 0;
+  for (int i = threadIdx.x; i < N; i += kSelThreads) {
+    unsigned long long k = ~0ULL;
+    if (i < nq) {
+      const int2 b = bp[i];
+      if (b.x < 128 && b.y >= 0) {  // node.cpp:572
+        const float dist = match_distance(b.x, rand31(key, 0u, (uint32_t)i));
+        k = ((unsigned long long)__float_as_uint(dist) << 32) | (unsigned)i;
+      }
+    }
+    keys[i] = k;
+  }
+  __syncthreads();
+  for (int k = 2; k <= N; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < (N >> 1); t += kSelThreads) {
+        const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // index with bit j cleared
+        const int hi = lo | j;
+        const bool up = (lo & k) == 0;
+        const unsigned long long a = keys[lo], b = keys[hi];
+        if ((a > b) == up) {
+          keys[lo] = b;
+          keys[hi] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < N; i += kSelThreads)
+    if (keys[i] != ~0ULL && (i == N - 1 || keys[i + 1] == ~0ULL)) s_count = i + 1;
+  __syncthreads();
+  const int maxM = c_params.max_matches;
+  const int M = min(s_count, maxM);
+  for (int k = threadIdx.x; k < M; k += kSelThreads) {
+    const unsigned long long kk = keys[k];
+    const int qi = (int)(kk & 0xffffffffULL);
+    const int ti = bp[qi].y;
+    rgbdslam_b200_dmatch m;
+    m.queryIdx = qi;
+    m.trainIdx = ti;
+    m.imgIdx = -1;
+    m.distance = __uint_as_float((unsigned)(kk >> 32));
+    matches[(size_t)p * maxM + k] = m;
+    mfrom[(size_t)p * maxM + k] = __ldg(pd.q_xyz + qi);
+    mto[(size_t)p * maxM + k] = __ldg(pd.t_xyz + ti);
+  }
+  if (threadIdx.x == 0) n_all[p] = M;
+}
+
+cudaError_t launch_select_matches(const PairDesc* pairs, int npairs, const int2* best, int stride, uint64_t seed,
+                                  int64_t first_pair, rgbdslam_b200_dmatch* matches, float4* mfrom, float4* mto,
+                                  int32_t* n_all, int max_nq, cudaStream_t stream) {
+  (void)max_nq;
+  if (npairs <= 0) return cudaSuccess;
+  select_matches_kernel<<<npairs, kSelThreads, 0, stream>>>(pairs, best, stride, seed, first_pair, matches, mfrom, mto,
+                                                            n_all);
+  return cudaGetLastError();
+}
+
+// =====================================================================================================
+// RANSAC building blocks (warp-cooperative; every lane ends up with identical, warp-uniform results).
+
+constexpr unsigned kFull = 0xffffffffu;
+
+__device__ __forceinline__ float wsum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+__device__ __forceinline__ double wsumd(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = __dadd_rn(v, __shfl_xor_sync(kFull, v, o));
+  return v;
+}
+
+struct Rt {
+  float R[9];  // row-major
+  float t[3];
+};
+
+// Weighted rigid fit == getTransformFromMatches (transformation_estimation_euclidean.cpp:7-61):
+// weight 1/(z_from*z_to) (:25), NaN-depth correspondences skipped (:22), then the closed form of
+// pcl::TransformationFromCorrespondences: weighted means, C = sum w (to-m2)(from-m1)^T, C = U S V^T,
+// R = U diag(1,1,det(U)det(V)) V^T, t = m2 - R m1.  The SVD is a Hestenes one-sided Jacobi; the
+// reflection-corrected product is formed as u1 v1^T + u2 v2^T + (u1 x u2)(v1 x v2)^T, which equals
+// U diag(1,1,det U det V) V^T for any sign choice of the third singular pair.
+// Returns false if the result is not finite (the reference's `transformation != transformation` test,
+// node.cpp:1144) or the correspondences are rank deficient (< 2 independent directions).
+__device__ bool fit_transform(const float4* __restrict__ sfrom, const float4* __restrict__ sto, int M,
+                              const uint32_t* sel, int nw, int lane, Rt& out) {
+  float W = 0.f, f0 = 0.f, f1 = 0.f, f2 = 0.f, t0 = 0.f, t1 = 0.f, t2 = 0.f;
+#pragma unroll
+  for (int w = 0; w < kMaxMaskWords; w++) {
+    if (w < nw && ((sel[w] >> lane) & 1u)) {
+      const float4 a = sfrom[w * 32 + lane], b = sto[w * 32 + lane];
+      if (!isnan(a.z) && !isnan(b.z)) {
+        const float wt = __fdiv_rn(1.0f, a.z * b.z);
+        W += wt;
+        f0 += wt * a.x; f1 += wt * a.y; f2 += wt * a.z;
+        t0 += wt * b.x; t1 += wt * b.y; t2 += wt * b.z;
+      }
+    }
+  }
+  W = wsum(W);
+  f0 = wsum(f0); f1 = wsum(f1); f2 = wsum(f2);
+  t0 = wsum(t0); t1 = wsum(t1); t2 = wsum(t2);
+  if (!(W > 0.f)) return false;
+  const float iW = __fdiv_rn(1.0f, W);
+  const float m1x = f0 * iW, m1y = f1 * iW, m1z = f2 * iW;
+  const float m2x = t0 * iW, m2y = t1 * iW, m2z = t2 * iW;
+  float c[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+  for (int w = 0; w < kMaxMaskWords; w++) {
+    if (w < nw && ((sel[w] >> lane) & 1u)) {
+      const float4 a = sfrom[w * 32 + lane], b = sto[w * 32 + lane];
+      if (!isnan(a.z) && !isnan(b.z)) {
+        const float wt = __fdiv_rn(1.0f, a.z * b.z) * iW;
+        const float d1x = a.x - m1x, d1y = a.y - m1y, d1z = a.z - m1z;
+        const float d2x = (b.x - m2x) * wt, d2y = (b.y - m2y) * wt, d2z = (b.z - m2z) * wt;
+        c[0] += d2x * d1x; c[1] += d2x * d1y; c[2] += d2x * d1z;
+        c[3] += d2y * d1x; c[4] += d2y * d1y; c[5] += d2y * d1z;
+        c[6] += d2z * d1x; c[7] += d2z * d1y; c[8] += d2z * d1z;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 9; i++) c[i] = wsum(c[i]);
+
+  // --- one-sided Jacobi SVD of c (row-major a[r][col]); v accumulates the right rotations ---
+  float a00 = c[0], a01 = c[1], a02 = c[2], a10 = c[3], a11 = c[4], a12 = c[5], a20 = c[6], a21 = c[7], a22 = c[8];
+  float v00 = 1, v01 = 0, v02 = 0, v10 = 0, v11 = 1, v12 = 0, v20 = 0, v21 = 0, v22 = 1;
+#define RB200_JROT(AP0, AP1, AP2, AQ0, AQ1, AQ2, VP0, VP1, VP2, VQ0, VQ1, VQ2)                       \
+  {                                                                                                  \
+    const float alpha = AP0 * AP0 + AP1 * AP1 + AP2 * AP2;                                           \
+    const float beta = AQ0 * AQ0 + AQ1 * AQ1 + AQ2 * AQ2;                                            \
+    const float gamma = AP0 * AQ0 + AP1 * AQ1 + AP2 * AQ2;                                           \
+    if (fabsf(gamma) > 1e-7f * sqrtf(alpha * beta) && gamma != 0.f) {                                \
+      rotated = true;                                                                                \
+      const float zeta = (beta - alpha) / (2.f * gamma);                                             \
+      const float tt = copysignf(1.f, zeta) / (fabsf(zeta) + sqrtf(1.f + zeta * zeta));             \
+      const float cs = 1.f / sqrtf(1.f + tt * tt), sn = cs * tt;                                         \
+      float x, y;                                                                                    \
+      x = AP0; y = AQ0; AP0 = cs * x - sn * y; AQ0 = sn * x + cs * y;                                \
+      x = AP1; y = AQ1; AP1 = cs * x - sn * y; AQ1 = sn * x + cs * y;                                \
+      x = AP2; y = AQ2; AP2 = cs * x - sn * y; AQ2 = sn * x + cs * y;                                \
+      x = VP0; y = VQ0; VP0 = cs * x - sn * y; VQ0 = sn * x + cs * y;                                \
+      x = VP1; y = VQ1; VP1 = cs * x - sn * y; VQ1 = sn * x + cs * y;                                \
+      x = VP2; y = VQ2; VP2 = cs * x - sn * y; VQ2 = sn * x + cs * y;                                \
+    }                                                                                                \
+  }
+  for (int sweep = 0; sweep < 10; sweep++) {
+    bool rotated = false;
+    RB200_JROT(a00, a10, a20, a01, a11, a21, v00, v10, v20, v01, v11, v21)  // columns 0,1
+    RB200_JROT(a00, a10, a20, a02, a12, a22, v00, v10, v20, v02, v12, v22)  // columns 0,2
+    RB200_JROT(a01, a11, a21, a02, a12, a22, v01, v11, v21, v02, v12, v22)  // columns 1,2
+    if (!rotated) break;
+  }
+#undef RB200_JROT
+  // column norms; pick the two largest columns (p >= q >= r)
+  const float n0 = a00 * a00 + a10 * a10 + a20 * a20;
+  const float n1 = a01 * a01 + a11 * a11 + a21 * a21;
+  const float n2 = a02 * a02 + a12 * a12 + a22 * a22;
+  float p0, p1, p2, q0, q1, q2, vp0, vp1, vp2, vq0, vq1, vq2, np, nq;
+  // largest
+  int ip = 0;
+  if (n1 > n0) ip = 1;
+  if (n2 > (ip == 0 ? n0 : n1)) ip = 2;
+  int iq;  // second largest
+  if (ip == 0) iq = (n2 > n1) ? 2 : 1;
+  else if (ip == 1) iq = (n2 > n0) ? 2 : 0;
+  else iq = (n1 > n0) ? 1 : 0;
+#define RB200_COL(I, X0, X1, X2, Y0, Y1, Y2, NN)                                      \
+  if (I == 0) { X0 = a00; X1 = a10; X2 = a20; Y0 = v00; Y1 = v10; Y2 = v20; NN = n0; } \
+  else if (I == 1) { X0 = a01; X1 = a11; X2 = a21; Y0 = v01; Y1 = v11; Y2 = v21; NN = n1; } \
+  else { X0 = a02; X1 = a12; X2 = a22; Y0 = v02; Y1 = v12; Y2 = v22; NN = n2; }
+  RB200_COL(ip, p0, p1, p2, vp0, vp1, vp2, np)
+  RB200_COL(iq, q0, q1, q2, vq0, vq1, vq2, nq)
+#undef RB200_COL
+  if (!(np > 0.f) || !(nq > 1e-24f * np)) return false;  // rank < 2: rotation undetermined
+  const float ip_ = 1.f / sqrtf(np), iq_ = 1.f / sqrtf(nq);
+  p0 *= ip_; p1 *= ip_; p2 *= ip_;
+  q0 *= iq_; q1 *= iq_; q2 *= iq_;
+  const float u30 = p1 * q2 - p2 * q1, u31 = p2 * q0 - p0 * q2, u32 = p0 * q1 - p1 * q0;
+  const float v30 = vp1 * vq2 - vp2 * vq1, v31 = vp2 * vq0 - vp0 * vq2, v32 = vp0 * vq1 - vp1 * vq0;
+  out.R[0] = p0 * vp0 + q0 * vq0 + u30 * v30;
+  out.R[1] = p0 * vp1 + q0 * vq1 + u30 * v31;
+  out.R[2] = p0 * vp2 + q0 * vq2 + u30 * v32;
+  out.R[3] = p1 * vp0 + q1 * vq0 + u31 * v30;
+  out.R[4] = p1 * vp1 + q1 * vq1 + u31 * v31;
+  out.R[5] = p1 * vp2 + q1 * vq2 + u31 * v32;
+  out.R[6] = p2 * vp0 + q2 * vq0 + u32 * v30;
+  out.R[7] = p2 * vp1 + q2 * vq1 + u32 * v31;
+  out.R[8] = p2 * vp2 + q2 * vq2 + u32 * v32;
+  out.t[0] = m2x - (out.R[0] * m1x + out.R[1] * m1y + out.R[2] * m1z);
+  out.t[1] = m2y - (out.R[3] * m1x + out.R[4] * m1y + out.R[5] * m1z);
+  out.t[2] = m2z - (out.R[6] * m1x + out.R[7] * m1y + out.R[8] * m1z);
+  bool fin = true;
+#pragma unroll
+  for (int i = 0; i < 9; i++) fin = fin && (out.R[i] == out.R[i]);
+#pragma unroll
+  for (int i = 0; i < 3; i++) fin = fin && (out.t[i] == out.t[i]);
+  return fin;
+}
+
+constexpr double kHuge = 1.7976931348623157e308;  // std::numeric_limits<double>::max()
+
+__device__ __forceinline__ double depth_cov(double z) {  // misc2.h:20-35 (static cache emulated by cov_z_const)
+  if (c_params.cov_z_const >= 0.0) return c_params.cov_z_const;
+  const double sd = __dmul_rn(c_params.sigma_depth, __dmul_rn(z, z));
+  return __dmul_rn(sd, sd);
+}
+
+// errorFunction2 (misc.cpp:697-770) in float64.  Written with explicit rounding intrinsics only, so the
+// hypothesis kernel and the selection kernel (which re-scores the winning transform) produce bit-identical
+// values regardless of how the compiler inlines/contracts.  The 3x3 SPD solve uses the adjugate form
+// d^T S^-1 d = d^T adj(S) d / det(S) instead of the reference's LLT (same value to rounding).
+__device__ __forceinline__ double mahal_sq(const float4 x1, const float4 x2, const double* Rd, const double* td) {
+  if (isnan(x1.z) || isnan(x2.z)) return kHuge;
+  const double a0 = x1.x, a1 = x1.y, a2 = x1.z, a3 = x1.w;
+  const double b0 = x2.x, b1 = x2.y, b2 = x2.z;
+  const double mu0 = fma(Rd[0], a0, fma(Rd[1], a1, fma(Rd[2], a2, __dmul_rn(td[0], a3))));
+  const double mu1 = fma(Rd[3], a0, fma(Rd[4], a1, fma(Rd[5], a2, __dmul_rn(td[1], a3))));
+  const double mu2 = fma(Rd[6], a0, fma(Rd[7], a1, fma(Rd[8], a2, __dmul_rn(td[2], a3))));
+  const double d0 = __dsub_rn(mu0, b0), d1 = __dsub_rn(mu1, b1), d2 = __dsub_rn(mu2, b2);
+  const double rcx = c_params.raster_cov_x, rcy = c_params.raster_cov_y;
+  const double cz1 = depth_cov(a2), cz2 = depth_cov(b2);
+  {
+    const double dsq = fma(d0, d0, fma(d1, d1, __dmul_rn(d2, d2)));
+    const double s1 = fmax(rcx, cz1), s2 = fmax(rcx, cz2);
+    if (dsq > __dmul_rn(2.0, __dadd_rn(s1, s2))) return kHuge;  // misc.cpp:726-735
+  }
+  if (isnan(d2)) return kHuge;
+  const double c10 = __dmul_rn(rcx, a2), c11 = __dmul_rn(rcy, a2), c12 = cz1;
+  const double c20 = __dmul_rn(rcx, b2), c21 = __dmul_rn(rcy, b2), c22 = cz2;
+  // S = R^T diag(c1) R + diag(c2):  S_ij = sum_k R[k][i] c1_k R[k][j]
+  const double r00 = __dmul_rn(Rd[0], c10), r01 = __dmul_rn(Rd[1], c10), r02 = __dmul_rn(Rd[2], c10);
+  const double r10 = __dmul_rn(Rd[3], c11), r11 = __dmul_rn(Rd[4], c11), r12 = __dmul_rn(Rd[5], c11);
+  const double r20 = __dmul_rn(Rd[6], c12), r21 = __dmul_rn(Rd[7], c12), r22 = __dmul_rn(Rd[8], c12);
+  const double S00 = fma(r00, Rd[0], fma(r10, Rd[3], fma(r20, Rd[6], c20)));
+  const double S11 = fma(r01, Rd[1], fma(r11, Rd[4], fma(r21, Rd[7], c21)));
+  const double S22 = fma(r02, Rd[2], fma(r12, Rd[5], fma(r22, Rd[8], c22)));
+  const double S01 = fma(r00, Rd[1], fma(r10, Rd[4], __dmul_rn(r20, Rd[7])));
+  const double S02 = fma(r00, Rd[2], fma(r10, Rd[5], __dmul_rn(r20, Rd[8])));
+  const double S12 = fma(r01, Rd[2], fma(r11, Rd[5], __dmul_rn(r21, Rd[8])));
+  const double A00 = fma(S11, S22, -__dmul_rn(S12, S12));
+  const double A01 = fma(S02, S12, -__dmul_rn(S01, S22));
+  const double A02 = fma(S01, S12, -__dmul_rn(S02, S11));
+  const double A11 = fma(S00, S22, -__dmul_rn(S02, S02));
+  const double A12 = fma(S01, S02, -__dmul_rn(S00, S12));
+  const double A22 = fma(S00, S11, -__dmul_rn(S01, S01));
+  const double det = fma(S00, A00, fma(S01, A01, __dmul_rn(S02, A02)));
+  const double e0 = fma(A00, d0, fma(A01, d1, __dmul_rn(A02, d2)));
+  const double e1 = fma(A01, d0, fma(A11, d1, __dmul_rn(A12, d2)));
+  const double e2 = fma(A02, d0, fma(A12, d1, __dmul_rn(A22, d2)));
+  const double num = fma(d0, e0, fma(d1, e1, __dmul_rn(d2, e2)));
+  const double m = __ddiv_rn(num, det);
+  if (!(m >= 0.0)) return kHuge;
+  return m;
+}
+
+// computeInliersAndError (node.cpp:968-1020): returns #inliers, fills the mask words (warp-uniform) and
+// the Mahalanobis RMS (1e9 if < 3 inliers).
+__device__ int score_all(const float4* __restrict__ sfrom, const float4* __restrict__ sto, int M, int nw, int lane,
+                         const Rt& T, uint32_t* words, double& err) {
+  double Rd[9], td[3];
+#pragma unroll
+  for (int i = 0; i < 9; i++) Rd[i] = (double)T.R[i];
+#pragma unroll
+  for (int i = 0; i < 3; i++) td[i] = (double)T.t[i];
+  const double sq_max = c_params.sq_max_dist;
+  double esum = 0.0;
+  int cnt = 0;
+#pragma unroll
+  for (int w = 0; w < kMaxMaskWords; w++) {
+    uint32_t word = 0;
+    if (w < nw) {
+      const int i = w * 32 + lane;
+      bool inl = false;
+      double m = 0.0;
+      if (i < M) {
+        const float4 a = sfrom[i], b = sto[i];
+        if (!(a.z == 0.0f || b.z == 0.0f)) {  // node.cpp:994 (does not trigger on NaN)
+          m = mahal_sq(a, b, Rd, td);
+          inl = !(m > sq_max) && (m >= 0.0);  // node.cpp:998-1005
+        }
+      }
+      word = __ballot_sync(kFull, inl);
+      if (inl) esum = __dadd_rn(esum, m);
+      cnt += __popc(word);
+    }
+    words[w] = word;
+  }
+  esum = wsumd(esum);
+  err = (cnt < 3) ? 1e9 : sqrt(__ddiv_rn(esum, (double)cnt));  // node.cpp:1011-1017
+  return cnt;
+}
+
+__device__ __forceinline__ unsigned min_inlier_threshold(int M) {  // node.cpp:1094-1099
+  unsigned thr = (unsigned)c_params.min_matches;
+  if ((double)thr > 0.75 * (double)M) thr = (unsigned)(0.75 * (double)M);
+  return thr;
+}
+
+constexpr int kRansacWarps = 8;
+
+__global__ void __launch_bounds__(kRansacWarps * 32)
+    ransac_hyp_kernel(int H, int maxM, uint64_t seed, int64_t first_pair, const float4* __restrict__ mfrom,
+                      const float4* __restrict__ mto, const int32_t* __restrict__ n_all, HypResult* __restrict__ hyp) {
+  __shared__ float4 sfrom[kMaxMatchesCap];
+  __shared__ float4 sto[kMaxMatchesCap];
+  const int p = blockIdx.y;
+  const int M = n_all[p];
+  if (M <= c_params.min_matches || M < 4) return;  // node.cpp:1087,1130 (selection kernel checks the same)
+  for (int i = threadIdx.x; i < M; i += blockDim.x) {
+    sfrom[i] = mfrom[(size_t)p * maxM + i];
+    sto[i] = mto[(size_t)p * maxM + i];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int n = blockIdx.x * kRansacWarps + (threadIdx.x >> 5);
+  if (n >= H) return;
+  const int nw = (M + 31) >> 5;
+  const unsigned min_thr = min_inlier_threshold(M);
+  const uint64_t key = pair_key(seed, (uint64_t)(first_pair + p));
+
+  // sample_matches_prefer_by_distance(4, ...) (node.cpp:1024-1047)
+  int ids[4] = {-1, -1, -1, -1};
+  {
+    int cnt = 0, safety = 0;
+    uint32_t ctr = 0;
+    while (cnt < 4) {
+      int id1 = (int)(rand31(key, 1u + (uint32_t)n, ctr) % (uint32_t)M);
+      const int id2 = (int)(rand31(key, 1u + (uint32_t)n, ctr + 1) % (uint32_t)M);
+      ctr += 2;
+      if (id1 > id2) id1 = id2;
+      if (id1 != ids[0] && id1 != ids[1] && id1 != ids[2] && id1 != ids[3]) {
+        if (cnt == 0) ids[0] = id1;
+        else if (cnt == 1) ids[1] = id1;
+        else if (cnt == 2) ids[2] = id1;
+        else ids[3] = id1;
+        cnt++;
+      }
+      if (++safety > 10000) break;
+    }
+  }
+  uint32_t sel[kMaxMaskWords];
+#pragma unroll
+  for (int w = 0; w < kMaxMaskWords; w++) {
+    uint32_t word = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+      if (ids[k] >= 0 && (ids[k] >> 5) == w) word |= 1u << (ids[k] & 31);
+    sel[w] = word;
+  }
+
+  double refined_err = 1e6;
+  int refined_cnt = 0;
+  Rt refined;
+#pragma unroll
+  for (int i = 0; i < 9; i++) refined.R[i] = (i % 4 == 0) ? 1.f : 0.f;
+  refined.t[0] = refined.t[1] = refined.t[2] = 0.f;
+
+  for (int refinements = 1; refinements < 20; refinements++) {  // node.cpp:1140
+    Rt T;
+    if (!fit_transform(sfrom, sto, M, sel, nw, lane, T)) break;  // node.cpp:1142-1145
+    double err;
+    const int cnt = score_all(sfrom, sto, M, nw, lane, T, sel, err);  // node.cpp:1148
+    if ((unsigned)cnt < min_thr || err > (double)c_params.max_dist_m) break;  // node.cpp:1154
+    if (cnt >= refined_cnt && err <= refined_err) {                             // node.cpp:1160
+      const int prev = refined_cnt;
+      refined = T;
+      refined_cnt = cnt;
+      refined_err = err;
+      if (cnt == prev) break;  // node.cpp:1166
+    } else
+      break;
+  }
+  if (lane == 0) {
+    HypResult r;
+    r.err = refined_err;
+    r.count = refined_cnt;
+    r.pad_ = 0;
+#pragma unroll
+    for (int i = 0; i < 9; i++) r.T[i] = refined.R[i];
+#pragma unroll
+    for (int i = 0; i < 3; i++) r.T[9 + i] = refined.t[i];
+    hyp[(size_t)p * H + n] = r;
+  }
+}
+
+cudaError_t launch_ransac_hypotheses(int npairs, int ransac_iterations, int max_matches, uint64_t seed,
+                                     int64_t first_pair, const float4* mfrom, const float4* mto,
+                                     const int32_t* n_all, HypResult* hyp, cudaStream_t stream) {
+  if (npairs <= 0 || ransac_iterations <= 0) return cudaSuccess;
+  dim3 grid((ransac_iterations + kRansacWarps - 1) / kRansacWarps, npairs);
+  ransac_hyp_kernel<<<grid, kRansacWarps * 32, 0, stream>>>(ransac_iterations, max_matches, seed, first_pair, mfrom, mto,
+                                                            n_all, hyp);
+  return cudaGetLastError();
+}
+
+// One warp per pair.
+__global__ void __launch_bounds__(32)
+    ransac_select_kernel(const PairDesc* __restrict__ pairs, int H, int maxM, const float4* __restrict__ mfrom,
+                         const float4* __restrict__ mto, const int32_t* __restrict__ n_all,
+                         const rgbdslam_b200_dmatch* __restrict__ matches, const HypResult* __restrict__ hyp,
+                         rgbdslam_b200_pair_result* __restrict__ results,
+                         rgbdslam_b200_dmatch* __restrict__ inlier_matches) {
+  const int p = blockIdx.x;
+  const int lane = threadIdx.x;
+  const PairDesc pd = pairs[p];
+  const int M = n_all[p];
+  const float4* sfrom = mfrom + (size_t)p * maxM;
+  const float4* sto = mto + (size_t)p * maxM;
+
+  rgbdslam_b200_pair_result res;
+  res.id1 = res.id2 = -1;
+  res.n_all_matches = M;
+  res.n_inliers = 0;
+  res.rmse = 0.f;  // MatchingResult(): rmse(0.0)
+  res.valid_iterations = 0;
+#pragma unroll
+  for (int i = 0; i < 16; i++) res.ransac_trafo[i] = (i % 5 == 0) ? 1.f : 0.f;
+  res.info_scale = 0.0;
+  res.used_identity = 0;
+  res.reserved_ = 0;
+
+  // matchNodePair: all_matches.size() < min_matches -> no RANSAC (node.cpp:1319);
+  // getRelativeTransformationTo: size <= min_matches -> false (node.cpp:1087)
+  const bool run = (M >= c_params.min_matches) && (M > c_params.min_matches);
+  if (run) {
+    const int nw = (M + 31) >> 5;
+    const unsigned min_thr = min_inlier_threshold(M);
+    float rmse = 1e6f;  // node.cpp:1110
+    int best_cnt = 0, best_n = -1, valid = 0;
+    const HypResult* hp = hyp + (size_t)p * H;
+    if (M >= 4) {
+      for (int n = 0; n < H; n++) {  // node.cpp:1130
+        const int cnt = hp[n].count;
+        if (cnt > 0) {  // node.cpp:1170
+          valid++;
+          const double err = hp[n].err;
+          if (err <= (double)rmse && cnt >= best_cnt && (unsigned)cnt >= min_thr) {  // node.cpp:1177-1179
+            rmse = (float)err;
+            best_cnt = cnt;
+            best_n = n;
+            if ((double)cnt > (double)M * 0.5) n += 10;   // node.cpp:1186
+            if ((double)cnt > (double)M * 0.75) n += 10;  // node.cpp:1187
+            if ((double)cnt > (double)M * 0.8) break;     // node.cpp:1188
+          }
+        }
+      }
+    }
+    Rt T;
+#pragma unroll
+    for (int i = 0; i < 9; i++) T.R[i] = (i % 4 == 0) ? 1.f : 0.f;
+    T.t[0] = T.t[1] = T.t[2] = 0.f;
+    uint32_t words[kMaxMaskWords];
+#pragma unroll
+    for (int w = 0; w < kMaxMaskWords; w++) words[w] = 0;
+    int n_inl = 0;
+    if (best_n >= 0) {
+#pragma unroll
+      for (int i = 0; i < 9; i++) T.R[i] = hp[best_n].T[i];
+#pragma unroll
+      for (int i = 0; i < 3; i++) T.t[i] = hp[best_n].T[9 + i];
+      double err;
+      n_inl = score_all(sfrom, sto, M, nw, lane, T, words, err);  // bit-identical to the hypothesis kernel's pass
+    } else if (valid == 0) {  // identity as last resort (node.cpp:1192-1215)
+      double err;
+      const int cnt = score_all(sfrom, sto, M, nw, lane, T, words, err);
+      if ((unsigned)cnt > min_thr && err < (double)c_params.max_dist_m) {
+        n_inl = cnt;
+        rmse = (float)err;
+        valid = 1;
+        res.used_identity = 1;
+      } else {
+#pragma unroll
+        for (int w = 0; w < kMaxMaskWords; w++) words[w] = 0;
+      }
+    }
+    res.valid_iterations = valid;
+    res.rmse = rmse;
+    res.n_inliers = n_inl;
+    // column-major Matrix4f
+    res.ransac_trafo[0] = T.R[0]; res.ransac_trafo[1] = T.R[3]; res.ransac_trafo[2] = T.R[6];
+    res.ransac_trafo[4] = T.R[1]; res.ransac_trafo[5] = T.R[4]; res.ransac_trafo[6] = T.R[7];
+    res.ransac_trafo[8] = T.R[2]; res.ransac_trafo[9] = T.R[5]; res.ransac_trafo[10] = T.R[8];
+    res.ransac_trafo[12] = T.t[0]; res.ransac_trafo[13] = T.t[1]; res.ransac_trafo[14] = T.t[2];
+    // compact the inlier matches in all_matches order
+    if (inlier_matches) {
+      int base = 0;
+#pragma unroll
+      for (int w = 0; w < kMaxMaskWords; w++) {
+        if (w < nw) {
+          const uint32_t word = words[w];
+          if ((word >> lane) & 1u) {
+            const int pos = base + __popc(word & ((1u << lane) - 1u));
+            inlier_matches[(size_t)p * maxM + pos] = matches[(size_t)p * maxM + w * 32 + lane];
+          }
+          base += __popc(word);
+        }
+      }
+    }
+    if ((unsigned)n_inl >= min_thr) {  // node.cpp:1275, then node.cpp:1335-1339
+      res.info_scale = (double)((float)n_inl / (rmse * rmse));
+      res.id1 = pd.id_t;
+      res.id2 = pd.id_q;
+    }
+  }
+  if (lane == 0) results[p] = res;
+}
+
+cudaError_t launch_ransac_select(const PairDesc* pairs, int npairs, int ransac_iterations, int max_matches,
+                                 const float4* mfrom, const float4* mto, const int32_t* n_all,
+                                 const rgbdslam_b200_dmatch* matches, const HypResult* hyp,
+                                 rgbdslam_b200_pair_result* results, rgbdslam_b200_dmatch* inlier_matches,
+                                 cudaStream_t stream) {
+  if (npairs <= 0) return cudaSuccess;
+  ransac_select_kernel<<<npairs, 32, 0, stream>>>(pairs, ransac_iterations, max_matches, mfrom, mto, n_all, matches, hyp,
+                                                  results, inlier_matches);
+  return cudaGetLastError();
+}
+
+}  // namespace rb200

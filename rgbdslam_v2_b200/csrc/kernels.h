@@ -1,0 +1,31 @@
+// kernels.h -- host-side launchers of the sm_100a kernels (implemented in *.cu).
+#pragma once
+#include "common.cuh"
+
+namespace rb200 {
+
+// Upload the constant-memory parameter block (synchronous w.r.t. `stream`).
+cudaError_t set_dev_params(const DevParams& p, cudaStream_t stream);
+
+// Hamming N x M brute force (features.cpp:168-182 batched): best[p*stride + i] = {hd, idx}.
+cudaError_t launch_hamming_simt(const PairDesc* pairs, int npairs, int max_nq, int2* best, int stride,
+                                cudaStream_t stream);
+
+// hd<128 filter + jitter distance + sort + keep max_matches (node.cpp:572-573,674,1127).
+cudaError_t launch_select_matches(const PairDesc* pairs, int npairs, const int2* best, int stride, uint64_t seed,
+                                  int64_t first_pair, rgbdslam_b200_dmatch* matches, float4* mfrom, float4* mto,
+                                  int32_t* n_all, int max_nq, cudaStream_t stream);
+
+// RANSAC hypotheses (node.cpp:1130-1169) -- one warp per hypothesis.
+cudaError_t launch_ransac_hypotheses(int npairs, int ransac_iterations, int max_matches, uint64_t seed,
+                                     int64_t first_pair, const float4* mfrom, const float4* mto,
+                                     const int32_t* n_all, HypResult* hyp, cudaStream_t stream);
+
+// Sequential replay of the hypothesis bookkeeping (node.cpp:1170-1216,1275) + edge (node.cpp:1335-1339).
+cudaError_t launch_ransac_select(const PairDesc* pairs, int npairs, int ransac_iterations, int max_matches,
+                                 const float4* mfrom, const float4* mto, const int32_t* n_all,
+                                 const rgbdslam_b200_dmatch* matches, const HypResult* hyp,
+                                 rgbdslam_b200_pair_result* results, rgbdslam_b200_dmatch* inlier_matches,
+                                 cudaStream_t stream);
+
+}  // namespace rb200

@@ -1,0 +1,66 @@
+// state.h -- host-side library state shared by the api_*.cu translation units.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <mutex>
+#include <string>
+
+#include "common.cuh"
+
+namespace rb200 {
+
+struct DevBuf {  // grow-only device buffer
+  void* ptr = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes);
+  void release();
+};
+struct PinBuf {  // grow-only pinned host buffer
+  void* ptr = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes);
+  void release();
+};
+
+// Device copy of what the reference's Node keeps per frame (node.h:167-174).
+struct NodeDev {
+  static constexpr uint32_t kMagic = 0x4e4f4445u;  // 'NODE'
+  uint32_t magic = 0;
+  int32_t id = -1;
+  int32_t n = 0;
+  uint8_t* desc = nullptr;    // n x 32 B ORB descriptors
+  float4* xyz = nullptr;      // n x (x,y,z,1)
+  int8_t* desc_i8 = nullptr;  // n_pad x 256 B  +-1 expansion for the tensor-core Hamming path (lazily built)
+  int32_t n_pad = 0;
+};
+
+struct State {
+  std::mutex mu;
+  bool inited = false;
+  int device = 0;
+  int sm_count = 0;
+  rgbdslam_b200_params params;
+  DevParams dp;
+  double z0 = 0.0;  // latched first depth for depth_covariance (misc2.h:30-35)
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  bool timing_valid = false;
+  int64_t launches = 0;
+  // workspaces
+  DevBuf d_pairs, d_best, d_matches, d_inliers, d_mfrom, d_mto, d_nall, d_hyp, d_results;
+  DevBuf d_feat_a, d_feat_b, d_xyz_a, d_xyz_b;
+  PinBuf h_pairs;
+  void release_workspaces() {
+    DevBuf* all[] = {&d_pairs, &d_best, &d_matches, &d_inliers, &d_mfrom, &d_mto, &d_nall,
+                     &d_hyp,   &d_results, &d_feat_a, &d_feat_b, &d_xyz_a, &d_xyz_b};
+    for (DevBuf* b : all) b->release();
+    h_pairs.release();
+  }
+};
+
+extern State g_state;
+void set_error(const std::string& s);
+int cuda_fail(cudaError_t e, const char* what);
+int check_inited();
+
+}  // namespace rb200
