@@ -33,7 +33,14 @@ def sources() -> list[Path]:
 
 def build_library(force: bool = False, verbose: bool = False) -> Path:
     """Compile csrc/*.cu into librgbdslam_b200.so (skipped if up to date)."""
+    import fcntl
     out = library_path()
+    with open(PKG_DIR / ".build.lock", "w") as lk:  # several ranks may call build() at once
+        fcntl.flock(lk, fcntl.LOCK_EX)
+        return _build_locked(out, force, verbose)
+
+
+def _build_locked(out: Path, force: bool, verbose: bool) -> Path:
     srcs = sources()
     deps = srcs + sorted(CSRC.glob("*.h")) + sorted(CSRC.glob("*.cuh")) + [PKG_DIR.parent / "include" / "rgbdslam_b200.h"]
     if out.exists() and not force:
