@@ -117,6 +117,10 @@ int rgbdslam_b200_set_stream(void* cuda_stream);
 /* Block until all work queued by the library has finished. */
 int rgbdslam_b200_synchronize(void);
 
+/* Which kernel computes the Hamming brute-force stage: 1 (default) = tcgen05 kind::i8 tensor-core GEMM
+ * with arg-max epilogue, 0 = SIMT popcount kernel.  Both are exact and give identical results. */
+int rgbdslam_b200_set_hamming_path(int path);
+
 const char* rgbdslam_b200_last_error(void);
 /* Number of kernels launched by this library since init (for bench gpu_launches). */
 int64_t rgbdslam_b200_launch_count(void);

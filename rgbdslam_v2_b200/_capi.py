@@ -114,6 +114,7 @@ def load_library(path: str | Path | None = None) -> C.CDLL:
     lib.rgbdslam_b200_node_destroy.argtypes = [u64]
     lib.rgbdslam_b200_match_pairs.argtypes = [vp, vp, C.c_int, u64, i64, vp, vp, vp]
     lib.rgbdslam_b200_match_pairs_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, u64, i64, vp, vp, vp]
+    lib.rgbdslam_b200_set_hamming_path.argtypes = [C.c_int]
     lib.rgbdslam_b200_last_timing.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float)]
     for name in declared_symbols():
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
@@ -162,6 +163,10 @@ class Frontend:
 
     def set_stream(self, stream_ptr: int | None):
         self._check(self.lib.rgbdslam_b200_set_stream(stream_ptr))
+
+    def set_hamming_path(self, path: int):
+        """1 = tcgen05 int8 tensor-core GEMM (default), 0 = SIMT popcount."""
+        self._check(self.lib.rgbdslam_b200_set_hamming_path(path))
 
     def synchronize(self):
         self._check(self.lib.rgbdslam_b200_synchronize())

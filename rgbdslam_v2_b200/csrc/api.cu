@@ -100,12 +100,75 @@ static int push_dev_params() {
   return 0;
 }
 
-// Hamming stage dispatcher (counts the launch).
-static cudaError_t launch_hamming(const PairDesc* d_pairs, const PairDesc* h_pairs, int npairs, int max_nq, int2* best,
-                                  int stride, cudaStream_t st) {
-  (void)h_pairs;
-  g_state.launches += 1;
-  return launch_hamming_simt(d_pairs, npairs, max_nq, best, stride, st);
+static inline int pad256(int n) { return ((n > 0 ? n : 1) + 255) / 256 * 256; }
+
+// +-1 int8 expansion of a set of nodes (tensor-core Hamming operands).
+static int expand_nodes(const std::vector<ExpandJob>& jobs) {
+  State& s = g_state;
+  if (jobs.empty()) return 0;
+  int rc;
+  if ((rc = s.d_jobs.ensure(sizeof(ExpandJob) * jobs.size()))) return rc;
+  if ((rc = s.h_jobs.ensure(sizeof(ExpandJob) * jobs.size()))) return rc;
+  int max_pad = 0;
+  for (const ExpandJob& j : jobs) max_pad = j.n_pad > max_pad ? j.n_pad : max_pad;
+  memcpy(s.h_jobs.ptr, jobs.data(), sizeof(ExpandJob) * jobs.size());
+  cudaError_t e = cudaMemcpyAsync(s.d_jobs.ptr, s.h_jobs.ptr, sizeof(ExpandJob) * jobs.size(), cudaMemcpyHostToDevice, s.stream);
+  if (e != cudaSuccess) return cuda_fail(e, "upload expand jobs");
+  e = launch_expand_i8((const ExpandJob*)s.d_jobs.ptr, (int)jobs.size(), max_pad, s.stream);
+  if (e != cudaSuccess) return cuda_fail(e, "expand_i8 kernel");
+  s.launches += 1;
+  return 0;
+}
+
+// Hamming stage dispatcher (counts the launch).  h_pairs carries the int8 operand pointers when the
+// tensor-core path is selected.
+static int launch_hamming(const PairDesc* d_pairs, const PairDesc* h_pairs, int npairs, int max_nq, int2* best,
+                          int stride, cudaStream_t st) {
+  State& s = g_state;
+  cudaError_t e;
+  if (s.hamming_path == 0) {
+    cudaEventRecord(s.ev[3], st);
+    e = launch_hamming_simt(d_pairs, npairs, max_nq, best, stride, st);
+  } else {
+    std::vector<HamItem> items;
+    items.reserve((size_t)npairs * ((max_nq + 127) / 128));
+    for (int p = 0; p < npairs; p++) {
+      const PairDesc& pd = h_pairs[p];
+      if (pd.nq > 0 && (!pd.q_i8 || !pd.t_i8)) {
+        set_error("internal: tensor-core Hamming path without int8 operands");
+        return RGBDSLAM_B200_ERR_STATE;
+      }
+      const int nsearch = pd.nt - 1 > 0 ? pd.nt - 1 : 0;
+      for (int m0 = 0; m0 < pd.nq; m0 += 128) {
+        HamItem it;
+        it.a = pd.q_i8 + (size_t)m0 * 256;
+        it.b = pd.t_i8;
+        it.out = best + (size_t)p * stride + m0;
+        it.nq_valid = pd.nq - m0 < 128 ? pd.nq - m0 : 128;
+        it.nsearch = nsearch;
+        it.n_btiles = (nsearch + 255) / 256;
+        it.pad_ = 0;
+        items.push_back(it);
+      }
+    }
+    if (items.empty()) {
+      cudaEventRecord(s.ev[3], st);
+      cudaEventRecord(s.ev[1], st);
+      return 0;
+    }
+    int rc;
+    if ((rc = s.d_items.ensure(sizeof(HamItem) * items.size()))) return rc;
+    if ((rc = s.h_items.ensure(sizeof(HamItem) * items.size()))) return rc;
+    memcpy(s.h_items.ptr, items.data(), sizeof(HamItem) * items.size());
+    e = cudaMemcpyAsync(s.d_items.ptr, s.h_items.ptr, sizeof(HamItem) * items.size(), cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return cuda_fail(e, "upload hamming items");
+    cudaEventRecord(s.ev[3], st);
+    e = launch_hamming_tc((const HamItem*)s.d_items.ptr, (int)items.size(), s.sm_count, st);
+  }
+  cudaEventRecord(s.ev[1], st);
+  if (e != cudaSuccess) return cuda_fail(e, "hamming kernel");
+  s.launches += 1;
+  return 0;
 }
 
 // Core of match_pairs*: h_pairs (device pointers inside) -> results on the host.
@@ -146,9 +209,8 @@ static int run_pairs(const std::vector<PairDesc>& h_pairs, uint64_t seed, int64_
   const PairDesc* d_pairs = (const PairDesc*)s.d_pairs.ptr;
 
   cudaEventRecord(s.ev[0], st);
-  e = launch_hamming(d_pairs, h_pairs.data(), npairs, max_nq, (int2*)s.d_best.ptr, stride, st);
-  if (e != cudaSuccess) return cuda_fail(e, "hamming kernel");
-  cudaEventRecord(s.ev[1], st);
+  // launch_hamming records ev[3] / ev[1] immediately around the kernel
+  if ((rc = launch_hamming(d_pairs, h_pairs.data(), npairs, max_nq, (int2*)s.d_best.ptr, stride, st))) return rc;
   e = launch_select_matches(d_pairs, npairs, (const int2*)s.d_best.ptr, stride, seed, first_pair,
                             (rgbdslam_b200_dmatch*)s.d_matches.ptr, (float4*)s.d_mfrom.ptr, (float4*)s.d_mto.ptr,
                             (int32_t*)s.d_nall.ptr, max_nq, st);
@@ -322,6 +384,16 @@ int rgbdslam_b200_synchronize(void) {
   return 0;
 }
 
+int rgbdslam_b200_set_hamming_path(int path) {
+  std::lock_guard<std::mutex> lk(g_state.mu);
+  if (path != 0 && path != 1) {
+    set_error("set_hamming_path: 0 = SIMT popcount, 1 = tcgen05 int8 GEMM");
+    return RGBDSLAM_B200_ERR_ARG;
+  }
+  g_state.hamming_path = path;
+  return 0;
+}
+
 int64_t rgbdslam_b200_launch_count(void) { return g_state.launches; }
 double rgbdslam_b200_depth_cov_z0(void) { return g_state.z0; }
 
@@ -334,7 +406,7 @@ int rgbdslam_b200_last_timing(float* hamming_ms, float* total_device_ms) {
     return RGBDSLAM_B200_ERR_STATE;
   }
   float a = 0, b = 0;
-  cudaError_t e = cudaEventElapsedTime(&a, g_state.ev[0], g_state.ev[1]);
+  cudaError_t e = cudaEventElapsedTime(&a, g_state.ev[3], g_state.ev[1]);
   if (e == cudaSuccess) e = cudaEventElapsedTime(&b, g_state.ev[0], g_state.ev[2]);
   if (e != cudaSuccess) return cuda_fail(e, "cudaEventElapsedTime");
   if (hamming_ms) *hamming_ms = a;
@@ -374,11 +446,21 @@ int rgbdslam_b200_brute_force_orb(const uint64_t* q, int nq, const uint64_t* t, 
   pd.nq = nq;
   pd.nt = nt;
   pd.id_q = pd.id_t = 0;
+  pd.q_i8 = pd.t_i8 = nullptr;
+  if (s.hamming_path != 0) {
+    if ((rc = s.d_i8_a.ensure(256 * (size_t)pad256(nq)))) return rc;
+    if ((rc = s.d_i8_b.ensure(256 * (size_t)pad256(nt)))) return rc;
+    std::vector<ExpandJob> jobs(2);
+    jobs[0] = {(const uint8_t*)s.d_feat_a.ptr, (int8_t*)s.d_i8_a.ptr, nq, pad256(nq)};
+    jobs[1] = {(const uint8_t*)s.d_feat_b.ptr, (int8_t*)s.d_i8_b.ptr, nt, pad256(nt)};
+    if ((rc = expand_nodes(jobs))) return rc;
+    pd.q_i8 = (const int8_t*)s.d_i8_a.ptr;
+    pd.t_i8 = (const int8_t*)s.d_i8_b.ptr;
+  }
   memcpy(s.h_pairs.ptr, &pd, sizeof(pd));
   e = cudaMemcpyAsync(s.d_pairs.ptr, s.h_pairs.ptr, sizeof(pd), cudaMemcpyHostToDevice, st);
   if (e != cudaSuccess) return cuda_fail(e, "brute_force_orb pair upload");
-  e = launch_hamming((const PairDesc*)s.d_pairs.ptr, &pd, 1, nq, (int2*)s.d_best.ptr, stride, st);
-  if (e != cudaSuccess) return cuda_fail(e, "hamming kernel");
+  if ((rc = launch_hamming((const PairDesc*)s.d_pairs.ptr, &pd, 1, nq, (int2*)s.d_best.ptr, stride, st))) return rc;
   std::vector<int2> h(nq);
   e = cudaMemcpyAsync(h.data(), s.d_best.ptr, sizeof(int2) * nq, cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -411,16 +493,33 @@ int rgbdslam_b200_node_create_from_features(int32_t id, const uint8_t* desc, con
     delete nd;
     return cuda_fail(e, "cudaMalloc(node)");
   }
-  if (n > 0) {
+  nd->n_pad = pad256(n);
+  e = cudaMalloc(&nd->desc_i8, 256 * (size_t)nd->n_pad);
+  if (e != cudaSuccess) {
+    cudaFree(nd->desc);
+    cudaFree(nd->xyz);
+    delete nd;
+    return cuda_fail(e, "cudaMalloc(node int8 descriptors)");
+  }
+  {
     cudaStream_t st = g_state.stream;
-    e = cudaMemcpyAsync(nd->desc, desc, 32 * (size_t)n, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(nd->xyz, xyz1, 16 * (size_t)n, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    if (e != cudaSuccess) {
+    if (n > 0) {
+      e = cudaMemcpyAsync(nd->desc, desc, 32 * (size_t)n, cudaMemcpyHostToDevice, st);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(nd->xyz, xyz1, 16 * (size_t)n, cudaMemcpyHostToDevice, st);
+    }
+    int rc2 = 0;
+    if (e == cudaSuccess) {
+      std::vector<ExpandJob> jobs(1);
+      jobs[0] = {nd->desc, nd->desc_i8, n, nd->n_pad};
+      rc2 = expand_nodes(jobs);
+    }
+    if (e == cudaSuccess && rc2 == 0) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess || rc2 != 0) {
       cudaFree(nd->desc);
       cudaFree(nd->xyz);
+      cudaFree(nd->desc_i8);
       delete nd;
-      return cuda_fail(e, "node upload");
+      return rc2 ? rc2 : cuda_fail(e, "node upload");
     }
   }
   *node_handle = (uint64_t)(uintptr_t)nd;
@@ -498,6 +597,8 @@ int rgbdslam_b200_match_pairs(const uint64_t* newer, const uint64_t* older, int 
     pairs[i].nt = b->n;
     pairs[i].id_q = a->id;
     pairs[i].id_t = b->id;
+    pairs[i].q_i8 = a->desc_i8;
+    pairs[i].t_i8 = b->desc_i8;
   }
   return run_pairs(pairs, seed, first_pair_index, results, all_matches, inlier_matches);
 }
@@ -545,8 +646,29 @@ int rgbdslam_b200_match_pairs_host(const uint8_t* desc_newer, const float* xyz_n
   }
   if (e != cudaSuccess) return cuda_fail(e, "match_pairs_host upload");
   std::vector<PairDesc> pairs(npairs);
-  size_t on = 0, oo = 0;
+  size_t on = 0, oo = 0, pn = 0, po = 0;
+  const bool tc = s.hamming_path != 0;
+  if (tc) {
+    size_t rows_n = 0, rows_o = 0;
+    for (int i = 0; i < npairs; i++) {
+      rows_n += pad256(n_newer[i]);
+      rows_o += pad256(n_older[i]);
+    }
+    if ((rc = s.d_i8_a.ensure(256 * rows_n))) return rc;
+    if ((rc = s.d_i8_b.ensure(256 * rows_o))) return rc;
+  }
+  std::vector<ExpandJob> jobs;
+  if (tc) jobs.reserve(2 * (size_t)npairs);
   for (int i = 0; i < npairs; i++) {
+    pairs[i].q_i8 = pairs[i].t_i8 = nullptr;
+    if (tc) {
+      pairs[i].q_i8 = (const int8_t*)s.d_i8_a.ptr + 256 * pn;
+      pairs[i].t_i8 = (const int8_t*)s.d_i8_b.ptr + 256 * po;
+      jobs.push_back({(const uint8_t*)s.d_feat_a.ptr + 32 * on, (int8_t*)s.d_i8_a.ptr + 256 * pn, n_newer[i], pad256(n_newer[i])});
+      jobs.push_back({(const uint8_t*)s.d_feat_b.ptr + 32 * oo, (int8_t*)s.d_i8_b.ptr + 256 * po, n_older[i], pad256(n_older[i])});
+      pn += pad256(n_newer[i]);
+      po += pad256(n_older[i]);
+    }
     pairs[i].q_desc = (const uint32_t*)((const uint8_t*)s.d_feat_a.ptr + 32 * on);
     pairs[i].t_desc = (const uint32_t*)((const uint8_t*)s.d_feat_b.ptr + 32 * oo);
     pairs[i].q_xyz = (const float4*)s.d_xyz_a.ptr + on;
@@ -558,6 +680,7 @@ int rgbdslam_b200_match_pairs_host(const uint8_t* desc_newer, const float* xyz_n
     on += n_newer[i];
     oo += n_older[i];
   }
+  if (tc && (rc = expand_nodes(jobs))) return rc;
   return run_pairs(pairs, seed, first_pair_index, results, all_matches, inlier_matches);
 }
 

@@ -19,6 +19,26 @@ struct PairDesc {
   const float4* t_xyz;     // older node points
   int32_t nq, nt;
   int32_t id_q, id_t;  // node ids (newer, older)
+  const int8_t* q_i8;  // +-1 int8 expansion, tiled (hamming_tc.cu); nullptr if the SIMT path is used
+  const int8_t* t_i8;
+};
+
+// One unit of the +-1 int8 expansion (one node).
+struct ExpandJob {
+  const uint8_t* desc;  // n x 32 B
+  int8_t* out;          // n_pad x 256 B, tiled
+  int32_t n, n_pad;     // n_pad: multiple of 256
+};
+
+// One work item of the tensor-core Hamming kernel = (pair, 128-query tile).
+struct HamItem {
+  const int8_t* a;     // query tile (32 KiB)
+  const int8_t* b;     // train matrix of the older node (n_btiles x 64 KiB)
+  int2* out;           // best[] slot of the tile's first query row
+  int32_t nq_valid;    // valid rows in this tile (1..128)
+  int32_t nsearch;     // nt - 1: only train rows [0, nt-2] are examined (features.cpp:174)
+  int32_t n_btiles;    // ceil(nsearch / 256)
+  int32_t pad_;
 };
 
 // Constant-memory copy of the parameters the kernels read.

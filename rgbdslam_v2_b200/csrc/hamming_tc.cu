@@ -1,0 +1,271 @@
+// hamming_tc.cu -- Hamming N x M brute-force match on the 5th-gen tensor cores (tcgen05, sm_100a).
+//
+// bruteForceSearchORB (features.cpp:168-182) for all query rows of all pairs, exact:
+//   256-bit descriptors are expanded once per node to +-1 int8 vectors (bit set -> +1, clear -> -1).
+//   For two descriptors a, b:  a . b = 256 - 2 * hamming(a, b)   (exact in int32)
+//   => argmin_j hd(q_i, t_j)  ==  argmax_j (Q T^T)_ij, ties -> lowest j  (features.cpp:176 strict <).
+// The N x M distance matrix is therefore an int8 GEMM with a row-arg-max epilogue:
+//   tcgen05.mma.kind::i8  M=128 (queries -> TMEM lanes)  N=256 (train rows -> TMEM columns)  K=32 x 8 steps,
+//   int32 accumulators in TMEM, double buffered (2 x 256 columns) so the epilogue of tile n overlaps the
+//   MMAs of tile n+1.
+//
+// Data movement: the expansion kernel writes each node's int8 matrix already in the UMMA canonical
+// K-major no-swizzle shared-memory layout, in 128-row tiles of 32 KiB:
+//     tile[row_group 16][k_chunk 16][row_in_group 8][16 B]
+// so a whole operand tile is ONE contiguous global block and is staged with a single
+// cp.async.bulk (TMA bulk copy, completes on an mbarrier).  No tensor map / swizzle is needed and the
+// MMA reads conflict-free 8x16 B core matrices.
+//
+// Warp roles (192 threads, 1 CTA / SM, persistent over work items = (pair, 128-query tile)):
+//   warp 0 lane 0 : bulk-copy producer (A tile per item, B tiles of 256 train rows, 2-stage rings)
+//   warp 1 lane 0 : tcgen05.mma issuer
+//   warps 2..5    : epilogue -- tcgen05.ld of the accumulator, running arg-max per query row, final store
+#include "kernels.h"
+
+namespace rb200 {
+
+// ---------------------------------------------------------------------------------------------
+// +-1 int8 expansion into the tiled layout described above.  One thread per 16-byte chunk.
+__global__ void __launch_bounds__(256) expand_i8_kernel(const ExpandJob* __restrict__ jobs) {
+  const ExpandJob job = jobs[blockIdx.y];
+  const int c = blockIdx.x * 256 + threadIdx.x;  // chunk index in output order
+  if (c >= job.n_pad * 16) return;
+  const int tile = c >> 11;          // 2048 chunks per 128-row tile
+  const int rg = (c >> 7) & 15;      // row group
+  const int kc = (c >> 3) & 15;      // 16-byte K chunk
+  const int rr = c & 7;              // row in group
+  const int row = tile * 128 + rg * 8 + rr;
+  uint4 out = make_uint4(0, 0, 0, 0);
+  if (row < job.n) {
+    const unsigned bits = (unsigned)job.desc[(size_t)row * 32 + kc * 2] | ((unsigned)job.desc[(size_t)row * 32 + kc * 2 + 1] << 8);
+    unsigned w[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      unsigned v = 0;
+#pragma unroll
+      for (int b = 0; b < 4; b++) v |= (((bits >> (i * 4 + b)) & 1u) ? 0x01u : 0xFFu) << (8 * b);
+      w[i] = v;
+    }
+    out = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  reinterpret_cast<uint4*>(job.out)[c] = out;
+}
+
+cudaError_t launch_expand_i8(const ExpandJob* d_jobs, int njobs, int max_n_pad, cudaStream_t stream) {
+  if (njobs <= 0 || max_n_pad <= 0) return cudaSuccess;
+  dim3 grid((max_n_pad * 16 + 255) / 256, njobs);
+  expand_i8_kernel<<<grid, 256, 0, stream>>>(d_jobs);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory matrix descriptor, K-major, SWIZZLE_NONE ("interleave"):
+//   bits [0,14)  start address >> 4
+//   bits [16,30) leading-dimension byte offset >> 4  = distance between the two 8x16 B core matrices of
+//                one K=32 B step                      = 128 B  (k_chunk stride of the tile layout)
+//   bits [32,46) stride-dimension byte offset >> 4   = distance between consecutive 8-row groups = 2048 B
+//   bits [46,48) descriptor version = 1 (Blackwell);  bits [61,64) layout type = 0 (no swizzle)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)(128u >> 4) << 16) | ((uint64_t)(2048u >> 4) << 32) |
+         (1ull << 46);
+}
+
+constexpr uint32_t kTileA = 128 * 256;   // 32 KiB: 128 query rows x 256 int8
+constexpr uint32_t kTileB = 256 * 256;   // 64 KiB: 256 train rows x 256 int8
+constexpr uint32_t kSmemBars = 2 * kTileA + 2 * kTileB;
+constexpr uint32_t kTcSmemBytes = kSmemBars + 128;
+constexpr int kTcThreads = 192;
+constexpr int kNoBest = (int)0x80000000;
+// instruction descriptor: D=S32 (2<<4), A=INT8 (1<<7), B=INT8 (1<<10), both K-major, N=256, M=128
+constexpr uint32_t kIdescI8 = (2u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+
+__global__ void __launch_bounds__(kTcThreads, 1) hamming_tc_kernel(const HamItem* __restrict__ items, int n_items) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sA = smem_u32(smem);
+  const uint32_t sB = sA + 2 * kTileA;
+  const uint32_t bars = sA + kSmemBars;
+  // barrier slots (8 B each): full_a[2] 0,1 | empty_a[2] 2,3 | full_b[2] 4,5 | empty_b[2] 6,7 | tmem_full[2] 8,9 |
+  // tmem_empty[2] 10,11 ; tmem base pointer at slot 12
+  auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + kSmemBars + 96);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 10; i++) mbar_init(bar(i), 1);
+    mbar_init(bar(10), 4);
+    mbar_init(bar(11), 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32((const void*)tmem_ptr_smem))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
+      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const HamItem item = items[it];
+        mbar_wait(bar(2 + sa), pa ^ 1);
+        mbar_expect_tx(bar(0 + sa), kTileA);
+        bulk_g2s(sA + sa * kTileA, item.a, kTileA, bar(0 + sa));
+        if (++sa == 2) { sa = 0; pa ^= 1; }
+        for (int nb = 0; nb < item.n_btiles; nb++) {
+          mbar_wait(bar(6 + sb), pb ^ 1);
+          mbar_expect_tx(bar(4 + sb), kTileB);
+          bulk_g2s(sB + sb * kTileB, item.b + (size_t)nb * kTileB, kTileB, bar(4 + sb));
+          if (++sb == 2) { sb = 0; pb ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t sa = 0, pa = 0, sb = 0, pb = 0, acc = 0, pacc = 0;
+      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const int n_btiles = items[it].n_btiles;
+        mbar_wait(bar(0 + sa), pa);
+        tc_fence_after();
+        for (int nb = 0; nb < n_btiles; nb++) {
+          mbar_wait(bar(4 + sb), pb);
+          mbar_wait(bar(10 + acc), pacc ^ 1);
+          tc_fence_after();
+          const uint32_t a0 = sA + sa * kTileA, b0 = sB + sb * kTileB;
+#pragma unroll
+          for (int k = 0; k < 8; k++)
+            tc_mma_i8(tmem_base + acc * 256, make_desc(a0 + k * 256), make_desc(b0 + k * 256), kIdescI8, k > 0 ? 1u : 0u);
+          tc_commit(bar(6 + sb));    // B stage may be refilled once these MMAs retire
+          tc_commit(bar(8 + acc));   // accumulator ready for the epilogue
+          if (++sb == 2) { sb = 0; pb ^= 1; }
+          if (++acc == 2) { acc = 0; pacc ^= 1; }
+        }
+        tc_commit(bar(2 + sa));  // A stage free
+        if (++sa == 2) { sa = 0; pa ^= 1; }
+      }
+    }
+  } else {
+    const int wq = warp & 3;  // TMEM lane quadrant this warp may access
+    const int row = wq * 32 + lane;
+    uint32_t acc = 0, pacc = 0;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+      const HamItem item = items[it];
+      int best = kNoBest;
+      for (int nb = 0; nb < item.n_btiles; nb++) {
+        mbar_wait(bar(8 + acc), pacc);
+        tc_fence_after();
+        const uint32_t t0 = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * 256;
+#pragma unroll 1
+        for (int c = 0; c < 8; c++) {
+          uint32_t v[32];
+          tc_ld32(t0 + c * 32, v);
+          tc_wait_ld();
+          const int col0 = nb * 256 + c * 32;
+          if (col0 + 32 <= item.nsearch) {
+#pragma unroll
+            for (int j = 0; j < 32; j++) best = max(best, (int)v[j] * 65536 + (65535 - (col0 + j)));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j++)
+              if (col0 + j < item.nsearch) best = max(best, (int)v[j] * 65536 + (65535 - (col0 + j)));
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(10 + acc));
+        if (++acc == 2) { acc = 0; pacc ^= 1; }
+      }
+      if (row < item.nq_valid) {
+        int2 o = make_int2(257, -1);  // features.cpp:172-173
+        if (best != kNoBest) {
+          const int s = best >> 16;  // dot product = 256 - 2*hd
+          o.x = (256 - s) >> 1;
+          o.y = 65535 - (best & 0xFFFF);
+        }
+        item.out[row] = o;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+cudaError_t launch_hamming_tc(const HamItem* d_items, int n_items, int sm_count, cudaStream_t stream) {
+  if (n_items <= 0) return cudaSuccess;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(hamming_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int grid = n_items < sm_count ? n_items : sm_count;
+  hamming_tc_kernel<<<grid, kTcThreads, kTcSmemBytes, stream>>>(d_items, n_items);
+  return cudaGetLastError();
+}
+
+}  // namespace rb200

@@ -11,6 +11,11 @@ cudaError_t set_dev_params(const DevParams& p, cudaStream_t stream);
 cudaError_t launch_hamming_simt(const PairDesc* pairs, int npairs, int max_nq, int2* best, int stride,
                                 cudaStream_t stream);
 
+// +-1 int8 expansion of the descriptors into the tiled UMMA operand layout (hamming_tc.cu).
+cudaError_t launch_expand_i8(const ExpandJob* d_jobs, int njobs, int max_n_pad, cudaStream_t stream);
+// Tensor-core (tcgen05 kind::i8) Hamming brute force over work items; same output as launch_hamming_simt.
+cudaError_t launch_hamming_tc(const HamItem* d_items, int n_items, int sm_count, cudaStream_t stream);
+
 // hd<128 filter + jitter distance + sort + keep max_matches (node.cpp:572-573,674,1127).
 cudaError_t launch_select_matches(const PairDesc* pairs, int npairs, const int2* best, int stride, uint64_t seed,
                                   int64_t first_pair, rgbdslam_b200_dmatch* matches, float4* mfrom, float4* mto,

@@ -49,12 +49,17 @@ struct State {
   // workspaces
   DevBuf d_pairs, d_best, d_matches, d_inliers, d_mfrom, d_mto, d_nall, d_hyp, d_results;
   DevBuf d_feat_a, d_feat_b, d_xyz_a, d_xyz_b;
-  PinBuf h_pairs;
+  DevBuf d_i8_a, d_i8_b, d_jobs, d_items;
+  PinBuf h_pairs, h_jobs, h_items;
+  int hamming_path = 1;  // 1 = tcgen05 int8 GEMM (hamming_tc.cu), 0 = SIMT popcount (frontend_kernels.cu)
   void release_workspaces() {
     DevBuf* all[] = {&d_pairs, &d_best, &d_matches, &d_inliers, &d_mfrom, &d_mto, &d_nall,
-                     &d_hyp,   &d_results, &d_feat_a, &d_feat_b, &d_xyz_a, &d_xyz_b};
+                     &d_hyp,   &d_results, &d_feat_a, &d_feat_b, &d_xyz_a, &d_xyz_b,
+                     &d_i8_a,  &d_i8_b,    &d_jobs,   &d_items};
     for (DevBuf* b : all) b->release();
     h_pairs.release();
+    h_jobs.release();
+    h_items.release();
   }
 };
 
