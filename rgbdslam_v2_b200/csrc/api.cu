@@ -244,15 +244,17 @@ static int run_pairs(const std::vector<PairDesc>& h_pairs, uint64_t seed, int64_
     if (s.z0 != 0.0 && (rc = push_dev_params())) return rc;
   }
 
+  int hyp_launches = 0;
   e = launch_ransac_hypotheses(npairs, H, maxM, seed, first_pair, (const float4*)s.d_mfrom.ptr,
-                               (const float4*)s.d_mto.ptr, (const int32_t*)s.d_nall.ptr, (HypResult*)s.d_hyp.ptr, st);
+                               (const float4*)s.d_mto.ptr, (const int32_t*)s.d_nall.ptr, (HypResult*)s.d_hyp.ptr, st,
+                               &hyp_launches);
   if (e != cudaSuccess) return cuda_fail(e, "ransac_hyp kernel");
   e = launch_ransac_select(d_pairs, npairs, H, maxM, (const float4*)s.d_mfrom.ptr, (const float4*)s.d_mto.ptr,
                            (const int32_t*)s.d_nall.ptr, (const rgbdslam_b200_dmatch*)s.d_matches.ptr,
                            (const HypResult*)s.d_hyp.ptr, (rgbdslam_b200_pair_result*)s.d_results.ptr,
                            (rgbdslam_b200_dmatch*)s.d_inliers.ptr, st);
   if (e != cudaSuccess) return cuda_fail(e, "ransac_select kernel");
-  s.launches += 2;
+  s.launches += 1 + hyp_launches;
   cudaEventRecord(s.ev[2], st);
 
   if (results) {

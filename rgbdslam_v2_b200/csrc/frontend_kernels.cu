@@ -306,17 +306,40 @@ __device__ __forceinline__ double depth_cov(double z) {  // misc2.h:20-35 (stati
   return __dmul_rn(sd, sd);
 }
 
+// Per-hypothesis constants of the scoring pass (warp-uniform), float64.
+struct ScoreCtx {
+  double R[9], t[3];
+  double P[6];   // rcx * r0_i r0_j + rcy * r1_i r1_j   (ij = 00,01,02,11,12,22), r_k = k-th row of R
+  double O2[6];  // r2_i r2_j
+};
+
+__device__ __forceinline__ void make_score_ctx(const Rt& T, ScoreCtx& c) {
+#pragma unroll
+  for (int i = 0; i < 9; i++) c.R[i] = (double)T.R[i];  // transformation4f.cast<double>() (node.cpp:984)
+#pragma unroll
+  for (int i = 0; i < 3; i++) c.t[i] = (double)T.t[i];
+  const double rcx = c_params.raster_cov_x, rcy = c_params.raster_cov_y;
+  const int I[6] = {0, 0, 0, 1, 1, 2}, J[6] = {0, 1, 2, 1, 2, 2};
+#pragma unroll
+  for (int k = 0; k < 6; k++) {
+    c.P[k] = fma(__dmul_rn(rcx, c.R[I[k]]), c.R[J[k]], __dmul_rn(__dmul_rn(rcy, c.R[3 + I[k]]), c.R[3 + J[k]]));
+    c.O2[k] = __dmul_rn(c.R[6 + I[k]], c.R[6 + J[k]]);
+  }
+}
+
 // errorFunction2 (misc.cpp:697-770) in float64.  Written with explicit rounding intrinsics only, so the
 // hypothesis kernel and the selection kernel (which re-scores the winning transform) produce bit-identical
-// values regardless of how the compiler inlines/contracts.  The 3x3 SPD solve uses the adjugate form
+// values regardless of how the compiler inlines/contracts.
+//   S = R^T diag(rcx z1, rcy z1, cz1) R + diag(rcx z2, rcy z2, cz2)  =  z1 * P + cz1 * O2 + diag(...)
+// (P, O2 precomputed per hypothesis).  The 3x3 SPD solve uses the adjugate form
 // d^T S^-1 d = d^T adj(S) d / det(S) instead of the reference's LLT (same value to rounding).
-__device__ __forceinline__ double mahal_sq(const float4 x1, const float4 x2, const double* Rd, const double* td) {
+__device__ __forceinline__ double mahal_sq(const float4 x1, const float4 x2, const ScoreCtx& c) {
   if (isnan(x1.z) || isnan(x2.z)) return kHuge;
   const double a0 = x1.x, a1 = x1.y, a2 = x1.z, a3 = x1.w;
   const double b0 = x2.x, b1 = x2.y, b2 = x2.z;
-  const double mu0 = fma(Rd[0], a0, fma(Rd[1], a1, fma(Rd[2], a2, __dmul_rn(td[0], a3))));
-  const double mu1 = fma(Rd[3], a0, fma(Rd[4], a1, fma(Rd[5], a2, __dmul_rn(td[1], a3))));
-  const double mu2 = fma(Rd[6], a0, fma(Rd[7], a1, fma(Rd[8], a2, __dmul_rn(td[2], a3))));
+  const double mu0 = fma(c.R[0], a0, fma(c.R[1], a1, fma(c.R[2], a2, __dmul_rn(c.t[0], a3))));
+  const double mu1 = fma(c.R[3], a0, fma(c.R[4], a1, fma(c.R[5], a2, __dmul_rn(c.t[1], a3))));
+  const double mu2 = fma(c.R[6], a0, fma(c.R[7], a1, fma(c.R[8], a2, __dmul_rn(c.t[2], a3))));
   const double d0 = __dsub_rn(mu0, b0), d1 = __dsub_rn(mu1, b1), d2 = __dsub_rn(mu2, b2);
   const double rcx = c_params.raster_cov_x, rcy = c_params.raster_cov_y;
   const double cz1 = depth_cov(a2), cz2 = depth_cov(b2);
@@ -326,18 +349,12 @@ __device__ __forceinline__ double mahal_sq(const float4 x1, const float4 x2, con
     if (dsq > __dmul_rn(2.0, __dadd_rn(s1, s2))) return kHuge;  // misc.cpp:726-735
   }
   if (isnan(d2)) return kHuge;
-  const double c10 = __dmul_rn(rcx, a2), c11 = __dmul_rn(rcy, a2), c12 = cz1;
-  const double c20 = __dmul_rn(rcx, b2), c21 = __dmul_rn(rcy, b2), c22 = cz2;
-  // S = R^T diag(c1) R + diag(c2):  S_ij = sum_k R[k][i] c1_k R[k][j]
-  const double r00 = __dmul_rn(Rd[0], c10), r01 = __dmul_rn(Rd[1], c10), r02 = __dmul_rn(Rd[2], c10);
-  const double r10 = __dmul_rn(Rd[3], c11), r11 = __dmul_rn(Rd[4], c11), r12 = __dmul_rn(Rd[5], c11);
-  const double r20 = __dmul_rn(Rd[6], c12), r21 = __dmul_rn(Rd[7], c12), r22 = __dmul_rn(Rd[8], c12);
-  const double S00 = fma(r00, Rd[0], fma(r10, Rd[3], fma(r20, Rd[6], c20)));
-  const double S11 = fma(r01, Rd[1], fma(r11, Rd[4], fma(r21, Rd[7], c21)));
-  const double S22 = fma(r02, Rd[2], fma(r12, Rd[5], fma(r22, Rd[8], c22)));
-  const double S01 = fma(r00, Rd[1], fma(r10, Rd[4], __dmul_rn(r20, Rd[7])));
-  const double S02 = fma(r00, Rd[2], fma(r10, Rd[5], __dmul_rn(r20, Rd[8])));
-  const double S12 = fma(r01, Rd[2], fma(r11, Rd[5], __dmul_rn(r21, Rd[8])));
+  const double S00 = fma(a2, c.P[0], fma(cz1, c.O2[0], __dmul_rn(rcx, b2)));
+  const double S01 = fma(a2, c.P[1], __dmul_rn(cz1, c.O2[1]));
+  const double S02 = fma(a2, c.P[2], __dmul_rn(cz1, c.O2[2]));
+  const double S11 = fma(a2, c.P[3], fma(cz1, c.O2[3], __dmul_rn(rcy, b2)));
+  const double S12 = fma(a2, c.P[4], __dmul_rn(cz1, c.O2[4]));
+  const double S22 = fma(a2, c.P[5], fma(cz1, c.O2[5], cz2));
   const double A00 = fma(S11, S22, -__dmul_rn(S12, S12));
   const double A01 = fma(S02, S12, -__dmul_rn(S01, S22));
   const double A02 = fma(S01, S12, -__dmul_rn(S02, S11));
@@ -358,11 +375,8 @@ __device__ __forceinline__ double mahal_sq(const float4 x1, const float4 x2, con
 // the Mahalanobis RMS (1e9 if < 3 inliers).
 __device__ int score_all(const float4* __restrict__ sfrom, const float4* __restrict__ sto, int M, int nw, int lane,
                          const Rt& T, uint32_t* words, double& err) {
-  double Rd[9], td[3];
-#pragma unroll
-  for (int i = 0; i < 9; i++) Rd[i] = (double)T.R[i];
-#pragma unroll
-  for (int i = 0; i < 3; i++) td[i] = (double)T.t[i];
+  ScoreCtx ctx;
+  make_score_ctx(T, ctx);
   const double sq_max = c_params.sq_max_dist;
   double esum = 0.0;
   int cnt = 0;
@@ -376,7 +390,7 @@ __device__ int score_all(const float4* __restrict__ sfrom, const float4* __restr
       if (i < M) {
         const float4 a = sfrom[i], b = sto[i];
         if (!(a.z == 0.0f || b.z == 0.0f)) {  // node.cpp:994 (does not trigger on NaN)
-          m = mahal_sq(a, b, Rd, td);
+          m = mahal_sq(a, b, ctx);
           inl = !(m > sq_max) && (m >= 0.0);  // node.cpp:998-1005
         }
       }
@@ -399,24 +413,77 @@ __device__ __forceinline__ unsigned min_inlier_threshold(int M) {  // node.cpp:1
 
 constexpr int kRansacWarps = 8;
 
+// The reference's bookkeeping over finished hypotheses (node.cpp:1170-1190), replayed in order over the
+// records of hypotheses [0, n_limit): global best by (error <=, inliers >=), the "n += 10" shortcuts for
+// > 50 % / > 75 % inliers and the break at > 80 %.  Returns the next hypothesis index the sequential loop
+// would visit (>= n_limit) -- hypotheses below it that were jumped over are never looked at.
+struct ScanState {
+  float rmse;
+  int best_cnt, best_n, valid, next_n;
+  bool done;
+};
+
+__device__ ScanState ransac_scan(const HypResult* __restrict__ hp, int M, unsigned min_thr, int n_limit) {
+  ScanState st;
+  st.rmse = 1e6f;  // node.cpp:1110
+  st.best_cnt = 0;
+  st.best_n = -1;
+  st.valid = 0;
+  st.done = false;
+  int n = 0;
+  for (; n < n_limit; n++) {  // node.cpp:1130
+    const int cnt = hp[n].count;
+    if (cnt > 0) {  // node.cpp:1170
+      st.valid++;
+      const double err = hp[n].err;
+      if (err <= (double)st.rmse && cnt >= st.best_cnt && (unsigned)cnt >= min_thr) {  // node.cpp:1177-1179
+        st.rmse = (float)err;
+        st.best_cnt = cnt;
+        st.best_n = n;
+        if ((double)cnt > (double)M * 0.5) n += 10;   // node.cpp:1186
+        if ((double)cnt > (double)M * 0.75) n += 10;  // node.cpp:1187
+        if ((double)cnt > (double)M * 0.8) {          // node.cpp:1188
+          st.done = true;
+          break;
+        }
+      }
+    }
+  }
+  st.next_n = n;
+  return st;
+}
+
+// Hypotheses [n_begin, n_end) of every pair.  The host launches this in growing phases ([0,8), [8,40),
+// [40,H)); a CTA first replays the scan over the already finished prefix [0, n_begin) and skips work the
+// sequential reference loop would never reach (pair finished by the > 80 % break, or index jumped over).
 __global__ void __launch_bounds__(kRansacWarps * 32)
-    ransac_hyp_kernel(int H, int maxM, uint64_t seed, int64_t first_pair, const float4* __restrict__ mfrom,
-                      const float4* __restrict__ mto, const int32_t* __restrict__ n_all, HypResult* __restrict__ hyp) {
+    ransac_hyp_kernel(int H, int maxM, int n_begin, int n_end, uint64_t seed, int64_t first_pair,
+                      const float4* __restrict__ mfrom, const float4* __restrict__ mto,
+                      const int32_t* __restrict__ n_all, HypResult* __restrict__ hyp) {
   __shared__ float4 sfrom[kMaxMatchesCap];
   __shared__ float4 sto[kMaxMatchesCap];
+  __shared__ int s_next_n;
   const int p = blockIdx.y;
   const int M = n_all[p];
   if (M <= c_params.min_matches || M < 4) return;  // node.cpp:1087,1130 (selection kernel checks the same)
+  const unsigned min_thr = min_inlier_threshold(M);
+  if (n_begin > 0) {
+    if (threadIdx.x == 0) {
+      const ScanState st = ransac_scan(hyp + (size_t)p * H, M, min_thr, n_begin);
+      s_next_n = st.done ? H : st.next_n;
+    }
+    __syncthreads();
+    if (s_next_n >= n_begin + (int)(blockIdx.x + 1) * kRansacWarps || s_next_n >= n_end) return;
+  }
   for (int i = threadIdx.x; i < M; i += blockDim.x) {
     sfrom[i] = mfrom[(size_t)p * maxM + i];
     sto[i] = mto[(size_t)p * maxM + i];
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  const int n = blockIdx.x * kRansacWarps + (threadIdx.x >> 5);
-  if (n >= H) return;
+  const int n = n_begin + blockIdx.x * kRansacWarps + (threadIdx.x >> 5);
+  if (n >= n_end || (n_begin > 0 && n < s_next_n)) return;
   const int nw = (M + 31) >> 5;
-  const unsigned min_thr = min_inlier_threshold(M);
   const uint64_t key = pair_key(seed, (uint64_t)(first_pair + p));
 
   // sample_matches_prefer_by_distance(4, ...) (node.cpp:1024-1047)
@@ -486,12 +553,22 @@ __global__ void __launch_bounds__(kRansacWarps * 32)
 
 cudaError_t launch_ransac_hypotheses(int npairs, int ransac_iterations, int max_matches, uint64_t seed,
                                      int64_t first_pair, const float4* mfrom, const float4* mto,
-                                     const int32_t* n_all, HypResult* hyp, cudaStream_t stream) {
+                                     const int32_t* n_all, HypResult* hyp, cudaStream_t stream, int* n_launches) {
+  if (n_launches) *n_launches = 0;
   if (npairs <= 0 || ransac_iterations <= 0) return cudaSuccess;
-  dim3 grid((ransac_iterations + kRansacWarps - 1) / kRansacWarps, npairs);
-  ransac_hyp_kernel<<<grid, kRansacWarps * 32, 0, stream>>>(ransac_iterations, max_matches, seed, first_pair, mfrom, mto,
-                                                            n_all, hyp);
-  return cudaGetLastError();
+  const int H = ransac_iterations;
+  const int bounds[4] = {0, 8, 40, H};
+  for (int ph = 0; ph < 3; ph++) {
+    const int n_begin = bounds[ph], n_end = bounds[ph + 1] < H ? bounds[ph + 1] : H;
+    if (n_begin >= n_end) continue;
+    dim3 grid((n_end - n_begin + kRansacWarps - 1) / kRansacWarps, npairs);
+    ransac_hyp_kernel<<<grid, kRansacWarps * 32, 0, stream>>>(H, max_matches, n_begin, n_end, seed, first_pair, mfrom,
+                                                              mto, n_all, hyp);
+    if (n_launches) (*n_launches)++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
 }
 
 // One warp per pair.
@@ -526,26 +603,10 @@ __global__ void __launch_bounds__(32)
   if (run) {
     const int nw = (M + 31) >> 5;
     const unsigned min_thr = min_inlier_threshold(M);
-    float rmse = 1e6f;  // node.cpp:1110
-    int best_cnt = 0, best_n = -1, valid = 0;
     const HypResult* hp = hyp + (size_t)p * H;
-    if (M >= 4) {
-      for (int n = 0; n < H; n++) {  // node.cpp:1130
-        const int cnt = hp[n].count;
-        if (cnt > 0) {  // node.cpp:1170
-          valid++;
-          const double err = hp[n].err;
-          if (err <= (double)rmse && cnt >= best_cnt && (unsigned)cnt >= min_thr) {  // node.cpp:1177-1179
-            rmse = (float)err;
-            best_cnt = cnt;
-            best_n = n;
-            if ((double)cnt > (double)M * 0.5) n += 10;   // node.cpp:1186
-            if ((double)cnt > (double)M * 0.75) n += 10;  // node.cpp:1187
-            if ((double)cnt > (double)M * 0.8) break;     // node.cpp:1188
-          }
-        }
-      }
-    }
+    const ScanState st = ransac_scan(hp, M, min_thr, M >= 4 ? H : 0);
+    float rmse = st.rmse;
+    int best_n = st.best_n, valid = st.valid;
     Rt T;
 #pragma unroll
     for (int i = 0; i < 9; i++) T.R[i] = (i % 4 == 0) ? 1.f : 0.f;
