@@ -1,0 +1,164 @@
+// node.hpp -- header-only C++ shim that keeps the reference's call sites compiling against the C ABI.
+//
+// Mirrors, for the frame-pair hot path only:
+//   LoadedEdge3D                 src/edge.h:24-32
+//   MatchingResult               src/matching_result.h:24-46
+//   Node (feature members, matchNodePair, featureMatching-free ctor from features)   src/node.h:64-178
+//   bruteForceSearchORB          src/features.h:13, src/features.cpp:168-182
+// The reference types Eigen::Matrix4f / Eigen::Isometry3d / cv::DMatch / cv::KeyPoint are replaced by
+// layout-compatible PODs (column-major float[16] etc.) so this header has no third-party dependency; a
+// maintainer who has Eigen/OpenCV maps them with Eigen::Map / reinterpret_cast.
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../rgbdslam_b200.h"
+
+namespace rgbdslam_b200 {
+
+struct Matrix4f {  // == Eigen::Matrix4f storage (column-major)
+  float m[16];
+  static Matrix4f Identity() {
+    Matrix4f r;
+    for (int i = 0; i < 16; i++) r.m[i] = (i % 5 == 0) ? 1.f : 0.f;
+    return r;
+  }
+  float operator()(int row, int col) const { return m[4 * col + row]; }
+};
+struct Isometry3d {  // == Eigen::Isometry3d storage (4x4 column-major double)
+  double m[16];
+};
+struct Matrix6d {
+  double m[36];
+};
+struct Vector4f {
+  float x, y, z, w;
+};
+typedef rgbdslam_b200_dmatch DMatch;      // == cv::DMatch
+typedef rgbdslam_b200_keypoint KeyPoint;  // == cv::KeyPoint
+
+struct LoadedEdge3D {  // src/edge.h:24-32
+  int id1, id2;
+  Isometry3d transform;
+  Matrix6d informationMatrix;
+};
+
+class MatchingResult {  // src/matching_result.h:24-46
+ public:
+  MatchingResult()
+      : rmse(0.0), ransac_trafo(Matrix4f::Identity()), final_trafo(Matrix4f::Identity()), icp_trafo(Matrix4f::Identity()),
+        inlier_points(0), outlier_points(0), occluded_points(0), all_points(0) {
+    edge.id1 = edge.id2 = -1;
+    std::memset(&edge.transform, 0, sizeof(edge.transform));
+    std::memset(&edge.informationMatrix, 0, sizeof(edge.informationMatrix));
+  }
+  std::vector<DMatch> inlier_matches;
+  std::vector<DMatch> all_matches;
+  LoadedEdge3D edge;
+  float rmse;
+  Matrix4f ransac_trafo, final_trafo, icp_trafo;
+  unsigned int inlier_points, outlier_points, occluded_points, all_points;
+};
+
+inline void check(int rc, const char* what) {
+  if (rc != 0) throw std::runtime_error(std::string(what) + ": " + rgbdslam_b200_last_error());
+}
+
+// Fill a MatchingResult from the flat ABI record (what node.cpp:1334-1339 does with the RANSAC output).
+inline MatchingResult to_matching_result(const rgbdslam_b200_pair_result& r, const DMatch* all, const DMatch* inl) {
+  MatchingResult mr;
+  mr.all_matches.assign(all, all + r.n_all_matches);
+  mr.inlier_matches.assign(inl, inl + r.n_inliers);
+  mr.rmse = r.rmse;
+  std::memcpy(mr.ransac_trafo.m, r.ransac_trafo, sizeof(r.ransac_trafo));
+  mr.edge.id1 = r.id1;
+  mr.edge.id2 = r.id2;
+  if (r.id1 >= 0) {
+    mr.final_trafo = mr.ransac_trafo;                                               // node.cpp:1334
+    for (int i = 0; i < 16; i++) mr.edge.transform.m[i] = (double)r.ransac_trafo[i];  // node.cpp:1339
+    for (int i = 0; i < 6; i++) mr.edge.informationMatrix.m[7 * i] = r.info_scale;    // node.cpp:1335
+  }
+  return mr;
+}
+
+class Node {  // src/node.h: the members the hot path reads + matchNodePair
+ public:
+  int id_ = -1, seq_id_ = -1, vertex_id_ = -1;
+  std::vector<KeyPoint> feature_locations_2d_;  // node.h:167
+  std::vector<Vector4f> feature_locations_3d_;  // node.h:174
+  std::vector<uint8_t> feature_descriptors_;    // N x 32 (cv::Mat CV_8U rows), node.h:169
+
+  Node() {}
+  // Construct from already extracted features (what the reference ctor node.cpp:101-240 leaves behind).
+  Node(int id, const std::vector<uint8_t>& desc, const std::vector<Vector4f>& xyz) : id_(id) {
+    feature_descriptors_ = desc;
+    feature_locations_3d_ = xyz;
+    upload();
+  }
+  ~Node() {  // Node::~Node (node.cpp:371)
+    if (handle_) rgbdslam_b200_node_destroy(handle_);
+  }
+  Node(const Node&) = delete;
+  Node& operator=(const Node&) = delete;
+
+  void upload() {
+    if (handle_) rgbdslam_b200_node_destroy(handle_);
+    handle_ = 0;
+    check(rgbdslam_b200_node_create_from_features(id_, feature_descriptors_.data(),
+                                                  reinterpret_cast<const float*>(feature_locations_3d_.data()),
+                                                  (int)feature_locations_3d_.size(), &handle_),
+          "node_create_from_features");
+  }
+  uint64_t handle() const { return handle_; }
+
+  // MatchingResult Node::matchNodePair(const Node* older_node)  (node.cpp:1305).  Never throws on a failed
+  // match: failure is edge.id1 == edge.id2 == -1 (node.cpp:1420), as in the reference.
+  MatchingResult matchNodePair(const Node* older_node, uint64_t seed = 0, int64_t pair_index = 0) const {
+    std::vector<MatchingResult> v = matchNodePairs(this, std::vector<const Node*>(1, older_node), seed, pair_index);
+    return v[0];
+  }
+
+  // The QtConcurrent::blockingMapped(nodes_to_comp, bind(&Node::matchNodePair, new_node, _1)) fan-out of
+  // graph_manager.cpp:548 as ONE batched launch.
+  static std::vector<MatchingResult> matchNodePairs(const Node* newer, const std::vector<const Node*>& older,
+                                                    uint64_t seed = 0, int64_t first_pair_index = 0) {
+    const int n = (int)older.size();
+    std::vector<MatchingResult> out(n);
+    if (n == 0) return out;
+    rgbdslam_b200_params prm;
+    rgbdslam_b200_default_params(&prm);  // only for max_matches of the output arrays; see max_matches()
+    const int mm = max_matches();
+    std::vector<uint64_t> a(n, newer->handle_), b(n);
+    for (int i = 0; i < n; i++) b[i] = older[i]->handle_;
+    std::vector<rgbdslam_b200_pair_result> res(n);
+    std::vector<DMatch> all((size_t)n * mm), inl((size_t)n * mm);
+    int rc = rgbdslam_b200_match_pairs(a.data(), b.data(), n, seed, first_pair_index, res.data(), all.data(), inl.data());
+    if (rc != 0) return out;  // invalid edges (-1,-1): matchNodePair never throws (node.cpp:1308,1424)
+    for (int i = 0; i < n; i++) out[i] = to_matching_result(res[i], &all[(size_t)i * mm], &inl[(size_t)i * mm]);
+    return out;
+  }
+
+  static int& max_matches() {  // set once after rgbdslam_b200_init with params.max_matches
+    static int v = 300;
+    return v;
+  }
+
+ private:
+  uint64_t handle_ = 0;
+};
+
+}  // namespace rgbdslam_b200
+
+// int bruteForceSearchORB(const uint64_t* v, const uint64_t* search_array, const unsigned int& size, int& result_index)
+// -- src/features.h:13.  Single-query form kept for source compatibility; batch callers should use
+// rgbdslam_b200_brute_force_orb directly (one launch for all query rows).
+inline int bruteForceSearchORB(const uint64_t* v, const uint64_t* search_array, const unsigned int& size, int& result_index) {
+  int32_t idx = -1, hd = 257;
+  if (rgbdslam_b200_brute_force_orb(v, 1, search_array, (int)size, &idx, &hd) != 0)
+    throw std::runtime_error(rgbdslam_b200_last_error());
+  result_index = idx;
+  return hd;
+}

@@ -313,8 +313,8 @@ int rgbdslam_b200_init(int device, const rgbdslam_b200_params* p) {
   if (p) prm = *p;
   else rgbdslam_b200_default_params(&prm);
   if (prm.max_matches < 1 || prm.max_matches > RGBDSLAM_B200_MAX_MATCHES_CAP || prm.min_matches < 0 ||
-      prm.ransac_iterations < 0 || prm.ransac_iterations > 100000) {
-    set_error("invalid parameters (max_matches must be in [1,512], ransac_iterations in [0,100000])");
+      prm.ransac_iterations < 0 || prm.ransac_iterations > 10000) {
+    set_error("invalid parameters (max_matches must be in [1,512], ransac_iterations in [0,10000])");
     return RGBDSLAM_B200_ERR_ARG;
   }
   int count = 0;

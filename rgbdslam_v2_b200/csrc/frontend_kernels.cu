@@ -230,7 +230,7 @@ __device__ bool fit_transform(const float4* __restrict__ sfrom, const float4* __
     const float alpha = AP0 * AP0 + AP1 * AP1 + AP2 * AP2;                                           \
     const float beta = AQ0 * AQ0 + AQ1 * AQ1 + AQ2 * AQ2;                                            \
     const float gamma = AP0 * AQ0 + AP1 * AQ1 + AP2 * AQ2;                                           \
-    if (fabsf(gamma) > 1e-7f * sqrtf(alpha * beta) && gamma != 0.f) {                                \
+    if (fabsf(gamma) > 4e-7f * sqrtf(alpha * beta) && gamma != 0.f) {                                \
       rotated = true;                                                                                \
       const float zeta = (beta - alpha) / (2.f * gamma);                                             \
       const float tt = copysignf(1.f, zeta) / (fabsf(zeta) + sqrtf(1.f + zeta * zeta));             \
@@ -244,7 +244,7 @@ __device__ bool fit_transform(const float4* __restrict__ sfrom, const float4* __
       x = VP2; y = VQ2; VP2 = cs * x - sn * y; VQ2 = sn * x + cs * y;                                \
     }                                                                                                \
   }
-  for (int sweep = 0; sweep < 10; sweep++) {
+  for (int sweep = 0; sweep < 6; sweep++) {
     bool rotated = false;
     RB200_JROT(a00, a10, a20, a01, a11, a21, v00, v10, v20, v01, v11, v21)  // columns 0,1
     RB200_JROT(a00, a10, a20, a02, a12, a22, v00, v10, v20, v02, v12, v22)  // columns 0,2
@@ -423,7 +423,9 @@ struct ScanState {
   bool done;
 };
 
-__device__ ScanState ransac_scan(const HypResult* __restrict__ hp, int M, unsigned min_thr, int n_limit) {
+// `cnt` / `err` are shared-memory copies of the records' count / err fields (staged in parallel by the
+// caller: a dependent chain of 200 global loads would cost ~60 us).
+__device__ ScanState ransac_scan(const int* cnt_s, const double* err_s, int M, unsigned min_thr, int n_limit) {
   ScanState st;
   st.rmse = 1e6f;  // node.cpp:1110
   st.best_cnt = 0;
@@ -432,10 +434,10 @@ __device__ ScanState ransac_scan(const HypResult* __restrict__ hp, int M, unsign
   st.done = false;
   int n = 0;
   for (; n < n_limit; n++) {  // node.cpp:1130
-    const int cnt = hp[n].count;
+    const int cnt = cnt_s[n];
     if (cnt > 0) {  // node.cpp:1170
       st.valid++;
-      const double err = hp[n].err;
+      const double err = err_s[n];
       if (err <= (double)st.rmse && cnt >= st.best_cnt && (unsigned)cnt >= min_thr) {  // node.cpp:1177-1179
         st.rmse = (float)err;
         st.best_cnt = cnt;
@@ -453,6 +455,8 @@ __device__ ScanState ransac_scan(const HypResult* __restrict__ hp, int M, unsign
   return st;
 }
 
+constexpr int kMaxScanPrefix = 64;  // largest n_begin of a non-final phase (phases: [0,8) [8,40) [40,H))
+
 // Hypotheses [n_begin, n_end) of every pair.  The host launches this in growing phases ([0,8), [8,40),
 // [40,H)); a CTA first replays the scan over the already finished prefix [0, n_begin) and skips work the
 // sequential reference loop would never reach (pair finished by the > 80 % break, or index jumped over).
@@ -463,13 +467,22 @@ __global__ void __launch_bounds__(kRansacWarps * 32)
   __shared__ float4 sfrom[kMaxMatchesCap];
   __shared__ float4 sto[kMaxMatchesCap];
   __shared__ int s_next_n;
+  __shared__ int s_cnt[kMaxScanPrefix];
+  __shared__ double s_err[kMaxScanPrefix];
   const int p = blockIdx.y;
   const int M = n_all[p];
   if (M <= c_params.min_matches || M < 4) return;  // node.cpp:1087,1130 (selection kernel checks the same)
   const unsigned min_thr = min_inlier_threshold(M);
   if (n_begin > 0) {
+    // records of hypotheses the sequential loop never visits are stale/unwritten: harmless, the scan skips them
+    for (int i = threadIdx.x; i < n_begin; i += blockDim.x) {
+      const HypResult* r = hyp + (size_t)p * H + i;
+      s_cnt[i] = r->count;
+      s_err[i] = r->err;
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
-      const ScanState st = ransac_scan(hyp + (size_t)p * H, M, min_thr, n_begin);
+      const ScanState st = ransac_scan(s_cnt, s_err, M, min_thr, n_begin);
       s_next_n = st.done ? H : st.next_n;
     }
     __syncthreads();
@@ -557,7 +570,7 @@ cudaError_t launch_ransac_hypotheses(int npairs, int ransac_iterations, int max_
   if (n_launches) *n_launches = 0;
   if (npairs <= 0 || ransac_iterations <= 0) return cudaSuccess;
   const int H = ransac_iterations;
-  const int bounds[4] = {0, 8, 40, H};
+  const int bounds[4] = {0, 8, 40, H};  // non-final phase ends must stay <= kMaxScanPrefix
   for (int ph = 0; ph < 3; ph++) {
     const int n_begin = bounds[ph], n_end = bounds[ph + 1] < H ? bounds[ph + 1] : H;
     if (n_begin >= n_end) continue;
@@ -604,7 +617,17 @@ __global__ void __launch_bounds__(32)
     const int nw = (M + 31) >> 5;
     const unsigned min_thr = min_inlier_threshold(M);
     const HypResult* hp = hyp + (size_t)p * H;
-    const ScanState st = ransac_scan(hp, M, min_thr, M >= 4 ? H : 0);
+    extern __shared__ double sel_smem[];  // H doubles (err) followed by H ints (count)
+    double* err_s = sel_smem;
+    int* cnt_s = reinterpret_cast<int*>(sel_smem + H);
+    if (M >= 4) {
+      for (int i = lane; i < H; i += 32) {
+        cnt_s[i] = hp[i].count;
+        err_s[i] = hp[i].err;
+      }
+    }
+    __syncwarp();
+    const ScanState st = ransac_scan(cnt_s, err_s, M, min_thr, M >= 4 ? H : 0);
     float rmse = st.rmse;
     int best_n = st.best_n, valid = st.valid;
     Rt T;
@@ -673,8 +696,13 @@ cudaError_t launch_ransac_select(const PairDesc* pairs, int npairs, int ransac_i
                                  rgbdslam_b200_pair_result* results, rgbdslam_b200_dmatch* inlier_matches,
                                  cudaStream_t stream) {
   if (npairs <= 0) return cudaSuccess;
-  ransac_select_kernel<<<npairs, 32, 0, stream>>>(pairs, ransac_iterations, max_matches, mfrom, mto, n_all, matches, hyp,
-                                                  results, inlier_matches);
+  const size_t smem = (size_t)ransac_iterations * 12 + 16;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(ransac_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  ransac_select_kernel<<<npairs, 32, smem, stream>>>(pairs, ransac_iterations, max_matches, mfrom, mto, n_all, matches, hyp,
+                                                     results, inlier_matches);
   return cudaGetLastError();
 }
 
