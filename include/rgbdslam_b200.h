@@ -180,6 +180,26 @@ int rgbdslam_b200_match_pairs_host(const uint8_t* desc_newer, const float* xyz_n
  * and of the whole device part of the last match_pairs* call. */
 int rgbdslam_b200_last_timing(float* hamming_ms, float* total_device_ms);
 
+/* ---- pose-graph solve --------------------------------------------------------
+ * == GraphManager::optimizeGraph(double iter, bool nonthreaded) -> optimizeGraphImpl
+ * (src/graph_manager.cpp:900-1066) on the optimizer createOptimizer builds (:107-201):
+ * Levenberg-Marquardt, 6x6 pose blocks, block-Jacobi PCG (backend_solver "pcg"), EdgeSE3 with the shared Huber
+ * kernel (graph_manager.h:382, delta 1.0), fixed vertices per fixationOfVertices (:911-937).
+ *   poses : nv x 7 doubles (tx ty tz qx qy qz qw), in = current estimates (vertex = v1 * T,
+ *           graph_manager.cpp:858), out = optimised estimates
+ *   fixed : nv bytes, 1 = setFixed(true)            ij : ne x 2 vertex indices (edge.id1, edge.id2)
+ *   meas  : ne x 7 (LoadedEdge3D::transform)         info : ne x 36 row-major (LoadedEdge3D::informationMatrix)
+ *   stop  : optimizer_iterations semantics (graph_manager.cpp:998-1014): >= 1 iteration budget,
+ *           (0,1) relative chi2 improvement per chunk of 5 iterations
+ * Returns chi2 = optimizer_->chi2() (sum e' Omega e), the number of LM iterations and of PCG iterations. */
+int rgbdslam_b200_posegraph_optimize(int nv, double* poses, const uint8_t* fixed, int ne, const int32_t* ij,
+                                     const double* meas, const double* info, double stop, double huber_delta,
+                                     double* chi2, int* iters, int* cg_iters);
+/* computeActiveErrors + chi2 (graph_manager.cpp:1002-1003); per_edge_chi2 (ne doubles, may be NULL) is what
+ * pruneEdgesWithErrorAbove (graph_manager.cpp:1106-1246) thresholds. */
+int rgbdslam_b200_posegraph_chi2(int nv, const double* poses, int ne, const int32_t* ij, const double* meas,
+                                 const double* info, double huber_delta, double* chi2, double* per_edge_chi2);
+
 #ifdef __cplusplus
 }
 #endif

@@ -148,3 +148,40 @@ def first_depth_z0(params: OParams, allm_row, n_all, xyz_newer, xyz_older):
             continue
         return float(zf)
     return 0.0
+
+
+# ---- pose graph ------------------------------------------------------------------------------------
+def edge_se3(xi, xj, z, want_jac=True):
+    xi = np.ascontiguousarray(xi, np.float64); xj = np.ascontiguousarray(xj, np.float64); z = np.ascontiguousarray(z, np.float64)
+    e = np.zeros(6); Ji = np.zeros(36); Jj = np.zeros(36)
+    lib().oracle_edge_se3(_p(xi), _p(xj), _p(z), _p(e), _p(Ji) if want_jac else None, _p(Jj) if want_jac else None)
+    return e, Ji.reshape(6, 6), Jj.reshape(6, 6)
+
+
+def vertex_oplus(x, d):
+    x = np.array(x, np.float64); d = np.ascontiguousarray(d, np.float64)
+    lib().oracle_vertex_oplus(_p(x), _p(d))
+    return x
+
+
+def posegraph_optimize(poses, fixed, ij, meas, info, stop=0.01, huber_delta=1.0):
+    """== GraphManager::optimizeGraph (graph_manager.cpp:900-1066); returns (poses, chi2, lm_iterations, cg_iterations)."""
+    x = np.array(poses, np.float64, order="C")
+    fixed = np.ascontiguousarray(fixed, np.uint8); ij = np.ascontiguousarray(ij, np.int32)
+    meas = np.ascontiguousarray(meas, np.float64); info = np.ascontiguousarray(info, np.float64)
+    it = C.c_int(0); cg = C.c_int(0)
+    fn = lib().oracle_posegraph_optimize
+    fn.restype = C.c_double
+    chi2 = fn(C.c_int(len(x)), _p(x), _p(fixed), C.c_int(len(ij)), _p(ij), _p(meas), _p(info), C.c_double(stop),
+              C.c_double(huber_delta), C.byref(it), C.byref(cg))
+    return x, chi2, it.value, cg.value
+
+
+def posegraph_chi2(poses, ij, meas, info, huber_delta=1.0):
+    x = np.ascontiguousarray(poses, np.float64); ij = np.ascontiguousarray(ij, np.int32)
+    meas = np.ascontiguousarray(meas, np.float64); info = np.ascontiguousarray(info, np.float64)
+    rob = C.c_double(0)
+    fn = lib().oracle_posegraph_chi2
+    fn.restype = C.c_double
+    chi2 = fn(C.c_int(len(x)), _p(x), C.c_int(len(ij)), _p(ij), _p(meas), _p(info), C.c_double(huber_delta), C.byref(rob))
+    return chi2, rob.value

@@ -14,8 +14,10 @@
  *   RobustKernelHuber          rho(e2) = e2 | 2*sqrt(e2)*d - d^2 ; weight = 1 | d/sqrt(e2)
  *   OptimizationAlgorithmLevenberg::solve  (lambda_init = 1e-5 * max diag H, nu doubling, <=10 trials,
  *                              rho = (chi_old - chi_new) / (x^T(lambda x + b) + 1e-3), lambda *= clamp(1-(2rho-1)^3, 1/3, 2/3))
- *   LinearSolverPCG            CG with block-Jacobi preconditioner, tolerance 1e-6 (absolute on r^T M^-1 r),
- *                              max iterations = matrix dimension, residual recomputed every 50 iterations
+ *   LinearSolverPCG            CG with block-Jacobi preconditioner, stop when r^T M^-1 r <= d0 with
+ *                              d0 = max(1e-6, 0.5 * final r^T M^-1 r of the previous solve) (absolute tolerance
+ *                              mode, _residual carried between solves), max iterations = matrix dimension,
+ *                              residual updated recursively (the periodic reset is a TODO in g2o)
  * The Jacobians are the exact derivatives of that error under that oplus (g2o uses the same, analytically);
  * tests/test_posegraph_oracle.py checks them against finite differences and the converged solution against an
  * independent scipy sparse Gauss-Newton.
@@ -127,6 +129,7 @@ typedef struct {
   double* Ho;  /* ne x 36: Ji^T W Jj */
   double* b;   /* nv x 6 */
   double* Minv; /* nv x 36 block-Jacobi */
+  double pcg_residual; /* LinearSolverPCG::_residual (-1 initially) */
 } pg_t;
 
 static void mat6_AtWB(const double* A, const double* W, const double* B, double s, double* out /* += s*A^T W B */) {
@@ -250,7 +253,7 @@ static int pg_pcg(pg_t* g, double lambda, double* x, int* iters_out) {
       d[6 * i + a] = v;
       dn += r[6 * i + a] * v;
     }
-  const double tol = 1e-6;
+  const double tol = (g->pcg_residual > 0.0 && g->pcg_residual > 1e-6) ? g->pcg_residual : 1e-6;
   int it = 0, maxit = n;
   int ok = 1;
   for (; it < maxit; it++) {
@@ -261,12 +264,7 @@ static int pg_pcg(pg_t* g, double lambda, double* x, int* iters_out) {
     if (!(dq > 0)) { ok = 0; break; }
     double alpha = dn / dq;
     for (int i = 0; i < n; i++) x[i] += alpha * d[i];
-    if (it % 50 == 0 && it > 0) {
-      pg_spmv(g, lambda, x, q);
-      for (int i = 0; i < n; i++) r[i] = (g->fixed[i / 6] ? 0.0 : g->b[i]) - q[i];
-    } else {
-      for (int i = 0; i < n; i++) r[i] -= alpha * q[i];
-    }
+    for (int i = 0; i < n; i++) r[i] -= alpha * q[i]; /* g2o: "TODO: reset residual here every 50 iterations" (not done) */
     double dold = dn;
     dn = 0;
     for (int i = 0; i < g->nv; i++)
@@ -280,6 +278,7 @@ static int pg_pcg(pg_t* g, double lambda, double* x, int* iters_out) {
     for (int i = 0; i < n; i++) d[i] = s[i] + beta * d[i];
   }
   free(r);
+  g->pcg_residual = 0.5 * dn;
   if (iters_out) *iters_out += it;
   return ok;
 }
@@ -360,6 +359,7 @@ double oracle_posegraph_optimize(int nv, double* poses, const uint8_t* fixed, in
   g.Ho = (double*)malloc(sizeof(double) * 36 * (ne > 0 ? ne : 1));
   g.b = (double*)malloc(sizeof(double) * 6 * nv);
   g.Minv = (double*)malloc(sizeof(double) * 36 * nv);
+  g.pcg_residual = -1.0;
   int it = 0, cg = 0;
   double chi2 = DBL_MAX, robust;
   if (stop >= 1.0) {

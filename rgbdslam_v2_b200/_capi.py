@@ -115,6 +115,9 @@ def load_library(path: str | Path | None = None) -> C.CDLL:
     lib.rgbdslam_b200_match_pairs.argtypes = [vp, vp, C.c_int, u64, i64, vp, vp, vp]
     lib.rgbdslam_b200_match_pairs_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, u64, i64, vp, vp, vp]
     lib.rgbdslam_b200_set_hamming_path.argtypes = [C.c_int]
+    lib.rgbdslam_b200_posegraph_optimize.argtypes = [C.c_int, vp, vp, C.c_int, vp, vp, vp, C.c_double, C.c_double,
+                                                     C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.rgbdslam_b200_posegraph_chi2.argtypes = [C.c_int, vp, C.c_int, vp, vp, vp, C.c_double, C.POINTER(C.c_double), vp]
     lib.rgbdslam_b200_last_timing.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float)]
     for name in declared_symbols():
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
@@ -251,6 +254,30 @@ class Frontend:
             _ptr(desc_newer), _ptr(xyz_newer), _ptr(n_newer), _ptr(desc_older), _ptr(xyz_older), _ptr(n_older),
             _ptr(idn), _ptr(ido), npairs, seed, first_pair_index, _ptr(res), _ptr(allm), _ptr(inl)))
         return res, allm, inl
+
+    # -- GraphManager::optimizeGraph ----------------------------------------------
+    def optimize_graph(self, poses, fixed, ij, meas, info, stop: float = 0.01, huber_delta: float = 1.0):
+        """== GraphManager::optimizeGraph (graph_manager.cpp:900).  Returns (poses, chi2, lm_iters, cg_iters)."""
+        x = np.array(poses, np.float64, order="C")
+        fixed = np.ascontiguousarray(fixed, np.uint8)
+        ij = np.ascontiguousarray(ij, np.int32)
+        meas = np.ascontiguousarray(meas, np.float64)
+        info = np.ascontiguousarray(info, np.float64)
+        chi2, it, cg = C.c_double(), C.c_int(), C.c_int()
+        self._check(self.lib.rgbdslam_b200_posegraph_optimize(len(x), _ptr(x), _ptr(fixed), len(ij), _ptr(ij), _ptr(meas),
+                                                              _ptr(info), stop, huber_delta, C.byref(chi2), C.byref(it), C.byref(cg)))
+        return x, chi2.value, it.value, cg.value
+
+    def graph_chi2(self, poses, ij, meas, info, huber_delta: float = 1.0, per_edge: bool = False):
+        x = np.ascontiguousarray(poses, np.float64)
+        ij = np.ascontiguousarray(ij, np.int32)
+        meas = np.ascontiguousarray(meas, np.float64)
+        info = np.ascontiguousarray(info, np.float64)
+        chi2 = C.c_double()
+        pe = np.zeros(len(ij), np.float64) if per_edge else None
+        self._check(self.lib.rgbdslam_b200_posegraph_chi2(len(x), _ptr(x), len(ij), _ptr(ij), _ptr(meas), _ptr(info),
+                                                          huber_delta, C.byref(chi2), _ptr(pe)))
+        return (chi2.value, pe) if per_edge else chi2.value
 
     def close(self):
         for h in list(self._nodes):

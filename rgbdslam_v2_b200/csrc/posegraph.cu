@@ -1,0 +1,710 @@
+// posegraph.cu -- pose-graph Levenberg-Marquardt on the GPU (float64), the optimiser behind
+// GraphManager::optimizeGraph (src/graph_manager.cpp:900-1066) as configured by createOptimizer
+// (src/graph_manager.cpp:107-201): OptimizationAlgorithmLevenberg / BlockSolver<6,3> / LinearSolverPCG,
+// EdgeSE3 edges with RobustKernelHuber(delta), vertex fixation (graph_manager.cpp:911-937).
+// The reference never marginalises (no Schur step anywhere): H is the 6x6-block sparse Hpp.
+//
+// Kernels (all deterministic: fixed-order reductions, no atomics):
+//   pg_linearize_kernel : per edge  e, Ji, Jj, Huber weight -> blocks A=Ji'WJi, B=Jj'WJj, C=Ji'WJj, gi, gj
+//   pg_assemble_kernel  : per vertex (CSR of incident edges) H_vv = sum A|B, b_v = -sum g ; max diag
+//   pg_pcg_kernel       : whole block-Jacobi PCG in ONE cooperative launch (grid.sync between the phases);
+//                         matrix-free SpMV: y_v = (H_vv + lambda I) d_v + sum_inc (C d_j | C' d_i)
+//   pg_update_kernel    : X <- X * fromVectorMQT(delta)      (VertexSE3::oplusImpl)
+//   pg_chi2_kernel      : sum rho(e'We) and sum e'We          (activeRobustChi2 / chi2)
+// Host: OptimizationAlgorithmLevenberg::solve bookkeeping + the optimizeGraphImpl stop rule
+// (graph_manager.cpp:998-1014).
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "posegraph.h"
+#include "state.h"
+
+namespace cg = cooperative_groups;
+
+namespace rb200 {
+
+// ------------------------------------------------------------------------------------------------
+// SE(3) helpers, poses are (tx,ty,tz,qx,qy,qz,qw)
+__device__ __forceinline__ void quat_to_R(const double* q, double* R) {
+  double x = q[0], y = q[1], z = q[2], w = q[3];
+  const double n = 1.0 / sqrt(x * x + y * y + z * z + w * w);
+  x *= n; y *= n; z *= n; w *= n;
+  R[0] = 1 - 2 * (y * y + z * z); R[1] = 2 * (x * y - z * w);     R[2] = 2 * (x * z + y * w);
+  R[3] = 2 * (x * y + z * w);     R[4] = 1 - 2 * (x * x + z * z); R[5] = 2 * (y * z - x * w);
+  R[6] = 2 * (x * z - y * w);     R[7] = 2 * (y * z + x * w);     R[8] = 1 - 2 * (x * x + y * y);
+}
+__device__ __forceinline__ void quat_mul(const double* a, const double* b, double* o) {
+  const double ax = a[0], ay = a[1], az = a[2], aw = a[3], bx = b[0], by = b[1], bz = b[2], bw = b[3];
+  o[0] = aw * bx + ax * bw + ay * bz - az * by;
+  o[1] = aw * by - ax * bz + ay * bw + az * bx;
+  o[2] = aw * bz + ax * by - ay * bx + az * bw;
+  o[3] = aw * bw - ax * bx - ay * by - az * bz;
+}
+__device__ __forceinline__ void quat_norm(double* q) {
+  const double n = 1.0 / sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  q[0] *= n; q[1] *= n; q[2] *= n; q[3] *= n;
+}
+
+// EdgeSE3::computeError: e = toVectorMQT(Z^-1 Xi^-1 Xj); optionally the exact Jacobians w.r.t. the
+// right-multiplicative increments of VertexSE3::oplusImpl:
+//   Ji = [ -Ra , 2 Ra [tb]x ; 0 , -(we I + [ve]x) Rb' ]   Jj = [ Re , 0 ; 0 , we I + [ve]x ]
+// with Ra = Rz', Rb = Ri' Rj, tb = Ri'(tj - ti), Re = Ra Rb, qe = (ve, we) the error quaternion (we >= 0).
+__device__ void edge_error(const double* xi, const double* xj, const double* z, double* e, double* Ji, double* Jj) {
+  double Ri[9], Rj[9], Rz[9];
+  quat_to_R(xi + 3, Ri);
+  quat_to_R(xj + 3, Rj);
+  quat_to_R(z + 3, Rz);
+  const double d0 = xj[0] - xi[0], d1 = xj[1] - xi[1], d2 = xj[2] - xi[2];
+  double tb[3], Rb[9];
+#pragma unroll
+  for (int r = 0; r < 3; r++) tb[r] = Ri[r] * d0 + Ri[3 + r] * d1 + Ri[6 + r] * d2;
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+#pragma unroll
+    for (int c = 0; c < 3; c++) Rb[3 * r + c] = Ri[r] * Rj[c] + Ri[3 + r] * Rj[3 + c] + Ri[6 + r] * Rj[6 + c];
+  const double dd0 = tb[0] - z[0], dd1 = tb[1] - z[1], dd2 = tb[2] - z[2];
+#pragma unroll
+  for (int r = 0; r < 3; r++) e[r] = Rz[r] * dd0 + Rz[3 + r] * dd1 + Rz[6 + r] * dd2;
+  double qi[4] = {-xi[3], -xi[4], -xi[5], xi[6]}, qj[4] = {xj[3], xj[4], xj[5], xj[6]}, qz[4] = {-z[3], -z[4], -z[5], z[6]};
+  quat_norm(qi); quat_norm(qj); quat_norm(qz);
+  double tmp[4], qe[4];
+  quat_mul(qz, qi, tmp);
+  quat_mul(tmp, qj, qe);
+  quat_norm(qe);
+  if (qe[3] < 0) { qe[0] = -qe[0]; qe[1] = -qe[1]; qe[2] = -qe[2]; qe[3] = -qe[3]; }
+  e[3] = qe[0]; e[4] = qe[1]; e[5] = qe[2];
+  if (!Ji) return;
+  const double we = qe[3], vx = qe[0], vy = qe[1], vz = qe[2];
+  const double Q[9] = {we, -vz, vy, vz, we, -vx, -vy, vx, we};
+  const double Tx[9] = {0, -tb[2], tb[1], tb[2], 0, -tb[0], -tb[1], tb[0], 0};
+#pragma unroll
+  for (int i = 0; i < 36; i++) { Ji[i] = 0; Jj[i] = 0; }
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      const double ra0 = Rz[r], ra1 = Rz[3 + r], ra2 = Rz[6 + r];  // row r of Ra = column r of Rz
+      Ji[6 * r + c] = -Rz[3 * c + r];
+      Ji[6 * r + 3 + c] = 2.0 * (ra0 * Tx[c] + ra1 * Tx[3 + c] + ra2 * Tx[6 + c]);
+      Ji[6 * (3 + r) + 3 + c] = -(Q[3 * r] * Rb[3 * c] + Q[3 * r + 1] * Rb[3 * c + 1] + Q[3 * r + 2] * Rb[3 * c + 2]);
+      Jj[6 * r + c] = ra0 * Rb[c] + ra1 * Rb[3 + c] + ra2 * Rb[6 + c];
+      Jj[6 * (3 + r) + 3 + c] = Q[3 * r + c];
+    }
+}
+
+// out = s * A' (W B), all 6x6 row-major
+__device__ void AtWB(const double* A, const double* W, const double* B, double s, double* out) {
+  double WB[36];
+  for (int r = 0; r < 6; r++)
+    for (int c = 0; c < 6; c++) {
+      double a = 0;
+#pragma unroll
+      for (int k = 0; k < 6; k++) a += W[6 * r + k] * B[6 * k + c];
+      WB[6 * r + c] = a;
+    }
+  for (int r = 0; r < 6; r++)
+    for (int c = 0; c < 6; c++) {
+      double a = 0;
+#pragma unroll
+      for (int k = 0; k < 6; k++) a += A[6 * k + r] * WB[6 * k + c];
+      out[6 * r + c] = s * a;
+    }
+}
+
+// per edge: 120 doubles  [A 36 | B 36 | C 36 | gi 6 | gj 6]
+constexpr int kEdgeBlk = 120;
+
+__global__ void __launch_bounds__(128) pg_linearize_kernel(int ne, const double* __restrict__ x, const int2* __restrict__ ij,
+                                                           const double* __restrict__ meas, const double* __restrict__ info,
+                                                           double delta, double* __restrict__ blk) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= ne) return;
+  const int2 v = ij[k];
+  double e[6], Ji[36], Jj[36], W[36];
+  edge_error(x + 7 * (size_t)v.x, x + 7 * (size_t)v.y, meas + 7 * (size_t)k, e, Ji, Jj);
+  for (int i = 0; i < 36; i++) W[i] = info[36 * (size_t)k + i];
+  double We[6], e2 = 0;
+  for (int a = 0; a < 6; a++) {
+    double s = 0;
+    for (int c = 0; c < 6; c++) s += W[6 * a + c] * e[c];
+    We[a] = s;
+    e2 += e[a] * s;
+  }
+  const double w = (e2 <= delta * delta) ? 1.0 : delta / sqrt(e2);  // RobustKernelHuber rho'
+  double* o = blk + (size_t)k * kEdgeBlk;
+  double t[36];
+  AtWB(Ji, W, Ji, w, t);
+  for (int i = 0; i < 36; i++) o[i] = t[i];
+  AtWB(Jj, W, Jj, w, t);
+  for (int i = 0; i < 36; i++) o[36 + i] = t[i];
+  AtWB(Ji, W, Jj, w, t);
+  for (int i = 0; i < 36; i++) o[72 + i] = t[i];
+  for (int c = 0; c < 6; c++) {
+    double si = 0, sj = 0;
+    for (int a = 0; a < 6; a++) {
+      si += Ji[6 * a + c] * We[a];
+      sj += Jj[6 * a + c] * We[a];
+    }
+    o[108 + c] = w * si;
+    o[114 + c] = w * sj;
+  }
+}
+
+// CSR adjacency: inc[off[v] .. off[v+1]) = (edge << 1 | role), role 0: v is vertex i of the edge, 1: vertex j.
+__global__ void __launch_bounds__(128) pg_assemble_kernel(int nv, const int* __restrict__ off, const int* __restrict__ inc,
+                                                          const uint8_t* __restrict__ fixed, const double* __restrict__ blk,
+                                                          double* __restrict__ Hd, double* __restrict__ b,
+                                                          double* __restrict__ maxdiag_part) {
+  // one thread per (vertex, entry): 42 entries = 36 of H_vv + 6 of b_v; blockDim = 128 -> 3 vertices x 42 (+2 idle)
+  const int lv = threadIdx.x / 42, ent = threadIdx.x % 42;
+  const int v = blockIdx.x * 3 + lv;
+  double val = 0.0;
+  const bool act = (lv < 3) && (v < nv);
+  if (act) {
+    for (int p = off[v]; p < off[v + 1]; p++) {
+      const int code = inc[p];
+      const double* o = blk + (size_t)(code >> 1) * kEdgeBlk;
+      if (ent < 36) val += o[(code & 1) * 36 + ent];
+      else val -= o[108 + (code & 1) * 6 + (ent - 36)];
+    }
+    if (ent < 36) Hd[(size_t)v * 36 + ent] = val;
+    else b[(size_t)v * 6 + (ent - 36)] = fixed[v] ? 0.0 : val;
+  }
+  // max |diag| over free vertices (computeLambdaInit): block partial, fixed order
+  __shared__ double sm[128];
+  double d = 0.0;
+  if (act && ent < 36 && (ent % 7) == 0 && !fixed[v]) d = fabs(val);
+  sm[threadIdx.x] = d;
+  __syncthreads();
+  for (int s = 64; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sm[threadIdx.x] = fmax(sm[threadIdx.x], sm[threadIdx.x + s]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) maxdiag_part[blockIdx.x] = sm[0];
+}
+
+// 6x6 inverse by Gauss-Jordan with partial pivoting (block-Jacobi preconditioner)
+__device__ bool inv6(const double* A, double* Ai) {
+  double M[6][12];
+  for (int r = 0; r < 6; r++)
+    for (int c = 0; c < 6; c++) {
+      M[r][c] = A[6 * r + c];
+      M[r][6 + c] = (r == c) ? 1.0 : 0.0;
+    }
+  for (int c = 0; c < 6; c++) {
+    int p = c;
+    for (int r = c + 1; r < 6; r++)
+      if (fabs(M[r][c]) > fabs(M[p][c])) p = r;
+    if (fabs(M[p][c]) < 1e-300) return false;
+    if (p != c)
+      for (int k = 0; k < 12; k++) {
+        const double t = M[c][k];
+        M[c][k] = M[p][k];
+        M[p][k] = t;
+      }
+    const double d = 1.0 / M[c][c];
+    for (int k = 0; k < 12; k++) M[c][k] *= d;
+    for (int r = 0; r < 6; r++)
+      if (r != c) {
+        const double f = M[r][c];
+        for (int k = 0; k < 12; k++) M[r][k] -= f * M[c][k];
+      }
+  }
+  for (int r = 0; r < 6; r++)
+    for (int c = 0; c < 6; c++) Ai[6 * r + c] = M[r][6 + c];
+  return true;
+}
+
+struct PcgArgs {
+  int nv, ne;
+  const int* off;
+  const int* inc;
+  const int2* ij;
+  const uint8_t* fixed;
+  const double* blk;   // per-edge blocks (C at +72)
+  const double* Hd;    // nv x 36
+  const double* b;     // nv x 6 (0 for fixed)
+  double* Minv;        // nv x 36
+  double* x;           // out: nv x 6
+  double* r;
+  double* d;
+  double* q;
+  double* part;        // grid partial sums (2 x gridDim)
+  double* result;      // [0] iterations, [1] final dn, [2] scale = x'(lambda x + b), [3] breakdown flag
+  double lambda;
+  double tol;
+  int maxit;
+};
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// deterministic grid-wide sum: block partial -> global -> grid.sync -> every block adds the partials in order
+__device__ double grid_sum(cg::grid_group& grid, double v, double* part, double* sm) {
+  v = warp_sum_d(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) sm[warp] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) s += sm[w];
+    part[blockIdx.x] = s;
+  }
+  grid.sync();
+  double tot = 0;
+  for (int i = 0; i < (int)gridDim.x; i++) tot += part[i];
+  return tot;
+}
+
+// y_v = (H_vv + lambda I) d_v + sum over incident edges of the off-diagonal block times the other end.
+// One warp per vertex; lanes split the incident edges.
+__device__ void spmv_vertex(const PcgArgs& a, int v, int lane, const double* __restrict__ vec, double* __restrict__ out) {
+  double acc[6] = {0, 0, 0, 0, 0, 0};
+  if (!a.fixed[v]) {
+    for (int p = a.off[v] + lane; p < a.off[v + 1]; p += 32) {
+      const int code = a.inc[p];
+      const int e = code >> 1;
+      const int2 vv = a.ij[e];
+      if (vv.x == vv.y) continue;
+      const double* C = a.blk + (size_t)e * kEdgeBlk + 72;
+      if ((code & 1) == 0) {  // v == i: C * d_j
+        const double* o = vec + 6 * (size_t)vv.y;
+#pragma unroll
+        for (int r = 0; r < 6; r++)
+#pragma unroll
+          for (int c = 0; c < 6; c++) acc[r] += C[6 * r + c] * o[c];
+      } else {  // v == j: C' * d_i
+        const double* o = vec + 6 * (size_t)vv.x;
+#pragma unroll
+        for (int r = 0; r < 6; r++)
+#pragma unroll
+          for (int c = 0; c < 6; c++) acc[c] += C[6 * r + c] * o[r];
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 6; r++) acc[r] = warp_sum_d(acc[r]);
+  if (lane < 6) {
+    double s = 0;
+    if (!a.fixed[v]) {
+      const double* H = a.Hd + 36 * (size_t)v + 6 * lane;
+      const double* dv = vec + 6 * (size_t)v;
+#pragma unroll
+      for (int c = 0; c < 6; c++) s += H[c] * dv[c];
+      s += a.lambda * dv[lane];
+      double t = 0;
+#pragma unroll
+      for (int r = 0; r < 6; r++) t = (r == lane) ? acc[r] : t;
+      s += t;
+    }
+    out[6 * (size_t)v + lane] = s;
+  }
+}
+
+// LinearSolverPCG: block-Jacobi preconditioned CG on (H + lambda I) x = b; stops when r' M^-1 r <= tol where
+// tol = max(1e-6, 0.5 * final value of the previous solve) (g2o's absolute-tolerance mode).
+__global__ void __launch_bounds__(256) pg_pcg_kernel(PcgArgs a) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double sm[8];
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nthreads = gridDim.x * blockDim.x;
+  const int lane = threadIdx.x & 31;
+  const int gwarp = tid >> 5, nwarps = nthreads >> 5;
+  const int n = 6 * a.nv;
+
+  // preconditioner, x = 0, r = b, d = M^-1 r
+  for (int v = tid; v < a.nv; v += nthreads) {
+    double A[36], Ai[36];
+    for (int i = 0; i < 36; i++) A[i] = a.Hd[36 * (size_t)v + i];
+    for (int k = 0; k < 6; k++) A[7 * k] += a.lambda;
+    const bool ok = !a.fixed[v] && inv6(A, Ai);
+    for (int i = 0; i < 36; i++) a.Minv[36 * (size_t)v + i] = ok ? Ai[i] : 0.0;
+  }
+  grid.sync();
+  double loc = 0;
+  for (int i = tid; i < n; i += nthreads) {
+    const int v = i / 6, rr = i % 6;
+    a.x[i] = 0.0;
+    const double ri = a.b[i];
+    a.r[i] = ri;
+    double s = 0;
+#pragma unroll
+    for (int c = 0; c < 6; c++) s += a.Minv[36 * (size_t)v + 6 * rr + c] * a.b[6 * (size_t)v + c];
+    a.d[i] = s;
+    loc += ri * s;
+  }
+  double dn = grid_sum(grid, loc, a.part, sm);
+  int it = 0;
+  bool breakdown = false;
+  for (; it < a.maxit; it++) {
+    if (dn <= a.tol) break;
+    for (int v = gwarp; v < a.nv; v += nwarps) spmv_vertex(a, v, lane, a.d, a.q);
+    grid.sync();
+    loc = 0;
+    for (int i = tid; i < n; i += nthreads) loc += a.d[i] * a.q[i];
+    const double dq = grid_sum(grid, loc, a.part + gridDim.x, sm);
+    if (!(dq > 0)) { breakdown = true; break; }
+    const double alpha = dn / dq;
+    for (int i = tid; i < n; i += nthreads) {
+      a.x[i] += alpha * a.d[i];
+      a.r[i] -= alpha * a.q[i];  // recursive residual (g2o never resets it)
+    }
+    grid.sync();
+    // s = M^-1 r (kept in q), dn_new = r.s
+    loc = 0;
+    for (int i = tid; i < n; i += nthreads) {
+      const int v = i / 6, rr = i % 6;
+      double s = 0;
+#pragma unroll
+      for (int c = 0; c < 6; c++) s += a.Minv[36 * (size_t)v + 6 * rr + c] * a.r[6 * (size_t)v + c];
+      a.q[i] = s;
+      loc += a.r[i] * s;
+    }
+    const double dn_new = grid_sum(grid, loc, a.part, sm);
+    const double beta = dn_new / dn;
+    dn = dn_new;
+    for (int i = tid; i < n; i += nthreads) a.d[i] = a.q[i] + beta * a.d[i];
+    grid.sync();
+  }
+  grid.sync();  // (uniform) make sure nobody is still summing partials of the last reduction
+  // computeScale(): sum x_j (lambda x_j + b_j)
+  loc = 0;
+  for (int i = tid; i < n; i += nthreads) loc += a.x[i] * (a.lambda * a.x[i] + a.b[i]);
+  const double scale = grid_sum(grid, loc, a.part + gridDim.x, sm);
+  if (tid == 0) {
+    a.result[0] = (double)it;
+    a.result[1] = dn;
+    a.result[2] = scale;
+    a.result[3] = breakdown ? 1.0 : 0.0;
+  }
+}
+
+__global__ void __launch_bounds__(128) pg_update_kernel(int nv, const double* __restrict__ xin, const double* __restrict__ dlt,
+                                                        const uint8_t* __restrict__ fixed, double* __restrict__ xout) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= nv) return;
+  double x[7];
+  for (int i = 0; i < 7; i++) x[i] = xin[7 * (size_t)v + i];
+  if (!fixed[v]) {
+    const double* d = dlt + 6 * (size_t)v;
+    double R[9];
+    quat_to_R(x + 3, R);
+    for (int r = 0; r < 3; r++) x[r] += R[3 * r] * d[0] + R[3 * r + 1] * d[1] + R[3 * r + 2] * d[2];
+    const double w = 1.0 - (d[3] * d[3] + d[4] * d[4] + d[5] * d[5]);
+    if (w >= 0) {  // fromCompactQuaternion: w < 0 -> identity rotation
+      double dq[4] = {d[3], d[4], d[5], sqrt(w)}, q[4] = {x[3], x[4], x[5], x[6]}, o[4];
+      quat_mul(q, dq, o);
+      quat_norm(o);
+      x[3] = o[0]; x[4] = o[1]; x[5] = o[2]; x[6] = o[3];
+    }
+  }
+  for (int i = 0; i < 7; i++) xout[7 * (size_t)v + i] = x[i];
+}
+
+// per-edge chi2 -> block partials of (robust, plain); optional per-edge output
+__global__ void __launch_bounds__(256) pg_chi2_kernel(int ne, const double* __restrict__ x, const int2* __restrict__ ij,
+                                                      const double* __restrict__ meas, const double* __restrict__ info,
+                                                      double delta, double* __restrict__ part, double* __restrict__ per_edge) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  double rob = 0, pl = 0;
+  if (k < ne) {
+    const int2 v = ij[k];
+    double e[6];
+    edge_error(x + 7 * (size_t)v.x, x + 7 * (size_t)v.y, meas + 7 * (size_t)k, e, nullptr, nullptr);
+    const double* W = info + 36 * (size_t)k;
+    double e2 = 0;
+    for (int a = 0; a < 6; a++)
+      for (int c = 0; c < 6; c++) e2 += e[a] * W[6 * a + c] * e[c];
+    pl = e2;
+    rob = (e2 <= delta * delta) ? e2 : 2 * sqrt(e2) * delta - delta * delta;
+    if (per_edge) per_edge[k] = e2;
+  }
+  __shared__ double s0[256], s1[256];
+  s0[threadIdx.x] = rob;
+  s1[threadIdx.x] = pl;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) {
+      s0[threadIdx.x] += s0[threadIdx.x + s];
+      s1[threadIdx.x] += s1[threadIdx.x + s];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    part[2 * blockIdx.x] = s0[0];
+    part[2 * blockIdx.x + 1] = s1[0];
+  }
+}
+
+// ================================================================================================
+// Host driver
+
+struct PgDevice {
+  DevBuf x, xtrial, meas, info, ij, fixed, off, inc, blk, Hd, b, Minv, dx, r, d, q, part, result, chipart, maxpart, per_edge;
+  ~PgDevice() {
+    DevBuf* all[] = {&x, &xtrial, &meas, &info, &ij, &fixed, &off, &inc, &blk, &Hd, &b, &Minv, &dx, &r, &d, &q,
+                     &part, &result, &chipart, &maxpart, &per_edge};
+    for (DevBuf* bb : all) bb->release();
+  }
+};
+
+#define PG_CUDA(call)                                   \
+  do {                                                  \
+    cudaError_t e__ = (call);                           \
+    if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+  } while (0)
+
+struct PgCtx {
+  PgDevice dev;
+  int nv = 0, ne = 0;
+  double delta = 1.0;
+  cudaStream_t st = nullptr;
+  int pcg_grid = 0;
+  int64_t launches = 0;
+  int cg_iters = 0;
+  double pcg_residual = -1.0;  // LinearSolverPCG::_residual
+};
+
+static int pg_errors(PgCtx& c, const double* dx_poses, double* robust, double* plain, double* per_edge) {
+  const int nb = (c.ne + 255) / 256;
+  if (c.ne == 0) {
+    *robust = *plain = 0;
+    return 0;
+  }
+  pg_chi2_kernel<<<nb, 256, 0, c.st>>>(c.ne, dx_poses, (const int2*)c.dev.ij.ptr, (const double*)c.dev.meas.ptr,
+                                       (const double*)c.dev.info.ptr, c.delta, (double*)c.dev.chipart.ptr, per_edge);
+  PG_CUDA(cudaGetLastError());
+  c.launches++;
+  std::vector<double> part(2 * (size_t)nb);
+  PG_CUDA(cudaMemcpyAsync(part.data(), c.dev.chipart.ptr, sizeof(double) * 2 * nb, cudaMemcpyDeviceToHost, c.st));
+  PG_CUDA(cudaStreamSynchronize(c.st));
+  double r = 0, p = 0;
+  for (int i = 0; i < nb; i++) {
+    r += part[2 * i];
+    p += part[2 * i + 1];
+  }
+  *robust = r;
+  *plain = p;
+  return 0;
+}
+
+static int pg_build(PgCtx& c, double* maxdiag) {
+  if (c.ne > 0) {
+    pg_linearize_kernel<<<(c.ne + 127) / 128, 128, 0, c.st>>>(c.ne, (const double*)c.dev.x.ptr, (const int2*)c.dev.ij.ptr,
+                                                               (const double*)c.dev.meas.ptr, (const double*)c.dev.info.ptr,
+                                                               c.delta, (double*)c.dev.blk.ptr);
+    PG_CUDA(cudaGetLastError());
+    c.launches++;
+  }
+  const int nb = (c.nv + 2) / 3;
+  pg_assemble_kernel<<<nb, 128, 0, c.st>>>(c.nv, (const int*)c.dev.off.ptr, (const int*)c.dev.inc.ptr,
+                                           (const uint8_t*)c.dev.fixed.ptr, (const double*)c.dev.blk.ptr,
+                                           (double*)c.dev.Hd.ptr, (double*)c.dev.b.ptr, (double*)c.dev.maxpart.ptr);
+  PG_CUDA(cudaGetLastError());
+  c.launches++;
+  if (maxdiag) {
+    std::vector<double> part(nb);
+    PG_CUDA(cudaMemcpyAsync(part.data(), c.dev.maxpart.ptr, sizeof(double) * nb, cudaMemcpyDeviceToHost, c.st));
+    PG_CUDA(cudaStreamSynchronize(c.st));
+    double m = 0;
+    for (double v : part) m = v > m ? v : m;
+    *maxdiag = m;
+  }
+  return 0;
+}
+
+static int pg_pcg(PgCtx& c, double lambda, double* scale, bool* ok) {
+  PcgArgs a;
+  a.nv = c.nv;
+  a.ne = c.ne;
+  a.off = (const int*)c.dev.off.ptr;
+  a.inc = (const int*)c.dev.inc.ptr;
+  a.ij = (const int2*)c.dev.ij.ptr;
+  a.fixed = (const uint8_t*)c.dev.fixed.ptr;
+  a.blk = (const double*)c.dev.blk.ptr;
+  a.Hd = (const double*)c.dev.Hd.ptr;
+  a.b = (const double*)c.dev.b.ptr;
+  a.Minv = (double*)c.dev.Minv.ptr;
+  a.x = (double*)c.dev.dx.ptr;
+  a.r = (double*)c.dev.r.ptr;
+  a.d = (double*)c.dev.d.ptr;
+  a.q = (double*)c.dev.q.ptr;
+  a.part = (double*)c.dev.part.ptr;
+  a.result = (double*)c.dev.result.ptr;
+  a.lambda = lambda;
+  a.tol = (c.pcg_residual > 0.0 && c.pcg_residual > 1e-6) ? c.pcg_residual : 1e-6;
+  a.maxit = 6 * c.nv;
+  void* args[] = {&a};
+  PG_CUDA(cudaLaunchCooperativeKernel((void*)pg_pcg_kernel, dim3(c.pcg_grid), dim3(256), args, 0, c.st));
+  c.launches++;
+  double res[4];
+  PG_CUDA(cudaMemcpyAsync(res, c.dev.result.ptr, sizeof(res), cudaMemcpyDeviceToHost, c.st));
+  PG_CUDA(cudaStreamSynchronize(c.st));
+  c.cg_iters += (int)res[0];
+  c.pcg_residual = 0.5 * res[1];
+  *scale = res[2];
+  *ok = res[3] == 0.0;
+  return 0;
+}
+
+// OptimizationAlgorithmLevenberg::solve(iteration): returns 1 OK / 0 Terminate / <0 error code
+static int pg_lm_solve(PgCtx& c, int iteration, double& lambda, double& ni) {
+  int rc;
+  double cur, plain, maxdiag = 0;
+  if ((rc = pg_errors(c, (const double*)c.dev.x.ptr, &cur, &plain, nullptr))) return -rc;
+  if ((rc = pg_build(c, iteration == 0 ? &maxdiag : nullptr))) return -rc;
+  if (iteration == 0) {
+    lambda = 1e-5 * maxdiag;  // computeLambdaInit: tau * max diag(H)
+    ni = 2;
+  }
+  double rho = 0;
+  int qmax = 0;
+  do {
+    double scale;
+    bool ok2;
+    if ((rc = pg_pcg(c, lambda, &scale, &ok2))) return -rc;
+    pg_update_kernel<<<(c.nv + 127) / 128, 128, 0, c.st>>>(c.nv, (const double*)c.dev.x.ptr, (const double*)c.dev.dx.ptr,
+                                                           (const uint8_t*)c.dev.fixed.ptr, (double*)c.dev.xtrial.ptr);
+    if (cudaGetLastError() != cudaSuccess) return -RGBDSLAM_B200_ERR_CUDA;
+    c.launches++;
+    double temp;
+    if ((rc = pg_errors(c, (const double*)c.dev.xtrial.ptr, &temp, &plain, nullptr))) return -rc;
+    if (!ok2) temp = DBL_MAX;
+    rho = (cur - temp) / (scale + 1e-3);
+    if (rho > 0 && std::isfinite(temp)) {
+      double alpha = 1. - std::pow(2 * rho - 1, 3);
+      alpha = std::fmin(alpha, 2. / 3.);
+      lambda *= std::fmax(1. / 3., alpha);
+      ni = 2;
+      cur = temp;
+      std::swap(c.dev.x.ptr, c.dev.xtrial.ptr);  // accept (discardTop)
+      std::swap(c.dev.x.cap, c.dev.xtrial.cap);
+    } else {
+      lambda *= ni;  // reject (pop)
+      ni *= 2;
+      if (!std::isfinite(lambda)) break;
+    }
+    qmax++;
+  } while (rho < 0 && qmax < 10);
+  if (qmax == 10 || rho == 0) return 0;
+  return 1;
+}
+
+static int pg_optimize(PgCtx& c, int iterations, int* done) {  // SparseOptimizer::optimize(iterations)
+  double lambda = 0, ni = 2;
+  int cj = 0;
+  for (int i = 0; i < iterations; i++) {
+    const int r = pg_lm_solve(c, i, lambda, ni);
+    if (r < 0) return -r;
+    cj++;
+    if (r == 0) break;
+  }
+  *done = cj;
+  return 0;
+}
+
+int posegraph_optimize(int nv, double* poses, const uint8_t* fixed, int ne, const int32_t* ij, const double* meas,
+                       const double* info, double stop, double huber_delta, double* chi2_out, int* iters_out,
+                       int* cg_iters_out, double* per_edge_chi2, bool optimize) {
+  State& s = g_state;
+  PgCtx c;
+  c.nv = nv;
+  c.ne = ne;
+  c.delta = huber_delta;
+  c.st = s.stream;
+  // CSR of incident edges (edge order => deterministic sums)
+  std::vector<int> off(nv + 1, 0), inc(2 * (size_t)ne);
+  for (int k = 0; k < ne; k++) {
+    if (ij[2 * k] < 0 || ij[2 * k] >= nv || ij[2 * k + 1] < 0 || ij[2 * k + 1] >= nv) {
+      set_error("posegraph: edge vertex index out of range");
+      return RGBDSLAM_B200_ERR_ARG;
+    }
+    off[ij[2 * k] + 1]++;
+    off[ij[2 * k + 1] + 1]++;
+  }
+  for (int v = 0; v < nv; v++) off[v + 1] += off[v];
+  {
+    std::vector<int> cur(off.begin(), off.end() - 1);
+    for (int k = 0; k < ne; k++) {
+      inc[cur[ij[2 * k]]++] = (k << 1) | 0;
+      inc[cur[ij[2 * k + 1]]++] = (k << 1) | 1;
+    }
+  }
+  int rc;
+  PgDevice& d = c.dev;
+  const size_t nv_ = (size_t)(nv > 0 ? nv : 1), ne_ = (size_t)(ne > 0 ? ne : 1);
+  const int chi_blocks = (ne + 255) / 256 + 1, max_blocks = (nv + 2) / 3 + 1;
+  if ((rc = d.x.ensure(56 * nv_)) || (rc = d.xtrial.ensure(56 * nv_)) || (rc = d.meas.ensure(56 * ne_)) ||
+      (rc = d.info.ensure(288 * ne_)) || (rc = d.ij.ensure(8 * ne_)) || (rc = d.fixed.ensure(nv_)) ||
+      (rc = d.off.ensure(4 * (nv_ + 1))) || (rc = d.inc.ensure(8 * ne_)) || (rc = d.blk.ensure(8 * kEdgeBlk * ne_)) ||
+      (rc = d.Hd.ensure(288 * nv_)) || (rc = d.b.ensure(48 * nv_)) || (rc = d.Minv.ensure(288 * nv_)) ||
+      (rc = d.dx.ensure(48 * nv_)) || (rc = d.r.ensure(48 * nv_)) || (rc = d.d.ensure(48 * nv_)) ||
+      (rc = d.q.ensure(48 * nv_)) || (rc = d.result.ensure(64)) || (rc = d.chipart.ensure(16 * (size_t)chi_blocks)) ||
+      (rc = d.maxpart.ensure(8 * (size_t)max_blocks)) || (rc = d.per_edge.ensure(8 * ne_)))
+    return rc;
+  // cooperative grid: all co-resident blocks of the PCG kernel
+  int per_sm = 0;
+  PG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pg_pcg_kernel, 256, 0));
+  if (per_sm < 1) {
+    set_error("posegraph: PCG kernel cannot be made resident");
+    return RGBDSLAM_B200_ERR_CUDA;
+  }
+  c.pcg_grid = s.sm_count * (per_sm > 2 ? 2 : per_sm);
+  if ((rc = d.part.ensure(16 * (size_t)c.pcg_grid))) return rc;
+  cudaStream_t st = c.st;
+  PG_CUDA(cudaMemcpyAsync(d.x.ptr, poses, 56 * (size_t)nv, cudaMemcpyHostToDevice, st));
+  PG_CUDA(cudaMemcpyAsync(d.fixed.ptr, fixed, (size_t)nv, cudaMemcpyHostToDevice, st));
+  PG_CUDA(cudaMemcpyAsync(d.off.ptr, off.data(), 4 * (size_t)(nv + 1), cudaMemcpyHostToDevice, st));
+  if (ne > 0) {
+    PG_CUDA(cudaMemcpyAsync(d.meas.ptr, meas, 56 * (size_t)ne, cudaMemcpyHostToDevice, st));
+    PG_CUDA(cudaMemcpyAsync(d.info.ptr, info, 288 * (size_t)ne, cudaMemcpyHostToDevice, st));
+    PG_CUDA(cudaMemcpyAsync(d.ij.ptr, ij, 8 * (size_t)ne, cudaMemcpyHostToDevice, st));
+    PG_CUDA(cudaMemcpyAsync(d.inc.ptr, inc.data(), 8 * (size_t)ne, cudaMemcpyHostToDevice, st));
+  }
+  PG_CUDA(cudaStreamSynchronize(st));  // host vectors (off/inc) go out of scope safely
+
+  int it = 0;
+  double chi2 = DBL_MAX, robust = 0;
+  if (optimize) {
+    // graph_manager.cpp:998-1014
+    if (stop >= 1.0) {
+      const int step = (int)std::ceil(stop / 10);
+      do {
+        int done = 0;
+        if ((rc = pg_optimize(c, step, &done))) return rc;
+        it += done;
+      } while (it < stop && it > 0);
+      if ((rc = pg_errors(c, (const double*)d.x.ptr, &robust, &chi2, per_edge_chi2 ? (double*)d.per_edge.ptr : nullptr))) return rc;
+    } else {
+      double prev;
+      do {
+        prev = chi2;
+        int done = 0;
+        if ((rc = pg_optimize(c, 5, &done))) return rc;
+        it += done;
+        if ((rc = pg_errors(c, (const double*)d.x.ptr, &robust, &chi2, per_edge_chi2 ? (double*)d.per_edge.ptr : nullptr))) return rc;
+      } while (chi2 / prev < (1.0 - stop));
+    }
+    PG_CUDA(cudaMemcpyAsync(poses, d.x.ptr, 56 * (size_t)nv, cudaMemcpyDeviceToHost, st));
+  } else {
+    if ((rc = pg_errors(c, (const double*)d.x.ptr, &robust, &chi2, per_edge_chi2 ? (double*)d.per_edge.ptr : nullptr))) return rc;
+  }
+  if (per_edge_chi2 && ne > 0)
+    PG_CUDA(cudaMemcpyAsync(per_edge_chi2, d.per_edge.ptr, 8 * (size_t)ne, cudaMemcpyDeviceToHost, st));
+  PG_CUDA(cudaStreamSynchronize(st));
+  if (chi2_out) *chi2_out = chi2;
+  if (iters_out) *iters_out = it;
+  if (cg_iters_out) *cg_iters_out = c.cg_iters;
+  s.launches += c.launches;
+  return 0;
+}
+
+}  // namespace rb200

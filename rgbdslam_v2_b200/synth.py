@@ -84,3 +84,98 @@ def make_batch(npairs: int, n_kp: int = 1000, seed0: int = 0, **kw):
         id_newer=np.arange(npairs, dtype=np.int32) + 1, id_older=np.arange(npairs, dtype=np.int32),
         T_true=np.stack([p["T_true"] for p in pairs]), n_common=np.array([p["n_common"] for p in pairs]),
         pairs=pairs)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Pose graph (BASELINE config C5 / SURVEY 8d): poses on a smooth closed trajectory, odometry + loop edges.
+
+def _quat_mul(a, b):  # (x y z w)
+    ax, ay, az, aw = a[..., 0], a[..., 1], a[..., 2], a[..., 3]
+    bx, by, bz, bw = b[..., 0], b[..., 1], b[..., 2], b[..., 3]
+    return np.stack([aw * bx + ax * bw + ay * bz - az * by, aw * by - ax * bz + ay * bw + az * bx,
+                     aw * bz + ax * by - ay * bx + az * bw, aw * bw - ax * bx - ay * by - az * bz], -1)
+
+
+def _quat_conj(q):
+    return q * np.array([-1, -1, -1, 1.0])
+
+
+def _quat_rot(q, v):
+    qv = np.concatenate([v, np.zeros(v.shape[:-1] + (1,))], -1)
+    return _quat_mul(_quat_mul(q, qv), _quat_conj(q))[..., :3]
+
+
+def pose_compose(a, b):  # a * b, 7-vectors (t, q)
+    return np.concatenate([a[..., :3] + _quat_rot(a[..., 3:], b[..., :3]), _quat_mul(a[..., 3:], b[..., 3:])], -1)
+
+
+def pose_inverse(a):
+    qc = _quat_conj(a[..., 3:])
+    return np.concatenate([-_quat_rot(qc, a[..., :3]), qc], -1)
+
+
+def make_pose_graph(nv: int = 5000, ne: int = 30000, seed: int = 0, laps: float = 2.5, trans_noise: float = 0.01,
+                    rot_noise_deg: float = 0.5, outlier_frac: float = 0.0):
+    """Returns dict(gt [nv,7], init [nv,7], ij [ne,2], meas [ne,7], info [ne,36], fixed [nv]).
+    Edges: nv-1 odometry edges (i, i+1) + loop/neighbour edges between poses that are close on the trajectory
+    (different laps or small index distance).  measurement = GT relative pose (+) noise; information =
+    I * n_inl/rmse^2 with n_inl ~ U[20,300], rmse ~ U[0.5,2] (the edge weights node.cpp:1335 produces).
+    init = odometry chain (vertex estimate = v1 * T, graph_manager.cpp:858); vertex 0 fixed (pose_relative_to=first)."""
+    rng = np.random.default_rng(seed)
+    s = np.linspace(0, 2 * np.pi * laps, nv)
+    pos = np.stack([3 * np.cos(s), 2 * np.sin(2 * s) * 0.5 + 2 * np.sin(s), 0.3 * np.sin(3 * s)], 1)
+    yaw = s + np.pi / 2
+    q = np.stack([np.zeros(nv), np.zeros(nv), np.sin(yaw / 2), np.cos(yaw / 2)], 1)
+    tilt = 0.1 * np.sin(5 * s)
+    qt = np.stack([np.sin(tilt / 2), np.zeros(nv), np.zeros(nv), np.cos(tilt / 2)], 1)
+    gt = np.concatenate([pos, _quat_mul(q, qt)], 1)
+    period = int(round(nv / laps))
+    ii = [np.arange(nv - 1)]
+    jj = [np.arange(1, nv)]
+    n_extra = ne - (nv - 1)
+    a = rng.integers(0, nv, size=4 * n_extra)
+    kind = rng.random(4 * n_extra)
+    lap_jump = rng.integers(1, int(np.ceil(laps)) + 1, size=4 * n_extra) * period
+    near = rng.integers(2, 12, size=4 * n_extra)
+    wob = rng.integers(-15, 16, size=4 * n_extra)
+    b = np.where(kind < 0.5, a + near, a + lap_jump + wob)
+    ok = (b < nv) & (b > a)
+    a, b = a[ok][:n_extra], b[ok][:n_extra]
+    assert len(a) == n_extra, "not enough loop candidates"
+    ii.append(a); jj.append(b)
+    ij = np.stack([np.concatenate(ii), np.concatenate(jj)], 1).astype(np.int32)
+    rel = pose_compose(pose_inverse(gt[ij[:, 0]]), gt[ij[:, 1]])
+    # noise (+): right-multiply a small random transform
+    ax = rng.normal(size=(ne, 3)); ax /= np.linalg.norm(ax, axis=1, keepdims=True)
+    ang = np.deg2rad(rot_noise_deg) * rng.normal(size=ne)
+    dq = np.concatenate([ax * np.sin(ang / 2)[:, None], np.cos(ang / 2)[:, None]], 1)
+    dt = rng.normal(size=(ne, 3)) * trans_noise
+    n_out = int(outlier_frac * n_extra)
+    if n_out:
+        idx = (nv - 1) + rng.permutation(n_extra)[:n_out]
+        dt[idx] += rng.normal(size=(n_out, 3)) * 1.0
+    meas = pose_compose(rel, np.concatenate([dt, dq], 1))
+    n_inl = rng.uniform(20, 300, ne); rmse = rng.uniform(0.5, 2.0, ne)
+    info = np.zeros((ne, 36)); info[:, ::7] = (n_inl / rmse ** 2)[:, None]
+    init = np.zeros((nv, 7)); init[0] = gt[0]
+    for k in range(nv - 1):
+        init[k + 1] = pose_compose(init[k], meas[k])
+    fixed = np.zeros(nv, np.uint8); fixed[0] = 1
+    return dict(gt=gt, init=init, ij=ij, meas=np.ascontiguousarray(meas), info=info, fixed=fixed)
+
+
+def ate_rmse(est_xyz: np.ndarray, gt_xyz: np.ndarray) -> float:
+    """Absolute trajectory error after Horn alignment without scale -- port of
+    rgbd_benchmark/evaluate_ate_module.pyx:35-55 (align) and :179-203 (rmse of the translational error)."""
+    model, data = est_xyz.T, gt_xyz.T
+    mz = model - model.mean(1, keepdims=True)
+    dz = data - data.mean(1, keepdims=True)
+    Wm = mz @ dz.T  # sum of outer(model, data)
+    U, d, Vh = np.linalg.svd(Wm.T)
+    S = np.eye(3)
+    if np.linalg.det(U) * np.linalg.det(Vh) < 0:
+        S[2, 2] = -1
+    rot = U @ S @ Vh
+    trans = data.mean(1, keepdims=True) - rot @ model.mean(1, keepdims=True)
+    err = rot @ model + trans - data
+    return float(np.sqrt((err * err).sum(0).mean()))
