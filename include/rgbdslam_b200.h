@@ -180,6 +180,40 @@ int rgbdslam_b200_match_pairs_host(const uint8_t* desc_newer, const float* xyz_n
  * and of the whole device part of the last match_pairs* call. */
 int rgbdslam_b200_last_timing(float* hamming_ms, float* total_device_ms);
 
+/* ---- Node construction from images -------------------------------------------
+ * The reference builds one detector / extractor pair and shares it between all Node constructors
+ * (openni_listener.cpp:130-132); the detector carries the adaptive FAST threshold of every grid cell across
+ * frames (feature_adjuster.cpp:131-150, .h:17).  A detector handle holds exactly that state. */
+/* == createDetector("ORB") (features.cpp:63-113): thresholds start at 20 (features.cpp:92). */
+int rgbdslam_b200_detector_create(uint64_t* detector);
+int rgbdslam_b200_detector_destroy(uint64_t detector);
+/* read (set = 0) or overwrite (set = 1) the 16 per-cell thresholds (cell = col + row * grid). */
+int rgbdslam_b200_detector_thresholds(uint64_t detector, double* thresholds16, int set);
+
+/* == detector->detect(gray, keypoints, mask) (node.cpp:160): VideoGridAdaptedFeatureDetector
+ * (feature_adjuster.cpp:286-317) over VideoDynamicAdaptedFeatureDetector (:185-224) over
+ * cv::ORB::create(10000, 1.2, 8, 15, 0, 2, HARRIS_SCORE, 31, int(thresh)) (:94).  gray/mask: w*h bytes (mask may be
+ * NULL).  Output order: cell-major, |response| descending inside a cell (the reference's nth_element order is
+ * unspecified).  *n_out = number found; at most `capacity` are written. */
+int rgbdslam_b200_orb_detect(uint64_t detector, const uint8_t* gray, const uint8_t* mask, int w, int h,
+                             rgbdslam_b200_keypoint* kp_out, int capacity, int* n_out);
+
+/* == extractor->compute(gray, keypoints, descriptors) (node.cpp:202) with cv::ORB::create() defaults
+ * (features.cpp:117-119): keypoints closer than 31 px (cvRound'ed) to the border are dropped, the rest is stably
+ * re-ordered by octave; kp_out (n_in entries) receives the surviving keypoints, desc_out n_out x 32 bytes. */
+int rgbdslam_b200_orb_compute(const uint8_t* gray, int w, int h, const rgbdslam_b200_keypoint* kp_in, int n_in,
+                              rgbdslam_b200_keypoint* kp_out, uint8_t* desc_out, int* n_out);
+
+/* == Node::Node(visual, depth, detection_mask, cam_info, header, detector, extractor) (node.cpp:101-240) for nframes
+ * frames IN ORDER (the detector state makes frames sequentially dependent): detect -> removeDepthless (:186) ->
+ * retainBest(max_keypoints) (:187-191) -> compute (:202) -> projectTo3D (:210).  gray / mask: nframes*w*h bytes,
+ * depth: nframes*w*h floats (metres, NaN = invalid), K4 = fx, fy, cx, cy.  Feature order inside a node:
+ * (octave, response descending, cell, y, x). */
+int rgbdslam_b200_nodes_create(uint64_t detector, int nframes, const uint8_t* gray, const float* depth, const uint8_t* mask,
+                               int w, int h, const float* K4, const int32_t* ids, uint64_t* node_handles, int32_t* n_features);
+/* feature_locations_2d_ (node.h:167) of a node built by nodes_create. */
+int rgbdslam_b200_node_download_keypoints(uint64_t node_handle, rgbdslam_b200_keypoint* kp_out);
+
 /* ---- pose-graph solve --------------------------------------------------------
  * == GraphManager::optimizeGraph(double iter, bool nonthreaded) -> optimizeGraphImpl
  * (src/graph_manager.cpp:900-1066) on the optimizer createOptimizer builds (:107-201):

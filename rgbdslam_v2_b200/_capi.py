@@ -115,6 +115,13 @@ def load_library(path: str | Path | None = None) -> C.CDLL:
     lib.rgbdslam_b200_match_pairs.argtypes = [vp, vp, C.c_int, u64, i64, vp, vp, vp]
     lib.rgbdslam_b200_match_pairs_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, u64, i64, vp, vp, vp]
     lib.rgbdslam_b200_set_hamming_path.argtypes = [C.c_int]
+    lib.rgbdslam_b200_detector_create.argtypes = [C.POINTER(u64)]
+    lib.rgbdslam_b200_detector_destroy.argtypes = [u64]
+    lib.rgbdslam_b200_detector_thresholds.argtypes = [u64, vp, C.c_int]
+    lib.rgbdslam_b200_orb_detect.argtypes = [u64, vp, vp, C.c_int, C.c_int, vp, C.c_int, C.POINTER(C.c_int)]
+    lib.rgbdslam_b200_orb_compute.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int, vp, vp, C.POINTER(C.c_int)]
+    lib.rgbdslam_b200_nodes_create.argtypes = [u64, C.c_int, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp]
+    lib.rgbdslam_b200_node_download_keypoints.argtypes = [u64, vp]
     lib.rgbdslam_b200_posegraph_optimize.argtypes = [C.c_int, vp, vp, C.c_int, vp, vp, vp, C.c_double, C.c_double,
                                                      C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.rgbdslam_b200_posegraph_chi2.argtypes = [C.c_int, vp, C.c_int, vp, vp, vp, C.c_double, C.POINTER(C.c_double), vp]
@@ -254,6 +261,59 @@ class Frontend:
             _ptr(desc_newer), _ptr(xyz_newer), _ptr(n_newer), _ptr(desc_older), _ptr(xyz_older), _ptr(n_older),
             _ptr(idn), _ptr(ido), npairs, seed, first_pair_index, _ptr(res), _ptr(allm), _ptr(inl)))
         return res, allm, inl
+
+    # -- Node construction from images (node.cpp:101-240) -------------------------------
+    def detector_create(self) -> int:
+        h = C.c_uint64()
+        self._check(self.lib.rgbdslam_b200_detector_create(C.byref(h)))
+        return h.value
+
+    def detector_destroy(self, det: int):
+        self._check(self.lib.rgbdslam_b200_detector_destroy(det))
+
+    def detector_thresholds(self, det: int, values=None) -> np.ndarray:
+        t = np.zeros(16, np.float64) if values is None else np.ascontiguousarray(values, np.float64)
+        self._check(self.lib.rgbdslam_b200_detector_thresholds(det, _ptr(t), 0 if values is None else 1))
+        return t
+
+    def orb_detect(self, det: int, gray: np.ndarray, mask: np.ndarray | None, capacity: int = 4096):
+        gray = np.ascontiguousarray(gray, np.uint8)
+        mask = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+        out = np.zeros(capacity, KEYPOINT_DTYPE)
+        n = C.c_int()
+        self._check(self.lib.rgbdslam_b200_orb_detect(det, _ptr(gray), _ptr(mask), gray.shape[1], gray.shape[0], _ptr(out),
+                                                      capacity, C.byref(n)))
+        return out[:min(n.value, capacity)]
+
+    def orb_compute(self, gray: np.ndarray, kps: np.ndarray):
+        gray = np.ascontiguousarray(gray, np.uint8)
+        kps = np.ascontiguousarray(kps, KEYPOINT_DTYPE)
+        out = np.zeros(max(len(kps), 1), KEYPOINT_DTYPE)
+        desc = np.zeros((max(len(kps), 1), 32), np.uint8)
+        n = C.c_int()
+        self._check(self.lib.rgbdslam_b200_orb_compute(_ptr(gray), gray.shape[1], gray.shape[0], _ptr(kps), len(kps), _ptr(out),
+                                                       _ptr(desc), C.byref(n)))
+        return out[:n.value], desc[:n.value]
+
+    def nodes_create(self, det: int, gray: np.ndarray, depth: np.ndarray, mask: np.ndarray | None, K4, ids=None):
+        """gray [F,H,W] u8, depth [F,H,W] f32, mask [F,H,W] u8 or None -> (handles, n_features)."""
+        gray = np.ascontiguousarray(gray, np.uint8)
+        depth = np.ascontiguousarray(depth, np.float32)
+        mask = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+        F, H, W = gray.shape
+        K4 = np.ascontiguousarray(K4, np.float32)
+        ids = None if ids is None else np.ascontiguousarray(ids, np.int32)
+        handles = np.zeros(F, np.uint64)
+        nf = np.zeros(F, np.int32)
+        self._check(self.lib.rgbdslam_b200_nodes_create(det, F, _ptr(gray), _ptr(depth), _ptr(mask), W, H, _ptr(K4), _ptr(ids),
+                                                        _ptr(handles), _ptr(nf)))
+        self._nodes += [int(h) for h in handles]
+        return [int(h) for h in handles], nf
+
+    def node_keypoints(self, h: int) -> np.ndarray:
+        out = np.zeros(self.node_num_features(h), KEYPOINT_DTYPE)
+        self._check(self.lib.rgbdslam_b200_node_download_keypoints(h, _ptr(out)))
+        return out
 
     # -- GraphManager::optimizeGraph ----------------------------------------------
     def optimize_graph(self, poses, fixed, ij, meas, info, stop: float = 0.01, huber_delta: float = 1.0):

@@ -120,6 +120,8 @@ static int expand_nodes(const std::vector<ExpandJob>& jobs) {
   return 0;
 }
 
+int expand_nodes_public(const std::vector<ExpandJob>& jobs) { return expand_nodes(jobs); }
+
 // Hamming stage dispatcher (counts the launch).  h_pairs carries the int8 operand pointers when the
 // tensor-core path is selected.
 static int launch_hamming(const PairDesc* d_pairs, const PairDesc* h_pairs, int npairs, int max_nq, int2* best,
@@ -572,6 +574,7 @@ int rgbdslam_b200_node_destroy(uint64_t node_handle) {
   if (nd->desc) cudaFree(nd->desc);
   if (nd->xyz) cudaFree(nd->xyz);
   if (nd->desc_i8) cudaFree(nd->desc_i8);
+  if (nd->kp) cudaFree(nd->kp);
   delete nd;
   return 0;
 }

@@ -4,6 +4,7 @@
 
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "common.cuh"
 
@@ -30,6 +31,7 @@ struct NodeDev {
   int32_t n = 0;
   uint8_t* desc = nullptr;    // n x 32 B ORB descriptors
   float4* xyz = nullptr;      // n x (x,y,z,1)
+  rgbdslam_b200_keypoint* kp = nullptr;  // n x cv::KeyPoint (only for nodes built from images)
   int8_t* desc_i8 = nullptr;  // n_pad x 256 B  +-1 expansion for the tensor-core Hamming path (lazily built)
   int32_t n_pad = 0;
 };
@@ -67,5 +69,6 @@ extern State g_state;
 void set_error(const std::string& s);
 int cuda_fail(cudaError_t e, const char* what);
 int check_inited();
+int expand_nodes_public(const std::vector<ExpandJob>& jobs);  // +-1 int8 expansion (api.cu)
 
 }  // namespace rb200

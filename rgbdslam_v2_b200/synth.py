@@ -179,3 +179,78 @@ def ate_rmse(est_xyz: np.ndarray, gt_xyz: np.ndarray) -> float:
     trans = data.mean(1, keepdims=True) - rot @ model.mean(1, keepdims=True)
     err = rot @ model + trans - data
     return float(np.sqrt((err * err).sum(0).mean()))
+
+
+# ---------------------------------------------------------------------------------------------------
+# Rendered RGB-D frames: a textured box room seen by a pinhole camera (cv2 only used for remap/blur).
+
+_TEX = {}
+
+
+def _texture(seed: int, size: int = 1024) -> np.ndarray:
+    """Band-limited noise + random rectangles: FAST fires thousands of times per frame."""
+    key = (seed, size)
+    if key not in _TEX:
+        import cv2
+        rng = np.random.default_rng(seed)
+        t = rng.random((size, size)).astype(np.float32)
+        t = cv2.GaussianBlur(t, (0, 0), 1.6)
+        t = (t - t.min()) / (t.max() - t.min())
+        img = (t * 255).astype(np.float32)
+        for _ in range(size // 3):
+            x, y = rng.integers(0, size - 8, 2)
+            w, h = rng.integers(6, 70, 2)
+            img[y:y + h, x:x + w] += rng.integers(-90, 90)
+        _TEX[key] = np.clip(img, 0, 255).astype(np.uint8)
+    return _TEX[key]
+
+
+def render_frame(pose_wc: np.ndarray, tex_seed: int = 7, nan_frac: float = 0.03, seed: int = 0, depth_noise: float = 0.0):
+    """pose_wc: 4x4 camera-to-world.  Scene: back wall z=4, floor y=1.3, left wall x=-3, right wall x=3 (world frame).
+    Returns gray u8 [480,640], depth f32 [480,640] (metres, NaN holes)."""
+    import cv2
+    rng = np.random.default_rng(seed)
+    v, u = np.mgrid[0:H, 0:W].astype(np.float64)
+    rays_c = np.stack([(u - CX) / FX, (v - CY) / FY, np.ones_like(u)], -1)
+    R, t = pose_wc[:3, :3], pose_wc[:3, 3]
+    rays_w = rays_c @ R.T
+    planes = [((0, 0, 1.0), 4.0, 0), ((0, 1.0, 0), 1.3, 1), ((-1.0, 0, 0), 3.0, 2), ((1.0, 0, 0), 3.0, 3)]  # n.x = d
+    best = np.full((H, W), np.inf)
+    tu = np.zeros((H, W)); tv = np.zeros((H, W)); tid = np.zeros((H, W), int)
+    for n, d, pid in planes:
+        n = np.array(n)
+        denom = rays_w @ n
+        lam = (d - t @ n) / np.where(np.abs(denom) < 1e-9, 1e-9, denom)
+        ok = (lam > 0.3) & (lam < best)
+        P = t + rays_w * lam[..., None]
+        if pid == 0: a, b = P[..., 0], P[..., 1]
+        elif pid == 1: a, b = P[..., 0], P[..., 2]
+        else: a, b = P[..., 2], P[..., 1]
+        best = np.where(ok, lam, best); tu = np.where(ok, a, tu); tv = np.where(ok, b, tv); tid = np.where(ok, pid, tid)
+    tex = _texture(tex_seed)
+    S = tex.shape[0]
+    mapx = ((tu * 110.0 + 37.0 * tid + 4000.0) % (S - 1)).astype(np.float32)
+    mapy = ((tv * 110.0 + 91.0 * tid + 4000.0) % (S - 1)).astype(np.float32)
+    gray = cv2.remap(tex, mapx, mapy, cv2.INTER_LINEAR)
+    depth = best.astype(np.float32)  # rays_c has z = 1 -> lambda is the camera-frame depth
+    depth[~np.isfinite(depth)] = np.nan
+    if depth_noise > 0:
+        depth = (depth + rng.normal(size=depth.shape) * depth_noise * depth * depth).astype(np.float32)
+    holes = rng.random((H // 8, W // 8)) < nan_frac
+    depth[np.kron(holes, np.ones((8, 8), bool))] = np.nan
+    depth[rng.random(depth.shape) < nan_frac / 3] = np.nan
+    return np.ascontiguousarray(gray), np.ascontiguousarray(depth)
+
+
+def trajectory(n: int, seed: int = 0) -> np.ndarray:
+    """Smooth camera-to-world poses [n,4,4]: Lissajous translation + yaw/pitch sweep that revisits places."""
+    s = np.linspace(0, 2 * np.pi, n, endpoint=False)
+    out = np.zeros((n, 4, 4))
+    for k, a in enumerate(s):
+        yaw = 0.45 * np.sin(a); pitch = 0.12 * np.sin(2 * a + 0.3)
+        Ry = np.array([[np.cos(yaw), 0, np.sin(yaw)], [0, 1, 0], [-np.sin(yaw), 0, np.cos(yaw)]])
+        Rx = np.array([[1, 0, 0], [0, np.cos(pitch), -np.sin(pitch)], [0, np.sin(pitch), np.cos(pitch)]])
+        out[k, :3, :3] = Ry @ Rx
+        out[k, :3, 3] = [0.9 * np.sin(a), 0.25 * np.sin(2 * a), 0.6 * np.cos(a) - 0.2]
+        out[k, 3, 3] = 1
+    return out

@@ -1,0 +1,143 @@
+"""GPU parity tests of the Node-constructor path (ORB detect / compute / back-projection) against OpenCV itself
+(cv2) + the reference's glue restated in oracle/orb_oracle.py."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def fe(built):
+    from rgbdslam_v2_b200 import Frontend
+    from rgbdslam_v2_b200._capi import default_params
+    p = default_params()
+    p.depth_cov_z0 = 2.0
+    p.max_keypoints = 600
+    f = Frontend(0, p)
+    yield f
+    f.close()
+
+
+@pytest.fixture(scope="module")
+def frames():
+    from rgbdslam_v2_b200 import synth
+    poses = synth.trajectory(40)
+    out = []
+    for k in (0, 1, 2, 9):
+        g, d = synth.render_frame(poses[k], seed=k)
+        out.append((g, d))
+    return out
+
+
+def _reinit(fe, **kw):
+    import ctypes as C
+    from rgbdslam_v2_b200._capi import default_params
+    p = default_params()
+    p.depth_cov_z0 = 2.0
+    for k, v in kw.items():
+        setattr(p, k, v)
+    fe.params = p
+    fe._check(fe.lib.rgbdslam_b200_init(0, C.byref(p)))
+
+
+def _canon(kp):
+    return np.sort(kp, order=["octave", "y", "x"])
+
+
+def test_orb_compute_bit_exact_vs_cv2(fe, frames):
+    """extractor->compute(): identical keypoint filtering/ordering and bit-identical 256-bit descriptors."""
+    import cv2
+    from oracle import orb_oracle
+    for gray, _ in frames[:2]:
+        det = cv2.ORB_create(10000, 1.2, 8, 15, 0, 2, 0, 31, 20)
+        kps = det.detect(gray, None)
+        rng = np.random.default_rng(0)
+        sel = rng.permutation(len(kps))[:1500]  # unordered input incl. all octaves and border cases
+        arr = np.zeros(len(sel), orb_oracle.KP_DTYPE)
+        for i, j in enumerate(sel):
+            k = kps[j]
+            arr[i] = (k.pt[0], k.pt[1], k.size, k.angle, k.response, k.octave, -1)
+        okp, odesc = orb_oracle.orb_compute(gray, arr)
+        gkp, gdesc = fe.orb_compute(gray, arr)
+        assert len(gkp) == len(okp) and len(okp) > 1000
+        assert gkp.tobytes() == okp.tobytes()
+        assert np.array_equal(gdesc, odesc)
+        assert set(np.unique(gkp["octave"])) == set(range(8))
+
+
+def test_orb_compute_edge_cases(fe, frames):
+    from oracle import orb_oracle
+    gray = frames[0][0]
+    arr = np.zeros(8, orb_oracle.KP_DTYPE)
+    xs = [30.4, 30.5, 30.6, 608.4, 608.5, 608.6, 320.0, 320.0]
+    ys = [100.0] * 6 + [30.5, 448.5]
+    for i in range(8):
+        arr[i] = (xs[i], ys[i], 31.0, 33.0 * i, 1.0, i % 8, -1)
+    okp, odesc = orb_oracle.orb_compute(gray, arr)
+    gkp, gdesc = fe.orb_compute(gray, arr)
+    assert gkp.tobytes() == okp.tobytes() and np.array_equal(gdesc, odesc)
+    e, d = fe.orb_compute(gray, arr[:0])
+    assert len(e) == 0
+
+
+def test_grid_detect_vs_cv2_over_a_sequence(fe, frames):
+    """detector->detect() incl. the per-cell adaptive thresholds carried across frames."""
+    from oracle import orb_oracle
+    _reinit(fe, max_keypoints=600)
+    det = fe.detector_create()
+    st = orb_oracle.DetectorState()
+    for gray, depth in frames:
+        mask = orb_oracle.depth_to_mask(depth)
+        orec = orb_oracle.grid_detect(gray, mask, st, max_keypoints=600)
+        okp = orb_oracle.records_to_array(orec)
+        gkp = fe.orb_detect(det, gray, mask)
+        assert len(gkp) == len(okp) and len(okp) > 300
+        assert _canon(gkp).tobytes() == _canon(okp).tobytes()  # same set, every field bit-exact
+        assert gkp.tobytes() == okp.tobytes()                  # and the documented canonical order
+        assert np.allclose(fe.detector_thresholds(det)[:9], st.thresh[:9], rtol=0, atol=0)
+    fe.detector_destroy(det)
+
+
+def test_nodes_create_vs_oracle(fe, frames, oracle_mod):
+    """Full Node constructor (node.cpp:101-240) for a batch of frames processed in order."""
+    from oracle import orb_oracle
+    from rgbdslam_v2_b200 import synth
+    _reinit(fe, max_keypoints=600)
+    det = fe.detector_create()
+    st = orb_oracle.DetectorState()
+    gray = np.stack([f[0] for f in frames]); depth = np.stack([f[1] for f in frames])
+    mask = np.stack([orb_oracle.depth_to_mask(f[1]) for f in frames])
+    K4 = (synth.FX, synth.FY, synth.CX, synth.CY)
+    handles, nf = fe.nodes_create(det, gray, depth, mask, K4, ids=[10, 11, 12, 13])
+    for i, h in enumerate(handles):
+        okp, odesc, oxyz = orb_oracle.node_construct(frames[i][0], frames[i][1], mask[i], K4, st, max_keypoints=600)
+        gkp = fe.node_keypoints(h)
+        gdesc, gxyz = fe.node_download(h)
+        assert nf[i] == len(okp) and 300 < len(okp) <= 600
+        assert gkp.tobytes() == okp.tobytes()
+        assert np.array_equal(gdesc, odesc)
+        assert np.array_equal(gxyz, oxyz)
+        assert not np.isnan(gxyz).any()
+    # nodes built from images feed the matcher like nodes built from features
+    res, allm, inl = fe.match_node_pairs([handles[1]], [handles[0]], seed=3)
+    assert res[0]["id1"] == 10 and res[0]["id2"] == 11 and res[0]["n_inliers"] > 50
+    fe.detector_destroy(det)
+
+
+def test_no_mask_and_other_parameters(fe, frames):
+    from oracle import orb_oracle
+    _reinit(fe, max_keypoints=1000)
+    det = fe.detector_create()
+    st = orb_oracle.DetectorState()
+    gray = frames[3][0]
+    orec = orb_oracle.grid_detect(gray, None, st, max_keypoints=1000)
+    gkp = fe.orb_detect(det, gray, None)
+    assert gkp.tobytes() == orb_oracle.records_to_array(orec).tobytes()
+    # a textureless frame: thresholds decay (x0.7, clamped at 2) exactly like the reference's adjuster
+    flat = np.full_like(gray, 128)
+    orec = orb_oracle.grid_detect(flat, None, st, max_keypoints=1000)
+    gkp = fe.orb_detect(det, flat, None)
+    assert len(gkp) == len(orec) == 0
+    assert np.array_equal(fe.detector_thresholds(det)[:9], np.array(st.thresh[:9]))
+    fe.detector_destroy(det)
+    _reinit(fe, max_keypoints=600)
