@@ -181,13 +181,28 @@ def run_ours(args, rank, local_rank, world):
     inl_np = out_inl.numpy().view(DMATCH_DTYPE).reshape(PAIRS_PER_GPU, mm)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
+    # the one exchange step of the multi-GPU path: all-gather of the edge records over NCCL
+    comm = None
+    all_edges = None
+    if world > 1:
+        uid = torch.from_numpy(fe.comm_unique_id() if rank == 0 else np.zeros(128, np.uint8)).cuda()
+        dist.broadcast(uid, 0)
+        comm = fe.comm_init(rank, world, uid.cpu().numpy())
+        all_edges = np.zeros(world * PAIRS_PER_GPU, PAIR_RESULT_DTYPE)
+
     def step_resident():
-        return fe.match_node_pairs(newer, older, seed=SEED, first_pair_index=first_pair, out=(res_np, None, None))
+        r = fe.match_node_pairs(newer, older, seed=SEED, first_pair_index=first_pair, out=(res_np, None, None))
+        if comm is not None:
+            fe.allgather_edges(comm, res_np, world, out=all_edges)
+        return r
 
     def step_e2e():
-        return fe.match_pairs_host(pin["desc_newer"], pin["xyz_newer"], b["n_newer"], pin["desc_older"], pin["xyz_older"],
-                                   b["n_older"], b["id_newer"], b["id_older"], seed=SEED, first_pair_index=first_pair,
-                                   out=(res_np, all_np, inl_np))
+        r = fe.match_pairs_host(pin["desc_newer"], pin["xyz_newer"], b["n_newer"], pin["desc_older"], pin["xyz_older"],
+                                b["n_older"], b["id_newer"], b["id_older"], seed=SEED, first_pair_index=first_pair,
+                                out=(res_np, all_np, inl_np))
+        if comm is not None:
+            fe.allgather_edges(comm, res_np, world, out=all_edges)
+        return r
 
     def barrier():
         torch.cuda.synchronize()
@@ -258,6 +273,8 @@ def run_ours(args, rank, local_rank, world):
             "config": {"workload": f"C2: {PAIRS_PER_GPU} frame pairs x {N_KP} ORB kp per GPU, Hamming BF match + 4-pt RANSAC "
                                    f"({prm.ransac_iterations} hypotheses, max_matches {prm.max_matches})",
                        "l2": "flushed (256 MiB memset) before every timed step", "pairs_per_gpu": PAIRS_PER_GPU,
+                       "exchange": "none (1 GPU)" if world == 1 else f"ncclAllGather of {world}x{PAIRS_PER_GPU} edge records (104 B) per step, inside the timed region",
+                       "edges_gathered": None if all_edges is None else int((all_edges["id1"] >= 0).sum()),
                        "valid_edges_rank0": n_valid, "wall_ms_per_step_incl_flush": 1e3 * wall_resident / args.steps},
             "roofline": {"bound": "hbm", "kernel": "hamming_match", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
@@ -282,6 +299,8 @@ def run_ours(args, rank, local_rank, world):
             agree = int(((ores["id1"] >= 0) == (res_np["id1"] >= 0)).sum())
             out["config"]["oracle_agreement_valid_flags"] = f"{agree}/{PAIRS_PER_GPU}"
         print(json.dumps(out), flush=True)
+    if comm is not None:
+        fe.comm_destroy(comm)
     fe.close()
     if world > 1:
         dist.destroy_process_group()

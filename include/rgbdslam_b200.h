@@ -148,6 +148,18 @@ int rgbdslam_b200_node_download(uint64_t node_handle, uint8_t* desc, float* xyz1
 /* == Node::~Node (node.cpp:371). */
 int rgbdslam_b200_node_destroy(uint64_t node_handle);
 
+/* ---- SIFT-128 float descriptors (feature_extractor_type SIFT / SURF / SIFTGPU) -----------
+ * Node with 128-d float descriptors.  squareroot_descriptor_space (RootSIFT, node.cpp:1557-1571) is applied when
+ * params.use_root_sift != 0 (node.cpp:233-239).  Such nodes are matched by rgbdslam_b200_match_pairs with the float
+ * branch of Node::featureMatching (node.cpp:610-667): 2-NN, ratio test against nn_distance_ratio, first-come
+ * uniqueness of trainIdx, distance = ratio.  The reference's approximate FLANN kd-tree search (4 trees, 16 checks,
+ * node.cpp:493-514,1573-1581) is replaced by an EXACT 2-NN: bf16 tensor-core score matrix, 4 best candidates per
+ * query re-ranked with exact fp32 distances. */
+int rgbdslam_b200_node_create_from_sift(int32_t id, const float* desc128, const float* xyz1, int n, uint64_t* node_handle);
+/* == Node::knnSearch(query, indices, dists, 2, ...) (node.cpp:1573-1581) with exact search: idx2 / dist2 hold 2
+ * entries per query row (squared L2 distances, as cv::flann returns them).  RootSIFT applied per params. */
+int rgbdslam_b200_knn2_l2(const float* q, int nq, const float* t, int nt, int32_t* idx2, float* dist2);
+
 /* ---- frame-pair matching --------------------------------------------------
  * == Node::matchNodePair (node.cpp:1305-1429) for npairs independent pairs
  * (the QtConcurrent::blockingMapped fan-out of graph_manager.cpp:548 as one
@@ -211,8 +223,26 @@ int rgbdslam_b200_orb_compute(const uint8_t* gray, int w, int h, const rgbdslam_
  * (octave, response descending, cell, y, x). */
 int rgbdslam_b200_nodes_create(uint64_t detector, int nframes, const uint8_t* gray, const float* depth, const uint8_t* mask,
                                int w, int h, const float* K4, const int32_t* ids, uint64_t* node_handles, int32_t* n_features);
+/* Inspection hook: FAST/NMS candidates {u16 x, u16 y, u8 level, u8 score, u16 0} and Harris responses (NaN = below
+ * the cell's final threshold) of grid cell `cell` in frame 0 of the last detect / nodes_create call. */
+int rgbdslam_b200_orb_debug_candidates(int cell, void* cand_out, float* resp_out, int capacity, int* n_out, int* thr_out);
+/* Inspection hook: one plane of frame 0 of the last call.  which: 0 cell image, 1 cell mask, 2 FAST score map
+ * (cell pyramids); 3 raw / 4 blurred extractor pyramid (cell ignored). */
+int rgbdslam_b200_orb_debug_plane(int which, int cell, int level, uint8_t* out, int capacity, int* w_out, int* h_out);
 /* feature_locations_2d_ (node.h:167) of a node built by nodes_create. */
 int rgbdslam_b200_node_download_keypoints(uint64_t node_handle, rgbdslam_b200_keypoint* kp_out);
+
+/* ---- multi-GPU exchange ---------------------------------------------------------
+ * Frame pairs are independent (the QtConcurrent fan-out of graph_manager.cpp:548 has no cross-pair state): ranks
+ * process disjoint pair ranges (first_pair_index keeps the random streams global) and all-gather the fixed-size edge
+ * records ONCE over NCCL before the replicated pose-graph solve.  One process per GPU; rank 0 obtains the unique id
+ * and distributes it to the other ranks out of band (e.g. torch.distributed / MPI / a file). */
+int rgbdslam_b200_comm_unique_id(uint8_t* id128);
+int rgbdslam_b200_comm_init(int rank, int world, const uint8_t* id128, uint64_t* comm_handle);
+int rgbdslam_b200_comm_destroy(uint64_t comm_handle);
+/* local: n_per_rank records of this rank (host); all: world * n_per_rank records, rank-major (host). */
+int rgbdslam_b200_allgather_edges(uint64_t comm_handle, const rgbdslam_b200_pair_result* local, int n_per_rank,
+                                  rgbdslam_b200_pair_result* all);
 
 /* ---- pose-graph solve --------------------------------------------------------
  * == GraphManager::optimizeGraph(double iter, bool nonthreaded) -> optimizeGraphImpl

@@ -591,3 +591,39 @@ int oracle_project_to_3d(const float* xy, int n, const float* depth, int w, int 
   }
   return cnt;
 }
+
+/* ------------------------------------------------------------------------ */
+/* matchNodePair (node.cpp:1305-1429) AFTER featureMatching, for callers that computed the sorted match list
+ * themselves (float-descriptor branch, restated in oracle/sift_oracle.py). */
+void oracle_match_node_pair_from_matches(const oracle_params* p, const float* xyz_newer, int id_newer, const float* xyz_older,
+                                         int id_older, const oracle_dmatch* matches, int n_all, uint64_t seed, uint64_t pair,
+                                         oracle_pair_result* res, oracle_dmatch* inlier_matches) {
+  static const float I4[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+  memset(res, 0, sizeof(*res));
+  res->id1 = res->id2 = -1;
+  memcpy(res->ransac_trafo, I4, sizeof(I4));
+  res->n_all_matches = n_all;
+  int found = 0;
+  if ((unsigned)n_all >= (unsigned)p->min_matches) {
+    uint8_t* inl = (uint8_t*)malloc((size_t)(n_all > 0 ? n_all : 1));
+    int n_inl, vi, ui, ri;
+    found = oracle_get_relative_transformation_to(p, xyz_newer, xyz_older, matches, n_all, seed, pair, res->ransac_trafo, &res->rmse,
+                                                  inl, &n_inl, &vi, &ui, &ri);
+    res->valid_iterations = vi;
+    res->used_identity = ui;
+    res->real_iterations = ri;
+    res->n_inliers = n_inl;
+    if (inlier_matches) {
+      int k = 0;
+      for (int i = 0; i < n_all; i++)
+        if (inl[i]) inlier_matches[k++] = matches[i];
+    }
+    free(inl);
+    if (found) {
+      res->info_scale = (double)((float)n_inl / (res->rmse * res->rmse));
+      res->id1 = id_older;
+      res->id2 = id_newer;
+    }
+  }
+  if (!found) res->id1 = res->id2 = -1;
+}

@@ -122,6 +122,14 @@ def load_library(path: str | Path | None = None) -> C.CDLL:
     lib.rgbdslam_b200_orb_compute.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int, vp, vp, C.POINTER(C.c_int)]
     lib.rgbdslam_b200_nodes_create.argtypes = [u64, C.c_int, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp]
     lib.rgbdslam_b200_node_download_keypoints.argtypes = [u64, vp]
+    lib.rgbdslam_b200_orb_debug_plane.argtypes = [C.c_int, C.c_int, C.c_int, vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.rgbdslam_b200_orb_debug_candidates.argtypes = [C.c_int, vp, vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.rgbdslam_b200_node_create_from_sift.argtypes = [C.c_int32, vp, vp, C.c_int, C.POINTER(u64)]
+    lib.rgbdslam_b200_knn2_l2.argtypes = [vp, C.c_int, vp, C.c_int, vp, vp]
+    lib.rgbdslam_b200_comm_unique_id.argtypes = [vp]
+    lib.rgbdslam_b200_comm_init.argtypes = [C.c_int, C.c_int, vp, C.POINTER(u64)]
+    lib.rgbdslam_b200_comm_destroy.argtypes = [u64]
+    lib.rgbdslam_b200_allgather_edges.argtypes = [u64, vp, C.c_int, vp]
     lib.rgbdslam_b200_posegraph_optimize.argtypes = [C.c_int, vp, vp, C.c_int, vp, vp, vp, C.c_double, C.c_double,
                                                      C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.rgbdslam_b200_posegraph_chi2.argtypes = [C.c_int, vp, C.c_int, vp, vp, vp, C.c_double, C.POINTER(C.c_double), vp]
@@ -212,6 +220,22 @@ class Frontend:
         self._check(self.lib.rgbdslam_b200_node_create_from_features(node_id, _ptr(desc), _ptr(xyz1), len(desc), C.byref(h)))
         self._nodes.append(h.value)
         return h.value
+
+    def node_from_sift(self, node_id: int, desc128: np.ndarray, xyz1: np.ndarray) -> int:
+        desc128 = np.ascontiguousarray(desc128, dtype=np.float32).reshape(-1, 128)
+        xyz1 = np.ascontiguousarray(xyz1, dtype=np.float32).reshape(-1, 4)
+        h = C.c_uint64()
+        self._check(self.lib.rgbdslam_b200_node_create_from_sift(node_id, _ptr(desc128), _ptr(xyz1), len(desc128), C.byref(h)))
+        self._nodes.append(h.value)
+        return h.value
+
+    def knn2_l2(self, q: np.ndarray, t: np.ndarray):
+        q = np.ascontiguousarray(q, np.float32).reshape(-1, 128)
+        t = np.ascontiguousarray(t, np.float32).reshape(-1, 128)
+        idx = np.zeros((len(q), 2), np.int32)
+        d = np.zeros((len(q), 2), np.float32)
+        self._check(self.lib.rgbdslam_b200_knn2_l2(_ptr(q), len(q), _ptr(t), len(t), _ptr(idx), _ptr(d)))
+        return idx, d
 
     def node_num_features(self, h: int) -> int:
         n = C.c_int()
@@ -310,9 +334,46 @@ class Frontend:
         self._nodes += [int(h) for h in handles]
         return [int(h) for h in handles], nf
 
+    def orb_debug_plane(self, which: int, cell: int, level: int) -> np.ndarray:
+        buf = np.zeros(1024 * 1024, np.uint8)
+        w, h = C.c_int(), C.c_int()
+        self._check(self.lib.rgbdslam_b200_orb_debug_plane(which, cell, level, _ptr(buf), buf.size, C.byref(w), C.byref(h)))
+        return buf[: w.value * h.value].reshape(h.value, w.value).copy()
+
+    def orb_debug_candidates(self, cell: int):
+        dt = np.dtype([("x", "<u2"), ("y", "<u2"), ("level", "u1"), ("score", "u1"), ("pad", "<u2")])
+        cand = np.zeros(12288, dt)
+        resp = np.zeros(12288, np.float32)
+        n, thr = C.c_int(), C.c_int()
+        self._check(self.lib.rgbdslam_b200_orb_debug_candidates(cell, _ptr(cand), _ptr(resp), 12288, C.byref(n), C.byref(thr)))
+        m = min(n.value, 12288)
+        return cand[:m], resp[:m], thr.value
+
     def node_keypoints(self, h: int) -> np.ndarray:
         out = np.zeros(self.node_num_features(h), KEYPOINT_DTYPE)
         self._check(self.lib.rgbdslam_b200_node_download_keypoints(h, _ptr(out)))
+        return out
+
+    # -- multi-GPU exchange -------------------------------------------------------------
+    def comm_unique_id(self) -> np.ndarray:
+        uid = np.zeros(128, np.uint8)
+        self._check(self.lib.rgbdslam_b200_comm_unique_id(_ptr(uid)))
+        return uid
+
+    def comm_init(self, rank: int, world: int, uid: np.ndarray) -> int:
+        h = C.c_uint64()
+        uid = np.ascontiguousarray(uid, np.uint8)
+        self._check(self.lib.rgbdslam_b200_comm_init(rank, world, _ptr(uid), C.byref(h)))
+        return h.value
+
+    def comm_destroy(self, comm: int):
+        self._check(self.lib.rgbdslam_b200_comm_destroy(comm))
+
+    def allgather_edges(self, comm: int, local: np.ndarray, world: int, out: np.ndarray | None = None) -> np.ndarray:
+        local = np.ascontiguousarray(local, PAIR_RESULT_DTYPE)
+        if out is None:
+            out = np.zeros(world * len(local), PAIR_RESULT_DTYPE)
+        self._check(self.lib.rgbdslam_b200_allgather_edges(comm, _ptr(local), len(local), _ptr(out)))
         return out
 
     # -- GraphManager::optimizeGraph ----------------------------------------------

@@ -11,6 +11,7 @@ CSRC = PKG_DIR / "csrc"
 LIB_NAME = "librgbdslam_b200.so"
 
 NVCC_FLAGS = [
+    "-ldl",
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",
 ]

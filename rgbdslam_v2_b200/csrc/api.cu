@@ -122,6 +122,65 @@ static int expand_nodes(const std::vector<ExpandJob>& jobs) {
 
 int expand_nodes_public(const std::vector<ExpandJob>& jobs) { return expand_nodes(jobs); }
 
+// RootSIFT + bf16 tiles + norms of a set of SIFT nodes.
+static int prepare_sift_nodes(const std::vector<SiftJob>& jobs) {
+  State& s = g_state;
+  if (jobs.empty()) return 0;
+  int rc;
+  if ((rc = s.d_jobs.ensure(sizeof(SiftJob) * jobs.size()))) return rc;
+  if ((rc = s.h_jobs.ensure(sizeof(SiftJob) * jobs.size()))) return rc;
+  int max_pad = 0;
+  for (const SiftJob& j : jobs) max_pad = j.n_pad > max_pad ? j.n_pad : max_pad;
+  memcpy(s.h_jobs.ptr, jobs.data(), sizeof(SiftJob) * jobs.size());
+  cudaError_t e = cudaMemcpyAsync(s.d_jobs.ptr, s.h_jobs.ptr, sizeof(SiftJob) * jobs.size(), cudaMemcpyHostToDevice, s.stream);
+  if (e != cudaSuccess) return cuda_fail(e, "upload sift jobs");
+  e = launch_sift_prepare((const SiftJob*)s.d_jobs.ptr, (int)jobs.size(), max_pad, s.params.use_root_sift ? 1 : 0, s.stream);
+  if (e != cudaSuccess) return cuda_fail(e, "sift_prepare kernel");
+  s.launches += 1;
+  return 0;
+}
+
+// SIFT matching stage: bf16 tensor-core scores -> exact fp32 2-NN among the 4 best -> (optionally) ratio/uniqueness.
+static int launch_sift_knn(const PairDesc* d_pairs, const PairDesc* h_pairs, int npairs, int max_nq, int stride, cudaStream_t st) {
+  State& s = g_state;
+  int rc;
+  if ((rc = s.d_top4.ensure(sizeof(int4) * (size_t)npairs * stride))) return rc;
+  if ((rc = s.d_knn.ensure(sizeof(float4) * (size_t)npairs * stride))) return rc;
+  std::vector<HamItem> items;
+  for (int p = 0; p < npairs; p++) {
+    const PairDesc& pd = h_pairs[p];
+    for (int m0 = 0; m0 < pd.nq; m0 += 128) {
+      HamItem it;
+      it.a = pd.q_i8 + (size_t)m0 * 256;
+      it.b = pd.t_i8;
+      it.out = reinterpret_cast<int2*>(reinterpret_cast<int4*>(s.d_top4.ptr) + (size_t)p * stride + m0);
+      it.nq_valid = pd.nq - m0 < 128 ? pd.nq - m0 : 128;
+      it.nsearch = pd.nt;  // FLANN searches every train row (no size-1 quirk on this path)
+      it.n_btiles = (pd.nt + 255) / 256;
+      it.pad_ = 0;
+      it.bnorm = pd.t_norm;
+      items.push_back(it);
+    }
+  }
+  cudaEventRecord(s.ev[3], st);
+  if (!items.empty()) {
+    if ((rc = s.d_items.ensure(sizeof(HamItem) * items.size()))) return rc;
+    if ((rc = s.h_items.ensure(sizeof(HamItem) * items.size()))) return rc;
+    memcpy(s.h_items.ptr, items.data(), sizeof(HamItem) * items.size());
+    cudaError_t e = cudaMemcpyAsync(s.d_items.ptr, s.h_items.ptr, sizeof(HamItem) * items.size(), cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return cuda_fail(e, "upload l2 items");
+    cudaEventRecord(s.ev[3], st);
+    e = launch_l2_tc((const HamItem*)s.d_items.ptr, (int)items.size(), s.sm_count, st);
+    if (e != cudaSuccess) return cuda_fail(e, "l2 tensor-core kernel");
+    s.launches += 1;
+  }
+  cudaEventRecord(s.ev[1], st);
+  cudaError_t e = launch_l2_refine(d_pairs, npairs, max_nq, (const int4*)s.d_top4.ptr, stride, (float4*)s.d_knn.ptr, st);
+  if (e != cudaSuccess) return cuda_fail(e, "l2 refine kernel");
+  s.launches += 1;
+  return 0;
+}
+
 // Hamming stage dispatcher (counts the launch).  h_pairs carries the int8 operand pointers when the
 // tensor-core path is selected.
 static int launch_hamming(const PairDesc* d_pairs, const PairDesc* h_pairs, int npairs, int max_nq, int2* best,
@@ -211,13 +270,28 @@ static int run_pairs(const std::vector<PairDesc>& h_pairs, uint64_t seed, int64_
   const PairDesc* d_pairs = (const PairDesc*)s.d_pairs.ptr;
 
   cudaEventRecord(s.ev[0], st);
-  // launch_hamming records ev[3] / ev[1] immediately around the kernel
-  if ((rc = launch_hamming(d_pairs, h_pairs.data(), npairs, max_nq, (int2*)s.d_best.ptr, stride, st))) return rc;
-  e = launch_select_matches(d_pairs, npairs, (const int2*)s.d_best.ptr, stride, seed, first_pair,
-                            (rgbdslam_b200_dmatch*)s.d_matches.ptr, (float4*)s.d_mfrom.ptr, (float4*)s.d_mto.ptr,
-                            (int32_t*)s.d_nall.ptr, max_nq, st);
-  if (e != cudaSuccess) return cuda_fail(e, "select_matches kernel");
-  s.launches += 1;
+  bool any_sift = false, any_orb = false;
+  for (const PairDesc& pd : h_pairs) (pd.q_f32 ? any_sift : any_orb) = true;
+  if (any_sift && any_orb) {
+    set_error("match_pairs: ORB and SIFT pairs cannot be mixed in one call");
+    return RGBDSLAM_B200_ERR_ARG;
+  }
+  if (any_sift) {
+    if ((rc = launch_sift_knn(d_pairs, h_pairs.data(), npairs, max_nq, stride, st))) return rc;
+    e = launch_select_sift(d_pairs, npairs, (const float4*)s.d_knn.ptr, stride, (float)s.params.nn_distance_ratio, maxM,
+                           (rgbdslam_b200_dmatch*)s.d_matches.ptr, (float4*)s.d_mfrom.ptr, (float4*)s.d_mto.ptr,
+                           (int32_t*)s.d_nall.ptr, st);
+    if (e != cudaSuccess) return cuda_fail(e, "select_sift kernel");
+    s.launches += 1;
+  } else {
+    // launch_hamming records ev[3] / ev[1] immediately around the kernel
+    if ((rc = launch_hamming(d_pairs, h_pairs.data(), npairs, max_nq, (int2*)s.d_best.ptr, stride, st))) return rc;
+    e = launch_select_matches(d_pairs, npairs, (const int2*)s.d_best.ptr, stride, seed, first_pair,
+                              (rgbdslam_b200_dmatch*)s.d_matches.ptr, (float4*)s.d_mfrom.ptr, (float4*)s.d_mto.ptr,
+                              (int32_t*)s.d_nall.ptr, max_nq, st);
+    if (e != cudaSuccess) return cuda_fail(e, "select_matches kernel");
+    s.launches += 1;
+  }
 
   if (s.params.depth_cov_z0 == 0.0 && s.z0 == 0.0) {
     // Emulate the function-static of depth_covariance (misc2.h:30-35): latch the z of the first
@@ -451,6 +525,7 @@ int rgbdslam_b200_brute_force_orb(const uint64_t* q, int nq, const uint64_t* t, 
   pd.nt = nt;
   pd.id_q = pd.id_t = 0;
   pd.q_i8 = pd.t_i8 = nullptr;
+  pd.q_f32 = pd.t_f32 = pd.t_norm = nullptr;
   if (s.hamming_path != 0) {
     if ((rc = s.d_i8_a.ensure(256 * (size_t)pad256(nq)))) return rc;
     if ((rc = s.d_i8_b.ensure(256 * (size_t)pad256(nt)))) return rc;
@@ -555,7 +630,7 @@ int rgbdslam_b200_node_download(uint64_t node_handle, uint8_t* desc, float* xyz1
   if (nd->n == 0) return 0;
   cudaStream_t st = g_state.stream;
   cudaError_t e = cudaSuccess;
-  if (desc) e = cudaMemcpyAsync(desc, nd->desc, 32 * (size_t)nd->n, cudaMemcpyDeviceToHost, st);
+  if (desc && nd->desc) e = cudaMemcpyAsync(desc, nd->desc, 32 * (size_t)nd->n, cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess && xyz1) e = cudaMemcpyAsync(xyz1, nd->xyz, 16 * (size_t)nd->n, cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) return cuda_fail(e, "node download");
@@ -575,6 +650,8 @@ int rgbdslam_b200_node_destroy(uint64_t node_handle) {
   if (nd->xyz) cudaFree(nd->xyz);
   if (nd->desc_i8) cudaFree(nd->desc_i8);
   if (nd->kp) cudaFree(nd->kp);
+  if (nd->desc_f32) cudaFree(nd->desc_f32);
+  if (nd->norms) cudaFree(nd->norms);
   delete nd;
   return 0;
 }
@@ -604,6 +681,13 @@ int rgbdslam_b200_match_pairs(const uint64_t* newer, const uint64_t* older, int 
     pairs[i].id_t = b->id;
     pairs[i].q_i8 = a->desc_i8;
     pairs[i].t_i8 = b->desc_i8;
+    pairs[i].q_f32 = a->desc_f32;
+    pairs[i].t_f32 = b->desc_f32;
+    pairs[i].t_norm = b->norms;
+    if ((a->desc_f32 != nullptr) != (b->desc_f32 != nullptr)) {
+      set_error("match_pairs: ORB node paired with a SIFT node");
+      return RGBDSLAM_B200_ERR_ARG;
+    }
   }
   return run_pairs(pairs, seed, first_pair_index, results, all_matches, inlier_matches);
 }
@@ -666,6 +750,7 @@ int rgbdslam_b200_match_pairs_host(const uint8_t* desc_newer, const float* xyz_n
   if (tc) jobs.reserve(2 * (size_t)npairs);
   for (int i = 0; i < npairs; i++) {
     pairs[i].q_i8 = pairs[i].t_i8 = nullptr;
+    pairs[i].q_f32 = pairs[i].t_f32 = pairs[i].t_norm = nullptr;
     if (tc) {
       pairs[i].q_i8 = (const int8_t*)s.d_i8_a.ptr + 256 * pn;
       pairs[i].t_i8 = (const int8_t*)s.d_i8_b.ptr + 256 * po;
@@ -687,6 +772,94 @@ int rgbdslam_b200_match_pairs_host(const uint8_t* desc_newer, const float* xyz_n
   }
   if (tc && (rc = expand_nodes(jobs))) return rc;
   return run_pairs(pairs, seed, first_pair_index, results, all_matches, inlier_matches);
+}
+
+int rgbdslam_b200_node_create_from_sift(int32_t id, const float* desc128, const float* xyz1, int n, uint64_t* node_handle) {
+  std::lock_guard<std::mutex> lk(g_state.mu);
+  int rc = check_inited();
+  if (rc) return rc;
+  if (!node_handle || n < 0 || n > kMaxFeatures || (n > 0 && (!desc128 || !xyz1))) {
+    set_error("node_create_from_sift: bad arguments (0 <= n <= 4096)");
+    return RGBDSLAM_B200_ERR_ARG;
+  }
+  State& s = g_state;
+  NodeDev* nd = new NodeDev();
+  nd->magic = NodeDev::kMagic;
+  nd->id = id;
+  nd->n = n;
+  nd->n_pad = pad256(n);
+  const size_t na = (size_t)(n > 0 ? n : 1);
+  if ((rc = s.d_f32_a.ensure(512 * na))) { delete nd; return rc; }
+  cudaError_t e = cudaMalloc(&nd->desc_f32, 512 * na);
+  if (e == cudaSuccess) e = cudaMalloc(&nd->xyz, 16 * na);
+  if (e == cudaSuccess) e = cudaMalloc(&nd->desc_i8, 256 * (size_t)nd->n_pad);
+  if (e == cudaSuccess) e = cudaMalloc(&nd->norms, 4 * (size_t)nd->n_pad);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(sift node)");
+  cudaStream_t st = s.stream;
+  if (n > 0) {
+    e = cudaMemcpyAsync(s.d_f32_a.ptr, desc128, 512 * (size_t)n, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(nd->xyz, xyz1, 16 * (size_t)n, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return cuda_fail(e, "sift node upload");
+  }
+  std::vector<SiftJob> jobs(1);
+  jobs[0] = {(const float*)s.d_f32_a.ptr, nd->desc_f32, (uint16_t*)nd->desc_i8, nd->norms, n, nd->n_pad};
+  if ((rc = prepare_sift_nodes(jobs))) return rc;
+  e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return cuda_fail(e, "sift node prepare");
+  *node_handle = (uint64_t)(uintptr_t)nd;
+  return 0;
+}
+
+int rgbdslam_b200_knn2_l2(const float* q, int nq, const float* t, int nt, int32_t* idx2, float* dist2) {
+  std::lock_guard<std::mutex> lk(g_state.mu);
+  int rc = check_inited();
+  if (rc) return rc;
+  if (nq < 0 || nt < 0 || nq > kMaxFeatures || nt > kMaxFeatures || (nq > 0 && (!q || !idx2 || !dist2)) || (nt > 0 && !t)) {
+    set_error("knn2_l2: bad arguments (at most 4096 rows)");
+    return RGBDSLAM_B200_ERR_ARG;
+  }
+  if (nq == 0) return 0;
+  State& s = g_state;
+  const int pq = pad256(nq), pt = pad256(nt);
+  const int stride = (nq + 127) / 128 * 128 + 128;
+  if ((rc = s.d_f32_a.ensure(512 * (size_t)nq)) || (rc = s.d_f32_b.ensure(512 * (size_t)(nt > 0 ? nt : 1))) ||
+      (rc = s.d_root_a.ensure(512 * (size_t)pq)) || (rc = s.d_root_b.ensure(512 * (size_t)pt)) ||
+      (rc = s.d_i8_a.ensure(256 * (size_t)pq)) || (rc = s.d_i8_b.ensure(256 * (size_t)pt)) ||
+      (rc = s.d_norm_a.ensure(4 * (size_t)pq)) || (rc = s.d_norm_b.ensure(4 * (size_t)pt)) ||
+      (rc = s.d_pairs.ensure(sizeof(PairDesc))) || (rc = s.h_pairs.ensure(sizeof(PairDesc))))
+    return rc;
+  cudaStream_t st = s.stream;
+  cudaError_t e = cudaMemcpyAsync(s.d_f32_a.ptr, q, 512 * (size_t)nq, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && nt > 0) e = cudaMemcpyAsync(s.d_f32_b.ptr, t, 512 * (size_t)nt, cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) return cuda_fail(e, "knn2_l2 upload");
+  std::vector<SiftJob> jobs(2);
+  jobs[0] = {(const float*)s.d_f32_a.ptr, (float*)s.d_root_a.ptr, (uint16_t*)s.d_i8_a.ptr, (float*)s.d_norm_a.ptr, nq, pq};
+  jobs[1] = {(const float*)s.d_f32_b.ptr, (float*)s.d_root_b.ptr, (uint16_t*)s.d_i8_b.ptr, (float*)s.d_norm_b.ptr, nt, pt};
+  if ((rc = prepare_sift_nodes(jobs))) return rc;
+  PairDesc pd;
+  memset(&pd, 0, sizeof(pd));
+  pd.nq = nq;
+  pd.nt = nt;
+  pd.q_i8 = (const int8_t*)s.d_i8_a.ptr;
+  pd.t_i8 = (const int8_t*)s.d_i8_b.ptr;
+  pd.q_f32 = (const float*)s.d_root_a.ptr;
+  pd.t_f32 = (const float*)s.d_root_b.ptr;
+  pd.t_norm = (const float*)s.d_norm_b.ptr;
+  memcpy(s.h_pairs.ptr, &pd, sizeof(pd));
+  e = cudaMemcpyAsync(s.d_pairs.ptr, s.h_pairs.ptr, sizeof(pd), cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) return cuda_fail(e, "knn2_l2 pair upload");
+  if ((rc = launch_sift_knn((const PairDesc*)s.d_pairs.ptr, &pd, 1, nq, stride, st))) return rc;
+  std::vector<float4> h(nq);
+  e = cudaMemcpyAsync(h.data(), s.d_knn.ptr, sizeof(float4) * nq, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return cuda_fail(e, "knn2_l2 download");
+  for (int i = 0; i < nq; i++) {
+    memcpy(&idx2[2 * i], &h[i].x, 4);
+    memcpy(&idx2[2 * i + 1], &h[i].y, 4);
+    dist2[2 * i] = h[i].z;
+    dist2[2 * i + 1] = h[i].w;
+  }
+  return 0;
 }
 
 }  // extern "C"

@@ -497,6 +497,60 @@ int rgbdslam_b200_nodes_create(uint64_t detector, int nframes, const uint8_t* gr
   return 0;
 }
 
+/* Debug/inspection hook (used by tools/debug_orb.py and the tests): the FAST/NMS candidates of grid cell `cell` of
+ * frame 0 of the last detect / nodes_create call: 8-byte records {u16 x, u16 y, u8 level, u8 score, u16 0} and their
+ * Harris responses (NaN = below the cell's final threshold). */
+int rgbdslam_b200_orb_debug_candidates(int cell, void* cand_out, float* resp_out, int capacity, int* n_out, int* thr_out) {
+  std::lock_guard<std::mutex> lk(g_state.mu);
+  int rc = check_inited();
+  if (rc) return rc;
+  OrbCtx& o = g_orb;
+  if (!o.ready || cell < 0 || cell >= o.g.ncells || !n_out) {
+    set_error("orb_debug_candidates: no detection has run / bad cell");
+    return RGBDSLAM_B200_ERR_STATE;
+  }
+  int n = 0, thr = 0;
+  cudaStream_t st = g_state.stream;
+  cudaMemcpyAsync(&n, (const int*)o.cand_count.ptr + cell, 4, cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(&thr, (const int*)o.thr.ptr + cell, 4, cudaMemcpyDeviceToHost, st);
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return cuda_fail(e, "orb_debug_candidates");
+  *n_out = n;
+  if (thr_out) *thr_out = thr;
+  const int m = std::min(std::min(n, capacity), kOrbCandCap);
+  if (m > 0 && cand_out) cudaMemcpyAsync(cand_out, (const OrbCand*)o.cand.ptr + (size_t)cell * kOrbCandCap, 8 * (size_t)m, cudaMemcpyDeviceToHost, st);
+  if (m > 0 && resp_out) cudaMemcpyAsync(resp_out, (const float*)o.resp.ptr + (size_t)cell * kOrbCandCap, 4 * (size_t)m, cudaMemcpyDeviceToHost, st);
+  e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return cuda_fail(e, "orb_debug_candidates copy");
+  return 0;
+}
+
+int rgbdslam_b200_orb_debug_plane(int which, int cell, int level, uint8_t* out, int capacity, int* w_out, int* h_out) {
+  std::lock_guard<std::mutex> lk(g_state.mu);
+  int rc = check_inited();
+  if (rc) return rc;
+  OrbCtx& o = g_orb;
+  if (!o.ready || level < 0 || level >= kOrbLevels || !w_out || !h_out) return RGBDSLAM_B200_ERR_ARG;
+  const OrbPlane* p;
+  const uint8_t* base;
+  if (which <= 2) {
+    if (cell < 0 || cell >= o.g.ncells) return RGBDSLAM_B200_ERR_ARG;
+    p = &o.g.cell[cell][level];
+    base = (const uint8_t*)(which == 0 ? o.cell_img.ptr : which == 1 ? o.cell_mask.ptr : o.score.ptr);
+  } else {
+    p = &o.g.full[level];
+    base = (const uint8_t*)(which == 3 ? o.pyr_raw.ptr : o.pyr_blur.ptr);
+  }
+  *w_out = p->w;
+  *h_out = p->h;
+  if (out && capacity >= p->w * p->h) {
+    cudaError_t e = cudaMemcpyAsync(out, base + p->off, (size_t)p->w * p->h, cudaMemcpyDeviceToHost, g_state.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g_state.stream);
+    if (e != cudaSuccess) return cuda_fail(e, "orb_debug_plane");
+  }
+  return 0;
+}
+
 int rgbdslam_b200_node_download_keypoints(uint64_t node_handle, rgbdslam_b200_keypoint* kp_out) {
   std::lock_guard<std::mutex> lk(g_state.mu);
   int rc = check_inited();

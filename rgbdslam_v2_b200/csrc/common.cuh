@@ -20,7 +20,10 @@ struct PairDesc {
   int32_t nq, nt;
   int32_t id_q, id_t;  // node ids (newer, older)
   const int8_t* q_i8;  // +-1 int8 expansion, tiled (hamming_tc.cu); nullptr if the SIMT path is used
-  const int8_t* t_i8;
+  const int8_t* t_i8;  // (SIFT nodes: the bf16 tiles)
+  const float* q_f32;  // SIFT nodes only: fp32 (Root)SIFT rows and train-row norms
+  const float* t_f32;
+  const float* t_norm;
 };
 
 // One unit of the +-1 int8 expansion (one node).
@@ -39,6 +42,16 @@ struct HamItem {
   int32_t nsearch;     // nt - 1: only train rows [0, nt-2] are examined (features.cpp:174)
   int32_t n_btiles;    // ceil(nsearch / 256)
   int32_t pad_;
+  const float* bnorm;  // SIFT L2 only: |b|^2 of the train rows (bf16-rounded values); out then points to int4 records
+};
+
+// One node of the SIFT preparation kernel (RootSIFT + bf16 tiles + norms).
+struct SiftJob {
+  const float* in;     // n x 128 raw descriptors
+  float* root;         // n x 128 RootSIFT (or copy) fp32, used for the exact re-ranking
+  uint16_t* tiles;     // n_pad x 128 bf16, tiled like the int8 Hamming operands (256 B per row)
+  float* norms;        // n_pad
+  int32_t n, n_pad;
 };
 
 // Constant-memory copy of the parameters the kernels read.

@@ -138,7 +138,25 @@ constexpr int kNoBest = (int)0x80000000;
 // instruction descriptor: D=S32 (2<<4), A=INT8 (1<<7), B=INT8 (1<<10), both K-major, N=256, M=128
 constexpr uint32_t kIdescI8 = (2u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
 
-__global__ void __launch_bounds__(kTcThreads, 1) hamming_tc_kernel(const HamItem* __restrict__ items, int n_items) {
+// instruction descriptor for the SIFT path: D=F32 (1<<4), A=BF16 (1<<7), B=BF16 (1<<10), K-major, N=256, M=128
+constexpr uint32_t kIdescBF16 = (1u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(acc)
+      : "memory");
+}
+
+// MODE 0: Hamming (int8 +-1 operands, int32 accumulators, arg-max of the dot product).
+// MODE 1: SIFT L2 (bf16 operands, 128-d rows are also 256 B => identical tile geometry; fp32 accumulators; the
+//         epilogue keeps the 4 best candidates per query by score 2 a.b - |b|^2; exact fp32 re-ranking follows).
+template <int MODE>
+__global__ void __launch_bounds__(kTcThreads, 1) tc_match_kernel(const HamItem* __restrict__ items, int n_items) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sA = smem_u32(smem);
   const uint32_t sB = sA + 2 * kTileA;
@@ -195,8 +213,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) hamming_tc_kernel(const HamItem
           tc_fence_after();
           const uint32_t a0 = sA + sa * kTileA, b0 = sB + sb * kTileB;
 #pragma unroll
-          for (int k = 0; k < 8; k++)
-            tc_mma_i8(tmem_base + acc * 256, make_desc(a0 + k * 256), make_desc(b0 + k * 256), kIdescI8, k > 0 ? 1u : 0u);
+          for (int k = 0; k < 8; k++) {
+            if (MODE == 0)
+              tc_mma_i8(tmem_base + acc * 256, make_desc(a0 + k * 256), make_desc(b0 + k * 256), kIdescI8, k > 0 ? 1u : 0u);
+            else
+              tc_mma_bf16(tmem_base + acc * 256, make_desc(a0 + k * 256), make_desc(b0 + k * 256), kIdescBF16, k > 0 ? 1u : 0u);
+          }
           tc_commit(bar(6 + sb));    // B stage may be refilled once these MMAs retire
           tc_commit(bar(8 + acc));   // accumulator ready for the epilogue
           if (++sb == 2) { sb = 0; pb ^= 1; }
@@ -213,6 +235,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) hamming_tc_kernel(const HamItem
     for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
       const HamItem item = items[it];
       int best = kNoBest;
+      float s0 = -3.0e38f, s1 = -3.0e38f, s2 = -3.0e38f, s3 = -3.0e38f;  // MODE 1: 4 best scores, descending
+      int i0 = -1, i1 = -1, i2 = -1, i3 = -1;
       for (int nb = 0; nb < item.n_btiles; nb++) {
         mbar_wait(bar(8 + acc), pacc);
         tc_fence_after();
@@ -223,13 +247,33 @@ __global__ void __launch_bounds__(kTcThreads, 1) hamming_tc_kernel(const HamItem
           tc_ld32(t0 + c * 32, v);
           tc_wait_ld();
           const int col0 = nb * 256 + c * 32;
-          if (col0 + 32 <= item.nsearch) {
+          if (MODE == 0) {
+            if (col0 + 32 <= item.nsearch) {
 #pragma unroll
-            for (int j = 0; j < 32; j++) best = max(best, (int)v[j] * 65536 + (65535 - (col0 + j)));
+              for (int j = 0; j < 32; j++) best = max(best, (int)v[j] * 65536 + (65535 - (col0 + j)));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; j++)
+                if (col0 + j < item.nsearch) best = max(best, (int)v[j] * 65536 + (65535 - (col0 + j)));
+            }
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; j++)
-              if (col0 + j < item.nsearch) best = max(best, (int)v[j] * 65536 + (65535 - (col0 + j)));
+            for (int j = 0; j < 32; j++) {
+              const int col = col0 + j;
+              if (col < item.nsearch) {
+                const float sc = fmaf(2.f, __uint_as_float(v[j]), -__ldg(item.bnorm + col));
+                if (sc > s3) {  // insert (ties keep the earlier = lower index)
+                  if (sc > s2) {
+                    s3 = s2; i3 = i2;
+                    if (sc > s1) {
+                      s2 = s1; i2 = i1;
+                      if (sc > s0) { s1 = s0; i1 = i0; s0 = sc; i0 = col; }
+                      else { s1 = sc; i1 = col; }
+                    } else { s2 = sc; i2 = col; }
+                  } else { s3 = sc; i3 = col; }
+                }
+              }
+            }
           }
         }
         tc_fence_before();
@@ -238,13 +282,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) hamming_tc_kernel(const HamItem
         if (++acc == 2) { acc = 0; pacc ^= 1; }
       }
       if (row < item.nq_valid) {
-        int2 o = make_int2(257, -1);  // features.cpp:172-173
-        if (best != kNoBest) {
-          const int s = best >> 16;  // dot product = 256 - 2*hd
-          o.x = (256 - s) >> 1;
-          o.y = 65535 - (best & 0xFFFF);
+        if (MODE == 0) {
+          int2 o = make_int2(257, -1);  // features.cpp:172-173
+          if (best != kNoBest) {
+            const int s = best >> 16;  // dot product = 256 - 2*hd
+            o.x = (256 - s) >> 1;
+            o.y = 65535 - (best & 0xFFFF);
+          }
+          item.out[row] = o;
+        } else {
+          reinterpret_cast<int4*>(item.out)[row] = make_int4(i0, i1, i2, i3);
         }
-        item.out[row] = o;
       }
     }
   }
@@ -259,12 +307,26 @@ cudaError_t launch_hamming_tc(const HamItem* d_items, int n_items, int sm_count,
   if (n_items <= 0) return cudaSuccess;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(hamming_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(tc_match_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
   const int grid = n_items < sm_count ? n_items : sm_count;
-  hamming_tc_kernel<<<grid, kTcThreads, kTcSmemBytes, stream>>>(d_items, n_items);
+  tc_match_kernel<0><<<grid, kTcThreads, kTcSmemBytes, stream>>>(d_items, n_items);
+  return cudaGetLastError();
+}
+
+// SIFT L2: items carry bf16 operand tiles, bnorm (|b|^2 of the bf16-rounded train rows) and an int4 output per query.
+cudaError_t launch_l2_tc(const HamItem* d_items, int n_items, int sm_count, cudaStream_t stream) {
+  if (n_items <= 0) return cudaSuccess;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tc_match_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int grid = n_items < sm_count ? n_items : sm_count;
+  tc_match_kernel<1><<<grid, kTcThreads, kTcSmemBytes, stream>>>(d_items, n_items);
   return cudaGetLastError();
 }
 

@@ -16,6 +16,14 @@ cudaError_t launch_expand_i8(const ExpandJob* d_jobs, int njobs, int max_n_pad, 
 // Tensor-core (tcgen05 kind::i8) Hamming brute force over work items; same output as launch_hamming_simt.
 cudaError_t launch_hamming_tc(const HamItem* d_items, int n_items, int sm_count, cudaStream_t stream);
 
+// SIFT-128 path (sift_l2.cu / hamming_tc.cu MODE 1)
+cudaError_t launch_sift_prepare(const SiftJob* d_jobs, int njobs, int max_n_pad, int root_sift, cudaStream_t stream);
+cudaError_t launch_l2_tc(const HamItem* d_items, int n_items, int sm_count, cudaStream_t stream);
+cudaError_t launch_l2_refine(const PairDesc* pairs, int npairs, int max_nq, const int4* top4, int stride, float4* knn,
+                             cudaStream_t stream);
+cudaError_t launch_select_sift(const PairDesc* pairs, int npairs, const float4* knn, int stride, float nn_ratio, int maxM,
+                               rgbdslam_b200_dmatch* matches, float4* mfrom, float4* mto, int32_t* n_all, cudaStream_t stream);
+
 // hd<128 filter + jitter distance + sort + keep max_matches (node.cpp:572-573,674,1127).
 cudaError_t launch_select_matches(const PairDesc* pairs, int npairs, const int2* best, int stride, uint64_t seed,
                                   int64_t first_pair, rgbdslam_b200_dmatch* matches, float4* mfrom, float4* mto,

@@ -93,20 +93,32 @@ __global__ void __launch_bounds__(256) k_fast_score(const uint8_t* __restrict__ 
     int d[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) d[k] = v - im[(y + dy[k]) * w + x + dx[k]];
-    // quick reject: a 9-arc always contains two opposite-quadrant compass points among {0,4,8,12}
-    int A = 0;
+    // corner(t): 9 contiguous circle pixels all darker than v - t (d > t) or all brighter than v + t (d < -t).
+    // S = largest t for which the pixel is still a corner (binary search; only corners pay for it).
+    auto corner = [&](int t) -> bool {
+      unsigned hi = 0, lo = 0;
 #pragma unroll
-    for (int k = 0; k < 16; k++) {
-      int mn = d[k], mx = d[k];
-#pragma unroll
-      for (int j = 1; j < 9; j++) {
-        const int t = d[(k + j) & 15];
-        mn = min(mn, t);
-        mx = max(mx, t);
+      for (int k = 0; k < 16; k++) {
+        hi |= (unsigned)(d[k] > t) << k;
+        lo |= (unsigned)(d[k] < -t) << k;
       }
-      A = max(A, max(mn, -mx));
+      hi |= hi << 16;  // wrap the circle
+      lo |= lo << 16;
+      unsigned a = hi & (hi >> 1), c2 = lo & (lo >> 1);
+      a &= a >> 2; c2 &= c2 >> 2;
+      a &= a >> 4; c2 &= c2 >> 4;   // runs of 8
+      a &= hi >> 8; c2 &= lo >> 8;  // runs of 9
+      return ((a | c2) & 0xFFFFu) != 0u;
+    };
+    if (corner(1)) {  // the adaptive threshold never goes below 2, scores < 2 are irrelevant
+      int lo_t = 1, hi_t = 254;
+      while (lo_t < hi_t) {
+        const int mid = (lo_t + hi_t + 1) >> 1;
+        if (corner(mid)) lo_t = mid;
+        else hi_t = mid - 1;
+      }
+      S = lo_t;
     }
-    S = max(A - 1, 0);
   }
   score[base + (size_t)y * p.w + x] = (uint8_t)min(S, 255);
 }

@@ -32,6 +32,8 @@ struct NodeDev {
   uint8_t* desc = nullptr;    // n x 32 B ORB descriptors
   float4* xyz = nullptr;      // n x (x,y,z,1)
   rgbdslam_b200_keypoint* kp = nullptr;  // n x cv::KeyPoint (only for nodes built from images)
+  float* desc_f32 = nullptr;  // SIFT nodes: n x 128 fp32 (Root)SIFT rows (desc == nullptr then)
+  float* norms = nullptr;     // SIFT nodes: n_pad |b|^2 of the bf16-rounded rows
   int8_t* desc_i8 = nullptr;  // n_pad x 256 B  +-1 expansion for the tensor-core Hamming path (lazily built)
   int32_t n_pad = 0;
 };
@@ -52,12 +54,14 @@ struct State {
   DevBuf d_pairs, d_best, d_matches, d_inliers, d_mfrom, d_mto, d_nall, d_hyp, d_results;
   DevBuf d_feat_a, d_feat_b, d_xyz_a, d_xyz_b;
   DevBuf d_i8_a, d_i8_b, d_jobs, d_items;
+  DevBuf d_top4, d_knn, d_f32_a, d_f32_b, d_root_a, d_root_b, d_norm_a, d_norm_b;
   PinBuf h_pairs, h_jobs, h_items;
   int hamming_path = 1;  // 1 = tcgen05 int8 GEMM (hamming_tc.cu), 0 = SIMT popcount (frontend_kernels.cu)
   void release_workspaces() {
     DevBuf* all[] = {&d_pairs, &d_best, &d_matches, &d_inliers, &d_mfrom, &d_mto, &d_nall,
                      &d_hyp,   &d_results, &d_feat_a, &d_feat_b, &d_xyz_a, &d_xyz_b,
-                     &d_i8_a,  &d_i8_b,    &d_jobs,   &d_items};
+                     &d_i8_a,  &d_i8_b,    &d_jobs,   &d_items,  &d_top4,   &d_knn,   &d_f32_a,
+                     &d_f32_b, &d_root_a,  &d_root_b, &d_norm_a, &d_norm_b};
     for (DevBuf* b : all) b->release();
     h_pairs.release();
     h_jobs.release();
