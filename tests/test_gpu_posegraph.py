@@ -78,7 +78,11 @@ def test_c5_size_properties(fe, oracle_mod):
     assert np.array_equal(x[0], g["init"][0])
     assert np.abs(np.linalg.norm(x[:, 3:], axis=1) - 1).max() < 1e-12
     ate0, ate = synth.ate_rmse(g["init"][:, :3], g["gt"][:, :3]), synth.ate_rmse(x[:, :3], g["gt"][:, :3])
-    assert ate < 0.02 and ate < 0.05 * ate0
+    assert ate < 0.05 and ate < 0.05 * ate0
+    # the CPU oracle stops at the same point of the same stop rule (graph_manager.cpp:1006-1014)
+    ox, ochi2, oit, _ = oracle_mod.posegraph_optimize(g["init"], g["fixed"], g["ij"], g["meas"], g["info"], stop=0.01)
+    assert abs(ate - synth.ate_rmse(ox[:, :3], g["gt"][:, :3])) < 1e-3 and synth.ate_rmse(x[:, :3], ox[:, :3]) < 1e-3
+    assert chi2 == pytest.approx(ochi2, rel=1e-4) and abs(it - oit) <= 2
     # idempotence: optimising the optimum again changes nothing measurable
     x2, chi2b, _, _ = fe.optimize_graph(x, g["fixed"], g["ij"], g["meas"], g["info"], stop=0.01)
     assert chi2b <= chi2 * (1 + 1e-9) and np.abs(x2[:, :3] - x[:, :3]).max() < 1e-4
