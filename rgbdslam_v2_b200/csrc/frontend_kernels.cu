@@ -182,45 +182,41 @@ struct Rt {
 // U diag(1,1,det U det V) V^T for any sign choice of the third singular pair.
 // Returns false if the result is not finite (the reference's `transformation != transformation` test,
 // node.cpp:1144) or the correspondences are rank deficient (< 2 independent directions).
-__device__ bool fit_transform(const float4* __restrict__ sfrom, const float4* __restrict__ sto, int M,
+// cfrom / cto hold the correspondences CENTRED on the pair's centroids (ca, cb) with the ORIGINAL depth in .w:
+// (x - cx, y - cy, z - cz, z).  Centring makes the single-pass raw-moment form of the weighted covariance
+// (sum w b a^T / W - m2 m1^T) as accurate in float32 as the reference's running-mean update.
+__device__ bool fit_transform(const float4* __restrict__ cfrom, const float4* __restrict__ cto, const float* ca, const float* cb,
                               const uint32_t* sel, int nw, int lane, Rt& out) {
   float W = 0.f, f0 = 0.f, f1 = 0.f, f2 = 0.f, t0 = 0.f, t1 = 0.f, t2 = 0.f;
+  float c[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
   for (int w = 0; w < kMaxMaskWords; w++) {
     if (w < nw && ((sel[w] >> lane) & 1u)) {
-      const float4 a = sfrom[w * 32 + lane], b = sto[w * 32 + lane];
-      if (!isnan(a.z) && !isnan(b.z)) {
-        const float wt = __fdiv_rn(1.0f, a.z * b.z);
+      const float4 a = cfrom[w * 32 + lane], b = cto[w * 32 + lane];
+      if (!isnan(a.w) && !isnan(b.w)) {  // transformation_estimation_euclidean.cpp:22
+        const float wt = __fdiv_rn(1.0f, a.w * b.w);  // :25
         W += wt;
         f0 += wt * a.x; f1 += wt * a.y; f2 += wt * a.z;
-        t0 += wt * b.x; t1 += wt * b.y; t2 += wt * b.z;
+        const float bx = wt * b.x, by = wt * b.y, bz = wt * b.z;
+        t0 += bx; t1 += by; t2 += bz;
+        c[0] += bx * a.x; c[1] += bx * a.y; c[2] += bx * a.z;
+        c[3] += by * a.x; c[4] += by * a.y; c[5] += by * a.z;
+        c[6] += bz * a.x; c[7] += bz * a.y; c[8] += bz * a.z;
       }
     }
   }
   W = wsum(W);
   f0 = wsum(f0); f1 = wsum(f1); f2 = wsum(f2);
   t0 = wsum(t0); t1 = wsum(t1); t2 = wsum(t2);
-  if (!(W > 0.f)) return false;
-  const float iW = __fdiv_rn(1.0f, W);
-  const float m1x = f0 * iW, m1y = f1 * iW, m1z = f2 * iW;
-  const float m2x = t0 * iW, m2y = t1 * iW, m2z = t2 * iW;
-  float c[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll
-  for (int w = 0; w < kMaxMaskWords; w++) {
-    if (w < nw && ((sel[w] >> lane) & 1u)) {
-      const float4 a = sfrom[w * 32 + lane], b = sto[w * 32 + lane];
-      if (!isnan(a.z) && !isnan(b.z)) {
-        const float wt = __fdiv_rn(1.0f, a.z * b.z) * iW;
-        const float d1x = a.x - m1x, d1y = a.y - m1y, d1z = a.z - m1z;
-        const float d2x = (b.x - m2x) * wt, d2y = (b.y - m2y) * wt, d2z = (b.z - m2z) * wt;
-        c[0] += d2x * d1x; c[1] += d2x * d1y; c[2] += d2x * d1z;
-        c[3] += d2y * d1x; c[4] += d2y * d1y; c[5] += d2y * d1z;
-        c[6] += d2z * d1x; c[7] += d2z * d1y; c[8] += d2z * d1z;
-      }
-    }
-  }
 #pragma unroll
   for (int i = 0; i < 9; i++) c[i] = wsum(c[i]);
+  if (!(W > 0.f)) return false;
+  const float iW = __fdiv_rn(1.0f, W);
+  const float m1x = f0 * iW, m1y = f1 * iW, m1z = f2 * iW;  // weighted means of the centred points
+  const float m2x = t0 * iW, m2y = t1 * iW, m2z = t2 * iW;
+  c[0] = c[0] * iW - m2x * m1x; c[1] = c[1] * iW - m2x * m1y; c[2] = c[2] * iW - m2x * m1z;
+  c[3] = c[3] * iW - m2y * m1x; c[4] = c[4] * iW - m2y * m1y; c[5] = c[5] * iW - m2y * m1z;
+  c[6] = c[6] * iW - m2z * m1x; c[7] = c[7] * iW - m2z * m1y; c[8] = c[8] * iW - m2z * m1z;
 
   // --- one-sided Jacobi SVD of c (row-major a[r][col]); v accumulates the right rotations ---
   float a00 = c[0], a01 = c[1], a02 = c[2], a10 = c[3], a11 = c[4], a12 = c[5], a20 = c[6], a21 = c[7], a22 = c[8];
@@ -287,9 +283,11 @@ __device__ bool fit_transform(const float4* __restrict__ sfrom, const float4* __
   out.R[6] = p2 * vp0 + q2 * vq0 + u32 * v30;
   out.R[7] = p2 * vp1 + q2 * vq1 + u32 * v31;
   out.R[8] = p2 * vp2 + q2 * vq2 + u32 * v32;
-  out.t[0] = m2x - (out.R[0] * m1x + out.R[1] * m1y + out.R[2] * m1z);
-  out.t[1] = m2y - (out.R[3] * m1x + out.R[4] * m1y + out.R[5] * m1z);
-  out.t[2] = m2z - (out.R[6] * m1x + out.R[7] * m1y + out.R[8] * m1z);
+  // t = mean2 - R mean1 with the centroids added back
+  const float g1x = m1x + ca[0], g1y = m1y + ca[1], g1z = m1z + ca[2];
+  out.t[0] = (m2x + cb[0]) - (out.R[0] * g1x + out.R[1] * g1y + out.R[2] * g1z);
+  out.t[1] = (m2y + cb[1]) - (out.R[3] * g1x + out.R[4] * g1y + out.R[5] * g1z);
+  out.t[2] = (m2z + cb[2]) - (out.R[6] * g1x + out.R[7] * g1y + out.R[8] * g1z);
   bool fin = true;
 #pragma unroll
   for (int i = 0; i < 9; i++) fin = fin && (out.R[i] == out.R[i]);
@@ -311,6 +309,7 @@ struct ScoreCtx {
   double R[9], t[3];
   double P[6];   // rcx * r0_i r0_j + rcy * r1_i r1_j   (ij = 00,01,02,11,12,22), r_k = k-th row of R
   double O2[6];  // r2_i r2_j
+  float Pf[6], O2f[6];  // float copies for the screening pass
 };
 
 __device__ __forceinline__ void make_score_ctx(const Rt& T, ScoreCtx& c) {
@@ -324,7 +323,53 @@ __device__ __forceinline__ void make_score_ctx(const Rt& T, ScoreCtx& c) {
   for (int k = 0; k < 6; k++) {
     c.P[k] = fma(__dmul_rn(rcx, c.R[I[k]]), c.R[J[k]], __dmul_rn(__dmul_rn(rcy, c.R[3 + I[k]]), c.R[3 + J[k]]));
     c.O2[k] = __dmul_rn(c.R[6 + I[k]], c.R[6 + J[k]]);
+    c.Pf[k] = (float)c.P[k];
+    c.O2f[k] = (float)c.O2[k];
   }
+}
+
+// float32 screening of errorFunction2: returns the class of the correspondence without touching the FP64 pipe when
+// the answer is not close to a decision boundary.
+//   0: certainly rejected (shortcut of misc.cpp:726-735 or d^2 > thr)    1: certainly an inlier, *m_out = d^2 (float)
+//   2: too close to call in float32 -> the caller evaluates the float64 reference formula
+// Margins: 1e-3 relative on both tests, orders of magnitude above the float32 evaluation error (~1e-5 relative for
+// the 3x3 SPD solve with condition number < 1e2).
+__device__ __forceinline__ int mahal_screen(const float4 x1, const float4 x2, const Rt& T, const ScoreCtx& c, float sq_max,
+                                            float* m_out) {
+  if (isnan(x1.z) || isnan(x2.z)) return 0;
+  const float d0 = fmaf(T.R[0], x1.x, fmaf(T.R[1], x1.y, fmaf(T.R[2], x1.z, T.t[0] * x1.w))) - x2.x;
+  const float d1 = fmaf(T.R[3], x1.x, fmaf(T.R[4], x1.y, fmaf(T.R[5], x1.z, T.t[1] * x1.w))) - x2.y;
+  const float d2 = fmaf(T.R[6], x1.x, fmaf(T.R[7], x1.y, fmaf(T.R[8], x1.z, T.t[2] * x1.w))) - x2.z;
+  const float rcx = (float)c_params.raster_cov_x, rcy = (float)c_params.raster_cov_y;
+  const float cz1 = (float)depth_cov((double)x1.z), cz2 = (float)depth_cov((double)x2.z);
+  const float dsq = fmaf(d0, d0, fmaf(d1, d1, d2 * d2));
+  const float lim = 2.f * (fmaxf(rcx, cz1) + fmaxf(rcx, cz2));
+  if (dsq > lim * 1.001f) return 0;
+  if (!(dsq < lim * 0.999f)) return 2;
+  const float a2 = x1.z, b2 = x2.z;
+  const float S00 = fmaf(a2, c.Pf[0], fmaf(cz1, c.O2f[0], rcx * b2));
+  const float S01 = fmaf(a2, c.Pf[1], cz1 * c.O2f[1]);
+  const float S02 = fmaf(a2, c.Pf[2], cz1 * c.O2f[2]);
+  const float S11 = fmaf(a2, c.Pf[3], fmaf(cz1, c.O2f[3], rcy * b2));
+  const float S12 = fmaf(a2, c.Pf[4], cz1 * c.O2f[4]);
+  const float S22 = fmaf(a2, c.Pf[5], fmaf(cz1, c.O2f[5], cz2));
+  // scale to O(1) to stay far from float under/overflow in the cubic determinant (entries are 1e-5 .. 1e-2)
+  const float k = 1024.f;
+  const float s00 = S00 * k, s01 = S01 * k, s02 = S02 * k, s11 = S11 * k, s12 = S12 * k, s22 = S22 * k;
+  const float A00 = fmaf(s11, s22, -s12 * s12), A01 = fmaf(s02, s12, -s01 * s22), A02 = fmaf(s01, s12, -s02 * s11);
+  const float A11 = fmaf(s00, s22, -s02 * s02), A12 = fmaf(s01, s02, -s00 * s12), A22 = fmaf(s00, s11, -s01 * s01);
+  const float det = fmaf(s00, A00, fmaf(s01, A01, s02 * A02));
+  const float e0 = fmaf(A00, d0, fmaf(A01, d1, A02 * d2));
+  const float e1 = fmaf(A01, d0, fmaf(A11, d1, A12 * d2));
+  const float e2 = fmaf(A02, d0, fmaf(A12, d1, A22 * d2));
+  const float m = fmaf(d0, e0, fmaf(d1, e1, d2 * e2)) * k / det;
+  if (!(m >= 0.f) || !(det > 0.f)) return 2;
+  if (m > sq_max * 1.001f) return 0;
+  if (m < sq_max * 0.999f) {
+    *m_out = m;
+    return 1;
+  }
+  return 2;
 }
 
 // errorFunction2 (misc.cpp:697-770) in float64.  Written with explicit rounding intrinsics only, so the
@@ -390,8 +435,15 @@ __device__ int score_all(const float4* __restrict__ sfrom, const float4* __restr
       if (i < M) {
         const float4 a = sfrom[i], b = sto[i];
         if (!(a.z == 0.0f || b.z == 0.0f)) {  // node.cpp:994 (does not trigger on NaN)
-          m = mahal_sq(a, b, ctx);
-          inl = !(m > sq_max) && (m >= 0.0);  // node.cpp:998-1005
+          float mf;
+          const int cls = mahal_screen(a, b, T, ctx, (float)sq_max, &mf);
+          if (cls == 1) {
+            m = (double)mf;
+            inl = true;
+          } else if (cls == 2) {  // float32 cannot decide: the float64 reference formula
+            m = mahal_sq(a, b, ctx);
+            inl = !(m > sq_max) && (m >= 0.0);  // node.cpp:998-1005
+          }
         }
       }
       word = __ballot_sync(kFull, inl);
@@ -466,6 +518,10 @@ __global__ void __launch_bounds__(kRansacWarps * 32)
                       const int32_t* __restrict__ n_all, HypResult* __restrict__ hyp) {
   __shared__ float4 sfrom[kMaxMatchesCap];
   __shared__ float4 sto[kMaxMatchesCap];
+  __shared__ float4 cfrom[kMaxMatchesCap];  // centred copies for the fit (see fit_transform)
+  __shared__ float4 cto[kMaxMatchesCap];
+  __shared__ float s_cen[8];
+  __shared__ float s_part[kRansacWarps][6];
   __shared__ int s_next_n;
   __shared__ int s_cnt[kMaxScanPrefix];
   __shared__ double s_err[kMaxScanPrefix];
@@ -488,9 +544,30 @@ __global__ void __launch_bounds__(kRansacWarps * 32)
     __syncthreads();
     if (s_next_n >= n_begin + (int)(blockIdx.x + 1) * kRansacWarps || s_next_n >= n_end) return;
   }
+  float cs[6] = {0, 0, 0, 0, 0, 0};
   for (int i = threadIdx.x; i < M; i += blockDim.x) {
-    sfrom[i] = mfrom[(size_t)p * maxM + i];
-    sto[i] = mto[(size_t)p * maxM + i];
+    const float4 a = mfrom[(size_t)p * maxM + i], b = mto[(size_t)p * maxM + i];
+    sfrom[i] = a;
+    sto[i] = b;
+    if (!isnan(a.x + a.y + a.z + b.x + b.y + b.z)) {
+      cs[0] += a.x; cs[1] += a.y; cs[2] += a.z; cs[3] += b.x; cs[4] += b.y; cs[5] += b.z;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 6; k++) cs[k] = wsum(cs[k]);
+  if ((threadIdx.x & 31) == 0)
+    for (int k = 0; k < 6; k++) s_part[threadIdx.x >> 5][k] = cs[k];
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    float t = 0.f;
+    for (int w = 0; w < kRansacWarps; w++) t += s_part[w][threadIdx.x];
+    s_cen[threadIdx.x] = t / (float)M;  // any common offset is valid; the (NaN-free) mean keeps the centred data small
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < M; i += blockDim.x) {
+    const float4 a = sfrom[i], b = sto[i];
+    cfrom[i] = make_float4(a.x - s_cen[0], a.y - s_cen[1], a.z - s_cen[2], a.z);
+    cto[i] = make_float4(b.x - s_cen[3], b.y - s_cen[4], b.z - s_cen[5], b.z);
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
@@ -538,7 +615,7 @@ __global__ void __launch_bounds__(kRansacWarps * 32)
 
   for (int refinements = 1; refinements < 20; refinements++) {  // node.cpp:1140
     Rt T;
-    if (!fit_transform(sfrom, sto, M, sel, nw, lane, T)) break;  // node.cpp:1142-1145
+    if (!fit_transform(cfrom, cto, s_cen, s_cen + 3, sel, nw, lane, T)) break;  // node.cpp:1142-1145
     double err;
     const int cnt = score_all(sfrom, sto, M, nw, lane, T, sel, err);  // node.cpp:1148
     if ((unsigned)cnt < min_thr || err > (double)c_params.max_dist_m) break;  // node.cpp:1154

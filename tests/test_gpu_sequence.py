@@ -1,0 +1,57 @@
+"""End-to-end sequence on the GPU (frames -> Node ctor -> pair matching -> pose graph) vs the same pipeline on the CPU
+oracle, and vs ground truth: the ATE part of the north-star metric (BASELINE config C4 at reduced length)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+class OracleBackend:
+    """cv2 ORB + reference glue (oracle/orb_oracle.py), C oracle for matching / RANSAC and the pose graph."""
+
+    def __init__(self, oracle_mod, max_keypoints):
+        from oracle import orb_oracle
+        self.o, self.orb = oracle_mod, orb_oracle
+        self.st = orb_oracle.DetectorState()
+        self.K = max_keypoints
+
+    def construct_nodes(self, gray, depth, mask, K4):
+        return [self.orb.node_construct(g, d, m, K4, self.st, max_keypoints=self.K) for g, d, m in zip(gray, depth, mask)]
+
+    def match(self, nodes, pairs, seed):
+        prm = self.o.make_params(depth_cov_z0=2.0)
+        dn = np.concatenate([nodes[a][1] for a, _ in pairs]); xn = np.concatenate([nodes[a][2] for a, _ in pairs])
+        do = np.concatenate([nodes[b][1] for _, b in pairs]); xo = np.concatenate([nodes[b][2] for _, b in pairs])
+        nn = [len(nodes[a][1]) for a, _ in pairs]; no = [len(nodes[b][1]) for _, b in pairs]
+        res, _, _ = self.o.match_pairs(prm, dn, xn, nn, do, xo, no, [a for a, _ in pairs], [b for _, b in pairs], seed=seed,
+                                       threads=8, want_matches=False)
+        return res
+
+    def optimize(self, graph, stop):
+        x, chi2, _, _ = self.o.posegraph_optimize(graph["init"], graph["fixed"], graph["ij"], graph["meas"], graph["info"], stop=stop)
+        return x, chi2
+
+
+def test_sequence_ate_within_1mm_of_the_oracle(built, oracle_mod):
+    from oracle import orb_oracle
+    from rgbdslam_v2_b200 import Frontend, pipeline, synth
+    from rgbdslam_v2_b200._capi import default_params
+    n = 36
+    poses = synth.trajectory(240)[:n]
+    frames = [synth.render_frame(poses[k], seed=k) for k in range(n)]
+    gray = np.stack([f[0] for f in frames]); depth = np.stack([f[1] for f in frames])
+    mask = np.stack([orb_oracle.depth_to_mask(d) for d in depth])
+    K4 = (synth.FX, synth.FY, synth.CX, synth.CY)
+    p = default_params(); p.depth_cov_z0 = 2.0; p.max_keypoints = 600
+    fe = Frontend(0, p)
+    out = pipeline.run_sequence(pipeline.GpuBackend(fe), gray, depth, mask, K4, seed=5)
+    ref = pipeline.run_sequence(OracleBackend(oracle_mod, 600), gray, depth, mask, K4, seed=5)
+    fe.close()
+    gt = np.stack([pipeline.mat_to_pose7(np.linalg.inv(poses[0]) @ P) for P in poses])
+    ate, ate_ref = synth.ate_rmse(out["traj"][:, :3], gt[:, :3]), synth.ate_rmse(ref["traj"][:, :3], gt[:, :3])
+    valid, valid_ref = out["results"]["id1"] >= 0, ref["results"]["id1"] >= 0
+    assert (valid == valid_ref).mean() > 0.98 and valid.sum() > 0.8 * len(valid)
+    assert out["graph"]["n_const_edges"] == ref["graph"]["n_const_edges"]
+    assert ate < 0.02, ate                                        # the synthetic room is tracked to < 2 cm
+    assert abs(ate - ate_ref) < 1e-3, (ate, ate_ref)              # north star: ATE within 1 mm of the reference path
+    assert synth.ate_rmse(out["traj"][:, :3], ref["traj"][:, :3]) < 1e-3
