@@ -139,3 +139,74 @@ class GpuBackend:
     def optimize(self, graph, stop):
         x, chi2, _, _ = self.fe.optimize_graph(graph["init"], graph["fixed"], graph["ij"], graph["meas"], graph["info"], stop=stop)
         return x, chi2
+
+
+# ---------------------------------------------------------------------------------------------------
+# Batch evaluation back-end: prune / re-optimise / trajectory export.
+
+def prune_edges(graph: dict, per_edge_chi2: np.ndarray, thresh: float) -> int:
+    """GraphManager::pruneEdgesWithErrorAbove (graph_manager.cpp:1106-1246), in place on `graph`.
+    For every ACTIVE edge with chi2 > thresh: measurement := identity; non-consecutive edges are removed from the
+    active set when both end vertices have more than one incident edge, else their information becomes 1e-100 * I;
+    consecutive edges get information I.  Returns the number of edges over the threshold."""
+    ij, n = graph["ij"], len(graph["ij"])
+    active = graph.setdefault("active", np.ones(n, bool))
+    # v->edges().size(): every edge ever added to the optimizer counts (removal only leaves the active set)
+    deg = np.bincount(ij.reshape(-1), minlength=len(graph["init"]))
+    ident = np.array([0, 0, 0, 0, 0, 0, 1.0])
+    counter = 0
+    for k in np.nonzero(active)[0]:
+        if per_edge_chi2[k] > thresh:
+            counter += 1
+            graph["meas"][k] = ident
+            a, b = ij[k]
+            if abs(int(a) - int(b)) != 1:
+                if deg[a] > 1 and deg[b] > 1:
+                    active[k] = False
+                else:
+                    graph["info"][k] = np.eye(6).reshape(-1) * 1e-100
+            else:
+                graph["info"][k] = np.eye(6).reshape(-1)
+    return counter
+
+
+def active_view(graph: dict) -> dict:
+    a = graph.get("active")
+    if a is None:
+        return graph
+    return dict(graph, ij=np.ascontiguousarray(graph["ij"][a]), meas=np.ascontiguousarray(graph["meas"][a]),
+                info=np.ascontiguousarray(graph["info"][a]))
+
+
+def evaluation_sequence(backend, graph: dict, stop: float = 0.01):
+    """OpenNIListener::evaluation (openni_listener.cpp:431-466): optimise, then prune at chi2 5 / 1 / 0.25, each
+    followed by optimizeGraph(-100) (= the parameter's stop rule) or a single iteration when nothing was pruned.
+    backend needs .optimize(graph, stop) and .edge_chi2(poses, graph).  Returns the trajectories of levels 1..4."""
+    g = dict(graph, meas=graph["meas"].copy(), info=graph["info"].copy())
+    levels = []
+    x, chi2 = backend.optimize(active_view(g), stop)
+    g["init"] = x
+    levels.append((x.copy(), chi2, 0))
+    for thr in (5.0, 1.0, 0.25):
+        full = backend.edge_chi2(x, g)
+        n = prune_edges(g, full, thr)
+        x, chi2 = backend.optimize(active_view(g), stop if n > 0 else 1.0)
+        g["init"] = x
+        levels.append((x.copy(), chi2, n))
+    return levels
+
+
+def save_trajectory(path: str, poses7: np.ndarray, stamps: np.ndarray):
+    """TUM trajectory format written by logTransform (misc.cpp:90-93): timestamp tx ty tz qx qy qz qw, fixed notation."""
+    with open(path, "w") as f:
+        f.write("# TF Coordinate Frame ID: (data: )\n")
+        for t, p in zip(stamps, poses7):
+            f.write("%f %f %f %f %f %f %f %f\n" % (t, *p))
+
+
+def _gpu_edge_chi2(self, poses, graph):
+    _, pe = self.fe.graph_chi2(poses, graph["ij"], graph["meas"], graph["info"], per_edge=True)
+    return pe
+
+
+GpuBackend.edge_chi2 = _gpu_edge_chi2

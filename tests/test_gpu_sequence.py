@@ -55,3 +55,44 @@ def test_sequence_ate_within_1mm_of_the_oracle(built, oracle_mod):
     assert ate < 0.02, ate                                        # the synthetic room is tracked to < 2 cm
     assert abs(ate - ate_ref) < 1e-3, (ate, ate_ref)              # north star: ATE within 1 mm of the reference path
     assert synth.ate_rmse(out["traj"][:, :3], ref["traj"][:, :3]) < 1e-3
+
+
+def _oracle_edge_chi2(self, poses, graph):
+    out = np.zeros(len(graph["ij"]))
+    for k, (i, j) in enumerate(graph["ij"]):
+        e = self.o.edge_se3(poses[i], poses[j], graph["meas"][k], False)[0]
+        out[k] = e @ graph["info"][k].reshape(6, 6) @ e
+    return out
+
+
+OracleBackend.edge_chi2 = _oracle_edge_chi2
+
+
+def test_prune_and_reoptimize_sequence(built, oracle_mod):
+    """pruneEdgesWithErrorAbove(5 / 1 / 0.25) + re-optimisation (openni_listener.cpp:431-466) on a graph with
+    outlier loop closures: the GPU back-end and the oracle back-end prune the same edges and land on the same
+    trajectories."""
+    from rgbdslam_v2_b200 import Frontend, pipeline, synth
+    g = synth.make_pose_graph(300, 1500, seed=21, outlier_frac=0.05)
+    fe = Frontend(0)
+    gpu_levels = pipeline.evaluation_sequence(pipeline.GpuBackend(fe), g)
+    ref_levels = pipeline.evaluation_sequence(OracleBackend(oracle_mod, 600), g)
+    fe.close()
+    for (x, chi2, n), (ox, ochi2, on) in zip(gpu_levels, ref_levels):
+        assert n == on
+        assert chi2 == pytest.approx(ochi2, rel=1e-4, abs=1e-6)
+        assert synth.ate_rmse(x[:, :3], ox[:, :3]) < 1e-3
+    assert gpu_levels[1][2] > 0  # the outlier edges are found at threshold 5
+    ate = [synth.ate_rmse(x[:, :3], g["gt"][:, :3]) for x, _, _ in gpu_levels]
+    assert ate[1] <= ate[0] + 1e-3  # pruning outliers does not hurt
+
+
+def test_tum_trajectory_format(tmp_path):
+    from rgbdslam_v2_b200 import pipeline
+    p = np.array([[1, 2, 3, 0, 0, 0, 1.0], [0.5, 0, 0, 0, 0, np.sin(0.1), np.cos(0.1)]])
+    f = tmp_path / "traj_estimate.txt"
+    pipeline.save_trajectory(str(f), p, np.array([10.0, 10.033333]))
+    lines = f.read_text().splitlines()
+    assert lines[0].startswith("#") and len(lines) == 3
+    v = [float(t) for t in lines[2].split()]
+    assert len(v) == 8 and v[0] == pytest.approx(10.033333) and v[7] == pytest.approx(np.cos(0.1), abs=1e-6)
