@@ -188,9 +188,26 @@ int rgbdslam_b200_match_pairs_host(const uint8_t* desc_newer, const float* xyz_n
                                    rgbdslam_b200_dmatch* all_matches,
                                    rgbdslam_b200_dmatch* inlier_matches);
 
+/* Pipelined variants: up to 4 independent slots (own CUDA stream + workspace each).  submit() only enqueues the
+ * uploads, kernels and result downloads and returns; wait(slot) blocks until that slot's results are in the output
+ * buffers (which must stay valid -- pinned memory recommended).  Successive batches submitted to different slots
+ * overlap on the GPU (host->device copies of batch k+1 with the kernels of batch k; the latency-bound RANSAC phases
+ * of several batches with each other).  slot 0 shares the stream of the synchronous calls.  Results are identical
+ * to the synchronous calls. */
+int rgbdslam_b200_match_pairs_submit(int slot, const uint64_t* newer, const uint64_t* older, int npairs, uint64_t seed,
+                                     int64_t first_pair_index, rgbdslam_b200_pair_result* results,
+                                     rgbdslam_b200_dmatch* all_matches, rgbdslam_b200_dmatch* inlier_matches);
+int rgbdslam_b200_match_pairs_host_submit(int slot, const uint8_t* desc_newer, const float* xyz_newer, const int32_t* n_newer,
+                                          const uint8_t* desc_older, const float* xyz_older, const int32_t* n_older,
+                                          const int32_t* id_newer, const int32_t* id_older, int npairs, uint64_t seed,
+                                          int64_t first_pair_index, rgbdslam_b200_pair_result* results,
+                                          rgbdslam_b200_dmatch* all_matches, rgbdslam_b200_dmatch* inlier_matches);
+int rgbdslam_b200_match_pairs_wait(int slot);
+
 /* Timing hook: CUDA-event duration (ms) of the dominant kernel (Hamming match)
  * and of the whole device part of the last match_pairs* call. */
 int rgbdslam_b200_last_timing(float* hamming_ms, float* total_device_ms);
+int rgbdslam_b200_last_timing_slot(int slot, float* hamming_ms, float* total_device_ms);
 
 /* ---- Node construction from images -------------------------------------------
  * The reference builds one detector / extractor pair and shares it between all Node constructors

@@ -114,6 +114,9 @@ def load_library(path: str | Path | None = None) -> C.CDLL:
     lib.rgbdslam_b200_node_destroy.argtypes = [u64]
     lib.rgbdslam_b200_match_pairs.argtypes = [vp, vp, C.c_int, u64, i64, vp, vp, vp]
     lib.rgbdslam_b200_match_pairs_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, u64, i64, vp, vp, vp]
+    lib.rgbdslam_b200_match_pairs_submit.argtypes = [C.c_int, vp, vp, C.c_int, u64, i64, vp, vp, vp]
+    lib.rgbdslam_b200_match_pairs_host_submit.argtypes = [C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, u64, i64, vp, vp, vp]
+    lib.rgbdslam_b200_match_pairs_wait.argtypes = [C.c_int]
     lib.rgbdslam_b200_set_hamming_path.argtypes = [C.c_int]
     lib.rgbdslam_b200_detector_create.argtypes = [C.POINTER(u64)]
     lib.rgbdslam_b200_detector_destroy.argtypes = [u64]
@@ -134,6 +137,7 @@ def load_library(path: str | Path | None = None) -> C.CDLL:
                                                      C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.rgbdslam_b200_posegraph_chi2.argtypes = [C.c_int, vp, C.c_int, vp, vp, vp, C.c_double, C.POINTER(C.c_double), vp]
     lib.rgbdslam_b200_last_timing.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    lib.rgbdslam_b200_last_timing_slot.argtypes = [C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     for name in declared_symbols():
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
         if fn.restype is C.c_int and name not in ("rgbdslam_b200_default_params",):
@@ -197,9 +201,9 @@ class Frontend:
     def depth_cov_z0(self) -> float:
         return float(self.lib.rgbdslam_b200_depth_cov_z0())
 
-    def last_timing(self) -> tuple[float, float]:
+    def last_timing(self, slot: int = 0) -> tuple[float, float]:
         a, b = C.c_float(), C.c_float()
-        self._check(self.lib.rgbdslam_b200_last_timing(C.byref(a), C.byref(b)))
+        self._check(self.lib.rgbdslam_b200_last_timing_slot(slot, C.byref(a), C.byref(b)))
         return a.value, b.value
 
     # -- bruteForceSearchORB ------------------------------------------------
@@ -271,6 +275,24 @@ class Frontend:
         self._check(self.lib.rgbdslam_b200_match_pairs(_ptr(a), _ptr(b), npairs, seed, first_pair_index,
                                                        _ptr(res), _ptr(allm), _ptr(inl)))
         return res, allm, inl
+
+    def submit_node_pairs(self, slot: int, newer_arr: np.ndarray, older_arr: np.ndarray, out, seed: int = 0,
+                          first_pair_index: int = 0):
+        """Asynchronous match_node_pairs on pipeline slot `slot`; newer_arr / older_arr: uint64 handle arrays that stay
+        alive until wait_slot(); out = (results, all_matches | None, inlier_matches | None) host arrays."""
+        res, allm, inl = out
+        self._check(self.lib.rgbdslam_b200_match_pairs_submit(slot, _ptr(newer_arr), _ptr(older_arr), len(newer_arr), seed,
+                                                              first_pair_index, _ptr(res), _ptr(allm), _ptr(inl)))
+
+    def submit_pairs_host(self, slot: int, desc_newer, xyz_newer, n_newer, desc_older, xyz_older, n_older, id_newer, id_older,
+                          out, seed: int = 0, first_pair_index: int = 0):
+        res, allm, inl = out
+        self._check(self.lib.rgbdslam_b200_match_pairs_host_submit(
+            slot, _ptr(desc_newer), _ptr(xyz_newer), _ptr(n_newer), _ptr(desc_older), _ptr(xyz_older), _ptr(n_older),
+            _ptr(id_newer), _ptr(id_older), len(n_newer), seed, first_pair_index, _ptr(res), _ptr(allm), _ptr(inl)))
+
+    def wait_slot(self, slot: int):
+        self._check(self.lib.rgbdslam_b200_match_pairs_wait(slot))
 
     def match_pairs_host(self, desc_newer, xyz_newer, n_newer, desc_older, xyz_older, n_older, id_newer=None,
                          id_older=None, seed: int = 0, first_pair_index: int = 0, want_matches: bool = True, out=None):

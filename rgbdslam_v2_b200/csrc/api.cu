@@ -88,6 +88,26 @@ int check_inited() {
   }
   cudaError_t e = cudaSetDevice(g_state.device);
   if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+  g_state.cur = &g_state.ws[0];  // synchronous entry points run on slot 0
+  g_state.ws[0].stream = g_state.stream;
+  return 0;
+}
+
+// select the pipeline slot of an asynchronous submit; a slot with unfinished work is drained first (its pinned
+// staging buffers are about to be reused)
+static int use_slot(int slot) {
+  if (slot < 0 || slot >= kSlots) {
+    set_error("slot out of range [0,4)");
+    return RGBDSLAM_B200_ERR_ARG;
+  }
+  State& s = g_state;
+  s.cur = &s.ws[slot];
+  if (slot == 0) s.ws[0].stream = s.stream;
+  if (s.cur->pending) {
+    cudaError_t e = cudaStreamSynchronize(s.cur->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "drain slot");
+    s.cur->pending = false;
+  }
   return 0;
 }
 
@@ -107,14 +127,14 @@ static int expand_nodes(const std::vector<ExpandJob>& jobs) {
   State& s = g_state;
   if (jobs.empty()) return 0;
   int rc;
-  if ((rc = s.d_jobs.ensure(sizeof(ExpandJob) * jobs.size()))) return rc;
-  if ((rc = s.h_jobs.ensure(sizeof(ExpandJob) * jobs.size()))) return rc;
+  if ((rc = s.W().d_jobs.ensure(sizeof(ExpandJob) * jobs.size()))) return rc;
+  if ((rc = s.W().h_jobs.ensure(sizeof(ExpandJob) * jobs.size()))) return rc;
   int max_pad = 0;
   for (const ExpandJob& j : jobs) max_pad = j.n_pad > max_pad ? j.n_pad : max_pad;
-  memcpy(s.h_jobs.ptr, jobs.data(), sizeof(ExpandJob) * jobs.size());
-  cudaError_t e = cudaMemcpyAsync(s.d_jobs.ptr, s.h_jobs.ptr, sizeof(ExpandJob) * jobs.size(), cudaMemcpyHostToDevice, s.stream);
+  memcpy(s.W().h_jobs.ptr, jobs.data(), sizeof(ExpandJob) * jobs.size());
+  cudaError_t e = cudaMemcpyAsync(s.W().d_jobs.ptr, s.W().h_jobs.ptr, sizeof(ExpandJob) * jobs.size(), cudaMemcpyHostToDevice, s.W().stream);
   if (e != cudaSuccess) return cuda_fail(e, "upload expand jobs");
-  e = launch_expand_i8((const ExpandJob*)s.d_jobs.ptr, (int)jobs.size(), max_pad, s.stream);
+  e = launch_expand_i8((const ExpandJob*)s.W().d_jobs.ptr, (int)jobs.size(), max_pad, s.W().stream);
   if (e != cudaSuccess) return cuda_fail(e, "expand_i8 kernel");
   s.launches += 1;
   return 0;
@@ -127,14 +147,14 @@ static int prepare_sift_nodes(const std::vector<SiftJob>& jobs) {
   State& s = g_state;
   if (jobs.empty()) return 0;
   int rc;
-  if ((rc = s.d_jobs.ensure(sizeof(SiftJob) * jobs.size()))) return rc;
-  if ((rc = s.h_jobs.ensure(sizeof(SiftJob) * jobs.size()))) return rc;
+  if ((rc = s.W().d_jobs.ensure(sizeof(SiftJob) * jobs.size()))) return rc;
+  if ((rc = s.W().h_jobs.ensure(sizeof(SiftJob) * jobs.size()))) return rc;
   int max_pad = 0;
   for (const SiftJob& j : jobs) max_pad = j.n_pad > max_pad ? j.n_pad : max_pad;
-  memcpy(s.h_jobs.ptr, jobs.data(), sizeof(SiftJob) * jobs.size());
-  cudaError_t e = cudaMemcpyAsync(s.d_jobs.ptr, s.h_jobs.ptr, sizeof(SiftJob) * jobs.size(), cudaMemcpyHostToDevice, s.stream);
+  memcpy(s.W().h_jobs.ptr, jobs.data(), sizeof(SiftJob) * jobs.size());
+  cudaError_t e = cudaMemcpyAsync(s.W().d_jobs.ptr, s.W().h_jobs.ptr, sizeof(SiftJob) * jobs.size(), cudaMemcpyHostToDevice, s.W().stream);
   if (e != cudaSuccess) return cuda_fail(e, "upload sift jobs");
-  e = launch_sift_prepare((const SiftJob*)s.d_jobs.ptr, (int)jobs.size(), max_pad, s.params.use_root_sift ? 1 : 0, s.stream);
+  e = launch_sift_prepare((const SiftJob*)s.W().d_jobs.ptr, (int)jobs.size(), max_pad, s.params.use_root_sift ? 1 : 0, s.W().stream);
   if (e != cudaSuccess) return cuda_fail(e, "sift_prepare kernel");
   s.launches += 1;
   return 0;
@@ -144,8 +164,8 @@ static int prepare_sift_nodes(const std::vector<SiftJob>& jobs) {
 static int launch_sift_knn(const PairDesc* d_pairs, const PairDesc* h_pairs, int npairs, int max_nq, int stride, cudaStream_t st) {
   State& s = g_state;
   int rc;
-  if ((rc = s.d_top4.ensure(sizeof(int4) * (size_t)npairs * stride))) return rc;
-  if ((rc = s.d_knn.ensure(sizeof(float4) * (size_t)npairs * stride))) return rc;
+  if ((rc = s.W().d_top4.ensure(sizeof(int4) * (size_t)npairs * stride))) return rc;
+  if ((rc = s.W().d_knn.ensure(sizeof(float4) * (size_t)npairs * stride))) return rc;
   std::vector<HamItem> items;
   for (int p = 0; p < npairs; p++) {
     const PairDesc& pd = h_pairs[p];
@@ -153,7 +173,7 @@ static int launch_sift_knn(const PairDesc* d_pairs, const PairDesc* h_pairs, int
       HamItem it;
       it.a = pd.q_i8 + (size_t)m0 * 256;
       it.b = pd.t_i8;
-      it.out = reinterpret_cast<int2*>(reinterpret_cast<int4*>(s.d_top4.ptr) + (size_t)p * stride + m0);
+      it.out = reinterpret_cast<int2*>(reinterpret_cast<int4*>(s.W().d_top4.ptr) + (size_t)p * stride + m0);
       it.nq_valid = pd.nq - m0 < 128 ? pd.nq - m0 : 128;
       it.nsearch = pd.nt;  // FLANN searches every train row (no size-1 quirk on this path)
       it.n_btiles = (pd.nt + 255) / 256;
@@ -162,20 +182,20 @@ static int launch_sift_knn(const PairDesc* d_pairs, const PairDesc* h_pairs, int
       items.push_back(it);
     }
   }
-  cudaEventRecord(s.ev[3], st);
+  cudaEventRecord(s.W().ev[3], st);
   if (!items.empty()) {
-    if ((rc = s.d_items.ensure(sizeof(HamItem) * items.size()))) return rc;
-    if ((rc = s.h_items.ensure(sizeof(HamItem) * items.size()))) return rc;
-    memcpy(s.h_items.ptr, items.data(), sizeof(HamItem) * items.size());
-    cudaError_t e = cudaMemcpyAsync(s.d_items.ptr, s.h_items.ptr, sizeof(HamItem) * items.size(), cudaMemcpyHostToDevice, st);
+    if ((rc = s.W().d_items.ensure(sizeof(HamItem) * items.size()))) return rc;
+    if ((rc = s.W().h_items.ensure(sizeof(HamItem) * items.size()))) return rc;
+    memcpy(s.W().h_items.ptr, items.data(), sizeof(HamItem) * items.size());
+    cudaError_t e = cudaMemcpyAsync(s.W().d_items.ptr, s.W().h_items.ptr, sizeof(HamItem) * items.size(), cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) return cuda_fail(e, "upload l2 items");
-    cudaEventRecord(s.ev[3], st);
-    e = launch_l2_tc((const HamItem*)s.d_items.ptr, (int)items.size(), s.sm_count, st);
+    cudaEventRecord(s.W().ev[3], st);
+    e = launch_l2_tc((const HamItem*)s.W().d_items.ptr, (int)items.size(), s.sm_count, st);
     if (e != cudaSuccess) return cuda_fail(e, "l2 tensor-core kernel");
     s.launches += 1;
   }
-  cudaEventRecord(s.ev[1], st);
-  cudaError_t e = launch_l2_refine(d_pairs, npairs, max_nq, (const int4*)s.d_top4.ptr, stride, (float4*)s.d_knn.ptr, st);
+  cudaEventRecord(s.W().ev[1], st);
+  cudaError_t e = launch_l2_refine(d_pairs, npairs, max_nq, (const int4*)s.W().d_top4.ptr, stride, (float4*)s.W().d_knn.ptr, st);
   if (e != cudaSuccess) return cuda_fail(e, "l2 refine kernel");
   s.launches += 1;
   return 0;
@@ -188,7 +208,7 @@ static int launch_hamming(const PairDesc* d_pairs, const PairDesc* h_pairs, int 
   State& s = g_state;
   cudaError_t e;
   if (s.hamming_path == 0) {
-    cudaEventRecord(s.ev[3], st);
+    cudaEventRecord(s.W().ev[3], st);
     e = launch_hamming_simt(d_pairs, npairs, max_nq, best, stride, st);
   } else {
     std::vector<HamItem> items;
@@ -213,20 +233,20 @@ static int launch_hamming(const PairDesc* d_pairs, const PairDesc* h_pairs, int 
       }
     }
     if (items.empty()) {
-      cudaEventRecord(s.ev[3], st);
-      cudaEventRecord(s.ev[1], st);
+      cudaEventRecord(s.W().ev[3], st);
+      cudaEventRecord(s.W().ev[1], st);
       return 0;
     }
     int rc;
-    if ((rc = s.d_items.ensure(sizeof(HamItem) * items.size()))) return rc;
-    if ((rc = s.h_items.ensure(sizeof(HamItem) * items.size()))) return rc;
-    memcpy(s.h_items.ptr, items.data(), sizeof(HamItem) * items.size());
-    e = cudaMemcpyAsync(s.d_items.ptr, s.h_items.ptr, sizeof(HamItem) * items.size(), cudaMemcpyHostToDevice, st);
+    if ((rc = s.W().d_items.ensure(sizeof(HamItem) * items.size()))) return rc;
+    if ((rc = s.W().h_items.ensure(sizeof(HamItem) * items.size()))) return rc;
+    memcpy(s.W().h_items.ptr, items.data(), sizeof(HamItem) * items.size());
+    e = cudaMemcpyAsync(s.W().d_items.ptr, s.W().h_items.ptr, sizeof(HamItem) * items.size(), cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) return cuda_fail(e, "upload hamming items");
-    cudaEventRecord(s.ev[3], st);
-    e = launch_hamming_tc((const HamItem*)s.d_items.ptr, (int)items.size(), s.sm_count, st);
+    cudaEventRecord(s.W().ev[3], st);
+    e = launch_hamming_tc((const HamItem*)s.W().d_items.ptr, (int)items.size(), s.sm_count, st);
   }
-  cudaEventRecord(s.ev[1], st);
+  cudaEventRecord(s.W().ev[1], st);
   if (e != cudaSuccess) return cuda_fail(e, "hamming kernel");
   s.launches += 1;
   return 0;
@@ -235,7 +255,7 @@ static int launch_hamming(const PairDesc* d_pairs, const PairDesc* h_pairs, int 
 // Core of match_pairs*: h_pairs (device pointers inside) -> results on the host.
 static int run_pairs(const std::vector<PairDesc>& h_pairs, uint64_t seed, int64_t first_pair,
                      rgbdslam_b200_pair_result* results, rgbdslam_b200_dmatch* all_matches,
-                     rgbdslam_b200_dmatch* inlier_matches) {
+                     rgbdslam_b200_dmatch* inlier_matches, bool sync = true) {
   State& s = g_state;
   const int npairs = (int)h_pairs.size();
   if (npairs == 0) return 0;
@@ -251,25 +271,25 @@ static int run_pairs(const std::vector<PairDesc>& h_pairs, uint64_t seed, int64_
   const int maxM = s.params.max_matches;
   const int H = s.params.ransac_iterations;
   int rc;
-  if ((rc = s.d_pairs.ensure(sizeof(PairDesc) * npairs))) return rc;
-  if ((rc = s.h_pairs.ensure(sizeof(PairDesc) * npairs))) return rc;
-  if ((rc = s.d_best.ensure(sizeof(int2) * (size_t)npairs * stride))) return rc;
-  if ((rc = s.d_matches.ensure(sizeof(rgbdslam_b200_dmatch) * (size_t)npairs * maxM))) return rc;
-  if ((rc = s.d_inliers.ensure(sizeof(rgbdslam_b200_dmatch) * (size_t)npairs * maxM))) return rc;
-  if ((rc = s.d_mfrom.ensure(sizeof(float4) * (size_t)npairs * maxM))) return rc;
-  if ((rc = s.d_mto.ensure(sizeof(float4) * (size_t)npairs * maxM))) return rc;
-  if ((rc = s.d_nall.ensure(sizeof(int32_t) * npairs))) return rc;
-  if ((rc = s.d_hyp.ensure(sizeof(HypResult) * (size_t)npairs * (H > 0 ? H : 1)))) return rc;
-  if ((rc = s.d_results.ensure(sizeof(rgbdslam_b200_pair_result) * npairs))) return rc;
+  if ((rc = s.W().d_pairs.ensure(sizeof(PairDesc) * npairs))) return rc;
+  if ((rc = s.W().h_pairs.ensure(sizeof(PairDesc) * npairs))) return rc;
+  if ((rc = s.W().d_best.ensure(sizeof(int2) * (size_t)npairs * stride))) return rc;
+  if ((rc = s.W().d_matches.ensure(sizeof(rgbdslam_b200_dmatch) * (size_t)npairs * maxM))) return rc;
+  if ((rc = s.W().d_inliers.ensure(sizeof(rgbdslam_b200_dmatch) * (size_t)npairs * maxM))) return rc;
+  if ((rc = s.W().d_mfrom.ensure(sizeof(float4) * (size_t)npairs * maxM))) return rc;
+  if ((rc = s.W().d_mto.ensure(sizeof(float4) * (size_t)npairs * maxM))) return rc;
+  if ((rc = s.W().d_nall.ensure(sizeof(int32_t) * npairs))) return rc;
+  if ((rc = s.W().d_hyp.ensure(sizeof(HypResult) * (size_t)npairs * (H > 0 ? H : 1)))) return rc;
+  if ((rc = s.W().d_results.ensure(sizeof(rgbdslam_b200_pair_result) * npairs))) return rc;
 
-  cudaStream_t st = s.stream;
+  cudaStream_t st = s.W().stream;
   cudaError_t e;
-  memcpy(s.h_pairs.ptr, h_pairs.data(), sizeof(PairDesc) * npairs);
-  e = cudaMemcpyAsync(s.d_pairs.ptr, s.h_pairs.ptr, sizeof(PairDesc) * npairs, cudaMemcpyHostToDevice, st);
+  memcpy(s.W().h_pairs.ptr, h_pairs.data(), sizeof(PairDesc) * npairs);
+  e = cudaMemcpyAsync(s.W().d_pairs.ptr, s.W().h_pairs.ptr, sizeof(PairDesc) * npairs, cudaMemcpyHostToDevice, st);
   if (e != cudaSuccess) return cuda_fail(e, "upload pair table");
-  const PairDesc* d_pairs = (const PairDesc*)s.d_pairs.ptr;
+  const PairDesc* d_pairs = (const PairDesc*)s.W().d_pairs.ptr;
 
-  cudaEventRecord(s.ev[0], st);
+  cudaEventRecord(s.W().ev[0], st);
   bool any_sift = false, any_orb = false;
   for (const PairDesc& pd : h_pairs) (pd.q_f32 ? any_sift : any_orb) = true;
   if (any_sift && any_orb) {
@@ -278,17 +298,17 @@ static int run_pairs(const std::vector<PairDesc>& h_pairs, uint64_t seed, int64_
   }
   if (any_sift) {
     if ((rc = launch_sift_knn(d_pairs, h_pairs.data(), npairs, max_nq, stride, st))) return rc;
-    e = launch_select_sift(d_pairs, npairs, (const float4*)s.d_knn.ptr, stride, (float)s.params.nn_distance_ratio, maxM,
-                           (rgbdslam_b200_dmatch*)s.d_matches.ptr, (float4*)s.d_mfrom.ptr, (float4*)s.d_mto.ptr,
-                           (int32_t*)s.d_nall.ptr, st);
+    e = launch_select_sift(d_pairs, npairs, (const float4*)s.W().d_knn.ptr, stride, (float)s.params.nn_distance_ratio, maxM,
+                           (rgbdslam_b200_dmatch*)s.W().d_matches.ptr, (float4*)s.W().d_mfrom.ptr, (float4*)s.W().d_mto.ptr,
+                           (int32_t*)s.W().d_nall.ptr, st);
     if (e != cudaSuccess) return cuda_fail(e, "select_sift kernel");
     s.launches += 1;
   } else {
     // launch_hamming records ev[3] / ev[1] immediately around the kernel
-    if ((rc = launch_hamming(d_pairs, h_pairs.data(), npairs, max_nq, (int2*)s.d_best.ptr, stride, st))) return rc;
-    e = launch_select_matches(d_pairs, npairs, (const int2*)s.d_best.ptr, stride, seed, first_pair,
-                              (rgbdslam_b200_dmatch*)s.d_matches.ptr, (float4*)s.d_mfrom.ptr, (float4*)s.d_mto.ptr,
-                              (int32_t*)s.d_nall.ptr, max_nq, st);
+    if ((rc = launch_hamming(d_pairs, h_pairs.data(), npairs, max_nq, (int2*)s.W().d_best.ptr, stride, st))) return rc;
+    e = launch_select_matches(d_pairs, npairs, (const int2*)s.W().d_best.ptr, stride, seed, first_pair,
+                              (rgbdslam_b200_dmatch*)s.W().d_matches.ptr, (float4*)s.W().d_mfrom.ptr, (float4*)s.W().d_mto.ptr,
+                              (int32_t*)s.W().d_nall.ptr, max_nq, st);
     if (e != cudaSuccess) return cuda_fail(e, "select_matches kernel");
     s.launches += 1;
   }
@@ -298,15 +318,15 @@ static int run_pairs(const std::vector<PairDesc>& h_pairs, uint64_t seed, int64_
     // correspondence errorFunction2 would see -- first pair that reaches RANSAC, first sorted match with
     // non-zero, non-NaN depth on both sides (node.cpp:994, misc.cpp:711-716).
     std::vector<int32_t> nall(npairs);
-    e = cudaMemcpyAsync(nall.data(), s.d_nall.ptr, sizeof(int32_t) * npairs, cudaMemcpyDeviceToHost, st);
+    e = cudaMemcpyAsync(nall.data(), s.W().d_nall.ptr, sizeof(int32_t) * npairs, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return cuda_fail(e, "z0 latch (n_all)");
     for (int p = 0; p < npairs && s.z0 == 0.0; p++) {
       if (nall[p] <= s.params.min_matches) continue;
       std::vector<float4> f(nall[p]), t(nall[p]);
-      cudaMemcpyAsync(f.data(), (float4*)s.d_mfrom.ptr + (size_t)p * maxM, sizeof(float4) * nall[p],
+      cudaMemcpyAsync(f.data(), (float4*)s.W().d_mfrom.ptr + (size_t)p * maxM, sizeof(float4) * nall[p],
                       cudaMemcpyDeviceToHost, st);
-      cudaMemcpyAsync(t.data(), (float4*)s.d_mto.ptr + (size_t)p * maxM, sizeof(float4) * nall[p],
+      cudaMemcpyAsync(t.data(), (float4*)s.W().d_mto.ptr + (size_t)p * maxM, sizeof(float4) * nall[p],
                       cudaMemcpyDeviceToHost, st);
       e = cudaStreamSynchronize(st);
       if (e != cudaSuccess) return cuda_fail(e, "z0 latch (points)");
@@ -321,35 +341,39 @@ static int run_pairs(const std::vector<PairDesc>& h_pairs, uint64_t seed, int64_
   }
 
   int hyp_launches = 0;
-  e = launch_ransac_hypotheses(npairs, H, maxM, seed, first_pair, (const float4*)s.d_mfrom.ptr,
-                               (const float4*)s.d_mto.ptr, (const int32_t*)s.d_nall.ptr, (HypResult*)s.d_hyp.ptr, st,
+  e = launch_ransac_hypotheses(npairs, H, maxM, seed, first_pair, (const float4*)s.W().d_mfrom.ptr,
+                               (const float4*)s.W().d_mto.ptr, (const int32_t*)s.W().d_nall.ptr, (HypResult*)s.W().d_hyp.ptr, st,
                                &hyp_launches);
   if (e != cudaSuccess) return cuda_fail(e, "ransac_hyp kernel");
-  e = launch_ransac_select(d_pairs, npairs, H, maxM, (const float4*)s.d_mfrom.ptr, (const float4*)s.d_mto.ptr,
-                           (const int32_t*)s.d_nall.ptr, (const rgbdslam_b200_dmatch*)s.d_matches.ptr,
-                           (const HypResult*)s.d_hyp.ptr, (rgbdslam_b200_pair_result*)s.d_results.ptr,
-                           (rgbdslam_b200_dmatch*)s.d_inliers.ptr, st);
+  e = launch_ransac_select(d_pairs, npairs, H, maxM, (const float4*)s.W().d_mfrom.ptr, (const float4*)s.W().d_mto.ptr,
+                           (const int32_t*)s.W().d_nall.ptr, (const rgbdslam_b200_dmatch*)s.W().d_matches.ptr,
+                           (const HypResult*)s.W().d_hyp.ptr, (rgbdslam_b200_pair_result*)s.W().d_results.ptr,
+                           (rgbdslam_b200_dmatch*)s.W().d_inliers.ptr, st);
   if (e != cudaSuccess) return cuda_fail(e, "ransac_select kernel");
   s.launches += 1 + hyp_launches;
-  cudaEventRecord(s.ev[2], st);
+  cudaEventRecord(s.W().ev[2], st);
 
   if (results) {
-    e = cudaMemcpyAsync(results, s.d_results.ptr, sizeof(rgbdslam_b200_pair_result) * npairs, cudaMemcpyDeviceToHost, st);
+    e = cudaMemcpyAsync(results, s.W().d_results.ptr, sizeof(rgbdslam_b200_pair_result) * npairs, cudaMemcpyDeviceToHost, st);
     if (e != cudaSuccess) return cuda_fail(e, "download results");
   }
   if (all_matches) {
-    e = cudaMemcpyAsync(all_matches, s.d_matches.ptr, sizeof(rgbdslam_b200_dmatch) * (size_t)npairs * maxM,
+    e = cudaMemcpyAsync(all_matches, s.W().d_matches.ptr, sizeof(rgbdslam_b200_dmatch) * (size_t)npairs * maxM,
                         cudaMemcpyDeviceToHost, st);
     if (e != cudaSuccess) return cuda_fail(e, "download all_matches");
   }
   if (inlier_matches) {
-    e = cudaMemcpyAsync(inlier_matches, s.d_inliers.ptr, sizeof(rgbdslam_b200_dmatch) * (size_t)npairs * maxM,
+    e = cudaMemcpyAsync(inlier_matches, s.W().d_inliers.ptr, sizeof(rgbdslam_b200_dmatch) * (size_t)npairs * maxM,
                         cudaMemcpyDeviceToHost, st);
     if (e != cudaSuccess) return cuda_fail(e, "download inlier_matches");
   }
-  e = cudaStreamSynchronize(st);
-  if (e != cudaSuccess) return cuda_fail(e, "match_pairs synchronize");
-  s.timing_valid = true;
+  s.W().timing_valid = true;
+  s.W().pending = true;
+  if (sync) {
+    e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return cuda_fail(e, "match_pairs synchronize");
+    s.W().pending = false;
+  }
   return 0;
 }
 
@@ -412,11 +436,18 @@ int rgbdslam_b200_init(int device, const rgbdslam_b200_params* p) {
   if (!s.inited) {
     e = cudaStreamCreateWithFlags(&s.own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
-    for (int i = 0; i < 4; i++) {
-      e = cudaEventCreate(&s.ev[i]);
-      if (e != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
+    for (int k = 0; k < kSlots; k++) {
+      for (int i = 0; i < 4; i++) {
+        e = cudaEventCreate(&s.ws[k].ev[i]);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
+      }
+      if (k > 0) {
+        e = cudaStreamCreateWithFlags(&s.ws[k].stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaStreamCreate(slot)");
+      }
     }
     s.stream = s.own_stream;
+    s.ws[0].stream = s.stream;
     s.launches = 0;
   }
   s.device = device;
@@ -424,7 +455,7 @@ int rgbdslam_b200_init(int device, const rgbdslam_b200_params* p) {
   s.params = prm;
   s.z0 = prm.depth_cov_z0 > 0 ? prm.depth_cov_z0 : 0.0;
   s.inited = true;
-  s.timing_valid = false;
+  s.W().timing_valid = false;
   int rc = push_dev_params();
   if (rc) return rc;
   e = cudaStreamSynchronize(s.stream);
@@ -439,7 +470,10 @@ int rgbdslam_b200_shutdown(void) {
   cudaSetDevice(s.device);
   cudaDeviceSynchronize();
   s.release_workspaces();
-  for (int i = 0; i < 4; i++) cudaEventDestroy(s.ev[i]);
+  for (int k = 0; k < kSlots; k++) {
+    for (int i = 0; i < 4; i++) cudaEventDestroy(s.ws[k].ev[i]);
+    if (k > 0) cudaStreamDestroy(s.ws[k].stream);
+  }
   cudaStreamDestroy(s.own_stream);
   s.inited = false;
   return 0;
@@ -476,16 +510,29 @@ int64_t rgbdslam_b200_launch_count(void) { return g_state.launches; }
 double rgbdslam_b200_depth_cov_z0(void) { return g_state.z0; }
 
 int rgbdslam_b200_last_timing(float* hamming_ms, float* total_device_ms) {
+  return rgbdslam_b200_last_timing_slot(0, hamming_ms, total_device_ms);
+}
+
+int rgbdslam_b200_last_timing_slot(int slot, float* hamming_ms, float* total_device_ms) {
   std::lock_guard<std::mutex> lk(g_state.mu);
   int rc = check_inited();
   if (rc) return rc;
-  if (!g_state.timing_valid) {
+  if (slot < 0 || slot >= kSlots) {
+    set_error("slot out of range [0,4)");
+    return RGBDSLAM_B200_ERR_ARG;
+  }
+  g_state.cur = &g_state.ws[slot];
+  if (g_state.cur->pending) {
+    set_error("last_timing_slot: the slot still has work in flight (call match_pairs_wait first)");
+    return RGBDSLAM_B200_ERR_STATE;
+  }
+  if (!g_state.W().timing_valid) {
     set_error("no match_pairs call has completed yet");
     return RGBDSLAM_B200_ERR_STATE;
   }
   float a = 0, b = 0;
-  cudaError_t e = cudaEventElapsedTime(&a, g_state.ev[3], g_state.ev[1]);
-  if (e == cudaSuccess) e = cudaEventElapsedTime(&b, g_state.ev[0], g_state.ev[2]);
+  cudaError_t e = cudaEventElapsedTime(&a, g_state.W().ev[3], g_state.W().ev[1]);
+  if (e == cudaSuccess) e = cudaEventElapsedTime(&b, g_state.W().ev[0], g_state.W().ev[2]);
   if (e != cudaSuccess) return cuda_fail(e, "cudaEventElapsedTime");
   if (hamming_ms) *hamming_ms = a;
   if (total_device_ms) *total_device_ms = b;
@@ -507,18 +554,18 @@ int rgbdslam_b200_brute_force_orb(const uint64_t* q, int nq, const uint64_t* t, 
   }
   State& s = g_state;
   const int stride = (nq + 127) / 128 * 128 + 128;
-  if ((rc = s.d_feat_a.ensure(32 * (size_t)nq))) return rc;
-  if ((rc = s.d_feat_b.ensure(32 * (size_t)(nt > 0 ? nt : 1)))) return rc;
-  if ((rc = s.d_best.ensure(sizeof(int2) * (size_t)stride))) return rc;
-  if ((rc = s.d_pairs.ensure(sizeof(PairDesc)))) return rc;
-  if ((rc = s.h_pairs.ensure(sizeof(PairDesc)))) return rc;
+  if ((rc = s.W().d_feat_a.ensure(32 * (size_t)nq))) return rc;
+  if ((rc = s.W().d_feat_b.ensure(32 * (size_t)(nt > 0 ? nt : 1)))) return rc;
+  if ((rc = s.W().d_best.ensure(sizeof(int2) * (size_t)stride))) return rc;
+  if ((rc = s.W().d_pairs.ensure(sizeof(PairDesc)))) return rc;
+  if ((rc = s.W().h_pairs.ensure(sizeof(PairDesc)))) return rc;
   cudaStream_t st = s.stream;
-  cudaError_t e = cudaMemcpyAsync(s.d_feat_a.ptr, q, 32 * (size_t)nq, cudaMemcpyHostToDevice, st);
-  if (e == cudaSuccess && nt > 0) e = cudaMemcpyAsync(s.d_feat_b.ptr, t, 32 * (size_t)nt, cudaMemcpyHostToDevice, st);
+  cudaError_t e = cudaMemcpyAsync(s.W().d_feat_a.ptr, q, 32 * (size_t)nq, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && nt > 0) e = cudaMemcpyAsync(s.W().d_feat_b.ptr, t, 32 * (size_t)nt, cudaMemcpyHostToDevice, st);
   if (e != cudaSuccess) return cuda_fail(e, "brute_force_orb upload");
   PairDesc pd;
-  pd.q_desc = (const uint32_t*)s.d_feat_a.ptr;
-  pd.t_desc = (const uint32_t*)s.d_feat_b.ptr;
+  pd.q_desc = (const uint32_t*)s.W().d_feat_a.ptr;
+  pd.t_desc = (const uint32_t*)s.W().d_feat_b.ptr;
   pd.q_xyz = nullptr;
   pd.t_xyz = nullptr;
   pd.nq = nq;
@@ -527,21 +574,21 @@ int rgbdslam_b200_brute_force_orb(const uint64_t* q, int nq, const uint64_t* t, 
   pd.q_i8 = pd.t_i8 = nullptr;
   pd.q_f32 = pd.t_f32 = pd.t_norm = nullptr;
   if (s.hamming_path != 0) {
-    if ((rc = s.d_i8_a.ensure(256 * (size_t)pad256(nq)))) return rc;
-    if ((rc = s.d_i8_b.ensure(256 * (size_t)pad256(nt)))) return rc;
+    if ((rc = s.W().d_i8_a.ensure(256 * (size_t)pad256(nq)))) return rc;
+    if ((rc = s.W().d_i8_b.ensure(256 * (size_t)pad256(nt)))) return rc;
     std::vector<ExpandJob> jobs(2);
-    jobs[0] = {(const uint8_t*)s.d_feat_a.ptr, (int8_t*)s.d_i8_a.ptr, nq, pad256(nq)};
-    jobs[1] = {(const uint8_t*)s.d_feat_b.ptr, (int8_t*)s.d_i8_b.ptr, nt, pad256(nt)};
+    jobs[0] = {(const uint8_t*)s.W().d_feat_a.ptr, (int8_t*)s.W().d_i8_a.ptr, nq, pad256(nq)};
+    jobs[1] = {(const uint8_t*)s.W().d_feat_b.ptr, (int8_t*)s.W().d_i8_b.ptr, nt, pad256(nt)};
     if ((rc = expand_nodes(jobs))) return rc;
-    pd.q_i8 = (const int8_t*)s.d_i8_a.ptr;
-    pd.t_i8 = (const int8_t*)s.d_i8_b.ptr;
+    pd.q_i8 = (const int8_t*)s.W().d_i8_a.ptr;
+    pd.t_i8 = (const int8_t*)s.W().d_i8_b.ptr;
   }
-  memcpy(s.h_pairs.ptr, &pd, sizeof(pd));
-  e = cudaMemcpyAsync(s.d_pairs.ptr, s.h_pairs.ptr, sizeof(pd), cudaMemcpyHostToDevice, st);
+  memcpy(s.W().h_pairs.ptr, &pd, sizeof(pd));
+  e = cudaMemcpyAsync(s.W().d_pairs.ptr, s.W().h_pairs.ptr, sizeof(pd), cudaMemcpyHostToDevice, st);
   if (e != cudaSuccess) return cuda_fail(e, "brute_force_orb pair upload");
-  if ((rc = launch_hamming((const PairDesc*)s.d_pairs.ptr, &pd, 1, nq, (int2*)s.d_best.ptr, stride, st))) return rc;
+  if ((rc = launch_hamming((const PairDesc*)s.W().d_pairs.ptr, &pd, 1, nq, (int2*)s.W().d_best.ptr, stride, st))) return rc;
   std::vector<int2> h(nq);
-  e = cudaMemcpyAsync(h.data(), s.d_best.ptr, sizeof(int2) * nq, cudaMemcpyDeviceToHost, st);
+  e = cudaMemcpyAsync(h.data(), s.W().d_best.ptr, sizeof(int2) * nq, cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) return cuda_fail(e, "brute_force_orb download");
   for (int i = 0; i < nq; i++) {
@@ -656,12 +703,13 @@ int rgbdslam_b200_node_destroy(uint64_t node_handle) {
   return 0;
 }
 
-int rgbdslam_b200_match_pairs(const uint64_t* newer, const uint64_t* older, int npairs, uint64_t seed,
-                              int64_t first_pair_index, rgbdslam_b200_pair_result* results,
-                              rgbdslam_b200_dmatch* all_matches, rgbdslam_b200_dmatch* inlier_matches) {
+static int match_pairs_impl(int slot, bool sync, const uint64_t* newer, const uint64_t* older, int npairs, uint64_t seed,
+                            int64_t first_pair_index, rgbdslam_b200_pair_result* results,
+                            rgbdslam_b200_dmatch* all_matches, rgbdslam_b200_dmatch* inlier_matches) {
   std::lock_guard<std::mutex> lk(g_state.mu);
   int rc = check_inited();
   if (rc) return rc;
+  if ((rc = use_slot(slot))) return rc;
   if (npairs < 0 || (npairs > 0 && (!newer || !older || !results))) {
     set_error("match_pairs: bad arguments");
     return RGBDSLAM_B200_ERR_ARG;
@@ -689,17 +737,45 @@ int rgbdslam_b200_match_pairs(const uint64_t* newer, const uint64_t* older, int 
       return RGBDSLAM_B200_ERR_ARG;
     }
   }
-  return run_pairs(pairs, seed, first_pair_index, results, all_matches, inlier_matches);
+  return run_pairs(pairs, seed, first_pair_index, results, all_matches, inlier_matches, sync);
 }
 
-int rgbdslam_b200_match_pairs_host(const uint8_t* desc_newer, const float* xyz_newer, const int32_t* n_newer,
-                                   const uint8_t* desc_older, const float* xyz_older, const int32_t* n_older,
-                                   const int32_t* id_newer, const int32_t* id_older, int npairs, uint64_t seed,
-                                   int64_t first_pair_index, rgbdslam_b200_pair_result* results,
-                                   rgbdslam_b200_dmatch* all_matches, rgbdslam_b200_dmatch* inlier_matches) {
+int rgbdslam_b200_match_pairs(const uint64_t* newer, const uint64_t* older, int npairs, uint64_t seed,
+                              int64_t first_pair_index, rgbdslam_b200_pair_result* results,
+                              rgbdslam_b200_dmatch* all_matches, rgbdslam_b200_dmatch* inlier_matches) {
+  return match_pairs_impl(0, true, newer, older, npairs, seed, first_pair_index, results, all_matches, inlier_matches);
+}
+
+int rgbdslam_b200_match_pairs_submit(int slot, const uint64_t* newer, const uint64_t* older, int npairs, uint64_t seed,
+                                     int64_t first_pair_index, rgbdslam_b200_pair_result* results,
+                                     rgbdslam_b200_dmatch* all_matches, rgbdslam_b200_dmatch* inlier_matches) {
+  return match_pairs_impl(slot, false, newer, older, npairs, seed, first_pair_index, results, all_matches, inlier_matches);
+}
+
+int rgbdslam_b200_match_pairs_wait(int slot) {
   std::lock_guard<std::mutex> lk(g_state.mu);
   int rc = check_inited();
   if (rc) return rc;
+  if (slot < 0 || slot >= kSlots) {
+    set_error("slot out of range [0,4)");
+    return RGBDSLAM_B200_ERR_ARG;
+  }
+  Workspace& w = g_state.ws[slot];
+  cudaError_t e = cudaStreamSynchronize(slot == 0 ? g_state.stream : w.stream);
+  if (e != cudaSuccess) return cuda_fail(e, "match_pairs_wait");
+  w.pending = false;
+  return 0;
+}
+
+static int match_pairs_host_impl(int slot, bool sync, const uint8_t* desc_newer, const float* xyz_newer, const int32_t* n_newer,
+                                 const uint8_t* desc_older, const float* xyz_older, const int32_t* n_older,
+                                 const int32_t* id_newer, const int32_t* id_older, int npairs, uint64_t seed,
+                                 int64_t first_pair_index, rgbdslam_b200_pair_result* results,
+                                 rgbdslam_b200_dmatch* all_matches, rgbdslam_b200_dmatch* inlier_matches) {
+  std::lock_guard<std::mutex> lk(g_state.mu);
+  int rc = check_inited();
+  if (rc) return rc;
+  if ((rc = use_slot(slot))) return rc;
   if (npairs < 0 || (npairs > 0 && (!n_newer || !n_older || !results))) {
     set_error("match_pairs_host: bad arguments");
     return RGBDSLAM_B200_ERR_ARG;
@@ -719,19 +795,19 @@ int rgbdslam_b200_match_pairs_host(const uint8_t* desc_newer, const float* xyz_n
     set_error("match_pairs_host: null feature buffer");
     return RGBDSLAM_B200_ERR_ARG;
   }
-  if ((rc = s.d_feat_a.ensure(32 * (tot_n + 1)))) return rc;
-  if ((rc = s.d_feat_b.ensure(32 * (tot_o + 1)))) return rc;
-  if ((rc = s.d_xyz_a.ensure(16 * (tot_n + 1)))) return rc;
-  if ((rc = s.d_xyz_b.ensure(16 * (tot_o + 1)))) return rc;
-  cudaStream_t st = s.stream;
+  if ((rc = s.W().d_feat_a.ensure(32 * (tot_n + 1)))) return rc;
+  if ((rc = s.W().d_feat_b.ensure(32 * (tot_o + 1)))) return rc;
+  if ((rc = s.W().d_xyz_a.ensure(16 * (tot_n + 1)))) return rc;
+  if ((rc = s.W().d_xyz_b.ensure(16 * (tot_o + 1)))) return rc;
+  cudaStream_t st = s.W().stream;
   cudaError_t e = cudaSuccess;
   if (tot_n) {
-    e = cudaMemcpyAsync(s.d_feat_a.ptr, desc_newer, 32 * tot_n, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(s.d_xyz_a.ptr, xyz_newer, 16 * tot_n, cudaMemcpyHostToDevice, st);
+    e = cudaMemcpyAsync(s.W().d_feat_a.ptr, desc_newer, 32 * tot_n, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(s.W().d_xyz_a.ptr, xyz_newer, 16 * tot_n, cudaMemcpyHostToDevice, st);
   }
   if (e == cudaSuccess && tot_o) {
-    e = cudaMemcpyAsync(s.d_feat_b.ptr, desc_older, 32 * tot_o, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(s.d_xyz_b.ptr, xyz_older, 16 * tot_o, cudaMemcpyHostToDevice, st);
+    e = cudaMemcpyAsync(s.W().d_feat_b.ptr, desc_older, 32 * tot_o, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(s.W().d_xyz_b.ptr, xyz_older, 16 * tot_o, cudaMemcpyHostToDevice, st);
   }
   if (e != cudaSuccess) return cuda_fail(e, "match_pairs_host upload");
   std::vector<PairDesc> pairs(npairs);
@@ -743,8 +819,8 @@ int rgbdslam_b200_match_pairs_host(const uint8_t* desc_newer, const float* xyz_n
       rows_n += pad256(n_newer[i]);
       rows_o += pad256(n_older[i]);
     }
-    if ((rc = s.d_i8_a.ensure(256 * rows_n))) return rc;
-    if ((rc = s.d_i8_b.ensure(256 * rows_o))) return rc;
+    if ((rc = s.W().d_i8_a.ensure(256 * rows_n))) return rc;
+    if ((rc = s.W().d_i8_b.ensure(256 * rows_o))) return rc;
   }
   std::vector<ExpandJob> jobs;
   if (tc) jobs.reserve(2 * (size_t)npairs);
@@ -752,17 +828,17 @@ int rgbdslam_b200_match_pairs_host(const uint8_t* desc_newer, const float* xyz_n
     pairs[i].q_i8 = pairs[i].t_i8 = nullptr;
     pairs[i].q_f32 = pairs[i].t_f32 = pairs[i].t_norm = nullptr;
     if (tc) {
-      pairs[i].q_i8 = (const int8_t*)s.d_i8_a.ptr + 256 * pn;
-      pairs[i].t_i8 = (const int8_t*)s.d_i8_b.ptr + 256 * po;
-      jobs.push_back({(const uint8_t*)s.d_feat_a.ptr + 32 * on, (int8_t*)s.d_i8_a.ptr + 256 * pn, n_newer[i], pad256(n_newer[i])});
-      jobs.push_back({(const uint8_t*)s.d_feat_b.ptr + 32 * oo, (int8_t*)s.d_i8_b.ptr + 256 * po, n_older[i], pad256(n_older[i])});
+      pairs[i].q_i8 = (const int8_t*)s.W().d_i8_a.ptr + 256 * pn;
+      pairs[i].t_i8 = (const int8_t*)s.W().d_i8_b.ptr + 256 * po;
+      jobs.push_back({(const uint8_t*)s.W().d_feat_a.ptr + 32 * on, (int8_t*)s.W().d_i8_a.ptr + 256 * pn, n_newer[i], pad256(n_newer[i])});
+      jobs.push_back({(const uint8_t*)s.W().d_feat_b.ptr + 32 * oo, (int8_t*)s.W().d_i8_b.ptr + 256 * po, n_older[i], pad256(n_older[i])});
       pn += pad256(n_newer[i]);
       po += pad256(n_older[i]);
     }
-    pairs[i].q_desc = (const uint32_t*)((const uint8_t*)s.d_feat_a.ptr + 32 * on);
-    pairs[i].t_desc = (const uint32_t*)((const uint8_t*)s.d_feat_b.ptr + 32 * oo);
-    pairs[i].q_xyz = (const float4*)s.d_xyz_a.ptr + on;
-    pairs[i].t_xyz = (const float4*)s.d_xyz_b.ptr + oo;
+    pairs[i].q_desc = (const uint32_t*)((const uint8_t*)s.W().d_feat_a.ptr + 32 * on);
+    pairs[i].t_desc = (const uint32_t*)((const uint8_t*)s.W().d_feat_b.ptr + 32 * oo);
+    pairs[i].q_xyz = (const float4*)s.W().d_xyz_a.ptr + on;
+    pairs[i].t_xyz = (const float4*)s.W().d_xyz_b.ptr + oo;
     pairs[i].nq = n_newer[i];
     pairs[i].nt = n_older[i];
     pairs[i].id_q = id_newer ? id_newer[i] : i;
@@ -771,7 +847,25 @@ int rgbdslam_b200_match_pairs_host(const uint8_t* desc_newer, const float* xyz_n
     oo += n_older[i];
   }
   if (tc && (rc = expand_nodes(jobs))) return rc;
-  return run_pairs(pairs, seed, first_pair_index, results, all_matches, inlier_matches);
+  return run_pairs(pairs, seed, first_pair_index, results, all_matches, inlier_matches, sync);
+}
+
+int rgbdslam_b200_match_pairs_host(const uint8_t* desc_newer, const float* xyz_newer, const int32_t* n_newer,
+                                   const uint8_t* desc_older, const float* xyz_older, const int32_t* n_older,
+                                   const int32_t* id_newer, const int32_t* id_older, int npairs, uint64_t seed,
+                                   int64_t first_pair_index, rgbdslam_b200_pair_result* results,
+                                   rgbdslam_b200_dmatch* all_matches, rgbdslam_b200_dmatch* inlier_matches) {
+  return match_pairs_host_impl(0, true, desc_newer, xyz_newer, n_newer, desc_older, xyz_older, n_older, id_newer, id_older, npairs,
+                               seed, first_pair_index, results, all_matches, inlier_matches);
+}
+
+int rgbdslam_b200_match_pairs_host_submit(int slot, const uint8_t* desc_newer, const float* xyz_newer, const int32_t* n_newer,
+                                          const uint8_t* desc_older, const float* xyz_older, const int32_t* n_older,
+                                          const int32_t* id_newer, const int32_t* id_older, int npairs, uint64_t seed,
+                                          int64_t first_pair_index, rgbdslam_b200_pair_result* results,
+                                          rgbdslam_b200_dmatch* all_matches, rgbdslam_b200_dmatch* inlier_matches) {
+  return match_pairs_host_impl(slot, false, desc_newer, xyz_newer, n_newer, desc_older, xyz_older, n_older, id_newer, id_older,
+                               npairs, seed, first_pair_index, results, all_matches, inlier_matches);
 }
 
 int rgbdslam_b200_node_create_from_sift(int32_t id, const float* desc128, const float* xyz1, int n, uint64_t* node_handle) {
@@ -824,33 +918,33 @@ int rgbdslam_b200_knn2_l2(const float* q, int nq, const float* t, int nt, int32_
   const int stride = (nq + 127) / 128 * 128 + 128;
   if ((rc = s.d_f32_a.ensure(512 * (size_t)nq)) || (rc = s.d_f32_b.ensure(512 * (size_t)(nt > 0 ? nt : 1))) ||
       (rc = s.d_root_a.ensure(512 * (size_t)pq)) || (rc = s.d_root_b.ensure(512 * (size_t)pt)) ||
-      (rc = s.d_i8_a.ensure(256 * (size_t)pq)) || (rc = s.d_i8_b.ensure(256 * (size_t)pt)) ||
+      (rc = s.W().d_i8_a.ensure(256 * (size_t)pq)) || (rc = s.W().d_i8_b.ensure(256 * (size_t)pt)) ||
       (rc = s.d_norm_a.ensure(4 * (size_t)pq)) || (rc = s.d_norm_b.ensure(4 * (size_t)pt)) ||
-      (rc = s.d_pairs.ensure(sizeof(PairDesc))) || (rc = s.h_pairs.ensure(sizeof(PairDesc))))
+      (rc = s.W().d_pairs.ensure(sizeof(PairDesc))) || (rc = s.W().h_pairs.ensure(sizeof(PairDesc))))
     return rc;
   cudaStream_t st = s.stream;
   cudaError_t e = cudaMemcpyAsync(s.d_f32_a.ptr, q, 512 * (size_t)nq, cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess && nt > 0) e = cudaMemcpyAsync(s.d_f32_b.ptr, t, 512 * (size_t)nt, cudaMemcpyHostToDevice, st);
   if (e != cudaSuccess) return cuda_fail(e, "knn2_l2 upload");
   std::vector<SiftJob> jobs(2);
-  jobs[0] = {(const float*)s.d_f32_a.ptr, (float*)s.d_root_a.ptr, (uint16_t*)s.d_i8_a.ptr, (float*)s.d_norm_a.ptr, nq, pq};
-  jobs[1] = {(const float*)s.d_f32_b.ptr, (float*)s.d_root_b.ptr, (uint16_t*)s.d_i8_b.ptr, (float*)s.d_norm_b.ptr, nt, pt};
+  jobs[0] = {(const float*)s.d_f32_a.ptr, (float*)s.d_root_a.ptr, (uint16_t*)s.W().d_i8_a.ptr, (float*)s.d_norm_a.ptr, nq, pq};
+  jobs[1] = {(const float*)s.d_f32_b.ptr, (float*)s.d_root_b.ptr, (uint16_t*)s.W().d_i8_b.ptr, (float*)s.d_norm_b.ptr, nt, pt};
   if ((rc = prepare_sift_nodes(jobs))) return rc;
   PairDesc pd;
   memset(&pd, 0, sizeof(pd));
   pd.nq = nq;
   pd.nt = nt;
-  pd.q_i8 = (const int8_t*)s.d_i8_a.ptr;
-  pd.t_i8 = (const int8_t*)s.d_i8_b.ptr;
+  pd.q_i8 = (const int8_t*)s.W().d_i8_a.ptr;
+  pd.t_i8 = (const int8_t*)s.W().d_i8_b.ptr;
   pd.q_f32 = (const float*)s.d_root_a.ptr;
   pd.t_f32 = (const float*)s.d_root_b.ptr;
   pd.t_norm = (const float*)s.d_norm_b.ptr;
-  memcpy(s.h_pairs.ptr, &pd, sizeof(pd));
-  e = cudaMemcpyAsync(s.d_pairs.ptr, s.h_pairs.ptr, sizeof(pd), cudaMemcpyHostToDevice, st);
+  memcpy(s.W().h_pairs.ptr, &pd, sizeof(pd));
+  e = cudaMemcpyAsync(s.W().d_pairs.ptr, s.W().h_pairs.ptr, sizeof(pd), cudaMemcpyHostToDevice, st);
   if (e != cudaSuccess) return cuda_fail(e, "knn2_l2 pair upload");
-  if ((rc = launch_sift_knn((const PairDesc*)s.d_pairs.ptr, &pd, 1, nq, stride, st))) return rc;
+  if ((rc = launch_sift_knn((const PairDesc*)s.W().d_pairs.ptr, &pd, 1, nq, stride, st))) return rc;
   std::vector<float4> h(nq);
-  e = cudaMemcpyAsync(h.data(), s.d_knn.ptr, sizeof(float4) * nq, cudaMemcpyDeviceToHost, st);
+  e = cudaMemcpyAsync(h.data(), s.W().d_knn.ptr, sizeof(float4) * nq, cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) return cuda_fail(e, "knn2_l2 download");
   for (int i = 0; i < nq; i++) {

@@ -38,6 +38,27 @@ struct NodeDev {
   int32_t n_pad = 0;
 };
 
+constexpr int kSlots = 4;  // independent in-flight match_pairs pipelines (stream + workspace each)
+
+struct Workspace {
+  cudaStream_t stream = nullptr;  // slot 0: the library / user stream; slots 1..: own non-blocking streams
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  bool timing_valid = false;
+  bool pending = false;
+  DevBuf d_pairs, d_best, d_matches, d_inliers, d_mfrom, d_mto, d_nall, d_hyp, d_results;
+  DevBuf d_feat_a, d_feat_b, d_xyz_a, d_xyz_b;
+  DevBuf d_i8_a, d_i8_b, d_jobs, d_items, d_top4, d_knn;
+  PinBuf h_pairs, h_jobs, h_items;
+  void release() {
+    DevBuf* all[] = {&d_pairs, &d_best, &d_matches, &d_inliers, &d_mfrom, &d_mto, &d_nall, &d_hyp, &d_results, &d_feat_a,
+                     &d_feat_b, &d_xyz_a, &d_xyz_b, &d_i8_a, &d_i8_b, &d_jobs, &d_items, &d_top4, &d_knn};
+    for (DevBuf* b : all) b->release();
+    h_pairs.release();
+    h_jobs.release();
+    h_items.release();
+  }
+};
+
 struct State {
   std::mutex mu;
   bool inited = false;
@@ -46,26 +67,17 @@ struct State {
   rgbdslam_b200_params params;
   DevParams dp;
   double z0 = 0.0;  // latched first depth for depth_covariance (misc2.h:30-35)
-  cudaStream_t own_stream = nullptr, stream = nullptr;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-  bool timing_valid = false;
+  cudaStream_t own_stream = nullptr, stream = nullptr;  // stream of the synchronous entry points (= slot 0)
   int64_t launches = 0;
-  // workspaces
-  DevBuf d_pairs, d_best, d_matches, d_inliers, d_mfrom, d_mto, d_nall, d_hyp, d_results;
-  DevBuf d_feat_a, d_feat_b, d_xyz_a, d_xyz_b;
-  DevBuf d_i8_a, d_i8_b, d_jobs, d_items;
-  DevBuf d_top4, d_knn, d_f32_a, d_f32_b, d_root_a, d_root_b, d_norm_a, d_norm_b;
-  PinBuf h_pairs, h_jobs, h_items;
+  Workspace ws[kSlots];
+  Workspace* cur = &ws[0];
+  Workspace& W() { return *cur; }
+  DevBuf d_f32_a, d_f32_b, d_root_a, d_root_b, d_norm_a, d_norm_b;  // SIFT staging of the synchronous calls
   int hamming_path = 1;  // 1 = tcgen05 int8 GEMM (hamming_tc.cu), 0 = SIMT popcount (frontend_kernels.cu)
   void release_workspaces() {
-    DevBuf* all[] = {&d_pairs, &d_best, &d_matches, &d_inliers, &d_mfrom, &d_mto, &d_nall,
-                     &d_hyp,   &d_results, &d_feat_a, &d_feat_b, &d_xyz_a, &d_xyz_b,
-                     &d_i8_a,  &d_i8_b,    &d_jobs,   &d_items,  &d_top4,   &d_knn,   &d_f32_a,
-                     &d_f32_b, &d_root_a,  &d_root_b, &d_norm_a, &d_norm_b};
+    for (Workspace& w : ws) w.release();
+    DevBuf* all[] = {&d_f32_a, &d_f32_b, &d_root_a, &d_root_b, &d_norm_a, &d_norm_b};
     for (DevBuf* b : all) b->release();
-    h_pairs.release();
-    h_jobs.release();
-    h_items.release();
   }
 };
 

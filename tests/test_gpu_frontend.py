@@ -281,3 +281,45 @@ def test_full_size_batch_properties(fe, oracle_mod):
     bs["desc_older"] = b["desc_older"][100 * 1000:132 * 1000]; bs["xyz_older"] = b["xyz_older"][100 * 1000:132 * 1000]
     ores, oall, oinl = _oracle_run(oracle_mod, bs, 99, first=100)
     _compare(res[sub], allm[sub], inl[sub], ores, oall, oinl, strict_frac=0.85)
+
+
+def test_pipelined_submit_wait_equals_synchronous(fe, oracle_mod):
+    """rgbdslam_b200_match_pairs_submit / _host_submit / _wait: batches in flight on different slots give exactly the
+    results of the synchronous calls."""
+    import torch
+    from rgbdslam_v2_b200 import synth
+    from rgbdslam_v2_b200._capi import PAIR_RESULT_DTYPE, DMATCH_DTYPE
+    _reinit(fe)
+    batches = [synth.make_batch(12, 800, seed0=7000 + 100 * j) for j in range(3)]
+    ref = []
+    for j, b in enumerate(batches):
+        ref.append(fe.match_pairs_host(b["desc_newer"], b["xyz_newer"], b["n_newer"], b["desc_older"], b["xyz_older"], b["n_older"],
+                                       b["id_newer"], b["id_older"], seed=31, first_pair_index=100 * j))
+    outs, keep = [], []
+    for j, b in enumerate(batches):
+        bufs = [torch.zeros(12 * PAIR_RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory(),
+                torch.zeros(12 * 300 * 16, dtype=torch.uint8).pin_memory(), torch.zeros(12 * 300 * 16, dtype=torch.uint8).pin_memory()]
+        keep.append(bufs)
+        out = (bufs[0].numpy().view(PAIR_RESULT_DTYPE), bufs[1].numpy().view(DMATCH_DTYPE).reshape(12, 300),
+               bufs[2].numpy().view(DMATCH_DTYPE).reshape(12, 300))
+        outs.append(out)
+        pins = {k: torch.from_numpy(b[k]).pin_memory() for k in ("desc_newer", "xyz_newer", "desc_older", "xyz_older")}
+        keep.append(pins)
+        fe.submit_pairs_host(1 + j, pins["desc_newer"], pins["xyz_newer"], b["n_newer"], pins["desc_older"], pins["xyz_older"],
+                             b["n_older"], b["id_newer"], b["id_older"], out, seed=31, first_pair_index=100 * j)
+    for j in range(3):
+        fe.wait_slot(1 + j)
+    for (r, a, i), (rr, ra, ri) in zip(outs, ref):
+        assert r.tobytes() == rr.tobytes() and a.tobytes() == ra.tobytes()
+        for k in range(12):
+            assert np.array_equal(i[k, :r[k]["n_inliers"]], ri[k, :rr[k]["n_inliers"]])
+    # device-resident variant, two slots reused several times
+    b = batches[0]
+    newer = np.array([fe.node_from_features(int(b["id_newer"][k]), p["desc_newer"], p["xyz_newer"]) for k, p in enumerate(b["pairs"])], np.uint64)
+    older = np.array([fe.node_from_features(int(b["id_older"][k]), p["desc_older"], p["xyz_older"]) for k, p in enumerate(b["pairs"])], np.uint64)
+    for it in range(5):
+        fe.submit_node_pairs(1 + it % 2, newer, older, (outs[it % 2][0], None, None), seed=31, first_pair_index=0)
+    fe.wait_slot(1); fe.wait_slot(2)
+    assert outs[0][0].tobytes() == ref[0][0].tobytes() and outs[1][0].tobytes() == ref[0][0].tobytes()
+    for h in list(newer) + list(older):
+        fe.node_destroy(int(h))
