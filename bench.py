@@ -229,7 +229,7 @@ def run_ours(args, rank, local_rank, world):
     # Two independent batches (A/B) alternate between two pipeline slots: their resident inputs (2 x 156 MB of node
     # data incl. the int8 operands) exceed the 126 MB L2, so no explicit flush is needed between steps, and the
     # host->device copies / latency-bound RANSAC phases of step k+1 overlap the kernels of step k.
-    DEPTH = 2
+    DEPTH = 3
     sets = []
     for j in range(DEPTH):
         b = make_workload(rank + j * world)
