@@ -185,12 +185,13 @@ struct Rt {
 // cfrom / cto hold the correspondences CENTRED on the pair's centroids (ca, cb) with the ORIGINAL depth in .w:
 // (x - cx, y - cy, z - cz, z).  Centring makes the single-pass raw-moment form of the weighted covariance
 // (sum w b a^T / W - m2 m1^T) as accurate in float32 as the reference's running-mean update.
+template <int NW>
 __device__ bool fit_transform(const float4* __restrict__ cfrom, const float4* __restrict__ cto, const float* ca, const float* cb,
                               const uint32_t* sel, int nw, int lane, Rt& out) {
   float W = 0.f, f0 = 0.f, f1 = 0.f, f2 = 0.f, t0 = 0.f, t1 = 0.f, t2 = 0.f;
   float c[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
-  for (int w = 0; w < kMaxMaskWords; w++) {
+  for (int w = 0; w < NW; w++) {
     if (w < nw && ((sel[w] >> lane) & 1u)) {
       const float4 a = cfrom[w * 32 + lane], b = cto[w * 32 + lane];
       if (!isnan(a.w) && !isnan(b.w)) {  // transformation_estimation_euclidean.cpp:22
@@ -418,6 +419,7 @@ __device__ __forceinline__ double mahal_sq(const float4 x1, const float4 x2, con
 
 // computeInliersAndError (node.cpp:968-1020): returns #inliers, fills the mask words (warp-uniform) and
 // the Mahalanobis RMS (1e9 if < 3 inliers).
+template <int NW>
 __device__ int score_all(const float4* __restrict__ sfrom, const float4* __restrict__ sto, int M, int nw, int lane,
                          const Rt& T, uint32_t* words, double& err) {
   ScoreCtx ctx;
@@ -426,7 +428,7 @@ __device__ int score_all(const float4* __restrict__ sfrom, const float4* __restr
   double esum = 0.0;
   int cnt = 0;
 #pragma unroll
-  for (int w = 0; w < kMaxMaskWords; w++) {
+  for (int w = 0; w < NW; w++) {
     uint32_t word = 0;
     if (w < nw) {
       const int i = w * 32 + lane;
@@ -512,7 +514,10 @@ constexpr int kMaxScanPrefix = 64;  // largest n_begin of a non-final phase (pha
 // Hypotheses [n_begin, n_end) of every pair.  The host launches this in growing phases ([0,8), [8,40),
 // [40,H)); a CTA first replays the scan over the already finished prefix [0, n_begin) and skips work the
 // sequential reference loop would never reach (pair finished by the > 80 % break, or index jumped over).
-__global__ void __launch_bounds__(kRansacWarps * 32)
+// NW = mask words compiled in (10 covers the default max_matches = 300, 16 the cap of 512): the unrolled
+// per-word code is the bulk of the kernel, the smaller instantiation relieves the instruction cache.
+template <int NW>
+__global__ void __launch_bounds__(kRansacWarps * 32, 3)
     ransac_hyp_kernel(int H, int maxM, int n_begin, int n_end, uint64_t seed, int64_t first_pair,
                       const float4* __restrict__ mfrom, const float4* __restrict__ mto,
                       const int32_t* __restrict__ n_all, HypResult* __restrict__ hyp) {
@@ -596,9 +601,9 @@ __global__ void __launch_bounds__(kRansacWarps * 32)
       if (++safety > 10000) break;
     }
   }
-  uint32_t sel[kMaxMaskWords];
+  uint32_t sel[NW];
 #pragma unroll
-  for (int w = 0; w < kMaxMaskWords; w++) {
+  for (int w = 0; w < NW; w++) {
     uint32_t word = 0;
 #pragma unroll
     for (int k = 0; k < 4; k++)
@@ -615,9 +620,9 @@ __global__ void __launch_bounds__(kRansacWarps * 32)
 
   for (int refinements = 1; refinements < 20; refinements++) {  // node.cpp:1140
     Rt T;
-    if (!fit_transform(cfrom, cto, s_cen, s_cen + 3, sel, nw, lane, T)) break;  // node.cpp:1142-1145
+    if (!fit_transform<NW>(cfrom, cto, s_cen, s_cen + 3, sel, nw, lane, T)) break;  // node.cpp:1142-1145
     double err;
-    const int cnt = score_all(sfrom, sto, M, nw, lane, T, sel, err);  // node.cpp:1148
+    const int cnt = score_all<NW>(sfrom, sto, M, nw, lane, T, sel, err);  // node.cpp:1148
     if ((unsigned)cnt < min_thr || err > (double)c_params.max_dist_m) break;  // node.cpp:1154
     if (cnt >= refined_cnt && err <= refined_err) {                             // node.cpp:1160
       const int prev = refined_cnt;
@@ -652,8 +657,12 @@ cudaError_t launch_ransac_hypotheses(int npairs, int ransac_iterations, int max_
     const int n_begin = bounds[ph], n_end = bounds[ph + 1] < H ? bounds[ph + 1] : H;
     if (n_begin >= n_end) continue;
     dim3 grid((n_end - n_begin + kRansacWarps - 1) / kRansacWarps, npairs);
-    ransac_hyp_kernel<<<grid, kRansacWarps * 32, 0, stream>>>(H, max_matches, n_begin, n_end, seed, first_pair, mfrom,
-                                                              mto, n_all, hyp);
+    if (max_matches <= 320)
+      ransac_hyp_kernel<10><<<grid, kRansacWarps * 32, 0, stream>>>(H, max_matches, n_begin, n_end, seed, first_pair, mfrom, mto,
+                                                                    n_all, hyp);
+    else
+      ransac_hyp_kernel<kMaxMaskWords><<<grid, kRansacWarps * 32, 0, stream>>>(H, max_matches, n_begin, n_end, seed, first_pair,
+                                                                               mfrom, mto, n_all, hyp);
     if (n_launches) (*n_launches)++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
@@ -662,6 +671,7 @@ cudaError_t launch_ransac_hypotheses(int npairs, int ransac_iterations, int max_
 }
 
 // One warp per pair.
+template <int NW>
 __global__ void __launch_bounds__(32)
     ransac_select_kernel(const PairDesc* __restrict__ pairs, int H, int maxM, const float4* __restrict__ mfrom,
                          const float4* __restrict__ mto, const int32_t* __restrict__ n_all,
@@ -711,9 +721,9 @@ __global__ void __launch_bounds__(32)
 #pragma unroll
     for (int i = 0; i < 9; i++) T.R[i] = (i % 4 == 0) ? 1.f : 0.f;
     T.t[0] = T.t[1] = T.t[2] = 0.f;
-    uint32_t words[kMaxMaskWords];
+    uint32_t words[NW];
 #pragma unroll
-    for (int w = 0; w < kMaxMaskWords; w++) words[w] = 0;
+    for (int w = 0; w < NW; w++) words[w] = 0;
     int n_inl = 0;
     if (best_n >= 0) {
 #pragma unroll
@@ -721,10 +731,10 @@ __global__ void __launch_bounds__(32)
 #pragma unroll
       for (int i = 0; i < 3; i++) T.t[i] = hp[best_n].T[9 + i];
       double err;
-      n_inl = score_all(sfrom, sto, M, nw, lane, T, words, err);  // bit-identical to the hypothesis kernel's pass
+      n_inl = score_all<NW>(sfrom, sto, M, nw, lane, T, words, err);  // bit-identical to the hypothesis kernel's pass
     } else if (valid == 0) {  // identity as last resort (node.cpp:1192-1215)
       double err;
-      const int cnt = score_all(sfrom, sto, M, nw, lane, T, words, err);
+      const int cnt = score_all<NW>(sfrom, sto, M, nw, lane, T, words, err);
       if ((unsigned)cnt > min_thr && err < (double)c_params.max_dist_m) {
         n_inl = cnt;
         rmse = (float)err;
@@ -732,7 +742,7 @@ __global__ void __launch_bounds__(32)
         res.used_identity = 1;
       } else {
 #pragma unroll
-        for (int w = 0; w < kMaxMaskWords; w++) words[w] = 0;
+        for (int w = 0; w < NW; w++) words[w] = 0;
       }
     }
     res.valid_iterations = valid;
@@ -747,7 +757,7 @@ __global__ void __launch_bounds__(32)
     if (inlier_matches) {
       int base = 0;
 #pragma unroll
-      for (int w = 0; w < kMaxMaskWords; w++) {
+      for (int w = 0; w < NW; w++) {
         if (w < nw) {
           const uint32_t word = words[w];
           if ((word >> lane) & 1u) {
@@ -775,11 +785,17 @@ cudaError_t launch_ransac_select(const PairDesc* pairs, int npairs, int ransac_i
   if (npairs <= 0) return cudaSuccess;
   const size_t smem = (size_t)ransac_iterations * 12 + 16;
   if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(ransac_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(ransac_select_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(ransac_select_kernel<kMaxMaskWords>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  ransac_select_kernel<<<npairs, 32, smem, stream>>>(pairs, ransac_iterations, max_matches, mfrom, mto, n_all, matches, hyp,
-                                                     results, inlier_matches);
+  if (max_matches <= 320)
+    ransac_select_kernel<10><<<npairs, 32, smem, stream>>>(pairs, ransac_iterations, max_matches, mfrom, mto, n_all, matches, hyp,
+                                                           results, inlier_matches);
+  else
+    ransac_select_kernel<kMaxMaskWords><<<npairs, 32, smem, stream>>>(pairs, ransac_iterations, max_matches, mfrom, mto, n_all,
+                                                                      matches, hyp, results, inlier_matches);
   return cudaGetLastError();
 }
 

@@ -1,0 +1,51 @@
+"""Where does the end-to-end (host buffers) step spend its time?  (GPU box)"""
+import sys, time
+from pathlib import Path
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+import numpy as np, torch
+from rgbdslam_v2_b200 import Frontend, synth
+from rgbdslam_v2_b200._capi import default_params, PAIR_RESULT_DTYPE, DMATCH_DTYPE
+
+p = default_params(); p.depth_cov_z0 = 2.0
+fe = Frontend(0, p)
+b = synth.make_batch(256, 1000, seed0=1)
+pin = {k: torch.from_numpy(b[k]).pin_memory() for k in ("desc_newer", "xyz_newer", "desc_older", "xyz_older")}
+res = torch.zeros(256 * PAIR_RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+allm = torch.zeros(256 * 300 * 16, dtype=torch.uint8).pin_memory(); inl = torch.zeros_like(allm).pin_memory()
+r = res.numpy().view(PAIR_RESULT_DTYPE); a = allm.numpy().view(DMATCH_DTYPE).reshape(256, 300); i = inl.numpy().view(DMATCH_DTYPE).reshape(256, 300)
+
+def t(fn, n=20):
+    for _ in range(3): fn()
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for _ in range(n): fn()
+    torch.cuda.synchronize(); return (time.perf_counter() - t0) / n * 1e3
+
+def host(out): return lambda: fe.match_pairs_host(pin["desc_newer"], pin["xyz_newer"], b["n_newer"], pin["desc_older"], pin["xyz_older"], b["n_older"], b["id_newer"], b["id_older"], seed=1, out=out)
+print("e2e sync, results+matches  ms", t(host((r, a, i))))
+print("e2e sync, results only     ms", t(host((r, None, None))))
+print("e2e sync, pageable inputs  ms", t(lambda: fe.match_pairs_host(b["desc_newer"], b["xyz_newer"], b["n_newer"], b["desc_older"], b["xyz_older"], b["n_older"], b["id_newer"], b["id_older"], seed=1, out=(r, None, None))))
+dev = {k: torch.empty_like(v, device="cuda") for k, v in pin.items()}
+print("torch H2D of the 4 buffers ms", t(lambda: [dev[k].copy_(pin[k], non_blocking=True) for k in pin]))
+newer = np.array([fe.node_from_features(int(b["id_newer"][k]), q["desc_newer"], q["xyz_newer"]) for k, q in enumerate(b["pairs"])], np.uint64)
+older = np.array([fe.node_from_features(int(b["id_older"][k]), q["desc_older"], q["xyz_older"]) for k, q in enumerate(b["pairs"])], np.uint64)
+print("resident sync              ms", t(lambda: fe.match_node_pairs(newer, older, seed=1, out=(r, None, None))), "device", fe.last_timing())
+fe.set_hamming_path(0)
+print("e2e sync SIMT hamming (no int8 expansion) ms", t(host((r, None, None))))
+fe.set_hamming_path(1)
+# pipelined e2e, depth 3
+outs = []
+for j in range(3):
+    rr = torch.zeros(256 * PAIR_RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+    outs.append((rr, rr.numpy().view(PAIR_RESULT_DTYPE)))
+def pipe(K=30):
+    for k in range(K):
+        fe.submit_pairs_host(1 + k % 3, pin["desc_newer"], pin["xyz_newer"], b["n_newer"], pin["desc_older"], pin["xyz_older"], b["n_older"], b["id_newer"], b["id_older"], (outs[k % 3][1], None, None), seed=1)
+    for j in range(3): fe.wait_slot(1 + j)
+pipe(6); torch.cuda.synchronize(); t0 = time.perf_counter(); pipe(30); torch.cuda.synchronize()
+print("e2e pipelined depth 3, results only ms/step", (time.perf_counter() - t0) / 30 * 1e3)
+t0 = time.perf_counter()
+for k in range(30):
+    fe.submit_pairs_host(1 + k % 3, pin["desc_newer"], pin["xyz_newer"], b["n_newer"], pin["desc_older"], pin["xyz_older"], b["n_older"], b["id_newer"], b["id_older"], (outs[k % 3][1], None, None), seed=1)
+host_ms = (time.perf_counter() - t0) / 30 * 1e3
+for j in range(3): fe.wait_slot(1 + j)
+print("host time per submit (incl. implicit drain) ms", host_ms)
