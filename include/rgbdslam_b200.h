@@ -208,6 +208,9 @@ int rgbdslam_b200_match_pairs_wait(int slot);
  * and of the whole device part of the last match_pairs* call. */
 int rgbdslam_b200_last_timing(float* hamming_ms, float* total_device_ms);
 int rgbdslam_b200_last_timing_slot(int slot, float* hamming_ms, float* total_device_ms);
+/* CUDA-event stage times (ms) of the last finished call on a slot: [0] host->device copies, [1] int8 expansion,
+ * [2] Hamming kernel, [3] match selection + RANSAC, [4] device->host copies, [5] whole call on the stream. */
+int rgbdslam_b200_slot_stage_times(int slot, float* ms6);
 
 /* ---- Node construction from images -------------------------------------------
  * The reference builds one detector / extractor pair and shares it between all Node constructors

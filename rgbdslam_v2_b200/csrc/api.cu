@@ -169,14 +169,15 @@ static int launch_sift_knn(const PairDesc* d_pairs, const PairDesc* h_pairs, int
   std::vector<HamItem> items;
   for (int p = 0; p < npairs; p++) {
     const PairDesc& pd = h_pairs[p];
-    for (int m0 = 0; m0 < pd.nq; m0 += 128) {
+    const int mblk = s.hamming_path == 2 ? 256 : 128, nblk = s.hamming_path == 2 ? 128 : 256;
+    for (int m0 = 0; m0 < pd.nq; m0 += mblk) {
       HamItem it;
       it.a = pd.q_i8 + (size_t)m0 * 256;
       it.b = pd.t_i8;
       it.out = reinterpret_cast<int2*>(reinterpret_cast<int4*>(s.W().d_top4.ptr) + (size_t)p * stride + m0);
-      it.nq_valid = pd.nq - m0 < 128 ? pd.nq - m0 : 128;
+      it.nq_valid = pd.nq - m0 < mblk ? pd.nq - m0 : mblk;
       it.nsearch = pd.nt;  // FLANN searches every train row (no size-1 quirk on this path)
-      it.n_btiles = (pd.nt + 255) / 256;
+      it.n_btiles = (pd.nt + nblk - 1) / nblk;
       it.pad_ = 0;
       it.bnorm = pd.t_norm;
       items.push_back(it);
@@ -190,7 +191,8 @@ static int launch_sift_knn(const PairDesc* d_pairs, const PairDesc* h_pairs, int
     cudaError_t e = cudaMemcpyAsync(s.W().d_items.ptr, s.W().h_items.ptr, sizeof(HamItem) * items.size(), cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) return cuda_fail(e, "upload l2 items");
     cudaEventRecord(s.W().ev[3], st);
-    e = launch_l2_tc((const HamItem*)s.W().d_items.ptr, (int)items.size(), s.sm_count, st);
+    e = s.hamming_path == 2 ? launch_l2_tc256((const HamItem*)s.W().d_items.ptr, (int)items.size(), s.sm_count, st)
+                            : launch_l2_tc((const HamItem*)s.W().d_items.ptr, (int)items.size(), s.sm_count, st);
     if (e != cudaSuccess) return cuda_fail(e, "l2 tensor-core kernel");
     s.launches += 1;
   }
@@ -220,15 +222,17 @@ static int launch_hamming(const PairDesc* d_pairs, const PairDesc* h_pairs, int 
         return RGBDSLAM_B200_ERR_STATE;
       }
       const int nsearch = pd.nt - 1 > 0 ? pd.nt - 1 : 0;
-      for (int m0 = 0; m0 < pd.nq; m0 += 128) {
+      const int mblk = s.hamming_path == 2 ? 256 : 128, nblk = s.hamming_path == 2 ? 128 : 256;
+      for (int m0 = 0; m0 < pd.nq; m0 += mblk) {
         HamItem it;
         it.a = pd.q_i8 + (size_t)m0 * 256;
         it.b = pd.t_i8;
         it.out = best + (size_t)p * stride + m0;
-        it.nq_valid = pd.nq - m0 < 128 ? pd.nq - m0 : 128;
+        it.nq_valid = pd.nq - m0 < mblk ? pd.nq - m0 : mblk;
         it.nsearch = nsearch;
-        it.n_btiles = (nsearch + 255) / 256;
+        it.n_btiles = (nsearch + nblk - 1) / nblk;
         it.pad_ = 0;
+        it.bnorm = nullptr;
         items.push_back(it);
       }
     }
@@ -244,7 +248,10 @@ static int launch_hamming(const PairDesc* d_pairs, const PairDesc* h_pairs, int 
     e = cudaMemcpyAsync(s.W().d_items.ptr, s.W().h_items.ptr, sizeof(HamItem) * items.size(), cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) return cuda_fail(e, "upload hamming items");
     cudaEventRecord(s.W().ev[3], st);
-    e = launch_hamming_tc((const HamItem*)s.W().d_items.ptr, (int)items.size(), s.sm_count, st);
+    if (s.hamming_path == 2)
+      e = launch_hamming_tc256((const HamItem*)s.W().d_items.ptr, (int)items.size(), s.sm_count, st);
+    else
+      e = launch_hamming_tc((const HamItem*)s.W().d_items.ptr, (int)items.size(), s.sm_count, st);
   }
   cudaEventRecord(s.W().ev[1], st);
   if (e != cudaSuccess) return cuda_fail(e, "hamming kernel");
@@ -367,6 +374,7 @@ static int run_pairs(const std::vector<PairDesc>& h_pairs, uint64_t seed, int64_
                         cudaMemcpyDeviceToHost, st);
     if (e != cudaSuccess) return cuda_fail(e, "download inlier_matches");
   }
+  cudaEventRecord(s.W().ev[6], st);
   s.W().timing_valid = true;
   s.W().pending = true;
   if (sync) {
@@ -437,7 +445,7 @@ int rgbdslam_b200_init(int device, const rgbdslam_b200_params* p) {
     e = cudaStreamCreateWithFlags(&s.own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
     for (int k = 0; k < kSlots; k++) {
-      for (int i = 0; i < 4; i++) {
+      for (int i = 0; i < 8; i++) {
         e = cudaEventCreate(&s.ws[k].ev[i]);
         if (e != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
       }
@@ -471,7 +479,7 @@ int rgbdslam_b200_shutdown(void) {
   cudaDeviceSynchronize();
   s.release_workspaces();
   for (int k = 0; k < kSlots; k++) {
-    for (int i = 0; i < 4; i++) cudaEventDestroy(s.ws[k].ev[i]);
+    for (int i = 0; i < 8; i++) cudaEventDestroy(s.ws[k].ev[i]);
     if (k > 0) cudaStreamDestroy(s.ws[k].stream);
   }
   cudaStreamDestroy(s.own_stream);
@@ -498,8 +506,8 @@ int rgbdslam_b200_synchronize(void) {
 
 int rgbdslam_b200_set_hamming_path(int path) {
   std::lock_guard<std::mutex> lk(g_state.mu);
-  if (path != 0 && path != 1) {
-    set_error("set_hamming_path: 0 = SIMT popcount, 1 = tcgen05 int8 GEMM");
+  if (path < 0 || path > 2) {
+    set_error("set_hamming_path: 0 = SIMT popcount, 1 = tcgen05 int8 GEMM (128-query items), 2 = tcgen05 (256-query items)");
     return RGBDSLAM_B200_ERR_ARG;
   }
   g_state.hamming_path = path;
@@ -511,6 +519,33 @@ double rgbdslam_b200_depth_cov_z0(void) { return g_state.z0; }
 
 int rgbdslam_b200_last_timing(float* hamming_ms, float* total_device_ms) {
   return rgbdslam_b200_last_timing_slot(0, hamming_ms, total_device_ms);
+}
+
+int rgbdslam_b200_slot_stage_times(int slot, float* ms6) {
+  std::lock_guard<std::mutex> lk(g_state.mu);
+  int rc = check_inited();
+  if (rc) return rc;
+  if (slot < 0 || slot >= kSlots || !ms6) {
+    set_error("slot_stage_times: bad arguments");
+    return RGBDSLAM_B200_ERR_ARG;
+  }
+  Workspace& w = g_state.ws[slot];
+  if (!w.timing_valid || w.pending) {
+    set_error("slot_stage_times: no finished call on this slot");
+    return RGBDSLAM_B200_ERR_STATE;
+  }
+  for (int i = 0; i < 6; i++) ms6[i] = 0.f;
+  cudaError_t e = cudaSuccess;
+  if (w.host_path) {
+    e = cudaEventElapsedTime(&ms6[0], w.ev[4], w.ev[5]);                          // host -> device copies
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms6[1], w.ev[5], w.ev[0]);    // int8 expansion + pair table
+  }
+  if (e == cudaSuccess) e = cudaEventElapsedTime(&ms6[2], w.ev[3], w.ev[1]);      // Hamming kernel
+  if (e == cudaSuccess) e = cudaEventElapsedTime(&ms6[3], w.ev[1], w.ev[2]);      // match selection + RANSAC
+  if (e == cudaSuccess) e = cudaEventElapsedTime(&ms6[4], w.ev[2], w.ev[6]);      // device -> host copies
+  if (e == cudaSuccess) e = cudaEventElapsedTime(&ms6[5], w.host_path ? w.ev[4] : w.ev[0], w.ev[6]);  // whole call
+  if (e != cudaSuccess) return cuda_fail(e, "slot_stage_times");
+  return 0;
 }
 
 int rgbdslam_b200_last_timing_slot(int slot, float* hamming_ms, float* total_device_ms) {
@@ -714,6 +749,7 @@ static int match_pairs_impl(int slot, bool sync, const uint64_t* newer, const ui
     set_error("match_pairs: bad arguments");
     return RGBDSLAM_B200_ERR_ARG;
   }
+  g_state.W().host_path = false;
   std::vector<PairDesc> pairs(npairs);
   for (int i = 0; i < npairs; i++) {
     NodeDev* a = get_node(newer[i]);
@@ -801,6 +837,7 @@ static int match_pairs_host_impl(int slot, bool sync, const uint8_t* desc_newer,
   if ((rc = s.W().d_xyz_b.ensure(16 * (tot_o + 1)))) return rc;
   cudaStream_t st = s.W().stream;
   cudaError_t e = cudaSuccess;
+  cudaEventRecord(s.W().ev[4], st);
   if (tot_n) {
     e = cudaMemcpyAsync(s.W().d_feat_a.ptr, desc_newer, 32 * tot_n, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(s.W().d_xyz_a.ptr, xyz_newer, 16 * tot_n, cudaMemcpyHostToDevice, st);
@@ -810,6 +847,8 @@ static int match_pairs_host_impl(int slot, bool sync, const uint8_t* desc_newer,
     if (e == cudaSuccess) e = cudaMemcpyAsync(s.W().d_xyz_b.ptr, xyz_older, 16 * tot_o, cudaMemcpyHostToDevice, st);
   }
   if (e != cudaSuccess) return cuda_fail(e, "match_pairs_host upload");
+  cudaEventRecord(s.W().ev[5], st);
+  s.W().host_path = true;
   std::vector<PairDesc> pairs(npairs);
   size_t on = 0, oo = 0, pn = 0, po = 0;
   const bool tc = s.hamming_path != 0;

@@ -303,6 +303,192 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_match_kernel(const HamItem* 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Variant with a 256-query A block per work item (two M=128 accumulator halves) and 128-row B tiles:
+//   smem  : A 2 x 64 KiB (double buffered across items) + B 2 x 32 KiB
+//   TMEM  : [stage 2][half 2][128 columns]  (512 columns)
+//   L2->SM traffic per 256 queries: 64 KiB + nt/128 * 32 KiB  (1.8x less than the 128-query kernel, whose operand
+//   fetch rate -- not the tensor pipe -- limits it: ncu shows 42 % tensor-pipe activity at ~29 B/clk/SM)
+//   warps : 0 = bulk-copy producer, 1 = MMA issuer, 2..9 = epilogue (warp group g drains half g)
+constexpr uint32_t kA256 = 256 * 256;  // 64 KiB
+constexpr uint32_t kB128 = 128 * 256;  // 32 KiB
+constexpr uint32_t kSmem256Bars = 2 * kA256 + 2 * kB128;
+constexpr uint32_t kTc256SmemBytes = kSmem256Bars + 128;
+constexpr int kTc256Threads = 320;
+constexpr uint32_t kIdescI8_N128 = (2u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t kIdescBF16_N128 = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+
+template <int MODE>
+__global__ void __launch_bounds__(kTc256Threads, 1) tc_match256_kernel(const HamItem* __restrict__ items, int n_items) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sA = smem_u32(smem);
+  const uint32_t sB = sA + 2 * kA256;
+  const uint32_t bars = sA + kSmem256Bars;
+  auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };  // same slot map as tc_match_kernel
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + kSmem256Bars + 96);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 10; i++) mbar_init(bar(i), 1);
+    mbar_init(bar(10), 8);  // tmem_empty: one arrival per epilogue warp
+    mbar_init(bar(11), 8);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32((const void*)tmem_ptr_smem))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
+      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const HamItem item = items[it];
+        mbar_wait(bar(2 + sa), pa ^ 1);
+        mbar_expect_tx(bar(0 + sa), kA256);
+        bulk_g2s(sA + sa * kA256, item.a, kA256, bar(0 + sa));
+        if (++sa == 2) { sa = 0; pa ^= 1; }
+        for (int nb = 0; nb < item.n_btiles; nb++) {
+          mbar_wait(bar(6 + sb), pb ^ 1);
+          mbar_expect_tx(bar(4 + sb), kB128);
+          bulk_g2s(sB + sb * kB128, item.b + (size_t)nb * kB128, kB128, bar(4 + sb));
+          if (++sb == 2) { sb = 0; pb ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t sa = 0, pa = 0, sb = 0, pb = 0, acc = 0, pacc = 0;
+      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const int n_btiles = items[it].n_btiles;
+        mbar_wait(bar(0 + sa), pa);
+        tc_fence_after();
+        for (int nb = 0; nb < n_btiles; nb++) {
+          mbar_wait(bar(4 + sb), pb);
+          mbar_wait(bar(10 + acc), pacc ^ 1);
+          tc_fence_after();
+          const uint32_t a0 = sA + sa * kA256, b0 = sB + sb * kB128;
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+              const uint32_t d = tmem_base + acc * 256 + h * 128;
+              if (MODE == 0)
+                tc_mma_i8(d, make_desc(a0 + h * kTileA + k * 256), make_desc(b0 + k * 256), kIdescI8_N128, k > 0 ? 1u : 0u);
+              else
+                tc_mma_bf16(d, make_desc(a0 + h * kTileA + k * 256), make_desc(b0 + k * 256), kIdescBF16_N128, k > 0 ? 1u : 0u);
+            }
+          }
+          tc_commit(bar(6 + sb));
+          tc_commit(bar(8 + acc));
+          if (++sb == 2) { sb = 0; pb ^= 1; }
+          if (++acc == 2) { acc = 0; pacc ^= 1; }
+        }
+        tc_commit(bar(2 + sa));
+        if (++sa == 2) { sa = 0; pa ^= 1; }
+      }
+    }
+  } else {
+    const int h = (warp - 2) >> 2;  // accumulator half drained by this warp group
+    const int wq = warp & 3;        // TMEM lane quadrant
+    const int row = h * 128 + wq * 32 + lane;
+    uint32_t acc = 0, pacc = 0;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+      const HamItem item = items[it];
+      int best = kNoBest;
+      float s0 = -3.0e38f, s1 = -3.0e38f, s2 = -3.0e38f, s3 = -3.0e38f;
+      int i0 = -1, i1 = -1, i2 = -1, i3 = -1;
+      for (int nb = 0; nb < item.n_btiles; nb++) {
+        mbar_wait(bar(8 + acc), pacc);
+        tc_fence_after();
+        const uint32_t t0 = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * 256 + h * 128;
+#pragma unroll 1
+        for (int c = 0; c < 4; c++) {
+          uint32_t v[32];
+          tc_ld32(t0 + c * 32, v);
+          tc_wait_ld();
+          const int col0 = nb * 128 + c * 32;
+          if (MODE == 0) {
+            if (col0 + 32 <= item.nsearch) {
+#pragma unroll
+              for (int j = 0; j < 32; j++) best = max(best, (int)v[j] * 65536 + (65535 - (col0 + j)));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; j++)
+                if (col0 + j < item.nsearch) best = max(best, (int)v[j] * 65536 + (65535 - (col0 + j)));
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+              const int col = col0 + j;
+              if (col < item.nsearch) {
+                const float sc = fmaf(2.f, __uint_as_float(v[j]), -__ldg(item.bnorm + col));
+                if (sc > s3) {
+                  if (sc > s2) {
+                    s3 = s2; i3 = i2;
+                    if (sc > s1) {
+                      s2 = s1; i2 = i1;
+                      if (sc > s0) { s1 = s0; i1 = i0; s0 = sc; i0 = col; }
+                      else { s1 = sc; i1 = col; }
+                    } else { s2 = sc; i2 = col; }
+                  } else { s3 = sc; i3 = col; }
+                }
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(10 + acc));
+        if (++acc == 2) { acc = 0; pacc ^= 1; }
+      }
+      if (row < item.nq_valid) {
+        if (MODE == 0) {
+          int2 o = make_int2(257, -1);
+          if (best != kNoBest) {
+            const int s = best >> 16;
+            o.x = (256 - s) >> 1;
+            o.y = 65535 - (best & 0xFFFF);
+          }
+          item.out[row] = o;
+        } else {
+          reinterpret_cast<int4*>(item.out)[row] = make_int4(i0, i1, i2, i3);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+template <int MODE>
+static cudaError_t launch_tc256(const HamItem* d_items, int n_items, int sm_count, cudaStream_t stream) {
+  if (n_items <= 0) return cudaSuccess;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tc_match256_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTc256SmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int grid = n_items < sm_count ? n_items : sm_count;
+  tc_match256_kernel<MODE><<<grid, kTc256Threads, kTc256SmemBytes, stream>>>(d_items, n_items);
+  return cudaGetLastError();
+}
+cudaError_t launch_hamming_tc256(const HamItem* d_items, int n_items, int sm_count, cudaStream_t stream) {
+  return launch_tc256<0>(d_items, n_items, sm_count, stream);
+}
+cudaError_t launch_l2_tc256(const HamItem* d_items, int n_items, int sm_count, cudaStream_t stream) {
+  return launch_tc256<1>(d_items, n_items, sm_count, stream);
+}
+
 cudaError_t launch_hamming_tc(const HamItem* d_items, int n_items, int sm_count, cudaStream_t stream) {
   if (n_items <= 0) return cudaSuccess;
   static bool attr_set = false;

@@ -42,8 +42,9 @@ constexpr int kSlots = 4;  // independent in-flight match_pairs pipelines (strea
 
 struct Workspace {
   cudaStream_t stream = nullptr;  // slot 0: the library / user stream; slots 1..: own non-blocking streams
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool timing_valid = false;
+  bool host_path = false;  // last call uploaded host features (ev[4], ev[5] valid)
   bool pending = false;
   DevBuf d_pairs, d_best, d_matches, d_inliers, d_mfrom, d_mto, d_nall, d_hyp, d_results;
   DevBuf d_feat_a, d_feat_b, d_xyz_a, d_xyz_b;

@@ -32,6 +32,10 @@ def test_knn2_matches_exact_search(fe, nq, nt):
     if k:
         q[:k] = np.maximum(t[rng.permutation(nt)[:k]] + rng.normal(0, 6.0, (k, 128)).astype(np.float32), 0)  # true matches
     idx, d = fe.knn2_l2(q, t)
+    fe.set_hamming_path(2)  # the 256-query tensor-core kernel must return the same neighbours
+    idx_b, d_b = fe.knn2_l2(q, t)
+    fe.set_hamming_path(1)
+    assert np.array_equal(idx, idx_b) and np.array_equal(d, d_b)
     qr, tr = sift_oracle.root_sift(q), sift_oracle.root_sift(t)
     oidx, od = sift_oracle.knn2_exact(qr, tr)
     # distances of the returned neighbours are exact fp32 evaluations: tolerance 1e-5 absolute on squared L2 <= 2

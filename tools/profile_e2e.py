@@ -29,6 +29,8 @@ print("torch H2D of the 4 buffers ms", t(lambda: [dev[k].copy_(pin[k], non_block
 newer = np.array([fe.node_from_features(int(b["id_newer"][k]), q["desc_newer"], q["xyz_newer"]) for k, q in enumerate(b["pairs"])], np.uint64)
 older = np.array([fe.node_from_features(int(b["id_older"][k]), q["desc_older"], q["xyz_older"]) for k, q in enumerate(b["pairs"])], np.uint64)
 print("resident sync              ms", t(lambda: fe.match_node_pairs(newer, older, seed=1, out=(r, None, None))), "device", fe.last_timing())
+fe.set_hamming_path(2)
+print("resident sync, 256-query tc kernel ms", t(lambda: fe.match_node_pairs(newer, older, seed=1, out=(r, None, None))), "device", fe.last_timing())
 fe.set_hamming_path(0)
 print("e2e sync SIMT hamming (no int8 expansion) ms", t(host((r, None, None))))
 fe.set_hamming_path(1)
@@ -43,6 +45,9 @@ def pipe(K=30):
     for j in range(3): fe.wait_slot(1 + j)
 pipe(6); torch.cuda.synchronize(); t0 = time.perf_counter(); pipe(30); torch.cuda.synchronize()
 print("e2e pipelined depth 3, results only ms/step", (time.perf_counter() - t0) / 30 * 1e3)
+for j in range(3): print("   slot", 1 + j, fe.stage_times(1 + j))
+fe.match_pairs_host(pin["desc_newer"], pin["xyz_newer"], b["n_newer"], pin["desc_older"], pin["xyz_older"], b["n_older"], b["id_newer"], b["id_older"], seed=1, out=(r, None, None))
+print("   sync call stage times", fe.stage_times(0))
 t0 = time.perf_counter()
 for k in range(30):
     fe.submit_pairs_host(1 + k % 3, pin["desc_newer"], pin["xyz_newer"], b["n_newer"], pin["desc_older"], pin["xyz_older"], b["n_older"], b["id_newer"], b["id_older"], (outs[k % 3][1], None, None), seed=1)
