@@ -211,6 +211,11 @@ int rgbdslam_b200_last_timing_slot(int slot, float* hamming_ms, float* total_dev
 /* CUDA-event stage times (ms) of the last finished call on a slot: [0] host->device copies, [1] int8 expansion,
  * [2] Hamming kernel, [3] match selection + RANSAC, [4] device->host copies, [5] whole call on the stream. */
 int rgbdslam_b200_slot_stage_times(int slot, float* ms6);
+/* Pipeline diagnostics: timeline_epoch() marks t = 0 on the device; slot_timeline() returns, for the last finished
+ * call on a slot, the device time (ms since the epoch) of [0] submit, [1] uploads done, [2] operand expansion done,
+ * [3] match kernel start, [4] match kernel end, [5] RANSAC end, [6] downloads done ([0], [1] = -1 for handle calls). */
+int rgbdslam_b200_timeline_epoch(void);
+int rgbdslam_b200_slot_timeline(int slot, float* ms7);
 
 /* ---- Node construction from images -------------------------------------------
  * The reference builds one detector / extractor pair and shares it between all Node constructors

@@ -138,6 +138,8 @@ def load_library(path: str | Path | None = None) -> C.CDLL:
     lib.rgbdslam_b200_posegraph_chi2.argtypes = [C.c_int, vp, C.c_int, vp, vp, vp, C.c_double, C.POINTER(C.c_double), vp]
     lib.rgbdslam_b200_last_timing.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float)]
     lib.rgbdslam_b200_slot_stage_times.argtypes = [C.c_int, vp]
+    lib.rgbdslam_b200_timeline_epoch.argtypes = []
+    lib.rgbdslam_b200_slot_timeline.argtypes = [C.c_int, vp]
     lib.rgbdslam_b200_last_timing_slot.argtypes = [C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     for name in declared_symbols():
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
@@ -206,6 +208,15 @@ class Frontend:
         t = np.zeros(6, np.float32)
         self._check(self.lib.rgbdslam_b200_slot_stage_times(slot, _ptr(t)))
         return dict(zip(("h2d", "expand", "hamming", "select_ransac", "d2h", "total"), (float(v) for v in t)))
+
+    def timeline_epoch(self) -> None:
+        self._check(self.lib.rgbdslam_b200_timeline_epoch())
+
+    def slot_timeline(self, slot: int) -> np.ndarray:
+        """device times (ms since timeline_epoch) of submit, h2d done, expand done, match start, match end, ransac end, d2h done"""
+        t = np.zeros(7, np.float32)
+        self._check(self.lib.rgbdslam_b200_slot_timeline(slot, _ptr(t)))
+        return t
 
     def last_timing(self, slot: int = 0) -> tuple[float, float]:
         a, b = C.c_float(), C.c_float()

@@ -18,7 +18,9 @@ NVCC_FLAGS = [
 
 
 def library_path() -> Path:
-    return PKG_DIR / LIB_NAME
+    """In-tree library; RGBDSLAM_B200_LIB points tools/ at an A/B variant built by tools/build_variants.py."""
+    override = os.environ.get("RGBDSLAM_B200_LIB")
+    return Path(override) if override else PKG_DIR / LIB_NAME
 
 
 def _nvcc() -> str:
@@ -35,7 +37,7 @@ def sources() -> list[Path]:
 def build_library(force: bool = False, verbose: bool = False) -> Path:
     """Compile csrc/*.cu into librgbdslam_b200.so (skipped if up to date)."""
     import fcntl
-    out = library_path()
+    out = PKG_DIR / LIB_NAME
     with open(PKG_DIR / ".build.lock", "w") as lk:  # several ranks may call build() at once
         fcntl.flock(lk, fcntl.LOCK_EX)
         return _build_locked(out, force, verbose)

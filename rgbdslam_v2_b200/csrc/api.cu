@@ -8,6 +8,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <functional>
 #include <vector>
 
 #include "kernels.h"
@@ -123,20 +124,29 @@ static int push_dev_params() {
 static inline int pad256(int n) { return ((n > 0 ? n : 1) + 255) / 256 * 256; }
 
 // +-1 int8 expansion of a set of nodes (tensor-core Hamming operands).
-static int expand_nodes(const std::vector<ExpandJob>& jobs) {
+// phase bit 1: stage the job table (a small host->device copy); bit 2: launch the expansion kernel.
+// The host-feature path stages every table BEFORE its bulk feature upload: a small copy issued behind the bulk
+// copies only reaches the copy engine once they have finished, i.e. behind the bulk copies of the other in-flight
+// slots, and holds this slot's kernels back by a whole upload (measured: 0.95 ms at 3 slots).
+static int expand_nodes(const std::vector<ExpandJob>& jobs, int phase = 3) {
   State& s = g_state;
   if (jobs.empty()) return 0;
   int rc;
-  if ((rc = s.W().d_jobs.ensure(sizeof(ExpandJob) * jobs.size()))) return rc;
-  if ((rc = s.W().h_jobs.ensure(sizeof(ExpandJob) * jobs.size()))) return rc;
-  int max_pad = 0;
-  for (const ExpandJob& j : jobs) max_pad = j.n_pad > max_pad ? j.n_pad : max_pad;
-  memcpy(s.W().h_jobs.ptr, jobs.data(), sizeof(ExpandJob) * jobs.size());
-  cudaError_t e = cudaMemcpyAsync(s.W().d_jobs.ptr, s.W().h_jobs.ptr, sizeof(ExpandJob) * jobs.size(), cudaMemcpyHostToDevice, s.W().stream);
-  if (e != cudaSuccess) return cuda_fail(e, "upload expand jobs");
-  e = launch_expand_i8((const ExpandJob*)s.W().d_jobs.ptr, (int)jobs.size(), max_pad, s.W().stream);
-  if (e != cudaSuccess) return cuda_fail(e, "expand_i8 kernel");
-  s.launches += 1;
+  cudaError_t e;
+  if (phase & 1) {
+    if ((rc = s.W().d_jobs.ensure(sizeof(ExpandJob) * jobs.size()))) return rc;
+    if ((rc = s.W().h_jobs.ensure(sizeof(ExpandJob) * jobs.size()))) return rc;
+    memcpy(s.W().h_jobs.ptr, jobs.data(), sizeof(ExpandJob) * jobs.size());
+    e = cudaMemcpyAsync(s.W().d_jobs.ptr, s.W().h_jobs.ptr, sizeof(ExpandJob) * jobs.size(), cudaMemcpyHostToDevice, s.W().stream);
+    if (e != cudaSuccess) return cuda_fail(e, "upload expand jobs");
+  }
+  if (phase & 2) {
+    int max_pad = 0;
+    for (const ExpandJob& j : jobs) max_pad = j.n_pad > max_pad ? j.n_pad : max_pad;
+    e = launch_expand_i8((const ExpandJob*)s.W().d_jobs.ptr, (int)jobs.size(), max_pad, s.W().stream);
+    if (e != cudaSuccess) return cuda_fail(e, "expand_i8 kernel");
+    s.launches += 1;
+  }
   return 0;
 }
 
@@ -160,39 +170,60 @@ static int prepare_sift_nodes(const std::vector<SiftJob>& jobs) {
   return 0;
 }
 
-// SIFT matching stage: bf16 tensor-core scores -> exact fp32 2-NN among the 4 best -> (optionally) ratio/uniqueness.
-static int launch_sift_knn(const PairDesc* d_pairs, const PairDesc* h_pairs, int npairs, int max_nq, int stride, cudaStream_t st) {
+// Work items of the tensor-core match kernels (128- or 256-query blocks of every pair), staged on the stream.
+// Returns the item count in *n_items.
+static int stage_match_items(const PairDesc* h_pairs, int npairs, int stride, bool sift, int* n_items) {
   State& s = g_state;
+  *n_items = 0;
+  if (!sift && s.hamming_path == 0) return 0;
   int rc;
-  if ((rc = s.W().d_top4.ensure(sizeof(int4) * (size_t)npairs * stride))) return rc;
-  if ((rc = s.W().d_knn.ensure(sizeof(float4) * (size_t)npairs * stride))) return rc;
+  if (sift) {
+    if ((rc = s.W().d_top4.ensure(sizeof(int4) * (size_t)npairs * stride))) return rc;
+    if ((rc = s.W().d_knn.ensure(sizeof(float4) * (size_t)npairs * stride))) return rc;
+  }
+  const int mblk = s.hamming_path == 2 ? 256 : 128, nblk = s.hamming_path == 2 ? 128 : 256;
   std::vector<HamItem> items;
+  items.reserve((size_t)npairs * 8);
   for (int p = 0; p < npairs; p++) {
     const PairDesc& pd = h_pairs[p];
-    const int mblk = s.hamming_path == 2 ? 256 : 128, nblk = s.hamming_path == 2 ? 128 : 256;
+    if (pd.nq > 0 && (!pd.q_i8 || !pd.t_i8)) {
+      set_error("internal: tensor-core match path without tiled operands");
+      return RGBDSLAM_B200_ERR_STATE;
+    }
+    // bruteForceSearchORB never looks at the last train row (features.cpp:174); FLANN searches every row
+    const int nsearch = sift ? pd.nt : (pd.nt - 1 > 0 ? pd.nt - 1 : 0);
     for (int m0 = 0; m0 < pd.nq; m0 += mblk) {
       HamItem it;
       it.a = pd.q_i8 + (size_t)m0 * 256;
       it.b = pd.t_i8;
-      it.out = reinterpret_cast<int2*>(reinterpret_cast<int4*>(s.W().d_top4.ptr) + (size_t)p * stride + m0);
+      it.out = sift ? reinterpret_cast<int2*>(reinterpret_cast<int4*>(s.W().d_top4.ptr) + (size_t)p * stride + m0)
+                    : reinterpret_cast<int2*>(s.W().d_best.ptr) + (size_t)p * stride + m0;
       it.nq_valid = pd.nq - m0 < mblk ? pd.nq - m0 : mblk;
-      it.nsearch = pd.nt;  // FLANN searches every train row (no size-1 quirk on this path)
-      it.n_btiles = (pd.nt + nblk - 1) / nblk;
+      it.nsearch = nsearch;
+      it.n_btiles = (nsearch + nblk - 1) / nblk;
       it.pad_ = 0;
-      it.bnorm = pd.t_norm;
+      it.bnorm = sift ? pd.t_norm : nullptr;
       items.push_back(it);
     }
   }
+  if (items.empty()) return 0;
+  if ((rc = s.W().d_items.ensure(sizeof(HamItem) * items.size()))) return rc;
+  if ((rc = s.W().h_items.ensure(sizeof(HamItem) * items.size()))) return rc;
+  memcpy(s.W().h_items.ptr, items.data(), sizeof(HamItem) * items.size());
+  cudaError_t e = cudaMemcpyAsync(s.W().d_items.ptr, s.W().h_items.ptr, sizeof(HamItem) * items.size(), cudaMemcpyHostToDevice,
+                                  s.W().stream);
+  if (e != cudaSuccess) return cuda_fail(e, "upload match items");
+  *n_items = (int)items.size();
+  return 0;
+}
+
+// SIFT matching stage: bf16 tensor-core scores -> exact fp32 2-NN among the 4 best -> (optionally) ratio/uniqueness.
+static int launch_sift_knn(const PairDesc* d_pairs, int npairs, int max_nq, int stride, int n_items, cudaStream_t st) {
+  State& s = g_state;
   cudaEventRecord(s.W().ev[3], st);
-  if (!items.empty()) {
-    if ((rc = s.W().d_items.ensure(sizeof(HamItem) * items.size()))) return rc;
-    if ((rc = s.W().h_items.ensure(sizeof(HamItem) * items.size()))) return rc;
-    memcpy(s.W().h_items.ptr, items.data(), sizeof(HamItem) * items.size());
-    cudaError_t e = cudaMemcpyAsync(s.W().d_items.ptr, s.W().h_items.ptr, sizeof(HamItem) * items.size(), cudaMemcpyHostToDevice, st);
-    if (e != cudaSuccess) return cuda_fail(e, "upload l2 items");
-    cudaEventRecord(s.W().ev[3], st);
-    e = s.hamming_path == 2 ? launch_l2_tc256((const HamItem*)s.W().d_items.ptr, (int)items.size(), s.sm_count, st)
-                            : launch_l2_tc((const HamItem*)s.W().d_items.ptr, (int)items.size(), s.sm_count, st);
+  if (n_items > 0) {
+    cudaError_t e = s.hamming_path == 2 ? launch_l2_tc256((const HamItem*)s.W().d_items.ptr, n_items, s.sm_count, st)
+                                        : launch_l2_tc((const HamItem*)s.W().d_items.ptr, n_items, s.sm_count, st);
     if (e != cudaSuccess) return cuda_fail(e, "l2 tensor-core kernel");
     s.launches += 1;
   }
@@ -203,55 +234,19 @@ static int launch_sift_knn(const PairDesc* d_pairs, const PairDesc* h_pairs, int
   return 0;
 }
 
-// Hamming stage dispatcher (counts the launch).  h_pairs carries the int8 operand pointers when the
-// tensor-core path is selected.
-static int launch_hamming(const PairDesc* d_pairs, const PairDesc* h_pairs, int npairs, int max_nq, int2* best,
-                          int stride, cudaStream_t st) {
+// Hamming stage dispatcher (counts the launch); records ev[3] / ev[1] immediately around the kernel.
+static int launch_hamming(const PairDesc* d_pairs, int npairs, int max_nq, int2* best, int stride, int n_items, cudaStream_t st) {
   State& s = g_state;
-  cudaError_t e;
+  cudaError_t e = cudaSuccess;
+  cudaEventRecord(s.W().ev[3], st);
   if (s.hamming_path == 0) {
-    cudaEventRecord(s.W().ev[3], st);
     e = launch_hamming_simt(d_pairs, npairs, max_nq, best, stride, st);
+  } else if (n_items > 0) {
+    e = s.hamming_path == 2 ? launch_hamming_tc256((const HamItem*)s.W().d_items.ptr, n_items, s.sm_count, st)
+                            : launch_hamming_tc((const HamItem*)s.W().d_items.ptr, n_items, s.sm_count, st);
   } else {
-    std::vector<HamItem> items;
-    items.reserve((size_t)npairs * ((max_nq + 127) / 128));
-    for (int p = 0; p < npairs; p++) {
-      const PairDesc& pd = h_pairs[p];
-      if (pd.nq > 0 && (!pd.q_i8 || !pd.t_i8)) {
-        set_error("internal: tensor-core Hamming path without int8 operands");
-        return RGBDSLAM_B200_ERR_STATE;
-      }
-      const int nsearch = pd.nt - 1 > 0 ? pd.nt - 1 : 0;
-      const int mblk = s.hamming_path == 2 ? 256 : 128, nblk = s.hamming_path == 2 ? 128 : 256;
-      for (int m0 = 0; m0 < pd.nq; m0 += mblk) {
-        HamItem it;
-        it.a = pd.q_i8 + (size_t)m0 * 256;
-        it.b = pd.t_i8;
-        it.out = best + (size_t)p * stride + m0;
-        it.nq_valid = pd.nq - m0 < mblk ? pd.nq - m0 : mblk;
-        it.nsearch = nsearch;
-        it.n_btiles = (nsearch + nblk - 1) / nblk;
-        it.pad_ = 0;
-        it.bnorm = nullptr;
-        items.push_back(it);
-      }
-    }
-    if (items.empty()) {
-      cudaEventRecord(s.W().ev[3], st);
-      cudaEventRecord(s.W().ev[1], st);
-      return 0;
-    }
-    int rc;
-    if ((rc = s.W().d_items.ensure(sizeof(HamItem) * items.size()))) return rc;
-    if ((rc = s.W().h_items.ensure(sizeof(HamItem) * items.size()))) return rc;
-    memcpy(s.W().h_items.ptr, items.data(), sizeof(HamItem) * items.size());
-    e = cudaMemcpyAsync(s.W().d_items.ptr, s.W().h_items.ptr, sizeof(HamItem) * items.size(), cudaMemcpyHostToDevice, st);
-    if (e != cudaSuccess) return cuda_fail(e, "upload hamming items");
-    cudaEventRecord(s.W().ev[3], st);
-    if (s.hamming_path == 2)
-      e = launch_hamming_tc256((const HamItem*)s.W().d_items.ptr, (int)items.size(), s.sm_count, st);
-    else
-      e = launch_hamming_tc((const HamItem*)s.W().d_items.ptr, (int)items.size(), s.sm_count, st);
+    cudaEventRecord(s.W().ev[1], st);
+    return 0;
   }
   cudaEventRecord(s.W().ev[1], st);
   if (e != cudaSuccess) return cuda_fail(e, "hamming kernel");
@@ -262,7 +257,8 @@ static int launch_hamming(const PairDesc* d_pairs, const PairDesc* h_pairs, int 
 // Core of match_pairs*: h_pairs (device pointers inside) -> results on the host.
 static int run_pairs(const std::vector<PairDesc>& h_pairs, uint64_t seed, int64_t first_pair,
                      rgbdslam_b200_pair_result* results, rgbdslam_b200_dmatch* all_matches,
-                     rgbdslam_b200_dmatch* inlier_matches, bool sync = true) {
+                     rgbdslam_b200_dmatch* inlier_matches, bool sync = true,
+                     const std::function<int()>& after_tables = nullptr) {
   State& s = g_state;
   const int npairs = (int)h_pairs.size();
   if (npairs == 0) return 0;
@@ -295,24 +291,27 @@ static int run_pairs(const std::vector<PairDesc>& h_pairs, uint64_t seed, int64_
   e = cudaMemcpyAsync(s.W().d_pairs.ptr, s.W().h_pairs.ptr, sizeof(PairDesc) * npairs, cudaMemcpyHostToDevice, st);
   if (e != cudaSuccess) return cuda_fail(e, "upload pair table");
   const PairDesc* d_pairs = (const PairDesc*)s.W().d_pairs.ptr;
-
-  cudaEventRecord(s.W().ev[0], st);
   bool any_sift = false, any_orb = false;
   for (const PairDesc& pd : h_pairs) (pd.q_f32 ? any_sift : any_orb) = true;
   if (any_sift && any_orb) {
     set_error("match_pairs: ORB and SIFT pairs cannot be mixed in one call");
     return RGBDSLAM_B200_ERR_ARG;
   }
+  int n_items = 0;
+  if ((rc = stage_match_items(h_pairs.data(), npairs, stride, any_sift, &n_items))) return rc;
+  // every table of this call is on its way; now the bulk uploads + operand expansion of the host-feature path
+  if (after_tables && (rc = after_tables())) return rc;
+
+  cudaEventRecord(s.W().ev[0], st);
   if (any_sift) {
-    if ((rc = launch_sift_knn(d_pairs, h_pairs.data(), npairs, max_nq, stride, st))) return rc;
+    if ((rc = launch_sift_knn(d_pairs, npairs, max_nq, stride, n_items, st))) return rc;
     e = launch_select_sift(d_pairs, npairs, (const float4*)s.W().d_knn.ptr, stride, (float)s.params.nn_distance_ratio, maxM,
                            (rgbdslam_b200_dmatch*)s.W().d_matches.ptr, (float4*)s.W().d_mfrom.ptr, (float4*)s.W().d_mto.ptr,
                            (int32_t*)s.W().d_nall.ptr, st);
     if (e != cudaSuccess) return cuda_fail(e, "select_sift kernel");
     s.launches += 1;
   } else {
-    // launch_hamming records ev[3] / ev[1] immediately around the kernel
-    if ((rc = launch_hamming(d_pairs, h_pairs.data(), npairs, max_nq, (int2*)s.W().d_best.ptr, stride, st))) return rc;
+    if ((rc = launch_hamming(d_pairs, npairs, max_nq, (int2*)s.W().d_best.ptr, stride, n_items, st))) return rc;
     e = launch_select_matches(d_pairs, npairs, (const int2*)s.W().d_best.ptr, stride, seed, first_pair,
                               (rgbdslam_b200_dmatch*)s.W().d_matches.ptr, (float4*)s.W().d_mfrom.ptr, (float4*)s.W().d_mto.ptr,
                               (int32_t*)s.W().d_nall.ptr, max_nq, st);
@@ -444,6 +443,8 @@ int rgbdslam_b200_init(int device, const rgbdslam_b200_params* p) {
   if (!s.inited) {
     e = cudaStreamCreateWithFlags(&s.own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
+    e = cudaEventCreate(&s.epoch);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
     for (int k = 0; k < kSlots; k++) {
       for (int i = 0; i < 8; i++) {
         e = cudaEventCreate(&s.ws[k].ev[i]);
@@ -483,6 +484,7 @@ int rgbdslam_b200_shutdown(void) {
     if (k > 0) cudaStreamDestroy(s.ws[k].stream);
   }
   cudaStreamDestroy(s.own_stream);
+  cudaEventDestroy(s.epoch);
   s.inited = false;
   return 0;
 }
@@ -545,6 +547,39 @@ int rgbdslam_b200_slot_stage_times(int slot, float* ms6) {
   if (e == cudaSuccess) e = cudaEventElapsedTime(&ms6[4], w.ev[2], w.ev[6]);      // device -> host copies
   if (e == cudaSuccess) e = cudaEventElapsedTime(&ms6[5], w.host_path ? w.ev[4] : w.ev[0], w.ev[6]);  // whole call
   if (e != cudaSuccess) return cuda_fail(e, "slot_stage_times");
+  return 0;
+}
+
+int rgbdslam_b200_timeline_epoch(void) {
+  std::lock_guard<std::mutex> lk(g_state.mu);
+  int rc = check_inited();
+  if (rc) return rc;
+  cudaError_t e = cudaEventRecord(g_state.epoch, g_state.own_stream);
+  if (e == cudaSuccess) e = cudaEventSynchronize(g_state.epoch);
+  if (e != cudaSuccess) return cuda_fail(e, "timeline_epoch");
+  return 0;
+}
+
+int rgbdslam_b200_slot_timeline(int slot, float* ms7) {
+  std::lock_guard<std::mutex> lk(g_state.mu);
+  int rc = check_inited();
+  if (rc) return rc;
+  if (slot < 0 || slot >= kSlots || !ms7) {
+    set_error("slot_timeline: bad arguments");
+    return RGBDSLAM_B200_ERR_ARG;
+  }
+  Workspace& w = g_state.ws[slot];
+  if (!w.timing_valid || w.pending) {
+    set_error("slot_timeline: no finished call on this slot");
+    return RGBDSLAM_B200_ERR_STATE;
+  }
+  const int order[7] = {4, 5, 0, 3, 1, 2, 6};
+  for (int i = 0; i < 7; i++) {
+    ms7[i] = -1.f;
+    if (!w.host_path && (order[i] == 4 || order[i] == 5)) continue;
+    cudaError_t e = cudaEventElapsedTime(&ms7[i], g_state.epoch, w.ev[order[i]]);
+    if (e != cudaSuccess) return cuda_fail(e, "slot_timeline (call rgbdslam_b200_timeline_epoch first)");
+  }
   return 0;
 }
 
@@ -621,7 +656,9 @@ int rgbdslam_b200_brute_force_orb(const uint64_t* q, int nq, const uint64_t* t, 
   memcpy(s.W().h_pairs.ptr, &pd, sizeof(pd));
   e = cudaMemcpyAsync(s.W().d_pairs.ptr, s.W().h_pairs.ptr, sizeof(pd), cudaMemcpyHostToDevice, st);
   if (e != cudaSuccess) return cuda_fail(e, "brute_force_orb pair upload");
-  if ((rc = launch_hamming((const PairDesc*)s.W().d_pairs.ptr, &pd, 1, nq, (int2*)s.W().d_best.ptr, stride, st))) return rc;
+  int n_items = 0;
+  if ((rc = stage_match_items(&pd, 1, stride, false, &n_items))) return rc;
+  if ((rc = launch_hamming((const PairDesc*)s.W().d_pairs.ptr, 1, nq, (int2*)s.W().d_best.ptr, stride, n_items, st))) return rc;
   std::vector<int2> h(nq);
   e = cudaMemcpyAsync(h.data(), s.W().d_best.ptr, sizeof(int2) * nq, cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -836,18 +873,7 @@ static int match_pairs_host_impl(int slot, bool sync, const uint8_t* desc_newer,
   if ((rc = s.W().d_xyz_a.ensure(16 * (tot_n + 1)))) return rc;
   if ((rc = s.W().d_xyz_b.ensure(16 * (tot_o + 1)))) return rc;
   cudaStream_t st = s.W().stream;
-  cudaError_t e = cudaSuccess;
   cudaEventRecord(s.W().ev[4], st);
-  if (tot_n) {
-    e = cudaMemcpyAsync(s.W().d_feat_a.ptr, desc_newer, 32 * tot_n, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(s.W().d_xyz_a.ptr, xyz_newer, 16 * tot_n, cudaMemcpyHostToDevice, st);
-  }
-  if (e == cudaSuccess && tot_o) {
-    e = cudaMemcpyAsync(s.W().d_feat_b.ptr, desc_older, 32 * tot_o, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(s.W().d_xyz_b.ptr, xyz_older, 16 * tot_o, cudaMemcpyHostToDevice, st);
-  }
-  if (e != cudaSuccess) return cuda_fail(e, "match_pairs_host upload");
-  cudaEventRecord(s.W().ev[5], st);
   s.W().host_path = true;
   std::vector<PairDesc> pairs(npairs);
   size_t on = 0, oo = 0, pn = 0, po = 0;
@@ -885,8 +911,22 @@ static int match_pairs_host_impl(int slot, bool sync, const uint8_t* desc_newer,
     on += n_newer[i];
     oo += n_older[i];
   }
-  if (tc && (rc = expand_nodes(jobs))) return rc;
-  return run_pairs(pairs, seed, first_pair_index, results, all_matches, inlier_matches, sync);
+  if (tc && (rc = expand_nodes(jobs, 1))) return rc;
+  auto bulk_uploads = [&]() -> int {
+    cudaError_t e = cudaSuccess;
+    if (tot_n) {
+      e = cudaMemcpyAsync(s.W().d_feat_a.ptr, desc_newer, 32 * tot_n, cudaMemcpyHostToDevice, st);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(s.W().d_xyz_a.ptr, xyz_newer, 16 * tot_n, cudaMemcpyHostToDevice, st);
+    }
+    if (e == cudaSuccess && tot_o) {
+      e = cudaMemcpyAsync(s.W().d_feat_b.ptr, desc_older, 32 * tot_o, cudaMemcpyHostToDevice, st);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(s.W().d_xyz_b.ptr, xyz_older, 16 * tot_o, cudaMemcpyHostToDevice, st);
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "match_pairs_host upload");
+    cudaEventRecord(s.W().ev[5], st);
+    return tc ? expand_nodes(jobs, 2) : 0;
+  };
+  return run_pairs(pairs, seed, first_pair_index, results, all_matches, inlier_matches, sync, bulk_uploads);
 }
 
 int rgbdslam_b200_match_pairs_host(const uint8_t* desc_newer, const float* xyz_newer, const int32_t* n_newer,
@@ -981,7 +1021,9 @@ int rgbdslam_b200_knn2_l2(const float* q, int nq, const float* t, int nt, int32_
   memcpy(s.W().h_pairs.ptr, &pd, sizeof(pd));
   e = cudaMemcpyAsync(s.W().d_pairs.ptr, s.W().h_pairs.ptr, sizeof(pd), cudaMemcpyHostToDevice, st);
   if (e != cudaSuccess) return cuda_fail(e, "knn2_l2 pair upload");
-  if ((rc = launch_sift_knn((const PairDesc*)s.W().d_pairs.ptr, &pd, 1, nq, stride, st))) return rc;
+  int n_items = 0;
+  if ((rc = stage_match_items(&pd, 1, stride, true, &n_items))) return rc;
+  if ((rc = launch_sift_knn((const PairDesc*)s.W().d_pairs.ptr, 1, nq, stride, n_items, st))) return rc;
   std::vector<float4> h(nq);
   e = cudaMemcpyAsync(h.data(), s.W().d_knn.ptr, sizeof(float4) * nq, cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);

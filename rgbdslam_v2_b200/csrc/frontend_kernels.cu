@@ -222,16 +222,42 @@ __device__ bool fit_transform(const float4* __restrict__ cfrom, const float4* __
   // --- one-sided Jacobi SVD of c (row-major a[r][col]); v accumulates the right rotations ---
   float a00 = c[0], a01 = c[1], a02 = c[2], a10 = c[3], a11 = c[4], a12 = c[5], a20 = c[6], a21 = c[7], a22 = c[8];
   float v00 = 1, v01 = 0, v02 = 0, v10 = 0, v11 = 1, v12 = 0, v20 = 0, v21 = 0, v22 = 1;
+#ifndef RB200_FAST_JACOBI
+#define RB200_FAST_JACOBI 1
+#endif
+#if RB200_FAST_JACOBI
+  // tan(theta) = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)), zeta = (beta - alpha) / (2 gamma), written without the first
+  // division; MUFU-based reciprocal / rsqrt (2 ulp): a Jacobi rotation only has to be orthogonal to rounding, the
+  // iteration corrects any error in the angle on the next sweep.
+#define RB200_JTEST(AL, BE, GA) ((GA) * (GA) > 1.6e-13f * ((AL) * (BE)))
+#define RB200_JANGLE(AL, BE, GA, CS, SN)                                                             \
+  {                                                                                                  \
+    const float dd = (BE) - (AL), g2 = 2.f * (GA);                                                   \
+    const float hh = sqrtf(fmaf(dd, dd, g2 * g2));                                                   \
+    const float sg = ((dd < 0.f) != (g2 < 0.f)) ? -1.f : 1.f;                                        \
+    const float tt = sg * __fdividef(fabsf(g2), fabsf(dd) + hh);                                     \
+    CS = rsqrtf(fmaf(tt, tt, 1.f));                                                                  \
+    SN = CS * tt;                                                                                    \
+  }
+#else
+#define RB200_JTEST(AL, BE, GA) (fabsf(GA) > 4e-7f * sqrtf((AL) * (BE)) && (GA) != 0.f)
+#define RB200_JANGLE(AL, BE, GA, CS, SN)                                                             \
+  {                                                                                                  \
+    const float zeta = ((BE) - (AL)) / (2.f * (GA));                                                 \
+    const float tt = copysignf(1.f, zeta) / (fabsf(zeta) + sqrtf(1.f + zeta * zeta));               \
+    CS = 1.f / sqrtf(1.f + tt * tt);                                                                 \
+    SN = CS * tt;                                                                                    \
+  }
+#endif
 #define RB200_JROT(AP0, AP1, AP2, AQ0, AQ1, AQ2, VP0, VP1, VP2, VQ0, VQ1, VQ2)                       \
   {                                                                                                  \
     const float alpha = AP0 * AP0 + AP1 * AP1 + AP2 * AP2;                                           \
     const float beta = AQ0 * AQ0 + AQ1 * AQ1 + AQ2 * AQ2;                                            \
     const float gamma = AP0 * AQ0 + AP1 * AQ1 + AP2 * AQ2;                                           \
-    if (fabsf(gamma) > 4e-7f * sqrtf(alpha * beta) && gamma != 0.f) {                                \
+    if (RB200_JTEST(alpha, beta, gamma)) {                                                           \
       rotated = true;                                                                                \
-      const float zeta = (beta - alpha) / (2.f * gamma);                                             \
-      const float tt = copysignf(1.f, zeta) / (fabsf(zeta) + sqrtf(1.f + zeta * zeta));             \
-      const float cs = 1.f / sqrtf(1.f + tt * tt), sn = cs * tt;                                         \
+      float cs, sn;                                                                                  \
+      RB200_JANGLE(alpha, beta, gamma, cs, sn)                                                       \
       float x, y;                                                                                    \
       x = AP0; y = AQ0; AP0 = cs * x - sn * y; AQ0 = sn * x + cs * y;                                \
       x = AP1; y = AQ1; AP1 = cs * x - sn * y; AQ1 = sn * x + cs * y;                                \
@@ -249,6 +275,8 @@ __device__ bool fit_transform(const float4* __restrict__ cfrom, const float4* __
     if (!rotated) break;
   }
 #undef RB200_JROT
+#undef RB200_JTEST
+#undef RB200_JANGLE
   // column norms; pick the two largest columns (p >= q >= r)
   const float n0 = a00 * a00 + a10 * a10 + a20 * a20;
   const float n1 = a01 * a01 + a11 * a11 + a21 * a21;
@@ -270,7 +298,11 @@ __device__ bool fit_transform(const float4* __restrict__ cfrom, const float4* __
   RB200_COL(iq, q0, q1, q2, vq0, vq1, vq2, nq)
 #undef RB200_COL
   if (!(np > 0.f) || !(nq > 1e-24f * np)) return false;  // rank < 2: rotation undetermined
+#if RB200_FAST_JACOBI
+  const float ip_ = rsqrtf(np), iq_ = rsqrtf(nq);
+#else
   const float ip_ = 1.f / sqrtf(np), iq_ = 1.f / sqrtf(nq);
+#endif
   p0 *= ip_; p1 *= ip_; p2 *= ip_;
   q0 *= iq_; q1 *= iq_; q2 *= iq_;
   const float u30 = p1 * q2 - p2 * q1, u31 = p2 * q0 - p0 * q2, u32 = p0 * q1 - p1 * q0;
@@ -465,7 +497,32 @@ __device__ __forceinline__ unsigned min_inlier_threshold(int M) {  // node.cpp:1
   return thr;
 }
 
-constexpr int kRansacWarps = 8;
+// Tuning knobs (defaults are the shipped configuration; tools/build_variants.py overrides them for A/B timing).
+#ifndef RB200_RANSAC_WARPS
+#define RB200_RANSAC_WARPS 8
+#endif
+#ifndef RB200_RANSAC_MINBLOCKS
+#define RB200_RANSAC_MINBLOCKS 3
+#endif
+#ifndef RB200_PH1
+#define RB200_PH1 8
+#endif
+#ifndef RB200_PH2
+#define RB200_PH2 40
+#endif
+constexpr int kRansacWarps = RB200_RANSAC_WARPS;
+#ifdef RB200_PROFILE
+// per phase: fit cycles, score cycles, refinement rounds, hypotheses, loop cycles, max loop cycles, max rounds
+__device__ unsigned long long g_ransac_prof[3][8];
+extern "C" int rb200_debug_ransac_profile(unsigned long long* out24, int reset) {
+  cudaError_t e = cudaMemcpyFromSymbol(out24, g_ransac_prof, sizeof(unsigned long long) * 24);
+  if (e == cudaSuccess && reset) {
+    unsigned long long z[24] = {0};
+    e = cudaMemcpyToSymbol(g_ransac_prof, z, sizeof(z));
+  }
+  return (int)e;
+}
+#endif
 
 // The reference's bookkeeping over finished hypotheses (node.cpp:1170-1190), replayed in order over the
 // records of hypotheses [0, n_limit): global best by (error <=, inliers >=), the "n += 10" shortcuts for
@@ -517,7 +574,7 @@ constexpr int kMaxScanPrefix = 64;  // largest n_begin of a non-final phase (pha
 // NW = mask words compiled in (10 covers the default max_matches = 300, 16 the cap of 512): the unrolled
 // per-word code is the bulk of the kernel, the smaller instantiation relieves the instruction cache.
 template <int NW>
-__global__ void __launch_bounds__(kRansacWarps * 32, 3)
+__global__ void __launch_bounds__(kRansacWarps * 32, RB200_RANSAC_MINBLOCKS)
     ransac_hyp_kernel(int H, int maxM, int n_begin, int n_end, uint64_t seed, int64_t first_pair,
                       const float4* __restrict__ mfrom, const float4* __restrict__ mto,
                       const int32_t* __restrict__ n_all, HypResult* __restrict__ hyp) {
@@ -618,11 +675,27 @@ __global__ void __launch_bounds__(kRansacWarps * 32, 3)
   for (int i = 0; i < 9; i++) refined.R[i] = (i % 4 == 0) ? 1.f : 0.f;
   refined.t[0] = refined.t[1] = refined.t[2] = 0.f;
 
+#ifdef RB200_PROFILE
+  long long pf_fit = 0, pf_score = 0, pf_rounds = 0;
+  const long long pf_t0 = clock64();
+#endif
   for (int refinements = 1; refinements < 20; refinements++) {  // node.cpp:1140
     Rt T;
-    if (!fit_transform<NW>(cfrom, cto, s_cen, s_cen + 3, sel, nw, lane, T)) break;  // node.cpp:1142-1145
+#ifdef RB200_PROFILE
+    const long long c0 = clock64();
+#endif
+    const bool fit_ok = fit_transform<NW>(cfrom, cto, s_cen, s_cen + 3, sel, nw, lane, T);
+#ifdef RB200_PROFILE
+    const long long c1 = clock64();
+    pf_fit += c1 - c0;
+    pf_rounds++;
+#endif
+    if (!fit_ok) break;  // node.cpp:1142-1145
     double err;
     const int cnt = score_all<NW>(sfrom, sto, M, nw, lane, T, sel, err);  // node.cpp:1148
+#ifdef RB200_PROFILE
+    pf_score += clock64() - c1;
+#endif
     if ((unsigned)cnt < min_thr || err > (double)c_params.max_dist_m) break;  // node.cpp:1154
     if (cnt >= refined_cnt && err <= refined_err) {                             // node.cpp:1160
       const int prev = refined_cnt;
@@ -633,6 +706,18 @@ __global__ void __launch_bounds__(kRansacWarps * 32, 3)
     } else
       break;
   }
+#ifdef RB200_PROFILE
+  if (lane == 0) {
+    const int ph = n_begin == 0 ? 0 : (n_end < H ? 1 : 2);
+    atomicAdd(&g_ransac_prof[ph][0], (unsigned long long)pf_fit);
+    atomicAdd(&g_ransac_prof[ph][1], (unsigned long long)pf_score);
+    atomicAdd(&g_ransac_prof[ph][2], (unsigned long long)pf_rounds);
+    atomicAdd(&g_ransac_prof[ph][3], 1ull);
+    atomicAdd(&g_ransac_prof[ph][4], (unsigned long long)(clock64() - pf_t0));
+    atomicMax(&g_ransac_prof[ph][5], (unsigned long long)(clock64() - pf_t0));
+    atomicMax(&g_ransac_prof[ph][6], (unsigned long long)pf_rounds);
+  }
+#endif
   if (lane == 0) {
     HypResult r;
     r.err = refined_err;
@@ -652,7 +737,7 @@ cudaError_t launch_ransac_hypotheses(int npairs, int ransac_iterations, int max_
   if (n_launches) *n_launches = 0;
   if (npairs <= 0 || ransac_iterations <= 0) return cudaSuccess;
   const int H = ransac_iterations;
-  const int bounds[4] = {0, 8, 40, H};  // non-final phase ends must stay <= kMaxScanPrefix
+  const int bounds[4] = {0, RB200_PH1, RB200_PH2, H};  // non-final phase ends must stay <= kMaxScanPrefix
   for (int ph = 0; ph < 3; ph++) {
     const int n_begin = bounds[ph], n_end = bounds[ph + 1] < H ? bounds[ph + 1] : H;
     if (n_begin >= n_end) continue;

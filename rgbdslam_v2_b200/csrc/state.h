@@ -67,6 +67,7 @@ struct State {
   int sm_count = 0;
   rgbdslam_b200_params params;
   DevParams dp;
+  cudaEvent_t epoch = nullptr;  // reference point of rgbdslam_b200_slot_timeline
   double z0 = 0.0;  // latched first depth for depth_covariance (misc2.h:30-35)
   cudaStream_t own_stream = nullptr, stream = nullptr;  // stream of the synchronous entry points (= slot 0)
   int64_t launches = 0;
@@ -74,7 +75,7 @@ struct State {
   Workspace* cur = &ws[0];
   Workspace& W() { return *cur; }
   DevBuf d_f32_a, d_f32_b, d_root_a, d_root_b, d_norm_a, d_norm_b;  // SIFT staging of the synchronous calls
-  int hamming_path = 1;  // 1 = tcgen05 int8 GEMM (hamming_tc.cu), 0 = SIMT popcount (frontend_kernels.cu)
+  int hamming_path = 2;  // 2 = tcgen05 int8 GEMM, 256-query items (default); 1 = 128-query items; 0 = SIMT popcount
   void release_workspaces() {
     for (Workspace& w : ws) w.release();
     DevBuf* all[] = {&d_f32_a, &d_f32_b, &d_root_a, &d_root_b, &d_norm_a, &d_norm_b};

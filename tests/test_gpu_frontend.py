@@ -81,7 +81,7 @@ def test_hamming_tensor_core_path_equals_simt_path(fe, oracle_mod, nq, nt):
         fe.set_hamming_path(0)
         hd0, idx0 = fe.brute_force_search_orb(q, t)
     finally:
-        fe.set_hamming_path(1)
+        fe.set_hamming_path(2)
     ohd, oidx = oracle_mod.brute_force_orb(q, t)
     assert np.array_equal(hd0, ohd) and np.array_equal(idx0, oidx)
     assert np.array_equal(hd1, ohd) and np.array_equal(idx1, oidx)

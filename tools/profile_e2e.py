@@ -28,12 +28,12 @@ dev = {k: torch.empty_like(v, device="cuda") for k, v in pin.items()}
 print("torch H2D of the 4 buffers ms", t(lambda: [dev[k].copy_(pin[k], non_blocking=True) for k in pin]))
 newer = np.array([fe.node_from_features(int(b["id_newer"][k]), q["desc_newer"], q["xyz_newer"]) for k, q in enumerate(b["pairs"])], np.uint64)
 older = np.array([fe.node_from_features(int(b["id_older"][k]), q["desc_older"], q["xyz_older"]) for k, q in enumerate(b["pairs"])], np.uint64)
-print("resident sync              ms", t(lambda: fe.match_node_pairs(newer, older, seed=1, out=(r, None, None))), "device", fe.last_timing())
-fe.set_hamming_path(2)
-print("resident sync, 256-query tc kernel ms", t(lambda: fe.match_node_pairs(newer, older, seed=1, out=(r, None, None))), "device", fe.last_timing())
+print("resident sync (256-query tc kernel) ms", t(lambda: fe.match_node_pairs(newer, older, seed=1, out=(r, None, None))), "device", fe.last_timing())
+fe.set_hamming_path(1)
+print("resident sync, 128-query tc kernel ms", t(lambda: fe.match_node_pairs(newer, older, seed=1, out=(r, None, None))), "device", fe.last_timing())
 fe.set_hamming_path(0)
 print("e2e sync SIMT hamming (no int8 expansion) ms", t(host((r, None, None))))
-fe.set_hamming_path(1)
+fe.set_hamming_path(2)
 # pipelined e2e, depth 3
 outs = []
 for j in range(3):
@@ -54,3 +54,18 @@ for k in range(30):
 host_ms = (time.perf_counter() - t0) / 30 * 1e3
 for j in range(3): fe.wait_slot(1 + j)
 print("host time per submit (incl. implicit drain) ms", host_ms)
+# steady-state timeline (device ms since epoch): submit, h2d done, expand done, match start, match end, ransac end, d2h done
+fe.timeline_epoch(); h0 = time.perf_counter()
+rows = []
+for k in range(24):
+    s = 1 + k % 3
+    tw0 = time.perf_counter()
+    if k >= 3:
+        fe.wait_slot(s); rows.append((k - 3, fe.slot_timeline(s).copy()))
+    tw1 = time.perf_counter()
+    fe.submit_pairs_host(s, pin["desc_newer"], pin["xyz_newer"], b["n_newer"], pin["desc_older"], pin["xyz_older"], b["n_older"], b["id_newer"], b["id_older"], (outs[k % 3][1], None, None), seed=1)
+    tw2 = time.perf_counter()
+    if 12 <= k < 20: print(f"   host k={k} t={1e3*(tw0-h0):7.3f} wait {1e3*(tw1-tw0):6.3f} submit {1e3*(tw2-tw1):6.3f}")
+for j in range(3): fe.wait_slot(1 + j)
+print("timeline  k  submit  h2d_done  expand_done  match_start  match_end  ransac_end  d2h_done")
+for k, tl in rows[8:18]: print("   ", k, " ".join(f"{v:8.3f}" for v in tl))
