@@ -136,6 +136,15 @@ class GpuBackend:
         res, _, _ = self.fe.match_node_pairs(newer, older, seed=seed, want_matches=False)
         return res
 
+    def n_features(self, handle) -> int:
+        return self.fe.node_num_features(handle)
+
+    def match_one_to_many(self, node, olds, seed):
+        """The comparisons of one new node as ONE batched call (graph_manager.cpp:548); RNG keys = 64 * node id + k."""
+        res, _, _ = self.fe.match_node_pairs([node.handle] * len(olds), [o.handle for o in olds], seed=seed,
+                                             first_pair_index=64 * node.id, want_matches=False)
+        return res
+
     def optimize(self, graph, stop):
         x, chi2, _, _ = self.fe.optimize_graph(graph["init"], graph["fixed"], graph["ij"], graph["meas"], graph["info"], stop=stop)
         return x, chi2

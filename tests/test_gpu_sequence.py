@@ -27,6 +27,19 @@ class OracleBackend:
                                        threads=8, want_matches=False)
         return res
 
+    def n_features(self, handle):
+        return len(handle[1])
+
+    def match_one_to_many(self, node, olds, seed):
+        prm = self.o.make_params(depth_cov_z0=2.0)
+        new = node.handle
+        dn = np.concatenate([new[1]] * len(olds)); xn = np.concatenate([new[2]] * len(olds))
+        do = np.concatenate([o.handle[1] for o in olds]); xo = np.concatenate([o.handle[2] for o in olds])
+        res, _, _ = self.o.match_pairs(prm, dn, xn, [len(new[1])] * len(olds), do, xo, [len(o.handle[1]) for o in olds],
+                                       [node.id] * len(olds), [o.id for o in olds], seed=seed, first_pair_index=64 * node.id,
+                                       threads=8, want_matches=False)
+        return res
+
     def optimize(self, graph, stop):
         x, chi2, _, _ = self.o.posegraph_optimize(graph["init"], graph["fixed"], graph["ij"], graph["meas"], graph["info"], stop=stop)
         return x, chi2
@@ -55,6 +68,36 @@ def test_sequence_ate_within_1mm_of_the_oracle(built, oracle_mod):
     assert ate < 0.02, ate                                        # the synthetic room is tracked to < 2 cm
     assert abs(ate - ate_ref) < 1e-3, (ate, ate_ref)              # north star: ATE within 1 mm of the reference path
     assert synth.ate_rmse(out["traj"][:, :3], ref["traj"][:, :3]) < 1e-3
+
+
+def test_online_graph_manager_sequence(built, oracle_mod):
+    """The live front (addNode -> nodeComparisons with Dijkstra / keyframe candidates -> addEdgeToG2O -> optimizeGraph per
+    node, graph_manager.cpp:204-324, 421-782) driven by the CUDA library vs driven by the CPU oracle: same comparisons,
+    same accepted edges, trajectories within 1 mm."""
+    from oracle import orb_oracle
+    from rgbdslam_v2_b200 import Frontend, graph_manager, pipeline, synth
+    from rgbdslam_v2_b200._capi import default_params
+    n = 30
+    poses = synth.trajectory(240)[:n]
+    frames = [synth.render_frame(poses[k], seed=k) for k in range(n)]
+    gray = np.stack([f[0] for f in frames]); depth = np.stack([f[1] for f in frames])
+    mask = np.stack([orb_oracle.depth_to_mask(d) for d in depth])
+    K4 = (synth.FX, synth.FY, synth.CX, synth.CY)
+    p = default_params(); p.depth_cov_z0 = 2.0; p.max_keypoints = 600
+    fe = Frontend(0, p)
+    gm = graph_manager.run_online(pipeline.GpuBackend(fe), gray, depth, mask, K4, seed=9)
+    ref = graph_manager.run_online(OracleBackend(oracle_mod, 600), gray, depth, mask, K4, seed=9)
+    fe.close()
+    assert gm.comparisons == ref.comparisons                      # same candidate sets (they depend on accepted edges)
+    assert len(gm.comparisons[-1][1]) >= 8 and gm.comparisons[-1][1][-1] == n - 2
+    same = len(set(gm.edges) & set(ref.edges)) / max(len(ref.edges), 1)
+    assert same > 0.98 and gm.n_const_edges == ref.n_const_edges and gm.keyframe_ids == ref.keyframe_ids
+    ids, traj = gm.trajectory(); rids, rtraj = ref.trajectory()
+    assert list(ids) == list(rids) == list(range(n))
+    gt = np.stack([pipeline.mat_to_pose7(np.linalg.inv(poses[0]) @ P) for P in poses])
+    ate, ate_ref = synth.ate_rmse(traj[:, :3], gt[:, :3]), synth.ate_rmse(rtraj[:, :3], gt[:, :3])
+    assert ate < 0.03 and abs(ate - ate_ref) < 1e-3, (ate, ate_ref)
+    assert synth.ate_rmse(traj[:, :3], rtraj[:, :3]) < 1e-3
 
 
 def _oracle_edge_chi2(self, poses, graph):
