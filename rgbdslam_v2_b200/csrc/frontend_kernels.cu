@@ -157,6 +157,9 @@ cudaError_t launch_select_matches(const PairDesc* pairs, int npairs, const int2*
 // RANSAC building blocks (warp-cooperative; every lane ends up with identical, warp-uniform results).
 
 constexpr unsigned kFull = 0xffffffffu;
+#ifndef RB200_SCORE_GROUP
+#define RB200_SCORE_GROUP 5  // correspondences (mask words) scored per lane without an intervening branch
+#endif
 
 __device__ __forceinline__ float wsum(float v) {
 #pragma unroll
@@ -337,15 +340,15 @@ __device__ __forceinline__ double depth_cov(double z) {  // misc2.h:20-35 (stati
   return __dmul_rn(sd, sd);
 }
 
-// Per-hypothesis constants of the scoring pass (warp-uniform), float64.
+// Per-hypothesis constants of the float64 scoring formula (warp-uniform).  Only built when some correspondence of the
+// warp's current 32 cannot be classified in float32 (score_all).
 struct ScoreCtx {
   double R[9], t[3];
   double P[6];   // rcx * r0_i r0_j + rcy * r1_i r1_j   (ij = 00,01,02,11,12,22), r_k = k-th row of R
   double O2[6];  // r2_i r2_j
-  float Pf[6], O2f[6];  // float copies for the screening pass
 };
 
-__device__ __forceinline__ void make_score_ctx(const Rt& T, ScoreCtx& c) {
+__device__ __noinline__ void make_score_ctx(const Rt& T, ScoreCtx& c) {
 #pragma unroll
   for (int i = 0; i < 9; i++) c.R[i] = (double)T.R[i];  // transformation4f.cast<double>() (node.cpp:984)
 #pragma unroll
@@ -356,29 +359,46 @@ __device__ __forceinline__ void make_score_ctx(const Rt& T, ScoreCtx& c) {
   for (int k = 0; k < 6; k++) {
     c.P[k] = fma(__dmul_rn(rcx, c.R[I[k]]), c.R[J[k]], __dmul_rn(__dmul_rn(rcy, c.R[3 + I[k]]), c.R[3 + J[k]]));
     c.O2[k] = __dmul_rn(c.R[6 + I[k]], c.R[6 + J[k]]);
-    c.Pf[k] = (float)c.P[k];
-    c.O2f[k] = (float)c.O2[k];
   }
 }
 
-// float32 screening of errorFunction2: returns the class of the correspondence without touching the FP64 pipe when
-// the answer is not close to a decision boundary.
-//   0: certainly rejected (shortcut of misc.cpp:726-735 or d^2 > thr)    1: certainly an inlier, *m_out = d^2 (float)
-//   2: too close to call in float32 -> the caller evaluates the float64 reference formula
+// The same constants in float32 for the screening pass, plus the loop invariants of the covariance model.
+struct ScreenCtx {
+  float Pf[6], O2f[6];
+  float rcx, rcy, sq_max, sigma_depth;
+  float czc;  // constant depth covariance (misc2.h static cache), < 0: per-point (sigma_depth * z^2)^2 model
+};
+
+__device__ __forceinline__ void make_screen_ctx(const Rt& T, ScreenCtx& c) {
+  c.rcx = (float)c_params.raster_cov_x;
+  c.rcy = (float)c_params.raster_cov_y;
+  c.sq_max = (float)c_params.sq_max_dist;
+  c.czc = (float)c_params.cov_z_const;
+  c.sigma_depth = (float)c_params.sigma_depth;
+  const int I[6] = {0, 0, 0, 1, 1, 2}, J[6] = {0, 1, 2, 1, 2, 2};
+#pragma unroll
+  for (int k = 0; k < 6; k++) {
+    c.Pf[k] = fmaf(c.rcx * T.R[I[k]], T.R[J[k]], (c.rcy * T.R[3 + I[k]]) * T.R[3 + J[k]]);
+    c.O2f[k] = T.R[6 + I[k]] * T.R[6 + J[k]];
+  }
+}
+
+// float32 screening of errorFunction2, branch-free so that the unrolled scoring loop interleaves several
+// correspondences (the kernel is bound by dependent-instruction latency, not by issue slots).  Returns
+//   m >= 0 : certainly an inlier, value = d^2 (float)          -1 : certainly rejected (shortcut of misc.cpp:726-735,
+//   d^2 > thr, NaN depth)                                      NaN: too close to call in float32 -> the caller
+//                                                                   evaluates the float64 reference formula
 // Margins: 1e-3 relative on both tests, orders of magnitude above the float32 evaluation error (~1e-5 relative for
 // the 3x3 SPD solve with condition number < 1e2).
-__device__ __forceinline__ int mahal_screen(const float4 x1, const float4 x2, const Rt& T, const ScoreCtx& c, float sq_max,
-                                            float* m_out) {
-  if (isnan(x1.z) || isnan(x2.z)) return 0;
+__device__ __forceinline__ float mahal_screen(const float4 x1, const float4 x2, const Rt& T, const ScreenCtx& c) {
   const float d0 = fmaf(T.R[0], x1.x, fmaf(T.R[1], x1.y, fmaf(T.R[2], x1.z, T.t[0] * x1.w))) - x2.x;
   const float d1 = fmaf(T.R[3], x1.x, fmaf(T.R[4], x1.y, fmaf(T.R[5], x1.z, T.t[1] * x1.w))) - x2.y;
   const float d2 = fmaf(T.R[6], x1.x, fmaf(T.R[7], x1.y, fmaf(T.R[8], x1.z, T.t[2] * x1.w))) - x2.z;
-  const float rcx = (float)c_params.raster_cov_x, rcy = (float)c_params.raster_cov_y;
-  const float cz1 = (float)depth_cov((double)x1.z), cz2 = (float)depth_cov((double)x2.z);
+  const float rcx = c.rcx, rcy = c.rcy;
+  const float sd1 = c.sigma_depth * (x1.z * x1.z), sd2 = c.sigma_depth * (x2.z * x2.z);
+  const float cz1 = c.czc < 0.f ? sd1 * sd1 : c.czc, cz2 = c.czc < 0.f ? sd2 * sd2 : c.czc;
   const float dsq = fmaf(d0, d0, fmaf(d1, d1, d2 * d2));
   const float lim = 2.f * (fmaxf(rcx, cz1) + fmaxf(rcx, cz2));
-  if (dsq > lim * 1.001f) return 0;
-  if (!(dsq < lim * 0.999f)) return 2;
   const float a2 = x1.z, b2 = x2.z;
   const float S00 = fmaf(a2, c.Pf[0], fmaf(cz1, c.O2f[0], rcx * b2));
   const float S01 = fmaf(a2, c.Pf[1], cz1 * c.O2f[1]);
@@ -395,14 +415,12 @@ __device__ __forceinline__ int mahal_screen(const float4 x1, const float4 x2, co
   const float e0 = fmaf(A00, d0, fmaf(A01, d1, A02 * d2));
   const float e1 = fmaf(A01, d0, fmaf(A11, d1, A12 * d2));
   const float e2 = fmaf(A02, d0, fmaf(A12, d1, A22 * d2));
-  const float m = fmaf(d0, e0, fmaf(d1, e1, d2 * e2)) * k / det;
-  if (!(m >= 0.f) || !(det > 0.f)) return 2;
-  if (m > sq_max * 1.001f) return 0;
-  if (m < sq_max * 0.999f) {
-    *m_out = m;
-    return 1;
-  }
-  return 2;
+  const float m = __fdividef(fmaf(d0, e0, fmaf(d1, e1, d2 * e2)) * k, det);
+  const float undecided = __int_as_float(0x7fc00000);
+  const bool reject1 = isnan(x1.z) || isnan(x2.z) || dsq > lim * 1.001f;
+  const bool unsure = !(dsq < lim * 0.999f) || !(m >= 0.f) || !(det > 0.f);
+  const float r = (m > c.sq_max * 1.001f) ? -1.f : ((m < c.sq_max * 0.999f) ? m : undecided);
+  return reject1 ? -1.f : (unsure ? undecided : r);
 }
 
 // errorFunction2 (misc.cpp:697-770) in float64.  Written with explicit rounding intrinsics only, so the
@@ -454,30 +472,50 @@ __device__ __forceinline__ double mahal_sq(const float4 x1, const float4 x2, con
 template <int NW>
 __device__ int score_all(const float4* __restrict__ sfrom, const float4* __restrict__ sto, int M, int nw, int lane,
                          const Rt& T, uint32_t* words, double& err) {
-  ScoreCtx ctx;
-  make_score_ctx(T, ctx);
+  ScreenCtx sc;
+  make_screen_ctx(T, sc);
   const double sq_max = c_params.sq_max_dist;
+  // pass 1: classify every correspondence in float32.  No branches inside a group of kGroup words, so the compiler
+  // interleaves kGroup independent dependency chains per lane.
+  constexpr int kGroup = (NW % RB200_SCORE_GROUP == 0) ? RB200_SCORE_GROUP : 4;
+  float code[NW];
+#pragma unroll
+  for (int g = 0; g < NW; g += kGroup) {
+    if (g < nw) {
+#pragma unroll
+      for (int w = g; w < g + kGroup; w++) {
+        const int i = w * 32 + lane;  // < kMaxMatchesCap: rows >= M hold stale but addressable shared memory
+        const float4 a = sfrom[i], b = sto[i];
+        const float cm = mahal_screen(a, b, T, sc);
+        code[w] = (i < M && !(a.z == 0.0f || b.z == 0.0f)) ? cm : -1.f;  // node.cpp:994 (does not trigger on NaN)
+      }
+    } else {
+#pragma unroll
+      for (int w = g; w < g + kGroup; w++) code[w] = -1.f;
+    }
+  }
+  // pass 2: the float64 reference formula where float32 could not decide, inlier masks, error sum
+  ScoreCtx ctx;
+  bool have_ctx = false;
   double esum = 0.0;
   int cnt = 0;
 #pragma unroll
   for (int w = 0; w < NW; w++) {
     uint32_t word = 0;
     if (w < nw) {
-      const int i = w * 32 + lane;
-      bool inl = false;
-      double m = 0.0;
-      if (i < M) {
-        const float4 a = sfrom[i], b = sto[i];
-        if (!(a.z == 0.0f || b.z == 0.0f)) {  // node.cpp:994 (does not trigger on NaN)
-          float mf;
-          const int cls = mahal_screen(a, b, T, ctx, (float)sq_max, &mf);
-          if (cls == 1) {
-            m = (double)mf;
-            inl = true;
-          } else if (cls == 2) {  // float32 cannot decide: the float64 reference formula
-            m = mahal_sq(a, b, ctx);
-            inl = !(m > sq_max) && (m >= 0.0);  // node.cpp:998-1005
-          }
+      const float cm = code[w];
+      const bool undecided = isnan(cm);
+      bool inl = cm >= 0.f;
+      double m = (double)cm;
+      if (__any_sync(kFull, undecided)) {
+        if (!have_ctx) {
+          make_score_ctx(T, ctx);
+          have_ctx = true;
+        }
+        if (undecided) {
+          const int i = w * 32 + lane;
+          m = mahal_sq(sfrom[i], sto[i], ctx);
+          inl = !(m > sq_max) && (m >= 0.0);  // node.cpp:998-1005
         }
       }
       word = __ballot_sync(kFull, inl);
@@ -505,10 +543,10 @@ __device__ __forceinline__ unsigned min_inlier_threshold(int M) {  // node.cpp:1
 #define RB200_RANSAC_MINBLOCKS 3
 #endif
 #ifndef RB200_PH1
-#define RB200_PH1 8
+#define RB200_PH1 4
 #endif
 #ifndef RB200_PH2
-#define RB200_PH2 40
+#define RB200_PH2 4
 #endif
 constexpr int kRansacWarps = RB200_RANSAC_WARPS;
 #ifdef RB200_PROFILE

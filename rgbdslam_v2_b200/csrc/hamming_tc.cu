@@ -312,8 +312,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_match_kernel(const HamItem* 
 //   warps : 0 = bulk-copy producer, 1 = MMA issuer, 2..9 = epilogue (warp group g drains half g)
 constexpr uint32_t kA256 = 256 * 256;  // 64 KiB
 constexpr uint32_t kB128 = 128 * 256;  // 32 KiB
-constexpr uint32_t kSmem256Bars = 2 * kA256 + 2 * kB128;
-constexpr uint32_t kTc256SmemBytes = kSmem256Bars + 128;
+// Ring depths: the query block (A, 64 KiB) is double-buffered across items, the train tiles (B, 32 KiB) stream through
+// a 3-deep ring -- one tile feeds ~1.1 k cycles of MMA, an L2 / HBM fetch takes longer than that, so two stages stall
+// the tensor pipe on every tile (measured 61 us vs 75 us for the shallower variants).  224 KiB + barriers <= 227 KiB.
+#ifndef RB200_TC256_ASTAGES
+#define RB200_TC256_ASTAGES 2
+#endif
+#ifndef RB200_TC256_BSTAGES
+#define RB200_TC256_BSTAGES 3
+#endif
+constexpr int kASt = RB200_TC256_ASTAGES, kBSt = RB200_TC256_BSTAGES;
+constexpr uint32_t kSmem256Bars = kASt * kA256 + kBSt * kB128;
+constexpr uint32_t kTc256SmemBytes = kSmem256Bars + 256;
+static_assert(kTc256SmemBytes <= 232448, "tc_match256: shared memory over the 227 KiB per-CTA limit");
+// barrier slots
+constexpr int kBarAFull = 0, kBarAEmpty = kASt, kBarBFull = 2 * kASt, kBarBEmpty = 2 * kASt + kBSt,
+              kBarAccFull = 2 * kASt + 2 * kBSt, kBarAccEmpty = kBarAccFull + 2, kBarCount = kBarAccEmpty + 2;
+static_assert(kBarCount * 8 <= 192, "barrier area");
 constexpr int kTc256Threads = 320;
 constexpr uint32_t kIdescI8_N128 = (2u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
 constexpr uint32_t kIdescBF16_N128 = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
@@ -322,16 +337,16 @@ template <int MODE>
 __global__ void __launch_bounds__(kTc256Threads, 1) tc_match256_kernel(const HamItem* __restrict__ items, int n_items) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sA = smem_u32(smem);
-  const uint32_t sB = sA + 2 * kA256;
+  const uint32_t sB = sA + kASt * kA256;
   const uint32_t bars = sA + kSmem256Bars;
-  auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };  // same slot map as tc_match_kernel
-  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + kSmem256Bars + 96);
+  auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + kSmem256Bars + 192);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 10; i++) mbar_init(bar(i), 1);
-    mbar_init(bar(10), 8);  // tmem_empty: one arrival per epilogue warp
-    mbar_init(bar(11), 8);
+    for (int i = 0; i < kBarAccEmpty; i++) mbar_init(bar(i), 1);
+    mbar_init(bar(kBarAccEmpty), 8);  // tmem_empty: one arrival per epilogue warp
+    mbar_init(bar(kBarAccEmpty + 1), 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -349,15 +364,15 @@ __global__ void __launch_bounds__(kTc256Threads, 1) tc_match256_kernel(const Ham
       uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
       for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
         const HamItem item = items[it];
-        mbar_wait(bar(2 + sa), pa ^ 1);
-        mbar_expect_tx(bar(0 + sa), kA256);
-        bulk_g2s(sA + sa * kA256, item.a, kA256, bar(0 + sa));
-        if (++sa == 2) { sa = 0; pa ^= 1; }
+        mbar_wait(bar(kBarAEmpty + sa), pa ^ 1);
+        mbar_expect_tx(bar(kBarAFull + sa), kA256);
+        bulk_g2s(sA + sa * kA256, item.a, kA256, bar(kBarAFull + sa));
+        if (++sa == kASt) { sa = 0; pa ^= 1; }
         for (int nb = 0; nb < item.n_btiles; nb++) {
-          mbar_wait(bar(6 + sb), pb ^ 1);
-          mbar_expect_tx(bar(4 + sb), kB128);
-          bulk_g2s(sB + sb * kB128, item.b + (size_t)nb * kB128, kB128, bar(4 + sb));
-          if (++sb == 2) { sb = 0; pb ^= 1; }
+          mbar_wait(bar(kBarBEmpty + sb), pb ^ 1);
+          mbar_expect_tx(bar(kBarBFull + sb), kB128);
+          bulk_g2s(sB + sb * kB128, item.b + (size_t)nb * kB128, kB128, bar(kBarBFull + sb));
+          if (++sb == kBSt) { sb = 0; pb ^= 1; }
         }
       }
     }
@@ -366,11 +381,11 @@ __global__ void __launch_bounds__(kTc256Threads, 1) tc_match256_kernel(const Ham
       uint32_t sa = 0, pa = 0, sb = 0, pb = 0, acc = 0, pacc = 0;
       for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
         const int n_btiles = items[it].n_btiles;
-        mbar_wait(bar(0 + sa), pa);
+        mbar_wait(bar(kBarAFull + sa), pa);
         tc_fence_after();
         for (int nb = 0; nb < n_btiles; nb++) {
-          mbar_wait(bar(4 + sb), pb);
-          mbar_wait(bar(10 + acc), pacc ^ 1);
+          mbar_wait(bar(kBarBFull + sb), pb);
+          mbar_wait(bar(kBarAccEmpty + acc), pacc ^ 1);
           tc_fence_after();
           const uint32_t a0 = sA + sa * kA256, b0 = sB + sb * kB128;
 #pragma unroll
@@ -384,13 +399,13 @@ __global__ void __launch_bounds__(kTc256Threads, 1) tc_match256_kernel(const Ham
                 tc_mma_bf16(d, make_desc(a0 + h * kTileA + k * 256), make_desc(b0 + k * 256), kIdescBF16_N128, k > 0 ? 1u : 0u);
             }
           }
-          tc_commit(bar(6 + sb));
-          tc_commit(bar(8 + acc));
-          if (++sb == 2) { sb = 0; pb ^= 1; }
+          tc_commit(bar(kBarBEmpty + sb));
+          tc_commit(bar(kBarAccFull + acc));
+          if (++sb == kBSt) { sb = 0; pb ^= 1; }
           if (++acc == 2) { acc = 0; pacc ^= 1; }
         }
-        tc_commit(bar(2 + sa));
-        if (++sa == 2) { sa = 0; pa ^= 1; }
+        tc_commit(bar(kBarAEmpty + sa));
+        if (++sa == kASt) { sa = 0; pa ^= 1; }
       }
     }
   } else {
@@ -404,7 +419,7 @@ __global__ void __launch_bounds__(kTc256Threads, 1) tc_match256_kernel(const Ham
       float s0 = -3.0e38f, s1 = -3.0e38f, s2 = -3.0e38f, s3 = -3.0e38f;
       int i0 = -1, i1 = -1, i2 = -1, i3 = -1;
       for (int nb = 0; nb < item.n_btiles; nb++) {
-        mbar_wait(bar(8 + acc), pacc);
+        mbar_wait(bar(kBarAccFull + acc), pacc);
         tc_fence_after();
         const uint32_t t0 = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * 256 + h * 128;
 #pragma unroll 1
@@ -444,7 +459,7 @@ __global__ void __launch_bounds__(kTc256Threads, 1) tc_match256_kernel(const Ham
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar(10 + acc));
+        if (lane == 0) mbar_arrive(bar(kBarAccEmpty + acc));
         if (++acc == 2) { acc = 0; pacc ^= 1; }
       }
       if (row < item.nq_valid) {

@@ -69,3 +69,28 @@ for k in range(24):
 for j in range(3): fe.wait_slot(1 + j)
 print("timeline  k  submit  h2d_done  expand_done  match_start  match_end  ransac_end  d2h_done")
 for k, tl in rows[8:18]: print("   ", k, " ".join(f"{v:8.3f}" for v in tl))
+# depth-1 split: host time inside submit vs inside wait (slot 0 = library stream, slot 1 = own stream)
+for s in (0, 1):
+    ts, tw = [], []
+    for k in range(12):
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        fe.submit_pairs_host(s, pin["desc_newer"], pin["xyz_newer"], b["n_newer"], pin["desc_older"], pin["xyz_older"], b["n_older"], b["id_newer"], b["id_older"], (r, None, None), seed=1)
+        t1 = time.perf_counter(); fe.wait_slot(s); t2 = time.perf_counter()
+        if k >= 2: ts.append(t1 - t0); tw.append(t2 - t1)
+    print(f"depth-1 slot {s}: submit {1e3*np.median(ts):.3f} ms, wait {1e3*np.median(tw):.3f} ms, stages", fe.stage_times(s))
+# pipelined with the match lists downloaded too, and with three distinct batches (cold L2) like bench.py
+bs = [synth.make_batch(256, 1000, seed0=1 + 256 * j) for j in range(3)]
+pins = [{k: torch.from_numpy(bb[k]).pin_memory() for k in ("desc_newer", "xyz_newer", "desc_older", "xyz_older")} for bb in bs]
+mm = [(torch.zeros(256 * 300 * 16, dtype=torch.uint8).pin_memory(), torch.zeros(256 * 300 * 16, dtype=torch.uint8).pin_memory()) for _ in range(3)]
+def pipe2(K, matches, distinct):
+    for k in range(K):
+        j = k % 3; bb, pp = (bs[j], pins[j]) if distinct else (b, pin)
+        o = (outs[j][1], mm[j][0].numpy().view(DMATCH_DTYPE).reshape(256, 300), mm[j][1].numpy().view(DMATCH_DTYPE).reshape(256, 300)) if matches else (outs[j][1], None, None)
+        if k >= 3: fe.wait_slot(1 + j)
+        fe.submit_pairs_host(1 + j, pp["desc_newer"], pp["xyz_newer"], bb["n_newer"], pp["desc_older"], pp["xyz_older"], bb["n_older"], bb["id_newer"], bb["id_older"], o, seed=1)
+    for j in range(3): fe.wait_slot(1 + j)
+for matches in (False, True):
+    for distinct in (False, True):
+        for K in (20, 200):
+            pipe2(6, matches, distinct); torch.cuda.synchronize(); t0 = time.perf_counter(); pipe2(K, matches, distinct); torch.cuda.synchronize()
+            print(f"pipelined e2e matches={matches} distinct_batches={distinct} K={K}: {(time.perf_counter() - t0) / K * 1e3:.3f} ms/step")

@@ -21,6 +21,23 @@ if len(sys.argv) > 1 and sys.argv[1] == "--child":
             fe.match_node_pairs(newer, older, seed=1, out=(r, None, None))
             if k >= 3: st.append(fe.stage_times(0))
         out[f"path{path}"] = {k: round(float(np.median([s[k] for s in st])) * 1e3, 1) for k in ("hamming", "select_ransac", "total")}
+    # pipelined resident throughput, 3 slots x 3 distinct batches (what bench.py's `value` measures)
+    import time
+    sets = []
+    for j in range(3):
+        bb = synth.make_batch(256, 1000, seed0=5000 + 256 * j)
+        nw = np.array([fe.node_from_features(int(bb["id_newer"][k]), q["desc_newer"], q["xyz_newer"]) for k, q in enumerate(bb["pairs"])], np.uint64)
+        od = np.array([fe.node_from_features(int(bb["id_older"][k]), q["desc_older"], q["xyz_older"]) for k, q in enumerate(bb["pairs"])], np.uint64)
+        sets.append((nw, od, np.zeros(256, PAIR_RESULT_DTYPE)))
+    def pipe(K):
+        for k in range(K):
+            j = k % 3
+            if k >= 3: fe.wait_slot(1 + j)
+            fe.submit_node_pairs(1 + j, sets[j][0], sets[j][1], (sets[j][2], None, None), seed=1)
+        for j in range(3): fe.wait_slot(1 + j)
+    fe.set_hamming_path(2)
+    pipe(9); torch.cuda.synchronize(); t0 = time.perf_counter(); pipe(60); torch.cuda.synchronize()
+    out["pipelined_us_per_step"] = round((time.perf_counter() - t0) / 60 * 1e6, 1)
     out["valid"] = int((r["id1"] >= 0).sum()); out["inl_sum"] = int(r["n_inliers"].sum()); out["rmse_sum"] = float(r["rmse"].sum())
     if hasattr(fe.lib, "rb200_debug_ransac_profile"):
         buf = (C.c_ulonglong * 24)()
