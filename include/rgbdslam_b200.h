@@ -160,6 +160,15 @@ int rgbdslam_b200_node_create_from_sift(int32_t id, const float* desc128, const 
  * entries per query row (squared L2 distances, as cv::flann returns them).  RootSIFT applied per params. */
 int rgbdslam_b200_knn2_l2(const float* q, int nq, const float* t, int nt, int32_t* idx2, float* dist2);
 
+/* Matcher used by float-descriptor nodes CREATED AFTER the call (parameter `matcher_type`, parameter_server.cpp:82):
+ *   0 (default)  exact 2-NN + ratio / uniqueness test -- the FLANN branch, src/node.cpp:610-667;
+ *   1            the SiftGPU matcher, src/node.cpp:553-557 -> SiftGPUWrapper::match (src/sift_gpu_wrapper.cpp:169-227):
+ *                descriptors quantised to unsigned 8 bit (external/SiftGPU/src/SiftGPU/SiftMatchCU.cpp:87-101), integer
+ *                dot-product matrix, acos distance < 0.9, ratio < 0.9, mutual best match (ProgramCU.cu:1405-1478,
+ *                1689-1784, SiftMatchCU.cpp:139-176), DMatch.distance = float L2 of the raw rows.  Bit-exact restatement;
+ *                the nodes keep the raw rows (no RootSIFT).  Both nodes of a pair must be of the same kind. */
+int rgbdslam_b200_set_sift_matcher(int matcher);
+
 /* ---- frame-pair matching --------------------------------------------------
  * == Node::matchNodePair (node.cpp:1305-1429) for npairs independent pairs
  * (the QtConcurrent::blockingMapped fan-out of graph_manager.cpp:548 as one

@@ -118,6 +118,7 @@ def load_library(path: str | Path | None = None) -> C.CDLL:
     lib.rgbdslam_b200_match_pairs_host_submit.argtypes = [C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, u64, i64, vp, vp, vp]
     lib.rgbdslam_b200_match_pairs_wait.argtypes = [C.c_int]
     lib.rgbdslam_b200_set_hamming_path.argtypes = [C.c_int]
+    lib.rgbdslam_b200_set_sift_matcher.argtypes = [C.c_int]
     lib.rgbdslam_b200_detector_create.argtypes = [C.POINTER(u64)]
     lib.rgbdslam_b200_detector_destroy.argtypes = [u64]
     lib.rgbdslam_b200_detector_thresholds.argtypes = [u64, vp, C.c_int]
@@ -192,6 +193,10 @@ class Frontend:
     def set_hamming_path(self, path: int):
         """1 = tcgen05 int8 tensor-core GEMM (default), 0 = SIMT popcount."""
         self._check(self.lib.rgbdslam_b200_set_hamming_path(path))
+
+    def set_sift_matcher(self, matcher: int):
+        """0 = exact 2-NN ratio matcher (FLANN branch), 1 = SiftGPU matcher; applies to SIFT nodes created afterwards"""
+        self._check(self.lib.rgbdslam_b200_set_sift_matcher(matcher))
 
     def synchronize(self):
         self._check(self.lib.rgbdslam_b200_synchronize())

@@ -153,7 +153,7 @@ static int expand_nodes(const std::vector<ExpandJob>& jobs, int phase = 3) {
 int expand_nodes_public(const std::vector<ExpandJob>& jobs) { return expand_nodes(jobs); }
 
 // RootSIFT + bf16 tiles + norms of a set of SIFT nodes.
-static int prepare_sift_nodes(const std::vector<SiftJob>& jobs) {
+static int prepare_sift_nodes(const std::vector<SiftJob>& jobs, int siftgpu = 0) {
   State& s = g_state;
   if (jobs.empty()) return 0;
   int rc;
@@ -164,7 +164,7 @@ static int prepare_sift_nodes(const std::vector<SiftJob>& jobs) {
   memcpy(s.W().h_jobs.ptr, jobs.data(), sizeof(SiftJob) * jobs.size());
   cudaError_t e = cudaMemcpyAsync(s.W().d_jobs.ptr, s.W().h_jobs.ptr, sizeof(SiftJob) * jobs.size(), cudaMemcpyHostToDevice, s.W().stream);
   if (e != cudaSuccess) return cuda_fail(e, "upload sift jobs");
-  e = launch_sift_prepare((const SiftJob*)s.W().d_jobs.ptr, (int)jobs.size(), max_pad, s.params.use_root_sift ? 1 : 0, s.W().stream);
+  e = launch_sift_prepare((const SiftJob*)s.W().d_jobs.ptr, (int)jobs.size(), max_pad, s.params.use_root_sift ? 1 : 0, siftgpu, s.W().stream);
   if (e != cudaSuccess) return cuda_fail(e, "sift_prepare kernel");
   s.launches += 1;
   return 0;
@@ -172,16 +172,20 @@ static int prepare_sift_nodes(const std::vector<SiftJob>& jobs) {
 
 // Work items of the tensor-core match kernels (128- or 256-query blocks of every pair), staged on the stream.
 // Returns the item count in *n_items.
-static int stage_match_items(const PairDesc* h_pairs, int npairs, int stride, bool sift, int* n_items) {
+// kind: 0 = ORB Hamming, 1 = SIFT bf16 scores (exact 2-NN matcher), 2 = SiftGPU matcher (u8 dots; one item set with the
+// newer node's rows as queries and one with the roles swapped -- the row and the column pass of GetSiftMatch)
+static int stage_match_items(const PairDesc* h_pairs, int npairs, int stride, int kind, int* n_items) {
   State& s = g_state;
   *n_items = 0;
+  const bool sift = kind != 0;
   if (!sift && s.hamming_path == 0) return 0;
   int rc;
   if (sift) {
     if ((rc = s.W().d_top4.ensure(sizeof(int4) * (size_t)npairs * stride))) return rc;
     if ((rc = s.W().d_knn.ensure(sizeof(float4) * (size_t)npairs * stride))) return rc;
   }
-  const int mblk = s.hamming_path == 2 ? 256 : 128, nblk = s.hamming_path == 2 ? 128 : 256;
+  const bool wide = s.hamming_path == 2 || kind == 2;  // 256-query items (tc_match256_kernel)
+  const int mblk = wide ? 256 : 128, nblk = wide ? 128 : 256;
   std::vector<HamItem> items;
   items.reserve((size_t)npairs * 8);
   for (int p = 0; p < npairs; p++) {
@@ -190,20 +194,26 @@ static int stage_match_items(const PairDesc* h_pairs, int npairs, int stride, bo
       set_error("internal: tensor-core match path without tiled operands");
       return RGBDSLAM_B200_ERR_STATE;
     }
-    // bruteForceSearchORB never looks at the last train row (features.cpp:174); FLANN searches every row
-    const int nsearch = sift ? pd.nt : (pd.nt - 1 > 0 ? pd.nt - 1 : 0);
-    for (int m0 = 0; m0 < pd.nq; m0 += mblk) {
-      HamItem it;
-      it.a = pd.q_i8 + (size_t)m0 * 256;
-      it.b = pd.t_i8;
-      it.out = sift ? reinterpret_cast<int2*>(reinterpret_cast<int4*>(s.W().d_top4.ptr) + (size_t)p * stride + m0)
-                    : reinterpret_cast<int2*>(s.W().d_best.ptr) + (size_t)p * stride + m0;
-      it.nq_valid = pd.nq - m0 < mblk ? pd.nq - m0 : mblk;
-      it.nsearch = nsearch;
-      it.n_btiles = (nsearch + nblk - 1) / nblk;
-      it.pad_ = 0;
-      it.bnorm = sift ? pd.t_norm : nullptr;
-      items.push_back(it);
+    for (int pass = 0; pass < (kind == 2 ? 2 : 1); pass++) {
+      const int8_t* a = pass ? pd.t_i8 : pd.q_i8;
+      const int8_t* b = pass ? pd.q_i8 : pd.t_i8;
+      const int na = pass ? pd.nt : pd.nq, nb = pass ? pd.nq : pd.nt;
+      // bruteForceSearchORB never looks at the last train row (features.cpp:174); the float matchers search every row
+      const int nsearch = sift ? nb : (nb - 1 > 0 ? nb - 1 : 0);
+      for (int m0 = 0; m0 < na; m0 += mblk) {
+        HamItem it;
+        it.a = a + (size_t)m0 * 256;
+        it.b = b;
+        if (!sift) it.out = reinterpret_cast<int2*>(s.W().d_best.ptr) + (size_t)p * stride + m0;
+        else if (pass == 0) it.out = reinterpret_cast<int2*>(reinterpret_cast<int4*>(s.W().d_top4.ptr) + (size_t)p * stride + m0);
+        else it.out = reinterpret_cast<int2*>(reinterpret_cast<int4*>(s.W().d_knn.ptr) + (size_t)p * stride + m0);
+        it.nq_valid = na - m0 < mblk ? na - m0 : mblk;
+        it.nsearch = nsearch;
+        it.n_btiles = (nsearch + nblk - 1) / nblk;
+        it.pad_ = pass;  // SiftGPU: tie rule of RowMatch_Kernel (0) / ColMatch_Kernel (1)
+        it.bnorm = kind == 1 ? pd.t_norm : nullptr;
+        items.push_back(it);
+      }
     }
   }
   if (items.empty()) return 0;
@@ -270,7 +280,11 @@ static int run_pairs(const std::vector<PairDesc>& h_pairs, uint64_t seed, int64_
     }
     max_nq = pd.nq > max_nq ? pd.nq : max_nq;
   }
-  const int stride = (max_nq + 127) / 128 * 128 + 128;
+  const bool siftgpu = h_pairs[0].q_f32 && h_pairs[0].sift_kind == 1;
+  int max_rows = max_nq;
+  if (siftgpu)
+    for (const PairDesc& pd : h_pairs) max_rows = pd.nt > max_rows ? pd.nt : max_rows;  // the column pass is indexed by train row
+  const int stride = (max_rows + 127) / 128 * 128 + 128;
   const int maxM = s.params.max_matches;
   const int H = s.params.ransac_iterations;
   int rc;
@@ -297,13 +311,31 @@ static int run_pairs(const std::vector<PairDesc>& h_pairs, uint64_t seed, int64_
     set_error("match_pairs: ORB and SIFT pairs cannot be mixed in one call");
     return RGBDSLAM_B200_ERR_ARG;
   }
+  for (const PairDesc& pd : h_pairs)
+    if (any_sift && (pd.sift_kind == 1) != siftgpu) {
+      set_error("match_pairs: SiftGPU-matcher nodes and ratio-matcher nodes cannot be mixed in one call");
+      return RGBDSLAM_B200_ERR_ARG;
+    }
   int n_items = 0;
-  if ((rc = stage_match_items(h_pairs.data(), npairs, stride, any_sift, &n_items))) return rc;
+  if ((rc = stage_match_items(h_pairs.data(), npairs, stride, any_sift ? (siftgpu ? 2 : 1) : 0, &n_items))) return rc;
   // every table of this call is on its way; now the bulk uploads + operand expansion of the host-feature path
   if (after_tables && (rc = after_tables())) return rc;
 
   cudaEventRecord(s.W().ev[0], st);
-  if (any_sift) {
+  if (siftgpu) {
+    cudaEventRecord(s.W().ev[3], st);
+    if (n_items > 0) {
+      e = launch_siftgpu_tc256((const HamItem*)s.W().d_items.ptr, n_items, s.sm_count, st);
+      if (e != cudaSuccess) return cuda_fail(e, "siftgpu tensor-core kernel");
+      s.launches += 1;
+    }
+    cudaEventRecord(s.W().ev[1], st);
+    e = launch_select_siftgpu(d_pairs, npairs, (const int4*)s.W().d_top4.ptr, (const int4*)s.W().d_knn.ptr, stride, maxM,
+                              (rgbdslam_b200_dmatch*)s.W().d_matches.ptr, (float4*)s.W().d_mfrom.ptr, (float4*)s.W().d_mto.ptr,
+                              (int32_t*)s.W().d_nall.ptr, st);
+    if (e != cudaSuccess) return cuda_fail(e, "select_siftgpu kernel");
+    s.launches += 1;
+  } else if (any_sift) {
     if ((rc = launch_sift_knn(d_pairs, npairs, max_nq, stride, n_items, st))) return rc;
     e = launch_select_sift(d_pairs, npairs, (const float4*)s.W().d_knn.ptr, stride, (float)s.params.nn_distance_ratio, maxM,
                            (rgbdslam_b200_dmatch*)s.W().d_matches.ptr, (float4*)s.W().d_mfrom.ptr, (float4*)s.W().d_mto.ptr,
@@ -506,6 +538,16 @@ int rgbdslam_b200_synchronize(void) {
   return 0;
 }
 
+int rgbdslam_b200_set_sift_matcher(int matcher) {
+  std::lock_guard<std::mutex> lk(g_state.mu);
+  if (matcher < 0 || matcher > 1) {
+    set_error("set_sift_matcher: 0 = exact 2-NN ratio matcher (FLANN branch), 1 = SiftGPU matcher");
+    return RGBDSLAM_B200_ERR_ARG;
+  }
+  g_state.sift_matcher = matcher;
+  return 0;
+}
+
 int rgbdslam_b200_set_hamming_path(int path) {
   std::lock_guard<std::mutex> lk(g_state.mu);
   if (path < 0 || path > 2) {
@@ -643,6 +685,7 @@ int rgbdslam_b200_brute_force_orb(const uint64_t* q, int nq, const uint64_t* t, 
   pd.id_q = pd.id_t = 0;
   pd.q_i8 = pd.t_i8 = nullptr;
   pd.q_f32 = pd.t_f32 = pd.t_norm = nullptr;
+  pd.sift_kind = pd.pad_ = 0;
   if (s.hamming_path != 0) {
     if ((rc = s.W().d_i8_a.ensure(256 * (size_t)pad256(nq)))) return rc;
     if ((rc = s.W().d_i8_b.ensure(256 * (size_t)pad256(nt)))) return rc;
@@ -657,7 +700,7 @@ int rgbdslam_b200_brute_force_orb(const uint64_t* q, int nq, const uint64_t* t, 
   e = cudaMemcpyAsync(s.W().d_pairs.ptr, s.W().h_pairs.ptr, sizeof(pd), cudaMemcpyHostToDevice, st);
   if (e != cudaSuccess) return cuda_fail(e, "brute_force_orb pair upload");
   int n_items = 0;
-  if ((rc = stage_match_items(&pd, 1, stride, false, &n_items))) return rc;
+  if ((rc = stage_match_items(&pd, 1, stride, 0, &n_items))) return rc;
   if ((rc = launch_hamming((const PairDesc*)s.W().d_pairs.ptr, 1, nq, (int2*)s.W().d_best.ptr, stride, n_items, st))) return rc;
   std::vector<int2> h(nq);
   e = cudaMemcpyAsync(h.data(), s.W().d_best.ptr, sizeof(int2) * nq, cudaMemcpyDeviceToHost, st);
@@ -805,8 +848,10 @@ static int match_pairs_impl(int slot, bool sync, const uint64_t* newer, const ui
     pairs[i].q_f32 = a->desc_f32;
     pairs[i].t_f32 = b->desc_f32;
     pairs[i].t_norm = b->norms;
-    if ((a->desc_f32 != nullptr) != (b->desc_f32 != nullptr)) {
-      set_error("match_pairs: ORB node paired with a SIFT node");
+    pairs[i].sift_kind = a->sift_kind;
+    pairs[i].pad_ = 0;
+    if ((a->desc_f32 != nullptr) != (b->desc_f32 != nullptr) || a->sift_kind != b->sift_kind) {
+      set_error("match_pairs: nodes of different descriptor / matcher kinds paired");
       return RGBDSLAM_B200_ERR_ARG;
     }
   }
@@ -892,6 +937,7 @@ static int match_pairs_host_impl(int slot, bool sync, const uint8_t* desc_newer,
   for (int i = 0; i < npairs; i++) {
     pairs[i].q_i8 = pairs[i].t_i8 = nullptr;
     pairs[i].q_f32 = pairs[i].t_f32 = pairs[i].t_norm = nullptr;
+    pairs[i].sift_kind = pairs[i].pad_ = 0;
     if (tc) {
       pairs[i].q_i8 = (const int8_t*)s.W().d_i8_a.ptr + 256 * pn;
       pairs[i].t_i8 = (const int8_t*)s.W().d_i8_b.ptr + 256 * po;
@@ -976,7 +1022,8 @@ int rgbdslam_b200_node_create_from_sift(int32_t id, const float* desc128, const 
   }
   std::vector<SiftJob> jobs(1);
   jobs[0] = {(const float*)s.d_f32_a.ptr, nd->desc_f32, (uint16_t*)nd->desc_i8, nd->norms, n, nd->n_pad};
-  if ((rc = prepare_sift_nodes(jobs))) return rc;
+  nd->sift_kind = s.sift_matcher;
+  if ((rc = prepare_sift_nodes(jobs, nd->sift_kind))) return rc;
   e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) return cuda_fail(e, "sift node prepare");
   *node_handle = (uint64_t)(uintptr_t)nd;
@@ -1022,7 +1069,7 @@ int rgbdslam_b200_knn2_l2(const float* q, int nq, const float* t, int nt, int32_
   e = cudaMemcpyAsync(s.W().d_pairs.ptr, s.W().h_pairs.ptr, sizeof(pd), cudaMemcpyHostToDevice, st);
   if (e != cudaSuccess) return cuda_fail(e, "knn2_l2 pair upload");
   int n_items = 0;
-  if ((rc = stage_match_items(&pd, 1, stride, true, &n_items))) return rc;
+  if ((rc = stage_match_items(&pd, 1, stride, 1, &n_items))) return rc;
   if ((rc = launch_sift_knn((const PairDesc*)s.W().d_pairs.ptr, 1, nq, stride, n_items, st))) return rc;
   std::vector<float4> h(nq);
   e = cudaMemcpyAsync(h.data(), s.W().d_knn.ptr, sizeof(float4) * nq, cudaMemcpyDeviceToHost, st);

@@ -24,6 +24,8 @@ struct PairDesc {
   const float* q_f32;  // SIFT nodes only: fp32 (Root)SIFT rows and train-row norms
   const float* t_f32;
   const float* t_norm;
+  int32_t sift_kind;   // float-descriptor nodes: 0 = RootSIFT / exact 2-NN ratio matcher, 1 = SiftGPU matcher (u8 tiles, raw rows)
+  int32_t pad_;
 };
 
 // One unit of the +-1 int8 expansion (one node).
@@ -41,7 +43,7 @@ struct HamItem {
   int32_t nq_valid;    // valid rows in this tile (1..128)
   int32_t nsearch;     // nt - 1: only train rows [0, nt-2] are examined (features.cpp:174)
   int32_t n_btiles;    // ceil(nsearch / 256)
-  int32_t pad_;
+  int32_t pad_;        // SiftGPU pass: tie rule of the arg-max (0 = RowMatch_Kernel's thread-major order, 1 = lowest index)
   const float* bnorm;  // SIFT L2 only: |b|^2 of the train rows (bf16-rounded values); out then points to int4 records
 };
 

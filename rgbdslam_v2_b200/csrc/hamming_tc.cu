@@ -331,6 +331,7 @@ constexpr int kBarAFull = 0, kBarAEmpty = kASt, kBarBFull = 2 * kASt, kBarBEmpty
 static_assert(kBarCount * 8 <= 192, "barrier area");
 constexpr int kTc256Threads = 320;
 constexpr uint32_t kIdescI8_N128 = (2u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t kIdescU8_N128 = (2u << 4) | ((128u >> 3) << 17) | ((128u >> 4) << 24);  // a/b format 0 = unsigned 8-bit
 constexpr uint32_t kIdescBF16_N128 = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
 
 template <int MODE>
@@ -391,10 +392,12 @@ __global__ void __launch_bounds__(kTc256Threads, 1) tc_match256_kernel(const Ham
 #pragma unroll
           for (int h = 0; h < 2; h++) {
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
+            for (int k = 0; k < (MODE == 2 ? 4 : 8); k++) {  // u8 SIFT rows carry 128 B of data: 4 k-steps of 32 B
               const uint32_t d = tmem_base + acc * 256 + h * 128;
               if (MODE == 0)
                 tc_mma_i8(d, make_desc(a0 + h * kTileA + k * 256), make_desc(b0 + k * 256), kIdescI8_N128, k > 0 ? 1u : 0u);
+              else if (MODE == 2)
+                tc_mma_i8(d, make_desc(a0 + h * kTileA + k * 256), make_desc(b0 + k * 256), kIdescU8_N128, k > 0 ? 1u : 0u);
               else
                 tc_mma_bf16(d, make_desc(a0 + h * kTileA + k * 256), make_desc(b0 + k * 256), kIdescBF16_N128, k > 0 ? 1u : 0u);
             }
@@ -418,6 +421,8 @@ __global__ void __launch_bounds__(kTc256Threads, 1) tc_match256_kernel(const Ham
       int best = kNoBest;
       float s0 = -3.0e38f, s1 = -3.0e38f, s2 = -3.0e38f, s3 = -3.0e38f;
       int i0 = -1, i1 = -1, i2 = -1, i3 = -1;
+      long long u8_best = -1;  // MODE 2: (dot << 17) | (0x1FFFF - tie priority); -1 = no positive dot yet
+      int u8_next = 0;
       for (int nb = 0; nb < item.n_btiles; nb++) {
         mbar_wait(bar(kBarAccFull + acc), pacc);
         tc_fence_after();
@@ -436,6 +441,24 @@ __global__ void __launch_bounds__(kTc256Threads, 1) tc_match256_kernel(const Ham
 #pragma unroll
               for (int j = 0; j < 32; j++)
                 if (col0 + j < item.nsearch) best = max(best, (int)v[j] * 65536 + (65535 - (col0 + j)));
+            }
+          } else if (MODE == 2) {
+            // SiftGPU RowMatch / ColMatch bookkeeping (ProgramCU.cu:1708-1736, 1463-1478, 1771-1777): strict >, only
+            // positive dots register, the runner-up VALUE counts duplicates of the maximum.
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+              const int col = col0 + j;
+              const int dv = (int)v[j];
+              if (col < item.nsearch && dv > 0) {
+                const int prio = item.pad_ ? col : (((col & 31) << 12) | (col >> 5));
+                const long long key = ((long long)dv << 17) | (long long)(0x1FFFF - prio);
+                if (key > u8_best) {
+                  if (u8_best >= 0) u8_next = max(u8_next, (int)(u8_best >> 17));
+                  u8_best = key;
+                } else {
+                  u8_next = max(u8_next, dv);
+                }
+              }
             }
           } else {
 #pragma unroll
@@ -471,6 +494,14 @@ __global__ void __launch_bounds__(kTc256Threads, 1) tc_match256_kernel(const Ham
             o.y = 65535 - (best & 0xFFFF);
           }
           item.out[row] = o;
+        } else if (MODE == 2) {
+          int4 o = make_int4(0, -1, u8_next, 0);
+          if (u8_best >= 0) {
+            const int prio = 0x1FFFF - (int)(u8_best & 0x1FFFF);
+            o.x = (int)(u8_best >> 17);
+            o.y = item.pad_ ? prio : (((prio & 0xFFF) << 5) | (prio >> 12));
+          }
+          reinterpret_cast<int4*>(item.out)[row] = o;
         } else {
           reinterpret_cast<int4*>(item.out)[row] = make_int4(i0, i1, i2, i3);
         }
@@ -502,6 +533,9 @@ cudaError_t launch_hamming_tc256(const HamItem* d_items, int n_items, int sm_cou
 }
 cudaError_t launch_l2_tc256(const HamItem* d_items, int n_items, int sm_count, cudaStream_t stream) {
   return launch_tc256<1>(d_items, n_items, sm_count, stream);
+}
+cudaError_t launch_siftgpu_tc256(const HamItem* d_items, int n_items, int sm_count, cudaStream_t stream) {
+  return launch_tc256<2>(d_items, n_items, sm_count, stream);
 }
 
 cudaError_t launch_hamming_tc(const HamItem* d_items, int n_items, int sm_count, cudaStream_t stream) {

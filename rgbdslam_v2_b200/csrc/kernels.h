@@ -20,7 +20,10 @@ cudaError_t launch_hamming_tc256(const HamItem* d_items, int n_items, int sm_cou
 cudaError_t launch_l2_tc256(const HamItem* d_items, int n_items, int sm_count, cudaStream_t stream);
 
 // SIFT-128 path (sift_l2.cu / hamming_tc.cu MODE 1)
-cudaError_t launch_sift_prepare(const SiftJob* d_jobs, int njobs, int max_n_pad, int root_sift, cudaStream_t stream);
+cudaError_t launch_sift_prepare(const SiftJob* d_jobs, int njobs, int max_n_pad, int root_sift, int siftgpu, cudaStream_t stream);
+cudaError_t launch_siftgpu_tc256(const HamItem* d_items, int n_items, int sm_count, cudaStream_t stream);
+cudaError_t launch_select_siftgpu(const PairDesc* pairs, int npairs, const int4* rowres, const int4* colres, int stride, int maxM,
+                                  rgbdslam_b200_dmatch* matches, float4* mfrom, float4* mto, int32_t* n_all, cudaStream_t stream);
 cudaError_t launch_l2_tc(const HamItem* d_items, int n_items, int sm_count, cudaStream_t stream);
 cudaError_t launch_l2_refine(const PairDesc* pairs, int npairs, int max_nq, const int4* top4, int stride, float4* knn,
                              cudaStream_t stream);

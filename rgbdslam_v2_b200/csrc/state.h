@@ -36,6 +36,7 @@ struct NodeDev {
   float* norms = nullptr;     // SIFT nodes: n_pad |b|^2 of the bf16-rounded rows
   int8_t* desc_i8 = nullptr;  // n_pad x 256 B  +-1 expansion for the tensor-core Hamming path (lazily built)
   int32_t n_pad = 0;
+  int32_t sift_kind = 0;      // SIFT nodes: 0 = RootSIFT rows + bf16 tiles, 1 = raw rows + u8 tiles (SiftGPU matcher)
 };
 
 constexpr int kSlots = 4;  // independent in-flight match_pairs pipelines (stream + workspace each)
@@ -75,6 +76,7 @@ struct State {
   Workspace* cur = &ws[0];
   Workspace& W() { return *cur; }
   DevBuf d_f32_a, d_f32_b, d_root_a, d_root_b, d_norm_a, d_norm_b;  // SIFT staging of the synchronous calls
+  int sift_matcher = 0;  // float-descriptor nodes created from now on: 0 = exact 2-NN ratio matcher (FLANN branch), 1 = SiftGPU matcher
   int hamming_path = 2;  // 2 = tcgen05 int8 GEMM, 256-query items (default); 1 = 128-query items; 0 = SIMT popcount
   void release_workspaces() {
     for (Workspace& w : ws) w.release();

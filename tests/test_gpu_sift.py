@@ -95,3 +95,65 @@ def test_mixing_orb_and_sift_nodes_is_rejected(fe):
     with pytest.raises(B200Error):
         fe.match_node_pairs([a], [s])
     fe.node_destroy(a); fe.node_destroy(s)
+
+
+def _unit_sift(rng, n):
+    """SiftGPU-style descriptors: non-negative, unit L2 norm, clipped at 0.2 and renormalised (values <= ~0.5)."""
+    d = rng.gamma(0.6, 1.0, size=(n, 128)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d = np.minimum(d, 0.2)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    return d.astype(np.float32)
+
+
+@pytest.mark.parametrize("nq,nt", [(1, 1), (40, 33), (700, 1000), (2000, 2000), (1300, 257)])
+def test_siftgpu_matcher_is_bit_exact(fe, nq, nt):
+    """matcher_type SIFTGPU (node.cpp:553-557): u8 dot-product matrix on the tensor cores, acos distance / ratio tests,
+    mutual best match, float L2 DMatch.distance -- all integer or order-pinned float work, so the match list must equal
+    the restated SiftMatchGPU + SiftGPUWrapper::match exactly (indices and distance bits)."""
+    from oracle import sift_oracle
+    rng = np.random.default_rng(nq * 7 + nt)
+    t = _unit_sift(rng, nt)
+    q = _unit_sift(rng, nq)
+    k = min(nq, nt) * 2 // 3
+    if k:
+        q[:k] = np.abs(t[rng.permutation(nt)[:k]] + rng.normal(0, 0.01, (k, 128)).astype(np.float32))
+    if nt > 40 and nq > 40:
+        t[37] = t[5]; t[9] = t[5]          # duplicated train rows: row-pass ties resolved by (col % 32, col)
+        q[3] = t[5]
+        q[20] = q[21]                      # duplicated query rows: column-pass ties resolved by the lowest row
+        q[30, :] = 0.0                     # all-zero descriptor: no positive dot product, never matched
+        t[12, 0] = 0.5                     # 512 * 0.5 + 0.5 = 256 wraps to 0 in the unsigned char
+    xyz_q = np.concatenate([rng.uniform(0.5, 3, (nq, 3)), np.ones((nq, 1))], 1).astype(np.float32)
+    xyz_t = np.concatenate([rng.uniform(0.5, 3, (nt, 3)), np.ones((nt, 1))], 1).astype(np.float32)
+    fe.set_sift_matcher(1)
+    try:
+        a, b = fe.node_from_sift(1, q, xyz_q), fe.node_from_sift(0, t, xyz_t)
+    finally:
+        fe.set_sift_matcher(0)
+    res, allm, _ = fe.match_node_pairs([a], [b], seed=3)
+    exp = sift_oracle.siftgpu_feature_matching(q, t, max_matches=300)
+    n = int(res[0]["n_all_matches"])
+    assert n == len(exp)
+    got = allm[0, :n]
+    assert np.array_equal(got["queryIdx"], exp["queryIdx"]) and np.array_equal(got["trainIdx"], exp["trainIdx"])
+    assert np.array_equal(got["distance"].view(np.uint32), exp["distance"].view(np.uint32))
+    if nq > 40 and nt > 40:
+        assert n > 20
+    fe.node_destroy(a); fe.node_destroy(b)
+
+
+def test_siftgpu_and_ratio_nodes_do_not_mix(fe):
+    from rgbdslam_v2_b200._capi import B200Error
+    rng = np.random.default_rng(1)
+    d = _unit_sift(rng, 64)
+    xyz = np.concatenate([rng.uniform(0.5, 3, (64, 3)), np.ones((64, 1))], 1).astype(np.float32)
+    a = fe.node_from_sift(1, d, xyz)
+    fe.set_sift_matcher(1)
+    try:
+        b = fe.node_from_sift(0, d, xyz)
+    finally:
+        fe.set_sift_matcher(0)
+    with pytest.raises(B200Error):
+        fe.match_node_pairs([a], [b])
+    fe.node_destroy(a); fe.node_destroy(b)
