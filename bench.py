@@ -183,8 +183,8 @@ def run_reference(args, rank, world):
     oracle.build()
     cores = os.cpu_count() or 1
     b = make_workload(0)
-    for _ in range(args.warmup):
-        oracle_run(b, 0, cores, npairs=32)
+    for _ in range(max(args.warmup, 1)):
+        oracle_run(b, 0, cores)  # full passes: the OpenMP team and the allocator arenas are warm before the timed steps
     times = []
     for _ in range(args.steps):
         dt, _ = oracle_run(b, 0, cores)

@@ -83,7 +83,9 @@ typedef struct rgbdslam_b200_params {
   double max_rotation_degree;   /* 360   :97                      */
   double nn_distance_ratio;     /* 0.95  :160 (SIFT path)         */
   int32_t use_root_sift;        /* 1     :92                      */
-  int32_t reserved_[7];
+  int32_t g2o_transformation_refinement; /* 0 :103 -- Gauss-Newton iterations of the pairwise refinement (node.cpp:1225-1268,
+                                          * transformation_estimation.cpp:126-170); needs nodes with 2-D keypoints */
+  int32_t reserved_[6];
 } rgbdslam_b200_params;
 
 /*
@@ -146,6 +148,9 @@ int rgbdslam_b200_node_num_features(uint64_t node_handle, int* n);
 /* Download (any pointer may be NULL). */
 int rgbdslam_b200_node_download(uint64_t node_handle, uint8_t* desc, float* xyz1);
 /* == Node::~Node (node.cpp:371). */
+/* Attach the 2-D keypoints (feature_locations_2d_, n entries) to a node created from features: only the pairwise g2o
+ * refinement reads them (edgeToFeature, transformation_estimation.cpp:91-124).  Nodes built from images carry theirs. */
+int rgbdslam_b200_node_set_keypoints(uint64_t node_handle, const rgbdslam_b200_keypoint* keypoints);
 int rgbdslam_b200_node_destroy(uint64_t node_handle);
 
 /* ---- SIFT-128 float descriptors (feature_extractor_type SIFT / SURF / SIFTGPU) -----------

@@ -185,3 +185,31 @@ def posegraph_chi2(poses, ij, meas, info, huber_delta=1.0):
     fn.restype = C.c_double
     chi2 = fn(C.c_int(len(x)), _p(x), C.c_int(len(ij)), _p(ij), _p(meas), _p(info), C.c_double(huber_delta), C.byref(rob))
     return chi2, rob.value
+
+
+# ---- pairwise g2o refinement (refine_oracle.c) ---------------------------------------------
+
+def get_transform_from_matches_g2o(params: OParams, xyz_newer, kp_newer, xyz_older, kp_older, matches, sel, T4x4, iterations):
+    """getTransformFromMatchesG2O (transformation_estimation.cpp:126-170).  kp_*: (n, 2) pixel coordinates;
+    T4x4: float 4x4 initial estimate (row-major numpy view of the Matrix4f); returns the refined float 4x4."""
+    x1 = np.ascontiguousarray(xyz_newer, np.float32); x2 = np.ascontiguousarray(xyz_older, np.float32)
+    k1 = np.ascontiguousarray(kp_newer, np.float32).reshape(-1, 2); k2 = np.ascontiguousarray(kp_older, np.float32).reshape(-1, 2)
+    m = np.ascontiguousarray(matches, DMATCH_DTYPE)
+    s = np.ascontiguousarray(sel, np.int32)
+    T = np.ascontiguousarray(np.asarray(T4x4, np.float32).T)  # column-major storage
+    lib().oracle_get_transform_from_matches_g2o(C.byref(params), _p(x1), _p(k1), _p(x2), _p(k2), _p(m), _p(s), C.c_int(len(s)), _p(T),
+                                                C.c_int(int(iterations)))
+    return T.T.copy()
+
+
+def refine_g2o(params: OParams, iterations, xyz_newer, kp_newer, xyz_older, kp_older, matches, T4x4, rmse, inl_mask, valid_iterations=0):
+    """node.cpp:1225-1268 on top of a RANSAC result.  inl_mask: uint8 per match.  Returns (T, rmse, inl_mask, n_inl, valid_it)."""
+    x1 = np.ascontiguousarray(xyz_newer, np.float32); x2 = np.ascontiguousarray(xyz_older, np.float32)
+    k1 = np.ascontiguousarray(kp_newer, np.float32).reshape(-1, 2); k2 = np.ascontiguousarray(kp_older, np.float32).reshape(-1, 2)
+    m = np.ascontiguousarray(matches, DMATCH_DTYPE)
+    T = np.ascontiguousarray(np.asarray(T4x4, np.float32).T)
+    inl = np.ascontiguousarray(inl_mask, np.uint8).copy()
+    r = C.c_float(float(rmse)); n = C.c_int(int(inl.sum())); vi = C.c_int(int(valid_iterations))
+    lib().oracle_refine_g2o(C.byref(params), C.c_int(int(iterations)), _p(x1), _p(k1), _p(x2), _p(k2), _p(m), C.c_int(len(m)), _p(T),
+                            C.byref(r), _p(inl), C.byref(n), C.byref(vi))
+    return T.T.copy(), float(r.value), inl, int(n.value), int(vi.value)

@@ -42,7 +42,7 @@ class Params(C.Structure):
         ("detector_grid_resolution", C.c_int32), ("adjuster_max_iterations", C.c_int32),
         ("min_translation_meter", C.c_double), ("min_rotation_degree", C.c_double),
         ("max_translation_meter", C.c_double), ("max_rotation_degree", C.c_double),
-        ("nn_distance_ratio", C.c_double), ("use_root_sift", C.c_int32), ("reserved_", C.c_int32 * 7),
+        ("nn_distance_ratio", C.c_double), ("use_root_sift", C.c_int32), ("g2o_transformation_refinement", C.c_int32), ("reserved_", C.c_int32 * 6),
     ]
 
 
@@ -119,6 +119,7 @@ def load_library(path: str | Path | None = None) -> C.CDLL:
     lib.rgbdslam_b200_match_pairs_wait.argtypes = [C.c_int]
     lib.rgbdslam_b200_set_hamming_path.argtypes = [C.c_int]
     lib.rgbdslam_b200_set_sift_matcher.argtypes = [C.c_int]
+    lib.rgbdslam_b200_node_set_keypoints.argtypes = [u64, vp]
     lib.rgbdslam_b200_detector_create.argtypes = [C.POINTER(u64)]
     lib.rgbdslam_b200_detector_destroy.argtypes = [u64]
     lib.rgbdslam_b200_detector_thresholds.argtypes = [u64, vp, C.c_int]
@@ -262,6 +263,13 @@ class Frontend:
         d = np.zeros((len(q), 2), np.float32)
         self._check(self.lib.rgbdslam_b200_knn2_l2(_ptr(q), len(q), _ptr(t), len(t), _ptr(idx), _ptr(d)))
         return idx, d
+
+    def node_set_keypoints(self, h: int, kp: np.ndarray):
+        """kp: KEYPOINT_DTYPE array (only pt.x / pt.y are used) with one entry per feature of the node"""
+        k = np.ascontiguousarray(kp, dtype=KEYPOINT_DTYPE)
+        if len(k) != self.node_num_features(h):
+            raise ValueError("one keypoint per feature")
+        self._check(self.lib.rgbdslam_b200_node_set_keypoints(C.c_uint64(int(h)), _ptr(k)))
 
     def node_num_features(self, h: int) -> int:
         n = C.c_int()

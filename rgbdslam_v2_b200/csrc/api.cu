@@ -293,8 +293,9 @@ static int run_pairs(const std::vector<PairDesc>& h_pairs, uint64_t seed, int64_
   if ((rc = s.W().d_best.ensure(sizeof(int2) * (size_t)npairs * stride))) return rc;
   if ((rc = s.W().d_matches.ensure(sizeof(rgbdslam_b200_dmatch) * (size_t)npairs * maxM))) return rc;
   if ((rc = s.W().d_inliers.ensure(sizeof(rgbdslam_b200_dmatch) * (size_t)npairs * maxM))) return rc;
-  if ((rc = s.W().d_mfrom.ensure(sizeof(float4) * (size_t)npairs * maxM))) return rc;
-  if ((rc = s.W().d_mto.ensure(sizeof(float4) * (size_t)npairs * maxM))) return rc;
+  // + kMaxMatchesCap rows of slack: the scoring loop reads whole 32-row words past a pair's last match (masked out)
+  if ((rc = s.W().d_mfrom.ensure(sizeof(float4) * ((size_t)npairs * maxM + kMaxMatchesCap)))) return rc;
+  if ((rc = s.W().d_mto.ensure(sizeof(float4) * ((size_t)npairs * maxM + kMaxMatchesCap)))) return rc;
   if ((rc = s.W().d_nall.ensure(sizeof(int32_t) * npairs))) return rc;
   if ((rc = s.W().d_hyp.ensure(sizeof(HypResult) * (size_t)npairs * (H > 0 ? H : 1)))) return rc;
   if ((rc = s.W().d_results.ensure(sizeof(rgbdslam_b200_pair_result) * npairs))) return rc;
@@ -389,6 +390,19 @@ static int run_pairs(const std::vector<PairDesc>& h_pairs, uint64_t seed, int64_
                            (rgbdslam_b200_dmatch*)s.W().d_inliers.ptr, st);
   if (e != cudaSuccess) return cuda_fail(e, "ransac_select kernel");
   s.launches += 1 + hyp_launches;
+  if (s.params.g2o_transformation_refinement > 0) {  // node.cpp:1225-1268
+    for (const PairDesc& pd : h_pairs)
+      if ((pd.nq > 0 && !pd.q_kp) || (pd.nt > 0 && !pd.t_kp)) {
+        set_error("g2o_transformation_refinement > 0 needs nodes with 2-D keypoints (nodes_create or node_set_keypoints)");
+        return RGBDSLAM_B200_ERR_STATE;
+      }
+    e = launch_refine_g2o(d_pairs, npairs, maxM, s.params.g2o_transformation_refinement, (const float4*)s.W().d_mfrom.ptr,
+                          (const float4*)s.W().d_mto.ptr, (const int32_t*)s.W().d_nall.ptr,
+                          (const rgbdslam_b200_dmatch*)s.W().d_matches.ptr, (rgbdslam_b200_pair_result*)s.W().d_results.ptr,
+                          (rgbdslam_b200_dmatch*)s.W().d_inliers.ptr, st);
+    if (e != cudaSuccess) return cuda_fail(e, "refine_g2o kernel");
+    s.launches += 1;
+  }
   cudaEventRecord(s.W().ev[2], st);
 
   if (results) {
@@ -535,6 +549,25 @@ int rgbdslam_b200_synchronize(void) {
   if (rc) return rc;
   cudaError_t e = cudaStreamSynchronize(g_state.stream);
   if (e != cudaSuccess) return cuda_fail(e, "cudaStreamSynchronize");
+  return 0;
+}
+
+int rgbdslam_b200_node_set_keypoints(uint64_t node_handle, const rgbdslam_b200_keypoint* keypoints) {
+  std::lock_guard<std::mutex> lk(g_state.mu);
+  int rc = check_inited();
+  if (rc) return rc;
+  NodeDev* nd = reinterpret_cast<NodeDev*>((uintptr_t)node_handle);
+  if (!nd || nd->magic != NodeDev::kMagic || (nd->n > 0 && !keypoints)) {
+    set_error("node_set_keypoints: bad handle or null keypoints");
+    return RGBDSLAM_B200_ERR_ARG;
+  }
+  if (nd->n == 0) return 0;
+  cudaError_t e = cudaSuccess;
+  if (!nd->kp) e = cudaMalloc(&nd->kp, sizeof(rgbdslam_b200_keypoint) * (size_t)nd->n);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(nd->kp, keypoints, sizeof(rgbdslam_b200_keypoint) * (size_t)nd->n, cudaMemcpyHostToDevice, g_state.stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(g_state.stream);
+  if (e != cudaSuccess) return cuda_fail(e, "node_set_keypoints");
   return 0;
 }
 
@@ -686,6 +719,7 @@ int rgbdslam_b200_brute_force_orb(const uint64_t* q, int nq, const uint64_t* t, 
   pd.q_i8 = pd.t_i8 = nullptr;
   pd.q_f32 = pd.t_f32 = pd.t_norm = nullptr;
   pd.sift_kind = pd.pad_ = 0;
+  pd.q_kp = pd.t_kp = nullptr;
   if (s.hamming_path != 0) {
     if ((rc = s.W().d_i8_a.ensure(256 * (size_t)pad256(nq)))) return rc;
     if ((rc = s.W().d_i8_b.ensure(256 * (size_t)pad256(nt)))) return rc;
@@ -850,6 +884,8 @@ static int match_pairs_impl(int slot, bool sync, const uint64_t* newer, const ui
     pairs[i].t_norm = b->norms;
     pairs[i].sift_kind = a->sift_kind;
     pairs[i].pad_ = 0;
+    pairs[i].q_kp = a->kp;
+    pairs[i].t_kp = b->kp;
     if ((a->desc_f32 != nullptr) != (b->desc_f32 != nullptr) || a->sift_kind != b->sift_kind) {
       set_error("match_pairs: nodes of different descriptor / matcher kinds paired");
       return RGBDSLAM_B200_ERR_ARG;
@@ -938,6 +974,7 @@ static int match_pairs_host_impl(int slot, bool sync, const uint8_t* desc_newer,
     pairs[i].q_i8 = pairs[i].t_i8 = nullptr;
     pairs[i].q_f32 = pairs[i].t_f32 = pairs[i].t_norm = nullptr;
     pairs[i].sift_kind = pairs[i].pad_ = 0;
+    pairs[i].q_kp = pairs[i].t_kp = nullptr;
     if (tc) {
       pairs[i].q_i8 = (const int8_t*)s.W().d_i8_a.ptr + 256 * pn;
       pairs[i].t_i8 = (const int8_t*)s.W().d_i8_b.ptr + 256 * po;

@@ -24,6 +24,8 @@ struct PairDesc {
   const float* q_f32;  // SIFT nodes only: fp32 (Root)SIFT rows and train-row norms
   const float* t_f32;
   const float* t_norm;
+  const rgbdslam_b200_keypoint* q_kp;  // 2-D keypoints (nullptr unless the node has them): pairwise g2o refinement only
+  const rgbdslam_b200_keypoint* t_kp;
   int32_t sift_kind;   // float-descriptor nodes: 0 = RootSIFT / exact 2-NN ratio matcher, 1 = SiftGPU matcher (u8 tiles, raw rows)
   int32_t pad_;
 };

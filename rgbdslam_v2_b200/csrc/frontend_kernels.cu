@@ -922,4 +922,409 @@ cudaError_t launch_ransac_select(const PairDesc* pairs, int npairs, int ransac_i
   return cudaGetLastError();
 }
 
+// =====================================================================================================
+// Pairwise g2o refinement (parameter g2o_transformation_refinement, default 0 = off).
+// getTransformFromMatchesG2O (transformation_estimation.cpp:126-170): a 2-camera bundle adjustment over the current
+// inliers -- camera 2 (newer node) fixed at identity, camera 1 (earlier node) seeded with the estimate, one
+// VertexPointXYZ per match seeded with the newer node's 3-D position, two EdgeSE3PointXYZDepth per match with
+// measurement (u, v, depth), information diag(1, 1, 1 / depth_covariance) (misc2.h:37-47), Kcam (521, 521, 319.5, 239.5)
+// (:56), `iterations` undamped Gauss-Newton steps.  The reference solves the full (6 + 3n) system with cholmod (no
+// marginalisation); here the 3x3 point blocks are eliminated analytically (Schur complement onto the 6x6 camera block),
+// which is the same linear solution.  One warp per pair, lanes own matches l, l+32, ...; float64 throughout.
+struct Cam {
+  double R[9], t[3];  // world-from-camera
+};
+
+// EdgeSE3PointXYZDepth: error and Jacobians (upstream g2o types/slam3d/edge_se3_pointxyz_depth.cpp)
+__device__ __forceinline__ void edge_depth(const Cam& c, const double pw[3], const double meas[3], double e[3], double Jc[18],
+                                           double Jp[9]) {
+  const double kfx = 521.0, kfy = 521.0, kcx = 319.5, kcy = 239.5;
+  const double d0 = pw[0] - c.t[0], d1 = pw[1] - c.t[1], d2 = pw[2] - c.t[2];
+  double zc[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) zc[k] = c.R[k] * d0 + c.R[3 + k] * d1 + c.R[6 + k] * d2;  // R^T (p - t)
+  double J[3][9];
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+#pragma unroll
+    for (int k = 0; k < 9; k++) J[r][k] = 0.0;
+  J[0][0] = J[1][1] = J[2][2] = -1.0;
+  J[0][4] = -2 * zc[2]; J[0][5] = 2 * zc[1];
+  J[1][3] = 2 * zc[2];  J[1][5] = -2 * zc[0];
+  J[2][3] = -2 * zc[1]; J[2][4] = 2 * zc[0];
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+#pragma unroll
+    for (int k = 0; k < 3; k++) J[r][6 + k] = c.R[3 * k + r];
+  const double zp0 = kfx * zc[0] + kcx * zc[2], zp1 = kfy * zc[1] + kcy * zc[2], zp2 = zc[2];
+  const double iz2 = 1.0 / (zp2 * zp2);
+#pragma unroll
+  for (int k = 0; k < 9; k++) {
+    const double j0 = kfx * J[0][k] + kcx * J[2][k], j1 = kfy * J[1][k] + kcy * J[2][k], j2 = J[2][k];
+    const double h0 = iz2 * (j0 * zp2 - zp0 * j2), h1 = iz2 * (j1 * zp2 - zp1 * j2);
+    if (k < 6) {
+      Jc[k] = h0; Jc[6 + k] = h1; Jc[12 + k] = j2;
+    } else {
+      Jp[k - 6] = h0; Jp[3 + k - 6] = h1; Jp[6 + k - 6] = j2;
+    }
+  }
+  e[0] = zp0 / zp2 - meas[0];
+  e[1] = zp1 / zp2 - meas[1];
+  e[2] = zp2 - meas[2];
+}
+
+__device__ __forceinline__ void cam_from_rt(const Rt& T, Cam& c) {  // Quaterniond(Matrix3d) -> normalise -> rotation matrix
+  double m[3][3];
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+#pragma unroll
+    for (int k = 0; k < 3; k++) m[r][k] = (double)T.R[3 * r + k];
+  double q[4];
+  const double tr = m[0][0] + m[1][1] + m[2][2];
+  if (tr > 0) {
+    double s = sqrt(tr + 1.0);
+    q[3] = 0.5 * s;
+    s = 0.5 / s;
+    q[0] = (m[2][1] - m[1][2]) * s; q[1] = (m[0][2] - m[2][0]) * s; q[2] = (m[1][0] - m[0][1]) * s;
+  } else {
+    int i = 0;
+    if (m[1][1] > m[0][0]) i = 1;
+    if (m[2][2] > m[i][i]) i = 2;
+    const int j = (i + 1) % 3, k = (j + 1) % 3;
+    double s = sqrt(m[i][i] - m[j][j] - m[k][k] + 1.0);
+    q[i] = 0.5 * s;
+    s = 0.5 / s;
+    q[3] = (m[k][j] - m[j][k]) * s;
+    q[j] = (m[j][i] + m[i][j]) * s;
+    q[k] = (m[k][i] + m[i][k]) * s;
+  }
+  const double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  const double x = q[0] / n, y = q[1] / n, z = q[2] / n, w = q[3] / n;
+  c.R[0] = 1 - 2 * (y * y + z * z); c.R[1] = 2 * (x * y - z * w);     c.R[2] = 2 * (x * z + y * w);
+  c.R[3] = 2 * (x * y + z * w);     c.R[4] = 1 - 2 * (x * x + z * z); c.R[5] = 2 * (y * z - x * w);
+  c.R[6] = 2 * (x * z - y * w);     c.R[7] = 2 * (y * z + x * w);     c.R[8] = 1 - 2 * (x * x + y * y);
+#pragma unroll
+  for (int r = 0; r < 3; r++) c.t[r] = (double)T.t[r];
+}
+
+__device__ __forceinline__ void cam_oplus(Cam& c, const double d[6]) {  // X <- X * fromVectorMQT(d)
+  const double vx = d[3], vy = d[4], vz = d[5];
+  double w = 1.0 - (vx * vx + vy * vy + vz * vz);
+  double dR[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  if (w >= 0) {
+    w = sqrt(w);
+    dR[0] = 1 - 2 * (vy * vy + vz * vz); dR[1] = 2 * (vx * vy - vz * w);     dR[2] = 2 * (vx * vz + vy * w);
+    dR[3] = 2 * (vx * vy + vz * w);     dR[4] = 1 - 2 * (vx * vx + vz * vz); dR[5] = 2 * (vy * vz - vx * w);
+    dR[6] = 2 * (vx * vz - vy * w);     dR[7] = 2 * (vy * vz + vx * w);     dR[8] = 1 - 2 * (vx * vx + vy * vy);
+  }
+  double nR[9], nt[3];
+#pragma unroll
+  for (int r = 0; r < 3; r++) nt[r] = c.t[r] + c.R[3 * r] * d[0] + c.R[3 * r + 1] * d[1] + c.R[3 * r + 2] * d[2];
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+#pragma unroll
+    for (int k = 0; k < 3; k++) nR[3 * r + k] = c.R[3 * r] * dR[k] + c.R[3 * r + 1] * dR[3 + k] + c.R[3 * r + 2] * dR[6 + k];
+#pragma unroll
+  for (int i = 0; i < 9; i++) c.R[i] = nR[i];
+#pragma unroll
+  for (int i = 0; i < 3; i++) c.t[i] = nt[i];
+}
+
+// The normal-equation blocks of one match (both edges).  Hpp / Hcc symmetric (full storage), Hcp 6x3.
+struct PointBlocks {
+  double Hpp[9], bp[3], Hcp[18], Hcc[36], bc[6];
+};
+
+__device__ __forceinline__ void point_blocks(const Cam& c1, const double pw[3], const double m1[3], double w1, const double m2[3],
+                                             double w2, PointBlocks& B) {
+  double e[3], Jc[18], Jp[9];
+  edge_depth(c1, pw, m1, e, Jc, Jp);
+  const double om1[3] = {1.0, 1.0, w1};
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    B.bp[i] = 0;
+#pragma unroll
+    for (int j = 0; j < 3; j++) B.Hpp[3 * i + j] = 0;
+  }
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    B.bc[i] = 0;
+#pragma unroll
+    for (int j = 0; j < 6; j++) B.Hcc[6 * i + j] = 0;
+#pragma unroll
+    for (int j = 0; j < 3; j++) B.Hcp[3 * i + j] = 0;
+  }
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      B.bp[i] -= Jp[3 * r + i] * om1[r] * e[r];
+#pragma unroll
+      for (int j = 0; j < 3; j++) B.Hpp[3 * i + j] += Jp[3 * r + i] * om1[r] * Jp[3 * r + j];
+    }
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+      B.bc[i] -= Jc[6 * r + i] * om1[r] * e[r];
+#pragma unroll
+      for (int j = 0; j < 6; j++) B.Hcc[6 * i + j] += Jc[6 * r + i] * om1[r] * Jc[6 * r + j];
+#pragma unroll
+      for (int j = 0; j < 3; j++) B.Hcp[3 * i + j] += Jc[6 * r + i] * om1[r] * Jp[3 * r + j];
+    }
+  }
+  Cam c2;
+#pragma unroll
+  for (int i = 0; i < 9; i++) c2.R[i] = (i % 4 == 0) ? 1.0 : 0.0;
+  c2.t[0] = c2.t[1] = c2.t[2] = 0.0;
+  edge_depth(c2, pw, m2, e, Jc, Jp);  // camera 2 is fixed: only the point block
+  const double om2[3] = {1.0, 1.0, w2};
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      B.bp[i] -= Jp[3 * r + i] * om2[r] * e[r];
+#pragma unroll
+      for (int j = 0; j < 3; j++) B.Hpp[3 * i + j] += Jp[3 * r + i] * om2[r] * Jp[3 * r + j];
+    }
+}
+
+__device__ __forceinline__ bool inv3_sym(const double A[9], double inv[9]) {
+  const double a = A[0], b = A[1], c = A[2], d = A[4], e = A[5], f = A[8];
+  const double c00 = d * f - e * e, c01 = c * e - b * f, c02 = b * e - c * d;
+  const double det = a * c00 + b * c01 + c * c02;
+  if (!(det > 0.0)) return false;
+  const double id = 1.0 / det;
+  inv[0] = c00 * id; inv[1] = c01 * id; inv[2] = c02 * id;
+  inv[3] = inv[1];   inv[4] = (a * f - c * c) * id; inv[5] = (b * c - a * e) * id;
+  inv[6] = inv[2];   inv[7] = inv[5]; inv[8] = (a * d - b * b) * id;
+  return true;
+}
+
+// Runs the bundle adjustment over the matches selected by `mask` (warp-uniform words); T in: estimate, out: result.
+template <int NW>
+__device__ void ba_refine(const float4* __restrict__ xyz_n, const float4* __restrict__ xyz_e, const float2* __restrict__ kp_n,
+                          const float2* __restrict__ kp_e, const uint32_t* mask, int nw, int lane, int iterations, Rt& T,
+                          double* __restrict__ pts /* 3 doubles per match, indexed like the match list */) {
+  Cam c1;
+  cam_from_rt(T, c1);
+  const double cz_const = c_params.cov_z_const;
+#pragma unroll 1
+  for (int w = 0; w < nw; w++)
+    if ((mask[w] >> lane) & 1u) {
+      const int i = w * 32 + lane;
+      const float4 pn = xyz_n[i];
+      double* q = pts + 3 * i;
+      if (!isnan(pn.z)) { q[0] = pn.x; q[1] = pn.y; q[2] = pn.z; }
+      else { q[0] = (double)pn.x * 10; q[1] = (double)pn.y * 10; q[2] = 10.0; }
+    }
+  __syncwarp();
+  for (int it = 0; it < iterations; it++) {
+    double S[27];  // 21 unique entries of the reduced 6x6 (upper triangle, row-major) + 6 right-hand sides
+#pragma unroll
+    for (int k = 0; k < 27; k++) S[k] = 0.0;
+    bool ok = true;
+#pragma unroll 1
+    for (int w = 0; w < nw; w++)
+      if ((mask[w] >> lane) & 1u) {
+        const int i = w * 32 + lane;
+        const float4 pe = xyz_e[i], pn = xyz_n[i];
+        const float2 ke = kp_e[i], kn = kp_n[i];
+        const double d1 = isnan(pe.z) ? 10.0 : (double)pe.z, d2 = isnan(pn.z) ? 10.0 : (double)pn.z;
+        const double m1[3] = {ke.x, ke.y, d1}, m2[3] = {kn.x, kn.y, d2};
+        const double w1 = 1.0 / (cz_const >= 0.0 ? cz_const : depth_cov(d1)), w2 = 1.0 / (cz_const >= 0.0 ? cz_const : depth_cov(d2));
+        PointBlocks B;
+        point_blocks(c1, pts + 3 * i, m1, w1, m2, w2, B);
+        double inv[9];
+        if (!inv3_sym(B.Hpp, inv)) { ok = false; continue; }
+        double Y[18];  // Hcp * Hpp^-1
+#pragma unroll
+        for (int r = 0; r < 6; r++)
+#pragma unroll
+          for (int k = 0; k < 3; k++) Y[3 * r + k] = B.Hcp[3 * r] * inv[k] + B.Hcp[3 * r + 1] * inv[3 + k] + B.Hcp[3 * r + 2] * inv[6 + k];
+        int idx = 0;
+#pragma unroll
+        for (int r = 0; r < 6; r++) {
+#pragma unroll
+          for (int k = r; k < 6; k++)
+            S[idx++] += B.Hcc[6 * r + k] - (Y[3 * r] * B.Hcp[3 * k] + Y[3 * r + 1] * B.Hcp[3 * k + 1] + Y[3 * r + 2] * B.Hcp[3 * k + 2]);
+        }
+#pragma unroll
+        for (int r = 0; r < 6; r++) S[21 + r] += B.bc[r] - (Y[3 * r] * B.bp[0] + Y[3 * r + 1] * B.bp[1] + Y[3 * r + 2] * B.bp[2]);
+      }
+#pragma unroll
+    for (int k = 0; k < 27; k++) S[k] = wsumd(S[k]);
+    ok = __all_sync(kFull, ok);
+    // 6x6 Cholesky solve (warp-uniform)
+    double L[36], dc[6];
+    {
+      int idx = 0;
+#pragma unroll
+      for (int r = 0; r < 6; r++)
+#pragma unroll
+        for (int k = r; k < 6; k++) { L[6 * k + r] = S[idx]; L[6 * r + k] = S[idx]; idx++; }
+    }
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+      double sj = L[6 * j + j];
+#pragma unroll
+      for (int k = 0; k < 6; k++) if (k < j) sj -= L[6 * j + k] * L[6 * j + k];
+      if (!(sj > 0.0)) ok = false;
+      const double l = sqrt(sj);
+      L[6 * j + j] = l;
+#pragma unroll
+      for (int i = 0; i < 6; i++)
+        if (i > j) {
+          double v = L[6 * i + j];
+#pragma unroll
+          for (int k = 0; k < 6; k++) if (k < j) v -= L[6 * i + k] * L[6 * j + k];
+          L[6 * i + j] = v / l;
+        }
+    }
+    if (!ok) break;  // the linear solver failed: the optimisation stops (g2o returns from optimize())
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+      double v = S[21 + i];
+#pragma unroll
+      for (int k = 0; k < 6; k++) if (k < i) v -= L[6 * i + k] * dc[k];
+      dc[i] = v / L[6 * i + i];
+    }
+#pragma unroll
+    for (int ii = 0; ii < 6; ii++) {
+      const int i = 5 - ii;
+      double v = dc[i];
+#pragma unroll
+      for (int k = 0; k < 6; k++) if (k > i) v -= L[6 * k + i] * dc[k];
+      dc[i] = v / L[6 * i + i];
+    }
+    // back-substitution of the points (same blocks, recomputed) BEFORE the camera moves
+#pragma unroll 1
+    for (int w = 0; w < nw; w++)
+      if ((mask[w] >> lane) & 1u) {
+        const int i = w * 32 + lane;
+        const float4 pe = xyz_e[i], pn = xyz_n[i];
+        const float2 ke = kp_e[i], kn = kp_n[i];
+        const double d1 = isnan(pe.z) ? 10.0 : (double)pe.z, d2 = isnan(pn.z) ? 10.0 : (double)pn.z;
+        const double m1[3] = {ke.x, ke.y, d1}, m2[3] = {kn.x, kn.y, d2};
+        const double w1 = 1.0 / (cz_const >= 0.0 ? cz_const : depth_cov(d1)), w2 = 1.0 / (cz_const >= 0.0 ? cz_const : depth_cov(d2));
+        PointBlocks B;
+        point_blocks(c1, pts + 3 * i, m1, w1, m2, w2, B);
+        double inv[9];
+        inv3_sym(B.Hpp, inv);
+        double r3[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          double v = B.bp[k];
+#pragma unroll
+          for (int r = 0; r < 6; r++) v -= B.Hcp[3 * r + k] * dc[r];
+          r3[k] = v;
+        }
+#pragma unroll
+        for (int k = 0; k < 3; k++) pts[3 * i + k] += inv[3 * k] * r3[0] + inv[3 * k + 1] * r3[1] + inv[3 * k + 2] * r3[2];
+      }
+    __syncwarp();
+    cam_oplus(c1, dc);
+  }
+  // cams.first->estimate().cast<float>().inverse().matrix()
+  float Rf[9], tf[3];
+#pragma unroll
+  for (int i = 0; i < 9; i++) Rf[i] = (float)c1.R[i];
+#pragma unroll
+  for (int i = 0; i < 3; i++) tf[i] = (float)c1.t[i];
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) T.R[3 * r + k] = Rf[3 * k + r];
+    T.t[r] = -(__fmul_rn(Rf[r], tf[0]) + __fmul_rn(Rf[3 + r], tf[1]) + __fmul_rn(Rf[6 + r], tf[2]));
+  }
+}
+
+// node.cpp:1225-1268 on the result of ransac_select_kernel.  One warp per pair.
+template <int NW>
+__global__ void __launch_bounds__(32)
+    refine_g2o_kernel(const PairDesc* __restrict__ pairs, int maxM, int iterations, const float4* __restrict__ mfrom,
+                      const float4* __restrict__ mto, const int32_t* __restrict__ n_all,
+                      const rgbdslam_b200_dmatch* __restrict__ matches, rgbdslam_b200_pair_result* __restrict__ results,
+                      rgbdslam_b200_dmatch* __restrict__ inlier_matches) {
+  extern __shared__ double refine_smem[];  // pts: 3 * maxM doubles, then keypoints 2 x maxM float2
+  const int p = blockIdx.x, lane = threadIdx.x;
+  const PairDesc pd = pairs[p];
+  const int M = n_all[p];
+  rgbdslam_b200_pair_result res = results[p];
+  const unsigned min_thr = min_inlier_threshold(M);
+  if (!(M > c_params.min_matches && M >= 4 && (unsigned)res.n_inliers > min_thr)) return;  // :1226
+  double* pts = refine_smem;
+  float2* kp_n = reinterpret_cast<float2*>(refine_smem + 3 * maxM);
+  float2* kp_e = kp_n + maxM;
+  const float4* sfrom = mfrom + (size_t)p * maxM;
+  const float4* sto = mto + (size_t)p * maxM;
+  for (int i = lane; i < M; i += 32) {
+    const rgbdslam_b200_dmatch m = matches[(size_t)p * maxM + i];
+    kp_n[i] = make_float2(pd.q_kp[m.queryIdx].x, pd.q_kp[m.queryIdx].y);
+    kp_e[i] = make_float2(pd.t_kp[m.trainIdx].x, pd.t_kp[m.trainIdx].y);
+  }
+  __syncwarp();
+  const int nw = (M + 31) >> 5;
+  Rt T;
+  T.R[0] = res.ransac_trafo[0]; T.R[1] = res.ransac_trafo[4]; T.R[2] = res.ransac_trafo[8];
+  T.R[3] = res.ransac_trafo[1]; T.R[4] = res.ransac_trafo[5]; T.R[5] = res.ransac_trafo[9];
+  T.R[6] = res.ransac_trafo[2]; T.R[7] = res.ransac_trafo[6]; T.R[8] = res.ransac_trafo[10];
+  T.t[0] = res.ransac_trafo[12]; T.t[1] = res.ransac_trafo[13]; T.t[2] = res.ransac_trafo[14];
+  uint32_t words0[NW], words1[NW];
+  double err0;
+  const int cnt0 = score_all<NW>(sfrom, sto, M, nw, lane, T, words0, err0);  // == the inlier set ransac_select stored
+  Rt T1 = T;
+  ba_refine<NW>(sfrom, sto, kp_n, kp_e, words0, nw, lane, iterations, T1, pts);
+  double err1;
+  int cnt1 = score_all<NW>(sfrom, sto, M, nw, lane, T1, words1, err1);
+  bool accept = false;
+  if (cnt1 >= cnt0 || ((unsigned)cnt1 >= min_thr && err1 < (double)res.rmse)) {  // :1241
+    if (cnt1 > cnt0) {                                                           // :1243-1251
+      ba_refine<NW>(sfrom, sto, kp_n, kp_e, words1, nw, lane, iterations, T1, pts);
+      cnt1 = score_all<NW>(sfrom, sto, M, nw, lane, T1, words1, err1);
+    }
+    accept = cnt1 >= cnt0;  // :1254
+  }
+  if (!accept) return;
+  res.n_inliers = cnt1;
+  res.rmse = (float)err1;
+  res.valid_iterations += 1;
+  res.ransac_trafo[0] = T1.R[0]; res.ransac_trafo[1] = T1.R[3]; res.ransac_trafo[2] = T1.R[6];
+  res.ransac_trafo[4] = T1.R[1]; res.ransac_trafo[5] = T1.R[4]; res.ransac_trafo[6] = T1.R[7];
+  res.ransac_trafo[8] = T1.R[2]; res.ransac_trafo[9] = T1.R[5]; res.ransac_trafo[10] = T1.R[8];
+  res.ransac_trafo[12] = T1.t[0]; res.ransac_trafo[13] = T1.t[1]; res.ransac_trafo[14] = T1.t[2];
+  if (inlier_matches) {
+    int base = 0;
+#pragma unroll
+    for (int w = 0; w < NW; w++) {
+      if (w < nw) {
+        const uint32_t word = words1[w];
+        if ((word >> lane) & 1u) {
+          const int pos = base + __popc(word & ((1u << lane) - 1u));
+          inlier_matches[(size_t)p * maxM + pos] = matches[(size_t)p * maxM + w * 32 + lane];
+        }
+        base += __popc(word);
+      }
+    }
+  }
+  if ((unsigned)cnt1 >= min_thr) {
+    res.info_scale = (double)((float)cnt1 / (res.rmse * res.rmse));
+    res.id1 = pd.id_t;
+    res.id2 = pd.id_q;
+  }
+  if (lane == 0) results[p] = res;
+}
+
+cudaError_t launch_refine_g2o(const PairDesc* pairs, int npairs, int max_matches, int iterations, const float4* mfrom,
+                              const float4* mto, const int32_t* n_all, const rgbdslam_b200_dmatch* matches,
+                              rgbdslam_b200_pair_result* results, rgbdslam_b200_dmatch* inlier_matches, cudaStream_t stream) {
+  if (npairs <= 0 || iterations <= 0) return cudaSuccess;
+  const size_t smem = (size_t)max_matches * (24 + 16);
+  if (max_matches <= 320)
+    refine_g2o_kernel<10><<<npairs, 32, smem, stream>>>(pairs, max_matches, iterations, mfrom, mto, n_all, matches, results,
+                                                        inlier_matches);
+  else
+    refine_g2o_kernel<kMaxMaskWords><<<npairs, 32, smem, stream>>>(pairs, max_matches, iterations, mfrom, mto, n_all, matches,
+                                                                   results, inlier_matches);
+  return cudaGetLastError();
+}
+
 }  // namespace rb200

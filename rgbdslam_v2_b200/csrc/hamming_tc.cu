@@ -117,6 +117,17 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "memory");
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// Compiler-level ordering only (no instruction): the values of v[] may not be consumed before this point, i.e. before
+// the tcgen05.wait::ld that precedes it, even when a later tcgen05.ld for another buffer has already been issued.
+__device__ __forceinline__ void tc_reg_fence(uint32_t (&v)[32]) {
+  asm volatile(""
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                 "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]),
+                 "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]),
+                 "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+               :
+               : "memory");
+}
 
 // UMMA shared-memory matrix descriptor, K-major, SWIZZLE_NONE ("interleave"):
 //   bits [0,14)  start address >> 4
@@ -418,7 +429,7 @@ __global__ void __launch_bounds__(kTc256Threads, 1) tc_match256_kernel(const Ham
     uint32_t acc = 0, pacc = 0;
     for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
       const HamItem item = items[it];
-      int best = kNoBest;
+      int best = kNoBest, best1 = kNoBest, best2 = kNoBest, best3 = kNoBest;
       float s0 = -3.0e38f, s1 = -3.0e38f, s2 = -3.0e38f, s3 = -3.0e38f;
       int i0 = -1, i1 = -1, i2 = -1, i3 = -1;
       long long u8_best = -1;  // MODE 2: (dot << 17) | (0x1FFFF - tie priority); -1 = no positive dot yet
@@ -427,22 +438,44 @@ __global__ void __launch_bounds__(kTc256Threads, 1) tc_match256_kernel(const Ham
         mbar_wait(bar(kBarAccFull + acc), pacc);
         tc_fence_after();
         const uint32_t t0 = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * 256 + h * 128;
+        if (MODE == 0) {
+          // Software-pipelined drain: the tcgen05.ld of chunk c+1 is in flight while chunk c is reduced, and the running
+          // arg-max is kept in 4 independent accumulators (keys are unique, so the split does not change the result).  A single
+          // dependent max chain plus exposed TMEM-load latency made the epilogue (~1.6 k cycles per tile), not the MMAs
+          // (~1.1 k), the critical path: ncu showed the tensor pipe 65 % active.
+          uint32_t va[32], vb[32];
+          tc_ld32(t0, va);
+#pragma unroll
+          for (int c = 0; c < 4; c++) {
+            tc_wait_ld();
+            uint32_t(&cur)[32] = (c & 1) ? vb : va;
+            if (c < 3) tc_ld32(t0 + (c + 1) * 32, (c & 1) ? va : vb);
+            tc_reg_fence(cur);
+            const int col0 = nb * 128 + c * 32;
+            if (col0 + 32 <= item.nsearch) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {  // max(max(a, b), c) compiles to one VIMNMX3
+#define RB200_KEY(J) ((int)cur[J] * 65536 + (65535 - (col0 + (J))))
+                best = max(max(best, RB200_KEY(j)), RB200_KEY(j + 4));
+                best1 = max(max(best1, RB200_KEY(j + 1)), RB200_KEY(j + 5));
+                best2 = max(max(best2, RB200_KEY(j + 2)), RB200_KEY(j + 6));
+                best3 = max(max(best3, RB200_KEY(j + 3)), RB200_KEY(j + 7));
+#undef RB200_KEY
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; j++)
+                if (col0 + j < item.nsearch) best = max(best, (int)cur[j] * 65536 + (65535 - (col0 + j)));
+            }
+          }
+        } else
 #pragma unroll 1
         for (int c = 0; c < 4; c++) {
           uint32_t v[32];
           tc_ld32(t0 + c * 32, v);
           tc_wait_ld();
           const int col0 = nb * 128 + c * 32;
-          if (MODE == 0) {
-            if (col0 + 32 <= item.nsearch) {
-#pragma unroll
-              for (int j = 0; j < 32; j++) best = max(best, (int)v[j] * 65536 + (65535 - (col0 + j)));
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; j++)
-                if (col0 + j < item.nsearch) best = max(best, (int)v[j] * 65536 + (65535 - (col0 + j)));
-            }
-          } else if (MODE == 2) {
+          if (MODE == 2) {
             // SiftGPU RowMatch / ColMatch bookkeeping (ProgramCU.cu:1708-1736, 1463-1478, 1771-1777): strict >, only
             // positive dots register, the runner-up VALUE counts duplicates of the maximum.
 #pragma unroll
@@ -487,6 +520,7 @@ __global__ void __launch_bounds__(kTc256Threads, 1) tc_match256_kernel(const Ham
       }
       if (row < item.nq_valid) {
         if (MODE == 0) {
+          best = max(max(best, best1), max(best2, best3));
           int2 o = make_int2(257, -1);
           if (best != kNoBest) {
             const int s = best >> 16;

@@ -254,3 +254,34 @@ def trajectory(n: int, seed: int = 0) -> np.ndarray:
         out[k, :3, 3] = [0.9 * np.sin(a), 0.25 * np.sin(2 * a), 0.6 * np.cos(a) - 0.2]
         out[k, 3, 3] = 1
     return out
+
+
+# ---- two views of a point set with pixel observations (pairwise g2o refinement tests) --------------------------------
+_KREF = np.array([[521.0, 0, 319.5], [0, 521.0, 239.5], [0, 0, 1]])  # the camera hard-coded in transformation_estimation.cpp:56
+
+
+def _rodrigues(axis, ang):
+    axis = np.asarray(axis, float) / np.linalg.norm(axis)
+    x, y, z = axis
+    Kx = np.array([[0, -z, y], [z, 0, -x], [-y, x, 0]])
+    return np.eye(3) + np.sin(ang) * Kx + (1 - np.cos(ang)) * Kx @ Kx
+
+
+def make_refine_scene(rng, n, noise_px=0.3, noise_z=0.002, angle=0.08, trans=(0.10, -0.03, 0.05)):
+    """Points seen by the newer camera (world frame) and by the earlier camera at pose X1 (world-from-earlier)."""
+    X1 = np.eye(4); X1[:3, :3] = _rodrigues([0.2, 1.0, 0.1], angle); X1[:3, 3] = trans
+    pw = np.stack([rng.uniform(-1.2, 1.2, n), rng.uniform(-0.9, 0.9, n), rng.uniform(1.0, 4.0, n)], 1)
+    pe = (np.linalg.inv(X1) @ np.c_[pw, np.ones(n)].T).T[:, :3]
+
+    def observe(p):
+        uv = (_KREF @ p.T).T
+        uv = uv[:, :2] / uv[:, 2:3] + rng.normal(0, noise_px, (len(p), 2))
+        z = p[:, 2] + rng.normal(0, noise_z, len(p))
+        xyz = np.c_[(uv[:, 0] - _KREF[0, 2]) * z / _KREF[0, 0], (uv[:, 1] - _KREF[1, 2]) * z / _KREF[1, 1], z, np.ones(len(p))]
+        return uv.astype(np.float32), xyz.astype(np.float32)
+
+    kp_n, xyz_n = observe(pw)
+    kp_e, xyz_e = observe(pe)
+    return X1, kp_n, xyz_n, kp_e, xyz_e
+
+

@@ -1,0 +1,88 @@
+"""oracle/refine_oracle.c (pairwise g2o refinement, transformation_estimation.cpp:126-170 + node.cpp:1225-1268):
+analytic Jacobians against numerical differentiation, convergence of the Gauss-Newton to the true pose, and the accept
+logic.  CPU only."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+K = np.array([[521.0, 0, 319.5], [0, 521.0, 239.5], [0, 0, 1]])
+
+
+def _rot(axis, ang):
+    axis = np.asarray(axis, float) / np.linalg.norm(axis)
+    x, y, z = axis
+    Kx = np.array([[0, -z, y], [z, 0, -x], [-y, x, 0]])
+    return np.eye(3) + np.sin(ang) * Kx + (1 - np.cos(ang)) * Kx @ Kx
+
+
+def _err(lib, R, t, pw, meas):
+    e = np.zeros(3)
+    lib.oracle_edge_depth_error(R.ctypes.data_as(C.c_void_p), t.ctypes.data_as(C.c_void_p), pw.ctypes.data_as(C.c_void_p),
+                                meas.ctypes.data_as(C.c_void_p), e.ctypes.data_as(C.c_void_p))
+    return e
+
+
+def test_edge_jacobians_match_numerical_differentiation(oracle_mod):
+    lib = oracle_mod.lib()
+    rng = np.random.default_rng(0)
+    for _ in range(5):
+        R = np.ascontiguousarray(_rot(rng.normal(size=3), rng.uniform(0, 0.6)))
+        t = rng.normal(0, 0.3, 3)
+        pw = R @ np.array([rng.uniform(-1, 1), rng.uniform(-1, 1), rng.uniform(1, 4)]) + t
+        meas = np.array([300.0, 200.0, 2.0])
+        Jc, Jp = np.zeros(18), np.zeros(9)
+        lib.oracle_edge_depth_jacobians(R.ctypes.data_as(C.c_void_p), t.ctypes.data_as(C.c_void_p), pw.ctypes.data_as(C.c_void_p),
+                                        meas.ctypes.data_as(C.c_void_p), Jc.ctypes.data_as(C.c_void_p), Jp.ctypes.data_as(C.c_void_p))
+        Jc, Jp = Jc.reshape(3, 6), Jp.reshape(3, 3)
+        h = 1e-6
+        for k in range(6):
+            d = np.zeros(6); d[k] = h
+            Rp, tp = R.copy(), t.copy(); lib.oracle_pose_oplus(Rp.ctypes.data_as(C.c_void_p), tp.ctypes.data_as(C.c_void_p), d.ctypes.data_as(C.c_void_p))
+            Rm, tm = R.copy(), t.copy(); lib.oracle_pose_oplus(Rm.ctypes.data_as(C.c_void_p), tm.ctypes.data_as(C.c_void_p), (-d).ctypes.data_as(C.c_void_p))
+            num = (_err(lib, Rp, tp, pw, meas) - _err(lib, Rm, tm, pw, meas)) / (2 * h)
+            assert np.allclose(num, Jc[:, k], rtol=1e-5, atol=1e-4), (k, num, Jc[:, k])
+        for k in range(3):
+            d = np.zeros(3); d[k] = h
+            num = (_err(lib, R, t, pw + d, meas) - _err(lib, R, t, pw - d, meas)) / (2 * h)
+            assert np.allclose(num, Jp[:, k], rtol=1e-5, atol=1e-4)
+
+
+from rgbdslam_v2_b200.synth import make_refine_scene as make_scene  # noqa: E402
+
+
+def test_gauss_newton_converges_to_the_true_relative_pose(oracle_mod):
+    rng = np.random.default_rng(3)
+    n = 120
+    X1, kp_n, xyz_n, kp_e, xyz_e = make_scene(rng, n)
+    m = np.zeros(n, oracle_mod.DMATCH_DTYPE); m["queryIdx"] = np.arange(n); m["trainIdx"] = np.arange(n)
+    prm = oracle_mod.make_params(depth_cov_z0=2.0)
+    T_true = np.linalg.inv(X1)          # maps newer-frame (world) points into the earlier frame
+    # the reference seeds cam1 with the estimate itself and returns the inverse of the optimised pose (:76-84, :168)
+    T0 = T_true.copy(); T0[:3, 3] += [0.02, -0.01, 0.015]; T0[:3, :3] = T0[:3, :3] @ _rot([0, 0, 1], 0.01)
+    T = oracle_mod.get_transform_from_matches_g2o(prm, xyz_n, kp_n, xyz_e, kp_e, m, np.arange(n), T0.astype(np.float32), 10)
+    # converged pose of cam1 is X1 -> returned matrix is X1^-1 = T_true
+    assert np.abs(T[:3, 3] - T_true[:3, 3]).max() < 2e-3 and np.abs(T[:3, :3] - T_true[:3, :3]).max() < 1e-3
+    assert np.abs(T - T_true).max() < np.abs(T0 - T_true).max()
+    # more iterations change nothing: exactly `iterations` undamped steps, already converged
+    T20 = oracle_mod.get_transform_from_matches_g2o(prm, xyz_n, kp_n, xyz_e, kp_e, m, np.arange(n), T0.astype(np.float32), 20)
+    assert np.abs(T20 - T).max() < 1e-5
+
+
+def test_refine_accepts_only_equal_or_better(oracle_mod):
+    rng = np.random.default_rng(4)
+    n = 150
+    X1, kp_n, xyz_n, kp_e, xyz_e = make_scene(rng, n)
+    xyz_e[:20] = xyz_e[rng.permutation(n)[:20]]   # 20 wrong correspondences
+    m = np.zeros(n, oracle_mod.DMATCH_DTYPE); m["queryIdx"] = np.arange(n); m["trainIdx"] = np.arange(n)
+    m["distance"] = np.linspace(0.1, 0.4, n).astype(np.float32)
+    prm = oracle_mod.make_params(depth_cov_z0=2.0)
+    T_true = np.linalg.inv(X1).astype(np.float32)
+    inl = np.ones(n, np.uint8); inl[:20] = 0
+    T, rmse, inl2, n_inl, vi = oracle_mod.refine_g2o(prm, 5, xyz_n, kp_n, xyz_e, kp_e, m, T_true, 2.5, inl, 7)
+    assert n_inl >= 130 and vi in (7, 8)
+    if vi == 8:
+        assert rmse < 3.0 and inl2.sum() == n_inl
+    # refinement off / too few inliers: untouched
+    T2, rmse2, _, n2, vi2 = oracle_mod.refine_g2o(prm, 0, xyz_n, kp_n, xyz_e, kp_e, m, T_true, 2.5, inl, 7)
+    assert np.array_equal(T2, T_true) and vi2 == 7 and n2 == 130
