@@ -184,8 +184,11 @@ static int stage_match_items(const PairDesc* h_pairs, int npairs, int stride, in
     if ((rc = s.W().d_top4.ensure(sizeof(int4) * (size_t)npairs * stride))) return rc;
     if ((rc = s.W().d_knn.ensure(sizeof(float4) * (size_t)npairs * stride))) return rc;
   }
-  const bool wide = s.hamming_path == 2 || kind == 2;  // 256-query items (tc_match256_kernel)
-  const int mblk = wide ? 256 : 128, nblk = wide ? 128 : 256;
+  // work-item shape (queries x train rows per tile): path 1 = 128 x 256 (tc_match_kernel), path 2 = 256 x 128
+  // (tc_match256_kernel; also every float-descriptor batch on paths 2 / 3 and the SiftGPU matcher), path 3 = 256 x 256
+  // (tc_match_wide_kernel, Hamming only)
+  const bool q256 = s.hamming_path >= 2 || kind == 2;
+  const int mblk = q256 ? 256 : 128, nblk = (kind == 0 && s.hamming_path == 3) || !q256 ? 256 : 128;
   std::vector<HamItem> items;
   items.reserve((size_t)npairs * 8);
   for (int p = 0; p < npairs; p++) {
@@ -232,7 +235,7 @@ static int launch_sift_knn(const PairDesc* d_pairs, int npairs, int max_nq, int 
   State& s = g_state;
   cudaEventRecord(s.W().ev[3], st);
   if (n_items > 0) {
-    cudaError_t e = s.hamming_path == 2 ? launch_l2_tc256((const HamItem*)s.W().d_items.ptr, n_items, s.sm_count, st)
+    cudaError_t e = s.hamming_path >= 2 ? launch_l2_tc256((const HamItem*)s.W().d_items.ptr, n_items, s.sm_count, st)
                                         : launch_l2_tc((const HamItem*)s.W().d_items.ptr, n_items, s.sm_count, st);
     if (e != cudaSuccess) return cuda_fail(e, "l2 tensor-core kernel");
     s.launches += 1;
@@ -252,8 +255,9 @@ static int launch_hamming(const PairDesc* d_pairs, int npairs, int max_nq, int2*
   if (s.hamming_path == 0) {
     e = launch_hamming_simt(d_pairs, npairs, max_nq, best, stride, st);
   } else if (n_items > 0) {
-    e = s.hamming_path == 2 ? launch_hamming_tc256((const HamItem*)s.W().d_items.ptr, n_items, s.sm_count, st)
-                            : launch_hamming_tc((const HamItem*)s.W().d_items.ptr, n_items, s.sm_count, st);
+    e = s.hamming_path == 3   ? launch_hamming_tc_wide((const HamItem*)s.W().d_items.ptr, n_items, s.sm_count, st)
+        : s.hamming_path == 2 ? launch_hamming_tc256((const HamItem*)s.W().d_items.ptr, n_items, s.sm_count, st)
+                              : launch_hamming_tc((const HamItem*)s.W().d_items.ptr, n_items, s.sm_count, st);
   } else {
     cudaEventRecord(s.W().ev[1], st);
     return 0;
@@ -583,8 +587,8 @@ int rgbdslam_b200_set_sift_matcher(int matcher) {
 
 int rgbdslam_b200_set_hamming_path(int path) {
   std::lock_guard<std::mutex> lk(g_state.mu);
-  if (path < 0 || path > 2) {
-    set_error("set_hamming_path: 0 = SIMT popcount, 1 = tcgen05 int8 GEMM (128-query items), 2 = tcgen05 (256-query items)");
+  if (path < 0 || path > 3) {
+    set_error("set_hamming_path: 0 = SIMT popcount, 1 / 2 / 3 = tcgen05 int8 GEMM with 128x256 / 256x128 / 256x256 work items");
     return RGBDSLAM_B200_ERR_ARG;
   }
   g_state.hamming_path = path;

@@ -104,6 +104,18 @@ __device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t desc_a, uint
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(acc)
       : "memory");
 }
+// One lane of a fully converged warp (elect.sync): the way to issue tcgen05 / bulk-copy instructions from warp-uniform code.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -211,33 +223,35 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_match_kernel(const HamItem* 
         }
       }
     }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      uint32_t sa = 0, pa = 0, sb = 0, pb = 0, acc = 0, pacc = 0;
-      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-        const int n_btiles = items[it].n_btiles;
-        mbar_wait(bar(0 + sa), pa);
+  } else if (warp == 1) {  // warp-uniform walk, one elected lane issues (see tc_match256_kernel)
+    uint32_t sa = 0, pa = 0, sb = 0, pb = 0, acc = 0, pacc = 0;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+      const int n_btiles = items[it].n_btiles;
+      mbar_wait(bar(0 + sa), pa);
+      tc_fence_after();
+      for (int nb = 0; nb < n_btiles; nb++) {
+        mbar_wait(bar(4 + sb), pb);
+        mbar_wait(bar(10 + acc), pacc ^ 1);
         tc_fence_after();
-        for (int nb = 0; nb < n_btiles; nb++) {
-          mbar_wait(bar(4 + sb), pb);
-          mbar_wait(bar(10 + acc), pacc ^ 1);
-          tc_fence_after();
-          const uint32_t a0 = sA + sa * kTileA, b0 = sB + sb * kTileB;
+        if (elect_one()) {
+          const uint64_t da = make_desc(sA + sa * kTileA), db = make_desc(sB + sb * kTileB);
 #pragma unroll
           for (int k = 0; k < 8; k++) {
             if (MODE == 0)
-              tc_mma_i8(tmem_base + acc * 256, make_desc(a0 + k * 256), make_desc(b0 + k * 256), kIdescI8, k > 0 ? 1u : 0u);
+              tc_mma_i8(tmem_base + acc * 256, da + (uint64_t)(k * 16), db + (uint64_t)(k * 16), kIdescI8, k > 0 ? 1u : 0u);
             else
-              tc_mma_bf16(tmem_base + acc * 256, make_desc(a0 + k * 256), make_desc(b0 + k * 256), kIdescBF16, k > 0 ? 1u : 0u);
+              tc_mma_bf16(tmem_base + acc * 256, da + (uint64_t)(k * 16), db + (uint64_t)(k * 16), kIdescBF16, k > 0 ? 1u : 0u);
           }
           tc_commit(bar(6 + sb));    // B stage may be refilled once these MMAs retire
           tc_commit(bar(8 + acc));   // accumulator ready for the epilogue
-          if (++sb == 2) { sb = 0; pb ^= 1; }
-          if (++acc == 2) { acc = 0; pacc ^= 1; }
         }
-        tc_commit(bar(2 + sa));  // A stage free
-        if (++sa == 2) { sa = 0; pa ^= 1; }
+        __syncwarp();
+        if (++sb == 2) { sb = 0; pb ^= 1; }
+        if (++acc == 2) { acc = 0; pacc ^= 1; }
       }
+      if (elect_one()) tc_commit(bar(2 + sa));  // A stage free
+      __syncwarp();
+      if (++sa == 2) { sa = 0; pa ^= 1; }
     }
   } else {
     const int wq = warp & 3;  // TMEM lane quadrant this warp may access
@@ -345,6 +359,18 @@ constexpr uint32_t kIdescI8_N128 = (2u << 4) | (1u << 7) | (1u << 10) | ((128u >
 constexpr uint32_t kIdescU8_N128 = (2u << 4) | ((128u >> 3) << 17) | ((128u >> 4) << 24);  // a/b format 0 = unsigned 8-bit
 constexpr uint32_t kIdescBF16_N128 = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
 
+#ifdef RB200_PROFILE_TC
+// [role: loader, MMA issuer, epilogue warps][cycles waiting on A, on B, on accumulators, total, participants]
+__device__ unsigned long long g_tc_prof[3][8];
+extern "C" int rb200_debug_tc_profile(unsigned long long* out24, int reset) {
+  cudaError_t e = cudaMemcpyFromSymbol(out24, g_tc_prof, sizeof(unsigned long long) * 24);
+  if (e == cudaSuccess && reset) {
+    unsigned long long z[24] = {0};
+    e = cudaMemcpyToSymbol(g_tc_prof, z, sizeof(z));
+  }
+  return (int)e;
+}
+#endif
 template <int MODE>
 __global__ void __launch_bounds__(kTc256Threads, 1) tc_match256_kernel(const HamItem* __restrict__ items, int n_items) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -370,18 +396,24 @@ __global__ void __launch_bounds__(kTc256Threads, 1) tc_match256_kernel(const Ham
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+#ifdef RB200_PROFILE_TC
+  long long pf_a = 0, pf_b = 0, pf_acc = 0, pf_t0 = clock64();
+#define RB200_TIMED_WAIT(ACC, ...) { const long long c0_ = clock64(); mbar_wait(__VA_ARGS__); ACC += clock64() - c0_; }
+#else
+#define RB200_TIMED_WAIT(ACC, ...) mbar_wait(__VA_ARGS__);
+#endif
 
   if (warp == 0) {
     if (lane == 0) {
       uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
       for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
         const HamItem item = items[it];
-        mbar_wait(bar(kBarAEmpty + sa), pa ^ 1);
+        RB200_TIMED_WAIT(pf_a, bar(kBarAEmpty + sa), pa ^ 1)
         mbar_expect_tx(bar(kBarAFull + sa), kA256);
         bulk_g2s(sA + sa * kA256, item.a, kA256, bar(kBarAFull + sa));
         if (++sa == kASt) { sa = 0; pa ^= 1; }
         for (int nb = 0; nb < item.n_btiles; nb++) {
-          mbar_wait(bar(kBarBEmpty + sb), pb ^ 1);
+          RB200_TIMED_WAIT(pf_b, bar(kBarBEmpty + sb), pb ^ 1)
           mbar_expect_tx(bar(kBarBFull + sb), kB128);
           bulk_g2s(sB + sb * kB128, item.b + (size_t)nb * kB128, kB128, bar(kBarBFull + sb));
           if (++sb == kBSt) { sb = 0; pb ^= 1; }
@@ -389,38 +421,42 @@ __global__ void __launch_bounds__(kTc256Threads, 1) tc_match256_kernel(const Ham
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      uint32_t sa = 0, pa = 0, sb = 0, pb = 0, acc = 0, pacc = 0;
-      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-        const int n_btiles = items[it].n_btiles;
-        mbar_wait(bar(kBarAFull + sa), pa);
+    // The whole warp walks the pipeline and one elected lane issues the tcgen05 instructions.  Issuing from inside an
+    // `if (lane == 0)` region made the compiler wrap every UTCIMMA in an ELECT / BRA.U.ANY retry loop and rebuild both
+    // descriptors from the shared-memory address: ~13 dependent instructions = 82 cycles per MMA that needs 68 cycles of
+    // tensor time (in-kernel clock64 profile: the issuer waited on barriers only 15 % of the time, i.e. it WAS the bottleneck).
+    uint32_t sa = 0, pa = 0, sb = 0, pb = 0, acc = 0, pacc = 0;
+    constexpr uint32_t kIdesc = MODE == 0 ? kIdescI8_N128 : (MODE == 2 ? kIdescU8_N128 : kIdescBF16_N128);
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+      const int n_btiles = items[it].n_btiles;
+      RB200_TIMED_WAIT(pf_a, bar(kBarAFull + sa), pa)
+      tc_fence_after();
+      for (int nb = 0; nb < n_btiles; nb++) {
+        RB200_TIMED_WAIT(pf_b, bar(kBarBFull + sb), pb)
+        RB200_TIMED_WAIT(pf_acc, bar(kBarAccEmpty + acc), pacc ^ 1)
         tc_fence_after();
-        for (int nb = 0; nb < n_btiles; nb++) {
-          mbar_wait(bar(kBarBFull + sb), pb);
-          mbar_wait(bar(kBarAccEmpty + acc), pacc ^ 1);
-          tc_fence_after();
-          const uint32_t a0 = sA + sa * kA256, b0 = sB + sb * kB128;
+        if (elect_one()) {
+          const uint64_t da = make_desc(sA + sa * kA256), db = make_desc(sB + sb * kB128);  // start-address field += bytes >> 4
 #pragma unroll
           for (int h = 0; h < 2; h++) {
 #pragma unroll
             for (int k = 0; k < (MODE == 2 ? 4 : 8); k++) {  // u8 SIFT rows carry 128 B of data: 4 k-steps of 32 B
               const uint32_t d = tmem_base + acc * 256 + h * 128;
-              if (MODE == 0)
-                tc_mma_i8(d, make_desc(a0 + h * kTileA + k * 256), make_desc(b0 + k * 256), kIdescI8_N128, k > 0 ? 1u : 0u);
-              else if (MODE == 2)
-                tc_mma_i8(d, make_desc(a0 + h * kTileA + k * 256), make_desc(b0 + k * 256), kIdescU8_N128, k > 0 ? 1u : 0u);
-              else
-                tc_mma_bf16(d, make_desc(a0 + h * kTileA + k * 256), make_desc(b0 + k * 256), kIdescBF16_N128, k > 0 ? 1u : 0u);
+              const uint64_t dak = da + (uint64_t)((h * kTileA + k * 256) >> 4), dbk = db + (uint64_t)((k * 256) >> 4);
+              if (MODE == 1) tc_mma_bf16(d, dak, dbk, kIdesc, k > 0 ? 1u : 0u);
+              else tc_mma_i8(d, dak, dbk, kIdesc, k > 0 ? 1u : 0u);
             }
           }
           tc_commit(bar(kBarBEmpty + sb));
           tc_commit(bar(kBarAccFull + acc));
-          if (++sb == kBSt) { sb = 0; pb ^= 1; }
-          if (++acc == 2) { acc = 0; pacc ^= 1; }
         }
-        tc_commit(bar(kBarAEmpty + sa));
-        if (++sa == kASt) { sa = 0; pa ^= 1; }
+        __syncwarp();
+        if (++sb == kBSt) { sb = 0; pb ^= 1; }
+        if (++acc == 2) { acc = 0; pacc ^= 1; }
       }
+      if (elect_one()) tc_commit(bar(kBarAEmpty + sa));
+      __syncwarp();
+      if (++sa == kASt) { sa = 0; pa ^= 1; }
     }
   } else {
     const int h = (warp - 2) >> 2;  // accumulator half drained by this warp group
@@ -429,53 +465,34 @@ __global__ void __launch_bounds__(kTc256Threads, 1) tc_match256_kernel(const Ham
     uint32_t acc = 0, pacc = 0;
     for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
       const HamItem item = items[it];
-      int best = kNoBest, best1 = kNoBest, best2 = kNoBest, best3 = kNoBest;
+      int best = kNoBest;
       float s0 = -3.0e38f, s1 = -3.0e38f, s2 = -3.0e38f, s3 = -3.0e38f;
       int i0 = -1, i1 = -1, i2 = -1, i3 = -1;
       long long u8_best = -1;  // MODE 2: (dot << 17) | (0x1FFFF - tie priority); -1 = no positive dot yet
       int u8_next = 0;
       for (int nb = 0; nb < item.n_btiles; nb++) {
-        mbar_wait(bar(kBarAccFull + acc), pacc);
+        RB200_TIMED_WAIT(pf_acc, bar(kBarAccFull + acc), pacc)
         tc_fence_after();
         const uint32_t t0 = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * 256 + h * 128;
-        if (MODE == 0) {
-          // Software-pipelined drain: the tcgen05.ld of chunk c+1 is in flight while chunk c is reduced, and the running
-          // arg-max is kept in 4 independent accumulators (keys are unique, so the split does not change the result).  A single
-          // dependent max chain plus exposed TMEM-load latency made the epilogue (~1.6 k cycles per tile), not the MMAs
-          // (~1.1 k), the critical path: ncu showed the tensor pipe 65 % active.
-          uint32_t va[32], vb[32];
-          tc_ld32(t0, va);
-#pragma unroll
-          for (int c = 0; c < 4; c++) {
-            tc_wait_ld();
-            uint32_t(&cur)[32] = (c & 1) ? vb : va;
-            if (c < 3) tc_ld32(t0 + (c + 1) * 32, (c & 1) ? va : vb);
-            tc_reg_fence(cur);
-            const int col0 = nb * 128 + c * 32;
-            if (col0 + 32 <= item.nsearch) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {  // max(max(a, b), c) compiles to one VIMNMX3
-#define RB200_KEY(J) ((int)cur[J] * 65536 + (65535 - (col0 + (J))))
-                best = max(max(best, RB200_KEY(j)), RB200_KEY(j + 4));
-                best1 = max(max(best1, RB200_KEY(j + 1)), RB200_KEY(j + 5));
-                best2 = max(max(best2, RB200_KEY(j + 2)), RB200_KEY(j + 6));
-                best3 = max(max(best3, RB200_KEY(j + 3)), RB200_KEY(j + 7));
-#undef RB200_KEY
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; j++)
-                if (col0 + j < item.nsearch) best = max(best, (int)cur[j] * 65536 + (65535 - (col0 + j)));
-            }
-          }
-        } else
 #pragma unroll 1
         for (int c = 0; c < 4; c++) {
           uint32_t v[32];
           tc_ld32(t0 + c * 32, v);
           tc_wait_ld();
           const int col0 = nb * 128 + c * 32;
-          if (MODE == 2) {
+          if (MODE == 0) {
+            // (a software-pipelined drain with the next tcgen05.ld in flight and 4 independent arg-max accumulators was
+            //  measured SLOWER: 63.5 vs 55.7 us -- the epilogue is not the critical path, the shared-memory operand
+            //  bandwidth of the M128 x N128 MMAs is; see tc_match_wide_kernel)
+            if (col0 + 32 <= item.nsearch) {
+#pragma unroll
+              for (int j = 0; j < 32; j++) best = max(best, (int)v[j] * 65536 + (65535 - (col0 + j)));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; j++)
+                if (col0 + j < item.nsearch) best = max(best, (int)v[j] * 65536 + (65535 - (col0 + j)));
+            }
+          } else if (MODE == 2) {
             // SiftGPU RowMatch / ColMatch bookkeeping (ProgramCU.cu:1708-1736, 1463-1478, 1771-1777): strict >, only
             // positive dots register, the runner-up VALUE counts duplicates of the maximum.
 #pragma unroll
@@ -520,7 +537,6 @@ __global__ void __launch_bounds__(kTc256Threads, 1) tc_match256_kernel(const Ham
       }
       if (row < item.nq_valid) {
         if (MODE == 0) {
-          best = max(max(best, best1), max(best2, best3));
           int2 o = make_int2(257, -1);
           if (best != kNoBest) {
             const int s = best >> 16;
@@ -542,6 +558,17 @@ __global__ void __launch_bounds__(kTc256Threads, 1) tc_match256_kernel(const Ham
       }
     }
   }
+#ifdef RB200_PROFILE_TC
+  if (lane == 0 && MODE == 0) {
+    const int role = warp == 0 ? 0 : (warp == 1 ? 1 : 2);
+    atomicAdd(&g_tc_prof[role][0], (unsigned long long)pf_a);
+    atomicAdd(&g_tc_prof[role][1], (unsigned long long)pf_b);
+    atomicAdd(&g_tc_prof[role][2], (unsigned long long)pf_acc);
+    atomicAdd(&g_tc_prof[role][3], (unsigned long long)(clock64() - pf_t0));
+    atomicAdd(&g_tc_prof[role][4], 1ull);
+  }
+#endif
+#undef RB200_TIMED_WAIT
   tc_fence_before();
   __syncthreads();
   if (warp == 2) {
@@ -570,6 +597,177 @@ cudaError_t launch_l2_tc256(const HamItem* d_items, int n_items, int sm_count, c
 }
 cudaError_t launch_siftgpu_tc256(const HamItem* d_items, int n_items, int sm_count, cudaStream_t stream) {
   return launch_tc256<2>(d_items, n_items, sm_count, stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Path 3 (default): 256-query items against 256-row train tiles.
+// ncu on tc_match256_kernel: tensor pipe 65 % active, L2 21 %, HBM 31 % -- and each M128 x N128 x K32 MMA reads 8 KiB of
+// operands from shared memory for 68 cycles of math (120 B/clk of a 128 B/clk port, plus the bulk-copy writes): the
+// shared-memory operand bandwidth is the limiter.  N = 256 halves the A re-reads per MAC (12 KiB per 136 cycles = 88 B/clk).
+// TMEM then holds exactly two M128 x N256 accumulators, one per query half; they double-buffer EACH OTHER: while half 1
+// accumulates tile b, the epilogue drains half 0 of tile b.  A ring: 3 x 32 KiB (one query half per slot), B ring:
+// 2 x 64 KiB.  16 epilogue warps: (half, column half, lane quadrant); the two column halves of a row meet in shared memory.
+constexpr int kWideEpiWarps = 16;
+constexpr int kWideThreads = 64 + kWideEpiWarps * 32;
+constexpr int kWASlots = 3, kWBSlots = 2;
+constexpr uint32_t kWideBarsOff = kWASlots * kTileA + kWBSlots * kTileB;  // 224 KiB
+constexpr uint32_t kWideSmemBytes = kWideBarsOff + 256 + 1024;
+static_assert(kWideSmemBytes <= 232448, "tc_match_wide: shared memory over the 227 KiB per-CTA limit");
+constexpr int kWAFull = 0, kWAEmpty = kWASlots, kWBFull = 2 * kWASlots, kWBEmpty = kWBFull + kWBSlots, kWAccFull = kWBEmpty + kWBSlots,
+              kWAccEmpty = kWAccFull + 2;
+static_assert((kWAccEmpty + 2) * 8 <= 192, "barrier area");
+
+__global__ void __launch_bounds__(kWideThreads, 1) tc_match_wide_kernel(const HamItem* __restrict__ items, int n_items) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sA = smem_u32(smem);
+  const uint32_t sB = sA + kWASlots * kTileA;
+  const uint32_t bars = sA + kWideBarsOff;
+  auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + kWideBarsOff + 192);
+  int* s_best = reinterpret_cast<int*>(smem + kWideBarsOff + 256);  // [half][128 rows]: partial arg-max of column half 1
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kWAccEmpty; i++) mbar_init(bar(i), 1);
+    mbar_init(bar(kWAccEmpty), 8);  // one arrival per epilogue warp of the half
+    mbar_init(bar(kWAccEmpty + 1), 8);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32((const void*)tmem_ptr_smem))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
+      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const HamItem item = items[it];
+        const int n_halves = item.nq_valid > 128 ? 2 : 1;
+        for (int h = 0; h < n_halves; h++) {
+          mbar_wait(bar(kWAEmpty + sa), pa ^ 1);
+          mbar_expect_tx(bar(kWAFull + sa), kTileA);
+          bulk_g2s(sA + sa * kTileA, item.a + (size_t)h * kTileA, kTileA, bar(kWAFull + sa));
+          if (++sa == kWASlots) { sa = 0; pa ^= 1; }
+        }
+        for (int nb = 0; nb < item.n_btiles; nb++) {
+          mbar_wait(bar(kWBEmpty + sb), pb ^ 1);
+          mbar_expect_tx(bar(kWBFull + sb), kTileB);
+          bulk_g2s(sB + sb * kTileB, item.b + (size_t)nb * kTileB, kTileB, bar(kWBFull + sb));
+          if (++sb == kWBSlots) { sb = 0; pb ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {  // warp-uniform walk, one elected lane issues (see tc_match256_kernel)
+    uint32_t sa = 0, pa = 0, sb = 0, pb = 0, pacc0 = 0, pacc1 = 0;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+      const HamItem item = items[it];
+      const int n_halves = item.nq_valid > 128 ? 2 : 1;
+      uint32_t slot[2], phase[2];
+      for (int h = 0; h < n_halves; h++) {
+        slot[h] = sa;
+        phase[h] = pa;
+        if (++sa == kWASlots) { sa = 0; pa ^= 1; }
+      }
+      for (int nb = 0; nb < item.n_btiles; nb++) {
+        mbar_wait(bar(kWBFull + sb), pb);
+        for (int h = 0; h < n_halves; h++) {
+          if (nb == 0) mbar_wait(bar(kWAFull + slot[h]), phase[h]);
+          mbar_wait(bar(kWAccEmpty + h), (h ? pacc1 : pacc0) ^ 1);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t da = make_desc(sA + slot[h] * kTileA), db = make_desc(sB + sb * kTileB);
+            const uint32_t d = tmem_base + h * 256;
+#pragma unroll
+            for (int k = 0; k < 8; k++) tc_mma_i8(d, da + (uint64_t)(k * 16), db + (uint64_t)(k * 16), kIdescI8, k > 0 ? 1u : 0u);
+            tc_commit(bar(kWAccFull + h));
+            if (h == n_halves - 1) tc_commit(bar(kWBEmpty + sb));
+          }
+          __syncwarp();
+          if (h) pacc1 ^= 1; else pacc0 ^= 1;
+        }
+        if (++sb == kWBSlots) { sb = 0; pb ^= 1; }
+      }
+      if (elect_one())
+        for (int h = 0; h < n_halves; h++) tc_commit(bar(kWAEmpty + slot[h]));
+      __syncwarp();
+    }
+  } else {
+    const int e = warp - 2;
+    const int h = e >> 3;         // query half whose accumulator this warp drains
+    const int c = (e >> 2) & 1;   // column half of the 256-column tile
+    const int wq = warp & 3;      // TMEM lane quadrant this warp may access
+    const int row = h * 128 + wq * 32 + lane;
+    uint32_t pacc = 0;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+      const HamItem item = items[it];
+      if (h == 1 && item.nq_valid <= 128) continue;  // the second half is never issued for short items
+      int best = kNoBest;
+      for (int nb = 0; nb < item.n_btiles; nb++) {
+        mbar_wait(bar(kWAccFull + h), pacc);
+        tc_fence_after();
+        const uint32_t t0 = tmem_base + ((uint32_t)(wq * 32) << 16) + h * 256 + c * 128;
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ch++) {
+          uint32_t v[32];
+          tc_ld32(t0 + ch * 32, v);
+          tc_wait_ld();
+          const int col0 = nb * 256 + c * 128 + ch * 32;
+          if (col0 + 32 <= item.nsearch) {
+#pragma unroll
+            for (int j = 0; j < 32; j++) best = max(best, (int)v[j] * 65536 + (65535 - (col0 + j)));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j++)
+              if (col0 + j < item.nsearch) best = max(best, (int)v[j] * 65536 + (65535 - (col0 + j)));
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(kWAccEmpty + h));
+        pacc ^= 1;
+      }
+      // the two column halves of a row meet here (8 warps = 256 threads per query half, named barriers 1 and 2)
+      if (c == 1) s_best[h * 128 + wq * 32 + lane] = best;
+      asm volatile("bar.sync %0, 256;" ::"r"(1 + h) : "memory");
+      if (c == 0) {
+        best = max(best, s_best[h * 128 + wq * 32 + lane]);
+        if (row < item.nq_valid) {
+          int2 o = make_int2(257, -1);
+          if (best != kNoBest) {
+            const int sdot = best >> 16;
+            o.x = (256 - sdot) >> 1;
+            o.y = 65535 - (best & 0xFFFF);
+          }
+          item.out[row] = o;
+        }
+      }
+      asm volatile("bar.sync %0, 256;" ::"r"(1 + h) : "memory");
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+cudaError_t launch_hamming_tc_wide(const HamItem* d_items, int n_items, int sm_count, cudaStream_t stream) {
+  if (n_items <= 0) return cudaSuccess;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tc_match_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWideSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int grid = n_items < sm_count ? n_items : sm_count;
+  tc_match_wide_kernel<<<grid, kWideThreads, kWideSmemBytes, stream>>>(d_items, n_items);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_hamming_tc(const HamItem* d_items, int n_items, int sm_count, cudaStream_t stream) {

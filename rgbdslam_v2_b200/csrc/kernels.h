@@ -17,6 +17,7 @@ cudaError_t launch_expand_i8(const ExpandJob* d_jobs, int njobs, int max_n_pad, 
 cudaError_t launch_hamming_tc(const HamItem* d_items, int n_items, int sm_count, cudaStream_t stream);
 // 256-query work items (HamItem::n_btiles counts 128-row B tiles, nq_valid <= 256)
 cudaError_t launch_hamming_tc256(const HamItem* d_items, int n_items, int sm_count, cudaStream_t stream);
+cudaError_t launch_hamming_tc_wide(const HamItem* d_items, int n_items, int sm_count, cudaStream_t stream);
 cudaError_t launch_l2_tc256(const HamItem* d_items, int n_items, int sm_count, cudaStream_t stream);
 
 // SIFT-128 path (sift_l2.cu / hamming_tc.cu MODE 1)

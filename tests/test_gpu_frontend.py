@@ -78,6 +78,8 @@ def test_hamming_tensor_core_path_equals_simt_path(fe, oracle_mod, nq, nt):
         hd1, idx1 = fe.brute_force_search_orb(q, t)
         fe.set_hamming_path(2)
         hd2, idx2 = fe.brute_force_search_orb(q, t)
+        fe.set_hamming_path(3)
+        hd3, idx3 = fe.brute_force_search_orb(q, t)
         fe.set_hamming_path(0)
         hd0, idx0 = fe.brute_force_search_orb(q, t)
     finally:
@@ -86,6 +88,7 @@ def test_hamming_tensor_core_path_equals_simt_path(fe, oracle_mod, nq, nt):
     assert np.array_equal(hd0, ohd) and np.array_equal(idx0, oidx)
     assert np.array_equal(hd1, ohd) and np.array_equal(idx1, oidx)
     assert np.array_equal(hd2, ohd) and np.array_equal(idx2, oidx)  # 256-query work items
+    assert np.array_equal(hd3, ohd) and np.array_equal(idx3, oidx)  # 256 x 256 work items
 
 
 def _oracle_run(oracle_mod, b, seed, first=0, **kw):
