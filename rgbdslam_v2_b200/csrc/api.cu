@@ -303,6 +303,8 @@ static int run_pairs(const std::vector<PairDesc>& h_pairs, uint64_t seed, int64_
   if ((rc = s.W().d_nall.ensure(sizeof(int32_t) * npairs))) return rc;
   if ((rc = s.W().d_hyp.ensure(sizeof(HypResult) * (size_t)npairs * (H > 0 ? H : 1)))) return rc;
   if ((rc = s.W().d_results.ensure(sizeof(rgbdslam_b200_pair_result) * npairs))) return rc;
+  if ((rc = s.W().d_cen.ensure(sizeof(float) * 8 * (size_t)npairs))) return rc;
+  if ((rc = s.W().d_nextn.ensure(sizeof(int32_t) * (size_t)npairs))) return rc;
 
   cudaStream_t st = s.W().stream;
   cudaError_t e;
@@ -385,8 +387,8 @@ static int run_pairs(const std::vector<PairDesc>& h_pairs, uint64_t seed, int64_
 
   int hyp_launches = 0;
   e = launch_ransac_hypotheses(npairs, H, maxM, seed, first_pair, (const float4*)s.W().d_mfrom.ptr,
-                               (const float4*)s.W().d_mto.ptr, (const int32_t*)s.W().d_nall.ptr, (HypResult*)s.W().d_hyp.ptr, st,
-                               &hyp_launches);
+                               (const float4*)s.W().d_mto.ptr, (const int32_t*)s.W().d_nall.ptr, (HypResult*)s.W().d_hyp.ptr,
+                               (float*)s.W().d_cen.ptr, (int32_t*)s.W().d_nextn.ptr, st, &hyp_launches);
   if (e != cudaSuccess) return cuda_fail(e, "ransac_hyp kernel");
   e = launch_ransac_select(d_pairs, npairs, H, maxM, (const float4*)s.W().d_mfrom.ptr, (const float4*)s.W().d_mto.ptr,
                            (const int32_t*)s.W().d_nall.ptr, (const rgbdslam_b200_dmatch*)s.W().d_matches.ptr,

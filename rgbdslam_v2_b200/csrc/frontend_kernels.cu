@@ -467,6 +467,8 @@ __device__ __forceinline__ double mahal_sq(const float4 x1, const float4 x2, con
   return m;
 }
 
+__device__ __noinline__ double mahal_sq_slow(const float4 x1, const float4 x2, const ScoreCtx& c) { return mahal_sq(x1, x2, c); }
+
 // computeInliersAndError (node.cpp:968-1020): returns #inliers, fills the mask words (warp-uniform) and
 // the Mahalanobis RMS (1e9 if < 3 inliers).
 template <int NW>
@@ -507,14 +509,14 @@ __device__ int score_all(const float4* __restrict__ sfrom, const float4* __restr
       const bool undecided = isnan(cm);
       bool inl = cm >= 0.f;
       double m = (double)cm;
-      if (__any_sync(kFull, undecided)) {
+      if (__any_sync(kFull, undecided)) {  // rare: kept out of line, the unrolled copies blew the instruction cache
         if (!have_ctx) {
           make_score_ctx(T, ctx);
           have_ctx = true;
         }
         if (undecided) {
           const int i = w * 32 + lane;
-          m = mahal_sq(sfrom[i], sto[i], ctx);
+          m = mahal_sq_slow(sfrom[i], sto[i], ctx);
           inl = !(m > sq_max) && (m >= 0.0);  // node.cpp:998-1005
         }
       }
@@ -615,7 +617,8 @@ template <int NW>
 __global__ void __launch_bounds__(kRansacWarps * 32, RB200_RANSAC_MINBLOCKS)
     ransac_hyp_kernel(int H, int maxM, int n_begin, int n_end, uint64_t seed, int64_t first_pair,
                       const float4* __restrict__ mfrom, const float4* __restrict__ mto,
-                      const int32_t* __restrict__ n_all, HypResult* __restrict__ hyp) {
+                      const int32_t* __restrict__ n_all, HypResult* __restrict__ hyp, float* __restrict__ cen,
+                      int32_t* __restrict__ next_n) {
   __shared__ float4 sfrom[kMaxMatchesCap];
   __shared__ float4 sto[kMaxMatchesCap];
   __shared__ float4 cfrom[kMaxMatchesCap];  // centred copies for the fit (see fit_transform)
@@ -629,50 +632,75 @@ __global__ void __launch_bounds__(kRansacWarps * 32, RB200_RANSAC_MINBLOCKS)
   const int M = n_all[p];
   if (M <= c_params.min_matches || M < 4) return;  // node.cpp:1087,1130 (selection kernel checks the same)
   const unsigned min_thr = min_inlier_threshold(M);
+  // The first phase (one CTA per pair when n_end <= kRansacWarps) publishes the pair's centroids and, after its
+  // hypotheses, the index the sequential loop would visit next; later phases read both instead of recomputing them
+  // (20 CTAs per pair used to replay the scan just to find out that 75 % of the pairs were finished).
+  const bool publish = n_begin == 0 && gridDim.x == 1 && next_n != nullptr;
+  int skip_below = 0;
   if (n_begin > 0) {
-    // records of hypotheses the sequential loop never visits are stale/unwritten: harmless, the scan skips them
-    for (int i = threadIdx.x; i < n_begin; i += blockDim.x) {
-      const HypResult* r = hyp + (size_t)p * H + i;
-      s_cnt[i] = r->count;
-      s_err[i] = r->err;
+    if (next_n != nullptr) {
+      skip_below = next_n[p];
+    } else {
+      // records of hypotheses the sequential loop never visits are stale/unwritten: harmless, the scan skips them
+      for (int i = threadIdx.x; i < n_begin; i += blockDim.x) {
+        const HypResult* r = hyp + (size_t)p * H + i;
+        s_cnt[i] = r->count;
+        s_err[i] = r->err;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const ScanState st = ransac_scan(s_cnt, s_err, M, min_thr, n_begin);
+        s_next_n = st.done ? H : st.next_n;
+      }
+      __syncthreads();
+      skip_below = s_next_n;
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      const ScanState st = ransac_scan(s_cnt, s_err, M, min_thr, n_begin);
-      s_next_n = st.done ? H : st.next_n;
-    }
-    __syncthreads();
-    if (s_next_n >= n_begin + (int)(blockIdx.x + 1) * kRansacWarps || s_next_n >= n_end) return;
+    if (skip_below >= n_begin + (int)(blockIdx.x + 1) * kRansacWarps || skip_below >= n_end) return;
   }
-  float cs[6] = {0, 0, 0, 0, 0, 0};
-  for (int i = threadIdx.x; i < M; i += blockDim.x) {
-    const float4 a = mfrom[(size_t)p * maxM + i], b = mto[(size_t)p * maxM + i];
-    sfrom[i] = a;
-    sto[i] = b;
-    if (!isnan(a.x + a.y + a.z + b.x + b.y + b.z)) {
-      cs[0] += a.x; cs[1] += a.y; cs[2] += a.z; cs[3] += b.x; cs[4] += b.y; cs[5] += b.z;
+  if (n_begin == 0 || next_n == nullptr) {
+    float cs[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = threadIdx.x; i < M; i += blockDim.x) {
+      const float4 a = mfrom[(size_t)p * maxM + i], b = mto[(size_t)p * maxM + i];
+      sfrom[i] = a;
+      sto[i] = b;
+      if (!isnan(a.x + a.y + a.z + b.x + b.y + b.z)) {
+        cs[0] += a.x; cs[1] += a.y; cs[2] += a.z; cs[3] += b.x; cs[4] += b.y; cs[5] += b.z;
+      }
     }
-  }
 #pragma unroll
-  for (int k = 0; k < 6; k++) cs[k] = wsum(cs[k]);
-  if ((threadIdx.x & 31) == 0)
-    for (int k = 0; k < 6; k++) s_part[threadIdx.x >> 5][k] = cs[k];
-  __syncthreads();
-  if (threadIdx.x < 6) {
-    float t = 0.f;
-    for (int w = 0; w < kRansacWarps; w++) t += s_part[w][threadIdx.x];
-    s_cen[threadIdx.x] = t / (float)M;  // any common offset is valid; the (NaN-free) mean keeps the centred data small
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < M; i += blockDim.x) {
-    const float4 a = sfrom[i], b = sto[i];
-    cfrom[i] = make_float4(a.x - s_cen[0], a.y - s_cen[1], a.z - s_cen[2], a.z);
-    cto[i] = make_float4(b.x - s_cen[3], b.y - s_cen[4], b.z - s_cen[5], b.z);
+    for (int k = 0; k < 6; k++) cs[k] = wsum(cs[k]);
+    if ((threadIdx.x & 31) == 0)
+      for (int k = 0; k < 6; k++) s_part[threadIdx.x >> 5][k] = cs[k];
+    __syncthreads();
+    if (threadIdx.x < 6) {
+      float t = 0.f;
+      for (int w = 0; w < kRansacWarps; w++) t += s_part[w][threadIdx.x];
+      s_cen[threadIdx.x] = t / (float)M;  // any common offset is valid; the (NaN-free) mean keeps the centred data small
+      if (publish) cen[(size_t)p * 8 + threadIdx.x] = s_cen[threadIdx.x];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < M; i += blockDim.x) {
+      const float4 a = sfrom[i], b = sto[i];
+      cfrom[i] = make_float4(a.x - s_cen[0], a.y - s_cen[1], a.z - s_cen[2], a.z);
+      cto[i] = make_float4(b.x - s_cen[3], b.y - s_cen[4], b.z - s_cen[5], b.z);
+    }
+  } else {
+    if (threadIdx.x < 6) s_cen[threadIdx.x] = cen[(size_t)p * 8 + threadIdx.x];
+    __syncthreads();
+    for (int i = threadIdx.x; i < M; i += blockDim.x) {
+      const float4 a = mfrom[(size_t)p * maxM + i], b = mto[(size_t)p * maxM + i];
+      sfrom[i] = a;
+      sto[i] = b;
+      cfrom[i] = make_float4(a.x - s_cen[0], a.y - s_cen[1], a.z - s_cen[2], a.z);
+      cto[i] = make_float4(b.x - s_cen[3], b.y - s_cen[4], b.z - s_cen[5], b.z);
+    }
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int n = n_begin + blockIdx.x * kRansacWarps + (threadIdx.x >> 5);
-  if (n >= n_end || (n_begin > 0 && n < s_next_n)) return;
+  const bool active = !(n >= n_end || (n_begin > 0 && n < skip_below));
+  if (!active && !publish) return;
+  if (active) {
   const int nw = (M + 31) >> 5;
   const uint64_t key = pair_key(seed, (uint64_t)(first_pair + p));
 
@@ -766,26 +794,42 @@ __global__ void __launch_bounds__(kRansacWarps * 32, RB200_RANSAC_MINBLOCKS)
 #pragma unroll
     for (int i = 0; i < 3; i++) r.T[9 + i] = refined.t[i];
     hyp[(size_t)p * H + n] = r;
+    if (publish) {
+      s_cnt[n] = refined_cnt;
+      s_err[n] = refined_err;
+    }
+  }
+  }  // active
+  if (publish) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const ScanState st = ransac_scan(s_cnt, s_err, M, min_thr, n_end < H ? n_end : H);
+      next_n[p] = st.done ? H : st.next_n;
+    }
   }
 }
 
 cudaError_t launch_ransac_hypotheses(int npairs, int ransac_iterations, int max_matches, uint64_t seed,
                                      int64_t first_pair, const float4* mfrom, const float4* mto,
-                                     const int32_t* n_all, HypResult* hyp, cudaStream_t stream, int* n_launches) {
+                                     const int32_t* n_all, HypResult* hyp, float* cen, int32_t* next_n, cudaStream_t stream,
+                                     int* n_launches) {
   if (n_launches) *n_launches = 0;
   if (npairs <= 0 || ransac_iterations <= 0) return cudaSuccess;
   const int H = ransac_iterations;
   const int bounds[4] = {0, RB200_PH1, RB200_PH2, H};  // non-final phase ends must stay <= kMaxScanPrefix
+  // the first phase can hand its scan result to the later ones when it runs as ONE CTA per pair
+  const int first_end = bounds[1] < H ? bounds[1] : H;
+  int32_t* nn = (first_end <= kRansacWarps && bounds[2] == bounds[1]) ? next_n : nullptr;
   for (int ph = 0; ph < 3; ph++) {
     const int n_begin = bounds[ph], n_end = bounds[ph + 1] < H ? bounds[ph + 1] : H;
     if (n_begin >= n_end) continue;
     dim3 grid((n_end - n_begin + kRansacWarps - 1) / kRansacWarps, npairs);
     if (max_matches <= 320)
       ransac_hyp_kernel<10><<<grid, kRansacWarps * 32, 0, stream>>>(H, max_matches, n_begin, n_end, seed, first_pair, mfrom, mto,
-                                                                    n_all, hyp);
+                                                                    n_all, hyp, cen, nn);
     else
       ransac_hyp_kernel<kMaxMaskWords><<<grid, kRansacWarps * 32, 0, stream>>>(H, max_matches, n_begin, n_end, seed, first_pair,
-                                                                               mfrom, mto, n_all, hyp);
+                                                                               mfrom, mto, n_all, hyp, cen, nn);
     if (n_launches) (*n_launches)++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;

@@ -40,9 +40,9 @@ cudaError_t launch_select_matches(const PairDesc* pairs, int npairs, const int2*
                                   int32_t* n_all, int max_nq, cudaStream_t stream);
 
 // RANSAC hypotheses (node.cpp:1130-1169) -- one warp per hypothesis, launched in phases [0,8) [8,40) [40,H).
-cudaError_t launch_ransac_hypotheses(int npairs, int ransac_iterations, int max_matches, uint64_t seed,
-                                     int64_t first_pair, const float4* mfrom, const float4* mto,
-                                     const int32_t* n_all, HypResult* hyp, cudaStream_t stream, int* n_launches);
+cudaError_t launch_ransac_hypotheses(int npairs, int ransac_iterations, int max_matches, uint64_t seed, int64_t first_pair,
+                                     const float4* mfrom, const float4* mto, const int32_t* n_all, HypResult* hyp, float* cen,
+                                     int32_t* next_n, cudaStream_t stream, int* n_launches);
 
 // Sequential replay of the hypothesis bookkeeping (node.cpp:1170-1216,1275) + edge (node.cpp:1335-1339).
 cudaError_t launch_ransac_select(const PairDesc* pairs, int npairs, int ransac_iterations, int max_matches,

@@ -49,11 +49,11 @@ struct Workspace {
   bool pending = false;
   DevBuf d_pairs, d_best, d_matches, d_inliers, d_mfrom, d_mto, d_nall, d_hyp, d_results;
   DevBuf d_feat_a, d_feat_b, d_xyz_a, d_xyz_b;
-  DevBuf d_i8_a, d_i8_b, d_jobs, d_items, d_top4, d_knn;
+  DevBuf d_i8_a, d_i8_b, d_jobs, d_items, d_top4, d_knn, d_cen, d_nextn;
   PinBuf h_pairs, h_jobs, h_items;
   void release() {
     DevBuf* all[] = {&d_pairs, &d_best, &d_matches, &d_inliers, &d_mfrom, &d_mto, &d_nall, &d_hyp, &d_results, &d_feat_a,
-                     &d_feat_b, &d_xyz_a, &d_xyz_b, &d_i8_a, &d_i8_b, &d_jobs, &d_items, &d_top4, &d_knn};
+                     &d_feat_b, &d_xyz_a, &d_xyz_b, &d_i8_a, &d_i8_b, &d_jobs, &d_items, &d_top4, &d_knn, &d_cen, &d_nextn};
     for (DevBuf* b : all) b->release();
     h_pairs.release();
     h_jobs.release();
