@@ -193,19 +193,31 @@ __device__ bool fit_transform(const float4* __restrict__ cfrom, const float4* __
                               const uint32_t* sel, int nw, int lane, Rt& out) {
   float W = 0.f, f0 = 0.f, f1 = 0.f, f2 = 0.f, t0 = 0.f, t1 = 0.f, t2 = 0.f;
   float c[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  constexpr int kFitGroup = (NW % 5 == 0) ? 5 : 4;
+#pragma unroll 1
+  for (int g = 0; g < NW / kFitGroup; g++) {  // rolled for code size, see score_all
+    uint32_t selg[kFitGroup];
 #pragma unroll
-  for (int w = 0; w < NW; w++) {
-    if (w < nw && ((sel[w] >> lane) & 1u)) {
-      const float4 a = cfrom[w * 32 + lane], b = cto[w * 32 + lane];
-      if (!isnan(a.w) && !isnan(b.w)) {  // transformation_estimation_euclidean.cpp:22
-        const float wt = __fdiv_rn(1.0f, a.w * b.w);  // :25
-        W += wt;
-        f0 += wt * a.x; f1 += wt * a.y; f2 += wt * a.z;
-        const float bx = wt * b.x, by = wt * b.y, bz = wt * b.z;
-        t0 += bx; t1 += by; t2 += bz;
-        c[0] += bx * a.x; c[1] += bx * a.y; c[2] += bx * a.z;
-        c[3] += by * a.x; c[4] += by * a.y; c[5] += by * a.z;
-        c[6] += bz * a.x; c[7] += bz * a.y; c[8] += bz * a.z;
+    for (int gg = 0; gg < NW / kFitGroup; gg++)
+      if (gg == g) {
+#pragma unroll
+        for (int j = 0; j < kFitGroup; j++) selg[j] = sel[gg * kFitGroup + j];
+      }
+#pragma unroll
+    for (int j = 0; j < kFitGroup; j++) {
+      const int w = g * kFitGroup + j;
+      if (w < nw && ((selg[j] >> lane) & 1u)) {
+        const float4 a = cfrom[w * 32 + lane], b = cto[w * 32 + lane];
+        if (!isnan(a.w) && !isnan(b.w)) {  // transformation_estimation_euclidean.cpp:22
+          const float wt = __fdiv_rn(1.0f, a.w * b.w);  // :25
+          W += wt;
+          f0 += wt * a.x; f1 += wt * a.y; f2 += wt * a.z;
+          const float bx = wt * b.x, by = wt * b.y, bz = wt * b.z;
+          t0 += bx; t1 += by; t2 += bz;
+          c[0] += bx * a.x; c[1] += bx * a.y; c[2] += bx * a.z;
+          c[3] += by * a.x; c[4] += by * a.y; c[5] += by * a.z;
+          c[6] += bz * a.x; c[7] += bz * a.y; c[8] += bz * a.z;
+        }
       }
     }
   }
@@ -477,54 +489,65 @@ __device__ int score_all(const float4* __restrict__ sfrom, const float4* __restr
   ScreenCtx sc;
   make_screen_ctx(T, sc);
   const double sq_max = c_params.sq_max_dist;
-  // pass 1: classify every correspondence in float32.  No branches inside a group of kGroup words, so the compiler
-  // interleaves kGroup independent dependency chains per lane.
+  // Per group of kGroup mask words: pass 1 classifies the correspondences in float32 with no branch in between (kGroup
+  // independent dependency chains per lane), pass 2 resolves the undecided ones with the float64 reference formula and
+  // builds the inlier masks.  The group loop is NOT unrolled: the fully unrolled body made the hot loop ~28 KiB of code and
+  // a quarter of all stall samples were instruction-cache misses (`stall_no_inst`); mask words are moved between the
+  // register array and the loop body with compile-time indices under a predicate.
   constexpr int kGroup = (NW % RB200_SCORE_GROUP == 0) ? RB200_SCORE_GROUP : 4;
-  float code[NW];
-#pragma unroll
-  for (int g = 0; g < NW; g += kGroup) {
-    if (g < nw) {
-#pragma unroll
-      for (int w = g; w < g + kGroup; w++) {
-        const int i = w * 32 + lane;  // < kMaxMatchesCap: rows >= M hold stale but addressable shared memory
-        const float4 a = sfrom[i], b = sto[i];
-        const float cm = mahal_screen(a, b, T, sc);
-        code[w] = (i < M && !(a.z == 0.0f || b.z == 0.0f)) ? cm : -1.f;  // node.cpp:994 (does not trigger on NaN)
-      }
-    } else {
-#pragma unroll
-      for (int w = g; w < g + kGroup; w++) code[w] = -1.f;
-    }
-  }
-  // pass 2: the float64 reference formula where float32 could not decide, inlier masks, error sum
+  constexpr int kGroups = NW / kGroup;
   ScoreCtx ctx;
   bool have_ctx = false;
   double esum = 0.0;
   int cnt = 0;
+#pragma unroll 1
+  for (int g = 0; g < kGroups; g++) {
+    float code[kGroup];
+    uint32_t wout[kGroup];
+    if (g * kGroup < nw) {
 #pragma unroll
-  for (int w = 0; w < NW; w++) {
-    uint32_t word = 0;
-    if (w < nw) {
-      const float cm = code[w];
-      const bool undecided = isnan(cm);
-      bool inl = cm >= 0.f;
-      double m = (double)cm;
-      if (__any_sync(kFull, undecided)) {  // rare: kept out of line, the unrolled copies blew the instruction cache
-        if (!have_ctx) {
-          make_score_ctx(T, ctx);
-          have_ctx = true;
-        }
-        if (undecided) {
-          const int i = w * 32 + lane;
-          m = mahal_sq_slow(sfrom[i], sto[i], ctx);
-          inl = !(m > sq_max) && (m >= 0.0);  // node.cpp:998-1005
-        }
+      for (int j = 0; j < kGroup; j++) {
+        const int i = (g * kGroup + j) * 32 + lane;  // < kMaxMatchesCap: rows >= M hold stale but addressable memory
+        const float4 a = sfrom[i], b = sto[i];
+        const float cm = mahal_screen(a, b, T, sc);
+        code[j] = (i < M && !(a.z == 0.0f || b.z == 0.0f)) ? cm : -1.f;  // node.cpp:994 (does not trigger on NaN)
       }
-      word = __ballot_sync(kFull, inl);
-      if (inl) esum = __dadd_rn(esum, m);
-      cnt += __popc(word);
+    } else {
+#pragma unroll
+      for (int j = 0; j < kGroup; j++) code[j] = -1.f;
     }
-    words[w] = word;
+#pragma unroll
+    for (int j = 0; j < kGroup; j++) {
+      const int w = g * kGroup + j;
+      uint32_t word = 0;
+      if (w < nw) {
+        const float cm = code[j];
+        const bool undecided = isnan(cm);
+        bool inl = cm >= 0.f;
+        double m = (double)cm;
+        if (__any_sync(kFull, undecided)) {  // rare: kept out of line
+          if (!have_ctx) {
+            make_score_ctx(T, ctx);
+            have_ctx = true;
+          }
+          if (undecided) {
+            const int i = w * 32 + lane;
+            m = mahal_sq_slow(sfrom[i], sto[i], ctx);
+            inl = !(m > sq_max) && (m >= 0.0);  // node.cpp:998-1005
+          }
+        }
+        word = __ballot_sync(kFull, inl);
+        if (inl) esum = __dadd_rn(esum, m);
+        cnt += __popc(word);
+      }
+      wout[j] = word;
+    }
+#pragma unroll
+    for (int gg = 0; gg < kGroups; gg++)
+      if (gg == g) {
+#pragma unroll
+        for (int j = 0; j < kGroup; j++) words[gg * kGroup + j] = wout[j];
+      }
   }
   esum = wsumd(esum);
   err = (cnt < 3) ? 1e9 : sqrt(__ddiv_rn(esum, (double)cnt));  // node.cpp:1011-1017
