@@ -426,7 +426,7 @@ def run_ours(args, rank, local_rank, world):
                              "the synchronous reference point flushes L2 (256 MiB memset) before every step",
                        "pipeline": f"{DEPTH} batches in flight on {DEPTH} library streams (rgbdslam_b200_match_pairs_submit / _wait)",
                        "pairs_per_gpu": PAIRS_PER_GPU,
-                       "exchange": "none (1 GPU)" if world == 1 else f"ncclAllGather of {world}x{PAIRS_PER_GPU} edge records (104 B) per step, inside the timed region",
+                       "exchange": "none (1 GPU)" if world == 1 else f"ncclAllGather of {world}x{PAIRS_PER_GPU} edge records (120 B) per step, inside the timed region",
                        "edges_gathered": None if all_edges is None else int((all_edges["id1"] >= 0).sum()),
                        "valid_edges_rank0": n_valid, "wall_ms_per_step_incl_flush": 1e3 * wall_resident / args.steps},
             "roofline": {"bound": "hbm", "kernel": "hamming_match", "achieved": achieved, "peak": peak, "unit": "GB/s",

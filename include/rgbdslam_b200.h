@@ -85,7 +85,14 @@ typedef struct rgbdslam_b200_params {
   int32_t use_root_sift;        /* 1     :92                      */
   int32_t g2o_transformation_refinement; /* 0 :103 -- Gauss-Newton iterations of the pairwise refinement (node.cpp:1225-1268,
                                           * transformation_estimation.cpp:126-170); needs nodes with 2-D keypoints */
-  int32_t reserved_[6];
+  /* Environment measurement model (node.cpp:1340-1342, misc.cpp:814-969, 1136-1148): > 0 enables it; an accepted RANSAC
+   * transformation is kept only if inliers / (inliers + outliers) > threshold and inliers / (inl + outl + occluded) > 0.25.
+   * Needs nodes with a depth cloud (rgbdslam_b200_nodes_create keeps one when this is > 0, or rgbdslam_b200_node_set_depth). */
+  double observability_threshold; /* -0.6 :114 (off) */
+  int32_t emm_skip_step;          /* 8    :112       */
+  int32_t cloud_creation_skip_step; /* 2  :36        */
+  float minimum_depth;            /* 0.1  :39        */
+  int32_t reserved_[1];
 } rgbdslam_b200_params;
 
 /*
@@ -102,6 +109,9 @@ typedef struct rgbdslam_b200_pair_result {
   float ransac_trafo[16];  /* Eigen::Matrix4f, column-major; maps newer-frame points into the older frame */
   double info_scale;       /* edge.informationMatrix = I6 * info_scale, = n_inliers / rmse^2 (node.cpp:1335) */
   int32_t used_identity;   /* 1 if the identity last-resort hypothesis was taken (node.cpp:1192-1215) */
+  /* MatchingResult::inlier_points / outlier_points / occluded_points / all_points (matching_result.h:40-42): filled by the
+   * environment measurement model when params.observability_threshold > 0, else 0 */
+  uint32_t inlier_points, outlier_points, occluded_points, all_points;
   int32_t reserved_;
 } rgbdslam_b200_pair_result;
 
@@ -149,6 +159,13 @@ int rgbdslam_b200_node_num_features(uint64_t node_handle, int* n);
 /* Download (any pointer may be NULL). */
 int rgbdslam_b200_node_download(uint64_t node_handle, uint8_t* desc, float* xyz1);
 /* == Node::~Node (node.cpp:371). */
+/* Give a node its point cloud (Node::pc_col) for the environment measurement model: the depth image in metres (row-major
+ * w x h float, NaN = no measurement) and K4 = (fx, fy, cx, cy).  Only the z-plane of createXYZRGBPointCloud
+ * (misc.cpp:467-556) at every params.cloud_creation_skip_step-th pixel is kept on the device. */
+int rgbdslam_b200_node_set_depth(uint64_t node_handle, const float* depth_m, int w, int h, const float K4[4]);
+/* == pairwiseObservationLikelihood(newer, older, mr) (node.cpp:1520-1554) for an explicit transformation T (Eigen::Matrix4f,
+ * column-major, newer -> older frame): counts[4] = inlier, outlier, occluded, all points. */
+int rgbdslam_b200_observation_likelihood(uint64_t newer, uint64_t older, const float T[16], uint32_t counts[4]);
 /* Attach the 2-D keypoints (feature_locations_2d_, n entries) to a node created from features: only the pairwise g2o
  * refinement reads them (edgeToFeature, transformation_estimation.cpp:91-124).  Nodes built from images carry theirs. */
 int rgbdslam_b200_node_set_keypoints(uint64_t node_handle, const rgbdslam_b200_keypoint* keypoints);

@@ -76,6 +76,10 @@ inline MatchingResult to_matching_result(const rgbdslam_b200_pair_result& r, con
   std::memcpy(mr.ransac_trafo.m, r.ransac_trafo, sizeof(r.ransac_trafo));
   mr.edge.id1 = r.id1;
   mr.edge.id2 = r.id2;
+  mr.inlier_points = r.inlier_points;  // environment measurement model (node.cpp:1551-1554), 0 when it is off
+  mr.outlier_points = r.outlier_points;
+  mr.occluded_points = r.occluded_points;
+  mr.all_points = r.all_points;
   if (r.id1 >= 0) {
     mr.final_trafo = mr.ransac_trafo;                                               // node.cpp:1334
     for (int i = 0; i < 16; i++) mr.edge.transform.m[i] = (double)r.ransac_trafo[i];  // node.cpp:1339

@@ -213,3 +213,31 @@ def refine_g2o(params: OParams, iterations, xyz_newer, kp_newer, xyz_older, kp_o
     lib().oracle_refine_g2o(C.byref(params), C.c_int(int(iterations)), _p(x1), _p(k1), _p(x2), _p(k2), _p(m), C.c_int(len(m)), _p(T),
                             C.byref(r), _p(inl), C.byref(n), C.byref(vi))
     return T.T.copy(), float(r.value), inl, int(n.value), int(vi.value)
+
+
+# ---- environment measurement model (emm_oracle.c) --------------------------------------------
+
+def create_cloud_z(depth, step=2, scaling=1.0, min_depth=0.1):
+    d = np.ascontiguousarray(depth, np.float32)
+    h, w = d.shape
+    out = np.zeros(((h + step - 1) // step, (w + step - 1) // step), np.float32)
+    lib().oracle_create_cloud_z(_p(d), C.c_int(w), C.c_int(h), C.c_int(step), C.c_float(scaling), C.c_float(min_depth), _p(out))
+    return out
+
+
+def pairwise_observation(params: OParams, T4x4, newer_z, newerK, older_z, olderK, cloud_step=2, skip_step=8):
+    """pairwiseObservationLikelihood (node.cpp:1520-1554): returns uint32[4] = inlier, outlier, occluded, all points."""
+    T = np.ascontiguousarray(np.asarray(T4x4, np.float32).T)
+    nz = np.ascontiguousarray(newer_z, np.float32); oz = np.ascontiguousarray(older_z, np.float32)
+    nk = np.ascontiguousarray(newerK, np.float32); ok = np.ascontiguousarray(olderK, np.float32)
+    out = np.zeros(4, np.uint32)
+    lib().oracle_pairwise_observation(C.byref(params), _p(T), _p(nz), C.c_int(nz.shape[1]), C.c_int(nz.shape[0]), _p(nk), _p(oz),
+                                      C.c_int(oz.shape[1]), C.c_int(oz.shape[0]), _p(ok), C.c_int(cloud_step), C.c_int(skip_step), _p(out))
+    return out
+
+
+def observation_criterion_met(inliers, outliers, occluded, obs_thresh):
+    q = C.c_double(0.0)
+    ok = lib().oracle_observation_criterion_met(C.c_uint32(int(inliers)), C.c_uint32(int(outliers)),
+                                                C.c_uint32(int(inliers + outliers + occluded)), C.c_double(obs_thresh), C.byref(q))
+    return bool(ok), q.value

@@ -42,7 +42,8 @@ class Params(C.Structure):
         ("detector_grid_resolution", C.c_int32), ("adjuster_max_iterations", C.c_int32),
         ("min_translation_meter", C.c_double), ("min_rotation_degree", C.c_double),
         ("max_translation_meter", C.c_double), ("max_rotation_degree", C.c_double),
-        ("nn_distance_ratio", C.c_double), ("use_root_sift", C.c_int32), ("g2o_transformation_refinement", C.c_int32), ("reserved_", C.c_int32 * 6),
+        ("nn_distance_ratio", C.c_double), ("use_root_sift", C.c_int32), ("g2o_transformation_refinement", C.c_int32), ("observability_threshold", C.c_double), ("emm_skip_step", C.c_int32),
+        ("cloud_creation_skip_step", C.c_int32), ("minimum_depth", C.c_float), ("reserved_", C.c_int32 * 1),
     ]
 
 
@@ -50,7 +51,8 @@ class PairResult(C.Structure):
     _fields_ = [
         ("id1", C.c_int32), ("id2", C.c_int32), ("n_all_matches", C.c_int32), ("n_inliers", C.c_int32),
         ("rmse", C.c_float), ("valid_iterations", C.c_int32), ("ransac_trafo", C.c_float * 16),
-        ("info_scale", C.c_double), ("used_identity", C.c_int32), ("reserved_", C.c_int32),
+        ("info_scale", C.c_double), ("used_identity", C.c_int32), ("inlier_points", C.c_uint32), ("outlier_points", C.c_uint32),
+        ("occluded_points", C.c_uint32), ("all_points", C.c_uint32), ("reserved_", C.c_int32),
     ]
 
 
@@ -60,9 +62,9 @@ KEYPOINT_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle"
 PAIR_RESULT_DTYPE = np.dtype([
     ("id1", "<i4"), ("id2", "<i4"), ("n_all_matches", "<i4"), ("n_inliers", "<i4"), ("rmse", "<f4"),
     ("valid_iterations", "<i4"), ("ransac_trafo", "<f4", (16,)), ("info_scale", "<f8"), ("used_identity", "<i4"),
-    ("reserved_", "<i4"),
+    ("inlier_points", "<u4"), ("outlier_points", "<u4"), ("occluded_points", "<u4"), ("all_points", "<u4"), ("reserved_", "<i4"),
 ])
-assert PAIR_RESULT_DTYPE.itemsize == C.sizeof(PairResult) == 104
+assert PAIR_RESULT_DTYPE.itemsize == C.sizeof(PairResult) == 120
 assert DMATCH_DTYPE.itemsize == C.sizeof(DMatch) == 16
 assert KEYPOINT_DTYPE.itemsize == C.sizeof(KeyPoint) == 28
 
@@ -120,6 +122,8 @@ def load_library(path: str | Path | None = None) -> C.CDLL:
     lib.rgbdslam_b200_set_hamming_path.argtypes = [C.c_int]
     lib.rgbdslam_b200_set_sift_matcher.argtypes = [C.c_int]
     lib.rgbdslam_b200_node_set_keypoints.argtypes = [u64, vp]
+    lib.rgbdslam_b200_node_set_depth.argtypes = [u64, vp, C.c_int, C.c_int, vp]
+    lib.rgbdslam_b200_observation_likelihood.argtypes = [u64, u64, vp, vp]
     lib.rgbdslam_b200_detector_create.argtypes = [C.POINTER(u64)]
     lib.rgbdslam_b200_detector_destroy.argtypes = [u64]
     lib.rgbdslam_b200_detector_thresholds.argtypes = [u64, vp, C.c_int]
@@ -270,6 +274,18 @@ class Frontend:
         if len(k) != self.node_num_features(h):
             raise ValueError("one keypoint per feature")
         self._check(self.lib.rgbdslam_b200_node_set_keypoints(C.c_uint64(int(h)), _ptr(k)))
+
+    def node_set_depth(self, h: int, depth_m: np.ndarray, K4):
+        d = np.ascontiguousarray(depth_m, np.float32)
+        k = np.ascontiguousarray(K4, np.float32)
+        self._check(self.lib.rgbdslam_b200_node_set_depth(C.c_uint64(int(h)), _ptr(d), d.shape[1], d.shape[0], _ptr(k)))
+
+    def observation_likelihood(self, newer: int, older: int, T4x4) -> np.ndarray:
+        """pairwiseObservationLikelihood for an explicit 4x4 transformation (newer -> older): inlier, outlier, occluded, all"""
+        T = np.ascontiguousarray(np.asarray(T4x4, np.float32).T)  # column-major Matrix4f
+        out = np.zeros(4, np.uint32)
+        self._check(self.lib.rgbdslam_b200_observation_likelihood(C.c_uint64(int(newer)), C.c_uint64(int(older)), _ptr(T), _ptr(out)))
+        return out
 
     def node_num_features(self, h: int) -> int:
         n = C.c_int()

@@ -409,6 +409,17 @@ static int run_pairs(const std::vector<PairDesc>& h_pairs, uint64_t seed, int64_
     if (e != cudaSuccess) return cuda_fail(e, "refine_g2o kernel");
     s.launches += 1;
   }
+  if (s.params.observability_threshold > 0.0) {  // node.cpp:1340-1342
+    for (const PairDesc& pd : h_pairs)
+      if (!pd.q_cloud || !pd.t_cloud) {
+        set_error("observability_threshold > 0 needs nodes with a depth cloud (nodes_create or node_set_depth)");
+        return RGBDSLAM_B200_ERR_STATE;
+      }
+    e = launch_emm_pairs(d_pairs, npairs, s.params.cloud_creation_skip_step, s.params.emm_skip_step, s.dp.cov_z_const,
+                         s.params.sigma_depth, s.params.observability_threshold, (rgbdslam_b200_pair_result*)s.W().d_results.ptr, st);
+    if (e != cudaSuccess) return cuda_fail(e, "emm kernel");
+    s.launches += 1;
+  }
   cudaEventRecord(s.W().ev[2], st);
 
   if (results) {
@@ -433,6 +444,26 @@ static int run_pairs(const std::vector<PairDesc>& h_pairs, uint64_t seed, int64_
     if (e != cudaSuccess) return cuda_fail(e, "match_pairs synchronize");
     s.W().pending = false;
   }
+  return 0;
+}
+
+int node_build_cloud(NodeDev* nd, const float* d_depth, int w, int h, const float K4[4], cudaStream_t st) {
+  State& s = g_state;
+  const int step = s.params.cloud_creation_skip_step > 0 ? s.params.cloud_creation_skip_step : 1;
+  const int cw = (w + step - 1) / step, ch = (h + step - 1) / step;  // ceil(cols / skip), misc.cpp:482-483
+  if (nd->cloud_z && (nd->cw != cw || nd->ch != ch)) {
+    cudaFree(nd->cloud_z);
+    nd->cloud_z = nullptr;
+  }
+  cudaError_t e = cudaSuccess;
+  if (!nd->cloud_z) e = cudaMalloc(&nd->cloud_z, sizeof(float) * (size_t)cw * ch);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(cloud)");
+  nd->cw = cw;
+  nd->ch = ch;
+  for (int k = 0; k < 4; k++) nd->K[k] = K4[k];
+  e = launch_build_cloud(d_depth, w, h, step, (float)s.params.depth_scaling_factor, s.params.minimum_depth, nd->cloud_z, cw, ch, st);
+  if (e != cudaSuccess) return cuda_fail(e, "build_cloud kernel");
+  s.launches += 1;
   return 0;
 }
 
@@ -461,6 +492,11 @@ void rgbdslam_b200_default_params(rgbdslam_b200_params* p) {
   p->max_rotation_degree = 360.0;
   p->nn_distance_ratio = 0.95;
   p->use_root_sift = 1;
+  p->g2o_transformation_refinement = 0;
+  p->observability_threshold = -0.6;
+  p->emm_skip_step = 8;
+  p->cloud_creation_skip_step = 2;
+  p->minimum_depth = 0.1f;
 }
 
 const char* rgbdslam_b200_last_error(void) { return t_last_error.c_str(); }
@@ -574,6 +610,53 @@ int rgbdslam_b200_node_set_keypoints(uint64_t node_handle, const rgbdslam_b200_k
     e = cudaMemcpyAsync(nd->kp, keypoints, sizeof(rgbdslam_b200_keypoint) * (size_t)nd->n, cudaMemcpyHostToDevice, g_state.stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(g_state.stream);
   if (e != cudaSuccess) return cuda_fail(e, "node_set_keypoints");
+  return 0;
+}
+
+int rgbdslam_b200_node_set_depth(uint64_t node_handle, const float* depth_m, int w, int h, const float K4[4]) {
+  std::lock_guard<std::mutex> lk(g_state.mu);
+  int rc = check_inited();
+  if (rc) return rc;
+  NodeDev* nd = reinterpret_cast<NodeDev*>((uintptr_t)node_handle);
+  if (!nd || nd->magic != NodeDev::kMagic || !depth_m || !K4 || w <= 0 || h <= 0) {
+    set_error("node_set_depth: bad arguments");
+    return RGBDSLAM_B200_ERR_ARG;
+  }
+  State& s = g_state;
+  if ((rc = s.d_f32_a.ensure(sizeof(float) * (size_t)w * h))) return rc;
+  cudaError_t e = cudaMemcpyAsync(s.d_f32_a.ptr, depth_m, sizeof(float) * (size_t)w * h, cudaMemcpyHostToDevice, s.stream);
+  if (e != cudaSuccess) return cuda_fail(e, "node_set_depth upload");
+  if ((rc = node_build_cloud(nd, (const float*)s.d_f32_a.ptr, w, h, K4, s.stream))) return rc;
+  e = cudaStreamSynchronize(s.stream);
+  if (e != cudaSuccess) return cuda_fail(e, "node_set_depth");
+  return 0;
+}
+
+int rgbdslam_b200_observation_likelihood(uint64_t newer, uint64_t older, const float T[16], uint32_t counts[4]) {
+  std::lock_guard<std::mutex> lk(g_state.mu);
+  int rc = check_inited();
+  if (rc) return rc;
+  NodeDev* a = reinterpret_cast<NodeDev*>((uintptr_t)newer);
+  NodeDev* b = reinterpret_cast<NodeDev*>((uintptr_t)older);
+  if (!a || !b || a->magic != NodeDev::kMagic || b->magic != NodeDev::kMagic || !T || !counts) {
+    set_error("observation_likelihood: bad arguments");
+    return RGBDSLAM_B200_ERR_ARG;
+  }
+  if (!a->cloud_z || !b->cloud_z) {
+    set_error("observation_likelihood: both nodes need a depth cloud (nodes_create with observability_threshold > 0 or node_set_depth)");
+    return RGBDSLAM_B200_ERR_STATE;
+  }
+  State& s = g_state;
+  if ((rc = s.d_f32_b.ensure(128))) return rc;
+  cudaError_t e = cudaMemcpyAsync(s.d_f32_b.ptr, T, 64, cudaMemcpyHostToDevice, s.stream);
+  if (e == cudaSuccess)
+    e = launch_emm_single(a->cloud_z, a->cw, a->ch, a->K, b->cloud_z, b->cw, b->ch, b->K, (const float*)s.d_f32_b.ptr,
+                          s.params.cloud_creation_skip_step, s.params.emm_skip_step, s.dp.cov_z_const, s.params.sigma_depth,
+                          (unsigned*)((char*)s.d_f32_b.ptr + 64), s.stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(counts, (char*)s.d_f32_b.ptr + 64, 16, cudaMemcpyDeviceToHost, s.stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
+  if (e != cudaSuccess) return cuda_fail(e, "observation_likelihood");
+  s.launches += 1;
   return 0;
 }
 
@@ -726,6 +809,8 @@ int rgbdslam_b200_brute_force_orb(const uint64_t* q, int nq, const uint64_t* t, 
   pd.q_f32 = pd.t_f32 = pd.t_norm = nullptr;
   pd.sift_kind = pd.pad_ = 0;
   pd.q_kp = pd.t_kp = nullptr;
+  pd.q_cloud = pd.t_cloud = nullptr;
+  pd.q_cw = pd.q_ch = pd.t_cw = pd.t_ch = 0;
   if (s.hamming_path != 0) {
     if ((rc = s.W().d_i8_a.ensure(256 * (size_t)pad256(nq)))) return rc;
     if ((rc = s.W().d_i8_b.ensure(256 * (size_t)pad256(nt)))) return rc;
@@ -852,6 +937,7 @@ int rgbdslam_b200_node_destroy(uint64_t node_handle) {
   if (nd->xyz) cudaFree(nd->xyz);
   if (nd->desc_i8) cudaFree(nd->desc_i8);
   if (nd->kp) cudaFree(nd->kp);
+  if (nd->cloud_z) cudaFree(nd->cloud_z);
   if (nd->desc_f32) cudaFree(nd->desc_f32);
   if (nd->norms) cudaFree(nd->norms);
   delete nd;
@@ -892,6 +978,13 @@ static int match_pairs_impl(int slot, bool sync, const uint64_t* newer, const ui
     pairs[i].pad_ = 0;
     pairs[i].q_kp = a->kp;
     pairs[i].t_kp = b->kp;
+    pairs[i].q_cloud = a->cloud_z;
+    pairs[i].t_cloud = b->cloud_z;
+    pairs[i].q_cw = a->cw; pairs[i].q_ch = a->ch; pairs[i].t_cw = b->cw; pairs[i].t_ch = b->ch;
+    for (int k = 0; k < 4; k++) {
+      pairs[i].q_K[k] = a->K[k];
+      pairs[i].t_K[k] = b->K[k];
+    }
     if ((a->desc_f32 != nullptr) != (b->desc_f32 != nullptr) || a->sift_kind != b->sift_kind) {
       set_error("match_pairs: nodes of different descriptor / matcher kinds paired");
       return RGBDSLAM_B200_ERR_ARG;
@@ -981,6 +1074,8 @@ static int match_pairs_host_impl(int slot, bool sync, const uint8_t* desc_newer,
     pairs[i].q_f32 = pairs[i].t_f32 = pairs[i].t_norm = nullptr;
     pairs[i].sift_kind = pairs[i].pad_ = 0;
     pairs[i].q_kp = pairs[i].t_kp = nullptr;
+    pairs[i].q_cloud = pairs[i].t_cloud = nullptr;
+    pairs[i].q_cw = pairs[i].q_ch = pairs[i].t_cw = pairs[i].t_ch = 0;
     if (tc) {
       pairs[i].q_i8 = (const int8_t*)s.W().d_i8_a.ptr + 256 * pn;
       pairs[i].t_i8 = (const int8_t*)s.W().d_i8_b.ptr + 256 * po;

@@ -485,6 +485,9 @@ int rgbdslam_b200_nodes_create(uint64_t detector, int nframes, const uint8_t* gr
         cudaMemcpyAsync(nd->kp, (const rgbdslam_b200_keypoint*)o.kp.ptr + (size_t)f * o.kp_stride,
                         sizeof(rgbdslam_b200_keypoint) * (size_t)n[f], cudaMemcpyDeviceToDevice, st);
       }
+      if (s.params.observability_threshold > 0.0 &&
+          (rc = node_build_cloud(nd, (const float*)o.depth.ptr + (size_t)f * px, w, h, K4, st)))  // Node::pc_col for the EMM
+        return rc;
       jobs.push_back({nd->desc, nd->desc_i8, nd->n, nd->n_pad});
       node_handles[f0 + f] = (uint64_t)(uintptr_t)nd;
       if (n_features) n_features[f0 + f] = n[f];

@@ -26,6 +26,10 @@ struct PairDesc {
   const float* t_norm;
   const rgbdslam_b200_keypoint* q_kp;  // 2-D keypoints (nullptr unless the node has them): pairwise g2o refinement only
   const rgbdslam_b200_keypoint* t_kp;
+  const float* q_cloud;  // depth-cloud z-planes (environment measurement model), nullptr if the node has none
+  const float* t_cloud;
+  int32_t q_cw, q_ch, t_cw, t_ch;
+  float q_K[4], t_K[4];  // fx, fy, cx, cy of the full-resolution cameras
   int32_t sift_kind;   // float-descriptor nodes: 0 = RootSIFT / exact 2-NN ratio matcher, 1 = SiftGPU matcher (u8 tiles, raw rows)
   int32_t pad_;
 };

@@ -885,6 +885,7 @@ __global__ void __launch_bounds__(32)
   for (int i = 0; i < 16; i++) res.ransac_trafo[i] = (i % 5 == 0) ? 1.f : 0.f;
   res.info_scale = 0.0;
   res.used_identity = 0;
+  res.inlier_points = res.outlier_points = res.occluded_points = res.all_points = 0;
   res.reserved_ = 0;
 
   // matchNodePair: all_matches.size() < min_matches -> no RANSAC (node.cpp:1319);

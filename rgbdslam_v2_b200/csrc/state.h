@@ -36,6 +36,9 @@ struct NodeDev {
   float* norms = nullptr;     // SIFT nodes: n_pad |b|^2 of the bf16-rounded rows
   int8_t* desc_i8 = nullptr;  // n_pad x 256 B  +-1 expansion for the tensor-core Hamming path (lazily built)
   int32_t n_pad = 0;
+  float* cloud_z = nullptr;   // depth cloud z-plane (cw x ch) for the environment measurement model
+  int32_t cw = 0, ch = 0;
+  float K[4] = {0, 0, 0, 0};  // fx, fy, cx, cy of the full-resolution camera
   int32_t sift_kind = 0;      // SIFT nodes: 0 = RootSIFT rows + bf16 tiles, 1 = raw rows + u8 tiles (SiftGPU matcher)
 };
 
@@ -89,6 +92,7 @@ extern State g_state;
 void set_error(const std::string& s);
 int cuda_fail(cudaError_t e, const char* what);
 int check_inited();
+int node_build_cloud(NodeDev* nd, const float* d_depth, int w, int h, const float K4[4], cudaStream_t st);
 int expand_nodes_public(const std::vector<ExpandJob>& jobs);  // +-1 int8 expansion (api.cu)
 
 }  // namespace rb200
