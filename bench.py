@@ -317,10 +317,16 @@ def run_ours(args, rank, local_rank, world):
         dist.broadcast(uid, 0)
         comm = fe.comm_init(rank, world, uid.cpu().numpy())
         all_edges = np.zeros(world * PAIRS_PER_GPU, PAIR_RESULT_DTYPE)
+        gathered = []
+        for j in range(DEPTH):  # one pinned destination per slot for the in-flight all-gather
+            t = torch.zeros(world * PAIRS_PER_GPU * PAIR_RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+            gathered.append((t, t.numpy().view(PAIR_RESULT_DTYPE)))
 
     def submit_resident(k):
         st = sets[k % DEPTH]
         fe.submit_node_pairs(1 + k % DEPTH, st["newer"], st["older"], (st["res"], None, None), seed=SEED, first_pair_index=st["first"])
+        if comm is not None:  # the exchange step rides behind the slot's kernels (no host round trip)
+            fe.allgather_slot_edges(comm, 1 + k % DEPTH, PAIRS_PER_GPU, gathered[k % DEPTH][1])
 
     def submit_e2e(k):
         st = sets[k % DEPTH]
@@ -328,12 +334,14 @@ def run_ours(args, rank, local_rank, world):
         fe.submit_pairs_host(1 + k % DEPTH, pp["desc_newer"], pp["xyz_newer"], bb["n_newer"], pp["desc_older"], pp["xyz_older"],
                              bb["n_older"], bb["id_newer"], bb["id_older"], (st["res"], st["allm"], st["inl"]), seed=SEED,
                              first_pair_index=st["first"])
+        if comm is not None:
+            fe.allgather_slot_edges(comm, 1 + k % DEPTH, PAIRS_PER_GPU, gathered[k % DEPTH][1])
 
     def finish(k):
-        """results of step k are on the host; exchange them (N > 1)"""
+        """results of step k (and, for N > 1, every rank's edge records) are on the host"""
         fe.wait_slot(1 + k % DEPTH)
         if comm is not None:
-            fe.allgather_edges(comm, sets[k % DEPTH]["res"], world, out=all_edges)
+            all_edges[:] = gathered[k % DEPTH][1]
 
     def run_steps(submit, K):
         for k in range(K):
@@ -426,7 +434,7 @@ def run_ours(args, rank, local_rank, world):
                              "the synchronous reference point flushes L2 (256 MiB memset) before every step",
                        "pipeline": f"{DEPTH} batches in flight on {DEPTH} library streams (rgbdslam_b200_match_pairs_submit / _wait)",
                        "pairs_per_gpu": PAIRS_PER_GPU,
-                       "exchange": "none (1 GPU)" if world == 1 else f"ncclAllGather of {world}x{PAIRS_PER_GPU} edge records (120 B) per step, inside the timed region",
+                       "exchange": "none (1 GPU)" if world == 1 else f"ncclAllGather of {world}x{PAIRS_PER_GPU} edge records (120 B) per step, queued behind each batch on the communicator stream (rgbdslam_b200_allgather_slot_edges), inside the timed region",
                        "edges_gathered": None if all_edges is None else int((all_edges["id1"] >= 0).sum()),
                        "valid_edges_rank0": n_valid, "wall_ms_per_step_incl_flush": 1e3 * wall_resident / args.steps},
             "roofline": {"bound": "hbm", "kernel": "hamming_match", "achieved": achieved, "peak": peak, "unit": "GB/s",

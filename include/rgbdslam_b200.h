@@ -300,6 +300,11 @@ int rgbdslam_b200_comm_destroy(uint64_t comm_handle);
 /* local: n_per_rank records of this rank (host); all: world * n_per_rank records, rank-major (host). */
 int rgbdslam_b200_allgather_edges(uint64_t comm_handle, const rgbdslam_b200_pair_result* local, int n_per_rank,
                                   rgbdslam_b200_pair_result* all);
+/* The same exchange for a batch still in flight on a pipeline slot: queued behind the slot's kernels on the communicator's
+ * own stream, straight from the device-side edge records (no host round trip); rgbdslam_b200_match_pairs_wait(slot) also
+ * waits for it.  Call right after match_pairs*_submit(slot, ...); all ranks must use the same slot order.  `all` (host)
+ * receives world * n_per_rank records ordered by rank. */
+int rgbdslam_b200_allgather_slot_edges(uint64_t comm, int slot, int n_per_rank, rgbdslam_b200_pair_result* all);
 
 /* ---- pose-graph solve --------------------------------------------------------
  * == GraphManager::optimizeGraph(double iter, bool nonthreaded) -> optimizeGraphImpl

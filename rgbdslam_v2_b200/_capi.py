@@ -139,6 +139,7 @@ def load_library(path: str | Path | None = None) -> C.CDLL:
     lib.rgbdslam_b200_comm_init.argtypes = [C.c_int, C.c_int, vp, C.POINTER(u64)]
     lib.rgbdslam_b200_comm_destroy.argtypes = [u64]
     lib.rgbdslam_b200_allgather_edges.argtypes = [u64, vp, C.c_int, vp]
+    lib.rgbdslam_b200_allgather_slot_edges.argtypes = [u64, C.c_int, C.c_int, vp]
     lib.rgbdslam_b200_posegraph_optimize.argtypes = [C.c_int, vp, vp, C.c_int, vp, vp, vp, C.c_double, C.c_double,
                                                      C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.rgbdslam_b200_posegraph_chi2.argtypes = [C.c_int, vp, C.c_int, vp, vp, vp, C.c_double, C.POINTER(C.c_double), vp]
@@ -445,6 +446,10 @@ class Frontend:
         return out
 
     # -- GraphManager::optimizeGraph ----------------------------------------------
+    def allgather_slot_edges(self, comm: int, slot: int, n_per_rank: int, out: np.ndarray):
+        """all-gather of the slot's in-flight edge records into `out` (host, world * n_per_rank records); wait_slot() completes it"""
+        self._check(self.lib.rgbdslam_b200_allgather_slot_edges(C.c_uint64(comm), slot, n_per_rank, _ptr(out)))
+
     def optimize_graph(self, poses, fixed, ij, meas, info, stop: float = 0.01, huber_delta: float = 1.0):
         """== GraphManager::optimizeGraph (graph_manager.cpp:900).  Returns (poses, chi2, lm_iters, cg_iters)."""
         x = np.array(poses, np.float64, order="C")

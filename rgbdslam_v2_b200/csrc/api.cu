@@ -106,8 +106,10 @@ static int use_slot(int slot) {
   if (slot == 0) s.ws[0].stream = s.stream;
   if (s.cur->pending) {
     cudaError_t e = cudaStreamSynchronize(s.cur->stream);
+    if (e == cudaSuccess && s.cur->gather_pending) e = cudaEventSynchronize(s.cur->ev_gather);
     if (e != cudaSuccess) return cuda_fail(e, "drain slot");
     s.cur->pending = false;
+    s.cur->gather_pending = false;
   }
   return 0;
 }
@@ -538,6 +540,8 @@ int rgbdslam_b200_init(int device, const rgbdslam_b200_params* p) {
         e = cudaEventCreate(&s.ws[k].ev[i]);
         if (e != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
       }
+      e = cudaEventCreateWithFlags(&s.ws[k].ev_gather, cudaEventDisableTiming);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
       if (k > 0) {
         e = cudaStreamCreateWithFlags(&s.ws[k].stream, cudaStreamNonBlocking);
         if (e != cudaSuccess) return cuda_fail(e, "cudaStreamCreate(slot)");
@@ -569,6 +573,7 @@ int rgbdslam_b200_shutdown(void) {
   s.release_workspaces();
   for (int k = 0; k < kSlots; k++) {
     for (int i = 0; i < 8; i++) cudaEventDestroy(s.ws[k].ev[i]);
+    cudaEventDestroy(s.ws[k].ev_gather);
     if (k > 0) cudaStreamDestroy(s.ws[k].stream);
   }
   cudaStreamDestroy(s.own_stream);
@@ -1015,8 +1020,10 @@ int rgbdslam_b200_match_pairs_wait(int slot) {
   }
   Workspace& w = g_state.ws[slot];
   cudaError_t e = cudaStreamSynchronize(slot == 0 ? g_state.stream : w.stream);
+  if (e == cudaSuccess && w.gather_pending) e = cudaEventSynchronize(w.ev_gather);
   if (e != cudaSuccess) return cuda_fail(e, "match_pairs_wait");
   w.pending = false;
+  w.gather_pending = false;
   return 0;
 }
 

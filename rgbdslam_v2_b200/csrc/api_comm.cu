@@ -60,6 +60,8 @@ struct Comm {
   ncclComm_t comm = nullptr;
   int rank = 0, world = 1;
   DevBuf send, recv;
+  cudaStream_t gstream = nullptr;        // the collectives of in-flight slots, in submission order
+  DevBuf slot_recv[kSlots];
 };
 
 }  // namespace rb200
@@ -110,6 +112,8 @@ int rgbdslam_b200_comm_destroy(uint64_t comm_handle) {
   if (g_nccl.ok && c->comm) g_nccl.CommDestroy(c->comm);
   c->send.release();
   c->recv.release();
+  for (int k = 0; k < kSlots; k++) c->slot_recv[k].release();
+  if (c->gstream) cudaStreamDestroy(c->gstream);
   c->magic = 0;
   delete c;
   return 0;
@@ -136,6 +140,46 @@ int rgbdslam_b200_allgather_edges(uint64_t comm_handle, const rgbdslam_b200_pair
   e = cudaMemcpyAsync(all, c->recv.ptr, bytes * c->world, cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) return cuda_fail(e, "allgather_edges download");
+  return 0;
+}
+
+// The exchange step of a batch in flight: the edge records of slot `slot` (still on the device) are all-gathered on the
+// communicator's own stream as soon as the slot's kernels have finished, and land in `all` (host, world * n_per_rank records);
+// rgbdslam_b200_match_pairs_wait(slot) also waits for this.  No host round trip, the next batch can be submitted meanwhile.
+// Every rank must issue these calls in the same slot order.
+int rgbdslam_b200_allgather_slot_edges(uint64_t comm_handle, int slot, int n_per_rank, rgbdslam_b200_pair_result* all) {
+  std::lock_guard<std::mutex> lk(g_state.mu);
+  int rc = check_inited();
+  if (rc) return rc;
+  Comm* c = (Comm*)(uintptr_t)comm_handle;
+  if (!c || c->magic != Comm::kMagic || slot < 0 || slot >= kSlots || n_per_rank < 0 || (n_per_rank > 0 && !all)) {
+    set_error("allgather_slot_edges: bad arguments");
+    return RGBDSLAM_B200_ERR_ARG;
+  }
+  Workspace& w = g_state.ws[slot];
+  if (!w.pending || n_per_rank == 0) {
+    set_error("allgather_slot_edges: the slot has no batch in flight (call it right after match_pairs*_submit)");
+    return RGBDSLAM_B200_ERR_STATE;
+  }
+  const size_t bytes = sizeof(rgbdslam_b200_pair_result) * (size_t)n_per_rank;
+  if (w.d_results.cap < bytes) {
+    set_error("allgather_slot_edges: n_per_rank exceeds the batch submitted on this slot");
+    return RGBDSLAM_B200_ERR_ARG;
+  }
+  cudaError_t e = cudaSuccess;
+  if (!c->gstream) e = cudaStreamCreateWithFlags(&c->gstream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaStreamCreate(gather)");
+  if ((rc = c->slot_recv[slot].ensure(bytes * c->world))) return rc;
+  cudaStream_t st = slot == 0 ? g_state.stream : w.stream;
+  e = cudaEventRecord(w.ev[7], st);  // everything the slot has queued so far
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(c->gstream, w.ev[7], 0);
+  if (e != cudaSuccess) return cuda_fail(e, "allgather_slot_edges dependency");
+  ncclResult_t r = g_nccl.AllGather(w.d_results.ptr, c->slot_recv[slot].ptr, bytes, 0 /* ncclInt8 */, c->comm, c->gstream);
+  if (r != 0) return nccl_fail(r, "ncclAllGather");
+  e = cudaMemcpyAsync(all, c->slot_recv[slot].ptr, bytes * c->world, cudaMemcpyDeviceToHost, c->gstream);
+  if (e == cudaSuccess) e = cudaEventRecord(w.ev_gather, c->gstream);
+  if (e != cudaSuccess) return cuda_fail(e, "allgather_slot_edges download");
+  w.gather_pending = true;
   return 0;
 }
 

@@ -50,6 +50,8 @@ struct Workspace {
   bool timing_valid = false;
   bool host_path = false;  // last call uploaded host features (ev[4], ev[5] valid)
   bool pending = false;
+  cudaEvent_t ev_gather = nullptr;  // rgbdslam_b200_allgather_slot_edges: the slot's collective + download have finished
+  bool gather_pending = false;
   DevBuf d_pairs, d_best, d_matches, d_inliers, d_mfrom, d_mto, d_nall, d_hyp, d_results;
   DevBuf d_feat_a, d_feat_b, d_xyz_a, d_xyz_b;
   DevBuf d_i8_a, d_i8_b, d_jobs, d_items, d_top4, d_knn, d_cen, d_nextn;
