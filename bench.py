@@ -143,6 +143,13 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE tc_match256_kernel<0> launch on this workload, from the committed
+# `ncu --set full` capture: 134.29 MB + 4.98 MB.  7.6 x the algorithmic 18.4 MB because the kernel reads the +-1 int8 operand
+# expansion (256 B per 256-bit descriptor) the nodes keep resident; the descriptors themselves are read once, by expand_i8.
+NCU_DRAM_BYTES_PER_LAUNCH = 139277312
+NCU_TRAFFIC_SOURCE = "profiles/r1_v8_tc_match256_ncu_full.txt (ncu --set full, 1 launch, C2 batch)"
+
+
 def tensor_roofline(kernel_ms: float) -> dict:
     """The match kernel against the tensor roofline: exact +-1 int8 GEMM, 2 * Nq * Nt * 256 integer ops per pair.  Peak:
     dense int8 = 2 x the dense bf16 rate on B200 (4.5 vs 2.25 POP/s nominal), scaled from the MEASURED bf16 number."""
@@ -438,7 +445,7 @@ def run_ours(args, rank, local_rank, world):
                        "edges_gathered": None if all_edges is None else int((all_edges["id1"] >= 0).sum()),
                        "valid_edges_rank0": n_valid, "wall_ms_per_step_incl_flush": 1e3 * wall_resident / args.steps},
             "roofline": {"bound": "hbm", "kernel": "hamming_match", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "traffic_source": NCU_TRAFFIC_SOURCE, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PAIR * PAIRS_PER_GPU, "kernel_ms": ham,
                          "kernel_share_of_step": ham / statistics.mean(sync_dev),
                          "kernel_ms_when_pipelined": statistics.mean(ham_ms),
