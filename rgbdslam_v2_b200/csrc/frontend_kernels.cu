@@ -157,6 +157,7 @@ cudaError_t launch_select_matches(const PairDesc* pairs, int npairs, const int2*
 // RANSAC building blocks (warp-cooperative; every lane ends up with identical, warp-uniform results).
 
 constexpr unsigned kFull = 0xffffffffu;
+constexpr unsigned kFullMask = 0xffffffffu;
 #ifndef RB200_SCORE_GROUP
 #define RB200_SCORE_GROUP 5  // correspondences (mask words) scored per lane without an intervening branch
 #endif
@@ -165,6 +166,24 @@ __device__ __forceinline__ float wsum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
   return v;
+}
+// All-lanes sums of 16 values per lane.  Step with offset o: a lane keeps the half of its values selected by bit o of its id,
+// hands the other half to lane ^ o and adds what it receives; after offsets 16, 8, 4, 2 one value per lane is left (index =
+// lane bits 4..1), offset 1 completes it, 16 indexed shuffles hand every total to every lane.  Deterministic, warp-uniform.
+__device__ __forceinline__ void wsum16(float (&v)[16], int lane) {
+  float r8[8], r4[4], r2[2], r1;
+  const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4, b2 = lane & 2;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r8[i] = (b16 ? v[i + 8] : v[i]) + __shfl_xor_sync(kFullMask, b16 ? v[i] : v[i + 8], 16);
+#pragma unroll
+  for (int i = 0; i < 4; i++) r4[i] = (b8 ? r8[i + 4] : r8[i]) + __shfl_xor_sync(kFullMask, b8 ? r8[i] : r8[i + 4], 8);
+#pragma unroll
+  for (int i = 0; i < 2; i++) r2[i] = (b4 ? r4[i + 2] : r4[i]) + __shfl_xor_sync(kFullMask, b4 ? r4[i] : r4[i + 2], 4);
+  r1 = (b2 ? r2[1] : r2[0]) + __shfl_xor_sync(kFullMask, b2 ? r2[0] : r2[1], 2);
+  r1 += __shfl_xor_sync(kFullMask, r1, 1);
+  // value j lives in the lanes with (bit4, bit3, bit2, bit1) = (j>>3 &1, j>>2 &1, j>>1 &1, j &1)
+#pragma unroll
+  for (int j = 0; j < 16; j++) v[j] = __shfl_sync(kFullMask, r1, ((j & 8) ? 16 : 0) | ((j & 4) ? 8 : 0) | ((j & 2) ? 4 : 0) | ((j & 1) ? 2 : 0));
 }
 __device__ __forceinline__ double wsumd(double v) {
 #pragma unroll
@@ -221,11 +240,13 @@ __device__ bool fit_transform(const float4* __restrict__ cfrom, const float4* __
       }
     }
   }
-  W = wsum(W);
-  f0 = wsum(f0); f1 = wsum(f1); f2 = wsum(f2);
-  t0 = wsum(t0); t1 = wsum(t1); t2 = wsum(t2);
+  {  // 16 warp sums in 32 shuffles instead of 80: halve the value set at every butterfly step, then broadcast
+    float v[16] = {W, f0, f1, f2, t0, t1, t2, c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7], c[8]};
+    wsum16(v, lane);
+    W = v[0]; f0 = v[1]; f1 = v[2]; f2 = v[3]; t0 = v[4]; t1 = v[5]; t2 = v[6];
 #pragma unroll
-  for (int i = 0; i < 9; i++) c[i] = wsum(c[i]);
+    for (int i = 0; i < 9; i++) c[i] = v[7 + i];
+  }
   if (!(W > 0.f)) return false;
   const float iW = __fdiv_rn(1.0f, W);
   const float m1x = f0 * iW, m1y = f1 * iW, m1z = f2 * iW;  // weighted means of the centred points
@@ -270,7 +291,7 @@ __device__ bool fit_transform(const float4* __restrict__ cfrom, const float4* __
     const float beta = AQ0 * AQ0 + AQ1 * AQ1 + AQ2 * AQ2;                                            \
     const float gamma = AP0 * AQ0 + AP1 * AQ1 + AP2 * AQ2;                                           \
     if (RB200_JTEST(alpha, beta, gamma)) {                                                           \
-      rotated = true;                                                                                \
+      if (gamma * gamma > 1e-7f * (alpha * beta)) rotated = true; /* else: converged after this one */ \
       float cs, sn;                                                                                  \
       RB200_JANGLE(alpha, beta, gamma, cs, sn)                                                       \
       float x, y;                                                                                    \
@@ -282,6 +303,8 @@ __device__ bool fit_transform(const float4* __restrict__ cfrom, const float4* __
       x = VP2; y = VQ2; VP2 = cs * x - sn * y; VQ2 = sn * x + cs * y;                                \
     }                                                                                                \
   }
+  // `rotated` = some column pair was still more than 3e-4 from orthogonal before its rotation.  One-sided Jacobi converges
+  // quadratically, so a sweep whose rotations were all below that leaves residuals ~1e-7 (float epsilon): no check sweep.
   for (int sweep = 0; sweep < 6; sweep++) {
     bool rotated = false;
     RB200_JROT(a00, a10, a20, a01, a11, a21, v00, v10, v20, v01, v11, v21)  // columns 0,1
@@ -379,6 +402,7 @@ struct ScreenCtx {
   float Pf[6], O2f[6];
   float rcx, rcy, sq_max, sigma_depth;
   float czc;  // constant depth covariance (misc2.h static cache), < 0: per-point (sigma_depth * z^2)^2 model
+  float Cc[6], lim_c;  // czc >= 0: czc * O2f (+ czc on the zz entry) and the constant shortcut limit
 };
 
 __device__ __forceinline__ void make_screen_ctx(const Rt& T, ScreenCtx& c) {
@@ -392,7 +416,9 @@ __device__ __forceinline__ void make_screen_ctx(const Rt& T, ScreenCtx& c) {
   for (int k = 0; k < 6; k++) {
     c.Pf[k] = fmaf(c.rcx * T.R[I[k]], T.R[J[k]], (c.rcy * T.R[3 + I[k]]) * T.R[3 + J[k]]);
     c.O2f[k] = T.R[6 + I[k]] * T.R[6 + J[k]];
+    c.Cc[k] = c.czc * c.O2f[k] + (k == 5 ? c.czc : 0.f);
   }
+  c.lim_c = 2.f * (fmaxf(c.rcx, c.czc) + fmaxf(c.rcx, c.czc));
 }
 
 // float32 screening of errorFunction2, branch-free so that the unrolled scoring loop interleaves several
@@ -402,22 +428,34 @@ __device__ __forceinline__ void make_screen_ctx(const Rt& T, ScreenCtx& c) {
 //                                                                   evaluates the float64 reference formula
 // Margins: 1e-3 relative on both tests, orders of magnitude above the float32 evaluation error (~1e-5 relative for
 // the 3x3 SPD solve with condition number < 1e2).
+template <bool kConstCov>
 __device__ __forceinline__ float mahal_screen(const float4 x1, const float4 x2, const Rt& T, const ScreenCtx& c) {
   const float d0 = fmaf(T.R[0], x1.x, fmaf(T.R[1], x1.y, fmaf(T.R[2], x1.z, T.t[0] * x1.w))) - x2.x;
   const float d1 = fmaf(T.R[3], x1.x, fmaf(T.R[4], x1.y, fmaf(T.R[5], x1.z, T.t[1] * x1.w))) - x2.y;
   const float d2 = fmaf(T.R[6], x1.x, fmaf(T.R[7], x1.y, fmaf(T.R[8], x1.z, T.t[2] * x1.w))) - x2.z;
   const float rcx = c.rcx, rcy = c.rcy;
-  const float sd1 = c.sigma_depth * (x1.z * x1.z), sd2 = c.sigma_depth * (x2.z * x2.z);
-  const float cz1 = c.czc < 0.f ? sd1 * sd1 : c.czc, cz2 = c.czc < 0.f ? sd2 * sd2 : c.czc;
   const float dsq = fmaf(d0, d0, fmaf(d1, d1, d2 * d2));
-  const float lim = 2.f * (fmaxf(rcx, cz1) + fmaxf(rcx, cz2));
   const float a2 = x1.z, b2 = x2.z;
-  const float S00 = fmaf(a2, c.Pf[0], fmaf(cz1, c.O2f[0], rcx * b2));
-  const float S01 = fmaf(a2, c.Pf[1], cz1 * c.O2f[1]);
-  const float S02 = fmaf(a2, c.Pf[2], cz1 * c.O2f[2]);
-  const float S11 = fmaf(a2, c.Pf[3], fmaf(cz1, c.O2f[3], rcy * b2));
-  const float S12 = fmaf(a2, c.Pf[4], cz1 * c.O2f[4]);
-  const float S22 = fmaf(a2, c.Pf[5], fmaf(cz1, c.O2f[5], cz2));
+  float lim, S00, S01, S02, S11, S12, S22;
+  if (kConstCov) {  // the default configuration: depth covariance latched to a constant (misc2.h:30-35)
+    lim = c.lim_c;
+    S00 = fmaf(a2, c.Pf[0], fmaf(rcx, b2, c.Cc[0]));
+    S01 = fmaf(a2, c.Pf[1], c.Cc[1]);
+    S02 = fmaf(a2, c.Pf[2], c.Cc[2]);
+    S11 = fmaf(a2, c.Pf[3], fmaf(rcy, b2, c.Cc[3]));
+    S12 = fmaf(a2, c.Pf[4], c.Cc[4]);
+    S22 = fmaf(a2, c.Pf[5], c.Cc[5]);
+  } else {
+    const float sd1 = c.sigma_depth * (x1.z * x1.z), sd2 = c.sigma_depth * (x2.z * x2.z);
+    const float cz1 = sd1 * sd1, cz2 = sd2 * sd2;
+    lim = 2.f * (fmaxf(rcx, cz1) + fmaxf(rcx, cz2));
+    S00 = fmaf(a2, c.Pf[0], fmaf(cz1, c.O2f[0], rcx * b2));
+    S01 = fmaf(a2, c.Pf[1], cz1 * c.O2f[1]);
+    S02 = fmaf(a2, c.Pf[2], cz1 * c.O2f[2]);
+    S11 = fmaf(a2, c.Pf[3], fmaf(cz1, c.O2f[3], rcy * b2));
+    S12 = fmaf(a2, c.Pf[4], cz1 * c.O2f[4]);
+    S22 = fmaf(a2, c.Pf[5], fmaf(cz1, c.O2f[5], cz2));
+  }
   // scale to O(1) to stay far from float under/overflow in the cubic determinant (entries are 1e-5 .. 1e-2)
   const float k = 1024.f;
   const float s00 = S00 * k, s01 = S01 * k, s02 = S02 * k, s11 = S11 * k, s12 = S12 * k, s22 = S22 * k;
@@ -505,12 +543,22 @@ __device__ int score_all(const float4* __restrict__ sfrom, const float4* __restr
     float code[kGroup];
     uint32_t wout[kGroup];
     if (g * kGroup < nw) {
+      if (sc.czc >= 0.f) {  // warp-uniform; decided once per group so the kGroup chains stay branch-free
 #pragma unroll
-      for (int j = 0; j < kGroup; j++) {
-        const int i = (g * kGroup + j) * 32 + lane;  // < kMaxMatchesCap: rows >= M hold stale but addressable memory
-        const float4 a = sfrom[i], b = sto[i];
-        const float cm = mahal_screen(a, b, T, sc);
-        code[j] = (i < M && !(a.z == 0.0f || b.z == 0.0f)) ? cm : -1.f;  // node.cpp:994 (does not trigger on NaN)
+        for (int j = 0; j < kGroup; j++) {
+          const int i = (g * kGroup + j) * 32 + lane;  // < kMaxMatchesCap: rows >= M hold stale but addressable memory
+          const float4 a = sfrom[i], b = sto[i];
+          const float cm = mahal_screen<true>(a, b, T, sc);
+          code[j] = (i < M && !(a.z == 0.0f || b.z == 0.0f)) ? cm : -1.f;  // node.cpp:994 (does not trigger on NaN)
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < kGroup; j++) {
+          const int i = (g * kGroup + j) * 32 + lane;
+          const float4 a = sfrom[i], b = sto[i];
+          const float cm = mahal_screen<false>(a, b, T, sc);
+          code[j] = (i < M && !(a.z == 0.0f || b.z == 0.0f)) ? cm : -1.f;
+        }
       }
     } else {
 #pragma unroll

@@ -89,6 +89,10 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+// Pull a block of global memory into L2 ahead of its bulk copy (no shared memory, no completion tracking).
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -340,6 +344,9 @@ constexpr uint32_t kB128 = 128 * 256;  // 32 KiB
 // Ring depths: the query block (A, 64 KiB) is double-buffered across items, the train tiles (B, 32 KiB) stream through
 // a 3-deep ring -- one tile feeds ~1.1 k cycles of MMA, an L2 / HBM fetch takes longer than that, so two stages stall
 // the tensor pipe on every tile (measured 61 us vs 75 us for the shallower variants).  224 KiB + barriers <= 227 KiB.
+#ifndef RB200_TC_L2_PREFETCH
+#define RB200_TC_L2_PREFETCH 0  // measured: prefetching the next item into L2 made the cold launch slower (92 vs 84 us)
+#endif
 #ifndef RB200_TC256_ASTAGES
 #define RB200_TC256_ASTAGES 2
 #endif
@@ -408,6 +415,15 @@ __global__ void __launch_bounds__(kTc256Threads, 1) tc_match256_kernel(const Ham
       uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
       for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
         const HamItem item = items[it];
+#if RB200_TC_L2_PREFETCH
+        // The operands of this CTA's NEXT item go to L2 now: with batches larger than L2 every tile is an HBM miss, and a
+        // 3-deep ring of 32 KiB tiles cannot cover HBM latency under load (cold launch 88 us vs 57 us with warm L2).
+        if (it + (int)gridDim.x < n_items) {
+          const HamItem nx = items[it + gridDim.x];
+          bulk_prefetch_l2(nx.a, kA256);
+          for (int nb = 0; nb < nx.n_btiles; nb++) bulk_prefetch_l2(nx.b + (size_t)nb * kB128, kB128);
+        }
+#endif
         RB200_TIMED_WAIT(pf_a, bar(kBarAEmpty + sa), pa ^ 1)
         mbar_expect_tx(bar(kBarAFull + sa), kA256);
         bulk_g2s(sA + sa * kA256, item.a, kA256, bar(kBarAFull + sa));
