@@ -91,11 +91,31 @@ inline MatchingResult to_matching_result(const rgbdslam_b200_pair_result& r, con
 class Node {  // src/node.h: the members the hot path reads + matchNodePair
  public:
   int id_ = -1, seq_id_ = -1, vertex_id_ = -1;
+  double stamp_ = 0.0;           // header_.stamp in seconds
+  bool matchable_ = true, valid_tf_estimate_ = true;  // node.h:160,178
   std::vector<KeyPoint> feature_locations_2d_;  // node.h:167
   std::vector<Vector4f> feature_locations_3d_;  // node.h:174
   std::vector<uint8_t> feature_descriptors_;    // N x 32 (cv::Mat CV_8U rows), node.h:169
 
   Node() {}
+  // Node(visual, depth, detection_mask, cam_info, depth_header, detector, extractor) (node.cpp:101-240): detect, filter,
+  // describe, back-project on the device; the public feature members are filled from the result.  `detector` is the handle of
+  // rgbdslam_b200_detector_create -- the counterpart of the detector_ / extractor_ pair OpenNIListener keeps
+  // (openni_listener.cpp:130-132), whose adaptive per-cell thresholds live across frames.
+  Node(const uint8_t* gray, const float* depth_m, const uint8_t* detection_mask, int w, int h, const float K4[4], int id,
+       uint64_t detector, double stamp = 0.0)
+      : id_(id), stamp_(stamp) {
+    int32_t n = 0, id32 = id;
+    check(rgbdslam_b200_nodes_create(detector, 1, gray, depth_m, detection_mask, w, h, K4, &id32, &handle_, &n), "nodes_create");
+    feature_locations_2d_.resize(n);
+    feature_locations_3d_.resize(n);
+    feature_descriptors_.resize((size_t)n * 32);
+    if (n > 0) {
+      check(rgbdslam_b200_node_download_keypoints(handle_, feature_locations_2d_.data()), "node_download_keypoints");
+      check(rgbdslam_b200_node_download(handle_, feature_descriptors_.data(), reinterpret_cast<float*>(feature_locations_3d_.data())),
+            "node_download");
+    }
+  }
   // Construct from already extracted features (what the reference ctor node.cpp:101-240 leaves behind).
   Node(int id, const std::vector<uint8_t>& desc, const std::vector<Vector4f>& xyz) : id_(id) {
     feature_descriptors_ = desc;
