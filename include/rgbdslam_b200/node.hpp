@@ -105,7 +105,7 @@ class Node {  // src/node.h: the members the hot path reads + matchNodePair
   Node(const uint8_t* gray, const float* depth_m, const uint8_t* detection_mask, int w, int h, const float K4[4], int id,
        uint64_t detector, double stamp = 0.0)
       : id_(id), stamp_(stamp) {
-    int32_t n = 0, id32 = id;
+    int32_t n = 0, id32 = id < 0 ? 0 : id;
     check(rgbdslam_b200_nodes_create(detector, 1, gray, depth_m, detection_mask, w, h, K4, &id32, &handle_, &n), "nodes_create");
     feature_locations_2d_.resize(n);
     feature_locations_3d_.resize(n);
@@ -131,7 +131,9 @@ class Node {  // src/node.h: the members the hot path reads + matchNodePair
   void upload() {
     if (handle_) rgbdslam_b200_node_destroy(handle_);
     handle_ = 0;
-    check(rgbdslam_b200_node_create_from_features(id_, feature_descriptors_.data(),
+    // the device copy only needs a non-negative id (negative ids in a result mean "no transformation"); the ids of the
+    // MatchingResult come from the host objects, which addNode may renumber (graph_manager.cpp:434)
+    check(rgbdslam_b200_node_create_from_features(id_ < 0 ? 0 : id_, feature_descriptors_.data(),
                                                   reinterpret_cast<const float*>(feature_locations_3d_.data()),
                                                   (int)feature_locations_3d_.size(), &handle_),
           "node_create_from_features");
@@ -161,7 +163,13 @@ class Node {  // src/node.h: the members the hot path reads + matchNodePair
     std::vector<DMatch> all((size_t)n * mm), inl((size_t)n * mm);
     int rc = rgbdslam_b200_match_pairs(a.data(), b.data(), n, seed, first_pair_index, res.data(), all.data(), inl.data());
     if (rc != 0) return out;  // invalid edges (-1,-1): matchNodePair never throws (node.cpp:1308,1424)
-    for (int i = 0; i < n; i++) out[i] = to_matching_result(res[i], &all[(size_t)i * mm], &inl[(size_t)i * mm]);
+    for (int i = 0; i < n; i++) {
+      out[i] = to_matching_result(res[i], &all[(size_t)i * mm], &inl[(size_t)i * mm]);
+      if (res[i].id1 >= 0) {  // node.cpp:1337-1338: edge.id1 = older_node->id_, edge.id2 = this->id_
+        out[i].edge.id1 = older[i]->id_;
+        out[i].edge.id2 = newer->id_;
+      }
+    }
     return out;
   }
 

@@ -690,10 +690,12 @@ __global__ void __launch_bounds__(kRansacWarps * 32, RB200_RANSAC_MINBLOCKS)
                       const float4* __restrict__ mfrom, const float4* __restrict__ mto,
                       const int32_t* __restrict__ n_all, HypResult* __restrict__ hyp, float* __restrict__ cen,
                       int32_t* __restrict__ next_n) {
-  __shared__ float4 sfrom[kMaxMatchesCap];
-  __shared__ float4 sto[kMaxMatchesCap];
-  __shared__ float4 cfrom[kMaxMatchesCap];  // centred copies for the fit (see fit_transform)
-  __shared__ float4 cto[kMaxMatchesCap];
+  // NW * 32 rows each (20 KiB in total for the default max_matches = 300): small enough for one CTA of this kernel to share
+  // an SM with a CTA of the tensor-core match kernel of another batch in flight
+  __shared__ float4 sfrom[NW * 32];
+  __shared__ float4 sto[NW * 32];
+  __shared__ float4 cfrom[NW * 32];  // centred copies for the fit (see fit_transform)
+  __shared__ float4 cto[NW * 32];
   __shared__ float s_cen[8];
   __shared__ float s_part[kRansacWarps][6];
   __shared__ int s_next_n;
