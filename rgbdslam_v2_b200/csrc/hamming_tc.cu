@@ -133,17 +133,6 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "memory");
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-// Compiler-level ordering only (no instruction): the values of v[] may not be consumed before this point, i.e. before
-// the tcgen05.wait::ld that precedes it, even when a later tcgen05.ld for another buffer has already been issued.
-__device__ __forceinline__ void tc_reg_fence(uint32_t (&v)[32]) {
-  asm volatile(""
-               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
-                 "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]),
-                 "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]),
-                 "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
-               :
-               : "memory");
-}
 
 // UMMA shared-memory matrix descriptor, K-major, SWIZZLE_NONE ("interleave"):
 //   bits [0,14)  start address >> 4
