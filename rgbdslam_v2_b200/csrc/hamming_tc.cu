@@ -334,7 +334,7 @@ constexpr uint32_t kB128 = 128 * 256;  // 32 KiB
 // a 3-deep ring -- one tile feeds ~1.1 k cycles of MMA, an L2 / HBM fetch takes longer than that, so two stages stall
 // the tensor pipe on every tile (measured 61 us vs 75 us for the shallower variants).  224 KiB + barriers <= 227 KiB.
 #ifndef RB200_TC_L2_PREFETCH
-#define RB200_TC_L2_PREFETCH 0  // measured: prefetching the next item into L2 made the cold launch slower (92 vs 84 us)
+#define RB200_TC_L2_PREFETCH 0  // measured: no gain (bench `value` 1.50-1.52 M with, 1.54-1.59 M pairs/s without)
 #endif
 #ifndef RB200_TC256_ASTAGES
 #define RB200_TC256_ASTAGES 2
@@ -405,8 +405,8 @@ __global__ void __launch_bounds__(kTc256Threads, 1) tc_match256_kernel(const Ham
       for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
         const HamItem item = items[it];
 #if RB200_TC_L2_PREFETCH
-        // The operands of this CTA's NEXT item go to L2 now: with batches larger than L2 every tile is an HBM miss, and a
-        // 3-deep ring of 32 KiB tiles cannot cover HBM latency under load (cold launch 88 us vs 57 us with warm L2).
+        // Experiment (off by default): the operands of this CTA's NEXT item go to L2 now.  No gain -- a cold launch is only
+        // ~2 us slower than a warm one (59 vs 57 us), the 3-deep ring already covers the HBM latency.
         if (it + (int)gridDim.x < n_items) {
           const HamItem nx = items[it + gridDim.x];
           bulk_prefetch_l2(nx.a, kA256);
