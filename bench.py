@@ -300,7 +300,9 @@ def run_ours(args, rank, local_rank, world):
     # Two independent batches (A/B) alternate between two pipeline slots: their resident inputs (2 x 156 MB of node
     # data incl. the int8 operands) exceed the 126 MB L2, so no explicit flush is needed between steps, and the
     # host->device copies / latency-bound RANSAC phases of step k+1 overlap the kernels of step k.
-    DEPTH = 3
+    # batches in flight (measured, 200 steps: depth 3 / 4 / 5 / 7 -> 1.62 / 1.71 / 1.75 / 1.73 M pairs/s on one GPU; with the
+    # per-step all-gather every batch also waits for the slowest rank: 2 GPUs, depth 4 / 6 -> 3.20 / 3.37 M pairs/s)
+    DEPTH = int(os.environ.get("RB200_BENCH_DEPTH", "5" if world == 1 else "6"))
     sets = []
     for j in range(DEPTH):
         b = make_workload(rank + j * world)

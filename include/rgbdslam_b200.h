@@ -220,7 +220,7 @@ int rgbdslam_b200_match_pairs_host(const uint8_t* desc_newer, const float* xyz_n
                                    rgbdslam_b200_dmatch* all_matches,
                                    rgbdslam_b200_dmatch* inlier_matches);
 
-/* Pipelined variants: up to 4 independent slots (own CUDA stream + workspace each).  submit() only enqueues the
+/* Pipelined variants: up to 8 independent slots (own CUDA stream + workspace each).  submit() only enqueues the
  * uploads, kernels and result downloads and returns; wait(slot) blocks until that slot's results are in the output
  * buffers (which must stay valid -- pinned memory recommended).  Successive batches submitted to different slots
  * overlap on the GPU (host->device copies of batch k+1 with the kernels of batch k; the latency-bound RANSAC phases

@@ -98,7 +98,7 @@ int check_inited() {
 // staging buffers are about to be reused)
 static int use_slot(int slot) {
   if (slot < 0 || slot >= kSlots) {
-    set_error("slot out of range [0,4)");
+    set_error("slot out of range [0,8)");
     return RGBDSLAM_B200_ERR_ARG;
   }
   State& s = g_state;
@@ -757,7 +757,7 @@ int rgbdslam_b200_last_timing_slot(int slot, float* hamming_ms, float* total_dev
   int rc = check_inited();
   if (rc) return rc;
   if (slot < 0 || slot >= kSlots) {
-    set_error("slot out of range [0,4)");
+    set_error("slot out of range [0,8)");
     return RGBDSLAM_B200_ERR_ARG;
   }
   g_state.cur = &g_state.ws[slot];
@@ -1015,7 +1015,7 @@ int rgbdslam_b200_match_pairs_wait(int slot) {
   int rc = check_inited();
   if (rc) return rc;
   if (slot < 0 || slot >= kSlots) {
-    set_error("slot out of range [0,4)");
+    set_error("slot out of range [0,8)");
     return RGBDSLAM_B200_ERR_ARG;
   }
   Workspace& w = g_state.ws[slot];

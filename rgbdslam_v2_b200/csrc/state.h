@@ -42,7 +42,7 @@ struct NodeDev {
   int32_t sift_kind = 0;      // SIFT nodes: 0 = RootSIFT rows + bf16 tiles, 1 = raw rows + u8 tiles (SiftGPU matcher)
 };
 
-constexpr int kSlots = 4;  // independent in-flight match_pairs pipelines (stream + workspace each)
+constexpr int kSlots = 8;  // independent in-flight match_pairs pipelines (stream + workspace each)
 
 struct Workspace {
   cudaStream_t stream = nullptr;  // slot 0: the library / user stream; slots 1..: own non-blocking streams
