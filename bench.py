@@ -190,8 +190,8 @@ def run_reference(args, rank, world):
     oracle.build()
     cores = os.cpu_count() or 1
     b = make_workload(0)
-    for _ in range(max(args.warmup, 1)):
-        oracle_run(b, 0, cores)  # full passes: the OpenMP team and the allocator arenas are warm before the timed steps
+    for _ in range(max(args.warmup, 3)):
+        oracle_run(b, 0, cores)  # full passes: the first two are 5-6 x slower (OpenMP team start-up, allocator arenas)
     times = []
     for _ in range(args.steps):
         dt, _ = oracle_run(b, 0, cores)
@@ -478,9 +478,11 @@ def run_ours(args, rank, local_rank, world):
             oracle.build()
             cores = os.cpu_count() or 1
             dt1, _ = oracle_run(b, 0, 1, npairs=32)
-            dtn, ores = oracle_run(b, 0, cores)
+            for _ in range(2):  # the first passes pay for the OpenMP team and the allocator arenas (5-6 x slower)
+                oracle_run(b, 0, cores)
+            dtn, ores = min((oracle_run(b, 0, cores) for _ in range(3)), key=lambda t: t[0])
             out["cpu_baseline"] = {"value": PAIRS_PER_GPU / dtn, "unit": UNIT, "cores": cores, "kind": "port",
-                                   "sample": f"the same {PAIRS_PER_GPU} pairs x {N_KP} kp, one pass, OpenMP over pairs",
+                                   "sample": f"the same {PAIRS_PER_GPU} pairs x {N_KP} kp, best of 3 warm passes, OpenMP over pairs",
                                    "single_thread_value": 32 / dt1}
             agree = int(((ores["id1"] >= 0) == (res_np["id1"] >= 0)).sum())
             out["config"]["oracle_agreement_valid_flags"] = f"{agree}/{PAIRS_PER_GPU}"
