@@ -124,7 +124,9 @@ void rgbdslam_b200_default_params(rgbdslam_b200_params* p);
 int rgbdslam_b200_init(int device, const rgbdslam_b200_params* p);
 int rgbdslam_b200_shutdown(void);
 
-/* Run all subsequent work on this cudaStream_t (NULL = the library's own stream). */
+/* Run all subsequent work of the synchronous calls (slot 0) on this cudaStream_t.  NULL = the library's own non-blocking
+ * stream -- note that the legacy default stream has handle 0 too, so it cannot be selected: work a caller queues on the
+ * default stream is NOT ordered against the library unless it passes a real stream here. */
 int rgbdslam_b200_set_stream(void* cuda_stream);
 /* Block until all work queued by the library has finished. */
 int rgbdslam_b200_synchronize(void);

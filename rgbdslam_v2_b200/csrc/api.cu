@@ -929,14 +929,8 @@ int rgbdslam_b200_node_download(uint64_t node_handle, uint8_t* desc, float* xyz1
   return 0;
 }
 
-int rgbdslam_b200_node_destroy(uint64_t node_handle) {
-  std::lock_guard<std::mutex> lk(g_state.mu);
-  NodeDev* nd = get_node(node_handle);
-  if (!nd) return RGBDSLAM_B200_ERR_ARG;
-  if (g_state.inited) {
-    cudaSetDevice(g_state.device);
-    cudaStreamSynchronize(g_state.stream);
-  }
+// frees everything a (possibly half-built) node owns
+static void free_node(NodeDev* nd) {
   nd->magic = 0;
   if (nd->desc) cudaFree(nd->desc);
   if (nd->xyz) cudaFree(nd->xyz);
@@ -946,6 +940,17 @@ int rgbdslam_b200_node_destroy(uint64_t node_handle) {
   if (nd->desc_f32) cudaFree(nd->desc_f32);
   if (nd->norms) cudaFree(nd->norms);
   delete nd;
+}
+
+int rgbdslam_b200_node_destroy(uint64_t node_handle) {
+  std::lock_guard<std::mutex> lk(g_state.mu);
+  NodeDev* nd = get_node(node_handle);
+  if (!nd) return RGBDSLAM_B200_ERR_ARG;
+  if (g_state.inited) {
+    cudaSetDevice(g_state.device);
+    cudaStreamSynchronize(g_state.stream);
+  }
+  free_node(nd);
   return 0;
 }
 
@@ -1158,19 +1163,31 @@ int rgbdslam_b200_node_create_from_sift(int32_t id, const float* desc128, const 
   if (e == cudaSuccess) e = cudaMalloc(&nd->xyz, 16 * na);
   if (e == cudaSuccess) e = cudaMalloc(&nd->desc_i8, 256 * (size_t)nd->n_pad);
   if (e == cudaSuccess) e = cudaMalloc(&nd->norms, 4 * (size_t)nd->n_pad);
-  if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(sift node)");
+  if (e != cudaSuccess) {
+    free_node(nd);
+    return cuda_fail(e, "cudaMalloc(sift node)");
+  }
   cudaStream_t st = s.stream;
   if (n > 0) {
     e = cudaMemcpyAsync(s.d_f32_a.ptr, desc128, 512 * (size_t)n, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(nd->xyz, xyz1, 16 * (size_t)n, cudaMemcpyHostToDevice, st);
-    if (e != cudaSuccess) return cuda_fail(e, "sift node upload");
+    if (e != cudaSuccess) {
+      free_node(nd);
+      return cuda_fail(e, "sift node upload");
+    }
   }
   std::vector<SiftJob> jobs(1);
   jobs[0] = {(const float*)s.d_f32_a.ptr, nd->desc_f32, (uint16_t*)nd->desc_i8, nd->norms, n, nd->n_pad};
   nd->sift_kind = s.sift_matcher;
-  if ((rc = prepare_sift_nodes(jobs, nd->sift_kind))) return rc;
+  if ((rc = prepare_sift_nodes(jobs, nd->sift_kind))) {
+    free_node(nd);
+    return rc;
+  }
   e = cudaStreamSynchronize(st);
-  if (e != cudaSuccess) return cuda_fail(e, "sift node prepare");
+  if (e != cudaSuccess) {
+    free_node(nd);
+    return cuda_fail(e, "sift node prepare");
+  }
   *node_handle = (uint64_t)(uintptr_t)nd;
   return 0;
 }
