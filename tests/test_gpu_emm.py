@@ -73,3 +73,29 @@ def test_emm_gates_accepted_transformations(built, oracle_mod):
     with pytest.raises(B200Error):
         fe.match_node_pairs([x], [y])
     fe.close()
+
+
+def test_refinement_and_emm_together_on_image_nodes(built, oracle_mod):
+    """Every optional stage of matchNodePair switched on at once (g2o refinement, then the measurement model) on nodes built
+    from images: the stages compose, the result stays close to the ground truth and to the plain RANSAC result."""
+    from rgbdslam_v2_b200 import Frontend
+    from rgbdslam_v2_b200._capi import default_params
+    poses, gray, depth, mask, K4 = _frames([0, 5])
+    outs = []
+    for refine, emm in ((0, -0.6), (4, 0.75)):
+        p = default_params(); p.depth_cov_z0 = 2.0; p.max_keypoints = 600
+        p.g2o_transformation_refinement = refine; p.observability_threshold = emm
+        fe = Frontend(0, p)
+        det = fe.detector_create()
+        handles, _ = fe.nodes_create(det, gray, depth, mask, K4, ids=np.arange(2, dtype=np.int32))
+        res, allm, inl = fe.match_node_pairs([handles[1]], [handles[0]], seed=8)
+        outs.append((res[0].copy(), inl[0, :res[0]["n_inliers"]].copy()))
+        fe.close()
+    (r0, i0), (r1, i1) = outs
+    assert r0["id1"] == 0 and r1["id1"] == 0 and r1["id2"] == 1
+    assert r0["all_points"] == 0 and r1["all_points"] == 2400 and r1["inlier_points"] > 0.75 * (r1["inlier_points"] + r1["outlier_points"])
+    assert r1["n_inliers"] >= r0["n_inliers"] and r1["valid_iterations"] in (r0["valid_iterations"], r0["valid_iterations"] + 1)
+    T_true = np.linalg.inv(poses[0]) @ poses[1]
+    T0, T1 = r0["ransac_trafo"].reshape(4, 4).T, r1["ransac_trafo"].reshape(4, 4).T
+    assert np.abs(T1[:3, 3] - T_true[:3, 3]).max() < 0.01 and np.abs(T1 - T0).max() < 0.01
+    assert len(i1) == r1["n_inliers"]
