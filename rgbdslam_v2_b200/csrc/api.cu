@@ -652,6 +652,12 @@ int rgbdslam_b200_observation_likelihood(uint64_t newer, uint64_t older, const f
     return RGBDSLAM_B200_ERR_STATE;
   }
   State& s = g_state;
+  if (s.params.depth_cov_z0 == 0.0 && s.z0 == 0.0) {
+    // the reference latches depth_covariance's static on its first call (misc2.h:30-35); here that happens in the first
+    // match_pairs call that reaches RANSAC
+    set_error("observation_likelihood: depth covariance not latched yet (depth_cov_z0 == 0): run match_pairs first or set depth_cov_z0");
+    return RGBDSLAM_B200_ERR_STATE;
+  }
   if ((rc = s.d_f32_b.ensure(128))) return rc;
   cudaError_t e = cudaMemcpyAsync(s.d_f32_b.ptr, T, 64, cudaMemcpyHostToDevice, s.stream);
   if (e == cudaSuccess)
