@@ -86,3 +86,40 @@ def test_refine_accepts_only_equal_or_better(oracle_mod):
     # refinement off / too few inliers: untouched
     T2, rmse2, _, n2, vi2 = oracle_mod.refine_g2o(prm, 0, xyz_n, kp_n, xyz_e, kp_e, m, T_true, 2.5, inl, 7)
     assert np.array_equal(T2, T_true) and vi2 == 7 and n2 == 130
+
+
+def test_gauss_newton_optimum_equals_an_independent_least_squares_solver(oracle_mod):
+    """The converged 2-camera BA of the oracle against scipy.optimize.least_squares on the SAME residuals (a different
+    optimiser, numerical Jacobian, rotation-vector parametrisation): same optimum."""
+    from scipy.optimize import least_squares
+    from scipy.spatial.transform import Rotation
+    lib = oracle_mod.lib()
+    rng = np.random.default_rng(11)
+    n = 40
+    X1, kp_n, xyz_n, kp_e, xyz_e = make_scene(rng, n)
+    m = np.zeros(n, oracle_mod.DMATCH_DTYPE); m["queryIdx"] = np.arange(n); m["trainIdx"] = np.arange(n)
+    prm = oracle_mod.make_params(depth_cov_z0=2.0)
+    T0 = np.linalg.inv(X1).astype(np.float32)
+    T = oracle_mod.get_transform_from_matches_g2o(prm, xyz_n, kp_n, xyz_e, kp_e, m, np.arange(n), T0, 15)
+    w = 1.0 / (0.01 * 2.0 * 2.0) ** 2                     # 1 / depth_covariance with the latched z0 = 2
+    sq = np.sqrt(np.array([1.0, 1.0, w]))
+    meas_e = np.c_[kp_e, xyz_e[:, 2]].astype(np.float64); meas_n = np.c_[kp_n, xyz_n[:, 2]].astype(np.float64)
+    I3, z3 = np.ascontiguousarray(np.eye(3)), np.zeros(3)
+
+    def residuals(p):
+        R1 = np.ascontiguousarray(Rotation.from_rotvec(p[:3]).as_matrix()); t1 = np.ascontiguousarray(p[3:6])
+        pts = p[6:].reshape(n, 3)
+        out = np.zeros((n, 2, 3))
+        for k in range(n):
+            pk = np.ascontiguousarray(pts[k])
+            out[k, 0] = _err(lib, R1, t1, pk, np.ascontiguousarray(meas_e[k])) * sq
+            out[k, 1] = _err(lib, I3, z3, pk, np.ascontiguousarray(meas_n[k])) * sq
+        return out.ravel()
+
+    # the oracle seeds camera 1 with the estimate itself (transformation_estimation.cpp:76-84): same starting point here
+    R0 = T0[:3, :3].astype(np.float64)
+    p0 = np.concatenate([Rotation.from_matrix(R0).as_rotvec(), T0[:3, 3].astype(np.float64), xyz_n[:, :3].astype(np.float64).ravel()])
+    sol = least_squares(residuals, p0, method="trf", xtol=1e-12, ftol=1e-12, gtol=1e-12)
+    Xs = np.eye(4); Xs[:3, :3] = Rotation.from_rotvec(sol.x[:3]).as_matrix(); Xs[:3, 3] = sol.x[3:6]
+    T_ls = np.linalg.inv(Xs)                                # the oracle returns the inverse of camera 1's pose (:168)
+    assert np.abs(T_ls - T).max() < 5e-5, np.abs(T_ls - T).max()
