@@ -93,6 +93,7 @@ class Node {  // src/node.h: the members the hot path reads + matchNodePair
   int id_ = -1, seq_id_ = -1, vertex_id_ = -1;
   double stamp_ = 0.0;           // header_.stamp in seconds
   bool matchable_ = true, valid_tf_estimate_ = true;  // node.h:160,178
+  mutable int initial_node_matches_ = 0;              // node.h:207: accepted transformations of this node (max_connections)
   std::vector<KeyPoint> feature_locations_2d_;  // node.h:167
   std::vector<Vector4f> feature_locations_3d_;  // node.h:174
   std::vector<uint8_t> feature_descriptors_;    // N x 32 (cv::Mat CV_8U rows), node.h:169
@@ -164,13 +165,22 @@ class Node {  // src/node.h: the members the hot path reads + matchNodePair
     int rc = rgbdslam_b200_match_pairs(a.data(), b.data(), n, seed, first_pair_index, res.data(), all.data(), inl.data());
     if (rc != 0) return out;  // invalid edges (-1,-1): matchNodePair never throws (node.cpp:1308,1424)
     for (int i = 0; i < n; i++) {
+      // "enough is enough" (node.cpp:1310-1312), in the order the reference's sequential loop would meet the candidates:
+      // once the node has more than max_connections accepted transformations the remaining comparisons return empty
+      if (max_connections() > 0 && newer->initial_node_matches_ > max_connections()) continue;
       out[i] = to_matching_result(res[i], &all[(size_t)i * mm], &inl[(size_t)i * mm]);
       if (res[i].id1 >= 0) {  // node.cpp:1337-1338: edge.id1 = older_node->id_, edge.id2 = this->id_
         out[i].edge.id1 = older[i]->id_;
         out[i].edge.id2 = newer->id_;
+        ++newer->initial_node_matches_;  // node.cpp:1417
       }
     }
     return out;
+  }
+
+  static int& max_connections() {  // parameter max_connections (parameter_server.cpp:104), -1 = unlimited
+    static int v = -1;
+    return v;
   }
 
   static int& max_matches() {  // set once after rgbdslam_b200_init with params.max_matches

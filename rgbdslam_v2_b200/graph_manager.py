@@ -63,6 +63,7 @@ class Params:
     optimizer_skip_step: int = 1
     optimizer_iterations: float = 0.01
     odom_frame_name: str = ""
+    max_connections: int = -1   # node.cpp:1310-1312: > 0 stops comparing once the node has that many accepted transformations
 
 
 def trafo_size(T: np.ndarray):
@@ -259,9 +260,13 @@ class GraphManager:
         self.comparisons.append((node.id, list(targets)))
 
         results = self.backend.match_one_to_many(node, [self.nodes[t] for t in targets], self.seed) if targets else []
+        accepted = 0  # Node::initial_node_matches_ (node.cpp:1417)
         for t, r in zip(targets, results):  # :550-583 (result order == candidate order)
+            if p.max_connections > 0 and accepted > p.max_connections:
+                continue  # "enough is enough": matchNodePair returns an empty result (node.cpp:1310-1312)
             if r["id1"] < 0:
                 continue
+            accepted += 1
             T = np.asarray(r["ransac_trafo"], np.float64).reshape(4, 4).T
             dt = node.stamp - self.nodes[t].stamp
             more = int(r["n_inliers"]) > self.curr_best["n_inliers"]

@@ -123,3 +123,18 @@ def test_motion_gates():
 def test_too_few_features_is_skipped():
     gm, _, _ = _run(3, lambda a, b: True)
     assert gm.add_node(99, 5, 1.0) is False and len(gm.nodes) == 3
+
+
+def test_max_connections_stops_further_comparisons():
+    # every comparison succeeds; with max_connections = 2 a node keeps 3 matched edges (the 4th comparison finds the counter at
+    # 3 > 2 and returns empty, node.cpp:1310-1312).  The predecessor is the LAST candidate, so it is among the skipped ones
+    # and the node also gets the constant-position edge (graph_manager.cpp:636-655) -- the reference does the same.
+    gm, be, _ = _run(12, lambda a, b: True, max_connections=2)
+    ident = np.array([0, 0, 0, 0, 0, 0, 1.0])
+    matched = {}
+    for (a, b), z in zip(gm.edges, gm.meas):
+        if not np.allclose(z, ident):
+            matched[b] = matched.get(b, 0) + 1
+    assert max(matched.values()) == 3 and matched[11] == 3 and gm.n_const_edges > 0
+    gm2, _, _ = _run(12, lambda a, b: True)
+    assert max(np.bincount([b for _, b in gm2.edges])) > 4 and gm2.n_const_edges == 0
