@@ -92,7 +92,11 @@ typedef struct rgbdslam_b200_params {
   int32_t emm_skip_step;          /* 8    :112       */
   int32_t cloud_creation_skip_step; /* 2  :36        */
   float minimum_depth;            /* 0.1  :39        */
-  int32_t reserved_[1];
+  /* Optional branches of the path that are NOT built; rgbdslam_b200_init fails with ERR_ARG when either is set:
+   * use_feature_min_depth (parameter_server.cpp:90; node.cpp:85, misc.cpp:774-791) and allow_features_without_depth
+   * (:115; node.cpp:1120-1125).  Both default to false in the reference. */
+  uint8_t use_feature_min_depth_, allow_features_without_depth_;
+  uint8_t reserved_[2];
 } rgbdslam_b200_params;
 
 /*
@@ -123,6 +127,8 @@ void rgbdslam_b200_default_params(rgbdslam_b200_params* p);
 /* Select CUDA device + parameters.  Replaces ParameterServer::instance() for this path. */
 int rgbdslam_b200_init(int device, const rgbdslam_b200_params* p);
 int rgbdslam_b200_shutdown(void);
+/* The parameter set the library currently runs with (what ParameterServer::instance()->get<>() would return). */
+int rgbdslam_b200_get_params(rgbdslam_b200_params* p);
 
 /* Run all subsequent work of the synchronous calls (slot 0) on this cudaStream_t.  NULL = the library's own non-blocking
  * stream -- note that the legacy default stream has handle 0 too, so it cannot be selected: work a caller queues on the
@@ -319,7 +325,10 @@ int rgbdslam_b200_allgather_slot_edges(uint64_t comm, int slot, int n_per_rank, 
  *   meas  : ne x 7 (LoadedEdge3D::transform)         info : ne x 36 row-major (LoadedEdge3D::informationMatrix)
  *   stop  : optimizer_iterations semantics (graph_manager.cpp:998-1014): >= 1 iteration budget,
  *           (0,1) relative chi2 improvement per chunk of 5 iterations
- * Returns chi2 = optimizer_->chi2() (sum e' Omega e), the number of LM iterations and of PCG iterations. */
+ * Returns chi2 = optimizer_->chi2() (sum e' Omega e), the number of LM iterations and of PCG iterations.
+ * backend_solver (graph_manager.cpp:126-180): only the reference default "pcg" is built -- cholmod / csparse / dense solve
+ * the same linear systems to a tighter residual, so they are not selectable here (SURVEY 8b's `solver` argument dropped).
+ * Non-finite information entries are rejected with ERR_ARG. */
 int rgbdslam_b200_posegraph_optimize(int nv, double* poses, const uint8_t* fixed, int ne, const int32_t* ij,
                                      const double* meas, const double* info, double stop, double huber_delta,
                                      double* chi2, int* iters, int* cg_iters);

@@ -69,9 +69,9 @@ def grid_detect(gray, mask, state: DetectorState, max_keypoints=600, grid=3, max
     ncells = grid * grid
     mn, mx = max_keypoints, int(max_keypoints * 1.5)
     if grid > 1:
-        cmin = int(np.float32(mn / np.float32(ncells)) + np.float32(0.5)) if False else int(round(mn / float(ncells)))
-        cmin = int(np.rint(np.float32(mn) / np.float32(ncells))) if False else int(np.floor(mn / float(ncells) + 0.5))
-        cmax = int(np.floor(mx / float(ncells) + 0.5))
+        # gridmin = round(min / static_cast<float>(gridcells)), likewise gridmax (features.cpp:52-53): C round(), half away from 0
+        cmin = int(np.floor(np.float32(mn) / np.float32(ncells) + 0.5))
+        cmax = int(np.floor(np.float32(mx) / np.float32(ncells) + 0.5))
         per_cell = mx // ncells
     else:
         cmin, cmax, per_cell = mn, mx, 10 ** 9

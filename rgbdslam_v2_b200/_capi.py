@@ -43,7 +43,8 @@ class Params(C.Structure):
         ("min_translation_meter", C.c_double), ("min_rotation_degree", C.c_double),
         ("max_translation_meter", C.c_double), ("max_rotation_degree", C.c_double),
         ("nn_distance_ratio", C.c_double), ("use_root_sift", C.c_int32), ("g2o_transformation_refinement", C.c_int32), ("observability_threshold", C.c_double), ("emm_skip_step", C.c_int32),
-        ("cloud_creation_skip_step", C.c_int32), ("minimum_depth", C.c_float), ("reserved_", C.c_int32 * 1),
+        ("cloud_creation_skip_step", C.c_int32), ("minimum_depth", C.c_float),
+        ("use_feature_min_depth_", C.c_uint8), ("allow_features_without_depth_", C.c_uint8), ("reserved_", C.c_uint8 * 2),
     ]
 
 
@@ -101,6 +102,7 @@ def load_library(path: str | Path | None = None) -> C.CDLL:
     lib.rgbdslam_b200_default_params.restype = None
     lib.rgbdslam_b200_init.argtypes = [C.c_int, C.POINTER(Params)]
     lib.rgbdslam_b200_shutdown.argtypes = []
+    lib.rgbdslam_b200_get_params.argtypes = [C.POINTER(Params)]
     lib.rgbdslam_b200_set_stream.argtypes = [vp]
     lib.rgbdslam_b200_synchronize.argtypes = []
     lib.rgbdslam_b200_last_error.argtypes = []

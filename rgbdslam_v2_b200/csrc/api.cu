@@ -360,6 +360,12 @@ static int run_pairs(const std::vector<PairDesc>& h_pairs, uint64_t seed, int64_
     s.launches += 1;
   }
 
+  if (s.params.depth_cov_z0 == 0.0 && s.z0 == 0.0 && (first_pair != 0 || s.comm_count > 0 || !sync)) {
+    // every rank / in-flight slot would latch a different z0 (and rewrite constant memory under running kernels)
+    set_error("depth_cov_z0 == 0 (latch like the reference) is only possible in a synchronous single-process call with "
+              "first_pair_index 0: set params.depth_cov_z0 for sharded or pipelined use");
+    return RGBDSLAM_B200_ERR_STATE;
+  }
   if (s.params.depth_cov_z0 == 0.0 && s.z0 == 0.0) {
     // Emulate the function-static of depth_covariance (misc2.h:30-35): latch the z of the first
     // correspondence errorFunction2 would see -- first pair that reaches RANSAC, first sorted match with
@@ -512,6 +518,20 @@ int rgbdslam_b200_init(int device, const rgbdslam_b200_params* p) {
   if (prm.max_matches < 1 || prm.max_matches > RGBDSLAM_B200_MAX_MATCHES_CAP || prm.min_matches < 0 ||
       prm.ransac_iterations < 0 || prm.ransac_iterations > 10000) {
     set_error("invalid parameters (max_matches must be in [1,512], ransac_iterations in [0,10000])");
+    return RGBDSLAM_B200_ERR_ARG;
+  }
+  if (!(prm.sigma_depth > 0.0) || !(prm.max_dist_for_inliers > 0.0)) {
+    set_error("invalid parameters (sigma_depth and max_dist_for_inliers must be positive)");
+    return RGBDSLAM_B200_ERR_ARG;
+  }
+  if (prm.observability_threshold > 0.0 && (prm.emm_skip_step <= 0 || prm.cloud_creation_skip_step <= 0)) {
+    // the reference treats emm__skip_step < 0 as "accept" (misc.cpp:828-832); the kernels divide by both steps
+    set_error("invalid parameters (observability_threshold > 0 needs emm_skip_step >= 1 and cloud_creation_skip_step >= 1)");
+    return RGBDSLAM_B200_ERR_ARG;
+  }
+  if (prm.use_feature_min_depth_ || prm.allow_features_without_depth_) {
+    // optional branches of the path that are not built (node.cpp:85, misc.cpp:774-791; node.cpp:1120-1125): fail loudly
+    set_error("use_feature_min_depth / allow_features_without_depth are not supported (reference defaults: false)");
     return RGBDSLAM_B200_ERR_ARG;
   }
   int count = 0;
@@ -688,6 +708,17 @@ int rgbdslam_b200_set_hamming_path(int path) {
     return RGBDSLAM_B200_ERR_ARG;
   }
   g_state.hamming_path = path;
+  return 0;
+}
+
+int rgbdslam_b200_get_params(rgbdslam_b200_params* p) {
+  std::lock_guard<std::mutex> lk(g_state.mu);
+  if (!p) return RGBDSLAM_B200_ERR_ARG;
+  if (!g_state.inited) {
+    set_error("rgbdslam_b200_init() has not been called");
+    return RGBDSLAM_B200_ERR_STATE;
+  }
+  *p = g_state.params;
   return 0;
 }
 

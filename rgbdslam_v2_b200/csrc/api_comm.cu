@@ -102,6 +102,7 @@ int rgbdslam_b200_comm_init(int rank, int world, const uint8_t* id128, uint64_t*
     return nccl_fail(r, "ncclCommInitRank");
   }
   *comm_handle = (uint64_t)(uintptr_t)c;
+  g_state.comm_count++;
   return 0;
 }
 
@@ -116,6 +117,7 @@ int rgbdslam_b200_comm_destroy(uint64_t comm_handle) {
   if (c->gstream) cudaStreamDestroy(c->gstream);
   c->magic = 0;
   delete c;
+  g_state.comm_count--;
   return 0;
 }
 

@@ -1,4 +1,5 @@
 // api_posegraph.cu -- C ABI of the pose-graph solve (declared in include/rgbdslam_b200.h).
+#include <cmath>
 #include <mutex>
 #include <vector>
 
@@ -19,6 +20,11 @@ int rgbdslam_b200_posegraph_optimize(int nv, double* poses, const uint8_t* fixed
     set_error("posegraph_optimize: bad arguments (nv > 0, stop > 0, huber_delta > 0)");
     return RGBDSLAM_B200_ERR_ARG;
   }
+  for (size_t k = 0; k < (size_t)ne * 36; k++)
+    if (!std::isfinite(info[k])) {  // 0 * inf = NaN in the linearisation: the solve would make no progress
+      set_error("posegraph_optimize: non-finite entry in an information matrix");
+      return RGBDSLAM_B200_ERR_ARG;
+    }
   return posegraph_optimize(nv, poses, fixed, ne, ij, meas, info, stop, huber_delta, chi2, iters, cg_iters, nullptr, true);
 }
 

@@ -77,6 +77,7 @@ struct State {
   double z0 = 0.0;  // latched first depth for depth_covariance (misc2.h:30-35)
   cudaStream_t own_stream = nullptr, stream = nullptr;  // stream of the synchronous entry points (= slot 0)
   int64_t launches = 0;
+  int comm_count = 0;  // live NCCL communicators (rgbdslam_b200_comm_init)
   Workspace ws[kSlots];
   Workspace* cur = &ws[0];
   Workspace& W() { return *cur; }

@@ -164,21 +164,32 @@ def make_pose_graph(nv: int = 5000, ne: int = 30000, seed: int = 0, laps: float 
     return dict(gt=gt, init=init, ij=ij, meas=np.ascontiguousarray(meas), info=info, fixed=fixed)
 
 
-def ate_rmse(est_xyz: np.ndarray, gt_xyz: np.ndarray) -> float:
-    """Absolute trajectory error after Horn alignment without scale -- port of
-    rgbd_benchmark/evaluate_ate_module.pyx:35-55 (align) and :179-203 (rmse of the translational error)."""
-    model, data = est_xyz.T, gt_xyz.T
+def ate_align(est_xyz: np.ndarray, gt_xyz: np.ndarray):
+    """Horn alignment without scale -- port of align(model, data), rgbd_benchmark/evaluate_ate_module.pyx:35-55
+    (model = estimated positions, data = ground truth, both [n,3] here).  Returns (rot [3,3], trans [3]).
+    Pinned to the reference's own function by tests/golden/ate_align.npz."""
+    model, data = np.asarray(est_xyz, np.float64).T, np.asarray(gt_xyz, np.float64).T
     mz = model - model.mean(1, keepdims=True)
     dz = data - data.mean(1, keepdims=True)
-    Wm = mz @ dz.T  # sum of outer(model, data)
+    Wm = np.zeros((3, 3))
+    for c in range(model.shape[1]):  # :41-42, same summation order
+        Wm += np.outer(mz[:, c], dz[:, c])
     U, d, Vh = np.linalg.svd(Wm.T)
     S = np.eye(3)
     if np.linalg.det(U) * np.linalg.det(Vh) < 0:
         S[2, 2] = -1
     rot = U @ S @ Vh
-    trans = data.mean(1, keepdims=True) - rot @ model.mean(1, keepdims=True)
-    err = rot @ model + trans - data
-    return float(np.sqrt((err * err).sum(0).mean()))
+    trans = data.mean(1) - rot @ model.mean(1)
+    return rot, trans
+
+
+def ate_rmse(est_xyz: np.ndarray, gt_xyz: np.ndarray) -> float:
+    """Absolute trajectory error: align (above), then the RMSE of the translational error
+    (evaluate_ate_module.pyx:50-53,197)."""
+    rot, trans = ate_align(est_xyz, gt_xyz)
+    err = rot @ np.asarray(est_xyz, np.float64).T + trans[:, None] - np.asarray(gt_xyz, np.float64).T
+    te = np.sqrt((err * err).sum(0))
+    return float(np.sqrt(np.dot(te, te) / len(te)))
 
 
 # ---------------------------------------------------------------------------------------------------
