@@ -288,12 +288,24 @@ int rgbdslam_b200_orb_compute(const uint8_t* gray, int w, int h, const rgbdslam_
  * (octave, response descending, cell, y, x). */
 int rgbdslam_b200_nodes_create(uint64_t detector, int nframes, const uint8_t* gray, const float* depth, const uint8_t* mask,
                                int w, int h, const float* K4, const int32_t* ids, uint64_t* node_handles, int32_t* n_features);
+/* The same with options.  RGBDSLAM_B200_MASK_FROM_DEPTH: the detection mask is what the caller of the reference's constructor
+ * builds from the depth image -- depthToCV8UC1 (misc.cpp:414-418: depth.convertTo(mono8, CV_8UC1, 100, 0), NaN -> 0; handed
+ * over as `depth_mono8_img`, openni_listener.cpp:779) -- computed on the device, `mask` is ignored (saves 1/6 of the upload).
+ * Host buffers may be pinned (copied straight from, asynchronously) or pageable (staged through pinned memory); the upload
+ * of a chunk of frames overlaps the kernels of the previous chunk; all nodes of a call share one device allocation. */
+#define RGBDSLAM_B200_MASK_FROM_DEPTH 1
+int rgbdslam_b200_nodes_create_ex(uint64_t detector, int nframes, const uint8_t* gray, const float* depth, const uint8_t* mask,
+                                  int w, int h, const float* K4, const int32_t* ids, int flags, uint64_t* node_handles,
+                                  int32_t* n_features);
 /* Inspection hook: FAST/NMS candidates {u16 x, u16 y, u8 level, u8 score, u16 0} and Harris responses (NaN = below
  * the cell's final threshold) of grid cell `cell` in frame 0 of the last detect / nodes_create call. */
 int rgbdslam_b200_orb_debug_candidates(int cell, void* cand_out, float* resp_out, int capacity, int* n_out, int* thr_out);
 /* Inspection hook: one plane of frame 0 of the last call.  which: 0 cell image, 1 cell mask, 2 FAST score map
  * (cell pyramids); 3 raw / 4 blurred extractor pyramid (cell ignored). */
 int rgbdslam_b200_orb_debug_plane(int which, int cell, int level, uint8_t* out, int capacity, int* w_out, int* h_out);
+/* Inspection hook: 1 = detect with the unfused kernels (FAST score by threshold search into a global score map -- the one
+ * orb_debug_plane(2, ...) returns --, separate NMS and resize passes), 0 = the default fused kernels.  Identical results. */
+int rgbdslam_b200_orb_debug_detect_path(int unfused);
 /* feature_locations_2d_ (node.h:167) of a node built by nodes_create. */
 int rgbdslam_b200_node_download_keypoints(uint64_t node_handle, rgbdslam_b200_keypoint* kp_out);
 

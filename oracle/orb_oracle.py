@@ -27,8 +27,12 @@ def layer_scale(level: int) -> np.float32:
 
 
 def depth_to_mask(depth: np.ndarray) -> np.ndarray:
-    """depthToCV8UC1 (misc.cpp:414-418): depth.convertTo(mono8, CV_8UC1, 100, 0); NaN -> 0."""
-    return cv2.convertScaleAbs(depth, alpha=100)
+    """depthToCV8UC1 (misc.cpp:414-418): depth.convertTo(mono8, CV_8UC1, 100, 0) = saturate_cast<uchar>(cvRound(d * 100)),
+    NaN -> 0, negative -> 0.  cv2's Python API has no Mat::convertTo; convertScaleAbs is the same conversion of |d * 100|,
+    so negative depths (which convertTo saturates to 0) are cleared afterwards."""
+    m = cv2.convertScaleAbs(depth, alpha=100)
+    m[depth < 0] = 0
+    return m
 
 
 class DetectorState:

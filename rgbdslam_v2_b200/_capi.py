@@ -132,7 +132,9 @@ def load_library(path: str | Path | None = None) -> C.CDLL:
     lib.rgbdslam_b200_orb_detect.argtypes = [u64, vp, vp, C.c_int, C.c_int, vp, C.c_int, C.POINTER(C.c_int)]
     lib.rgbdslam_b200_orb_compute.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int, vp, vp, C.POINTER(C.c_int)]
     lib.rgbdslam_b200_nodes_create.argtypes = [u64, C.c_int, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp]
+    lib.rgbdslam_b200_nodes_create_ex.argtypes = [u64, C.c_int, vp, vp, vp, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp]
     lib.rgbdslam_b200_node_download_keypoints.argtypes = [u64, vp]
+    lib.rgbdslam_b200_orb_debug_detect_path.argtypes = [C.c_int]
     lib.rgbdslam_b200_orb_debug_plane.argtypes = [C.c_int, C.c_int, C.c_int, vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.rgbdslam_b200_orb_debug_candidates.argtypes = [C.c_int, vp, vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.rgbdslam_b200_node_create_from_sift.argtypes = [C.c_int32, vp, vp, C.c_int, C.POINTER(u64)]
@@ -390,20 +392,25 @@ class Frontend:
                                                        _ptr(desc), C.byref(n)))
         return out[:n.value], desc[:n.value]
 
-    def nodes_create(self, det: int, gray: np.ndarray, depth: np.ndarray, mask: np.ndarray | None, K4, ids=None):
-        """gray [F,H,W] u8, depth [F,H,W] f32, mask [F,H,W] u8 or None -> (handles, n_features)."""
-        gray = np.ascontiguousarray(gray, np.uint8)
-        depth = np.ascontiguousarray(depth, np.float32)
-        mask = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+    def nodes_create(self, det: int, gray, depth, mask, K4, ids=None, mask_from_depth: bool = False):
+        """gray [F,H,W] u8, depth [F,H,W] f32, mask [F,H,W] u8 or None -> (handles, n_features).  numpy arrays or pinned torch
+        tensors (copied from asynchronously).  mask_from_depth: derive the detection mask on the device (depthToCV8UC1)."""
+        if isinstance(gray, np.ndarray):
+            gray = np.ascontiguousarray(gray, np.uint8)
+            depth = np.ascontiguousarray(depth, np.float32)
+            mask = None if mask is None else np.ascontiguousarray(mask, np.uint8)
         F, H, W = gray.shape
         K4 = np.ascontiguousarray(K4, np.float32)
         ids = None if ids is None else np.ascontiguousarray(ids, np.int32)
         handles = np.zeros(F, np.uint64)
         nf = np.zeros(F, np.int32)
-        self._check(self.lib.rgbdslam_b200_nodes_create(det, F, _ptr(gray), _ptr(depth), _ptr(mask), W, H, _ptr(K4), _ptr(ids),
-                                                        _ptr(handles), _ptr(nf)))
+        self._check(self.lib.rgbdslam_b200_nodes_create_ex(det, F, _ptr(gray), _ptr(depth), _ptr(None if mask_from_depth else mask), W, H,
+                                                           _ptr(K4), _ptr(ids), 1 if mask_from_depth else 0, _ptr(handles), _ptr(nf)))
         self._nodes += [int(h) for h in handles]
         return [int(h) for h in handles], nf
+
+    def orb_debug_detect_path(self, unfused: bool):
+        self._check(self.lib.rgbdslam_b200_orb_debug_detect_path(1 if unfused else 0))
 
     def orb_debug_plane(self, which: int, cell: int, level: int) -> np.ndarray:
         buf = np.zeros(1024 * 1024, np.uint8)

@@ -455,6 +455,26 @@ static int run_pairs(const std::vector<PairDesc>& h_pairs, uint64_t seed, int64_
   return 0;
 }
 
+// frees everything a (possibly half-built) node owns
+void free_node(NodeDev* nd) {
+  nd->magic = 0;
+  if (nd->slab) {
+    if (--nd->slab->refs == 0) {
+      cudaFree(nd->slab->base);
+      delete nd->slab;
+    }
+  } else {
+    if (nd->desc) cudaFree(nd->desc);
+    if (nd->xyz) cudaFree(nd->xyz);
+    if (nd->desc_i8) cudaFree(nd->desc_i8);
+    if (nd->kp) cudaFree(nd->kp);
+  }
+  if (nd->cloud_z) cudaFree(nd->cloud_z);
+  if (nd->desc_f32) cudaFree(nd->desc_f32);
+  if (nd->norms) cudaFree(nd->norms);
+  delete nd;
+}
+
 int node_build_cloud(NodeDev* nd, const float* d_depth, int w, int h, const float K4[4], cudaStream_t st) {
   State& s = g_state;
   const int step = s.params.cloud_creation_skip_step > 0 ? s.params.cloud_creation_skip_step : 1;
@@ -966,18 +986,7 @@ int rgbdslam_b200_node_download(uint64_t node_handle, uint8_t* desc, float* xyz1
   return 0;
 }
 
-// frees everything a (possibly half-built) node owns
-static void free_node(NodeDev* nd) {
-  nd->magic = 0;
-  if (nd->desc) cudaFree(nd->desc);
-  if (nd->xyz) cudaFree(nd->xyz);
-  if (nd->desc_i8) cudaFree(nd->desc_i8);
-  if (nd->kp) cudaFree(nd->kp);
-  if (nd->cloud_z) cudaFree(nd->cloud_z);
-  if (nd->desc_f32) cudaFree(nd->desc_f32);
-  if (nd->norms) cudaFree(nd->norms);
-  delete nd;
-}
+// (free_node is defined in namespace rb200 above)
 
 int rgbdslam_b200_node_destroy(uint64_t node_handle) {
   std::lock_guard<std::mutex> lk(g_state.mu);

@@ -19,7 +19,9 @@ namespace rb200 {
 struct Detector {
   static constexpr uint32_t kMagic = 0x44455443u;  // 'DETC'
   uint32_t magic = kMagic;
-  double thresh[kOrbMaxCells];
+  double thresh[kOrbMaxCells];  // host mirror of the persistent per-cell thresholds
+  DevBuf d_state;               // the same on the device: the recurrence runs there (k_adapt_thresholds)
+  bool host_valid = true, dev_valid = false;
   Detector() {
     for (int i = 0; i < kOrbMaxCells; i++) thresh[i] = 20.0;  // new DetectorAdjuster("ORB", 20)  features.cpp:92
   }
@@ -34,13 +36,20 @@ struct OrbCtx {
   DevBuf d_ofs, d_w1;
   OrbTables tab;
   int max_per_cell = 0, min_cell = 0, max_cell = 0, kp_stride = 0;
-  int chunk = 0;  // frames per pass
-  DevBuf gray, mask, depth, cell_img, cell_mask, score, cand, cand_count, hist, thr, resp, cell_out, cell_out_count, scratch, kp,
-      xyz, n, pyr_raw, pyr_blur, desc;
+  DevBuf in_gray[2], in_mask[2], in_depth[2];  // double-buffered chunk inputs (upload of chunk k+1 under the kernels of chunk k)
+  PinBuf stage[2];                             // pinned staging for callers that pass pageable memory
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+  DevBuf cell_img, cell_mask, score, cand, cand_count, hist, mask_any, thr, resp, cell_out, cell_out_count, scratch, kp, xyz, n,
+      pyr_raw, pyr_blur, desc, err;
+  const uint8_t* last_gray = nullptr;  // device pointers of frame 0 of the last call (debug hooks)
   void release() {
-    DevBuf* all[] = {&d_ofs, &d_w1, &gray, &mask, &depth, &cell_img, &cell_mask, &score, &cand, &cand_count, &hist, &thr, &resp,
-                     &cell_out, &cell_out_count, &scratch, &kp, &xyz, &n, &pyr_raw, &pyr_blur, &desc};
+    DevBuf* all[] = {&d_ofs, &d_w1, &in_gray[0], &in_gray[1], &in_mask[0], &in_mask[1], &in_depth[0], &in_depth[1], &cell_img,
+                     &cell_mask, &score, &cand, &cand_count, &hist, &mask_any, &thr, &resp, &cell_out, &cell_out_count, &scratch,
+                     &kp, &xyz, &n, &pyr_raw, &pyr_blur, &desc, &err};
     for (DevBuf* b : all) b->release();
+    stage[0].release();
+    stage[1].release();
     ready = false;
   }
 };
@@ -188,7 +197,7 @@ static int orb_prepare(int W, int H, int nframes_hint) {
   }
   o.kp_stride = std::min(kOrbFrameCap, o.max_per_cell * g.ncells);
   o.W = W; o.H = H; o.grid = grid; o.max_kp = K;
-  o.chunk = std::max(1, std::min(nframes_hint > 0 ? nframes_hint : 1, 64));
+  (void)nframes_hint;
   int rc;
   if ((rc = o.d_ofs.ensure(o.h_ofs.size() * 2 + 16)) || (rc = o.d_w1.ensure(o.h_w1.size() * 2 + 16))) return rc;
   cudaStream_t st = s.stream;
@@ -203,53 +212,42 @@ static int orb_prepare(int W, int H, int nframes_hint) {
   return 0;
 }
 
-static int orb_ensure_buffers(int F) {
+constexpr int kOrbChunk = 32;  // frames per pass of nodes_create
+
+static int orb_ensure_streams() {
+  OrbCtx& o = g_orb;
+  if (o.copy_stream) return 0;
+  cudaError_t e = cudaStreamCreateWithFlags(&o.copy_stream, cudaStreamNonBlocking);
+  for (int i = 0; i < 2 && e == cudaSuccess; i++) {
+    e = cudaEventCreateWithFlags(&o.ev_ready[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&o.ev_free[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&o.ev_copied[i], cudaEventDisableTiming);
+  }
+  if (e != cudaSuccess) return cuda_fail(e, "orb streams / events");
+  return 0;
+}
+
+// work buffers for F frames per pass; nbuf input buffers (1: synchronous single-frame entry points, 2: nodes_create)
+static int orb_ensure_buffers(int F, int nbuf, bool want_mask) {
   OrbCtx& o = g_orb;
   const OrbGeom& g = o.g;
   const size_t px = (size_t)g.W * g.H, z = (size_t)F * g.ncells;
   int rc;
-  if ((rc = o.gray.ensure(px * F)) || (rc = o.mask.ensure(px * F)) || (rc = o.depth.ensure(px * F * 4)) ||
-      (rc = o.cell_img.ensure((size_t)g.cell_bytes * F)) || (rc = o.cell_mask.ensure((size_t)g.cell_bytes * F)) ||
+  for (int b = 0; b < nbuf; b++)
+    if ((rc = o.in_gray[b].ensure(px * F)) || (want_mask && (rc = o.in_mask[b].ensure(px * F))) || (rc = o.in_depth[b].ensure(px * F * 4)))
+      return rc;
+  if ((rc = o.cell_img.ensure((size_t)g.cell_bytes * F)) || (rc = o.cell_mask.ensure((size_t)g.cell_bytes * F)) ||
       (rc = o.score.ensure((size_t)g.cell_bytes * F)) || (rc = o.cand.ensure(z * kOrbCandCap * sizeof(OrbCand))) ||
-      (rc = o.cand_count.ensure(z * 4)) || (rc = o.hist.ensure(z * 256 * 4)) || (rc = o.thr.ensure(z * 4)) ||
-      (rc = o.resp.ensure(z * kOrbCandCap * 4)) || (rc = o.cell_out.ensure(z * (size_t)o.max_per_cell * 8)) ||
-      (rc = o.cell_out_count.ensure(z * 4)) || (rc = o.scratch.ensure((size_t)F * 2 * kOrbFrameCap * 24)) ||
+      (rc = o.cand_count.ensure(z * 4)) || (rc = o.hist.ensure(z * 256 * 4)) || (rc = o.mask_any.ensure(z * 4)) ||
+      (rc = o.thr.ensure(z * 4)) || (rc = o.resp.ensure(z * kOrbCandCap * 4)) ||
+      (rc = o.cell_out.ensure(z * (size_t)o.max_per_cell * 8)) || (rc = o.cell_out_count.ensure(z * 4)) ||
+      (rc = o.scratch.ensure((size_t)F * 2 * kOrbFrameCap * 24)) ||
       (rc = o.kp.ensure((size_t)F * o.kp_stride * sizeof(rgbdslam_b200_keypoint))) ||
       (rc = o.xyz.ensure((size_t)F * o.kp_stride * 16)) || (rc = o.n.ensure((size_t)F * 4)) ||
       (rc = o.pyr_raw.ensure((size_t)g.full_bytes * F)) || (rc = o.pyr_blur.ensure((size_t)g.full_bytes * F)) ||
-      (rc = o.desc.ensure((size_t)F * o.kp_stride * 32)))
+      (rc = o.desc.ensure((size_t)F * o.kp_stride * 32)) || (rc = o.err.ensure(16)))
     return rc;
   return 0;
-}
-
-// VideoDynamicAdaptedFeatureDetector::detect (feature_adjuster.cpp:185-224) on the histogram of corner scores:
-// returns the FAST threshold of the LAST detection call and updates the persistent threshold.
-static int adapt_threshold(double& thresh, const int* hist, bool mask_nonzero, int min_features, int max_features, int max_iters) {
-  int cnt_ge[257];
-  cnt_ge[256] = 0;
-  for (int t = 255; t >= 0; t--) cnt_ge[t] = cnt_ge[t + 1] + hist[t];
-  int iter = max_iters, used = 0;
-  bool checked = false;
-  do {
-    int t = (int)thresh;  // static_cast<int>(thresh_) feature_adjuster.cpp:94
-    used = t;
-    const int found = t > 255 ? 0 : cnt_ge[t < 0 ? 0 : t];
-    if (found < min_features) {
-      thresh *= 0.7;  // tooFew
-      if (thresh < 2.0) thresh = 2.0;
-      if (found == 0 && !checked) {
-        checked = true;
-        if (!mask_nonzero) break;
-      }
-    } else if (found > max_features) {
-      thresh *= 1.3;  // tooMany
-      if (thresh > 10000.0) thresh = 10000.0;
-      break;
-    } else
-      break;
-    iter--;
-  } while (iter > 0 && thresh > 2.0 && thresh < 10000.0);
-  return used;
 }
 
 static Detector* get_detector(uint64_t h) {
@@ -261,46 +259,50 @@ static Detector* get_detector(uint64_t h) {
   return d;
 }
 
-// detection stage for F frames already resident in o.gray / o.mask (mask_present) -> thresholds decided, o.thr uploaded
-static int orb_detect_stage(Detector* det, int F, const uint8_t* h_mask, int* launches) {
-  const bool mask_present = h_mask != nullptr;
+// the detector's thresholds live on the device while frames are being processed; the host mirror is refreshed on demand
+static int detector_to_device(Detector* det, cudaStream_t st) {
+  int rc;
+  if ((rc = det->d_state.ensure(sizeof(double) * kOrbMaxCells))) return rc;
+  if (!det->dev_valid) {
+    cudaError_t e = cudaMemcpyAsync(det->d_state.ptr, det->thresh, sizeof(double) * kOrbMaxCells, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return cuda_fail(e, "detector state upload");
+    det->dev_valid = true;
+  }
+  return 0;
+}
+static int detector_to_host(Detector* det) {
+  if (det->host_valid) return 0;
+  cudaError_t e = cudaMemcpy(det->thresh, det->d_state.ptr, sizeof(double) * kOrbMaxCells, cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) return cuda_fail(e, "detector state download");
+  det->host_valid = true;
+  return 0;
+}
+
+// detection stage for F frames resident at d_gray / d_mask (or the mask derived from d_depth_for_mask): candidates,
+// histograms, and the adaptive-threshold recurrence of the F frames in order -- all queued on `st`, no host round trip
+static int orb_detect_stage(Detector* det, int F, const uint8_t* d_gray, const uint8_t* d_mask, const float* d_depth_for_mask,
+                            cudaStream_t st, int* launches) {
   State& s = g_state;
   OrbCtx& o = g_orb;
   const OrbGeom& g = o.g;
-  cudaStream_t st = s.stream;
-  cudaError_t e = orb_run_detect(g, o.tab, F, (const uint8_t*)o.gray.ptr, mask_present ? (const uint8_t*)o.mask.ptr : nullptr,
-                                 (uint8_t*)o.cell_img.ptr, (uint8_t*)o.cell_mask.ptr, (uint8_t*)o.score.ptr, (OrbCand*)o.cand.ptr,
-                                 (int*)o.cand_count.ptr, (int*)o.hist.ptr, st, launches);
+  int rc;
+  if ((rc = detector_to_device(det, st))) return rc;
+  cudaError_t e = orb_run_detect(g, o.tab, F, d_gray, d_mask, d_depth_for_mask, (uint8_t*)o.cell_img.ptr, (uint8_t*)o.cell_mask.ptr,
+                                 (uint8_t*)o.score.ptr, (OrbCand*)o.cand.ptr, (int*)o.cand_count.ptr, (int*)o.hist.ptr,
+                                 (int*)o.mask_any.ptr, st, launches);
   if (e != cudaSuccess) return cuda_fail(e, "orb detect kernels");
-  const size_t z = (size_t)F * g.ncells;
-  std::vector<int> hist(z * 256), cnt(z), thr(z);
-  e = cudaMemcpyAsync(hist.data(), o.hist.ptr, z * 256 * 4, cudaMemcpyDeviceToHost, st);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(cnt.data(), o.cand_count.ptr, z * 4, cudaMemcpyDeviceToHost, st);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-  if (e != cudaSuccess) return cuda_fail(e, "orb histogram download");
-  for (size_t i = 0; i < z; i++)
-    if (cnt[i] > kOrbCandCap) {
-      set_error("ORB candidate buffer overflow (more than 12288 FAST corners in one grid cell)");
-      return RGBDSLAM_B200_ERR_STATE;
-    }
-  // mask-all-zero test (hasNonZero, feature_adjuster.cpp:176-183): a cell with candidates has a non-zero mask; for a
-  // cell without any candidate the distinction only affects how far the threshold decays, decided from the mask itself
-  for (int f = 0; f < F; f++)
-    for (int c = 0; c < g.ncells; c++) {
-      const size_t i = (size_t)f * g.ncells + c;
-      bool nz = cnt[i] > 0 || !mask_present;
-      if (!nz) {  // scan the cell rectangle of the host mask
-        const OrbPlane& p0 = g.cell[c][0];
-        const uint8_t* m = h_mask + (size_t)f * g.W * g.H;
-        for (int y = 0; y < p0.h && !nz; y++)
-          for (int x = 0; x < p0.w; x++)
-            if (m[(size_t)(g.cell_y0[c] + y) * g.W + g.cell_x0[c] + x]) { nz = true; break; }
-      }
-      thr[i] = adapt_threshold(det->thresh[c], &hist[i * 256], nz, o.min_cell, o.max_cell, s.params.adjuster_max_iterations);
-    }
-  e = cudaMemcpyAsync(o.thr.ptr, thr.data(), z * 4, cudaMemcpyHostToDevice, st);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-  if (e != cudaSuccess) return cuda_fail(e, "orb threshold upload");
+  e = orb_run_adapt(g, F, (const int*)o.hist.ptr, (const int*)o.cand_count.ptr, (const int*)o.mask_any.ptr, (double*)det->d_state.ptr,
+                    (int*)o.thr.ptr, o.min_cell, o.max_cell, s.params.adjuster_max_iterations, (int*)o.err.ptr, st, launches);
+  if (e != cudaSuccess) return cuda_fail(e, "orb threshold kernel");
+  det->host_valid = false;
+  return 0;
+}
+
+static int orb_check_err_flag(int flag) {
+  if (flag & 1) {
+    set_error("ORB candidate buffer overflow (more than 12288 FAST corners in one grid cell)");
+    return RGBDSLAM_B200_ERR_STATE;
+  }
   return 0;
 }
 
@@ -316,30 +318,34 @@ int rgbdslam_b200_detector_create(uint64_t* detector) {
   return 0;
 }
 int rgbdslam_b200_detector_destroy(uint64_t detector) {
+  std::lock_guard<std::mutex> lk(g_state.mu);
   Detector* d = get_detector(detector);
   if (!d) return RGBDSLAM_B200_ERR_ARG;
+  if (g_state.inited) {
+    cudaSetDevice(g_state.device);
+    cudaStreamSynchronize(g_state.stream);
+  }
+  d->d_state.release();
   d->magic = 0;
   delete d;
   return 0;
 }
 int rgbdslam_b200_detector_thresholds(uint64_t detector, double* thresholds16, int set) {
+  std::lock_guard<std::mutex> lk(g_state.mu);
   Detector* d = get_detector(detector);
   if (!d || !thresholds16) return RGBDSLAM_B200_ERR_ARG;
+  if (!d->host_valid) {
+    int rc = check_inited();
+    if (rc) return rc;
+    cudaError_t e = cudaStreamSynchronize(g_state.stream);
+    if (e != cudaSuccess) return cuda_fail(e, "detector_thresholds");
+    if ((rc = detector_to_host(d))) return rc;
+  }
   for (int i = 0; i < kOrbMaxCells; i++) {
     if (set) d->thresh[i] = thresholds16[i];
     else thresholds16[i] = d->thresh[i];
   }
-  return 0;
-}
-
-static int upload_frames(int F, const uint8_t* gray, const float* depth, const uint8_t* mask) {
-  OrbCtx& o = g_orb;
-  const size_t px = (size_t)o.g.W * o.g.H;
-  cudaStream_t st = g_state.stream;
-  cudaError_t e = cudaMemcpyAsync(o.gray.ptr, gray, px * F, cudaMemcpyHostToDevice, st);
-  if (e == cudaSuccess && mask) e = cudaMemcpyAsync(o.mask.ptr, mask, px * F, cudaMemcpyHostToDevice, st);
-  if (e == cudaSuccess && depth) e = cudaMemcpyAsync(o.depth.ptr, depth, px * F * 4, cudaMemcpyHostToDevice, st);
-  if (e != cudaSuccess) return cuda_fail(e, "frame upload");
+  if (set) d->dev_valid = false;
   return 0;
 }
 
@@ -353,21 +359,30 @@ int rgbdslam_b200_orb_detect(uint64_t detector, const uint8_t* gray, const uint8
     set_error("orb_detect: bad arguments");
     return RGBDSLAM_B200_ERR_ARG;
   }
-  if ((rc = orb_prepare(w, h, 1)) || (rc = orb_ensure_buffers(1)) || (rc = upload_frames(1, gray, nullptr, mask))) return rc;
+  if ((rc = orb_prepare(w, h, 1)) || (rc = orb_ensure_buffers(1, 1, true))) return rc;
   OrbCtx& o = g_orb;
-  int launches = 0;
-  if ((rc = orb_detect_stage(det, 1, mask, &launches))) return rc;
   cudaStream_t st = g_state.stream;
-  cudaError_t e = orb_run_select(o.g, 1, 0, o.max_per_cell, g_state.params.max_keypoints, (const uint8_t*)o.cell_img.ptr,
-                                 (const OrbCand*)o.cand.ptr, (const int*)o.cand_count.ptr, (const int*)o.thr.ptr, (float*)o.resp.ptr,
-                                 (unsigned long long*)o.cell_out.ptr, (int*)o.cell_out_count.ptr, nullptr, 1.f,
-                                 make_float4(0, 0, 0, 0), o.scratch.ptr, (rgbdslam_b200_keypoint*)o.kp.ptr, (float4*)o.xyz.ptr,
-                                 (int*)o.n.ptr, o.kp_stride, st, &launches);
+  const size_t px = (size_t)w * h;
+  cudaError_t e = cudaMemsetAsync(o.err.ptr, 0, 4, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(o.in_gray[0].ptr, gray, px, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && mask) e = cudaMemcpyAsync(o.in_mask[0].ptr, mask, px, cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) return cuda_fail(e, "orb_detect upload");
+  o.last_gray = (const uint8_t*)o.in_gray[0].ptr;
+  int launches = 0;
+  if ((rc = orb_detect_stage(det, 1, (const uint8_t*)o.in_gray[0].ptr, mask ? (const uint8_t*)o.in_mask[0].ptr : nullptr, nullptr, st,
+                             &launches)))
+    return rc;
+  e = orb_run_select(o.g, 1, 0, o.max_per_cell, g_state.params.max_keypoints, (const uint8_t*)o.cell_img.ptr,
+                     (const OrbCand*)o.cand.ptr, (const int*)o.cand_count.ptr, (const int*)o.thr.ptr, (float*)o.resp.ptr,
+                     (unsigned long long*)o.cell_out.ptr, (int*)o.cell_out_count.ptr, nullptr, 1.f, make_float4(0, 0, 0, 0),
+                     o.scratch.ptr, (rgbdslam_b200_keypoint*)o.kp.ptr, (float4*)o.xyz.ptr, (int*)o.n.ptr, o.kp_stride, st, &launches);
   if (e != cudaSuccess) return cuda_fail(e, "orb select kernels");
-  int n = 0;
+  int n = 0, flag = 0;
   e = cudaMemcpyAsync(&n, o.n.ptr, 4, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&flag, o.err.ptr, 4, cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) return cuda_fail(e, "orb_detect download count");
+  if ((rc = orb_check_err_flag(flag))) return rc;
   *n_out = n;
   const int m = n < capacity ? n : capacity;
   if (m > 0) {
@@ -388,7 +403,7 @@ int rgbdslam_b200_orb_compute(const uint8_t* gray, int w, int h, const rgbdslam_
     set_error("orb_compute: bad arguments");
     return RGBDSLAM_B200_ERR_ARG;
   }
-  if ((rc = orb_prepare(w, h, 1)) || (rc = orb_ensure_buffers(1))) return rc;
+  if ((rc = orb_prepare(w, h, 1)) || (rc = orb_ensure_buffers(1, 1, true))) return rc;
   OrbCtx& o = g_orb;
   // cv::ORB::compute: runByImageBorder(31) on cvRound'ed coordinates, then group by octave (stable)
   std::vector<rgbdslam_b200_keypoint> kept;
@@ -411,11 +426,11 @@ int rgbdslam_b200_orb_compute(const uint8_t* gray, int w, int h, const rgbdslam_
   if ((rc = dk.ensure(sizeof(rgbdslam_b200_keypoint) * (size_t)n)) || (rc = dd.ensure(32 * (size_t)n))) { dk.release(); dd.release(); return rc; }
   cudaStream_t st = g_state.stream;
   int launches = 0;
-  cudaError_t e = cudaMemcpyAsync(o.gray.ptr, gray, (size_t)w * h, cudaMemcpyHostToDevice, st);
+  cudaError_t e = cudaMemcpyAsync(o.in_gray[0].ptr, gray, (size_t)w * h, cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(dk.ptr, kept.data(), sizeof(rgbdslam_b200_keypoint) * (size_t)n, cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(o.n.ptr, &n, 4, cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess)
-    e = orb_run_describe(o.g, o.tab, 1, (const uint8_t*)o.gray.ptr, (uint8_t*)o.pyr_raw.ptr, (uint8_t*)o.pyr_blur.ptr,
+    e = orb_run_describe(o.g, o.tab, 1, (const uint8_t*)o.in_gray[0].ptr, (uint8_t*)o.pyr_raw.ptr, (uint8_t*)o.pyr_blur.ptr,
                          (const rgbdslam_b200_keypoint*)dk.ptr, (const int*)o.n.ptr, n, n, (uint8_t*)dd.ptr, st, &launches);
   if (e == cudaSuccess) e = cudaMemcpyAsync(desc_out, dd.ptr, 32 * (size_t)n, cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -427,77 +442,167 @@ int rgbdslam_b200_orb_compute(const uint8_t* gray, int w, int h, const rgbdslam_
   return 0;
 }
 
-int rgbdslam_b200_nodes_create(uint64_t detector, int nframes, const uint8_t* gray, const float* depth, const uint8_t* mask,
-                               int w, int h, const float* K4, const int32_t* ids, uint64_t* node_handles, int32_t* n_features) {
+static bool is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
+// Node::Node for nframes frames in order.  Pipeline per chunk of kOrbChunk frames:
+//   copy stream    : host -> device of the chunk's gray / depth / mask into one of two input buffers (straight from the caller's
+//                    buffers when they are pinned, else through pinned staging filled by this thread)
+//   compute stream : detect kernels -> threshold recurrence (device) -> Harris / keepStrongest / finalize -> describe, writing
+//                    straight into the slab that holds all nodes of the call (no per-node allocation, no device->device copy)
+// The only host synchronisation is the download of the feature counts at the end.
+int rgbdslam_b200_nodes_create_ex(uint64_t detector, int nframes, const uint8_t* gray, const float* depth, const uint8_t* mask,
+                                  int w, int h, const float* K4, const int32_t* ids, int flags, uint64_t* node_handles,
+                                  int32_t* n_features) {
   std::lock_guard<std::mutex> lk(g_state.mu);
   int rc = check_inited();
   if (rc) return rc;
   Detector* det = get_detector(detector);
-  if (!det || nframes < 0 || (nframes > 0 && (!gray || !depth || !K4 || !node_handles))) {
+  if (!det || nframes < 0 || (nframes > 0 && (!gray || !depth || !K4 || !node_handles)) ||
+      (flags & ~RGBDSLAM_B200_MASK_FROM_DEPTH)) {
     set_error("nodes_create: bad arguments");
     return RGBDSLAM_B200_ERR_ARG;
   }
   if (nframes == 0) return 0;
   State& s = g_state;
-  if ((rc = orb_prepare(w, h, nframes))) return rc;
+  const bool mask_from_depth = (flags & RGBDSLAM_B200_MASK_FROM_DEPTH) != 0;
+  if (mask_from_depth) mask = nullptr;
+  if ((rc = orb_prepare(w, h, nframes)) || (rc = orb_ensure_streams())) return rc;
   OrbCtx& o = g_orb;
-  const int chunk = std::min(nframes, 64);
-  if ((rc = orb_ensure_buffers(chunk))) return rc;
+  const int chunk = std::min(nframes, kOrbChunk);
+  if ((rc = orb_ensure_buffers(chunk, 2, mask != nullptr))) return rc;
   const size_t px = (size_t)w * h;
-  cudaStream_t st = s.stream;
+  cudaStream_t st = s.stream, cs = o.copy_stream;
+  const int K = std::min(o.kp_stride, s.params.max_keypoints);  // features per node (finalize mode 1 emits <= max_keypoints)
+  const int Kpad = ((K > 0 ? K : 1) + 255) / 256 * 256;
+  // slab: [desc F x K x 32][xyz F x K x 16][kp F x K x 28 (padded to 16)][i8 F x Kpad x 256][n F x 4]
+  const size_t b_desc = ((size_t)nframes * K * 32 + 255) / 256 * 256, b_xyz = ((size_t)nframes * K * 16 + 255) / 256 * 256;
+  const size_t b_kp = ((size_t)nframes * K * sizeof(rgbdslam_b200_keypoint) + 255) / 256 * 256;
+  const size_t b_i8 = (size_t)nframes * Kpad * 256, b_n = ((size_t)nframes * 4 + 255) / 256 * 256;
+  NodeSlab* slab = new NodeSlab();
+  cudaError_t e = cudaMalloc(&slab->base, b_desc + b_xyz + b_kp + b_i8 + b_n);
+  if (e != cudaSuccess) {
+    delete slab;
+    return cuda_fail(e, "cudaMalloc(node slab)");
+  }
+  uint8_t* sl_desc = (uint8_t*)slab->base;
+  float4* sl_xyz = (float4*)(sl_desc + b_desc);
+  rgbdslam_b200_keypoint* sl_kp = (rgbdslam_b200_keypoint*)((uint8_t*)sl_xyz + b_xyz);
+  int8_t* sl_i8 = (int8_t*)((uint8_t*)sl_kp + b_kp);
+  int* sl_n = (int*)((uint8_t*)sl_i8 + b_i8);
+  auto fail = [&](int code) {
+    cudaStreamSynchronize(cs);
+    cudaStreamSynchronize(st);
+    cudaFree(slab->base);
+    delete slab;
+    return code;
+  };
+  const bool pinned = is_pinned(gray) && is_pinned(depth) && (!mask || is_pinned(mask));
+  const size_t stage_bytes = (px + px * 4 + (mask ? px : 0)) * chunk;
+  if (!pinned && ((rc = o.stage[0].ensure(stage_bytes)) || (rc = o.stage[1].ensure(stage_bytes)))) return fail(rc);
   // projectTo3D intrinsics (node.cpp:913-916): fxinv, fyinv as float(1./fx)
   const float4 Kinv = make_float4((float)(1. / (double)K4[0]), (float)(1. / (double)K4[1]), K4[2], K4[3]);
-  for (int f0 = 0; f0 < nframes; f0 += chunk) {
-    const int F = std::min(chunk, nframes - f0);
-    int launches = 0;
-    if ((rc = upload_frames(F, gray + px * f0, depth + px * f0, mask ? mask + px * f0 : nullptr))) return rc;
-    if ((rc = orb_detect_stage(det, F, mask ? mask + px * f0 : nullptr, &launches))) return rc;
-    cudaError_t e = orb_run_select(o.g, F, 1, o.max_per_cell, s.params.max_keypoints, (const uint8_t*)o.cell_img.ptr,
-                                   (const OrbCand*)o.cand.ptr, (const int*)o.cand_count.ptr, (const int*)o.thr.ptr,
-                                   (float*)o.resp.ptr, (unsigned long long*)o.cell_out.ptr, (int*)o.cell_out_count.ptr,
-                                   (const float*)o.depth.ptr, (float)s.params.depth_scaling_factor, Kinv, o.scratch.ptr,
-                                   (rgbdslam_b200_keypoint*)o.kp.ptr, (float4*)o.xyz.ptr, (int*)o.n.ptr, o.kp_stride, st, &launches);
-    if (e != cudaSuccess) return cuda_fail(e, "orb select kernels");
-    e = orb_run_describe(o.g, o.tab, F, (const uint8_t*)o.gray.ptr, (uint8_t*)o.pyr_raw.ptr, (uint8_t*)o.pyr_blur.ptr,
-                         (const rgbdslam_b200_keypoint*)o.kp.ptr, (const int*)o.n.ptr, o.kp_stride,
-                         std::min(o.kp_stride, s.params.max_keypoints), (uint8_t*)o.desc.ptr, st, &launches);
-    if (e != cudaSuccess) return cuda_fail(e, "orb describe kernels");
-    std::vector<int> n(F);
-    e = cudaMemcpyAsync(n.data(), o.n.ptr, 4 * (size_t)F, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    if (e != cudaSuccess) return cuda_fail(e, "nodes_create count download");
-    std::vector<ExpandJob> jobs;
-    for (int f = 0; f < F; f++) {
-      NodeDev* nd = new NodeDev();
-      nd->magic = NodeDev::kMagic;
-      nd->id = ids ? ids[f0 + f] : f0 + f;
-      nd->n = n[f];
-      nd->n_pad = ((n[f] > 0 ? n[f] : 1) + 255) / 256 * 256;
-      const size_t na = (size_t)(n[f] > 0 ? n[f] : 1);
-      e = cudaMalloc(&nd->desc, 32 * na);
-      if (e == cudaSuccess) e = cudaMalloc(&nd->xyz, 16 * na);
-      if (e == cudaSuccess) e = cudaMalloc(&nd->kp, sizeof(rgbdslam_b200_keypoint) * na);
-      if (e == cudaSuccess) e = cudaMalloc(&nd->desc_i8, 256 * (size_t)nd->n_pad);
-      if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(node)");
-      if (n[f] > 0) {
-        cudaMemcpyAsync(nd->desc, (const uint8_t*)o.desc.ptr + (size_t)f * o.kp_stride * 32, 32 * (size_t)n[f], cudaMemcpyDeviceToDevice, st);
-        cudaMemcpyAsync(nd->xyz, (const float4*)o.xyz.ptr + (size_t)f * o.kp_stride, 16 * (size_t)n[f], cudaMemcpyDeviceToDevice, st);
-        cudaMemcpyAsync(nd->kp, (const rgbdslam_b200_keypoint*)o.kp.ptr + (size_t)f * o.kp_stride,
-                        sizeof(rgbdslam_b200_keypoint) * (size_t)n[f], cudaMemcpyDeviceToDevice, st);
-      }
-      if (s.params.observability_threshold > 0.0 &&
-          (rc = node_build_cloud(nd, (const float*)o.depth.ptr + (size_t)f * px, w, h, K4, st)))  // Node::pc_col for the EMM
-        return rc;
-      jobs.push_back({nd->desc, nd->desc_i8, nd->n, nd->n_pad});
-      node_handles[f0 + f] = (uint64_t)(uintptr_t)nd;
-      if (n_features) n_features[f0 + f] = n[f];
+  e = cudaMemsetAsync(o.err.ptr, 0, 4, st);
+  if (e != cudaSuccess) return fail(cuda_fail(e, "nodes_create"));
+  // the copy stream must not run ahead of work already queued on the compute stream that still reads the input buffers
+  e = cudaEventRecord(o.ev_free[0], st);
+  if (e == cudaSuccess) e = cudaEventRecord(o.ev_free[1], st);
+  if (e != cudaSuccess) return fail(cuda_fail(e, "nodes_create events"));
+  int launches = 0, ci = 0;
+  std::vector<NodeDev*> made;
+  for (int f0 = 0; f0 < nframes; f0 += chunk, ci++) {
+    const int F = std::min(chunk, nframes - f0), b = ci & 1;
+    const uint8_t* hg = gray + px * f0;
+    const float* hd = depth + px * f0;
+    const uint8_t* hm = mask ? mask + px * f0 : nullptr;
+    if (!pinned) {  // stage through pinned memory (the previous copy out of this staging buffer must have finished)
+      if (ci >= 2 && (e = cudaEventSynchronize(o.ev_copied[b])) != cudaSuccess) return fail(cuda_fail(e, "staging wait"));
+      uint8_t* sp = (uint8_t*)o.stage[b].ptr;
+      memcpy(sp, hg, px * F);
+      memcpy(sp + px * chunk, hd, px * 4 * F);
+      if (hm) memcpy(sp + px * 5 * chunk, hm, px * F);
+      hg = sp;
+      hd = (const float*)(sp + px * chunk);
+      if (hm) hm = sp + px * 5 * chunk;
     }
-    if ((rc = expand_nodes_public(jobs))) return rc;
-    e = cudaStreamSynchronize(st);
-    if (e != cudaSuccess) return cuda_fail(e, "nodes_create finish");
-    s.launches += launches;
+    e = cudaStreamWaitEvent(cs, o.ev_free[b], 0);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(o.in_gray[b].ptr, hg, px * F, cudaMemcpyHostToDevice, cs);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(o.in_depth[b].ptr, hd, px * 4 * F, cudaMemcpyHostToDevice, cs);
+    if (e == cudaSuccess && hm) e = cudaMemcpyAsync(o.in_mask[b].ptr, hm, px * F, cudaMemcpyHostToDevice, cs);
+    if (e == cudaSuccess) e = cudaEventRecord(o.ev_ready[b], cs);
+    if (e == cudaSuccess) e = cudaEventRecord(o.ev_copied[b], cs);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(st, o.ev_ready[b], 0);
+    if (e != cudaSuccess) return fail(cuda_fail(e, "frame upload"));
+    const uint8_t* dg = (const uint8_t*)o.in_gray[b].ptr;
+    const float* dd = (const float*)o.in_depth[b].ptr;
+    if (f0 == 0) o.last_gray = dg;
+    if ((rc = orb_detect_stage(det, F, dg, hm ? (const uint8_t*)o.in_mask[b].ptr : nullptr, mask_from_depth ? dd : nullptr, st,
+                               &launches)))
+      return fail(rc);
+    e = orb_run_select(o.g, F, 1, o.max_per_cell, s.params.max_keypoints, (const uint8_t*)o.cell_img.ptr,
+                       (const OrbCand*)o.cand.ptr, (const int*)o.cand_count.ptr, (const int*)o.thr.ptr, (float*)o.resp.ptr,
+                       (unsigned long long*)o.cell_out.ptr, (int*)o.cell_out_count.ptr, dd, (float)s.params.depth_scaling_factor, Kinv,
+                       o.scratch.ptr, sl_kp + (size_t)f0 * K, sl_xyz + (size_t)f0 * K, sl_n + f0, K, st, &launches);
+    if (e != cudaSuccess) return fail(cuda_fail(e, "orb select kernels"));
+    e = orb_run_describe(o.g, o.tab, F, dg, (uint8_t*)o.pyr_raw.ptr, (uint8_t*)o.pyr_blur.ptr, sl_kp + (size_t)f0 * K, sl_n + f0, K, K,
+                         sl_desc + (size_t)f0 * K * 32, st, &launches);
+    if (e != cudaSuccess) return fail(cuda_fail(e, "orb describe kernels"));
+    {
+      e = launch_expand_i8_strided(sl_desc + (size_t)f0 * K * 32, sl_i8 + (size_t)f0 * Kpad * 256, sl_n + f0, F, K, Kpad, st);
+      if (e != cudaSuccess) return fail(cuda_fail(e, "expand_i8 kernel"));
+      launches++;
+    }
+    if (s.params.observability_threshold > 0.0) {  // Node::pc_col for the environment measurement model
+      for (int f = 0; f < F; f++) {
+        NodeDev* nd = new NodeDev();
+        made.push_back(nd);
+        if ((rc = node_build_cloud(nd, dd + (size_t)f * px, w, h, K4, st))) {
+          for (NodeDev* x : made) { if (x->cloud_z) cudaFree(x->cloud_z); delete x; }
+          return fail(rc);
+        }
+      }
+    }
+    e = cudaEventRecord(o.ev_free[b], st);
+    if (e != cudaSuccess) return fail(cuda_fail(e, "nodes_create events"));
   }
+  std::vector<int> n(nframes);
+  int flag = 0;
+  e = cudaMemcpyAsync(n.data(), sl_n, 4 * (size_t)nframes, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&flag, o.err.ptr, 4, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(cs);
+  if (e != cudaSuccess || (rc = orb_check_err_flag(flag))) {
+    for (NodeDev* x : made) { if (x->cloud_z) cudaFree(x->cloud_z); delete x; }
+    return fail(e != cudaSuccess ? cuda_fail(e, "nodes_create finish") : rc);
+  }
+  for (int f = 0; f < nframes; f++) {
+    NodeDev* nd = made.empty() ? new NodeDev() : made[f];
+    nd->magic = NodeDev::kMagic;
+    nd->id = ids ? ids[f] : f;
+    nd->n = n[f];
+    nd->n_pad = Kpad;
+    nd->desc = sl_desc + (size_t)f * K * 32;
+    nd->xyz = sl_xyz + (size_t)f * K;
+    nd->kp = sl_kp + (size_t)f * K;
+    nd->desc_i8 = sl_i8 + (size_t)f * Kpad * 256;
+    nd->slab = slab;
+    slab->refs++;
+    node_handles[f] = (uint64_t)(uintptr_t)nd;
+    if (n_features) n_features[f] = n[f];
+  }
+  s.launches += launches;
   return 0;
+}
+
+int rgbdslam_b200_nodes_create(uint64_t detector, int nframes, const uint8_t* gray, const float* depth, const uint8_t* mask,
+                               int w, int h, const float* K4, const int32_t* ids, uint64_t* node_handles, int32_t* n_features) {
+  return rgbdslam_b200_nodes_create_ex(detector, nframes, gray, depth, mask, w, h, K4, ids, 0, node_handles, n_features);
 }
 
 /* Debug/inspection hook (used by tools/debug_orb.py and the tests): the FAST/NMS candidates of grid cell `cell` of
@@ -525,6 +630,12 @@ int rgbdslam_b200_orb_debug_candidates(int cell, void* cand_out, float* resp_out
   if (m > 0 && resp_out) cudaMemcpyAsync(resp_out, (const float*)o.resp.ptr + (size_t)cell * kOrbCandCap, 4 * (size_t)m, cudaMemcpyDeviceToHost, st);
   e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) return cuda_fail(e, "orb_debug_candidates copy");
+  return 0;
+}
+
+int rgbdslam_b200_orb_debug_detect_path(int unfused) {
+  std::lock_guard<std::mutex> lk(g_state.mu);
+  orb_set_legacy_detect(unfused);
   return 0;
 }
 

@@ -51,6 +51,40 @@ __global__ void __launch_bounds__(256) expand_i8_kernel(const ExpandJob* __restr
   reinterpret_cast<uint4*>(job.out)[c] = out;
 }
 
+// The same expansion for the nodes of one rgbdslam_b200_nodes_create chunk: node f has its descriptors at desc + f * K * 32,
+// its feature count in n[f] (device memory: no host round trip) and its tiles at out + f * n_pad * 256.
+__global__ void __launch_bounds__(256) expand_i8_strided_kernel(const uint8_t* __restrict__ desc, int8_t* __restrict__ out,
+                                                                const int* __restrict__ n, int K, int n_pad) {
+  const int f = blockIdx.y;
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= n_pad * 16) return;
+  const int tile = c >> 11, rg = (c >> 7) & 15, kc = (c >> 3) & 15, rr = c & 7;
+  const int row = tile * 128 + rg * 8 + rr;
+  uint4 o = make_uint4(0, 0, 0, 0);
+  if (row < n[f]) {
+    const uint8_t* d = desc + ((size_t)f * K + row) * 32 + kc * 2;
+    const unsigned bits = (unsigned)d[0] | ((unsigned)d[1] << 8);
+    unsigned w[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      unsigned v = 0;
+#pragma unroll
+      for (int b = 0; b < 4; b++) v |= (((bits >> (i * 4 + b)) & 1u) ? 0x01u : 0xFFu) << (8 * b);
+      w[i] = v;
+    }
+    o = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  reinterpret_cast<uint4*>(out + (size_t)f * n_pad * 256)[c] = o;
+}
+
+cudaError_t launch_expand_i8_strided(const uint8_t* desc, int8_t* out, const int* d_n, int nframes, int K, int n_pad,
+                                     cudaStream_t stream) {
+  if (nframes <= 0 || n_pad <= 0) return cudaSuccess;
+  dim3 grid((n_pad * 16 + 255) / 256, nframes);
+  expand_i8_strided_kernel<<<grid, 256, 0, stream>>>(desc, out, d_n, K, n_pad);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_expand_i8(const ExpandJob* d_jobs, int njobs, int max_n_pad, cudaStream_t stream) {
   if (njobs <= 0 || max_n_pad <= 0) return cudaSuccess;
   dim3 grid((max_n_pad * 16 + 255) / 256, njobs);

@@ -13,6 +13,8 @@ cudaError_t launch_hamming_simt(const PairDesc* pairs, int npairs, int max_nq, i
 
 // +-1 int8 expansion of the descriptors into the tiled UMMA operand layout (hamming_tc.cu).
 cudaError_t launch_expand_i8(const ExpandJob* d_jobs, int njobs, int max_n_pad, cudaStream_t stream);
+cudaError_t launch_expand_i8_strided(const uint8_t* desc, int8_t* out, const int* d_n, int nframes, int K, int n_pad,
+                                     cudaStream_t stream);
 // Tensor-core (tcgen05 kind::i8) Hamming brute force over work items; same output as launch_hamming_simt.
 cudaError_t launch_hamming_tc(const HamItem* d_items, int n_items, int sm_count, cudaStream_t stream);
 // 256-query work items (HamItem::n_btiles counts 128-row B tiles, nq_valid <= 256)

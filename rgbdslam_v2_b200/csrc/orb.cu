@@ -17,6 +17,8 @@
 
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "orb_tables_generated.h"
 #include "orb_host.h"
 
@@ -26,6 +28,20 @@ __constant__ OrbGeom c_geom;
 __constant__ float c_gauss[7];
 __constant__ int8_t c_pattern[256][4];
 __constant__ int c_umax[kOrbHalfPatch + 2];
+constexpr int kFT_W = 56, kFT_H = 30;  // output pixels per CTA
+constexpr int kFS_W = 64, kFS_H = 32;  // scores computed per CTA: x in [-4, 60), y in [-1, 31) relative to the tile origin
+constexpr int kFI_W = 72, kFI_H = 38;  // image pixels staged: x in [-8, 64), y in [-4, 34)
+constexpr int kFastEdge = 15;          // ORB::create(..., edgeThreshold = 15, ...)  feature_adjuster.cpp:94
+
+struct FastTiling {  // tiles of the fused kernel: per level the tile grid of the LARGEST cell, prefix sums over levels
+  int32_t tiles_x[kOrbLevels], tiles_y[kOrbLevels], first[kOrbLevels + 1];
+};
+__constant__ FastTiling c_fast_tiling;
+
+static int g_fast_tiles = 0;  // CTAs per (frame, cell) of the fused FAST + NMS kernel
+static int g_orb_legacy = -1;  // RB200_ORB_LEGACY=1: the unfused k_fast_score / k_nms_collect / k_resize detect path (cross-check)
+
+void orb_set_legacy_detect(int on) { g_orb_legacy = on ? 1 : 0; }
 
 cudaError_t orb_upload_constants(const OrbGeom& g, const int* umax, cudaStream_t st) {
   cudaError_t e = cudaMemcpyToSymbolAsync(c_geom, &g, sizeof(OrbGeom), 0, cudaMemcpyHostToDevice, st);
@@ -34,21 +50,53 @@ cudaError_t orb_upload_constants(const OrbGeom& g, const int* umax, cudaStream_t
   if (e != cudaSuccess) return e;
   e = cudaMemcpyToSymbolAsync(c_pattern, kOrbPattern, sizeof(kOrbPattern), 0, cudaMemcpyHostToDevice, st);
   if (e != cudaSuccess) return e;
-  return cudaMemcpyToSymbolAsync(c_umax, umax, sizeof(int) * (kOrbHalfPatch + 2), 0, cudaMemcpyHostToDevice, st);
+  e = cudaMemcpyToSymbolAsync(c_umax, umax, sizeof(int) * (kOrbHalfPatch + 2), 0, cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) return e;
+  FastTiling ft;
+  ft.first[0] = 0;
+  for (int l = 0; l < kOrbLevels; l++) {
+    int lw = 0, lh = 0;
+    for (int c = 0; c < g.ncells; c++) {
+      lw = g.cell[c][l].w > lw ? g.cell[c][l].w : lw;
+      lh = g.cell[c][l].h > lh ? g.cell[c][l].h : lh;
+    }
+    const int iw = lw - 2 * kFastEdge, ih = lh - 2 * kFastEdge;  // pixels that can become keypoints
+    ft.tiles_x[l] = iw > 0 ? (iw + kFT_W - 1) / kFT_W : 0;
+    ft.tiles_y[l] = ih > 0 ? (ih + kFT_H - 1) / kFT_H : 0;
+    if (ft.tiles_x[l] == 0 || ft.tiles_y[l] == 0) ft.tiles_x[l] = ft.tiles_y[l] = 0;
+    ft.first[l + 1] = ft.first[l] + ft.tiles_x[l] * ft.tiles_y[l];
+    if (ft.tiles_x[l] == 0) ft.tiles_x[l] = 1;  // never divided by for an empty level (no CTA maps to it)
+  }
+  g_fast_tiles = ft.first[kOrbLevels];
+  return cudaMemcpyToSymbolAsync(c_fast_tiling, &ft, sizeof(ft), 0, cudaMemcpyHostToDevice, st);
 }
 
 // -------------------------------------------------------------------------------------------------
-// level 0 of the per-cell pyramids: sub-image copy; mask binarised (cv2: any non-zero mask pixel is valid)
+// level 0 of the per-cell pyramids: sub-image copy; mask binarised (cv2: any non-zero mask pixel is valid).
+// depth != nullptr: the detection mask is derived on the device as the caller of the reference does on the host --
+// depthToCV8UC1 (misc.cpp:414-418): depth.convertTo(mono8, CV_8UC1, 100, 0) = saturate_cast<uchar>(cvRound(d * 100.f)),
+// NaN -> 0 -- of which only "non-zero" matters: valid iff d * 100.f rounds (half to even) to an int in [1, 2^31).
+// mask_any[f * ncells + c] receives 1 when the cell's mask has any non-zero pixel (hasNonZero, feature_adjuster.cpp:176-183).
 __global__ void __launch_bounds__(256) k_cell_extract(const uint8_t* __restrict__ gray, const uint8_t* __restrict__ mask,
-                                                      uint8_t* __restrict__ cell_img, uint8_t* __restrict__ cell_mask) {
+                                                      const float* __restrict__ depth, uint8_t* __restrict__ cell_img,
+                                                      uint8_t* __restrict__ cell_mask, int* __restrict__ mask_any) {
   const int f = blockIdx.z / c_geom.ncells, c = blockIdx.z % c_geom.ncells;
   const OrbPlane& p = c_geom.cell[c][0];
   const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
-  if (x >= p.w || y >= p.h) return;
-  const size_t src = (size_t)f * c_geom.W * c_geom.H + (size_t)(c_geom.cell_y0[c] + y) * c_geom.W + c_geom.cell_x0[c] + x;
-  const size_t dst = (size_t)f * c_geom.cell_bytes + p.off + (size_t)y * p.w + x;
-  cell_img[dst] = gray[src];
-  cell_mask[dst] = mask ? (mask[src] ? 255 : 0) : 255;
+  bool nz = false;
+  if (x < p.w && y < p.h) {
+    const size_t src = (size_t)f * c_geom.W * c_geom.H + (size_t)(c_geom.cell_y0[c] + y) * c_geom.W + c_geom.cell_x0[c] + x;
+    const size_t dst = (size_t)f * c_geom.cell_bytes + p.off + (size_t)y * p.w + x;
+    cell_img[dst] = gray[src];
+    if (depth) {
+      const float v = __fmul_rn(depth[src], 100.f);
+      nz = v == v && v < 2147483648.f && __float2int_rn(v) >= 1;  // cvRound of +inf / >= 2^31 is INT_MIN -> saturates to 0
+    } else {
+      nz = mask ? mask[src] != 0 : true;
+    }
+    cell_mask[dst] = nz ? 255 : 0;
+  }
+  if (__any_sync(0xffffffffu, nz) && (threadIdx.x & 31) == 0) mask_any[blockIdx.z] = 1;
 }
 
 // dst plane = INTER_LINEAR_EXACT resize of the previous level (8.8 fixed-point taps, round to nearest at the end).
@@ -153,6 +201,201 @@ __global__ void __launch_bounds__(256) k_nms_collect(const uint8_t* __restrict__
     cd.pad_ = 0;
     cand[(size_t)fc * kOrbCandCap + slot] = cd;
   }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Fused FAST score + NMS for ALL pyramid levels of all (frame, cell) planes in one launch (the default detect path).
+// The score is computed directly instead of by binary search over thresholds:
+//   S + 1 = max( v - min_k max_{j<9} p[k+j] ,  max_k min_{j<9} p[k+j] - v )       (k, j on the 16-pixel circle)
+// which equals the largest threshold t for which 9 contiguous circle pixels are all darker than v - t or all brighter than
+// v + t (== cv::FAST's cornerScore<16>), clamped at 0.  Two horizontally adjacent pixels share a register as s16x2 halves
+// (VIMNMX3.S16x2: three-input packed min / max), the image tile is staged in shared memory as 16-bit values so that a pixel
+// pair is one aligned 32-bit word (even offsets) or one PRMT of two words (odd offsets).  The 8-bit scores of a tile plus a
+// one-pixel halo stay in shared memory for the 3x3 non-maximum suppression: the score plane never goes to global memory.
+__device__ __forceinline__ uint32_t pair_at(const uint16_t (*simg)[kFI_W], int row, int col) {  // pixels (col, col+1) as s16x2
+  const uint32_t* r = reinterpret_cast<const uint32_t*>(simg[row]);
+  const uint32_t w0 = r[col >> 1];
+  if ((col & 1) == 0) return w0;
+  return __byte_perm(w0, r[(col >> 1) + 1], 0x5432);
+}
+
+__device__ __forceinline__ uint32_t fast_score_pair(const uint16_t (*simg)[kFI_W], int row, int col) {
+  // circle offsets in cv::FAST order (any rotation of the ring gives the same arcs)
+  constexpr int dx[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
+  constexpr int dy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
+  uint32_t r[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) r[k] = pair_at(simg, row + dy[k], col + dx[k]);
+  const uint32_t v = pair_at(simg, row, col);
+  uint32_t hi3[16], lo3[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) {
+    hi3[k] = __vimax3_s16x2(r[k], r[(k + 1) & 15], r[(k + 2) & 15]);
+    lo3[k] = __vimin3_s16x2(r[k], r[(k + 1) & 15], r[(k + 2) & 15]);
+  }
+  uint32_t mn = 0x7fff7fffu, mx = 0u;  // min over arcs of the arc maximum / max over arcs of the arc minimum
+#pragma unroll
+  for (int k = 0; k < 16; k += 2) {
+    const uint32_t a0 = __vimax3_s16x2(hi3[k], hi3[(k + 3) & 15], hi3[(k + 6) & 15]);
+    const uint32_t a1 = __vimax3_s16x2(hi3[k + 1], hi3[(k + 4) & 15], hi3[(k + 7) & 15]);
+    mn = __vimin3_s16x2(mn, a0, a1);
+    const uint32_t b0 = __vimin3_s16x2(lo3[k], lo3[(k + 3) & 15], lo3[(k + 6) & 15]);
+    const uint32_t b1 = __vimin3_s16x2(lo3[k + 1], lo3[(k + 4) & 15], lo3[(k + 7) & 15]);
+    mx = __vimax3_s16x2(mx, b0, b1);
+  }
+  // per half: S = max(v - mn, mx - v) - 1, clamped at 0 (all quantities within [-255, 255]: no cross-half borrow after biasing)
+  const uint32_t bias = 0x01000100u;
+  const uint32_t apos = (v + bias) - mn;  // v - mn + 256 in [1, 511]
+  const uint32_t aneg = (mx + bias) - v;  // mx - v + 256
+  const uint32_t m = __vmaxs2(apos, aneg);
+  return __vmaxs2(m, 0x01010101u) - 0x01010101u;  // (max(., 257) - 257) per half = max(A - 1, 0)
+}
+
+__global__ void __launch_bounds__(256) k_fast_nms(const uint8_t* __restrict__ cell_img, const uint8_t* __restrict__ cell_mask,
+                                                  OrbCand* __restrict__ cand, int* __restrict__ cand_count, int* __restrict__ hist) {
+  __shared__ __align__(16) uint16_t simg[kFI_H][kFI_W];
+  __shared__ __align__(16) uint8_t ssc[kFS_H][kFS_W];
+  int level = 0;
+#pragma unroll
+  for (int l = 1; l < kOrbLevels; l++)
+    if ((int)blockIdx.x >= c_fast_tiling.first[l]) level = l;
+  const int t = blockIdx.x - c_fast_tiling.first[level];
+  const int tx = t % c_fast_tiling.tiles_x[level], ty = t / c_fast_tiling.tiles_x[level];
+  const int fc = blockIdx.y;
+  const int f = fc / c_geom.ncells, c = fc % c_geom.ncells;
+  const int pw = c_geom.cell[c][level].w, ph = c_geom.cell[c][level].h;
+  const int ox0 = kFastEdge + tx * kFT_W, oy0 = kFastEdge + ty * kFT_H;
+  if (ox0 >= pw - kFastEdge || oy0 >= ph - kFastEdge) return;
+  const size_t base = (size_t)f * c_geom.cell_bytes + c_geom.cell[c][level].off;
+  const uint8_t* im = cell_img + base;
+  for (int i = threadIdx.x; i < kFI_H * kFI_W; i += 256) {
+    const int rr = i / kFI_W, cc = i - rr * kFI_W;
+    const int gx = ox0 - 8 + cc, gy = oy0 - 4 + rr;
+    simg[rr][cc] = (gx >= 0 && gx < pw && gy >= 0 && gy < ph) ? im[gy * pw + gx] : 0;
+  }
+  __syncthreads();
+  {  // scores: thread = (quad of 4 columns, row), two row passes
+    const int q = threadIdx.x & 15, r0 = threadIdx.x >> 4;
+#pragma unroll
+    for (int pass = 0; pass < 2; pass++) {
+      const int sy = r0 + 16 * pass;  // score row (relative y = sy - 1) -> image row sy + 3
+      const uint32_t s01 = fast_score_pair(simg, sy + 3, 4 * q + 4);
+      const uint32_t s23 = fast_score_pair(simg, sy + 3, 4 * q + 6);
+      // halves hold 0..254: pack the four scores into bytes
+      reinterpret_cast<uint32_t*>(ssc[sy])[q] = __byte_perm(s01, s23, 0x6420);
+    }
+  }
+  __syncthreads();
+  // strict 3x3 non-maximum suppression on S, runByPixelsMask, runByImageBorder(15) -> candidates + histogram
+  for (int i = threadIdx.x; i < kFT_W * kFT_H; i += 256) {
+    const int oy = i / kFT_W, ox = i - oy * kFT_W;
+    const int gx = ox0 + ox, gy = oy0 + oy;
+    if (gx >= pw - kFastEdge || gy >= ph - kFastEdge) continue;
+    const int sx = ox + 4, sy = oy + 1;
+    const int v = ssc[sy][sx];
+    if (v < 2) continue;  // the adaptive threshold never drops below 2 (DetectorAdjuster min_thresh)
+    const bool mxm = v > ssc[sy - 1][sx - 1] && v > ssc[sy - 1][sx] && v > ssc[sy - 1][sx + 1] && v > ssc[sy][sx - 1] &&
+                     v > ssc[sy][sx + 1] && v > ssc[sy + 1][sx - 1] && v > ssc[sy + 1][sx] && v > ssc[sy + 1][sx + 1];
+    if (!mxm) continue;
+    if (cell_mask && cell_mask[base + (size_t)gy * pw + gx] == 0) continue;
+    atomicAdd(&hist[fc * 256 + v], 1);
+    const int slot = atomicAdd(&cand_count[fc], 1);
+    if (slot < kOrbCandCap) {
+      OrbCand cd;
+      cd.x = (uint16_t)gx;
+      cd.y = (uint16_t)gy;
+      cd.level = (uint8_t)level;
+      cd.score = (uint8_t)v;
+      cd.pad_ = 0;
+      cand[(size_t)fc * kOrbCandCap + slot] = cd;
+    }
+  }
+}
+
+// All cell planes of one level from the previous level, image and mask together (INTER_LINEAR_EXACT, 8.8 fixed-point taps;
+// the mask level is THRESH_TOZERO(254) of its resize, i.e. 255 exactly when every tap with a non-zero weight is 255).
+__global__ void __launch_bounds__(256) k_resize_cells(uint8_t* __restrict__ cell_img, uint8_t* __restrict__ cell_mask, int level,
+                                                      OrbTables tab) {
+  const int fc = blockIdx.z;
+  const int f = fc / c_geom.ncells, c = fc - f * c_geom.ncells;
+  const int dw = c_geom.cell[c][level].w, dh = c_geom.cell[c][level].h;
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= dw || y >= dh) return;
+  const int sw = c_geom.cell[c][level - 1].w, sh = c_geom.cell[c][level - 1].h;
+  const unsigned fbase = (unsigned)f * (unsigned)c_geom.cell_bytes;
+  const unsigned soff = fbase + c_geom.cell[c][level - 1].off, doff = fbase + c_geom.cell[c][level].off;
+  const int tx = c_geom.cell[c][level].tx + x, ty = c_geom.cell[c][level].ty + y;
+  const int ox = tab.ofs[tx], ax1 = tab.w1[tx], ax0 = 256 - ax1;
+  const int oy = tab.ofs[ty], ay1 = tab.w1[ty], ay0 = 256 - ay1;
+  const int x1 = min(ox + 1, sw - 1), y1 = min(oy + 1, sh - 1);
+  const unsigned i00 = soff + oy * sw + ox, i01 = soff + oy * sw + x1, i10 = soff + y1 * sw + ox, i11 = soff + y1 * sw + x1;
+  {
+    const int h0 = cell_img[i00] * ax0 + cell_img[i01] * ax1;
+    const int h1 = cell_img[i10] * ax0 + cell_img[i11] * ax1;
+    cell_img[doff + y * dw + x] = (uint8_t)((h0 * ay0 + h1 * ay1 + (1 << 15)) >> 16);
+  }
+  if (cell_mask) {
+    const int h0 = cell_mask[i00] * ax0 + cell_mask[i01] * ax1;
+    const int h1 = cell_mask[i10] * ax0 + cell_mask[i11] * ax1;
+    const int v = (h0 * ay0 + h1 * ay1 + (1 << 15)) >> 16;
+    cell_mask[doff + y * dw + x] = v <= 254 ? 0 : (uint8_t)v;
+  }
+}
+
+// VideoDynamicAdaptedFeatureDetector::detect (feature_adjuster.cpp:185-224) on the histogram of corner scores, for the
+// F frames of a chunk IN ORDER (the threshold of a cell persists from frame to frame, feature_adjuster.cpp:131-150).
+// The re-detect loop (x0.7 while too few, <= max_iters detections) only needs #candidates(S >= t): a histogram lookup.
+// One warp per grid cell; lane l owns score bins [8l, 8l+8).  state[c] = the detector's persistent threshold (double, as in
+// the reference); thr_out[f * ncells + c] = the integer FAST threshold of the LAST detection call of that frame.
+// err_flag bit 0: a cell overflowed the candidate buffer.
+__global__ void __launch_bounds__(32 * kOrbMaxCells) k_adapt_thresholds(const int* __restrict__ hist, const int* __restrict__ cand_count,
+                                                                         const int* __restrict__ mask_any, double* __restrict__ state,
+                                                                         int* __restrict__ thr_out, int nframes, int ncells,
+                                                                         int min_features, int max_features, int max_iters,
+                                                                         int* __restrict__ err_flag) {
+  const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (c >= ncells) return;
+  double thresh = state[c];
+  for (int f = 0; f < nframes; f++) {
+    const int fc = f * ncells + c;
+    int h[8];
+    {
+      const int4 a = reinterpret_cast<const int4*>(hist + (size_t)fc * 256)[lane * 2];
+      const int4 b = reinterpret_cast<const int4*>(hist + (size_t)fc * 256)[lane * 2 + 1];
+      h[0] = a.x; h[1] = a.y; h[2] = a.z; h[3] = a.w; h[4] = b.x; h[5] = b.y; h[6] = b.z; h[7] = b.w;
+    }
+    const int cnt = cand_count[fc];
+    if (cnt > kOrbCandCap && lane == 0) atomicOr(err_flag, 1);
+    const bool mask_nonzero = cnt > 0 || mask_any[fc] != 0;
+    int iter = max_iters, used = 0;
+    bool checked = false;
+    do {
+      const int t = (int)thresh;  // static_cast<int>(thresh_) feature_adjuster.cpp:94
+      used = t;
+      int part = 0;
+#pragma unroll
+      for (int k = 0; k < 8; k++) part += (lane * 8 + k >= t) ? h[k] : 0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+      const int found = part;  // t > 255 -> 0
+      if (found < min_features) {
+        thresh = __dmul_rn(thresh, 0.7);  // tooFew
+        if (thresh < 2.0) thresh = 2.0;
+        if (found == 0 && !checked) {
+          checked = true;
+          if (!mask_nonzero) break;
+        }
+      } else if (found > max_features) {
+        thresh = __dmul_rn(thresh, 1.3);  // tooMany
+        if (thresh > 10000.0) thresh = 10000.0;
+        break;
+      } else
+        break;
+      iter--;
+    } while (iter > 0 && thresh > 2.0 && thresh < 10000.0);
+    if (lane == 0) thr_out[fc] = used;
+  }
+  if (lane == 0) state[c] = thresh;
 }
 
 // HarrisResponses(img, pts, blockSize 7, k 0.04): Sobel-3 sums over 7x7, float formula evaluated in the same order
@@ -542,8 +785,8 @@ __global__ void __launch_bounds__(256) k_describe(const uint8_t* __restrict__ py
 static inline dim3 plane_grid(int w, int h, int z) { return dim3((w + 31) / 32, (h + 7) / 8, z); }
 
 cudaError_t orb_run_detect(const OrbGeom& g, const OrbTables& tab, int nframes, const uint8_t* d_gray, const uint8_t* d_mask,
-                           uint8_t* d_cell_img, uint8_t* d_cell_mask, uint8_t* d_score, OrbCand* d_cand, int* d_cand_count,
-                           int* d_hist, cudaStream_t st, int* launches) {
+                           const float* d_depth_for_mask, uint8_t* d_cell_img, uint8_t* d_cell_mask, uint8_t* d_score, OrbCand* d_cand,
+                           int* d_cand_count, int* d_hist, int* d_mask_any, cudaStream_t st, int* launches) {
   int maxw = 0, maxh = 0;
   for (int c = 0; c < g.ncells; c++) {
     maxw = g.cell[c][0].w > maxw ? g.cell[c][0].w : maxw;
@@ -552,8 +795,30 @@ cudaError_t orb_run_detect(const OrbGeom& g, const OrbTables& tab, int nframes, 
   const int z = nframes * g.ncells;
   cudaMemsetAsync(d_cand_count, 0, sizeof(int) * z, st);
   cudaMemsetAsync(d_hist, 0, sizeof(int) * 256 * z, st);
-  k_cell_extract<<<plane_grid(maxw, maxh, z), 256, 0, st>>>(d_gray, d_mask, d_cell_img, d_cell_mask);
+  cudaMemsetAsync(d_mask_any, 0, sizeof(int) * z, st);
+  k_cell_extract<<<plane_grid(maxw, maxh, z), 256, 0, st>>>(d_gray, d_mask, d_depth_for_mask, d_cell_img, d_cell_mask, d_mask_any);
   (*launches)++;
+  const bool all_valid = d_mask == nullptr && d_depth_for_mask == nullptr;  // mask pyramid would stay 255 everywhere
+  if (g_orb_legacy < 0) {
+    const char* ev = getenv("RB200_ORB_LEGACY");
+    g_orb_legacy = (ev && ev[0] == '1') ? 1 : 0;
+  }
+  if (!g_orb_legacy) {
+    for (int l = 1; l < kOrbLevels; l++) {
+      int lw = 0, lh = 0;
+      for (int c = 0; c < g.ncells; c++) {
+        lw = g.cell[c][l].w > lw ? g.cell[c][l].w : lw;
+        lh = g.cell[c][l].h > lh ? g.cell[c][l].h : lh;
+      }
+      k_resize_cells<<<plane_grid(lw, lh, z), 256, 0, st>>>(d_cell_img, all_valid ? nullptr : d_cell_mask, l, tab);
+      (*launches)++;
+    }
+    if (g_fast_tiles > 0) {
+      k_fast_nms<<<dim3(g_fast_tiles, z), 256, 0, st>>>(d_cell_img, all_valid ? nullptr : d_cell_mask, d_cand, d_cand_count, d_hist);
+      (*launches)++;
+    }
+    return cudaGetLastError();
+  }
   for (int l = 0; l < kOrbLevels; l++) {
     int lw = 0, lh = 0;
     for (int c = 0; c < g.ncells; c++) {
@@ -569,6 +834,15 @@ cudaError_t orb_run_detect(const OrbGeom& g, const OrbTables& tab, int nframes, 
     k_nms_collect<<<plane_grid(lw, lh, z), 256, 0, st>>>(d_score, d_cell_mask, l, d_cand, d_cand_count, d_hist);
     (*launches) += 2;
   }
+  return cudaGetLastError();
+}
+
+cudaError_t orb_run_adapt(const OrbGeom& g, int nframes, const int* d_hist, const int* d_cand_count, const int* d_mask_any,
+                          double* d_state, int* d_thr, int min_features, int max_features, int max_iters, int* d_err,
+                          cudaStream_t st, int* launches) {
+  k_adapt_thresholds<<<1, 32 * kOrbMaxCells, 0, st>>>(d_hist, d_cand_count, d_mask_any, d_state, d_thr, nframes, g.ncells,
+                                                      min_features, max_features, max_iters, d_err);
+  (*launches)++;
   return cudaGetLastError();
 }
 

@@ -23,6 +23,13 @@ struct PinBuf {  // grow-only pinned host buffer
   void release();
 };
 
+// One device allocation shared by all nodes of a rgbdslam_b200_nodes_create call (no per-node cudaMalloc); freed when
+// its last node is destroyed.
+struct NodeSlab {
+  void* base = nullptr;
+  int refs = 0;
+};
+
 // Device copy of what the reference's Node keeps per frame (node.h:167-174).
 struct NodeDev {
   static constexpr uint32_t kMagic = 0x4e4f4445u;  // 'NODE'
@@ -40,6 +47,7 @@ struct NodeDev {
   int32_t cw = 0, ch = 0;
   float K[4] = {0, 0, 0, 0};  // fx, fy, cx, cy of the full-resolution camera
   int32_t sift_kind = 0;      // SIFT nodes: 0 = RootSIFT rows + bf16 tiles, 1 = raw rows + u8 tiles (SiftGPU matcher)
+  NodeSlab* slab = nullptr;   // desc / xyz / kp / desc_i8 live inside this shared allocation (cloud_z is always separate)
 };
 
 constexpr int kSlots = 8;  // independent in-flight match_pairs pipelines (stream + workspace each)
@@ -97,5 +105,6 @@ int cuda_fail(cudaError_t e, const char* what);
 int check_inited();
 int node_build_cloud(NodeDev* nd, const float* d_depth, int w, int h, const float K4[4], cudaStream_t st);
 int expand_nodes_public(const std::vector<ExpandJob>& jobs);  // +-1 int8 expansion (api.cu)
+void free_node(NodeDev* nd);  // frees everything a (possibly half-built) node owns (api.cu)
 
 }  // namespace rb200

@@ -141,3 +141,92 @@ def test_no_mask_and_other_parameters(fe, frames):
     assert np.array_equal(fe.detector_thresholds(det)[:9], np.array(st.thresh[:9]))
     fe.detector_destroy(det)
     _reinit(fe, max_keypoints=600)
+
+
+def _node_dump(fe, handles):
+    return [(fe.node_keypoints(h), *fe.node_download(h)) for h in handles]
+
+
+def _same_nodes(a, b):
+    for (ka, da, xa), (kb, db, xb) in zip(a, b):
+        if not (np.array_equal(ka, kb) and np.array_equal(da, db) and np.array_equal(xa.view(np.uint32), xb.view(np.uint32))):
+            return False
+    return len(a) == len(b)
+
+
+@pytest.fixture(scope="module")
+def seq40():
+    from oracle import orb_oracle
+    from rgbdslam_v2_b200 import synth
+    poses = synth.trajectory(240)[:40]
+    fr = [synth.render_frame(poses[k], seed=k) for k in range(40)]
+    gray = np.stack([f[0] for f in fr]); depth = np.stack([f[1] for f in fr])
+    mask = np.stack([orb_oracle.depth_to_mask(d) for d in depth])
+    return gray, depth, mask
+
+
+def test_nodes_create_pipeline_variants_identical(fe, seq40):
+    """The chunked, double-buffered constructor (40 frames = 2 chunks) gives bit-identical nodes and detector thresholds
+    (a) frame by frame, (b) from pinned host memory, (c) with the mask derived from depth on the device,
+    (d) through the unfused detect kernels."""
+    import torch
+    from rgbdslam_v2_b200 import synth
+    gray, depth, mask = seq40
+    K4 = (synth.FX, synth.FY, synth.CX, synth.CY)
+    _reinit(fe, max_keypoints=600)
+
+    def run(fn):
+        det = fe.detector_create()
+        out = fn(det)
+        thr = fe.detector_thresholds(det).copy()
+        fe.detector_destroy(det)
+        dump = _node_dump(fe, out)
+        for h in out:
+            fe.node_destroy(h)
+        return dump, thr
+
+    ref, thr_ref = run(lambda det: fe.nodes_create(det, gray, depth, mask, K4)[0])
+    assert len(ref) == 40 and min(len(k) for k, _, _ in ref) > 300
+
+    def one_by_one(det):
+        hs = []
+        for k in range(40):
+            hs += fe.nodes_create(det, gray[k:k + 1], depth[k:k + 1], mask[k:k + 1], K4, ids=[k])[0]
+        return hs
+    a, thr_a = run(one_by_one)
+    assert _same_nodes(ref, a) and np.array_equal(thr_ref, thr_a)
+
+    pg, pd, pm = (torch.from_numpy(x).pin_memory() for x in (gray, depth, mask))
+    b, thr_b = run(lambda det: fe.nodes_create(det, pg, pd, pm, K4)[0])
+    assert _same_nodes(ref, b) and np.array_equal(thr_ref, thr_b)
+
+    c, thr_c = run(lambda det: fe.nodes_create(det, gray, depth, None, K4, mask_from_depth=True)[0])
+    assert _same_nodes(ref, c) and np.array_equal(thr_ref, thr_c)
+
+    fe.orb_debug_detect_path(True)
+    try:
+        d, thr_d = run(lambda det: fe.nodes_create(det, gray, depth, mask, K4)[0])
+    finally:
+        fe.orb_debug_detect_path(False)
+    assert _same_nodes(ref, d) and np.array_equal(thr_ref, thr_d)
+
+
+def test_nodes_create_without_mask_and_small_batches(fe, seq40):
+    """mask = NULL (no mask pyramid at all) equals an all-255 mask; nodes of one call share a slab and survive the others"""
+    from rgbdslam_v2_b200 import synth
+    gray, depth, _ = seq40
+    K4 = (synth.FX, synth.FY, synth.CX, synth.CY)
+    _reinit(fe, max_keypoints=600)
+    det = fe.detector_create()
+    h1, _ = fe.nodes_create(det, gray[:3], depth[:3], None, K4)
+    fe.detector_destroy(det)
+    det = fe.detector_create()
+    h2, _ = fe.nodes_create(det, gray[:3], depth[:3], np.full_like(gray[:3], 255), K4)
+    fe.detector_destroy(det)
+    a, b = _node_dump(fe, h1), _node_dump(fe, h2)
+    assert _same_nodes(a, b)
+    fe.node_destroy(h1[0]); fe.node_destroy(h1[2])  # the slab stays alive for the remaining node
+    k, d, x = fe.node_keypoints(h1[1]), *fe.node_download(h1[1])
+    assert np.array_equal(k, b[1][0]) and np.array_equal(d, b[1][1])
+    for h in [h1[1]] + h2:
+        fe.node_destroy(h)

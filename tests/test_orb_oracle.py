@@ -61,3 +61,19 @@ def test_node_constructor_invariants():
         z = d[v, u]
         assert xyz[i, 2] == z
         assert abs(xyz[i, 0] - (kp["x"][i] - K4[2]) * z / K4[0]) < 1e-5 and abs(xyz[i, 1] - (kp["y"][i] - K4[3]) * z / K4[1]) < 1e-5
+
+
+def test_mask_from_depth_rule_matches_cv2():
+    """RGBDSLAM_B200_MASK_FROM_DEPTH derives the detection mask on the device as `d * 100.f rounds (half to even) to an int in [1, 2^31)`;
+    the same rule in numpy must agree with cv2's conversion (depthToCV8UC1, misc.cpp:414-418) on non-zero-ness."""
+    from oracle import orb_oracle
+    rng = np.random.default_rng(3)
+    d = rng.uniform(0.0, 6.0, (120, 160)).astype(np.float32)
+    d[rng.random(d.shape) < 0.1] = np.nan
+    d[:2, :8] = np.array([0.0, 0.004, 0.005, 0.0050001, 0.0149, 0.015, 2.55, 100.0], np.float32)
+    d[2, :6] = np.array([-0.5, -0.004, np.inf, 1e-30, 3e7, 2e7], np.float32)
+    m = orb_oracle.depth_to_mask(d)
+    with np.errstate(invalid="ignore"):
+        v = d * np.float32(100.0)
+        rule = ~np.isnan(v) & (v < np.float32(2147483648.0)) & (np.rint(v) >= 1)
+    assert np.array_equal(m != 0, rule)

@@ -29,19 +29,31 @@ def frames(n):
 
 
 if "orb" in which:
-    n = int(__import__("os").environ.get("RB200_ORB_FRAMES", "64"))
-    gray, depth, mask = frames(n)
+    import os
+    import torch
+    n = int(os.environ.get("RB200_ORB_FRAMES", "64"))
+    reps = int(os.environ.get("RB200_ORB_REPS", "4"))
+    gray, depth, mask = frames(min(n, 64))
+    if n > 64:  # tile the rendered frames (timing only)
+        k = (n + 63) // 64
+        gray, depth, mask = (np.concatenate([x] * k)[:n] for x in (gray, depth, mask))
     p = default_params(); p.depth_cov_z0 = 2.0; p.max_keypoints = 1000
     fe = Frontend(0, p)
-    det = fe.detector_create()
-    ts = []
-    for it in range(4):
-        t0 = time.perf_counter()
-        h, nf = fe.nodes_create(det, gray, depth, mask, K4)
-        ts.append(time.perf_counter() - t0)
-        for x in h:
-            fe.node_destroy(x)
-    out["orb"] = {"frames": n, "frames_per_s": n / min(ts[1:]), "mean_features": float(np.mean(nf))}
+    res = {}
+    pin = [torch.from_numpy(x).pin_memory() for x in (gray, depth, mask)]
+    for name, args, kw in (("pageable_mask", (gray, depth, mask), {}), ("pinned_mask", tuple(pin), {}),
+                           ("pinned_mask_from_depth", (pin[0], pin[1], None), {"mask_from_depth": True})):
+        det = fe.detector_create()
+        ts = []
+        for it in range(reps):
+            t0 = time.perf_counter()
+            h, nf = fe.nodes_create(det, *args, K4, **kw)
+            ts.append(time.perf_counter() - t0)
+            for x in h:
+                fe.node_destroy(x)
+        fe.detector_destroy(det)
+        res[name] = n / min(ts[1:]) if len(ts) > 1 else n / ts[0]
+    out["orb"] = {"frames": n, "frames_per_s": res, "mean_features": float(np.mean(nf))}
     fe.close()
 
 if "sift" in which:
