@@ -316,6 +316,132 @@ def bench_posegraph(fe):
             "sample_1000V_6000E": {"gpu_seconds": dts, "cpu_oracle_seconds": dto, "cpu_threads": 1}}
 
 
+C4_FRAMES = 2000
+C4_SEED = 11
+
+
+def bench_sequence(fe, local_rank, rank, world, comm, n_frames=C4_FRAMES, with_oracle=False, oracle_frames=120):
+    """BASELINE config C4: a 2000-frame synthetic sequence end to end through the C ABI -- pinned HOST images in,
+    optimised trajectory out: Node::Node for every frame (rgbdslam_b200_nodes_create_ex), the 3 sequential + 4 window +
+    4 random candidate pairs per frame (~22 k pairs) through Node::matchNodePair in batches of 256 on the pipeline slots,
+    (N > 1: frames and pairs sharded over the ranks, ONE all-gather of the edge records), addEdgeToG2O glue, optimizeGraph
+    on every rank, ATE against the rendering ground truth.  Strong scaling: the work is fixed as N grows."""
+    import torch
+    from rgbdslam_v2_b200 import pipeline, synth
+    from rgbdslam_v2_b200._capi import PAIR_RESULT_DTYPE, default_params
+    import ctypes as C
+    dev = torch.device("cuda", local_rank)
+    poses = synth.trajectory(n_frames)
+    K4 = (synth.FX, synth.FY, synth.CX, synth.CY)
+    prm = default_params(); prm.depth_cov_z0 = 2.0; prm.max_keypoints = N_KP
+    old = fe.params
+    fe.params = prm
+    fe._check(fe.lib.rgbdslam_b200_init(local_rank, C.byref(prm)))
+    out = {"workload": f"C4: {n_frames}-frame synthetic sequence 640x480 (torch-rendered box room, trajectory with revisits), "
+                       f"max_keypoints {N_KP}, candidates 3 sequential + 4 window + 4 random per frame, pose_relative_to first, "
+                       f"optimizer_iterations 0.01", "n_gpus": world}
+    try:
+        # ---- data (not timed): this rank's frames rendered on its GPU, copied to pinned host memory
+        per = -(-n_frames // world)
+        f0, f1 = (0, n_frames) if world == 1 else (min(rank * per, n_frames), min((rank + 1) * per, n_frames))
+        g_d, d_d = synth.render_frames_torch(poses[f0:f1], dev, first_index=f0)
+        gray = torch.empty(g_d.shape, dtype=torch.uint8).pin_memory(); gray.copy_(g_d)
+        depth = torch.empty(d_d.shape, dtype=torch.float32).pin_memory(); depth.copy_(d_d)
+        del g_d, d_d
+        torch.cuda.synchronize()
+        pairs = np.array(pipeline.candidate_pairs(n_frames, seed=C4_SEED), np.int64)
+        gt = np.stack([pipeline.mat_to_pose7(np.linalg.inv(poses[0]) @ P) for P in poses])
+
+        def run(nf):
+            """frames [0, nf) (own shard of them) -> trajectory; returns (traj, stage seconds, info)"""
+            t = {}
+            if world > 1:
+                torch.distributed.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            det = fe.detector_create()
+            if world == 1:
+                handles, nfeat = fe.nodes_create(det, gray[:nf], depth[:nf], None, K4, ids=np.arange(nf, dtype=np.int32),
+                                                 mask_from_depth=True)
+            else:
+                handles, nfeat = fe.nodes_create_sharded(det, comm, nf, gray, depth, None, K4, mask_from_depth=True)
+            t["nodes"] = time.perf_counter() - t0
+            pp = pairs[pairs[:, 0] < nf]
+            per_p = -(-len(pp) // world)
+            p0, p1 = min(rank * per_p, len(pp)), min((rank + 1) * per_p, len(pp))
+            t1 = time.perf_counter()
+            local = np.zeros(per_p, PAIR_RESULT_DTYPE); local["id1"] = -1; local["id2"] = -1
+            pipeline.match_pairs_pipelined(fe, handles, pp[p0:p1], seed=C4_SEED, first_pair_index=p0, out=local[: p1 - p0])
+            t["match"] = time.perf_counter() - t1
+            t2 = time.perf_counter()
+            if world > 1:
+                res = fe.allgather_edges(comm, local, world)[: len(pp)]  # the ONE exchange of the pair stage (SURVEY 8e)
+            else:
+                res = local[: len(pp)]
+            t["gather"] = time.perf_counter() - t2
+            t3 = time.perf_counter()
+            graph = pipeline.build_graph_fast(pp, res, nf)
+            t["graph_host"] = time.perf_counter() - t3
+            t4 = time.perf_counter()
+            traj, chi2, lm, cg = fe.optimize_graph(graph["init"], graph["fixed"], graph["ij"], graph["meas"], graph["info"], stop=0.01)
+            t["solve"] = time.perf_counter() - t4
+            t["total"] = time.perf_counter() - t0
+            info = dict(pairs=int(len(pp)), valid_edges=int(graph["n_valid_edges"]), const_edges=int(graph["n_const_edges"]),
+                        mean_features=float(np.mean(nfeat)), lm_iterations=lm, pcg_iterations=cg, chi2=chi2)
+            fe.detector_destroy(det)
+            for h in handles:
+                fe.node_destroy(h)
+            return traj, t, info, res
+
+        run(min(n_frames, 96 * world))  # warm-up (allocations, first launches)
+        traj, t, info, _ = run(n_frames)
+        tt = torch.tensor([t[k] for k in ("nodes", "match", "gather", "graph_host", "solve", "total")], dtype=torch.float64, device=dev)
+        if world > 1:
+            torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
+        tt = tt.tolist()
+        out.update(info)
+        out["seconds"] = dict(zip(("nodes", "match", "gather", "graph_host", "solve", "total"), tt))
+        out["frames_per_s"] = n_frames / tt[5]
+        out["pairs_per_s"] = info["pairs"] / tt[5]
+        out["node_constructor_frames_per_s"] = n_frames / tt[0]
+        out["match_stage_pairs_per_s"] = info["pairs"] / tt[1]
+        out["ate_vs_gt_m"] = synth.ate_rmse(traj[:, :3], gt[:, :3])
+        out["h2d_bytes"] = int(n_frames * synth.W * synth.H * 5)
+        out["scaling"] = "strong (fixed 2000 frames / pair list)"
+        if with_oracle and world == 1 and rank == 0:
+            # the same pipeline on the CPU oracle (cv2 ORB + C port) on a prefix of the sequence: ATE of both against the
+            # ground truth and against each other (north star: within 1 mm), and the CPU frames/s of the whole chain
+            from oracle import oracle
+            from oracle.backend import OracleBackend
+            from oracle import orb_oracle
+            nf = oracle_frames
+            g_traj, _, g_info, g_res = run(nf)
+            gn, dn = gray[:nf].numpy(), depth[:nf].numpy()
+            mn = np.stack([orb_oracle.depth_to_mask(d) for d in dn])
+            ob = OracleBackend(oracle, N_KP)
+            c0 = time.perf_counter()
+            nodes = ob.construct_nodes(gn, dn, mn, K4)
+            c1 = time.perf_counter()
+            pp = pairs[pairs[:, 0] < nf]
+            ores = ob.match(nodes, [tuple(x) for x in pp], C4_SEED)
+            c2 = time.perf_counter()
+            ograph = pipeline.build_graph_fast(pp, ores, nf)
+            o_traj, o_chi2 = ob.optimize(ograph, 0.01)
+            c3 = time.perf_counter()
+            out["oracle_prefix"] = {
+                "frames": nf, "pairs": int(len(pp)),
+                "ate_gpu_vs_gt_m": synth.ate_rmse(g_traj[:, :3], gt[:nf, :3]), "ate_oracle_vs_gt_m": synth.ate_rmse(o_traj[:, :3], gt[:nf, :3]),
+                "ate_gpu_vs_oracle_m": synth.ate_rmse(g_traj[:, :3], o_traj[:, :3]),
+                "valid_flag_agreement": float(((g_res["id1"] >= 0) == (ores["id1"] >= 0)).mean()),
+                "cpu_seconds": {"nodes_cv2": c1 - c0, "match_port": c2 - c1, "graph_and_solve": c3 - c2},
+                "cpu_frames_per_s": nf / (c3 - c0), "cpu_threads": usable_cpus(),
+                "note": "oracle = cv2 ORB + reference glue + C port of matching / RANSAC / LM on the first frames of the same sequence"}
+    finally:
+        fe.params = old
+        fe._check(fe.lib.rgbdslam_b200_init(local_rank, C.byref(old)))
+    return out
+
+
 def run_ours(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
@@ -472,6 +598,15 @@ def run_ours(args, rank, local_rank, world):
     clocks = sampler.stop() if rank == 0 else None
     del flush
 
+    c4 = None
+    if not args.no_c4:
+        try:
+            c4 = bench_sequence(fe, local_rank, rank, world, comm, n_frames=args.c4_frames,
+                                with_oracle=(world == 1 and not args.no_cpu_baseline))
+        except Exception as ex:  # secondary measurements must never hide the headline line
+            import traceback
+            c4 = {"error": repr(ex), "trace": traceback.format_exc()[-800:]}
+
     if rank == 0:
         value = world * PAIRS_PER_GPU * args.steps / (total_ms * 1e-3)
         e2e_value = world * PAIRS_PER_GPU * args.steps / e2e_total
@@ -509,6 +644,7 @@ def run_ours(args, rank, local_rank, world):
             "synchronous": {"value": PAIRS_PER_GPU / (statistics.mean(sync_ms) * 1e-3), "ms_per_step": statistics.mean(sync_ms),
                             "device_ms_per_step": statistics.mean(sync_dev), "note": "one batch at a time, L2 flushed, rank 0"},
         }
+        out["c4"] = c4
         if world == 1 and not args.no_cpu_baseline:
             try:
                 out["node_create"] = bench_node_create(fe)
@@ -542,6 +678,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c4", action="store_true", help="skip the 2000-frame sequence (config C4) sub-measurement")
+    ap.add_argument("--c4-frames", type=int, default=C4_FRAMES)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

@@ -8,25 +8,14 @@
 #include <cstring>
 #include <mutex>
 
+#include "comm.h"
 #include "state.h"
 
 namespace rb200 {
 
-typedef struct ncclComm* ncclComm_t;
-typedef struct { char internal[128]; } ncclUniqueId;
-typedef int ncclResult_t;
+NcclApi g_nccl;
 
-struct NcclApi {
-  bool ok = false;
-  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
-  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
-  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
-  ncclResult_t (*AllGather)(const void*, void*, size_t, int /*ncclDataType_t*/, ncclComm_t, cudaStream_t) = nullptr;
-  const char* (*GetErrorString)(ncclResult_t) = nullptr;
-};
-static NcclApi g_nccl;
-
-static int load_nccl() {
+int load_nccl() {
   if (g_nccl.ok) return 0;
   void* h = RTLD_DEFAULT;
   if (!dlsym(h, "ncclAllGather")) {
@@ -49,20 +38,10 @@ static int load_nccl() {
   return 0;
 }
 
-static int nccl_fail(ncclResult_t r, const char* what) {
+int nccl_fail(ncclResult_t r, const char* what) {
   set_error(std::string("NCCL error in ") + what + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
   return RGBDSLAM_B200_ERR_NCCL;
 }
-
-struct Comm {
-  static constexpr uint32_t kMagic = 0x434f4d4du;
-  uint32_t magic = kMagic;
-  ncclComm_t comm = nullptr;
-  int rank = 0, world = 1;
-  DevBuf send, recv;
-  cudaStream_t gstream = nullptr;        // the collectives of in-flight slots, in submission order
-  DevBuf slot_recv[kSlots];
-};
 
 }  // namespace rb200
 

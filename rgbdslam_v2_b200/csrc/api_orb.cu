@@ -41,12 +41,12 @@ struct OrbCtx {
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
   DevBuf cell_img, cell_mask, score, cand, cand_count, hist, mask_any, thr, resp, cell_out, cell_out_count, scratch, kp, xyz, n,
-      pyr_raw, pyr_blur, desc, err;
+      pyr_raw, pyr_blur, desc, err, trig;
   const uint8_t* last_gray = nullptr;  // device pointers of frame 0 of the last call (debug hooks)
   void release() {
     DevBuf* all[] = {&d_ofs, &d_w1, &in_gray[0], &in_gray[1], &in_mask[0], &in_mask[1], &in_depth[0], &in_depth[1], &cell_img,
                      &cell_mask, &score, &cand, &cand_count, &hist, &mask_any, &thr, &resp, &cell_out, &cell_out_count, &scratch,
-                     &kp, &xyz, &n, &pyr_raw, &pyr_blur, &desc, &err};
+                     &kp, &xyz, &n, &pyr_raw, &pyr_blur, &desc, &err, &trig};
     for (DevBuf* b : all) b->release();
     stage[0].release();
     stage[1].release();
@@ -212,7 +212,7 @@ static int orb_prepare(int W, int H, int nframes_hint) {
   return 0;
 }
 
-constexpr int kOrbChunk = 32;  // frames per pass of nodes_create
+constexpr int kOrbChunk = 64;  // frames per pass of nodes_create
 
 static int orb_ensure_streams() {
   OrbCtx& o = g_orb;
@@ -245,7 +245,8 @@ static int orb_ensure_buffers(int F, int nbuf, bool want_mask) {
       (rc = o.kp.ensure((size_t)F * o.kp_stride * sizeof(rgbdslam_b200_keypoint))) ||
       (rc = o.xyz.ensure((size_t)F * o.kp_stride * 16)) || (rc = o.n.ensure((size_t)F * 4)) ||
       (rc = o.pyr_raw.ensure((size_t)g.full_bytes * F)) || (rc = o.pyr_blur.ensure((size_t)g.full_bytes * F)) ||
-      (rc = o.desc.ensure((size_t)F * o.kp_stride * 32)) || (rc = o.err.ensure(16)))
+      (rc = o.desc.ensure((size_t)F * o.kp_stride * 32)) || (rc = o.err.ensure(16)) ||
+      (rc = o.trig.ensure((size_t)F * o.kp_stride * 8)))
     return rc;
   return 0;
 }
@@ -375,7 +376,8 @@ int rgbdslam_b200_orb_detect(uint64_t detector, const uint8_t* gray, const uint8
   e = orb_run_select(o.g, 1, 0, o.max_per_cell, g_state.params.max_keypoints, (const uint8_t*)o.cell_img.ptr,
                      (const OrbCand*)o.cand.ptr, (const int*)o.cand_count.ptr, (const int*)o.thr.ptr, (float*)o.resp.ptr,
                      (unsigned long long*)o.cell_out.ptr, (int*)o.cell_out_count.ptr, nullptr, 1.f, make_float4(0, 0, 0, 0),
-                     o.scratch.ptr, (rgbdslam_b200_keypoint*)o.kp.ptr, (float4*)o.xyz.ptr, (int*)o.n.ptr, o.kp_stride, st, &launches);
+                     o.scratch.ptr, (rgbdslam_b200_keypoint*)o.kp.ptr, (float4*)o.xyz.ptr, nullptr, (int*)o.n.ptr, o.kp_stride, st,
+                     &launches);
   if (e != cudaSuccess) return cuda_fail(e, "orb select kernels");
   int n = 0, flag = 0;
   e = cudaMemcpyAsync(&n, o.n.ptr, 4, cudaMemcpyDeviceToHost, st);
@@ -431,7 +433,7 @@ int rgbdslam_b200_orb_compute(const uint8_t* gray, int w, int h, const rgbdslam_
   if (e == cudaSuccess) e = cudaMemcpyAsync(o.n.ptr, &n, 4, cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess)
     e = orb_run_describe(o.g, o.tab, 1, (const uint8_t*)o.in_gray[0].ptr, (uint8_t*)o.pyr_raw.ptr, (uint8_t*)o.pyr_blur.ptr,
-                         (const rgbdslam_b200_keypoint*)dk.ptr, (const int*)o.n.ptr, n, n, (uint8_t*)dd.ptr, st, &launches);
+                         (const rgbdslam_b200_keypoint*)dk.ptr, (const int*)o.n.ptr, n, n, nullptr, (uint8_t*)dd.ptr, st, &launches);
   if (e == cudaSuccess) e = cudaMemcpyAsync(desc_out, dd.ptr, 32 * (size_t)n, cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   dk.release();
@@ -548,10 +550,10 @@ int rgbdslam_b200_nodes_create_ex(uint64_t detector, int nframes, const uint8_t*
     e = orb_run_select(o.g, F, 1, o.max_per_cell, s.params.max_keypoints, (const uint8_t*)o.cell_img.ptr,
                        (const OrbCand*)o.cand.ptr, (const int*)o.cand_count.ptr, (const int*)o.thr.ptr, (float*)o.resp.ptr,
                        (unsigned long long*)o.cell_out.ptr, (int*)o.cell_out_count.ptr, dd, (float)s.params.depth_scaling_factor, Kinv,
-                       o.scratch.ptr, sl_kp + (size_t)f0 * K, sl_xyz + (size_t)f0 * K, sl_n + f0, K, st, &launches);
+                       o.scratch.ptr, sl_kp + (size_t)f0 * K, sl_xyz + (size_t)f0 * K, (float2*)o.trig.ptr, sl_n + f0, K, st, &launches);
     if (e != cudaSuccess) return fail(cuda_fail(e, "orb select kernels"));
     e = orb_run_describe(o.g, o.tab, F, dg, (uint8_t*)o.pyr_raw.ptr, (uint8_t*)o.pyr_blur.ptr, sl_kp + (size_t)f0 * K, sl_n + f0, K, K,
-                         sl_desc + (size_t)f0 * K * 32, st, &launches);
+                         (const float2*)o.trig.ptr, sl_desc + (size_t)f0 * K * 32, st, &launches);
     if (e != cudaSuccess) return fail(cuda_fail(e, "orb describe kernels"));
     {
       e = launch_expand_i8_strided(sl_desc + (size_t)f0 * K * 32, sl_i8 + (size_t)f0 * Kpad * 256, sl_n + f0, F, K, Kpad, st);

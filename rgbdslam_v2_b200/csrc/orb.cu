@@ -96,7 +96,8 @@ __global__ void __launch_bounds__(256) k_cell_extract(const uint8_t* __restrict_
     }
     cell_mask[dst] = nz ? 255 : 0;
   }
-  if (__any_sync(0xffffffffu, nz) && (threadIdx.x & 31) == 0) mask_any[blockIdx.z] = 1;
+  // one (conditional) flag write per CTA: thousands of warps storing to the same word serialise in L2
+  if (__syncthreads_or(nz) && threadIdx.x == 0 && mask_any[blockIdx.z] == 0) mask_any[blockIdx.z] = 1;
 }
 
 // dst plane = INTER_LINEAR_EXACT resize of the previous level (8.8 fixed-point taps, round to nearest at the end).
@@ -672,35 +673,52 @@ __global__ void __launch_bounds__(1024)
     __syncthreads();
     bitonic_sort_u64(keys, N);
   }
-  // E. emit in final order; orientation by one warp per keypoint on the detector's (cell) pyramid
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  for (int t = warp; t < n_final; t += nwarps) {
-    const FrameKp q = kc[keys[t] & 0xFFFFu];
-    const OrbPlane& p = c_geom.cell[q.cell][q.level];
-    const float ang = ic_angle_warp(cell_img + (size_t)f * c_geom.cell_bytes + p.off, p.w, q.lx, q.ly, lane);
-    if (lane == 0) {
-      rgbdslam_b200_keypoint o;
-      o.x = q.x;
-      o.y = q.y;
-      o.size = __fmul_rn(31.f, p.scale);
-      o.angle = ang;
-      o.response = q.resp;
-      o.octave = q.level;
-      o.class_id = -1;
-      kp_out[(size_t)f * kp_stride + t] = o;
-      if (mode == 1) {  // projectTo3D (node.cpp:900-965) + backProject (misc2.h:49-65)
-        const int rx = (int)floorf(q.x + 0.5f), ry = (int)floorf(q.y + 0.5f);
-        const float Z = (float)((double)depth[(size_t)f * W * H + (size_t)ry * W + rx] * (double)depth_scaling);
-        float4 v;
-        v.x = __fmul_rn(__fmul_rn(__fsub_rn(q.x, Kinv.z), Z), Kinv.x);
-        v.y = __fmul_rn(__fmul_rn(__fsub_rn(q.y, Kinv.w), Z), Kinv.y);
-        v.z = Z;
-        v.w = 1.f;
-        xyz_out[(size_t)f * kp_stride + t] = v;
+  // E. hand the final order to k_frame_emit (one warp per keypoint across the whole grid: orientation, cv::KeyPoint,
+  //    projectTo3D); the gather-order half of the scratch is free by now and receives the 16-bit indices into kc
+  uint16_t* ord = reinterpret_cast<uint16_t*>(ka);
+  for (int t = threadIdx.x; t < n_final; t += blockDim.x) ord[t] = (uint16_t)(keys[t] & 0xFFFFu);
+  if (threadIdx.x == 0) n_out[f] = n_final;
+}
+
+// One warp per output keypoint: intensity-centroid orientation on the detector's (cell) pyramid, the cv::KeyPoint record,
+// in mode 1 projectTo3D (node.cpp:900-965) + backProject (misc2.h:49-65) and the rotation (cos, sin) compute() will use.
+__global__ void __launch_bounds__(256)
+    k_frame_emit(int mode, const FrameKp* __restrict__ scratch, const uint8_t* __restrict__ cell_img, const float* __restrict__ depth,
+                 float depth_scaling, float4 Kinv, rgbdslam_b200_keypoint* __restrict__ kp_out, float4* __restrict__ xyz_out,
+                 float2* __restrict__ trig_out, const int* __restrict__ n_out, int kp_stride) {
+  const int f = blockIdx.y;
+  const int t = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (t >= n_out[f]) return;
+  const int W = c_geom.W, H = c_geom.H;
+  const FrameKp* ka = scratch + (size_t)f * 2 * kFrameCap;
+  const FrameKp q = (ka + kFrameCap)[reinterpret_cast<const uint16_t*>(ka)[t]];
+  const OrbPlane& p = c_geom.cell[q.cell][q.level];
+  const float ang = ic_angle_warp(cell_img + (size_t)f * c_geom.cell_bytes + p.off, p.w, q.lx, q.ly, lane);
+  if (lane == 0) {
+    rgbdslam_b200_keypoint o;
+    o.x = q.x;
+    o.y = q.y;
+    o.size = __fmul_rn(31.f, p.scale);
+    o.angle = ang;
+    o.response = q.resp;
+    o.octave = q.level;
+    o.class_id = -1;
+    kp_out[(size_t)f * kp_stride + t] = o;
+    if (mode == 1) {
+      const int rx = (int)floorf(q.x + 0.5f), ry = (int)floorf(q.y + 0.5f);
+      const float Z = (float)((double)depth[(size_t)f * W * H + (size_t)ry * W + rx] * (double)depth_scaling);
+      float4 v;
+      v.x = __fmul_rn(__fmul_rn(__fsub_rn(q.x, Kinv.z), Z), Kinv.x);
+      v.y = __fmul_rn(__fmul_rn(__fsub_rn(q.y, Kinv.w), Z), Kinv.y);
+      v.z = Z;
+      v.w = 1.f;
+      xyz_out[(size_t)f * kp_stride + t] = v;
+      if (trig_out) {  // angle *= (float)(CV_PI/180.f); a = (float)cos(angle), b = (float)sin(angle)  (cv::ORB computeOrbDescriptors)
+        const float ar = __fmul_rn(ang, 0.017453292519943295f);
+        trig_out[(size_t)f * kp_stride + t] = make_float2((float)cos((double)ar), (float)sin((double)ar));
       }
     }
   }
-  if (threadIdx.x == 0) n_out[f] = n_final;
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -716,32 +734,35 @@ __global__ void __launch_bounds__(256) k_blur(const uint8_t* __restrict__ src, u
                                               int level) {
   const OrbPlane& p = c_geom.full[level];
   const int f = blockIdx.z;
-  __shared__ float rows[22][32];  // 16 output rows + 6 halo rows, 32 columns
+  const int pw = p.w, ph = p.h;
+  __shared__ float tile[22][40];  // 16 output rows + 6 halo rows, 32 output columns + 6 halo columns, as float (reflect-101 applied)
+  __shared__ float rows[22][32];  // row-pass results
   const uint8_t* im = src + (size_t)f * frame_stride + p.off;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
-  const int x = blockIdx.x * 32 + tx, y0 = blockIdx.y * 16;
+  const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 16;
+  for (int i = threadIdx.x; i < 22 * 38; i += 256) {
+    const int r = i / 38, c = i - r * 38;
+    const int xx = reflect101(min(x0 + c - 3, pw + 2), pw), yy = reflect101(min(y0 + r - 3, ph + 2), ph);
+    tile[r][c] = (float)im[yy * pw + xx];
+  }
+  __syncthreads();
   for (int r = ty; r < 22; r += 8) {
-    const int yy = reflect101(y0 + r - 3, p.h);
     float acc = 0.f;
-    if (x < p.w) {
 #pragma unroll
-      for (int j = 0; j < 7; j++) {
-        const int xx = reflect101(x + j - 3, p.w);
-        acc = __fadd_rn(acc, __fmul_rn(c_gauss[j], (float)im[yy * p.w + xx]));
-      }
-    }
+    for (int j = 0; j < 7; j++) acc = __fadd_rn(acc, __fmul_rn(c_gauss[j], tile[r][tx + j]));  // left to right, as cv::sepFilter2D
     rows[r][tx] = acc;
   }
   __syncthreads();
+  const int x = x0 + tx;
   for (int r = ty; r < 16; r += 8) {
     const int y = y0 + r;
-    if (x < p.w && y < p.h) {
+    if (x < pw && y < ph) {
       float c = __fmul_rn(c_gauss[3], rows[r + 3][tx]);
 #pragma unroll
       for (int j = 1; j <= 3; j++) c = __fadd_rn(c, __fmul_rn(c_gauss[3 + j], __fadd_rn(rows[r + 3 + j][tx], rows[r + 3 - j][tx])));
       int v = __float2int_rn(c);
       v = min(max(v, 0), 255);
-      dst[(size_t)f * frame_stride + p.off + (size_t)y * p.w + x] = (uint8_t)v;
+      dst[(size_t)f * frame_stride + p.off + (size_t)y * pw + x] = (uint8_t)v;
     }
   }
 }
@@ -750,7 +771,8 @@ __global__ void __launch_bounds__(256) k_blur(const uint8_t* __restrict__ src, u
 // from the UNBLURRED level with reflect-101 (OpenCV blurs only the level ROI of its bordered pyramid buffer).
 __global__ void __launch_bounds__(256) k_describe(const uint8_t* __restrict__ pyr_raw, const uint8_t* __restrict__ pyr_blur,
                                                   int frame_stride, const rgbdslam_b200_keypoint* __restrict__ kps,
-                                                  const int* __restrict__ n_kp, int kp_stride, uint8_t* __restrict__ desc) {
+                                                  const int* __restrict__ n_kp, int kp_stride, const float2* __restrict__ trig,
+                                                  uint8_t* __restrict__ desc) {
   const int f = blockIdx.y;
   const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -759,8 +781,16 @@ __global__ void __launch_bounds__(256) k_describe(const uint8_t* __restrict__ py
   const OrbPlane& p = c_geom.full[kp.octave];
   const float sinv = __fdiv_rn(1.f, p.scale);
   const int cx = __float2int_rn(__fmul_rn(kp.x, sinv)), cy = __float2int_rn(__fmul_rn(kp.y, sinv));
-  const float ang = __fmul_rn(kp.angle, 0.017453292519943295f);  // angle *= (float)(CV_PI/180.f)
-  const float a = (float)cos((double)ang), b = (float)sin((double)ang);
+  float a, b;
+  if (trig) {  // rotation written by k_frame_emit (once per keypoint instead of once per lane)
+    const float2 cs = trig[(size_t)f * kp_stride + i];
+    a = cs.x;
+    b = cs.y;
+  } else {
+    const float ang = __fmul_rn(kp.angle, 0.017453292519943295f);  // angle *= (float)(CV_PI/180.f)
+    a = (float)cos((double)ang);
+    b = (float)sin((double)ang);
+  }
   const uint8_t* raw = pyr_raw + (size_t)f * frame_stride + p.off;
   const uint8_t* blr = pyr_blur + (size_t)f * frame_stride + p.off;
   auto pix = [&](int k, int which) -> int {
@@ -849,8 +879,8 @@ cudaError_t orb_run_adapt(const OrbGeom& g, int nframes, const int* d_hist, cons
 cudaError_t orb_run_select(const OrbGeom& g, int nframes, int mode, int max_per_cell, int max_keypoints,
                            const uint8_t* d_cell_img, const OrbCand* d_cand, const int* d_cand_count, const int* d_thr,
                            float* d_resp, unsigned long long* d_cell_out, int* d_cell_out_count, const float* d_depth,
-                           float depth_scaling, float4 Kinv, void* d_scratch, rgbdslam_b200_keypoint* d_kp, float4* d_xyz, int* d_n,
-                           int kp_stride, cudaStream_t st, int* launches) {
+                           float depth_scaling, float4 Kinv, void* d_scratch, rgbdslam_b200_keypoint* d_kp, float4* d_xyz,
+                           float2* d_trig, int* d_n, int kp_stride, cudaStream_t st, int* launches) {
   const int z = nframes * g.ncells;
   k_harris<<<dim3((kOrbCandCap + 255) / 256, z), 256, 0, st>>>(d_cell_img, d_cand, d_cand_count, d_thr, d_resp);
   static bool attr = false;
@@ -862,13 +892,16 @@ cudaError_t orb_run_select(const OrbGeom& g, int nframes, int mode, int max_per_
   k_cell_select<<<z, 1024, 16384 * 8, st>>>(d_cand, d_cand_count, d_resp, max_per_cell, d_cell_out, d_cell_out_count, max_per_cell);
   k_frame_finalize<<<nframes, 1024, 0, st>>>(mode, max_keypoints, d_cell_out, d_cell_out_count, max_per_cell, d_cell_img, d_depth,
                                              depth_scaling, Kinv, (FrameKp*)d_scratch, d_kp, d_xyz, d_n, kp_stride);
-  (*launches) += 3;
+  const int max_out = mode == 1 ? (max_keypoints < kp_stride ? max_keypoints : kp_stride) : kp_stride;
+  k_frame_emit<<<dim3((max_out + 7) / 8, nframes), 256, 0, st>>>(mode, (const FrameKp*)d_scratch, d_cell_img, d_depth, depth_scaling,
+                                                                 Kinv, d_kp, d_xyz, d_trig, d_n, kp_stride);
+  (*launches) += 4;
   return cudaGetLastError();
 }
 
 cudaError_t orb_run_describe(const OrbGeom& g, const OrbTables& tab, int nframes, const uint8_t* d_gray, uint8_t* d_pyr_raw,
                              uint8_t* d_pyr_blur, const rgbdslam_b200_keypoint* d_kp, const int* d_n, int kp_stride, int max_kp,
-                             uint8_t* d_desc, cudaStream_t st, int* launches) {
+                             const float2* d_trig, uint8_t* d_desc, cudaStream_t st, int* launches) {
   // level 0 = the image itself
   cudaError_t e = cudaMemcpy2DAsync(d_pyr_raw, g.full_bytes, d_gray, (size_t)g.W * g.H, (size_t)g.W * g.H, nframes,
                                     cudaMemcpyDeviceToDevice, st);
@@ -881,7 +914,7 @@ cudaError_t orb_run_describe(const OrbGeom& g, const OrbTables& tab, int nframes
     k_blur<<<dim3((g.full[l].w + 31) / 32, (g.full[l].h + 15) / 16, nframes), 256, 0, st>>>(d_pyr_raw, d_pyr_blur, g.full_bytes, l);
     (*launches)++;
   }
-  k_describe<<<dim3((max_kp + 7) / 8, nframes), 256, 0, st>>>(d_pyr_raw, d_pyr_blur, g.full_bytes, d_kp, d_n, kp_stride, d_desc);
+  k_describe<<<dim3((max_kp + 7) / 8, nframes), 256, 0, st>>>(d_pyr_raw, d_pyr_blur, g.full_bytes, d_kp, d_n, kp_stride, d_trig, d_desc);
   (*launches)++;
   return cudaGetLastError();
 }

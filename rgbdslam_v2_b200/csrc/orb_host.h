@@ -25,12 +25,13 @@ cudaError_t orb_run_adapt(const OrbGeom& g, int nframes, const int* d_hist, cons
 cudaError_t orb_run_select(const OrbGeom& g, int nframes, int mode, int max_per_cell, int max_keypoints,
                            const uint8_t* d_cell_img, const OrbCand* d_cand, const int* d_cand_count, const int* d_thr,
                            float* d_resp, unsigned long long* d_cell_out, int* d_cell_out_count, const float* d_depth,
-                           float depth_scaling, float4 Kinv, void* d_scratch, rgbdslam_b200_keypoint* d_kp, float4* d_xyz, int* d_n,
-                           int kp_stride, cudaStream_t st, int* launches);
+                           float depth_scaling, float4 Kinv, void* d_scratch, rgbdslam_b200_keypoint* d_kp, float4* d_xyz,
+                           float2* d_trig /* mode 1: (cos, sin) of every keypoint's orientation for orb_run_describe, may be NULL */,
+                           int* d_n, int kp_stride, cudaStream_t st, int* launches);
 
 cudaError_t orb_run_describe(const OrbGeom& g, const OrbTables& tab, int nframes, const uint8_t* d_gray, uint8_t* d_pyr_raw,
                              uint8_t* d_pyr_blur, const rgbdslam_b200_keypoint* d_kp, const int* d_n, int kp_stride, int max_kp,
-                             uint8_t* d_desc, cudaStream_t st, int* launches);
+                             const float2* d_trig, uint8_t* d_desc, cudaStream_t st, int* launches);
 
 constexpr int kOrbFrameCap = 4096;       // == kFrameCap in orb.cu
 constexpr int kOrbFrameKpBytes = 20;     // sizeof(FrameKp)

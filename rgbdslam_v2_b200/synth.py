@@ -253,6 +253,62 @@ def render_frame(pose_wc: np.ndarray, tex_seed: int = 7, nan_frac: float = 0.03,
     return np.ascontiguousarray(gray), np.ascontiguousarray(depth)
 
 
+def render_frames_torch(poses_wc: np.ndarray, device, first_index: int = 0, tex_seed: int = 7, nan_frac: float = 0.03,
+                        chunk: int = 32):
+    """The scene of render_frame, rendered for many frames on a CUDA device with torch (data generation for the sequence
+    bench: 2000 frames take minutes in numpy).  Same geometry and texture; bilinear texture lookup and the NaN-hole pattern
+    come from torch, so the pixels are NOT bit-identical to render_frame -- every consumer (CUDA path, CPU oracle) must use
+    the same arrays.  The hole pattern of frame k is seeded by first_index + k, i.e. independent of how a sequence is
+    sharded over ranks.  Returns (gray u8 [n,H,W], depth f32 [n,H,W]) torch tensors on `device`."""
+    import torch
+    n = len(poses_wc)
+    dev = torch.device(device)
+    tex = torch.from_numpy(_texture(tex_seed).astype(np.float32)).to(dev)
+    S = tex.shape[0]
+    v, u = torch.meshgrid(torch.arange(H, device=dev, dtype=torch.float64), torch.arange(W, device=dev, dtype=torch.float64),
+                          indexing="ij")
+    rays_c = torch.stack([(u - CX) / FX, (v - CY) / FY, torch.ones_like(u)], -1)  # [H,W,3]
+    planes = [((0, 0, 1.0), 4.0, 0), ((0, 1.0, 0), 1.3, 1), ((-1.0, 0, 0), 3.0, 2), ((1.0, 0, 0), 3.0, 3)]
+    grays, depths = [], []
+    for c0 in range(0, n, chunk):
+        P = torch.from_numpy(np.asarray(poses_wc[c0:c0 + chunk], np.float64)).to(dev)  # [b,4,4]
+        b = P.shape[0]
+        R, t = P[:, :3, :3], P[:, :3, 3]
+        rays_w = torch.einsum("hwk,bjk->bhwj", rays_c, R)  # rays_c @ R^T
+        best = torch.full((b, H, W), float("inf"), device=dev, dtype=torch.float64)
+        tu = torch.zeros_like(best); tv = torch.zeros_like(best); tid = torch.zeros_like(best)
+        for nrm, d, pid in planes:
+            nv = torch.tensor(nrm, device=dev, dtype=torch.float64)
+            denom = rays_w @ nv
+            denom = torch.where(denom.abs() < 1e-9, torch.full_like(denom, 1e-9), denom)
+            lam = (d - t @ nv)[:, None, None] / denom
+            ok = (lam > 0.3) & (lam < best)
+            Pw = t[:, None, None, :] + rays_w * lam[..., None]
+            if pid == 0: a, bb = Pw[..., 0], Pw[..., 1]
+            elif pid == 1: a, bb = Pw[..., 0], Pw[..., 2]
+            else: a, bb = Pw[..., 2], Pw[..., 1]
+            best = torch.where(ok, lam, best); tu = torch.where(ok, a, tu); tv = torch.where(ok, bb, tv)
+            tid = torch.where(ok, torch.full_like(tid, float(pid)), tid)
+        mapx = torch.remainder(tu * 110.0 + 37.0 * tid + 4000.0, S - 1)
+        mapy = torch.remainder(tv * 110.0 + 91.0 * tid + 4000.0, S - 1)
+        x0 = mapx.floor().long().clamp_(0, S - 2); y0 = mapy.floor().long().clamp_(0, S - 2)
+        fx = (mapx - x0).float(); fy = (mapy - y0).float()
+        t00 = tex[y0, x0]; t01 = tex[y0, x0 + 1]; t10 = tex[y0 + 1, x0]; t11 = tex[y0 + 1, x0 + 1]
+        g = (t00 * (1 - fx) + t01 * fx) * (1 - fy) + (t10 * (1 - fx) + t11 * fx) * fy
+        gray = g.round().clamp_(0, 255).to(torch.uint8)
+        depth = best.float()
+        depth[~torch.isfinite(depth)] = float("nan")
+        for k in range(b):
+            gen = torch.Generator(device=dev)
+            gen.manual_seed(1000003 * (first_index + c0 + k) + 17)
+            holes = torch.rand((H // 8, W // 8), device=dev, generator=gen) < nan_frac
+            holes = holes.repeat_interleave(8, 0).repeat_interleave(8, 1)
+            speck = torch.rand((H, W), device=dev, generator=gen) < nan_frac / 3
+            depth[k][holes | speck] = float("nan")
+        grays.append(gray); depths.append(depth)
+    return torch.cat(grays), torch.cat(depths)
+
+
 def trajectory(n: int, seed: int = 0) -> np.ndarray:
     """Smooth camera-to-world poses [n,4,4]: Lissajous translation + yaw/pitch sweep that revisits places."""
     s = np.linspace(0, 2 * np.pi, n, endpoint=False)

@@ -73,3 +73,28 @@ def test_save_trajectory_roundtrip(tmp_path):
     pipeline.save_trajectory(str(f), poses, np.array([1.0, 1.5]))
     rows = np.loadtxt(str(f), comments="#")
     assert rows.shape == (2, 8) and np.allclose(rows[:, 1:], poses, atol=1e-6) and np.allclose(rows[:, 0], [1.0, 1.5])
+
+
+def test_build_graph_fast_equals_build_graph():
+    """the vectorised graph builder of the long-sequence path == the reference-order loop"""
+    from rgbdslam_v2_b200 import pipeline
+    from rgbdslam_v2_b200._capi import PAIR_RESULT_DTYPE
+    rng = np.random.default_rng(4)
+    n = 60
+    pairs = pipeline.candidate_pairs(n, seed=2)
+    res = np.zeros(len(pairs), PAIR_RESULT_DTYPE)
+    for i, (a, b) in enumerate(pairs):
+        ok = rng.random() < (0.9 if a - b <= 3 else 0.4)
+        if a == 17 or a == 30:
+            ok = False  # frames without any edge -> constant-position edge
+        res[i]["id1"], res[i]["id2"] = (b, a) if ok else (-1, -1)
+        ang = rng.normal() * 0.05
+        T = np.eye(4); T[:3, :3] = [[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1]]; T[:3, 3] = rng.normal(size=3) * 0.1
+        res[i]["ransac_trafo"] = T.T.reshape(-1).astype(np.float32)
+        res[i]["n_inliers"] = rng.integers(20, 40)  # ties are frequent: the FIRST maximum must win
+        res[i]["info_scale"] = rng.uniform(10, 500)
+    a = pipeline.build_graph(pairs, res, n)
+    b = pipeline.build_graph_fast(np.array(pairs), res, n)
+    for k in ("init", "fixed", "ij", "meas", "info"):
+        assert np.array_equal(a[k], b[k]), k
+    assert a["n_const_edges"] == b["n_const_edges"] and a["n_valid_edges"] == b["n_valid_edges"]
