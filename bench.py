@@ -328,7 +328,7 @@ def bench_sequence(fe, local_rank, rank, world, comm, n_frames=C4_FRAMES, with_o
     on every rank, ATE against the rendering ground truth.  Strong scaling: the work is fixed as N grows."""
     import torch
     from rgbdslam_v2_b200 import pipeline, synth
-    from rgbdslam_v2_b200._capi import PAIR_RESULT_DTYPE, default_params
+    from rgbdslam_v2_b200._capi import PAIR_RESULT_DTYPE, default_params, graph_from_pairs
     import ctypes as C
     dev = torch.device("cuda", local_rank)
     poses = synth.trajectory(n_frames)
@@ -380,7 +380,7 @@ def bench_sequence(fe, local_rank, rank, world, comm, n_frames=C4_FRAMES, with_o
                 res = local[: len(pp)]
             t["gather"] = time.perf_counter() - t2
             t3 = time.perf_counter()
-            graph = pipeline.build_graph_fast(pp, res, nf)
+            graph = graph_from_pairs(pp, res, nf)  # host glue of the C ABI (addEdgeToG2O bookkeeping)
             t["graph_host"] = time.perf_counter() - t3
             t4 = time.perf_counter()
             traj, chi2, lm, cg = fe.optimize_graph(graph["init"], graph["fixed"], graph["ij"], graph["meas"], graph["info"], stop=0.01)

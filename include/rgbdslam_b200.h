@@ -297,6 +297,19 @@ int rgbdslam_b200_nodes_create(uint64_t detector, int nframes, const uint8_t* gr
 int rgbdslam_b200_nodes_create_ex(uint64_t detector, int nframes, const uint8_t* gray, const float* depth, const uint8_t* mask,
                                   int w, int h, const float* K4, const int32_t* ids, int flags, uint64_t* node_handles,
                                   int32_t* n_features);
+/* The same for a sequence whose frames are SHARDED over the ranks of a communicator (one process per GPU; BASELINE config C4):
+ * rank r passes only its own frames [r * per, min((r + 1) * per, total_frames)), per = ceil(total_frames / world), in order.
+ * The reference's detector makes frames sequentially dependent -- the adaptive FAST threshold of every grid cell persists
+ * from frame to frame (feature_adjuster.cpp:131-150) -- but only through the number of corners above a threshold: ranks
+ * detect their frames without a threshold (corner score histograms), all-gather the histograms (NCCL), EVERY rank replays the
+ * threshold recurrence of the whole sequence (:185-224) and finishes its own frames with exactly the thresholds one process
+ * would have used; the finished features (descriptors, 3-D points, counts) are all-gathered so that every rank holds every
+ * node.  node_handles / n_features / ids: total_frames entries.  Bit-identical to rgbdslam_b200_nodes_create_ex on one GPU
+ * (2-D keypoints, which only the pairwise g2o refinement reads, stay on the rank that built the node).  Collective: every
+ * rank of the communicator must call it with the same total_frames and parameters. */
+int rgbdslam_b200_nodes_create_sharded(uint64_t detector, uint64_t comm_handle, int total_frames, const uint8_t* gray,
+                                       const float* depth, const uint8_t* mask, int w, int h, const float* K4, const int32_t* ids,
+                                       int flags, uint64_t* node_handles, int32_t* n_features);
 /* Inspection hook: FAST/NMS candidates {u16 x, u16 y, u8 level, u8 score, u16 0} and Harris responses (NaN = below
  * the cell's final threshold) of grid cell `cell` in frame 0 of the last detect / nodes_create call. */
 int rgbdslam_b200_orb_debug_candidates(int cell, void* cand_out, float* resp_out, int capacity, int* n_out, int* thr_out);
@@ -344,6 +357,16 @@ int rgbdslam_b200_allgather_slot_edges(uint64_t comm, int slot, int n_per_rank, 
 int rgbdslam_b200_posegraph_optimize(int nv, double* poses, const uint8_t* fixed, int ne, const int32_t* ij,
                                      const double* meas, const double* info, double stop, double huber_delta,
                                      double* chi2, int* iters, int* cg_iters);
+/* Host glue (no device work): what GraphManager::nodeComparisons + addEdgeToG2O (graph_manager.cpp:550-583, 636-655,
+ * 811-898) do with the MatchingResults of a new node, for an OFFLINE candidate list (no Dijkstra feedback).
+ * pairs: n_pairs x (newer, older) frame indices grouped by ascending newer frame, results aligned with them.  Per new frame:
+ * every valid result becomes an edge (older -> newer, measurement = ransac_trafo, information = I6 * info_scale); the vertex
+ * estimate is v_older * T of the first edge and is replaced whenever a later edge has strictly more inliers; without an edge
+ * to the predecessor a constant-position edge (identity, information I6 / const_edge_dt) is appended.  Vertex 0 is fixed.
+ * Outputs: poses7 n_frames x 7, fixed n_frames, ij / meas7 / info36 with capacity n_pairs + n_frames edges. */
+int rgbdslam_b200_graph_from_pairs(int n_frames, int n_pairs, const int32_t* pairs, const rgbdslam_b200_pair_result* results,
+                                   double const_edge_dt, double* poses7, uint8_t* fixed, int32_t* ij, double* meas7, double* info36,
+                                   int* n_edges, int* n_const_edges);
 /* computeActiveErrors + chi2 (graph_manager.cpp:1002-1003); per_edge_chi2 (ne doubles, may be NULL) is what
  * pruneEdgesWithErrorAbove (graph_manager.cpp:1106-1246) thresholds. */
 int rgbdslam_b200_posegraph_chi2(int nv, const double* poses, int ne, const int32_t* ij, const double* meas,

@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "../rgbdslam_b200.h"
+#include "features.hpp"
 
 namespace rgbdslam_b200 {
 
@@ -37,8 +38,7 @@ struct Matrix6d {
 struct Vector4f {
   float x, y, z, w;
 };
-typedef rgbdslam_b200_dmatch DMatch;      // == cv::DMatch
-typedef rgbdslam_b200_keypoint KeyPoint;  // == cv::KeyPoint
+typedef rgbdslam_b200_dmatch DMatch;  // == cv::DMatch  (KeyPoint: features.hpp)
 
 struct LoadedEdge3D {  // src/edge.h:24-32
   int id1, id2;
@@ -99,6 +99,29 @@ class Node {  // src/node.h: the members the hot path reads + matchNodePair
   std::vector<uint8_t> feature_descriptors_;    // N x 32 (cv::Mat CV_8U rows), node.h:169
 
   Node() {}
+  // The reference's constructor, argument for argument (node.h:64-70, call site openni_listener.cpp:779):
+  //   Node(visual, depth, detection_mask, cam_info, depth_header, detector, extractor)
+  // visual CV_8UC1, depth CV_32FC1 metres (NaN = invalid), detection_mask CV_8UC1 non-zero at potential keypoint locations
+  // (node.h:61-63).  detector / extractor: createDetector / createDescriptorExtractor (features.hpp); the whole constructor
+  // -- detect, removeDepthless, retainBest, compute, projectTo3D -- runs as one rgbdslam_b200_nodes_create call, the
+  // extractor argument only documents the pairing (ORB with ORB).  id_ stays -1 until GraphManager::addNode assigns it.
+  Node(const Mat& visual, const Mat& depth, const Mat& detection_mask, const CameraInfoConstPtr& cam_info, myHeader depth_header,
+       Ptr<Feature2D> detector, Ptr<DescriptorExtractor> extractor)
+      : stamp_(depth_header.stamp) {
+    if (!detector || !detector->handle()) throw std::invalid_argument("Node: detector must come from createDetector(\"ORB\")");
+    if (!extractor) throw std::invalid_argument("Node: null extractor");
+    if (visual.type() != RB_8UC1 || depth.type() != RB_32FC1 || depth.rows != visual.rows || depth.cols != visual.cols)
+      throw std::invalid_argument("Node: visual must be CV_8UC1 and depth CV_32FC1 of the same size");
+    seq_id_ = (int)depth_header.seq;
+    std::vector<uint8_t> tg, tm;
+    std::vector<float> td;
+    const uint8_t* g = detail::packed<uint8_t>(visual, tg);
+    const float* d = detail::packed<float>(depth, td);
+    const uint8_t* m = detection_mask.empty() ? nullptr : detail::packed<uint8_t>(detection_mask, tm);
+    const CameraInfo ci = cam_info ? *cam_info : CameraInfo();
+    const float K4[4] = {(float)ci.K[0], (float)ci.K[4], (float)ci.K[2], (float)ci.K[5]};  // node.cpp:913-916
+    construct(g, d, m, visual.cols, visual.rows, K4, detector->handle());
+  }
   // Node(visual, depth, detection_mask, cam_info, depth_header, detector, extractor) (node.cpp:101-240): detect, filter,
   // describe, back-project on the device; the public feature members are filled from the result.  `detector` is the handle of
   // rgbdslam_b200_detector_create -- the counterpart of the detector_ / extractor_ pair OpenNIListener keeps
@@ -106,16 +129,7 @@ class Node {  // src/node.h: the members the hot path reads + matchNodePair
   Node(const uint8_t* gray, const float* depth_m, const uint8_t* detection_mask, int w, int h, const float K4[4], int id,
        uint64_t detector, double stamp = 0.0)
       : id_(id), stamp_(stamp) {
-    int32_t n = 0, id32 = id < 0 ? 0 : id;
-    check(rgbdslam_b200_nodes_create(detector, 1, gray, depth_m, detection_mask, w, h, K4, &id32, &handle_, &n), "nodes_create");
-    feature_locations_2d_.resize(n);
-    feature_locations_3d_.resize(n);
-    feature_descriptors_.resize((size_t)n * 32);
-    if (n > 0) {
-      check(rgbdslam_b200_node_download_keypoints(handle_, feature_locations_2d_.data()), "node_download_keypoints");
-      check(rgbdslam_b200_node_download(handle_, feature_descriptors_.data(), reinterpret_cast<float*>(feature_locations_3d_.data())),
-            "node_download");
-    }
+    construct(gray, depth_m, detection_mask, w, h, K4, detector);
   }
   // Construct from already extracted features (what the reference ctor node.cpp:101-240 leaves behind).
   Node(int id, const std::vector<uint8_t>& desc, const std::vector<Vector4f>& xyz) : id_(id) {
@@ -128,6 +142,20 @@ class Node {  // src/node.h: the members the hot path reads + matchNodePair
   }
   Node(const Node&) = delete;
   Node& operator=(const Node&) = delete;
+
+  void construct(const uint8_t* gray, const float* depth_m, const uint8_t* detection_mask, int w, int h, const float K4[4],
+                 uint64_t detector) {
+    int32_t n = 0, id32 = id_ < 0 ? 0 : id_;
+    check(rgbdslam_b200_nodes_create(detector, 1, gray, depth_m, detection_mask, w, h, K4, &id32, &handle_, &n), "nodes_create");
+    feature_locations_2d_.resize(n);
+    feature_locations_3d_.resize(n);
+    feature_descriptors_.resize((size_t)n * 32);
+    if (n > 0) {
+      check(rgbdslam_b200_node_download_keypoints(handle_, feature_locations_2d_.data()), "node_download_keypoints");
+      check(rgbdslam_b200_node_download(handle_, feature_descriptors_.data(), reinterpret_cast<float*>(feature_locations_3d_.data())),
+            "node_download");
+    }
+  }
 
   void upload() {
     if (handle_) rgbdslam_b200_node_destroy(handle_);
@@ -155,9 +183,10 @@ class Node {  // src/node.h: the members the hot path reads + matchNodePair
     const int n = (int)older.size();
     std::vector<MatchingResult> out(n);
     if (n == 0) return out;
+    // the match arrays of the C ABI hold params.max_matches entries per pair: ask the library, never assume the default
     rgbdslam_b200_params prm;
-    rgbdslam_b200_default_params(&prm);  // only for max_matches of the output arrays; see max_matches()
-    const int mm = max_matches();
+    if (rgbdslam_b200_get_params(&prm) != 0) return out;  // not initialised: invalid edges, matchNodePair never throws
+    const int mm = prm.max_matches;
     std::vector<uint64_t> a(n, newer->handle_), b(n);
     for (int i = 0; i < n; i++) b[i] = older[i]->handle_;
     std::vector<rgbdslam_b200_pair_result> res(n);
@@ -180,11 +209,6 @@ class Node {  // src/node.h: the members the hot path reads + matchNodePair
 
   static int& max_connections() {  // parameter max_connections (parameter_server.cpp:104), -1 = unlimited
     static int v = -1;
-    return v;
-  }
-
-  static int& max_matches() {  // set once after rgbdslam_b200_init with params.max_matches
-    static int v = 300;
     return v;
   }
 

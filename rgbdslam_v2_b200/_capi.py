@@ -133,6 +133,7 @@ def load_library(path: str | Path | None = None) -> C.CDLL:
     lib.rgbdslam_b200_orb_compute.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int, vp, vp, C.POINTER(C.c_int)]
     lib.rgbdslam_b200_nodes_create.argtypes = [u64, C.c_int, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp]
     lib.rgbdslam_b200_nodes_create_ex.argtypes = [u64, C.c_int, vp, vp, vp, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp]
+    lib.rgbdslam_b200_nodes_create_sharded.argtypes = [u64, u64, C.c_int, vp, vp, vp, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp]
     lib.rgbdslam_b200_node_download_keypoints.argtypes = [u64, vp]
     lib.rgbdslam_b200_orb_debug_detect_path.argtypes = [C.c_int]
     lib.rgbdslam_b200_orb_debug_plane.argtypes = [C.c_int, C.c_int, C.c_int, vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
@@ -146,6 +147,7 @@ def load_library(path: str | Path | None = None) -> C.CDLL:
     lib.rgbdslam_b200_allgather_slot_edges.argtypes = [u64, C.c_int, C.c_int, vp]
     lib.rgbdslam_b200_posegraph_optimize.argtypes = [C.c_int, vp, vp, C.c_int, vp, vp, vp, C.c_double, C.c_double,
                                                      C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.rgbdslam_b200_graph_from_pairs.argtypes = [C.c_int, C.c_int, vp, vp, C.c_double, vp, vp, vp, vp, vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.rgbdslam_b200_posegraph_chi2.argtypes = [C.c_int, vp, C.c_int, vp, vp, vp, C.c_double, C.POINTER(C.c_double), vp]
     lib.rgbdslam_b200_last_timing.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float)]
     lib.rgbdslam_b200_slot_stage_times.argtypes = [C.c_int, vp]
@@ -159,6 +161,24 @@ def load_library(path: str | Path | None = None) -> C.CDLL:
     if path is None:
         _lib = lib
     return lib
+
+
+def graph_from_pairs(pairs: np.ndarray, results: np.ndarray, n_frames: int, dt: float = 1.0 / 30.0) -> dict:
+    """rgbdslam_b200_graph_from_pairs (host glue, runs without a GPU): same dict as pipeline.build_graph."""
+    lib = load_library()
+    pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
+    results = np.ascontiguousarray(results, PAIR_RESULT_DTYPE)
+    cap = len(pairs) + n_frames
+    poses = np.zeros((n_frames, 7)); fixed = np.zeros(n_frames, np.uint8)
+    ij = np.zeros((cap, 2), np.int32); meas = np.zeros((cap, 7)); info = np.zeros((cap, 36))
+    ne, nc = C.c_int(), C.c_int()
+    rc = lib.rgbdslam_b200_graph_from_pairs(n_frames, len(pairs), _ptr(pairs), _ptr(results), dt, _ptr(poses), _ptr(fixed), _ptr(ij),
+                                            _ptr(meas), _ptr(info), C.byref(ne), C.byref(nc))
+    if rc != 0:
+        raise B200Error(f"rgbdslam_b200 error {rc}: {lib.rgbdslam_b200_last_error().decode()}")
+    n = ne.value
+    return dict(init=poses, fixed=fixed, ij=ij[:n].copy(), meas=meas[:n].copy(), info=info[:n].copy(), n_valid_edges=n - nc.value,
+                n_const_edges=nc.value)
 
 
 def default_params() -> Params:
@@ -406,6 +426,26 @@ class Frontend:
         nf = np.zeros(F, np.int32)
         self._check(self.lib.rgbdslam_b200_nodes_create_ex(det, F, _ptr(gray), _ptr(depth), _ptr(None if mask_from_depth else mask), W, H,
                                                            _ptr(K4), _ptr(ids), 1 if mask_from_depth else 0, _ptr(handles), _ptr(nf)))
+        self._nodes += [int(h) for h in handles]
+        return [int(h) for h in handles], nf
+
+    def nodes_create_sharded(self, det: int, comm: int, total_frames: int, gray, depth, mask, K4, ids=None,
+                             mask_from_depth: bool = False):
+        """Frame-sharded nodes_create: gray / depth / mask hold THIS rank's frames (sharding.frame_shard); returns handles and
+        feature counts of ALL total_frames nodes (every rank ends up holding every node)."""
+        if isinstance(gray, np.ndarray):
+            gray = np.ascontiguousarray(gray, np.uint8)
+            depth = np.ascontiguousarray(depth, np.float32)
+            mask = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+        _, H, W = gray.shape
+        K4 = np.ascontiguousarray(K4, np.float32)
+        ids = None if ids is None else np.ascontiguousarray(ids, np.int32)
+        handles = np.zeros(total_frames, np.uint64)
+        nf = np.zeros(total_frames, np.int32)
+        own = gray.shape[0] > 0
+        self._check(self.lib.rgbdslam_b200_nodes_create_sharded(
+            det, C.c_uint64(comm), total_frames, _ptr(gray) if own else None, _ptr(depth) if own else None,
+            _ptr(None if (mask_from_depth or not own) else mask), W, H, _ptr(K4), _ptr(ids), 1 if mask_from_depth else 0, _ptr(handles), _ptr(nf)))
         self._nodes += [int(h) for h in handles]
         return [int(h) for h in handles], nf
 

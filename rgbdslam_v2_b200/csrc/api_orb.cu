@@ -10,6 +10,7 @@
 #include <mutex>
 #include <vector>
 
+#include "comm.h"
 #include "kernels.h"
 #include "orb_host.h"
 #include "state.h"
@@ -42,11 +43,15 @@ struct OrbCtx {
   cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
   DevBuf cell_img, cell_mask, score, cand, cand_count, hist, mask_any, thr, resp, cell_out, cell_out_count, scratch, kp, xyz, n,
       pyr_raw, pyr_blur, desc, err, trig;
+  // rgbdslam_b200_nodes_create_sharded: what must survive between the detection pass and the finishing pass of ALL own frames,
+  // and the per-(frame, cell) tables every rank holds for ALL frames of the sequence
+  DevBuf sh_gray, sh_depth, sh_mask, sh_cell_img, sh_cand, all_hist, all_cnt, all_many, all_thr;
   const uint8_t* last_gray = nullptr;  // device pointers of frame 0 of the last call (debug hooks)
   void release() {
     DevBuf* all[] = {&d_ofs, &d_w1, &in_gray[0], &in_gray[1], &in_mask[0], &in_mask[1], &in_depth[0], &in_depth[1], &cell_img,
                      &cell_mask, &score, &cand, &cand_count, &hist, &mask_any, &thr, &resp, &cell_out, &cell_out_count, &scratch,
-                     &kp, &xyz, &n, &pyr_raw, &pyr_blur, &desc, &err, &trig};
+                     &kp, &xyz, &n, &pyr_raw, &pyr_blur, &desc, &err, &trig, &sh_gray, &sh_depth, &sh_mask, &sh_cell_img, &sh_cand,
+                     &all_hist, &all_cnt, &all_many, &all_thr};
     for (DevBuf* b : all) b->release();
     stage[0].release();
     stage[1].release();
@@ -592,6 +597,190 @@ int rgbdslam_b200_nodes_create_ex(uint64_t detector, int nframes, const uint8_t*
     nd->desc = sl_desc + (size_t)f * K * 32;
     nd->xyz = sl_xyz + (size_t)f * K;
     nd->kp = sl_kp + (size_t)f * K;
+    nd->desc_i8 = sl_i8 + (size_t)f * Kpad * 256;
+    nd->slab = slab;
+    slab->refs++;
+    node_handles[f] = (uint64_t)(uintptr_t)nd;
+    if (n_features) n_features[f] = n[f];
+  }
+  s.launches += launches;
+  return 0;
+}
+
+// Frame-sharded Node construction: see include/rgbdslam_b200.h.  Two passes over the rank's own frames around ONE exchange of
+// the score histograms; then one exchange of the finished features.
+int rgbdslam_b200_nodes_create_sharded(uint64_t detector, uint64_t comm_handle, int total_frames, const uint8_t* gray,
+                                       const float* depth, const uint8_t* mask, int w, int h, const float* K4, const int32_t* ids,
+                                       int flags, uint64_t* node_handles, int32_t* n_features) {
+  std::lock_guard<std::mutex> lk(g_state.mu);
+  int rc = check_inited();
+  if (rc) return rc;
+  Detector* det = get_detector(detector);
+  Comm* cm = get_comm(comm_handle);
+  if (!det || !cm || total_frames < 0 || (total_frames > 0 && (!K4 || !node_handles)) || (flags & ~RGBDSLAM_B200_MASK_FROM_DEPTH)) {
+    set_error("nodes_create_sharded: bad arguments");
+    return RGBDSLAM_B200_ERR_ARG;
+  }
+  if (total_frames == 0) return 0;
+  State& s = g_state;
+  if (s.params.observability_threshold > 0.0) {
+    set_error("nodes_create_sharded: the environment measurement model needs every node's depth cloud on every rank (not exchanged)");
+    return RGBDSLAM_B200_ERR_STATE;
+  }
+  const int world = cm->world, rank = cm->rank;
+  const int per = (total_frames + world - 1) / world;
+  const int f0 = std::min(rank * per, total_frames), f1 = std::min((rank + 1) * per, total_frames);
+  const int own = f1 - f0, Wp = world * per;
+  if (own > 0 && (!gray || !depth)) {
+    set_error("nodes_create_sharded: null image buffers");
+    return RGBDSLAM_B200_ERR_ARG;
+  }
+  const bool mask_from_depth = (flags & RGBDSLAM_B200_MASK_FROM_DEPTH) != 0;
+  if (mask_from_depth) mask = nullptr;
+  if ((rc = orb_prepare(w, h, own)) || (rc = orb_ensure_streams())) return rc;
+  OrbCtx& o = g_orb;
+  const OrbGeom& g = o.g;
+  const int chunk = std::max(1, std::min(own, kOrbChunk));
+  if ((rc = orb_ensure_buffers(chunk, 0, false))) return rc;
+  const size_t px = (size_t)w * h, nc = (size_t)g.ncells;
+  const size_t own_ = (size_t)std::max(own, 1);
+  if ((rc = o.sh_gray.ensure(px * own_)) || (rc = o.sh_depth.ensure(px * 4 * own_)) || (mask && (rc = o.sh_mask.ensure(px * own_))) ||
+      (rc = o.sh_cell_img.ensure((size_t)g.cell_bytes * own_)) || (rc = o.sh_cand.ensure(own_ * nc * kOrbCandCap * sizeof(OrbCand))) ||
+      (rc = o.all_hist.ensure((size_t)Wp * nc * 256 * 4)) || (rc = o.all_cnt.ensure((size_t)Wp * nc * 4)) ||
+      (rc = o.all_many.ensure((size_t)Wp * nc * 4)) || (rc = o.all_thr.ensure((size_t)Wp * nc * 4)))
+    return rc;
+  cudaStream_t st = s.stream, cs = o.copy_stream;
+  const int K = std::min(o.kp_stride, s.params.max_keypoints);
+  const int Kpad = ((K > 0 ? K : 1) + 255) / 256 * 256;
+  // slab: [desc Wp x K x 32][xyz Wp x K x 16][n Wp x 4][kp own x K x 28][i8 total x Kpad x 256]
+  auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+  const size_t b_desc = up((size_t)Wp * K * 32), b_xyz = up((size_t)Wp * K * 16), b_n = up((size_t)Wp * 4);
+  const size_t b_kp = up(own_ * K * sizeof(rgbdslam_b200_keypoint)), b_i8 = (size_t)total_frames * Kpad * 256;
+  NodeSlab* slab = new NodeSlab();
+  cudaError_t e = cudaMalloc(&slab->base, b_desc + b_xyz + b_n + b_kp + b_i8);
+  if (e != cudaSuccess) {
+    delete slab;
+    return cuda_fail(e, "cudaMalloc(node slab)");
+  }
+  uint8_t* sl_desc = (uint8_t*)slab->base;
+  float4* sl_xyz = (float4*)(sl_desc + b_desc);
+  int* sl_n = (int*)((uint8_t*)sl_xyz + b_xyz);
+  rgbdslam_b200_keypoint* sl_kp = (rgbdslam_b200_keypoint*)((uint8_t*)sl_n + b_n);
+  int8_t* sl_i8 = (int8_t*)((uint8_t*)sl_kp + b_kp);
+  auto fail = [&](int code) {
+    cudaStreamSynchronize(cs);
+    cudaStreamSynchronize(st);
+    cudaFree(slab->base);
+    delete slab;
+    return code;
+  };
+  const bool pinned = own == 0 || (is_pinned(gray) && is_pinned(depth) && (!mask || is_pinned(mask)));
+  const size_t stage_bytes = (px + px * 4 + (mask ? px : 0)) * chunk;
+  if (!pinned && ((rc = o.stage[0].ensure(stage_bytes)) || (rc = o.stage[1].ensure(stage_bytes)))) return fail(rc);
+  const float4 Kinv = make_float4((float)(1. / (double)K4[0]), (float)(1. / (double)K4[1]), K4[2], K4[3]);
+  int* hist_all = (int*)o.all_hist.ptr;
+  int* cnt_all = (int*)o.all_cnt.ptr;
+  int* many_all = (int*)o.all_many.ptr;
+  int* thr_all = (int*)o.all_thr.ptr;
+  e = cudaMemsetAsync(o.err.ptr, 0, 4, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(sl_n, 0, b_n, st);
+  // frames of the padding (Wp > total_frames) and of ranks without frames must read as "no candidates"
+  if (e == cudaSuccess) e = cudaMemsetAsync(hist_all, 0, (size_t)Wp * nc * 256 * 4, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(cnt_all, 0, (size_t)Wp * nc * 4, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(many_all, 0, (size_t)Wp * nc * 4, st);
+  if (e == cudaSuccess) e = cudaEventRecord(o.ev_free[0], st);  // uploads start after everything queued so far
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(cs, o.ev_free[0], 0);
+  if (e != cudaSuccess) return fail(cuda_fail(e, "nodes_create_sharded setup"));
+  int launches = 0, ci = 0;
+  // ---- pass A: upload + pyramids + FAST / NMS candidates + score histograms of the own frames
+  for (int c0 = 0; c0 < own; c0 += chunk, ci++) {
+    const int F = std::min(chunk, own - c0), b = ci & 1;
+    const uint8_t* hg = gray + px * c0;
+    const float* hd = depth + px * c0;
+    const uint8_t* hm = mask ? mask + px * c0 : nullptr;
+    if (!pinned) {
+      if (ci >= 2 && (e = cudaEventSynchronize(o.ev_copied[b])) != cudaSuccess) return fail(cuda_fail(e, "staging wait"));
+      uint8_t* sp = (uint8_t*)o.stage[b].ptr;
+      memcpy(sp, hg, px * F);
+      memcpy(sp + px * chunk, hd, px * 4 * F);
+      if (hm) memcpy(sp + px * 5 * chunk, hm, px * F);
+      hg = sp;
+      hd = (const float*)(sp + px * chunk);
+      if (hm) hm = sp + px * 5 * chunk;
+    }
+    uint8_t* dg = (uint8_t*)o.sh_gray.ptr + px * c0;
+    float* dd = (float*)o.sh_depth.ptr + px * c0;
+    uint8_t* dm = hm ? (uint8_t*)o.sh_mask.ptr + px * c0 : nullptr;
+    e = cudaMemcpyAsync(dg, hg, px * F, cudaMemcpyHostToDevice, cs);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dd, hd, px * 4 * F, cudaMemcpyHostToDevice, cs);
+    if (e == cudaSuccess && hm) e = cudaMemcpyAsync(dm, hm, px * F, cudaMemcpyHostToDevice, cs);
+    if (e == cudaSuccess) e = cudaEventRecord(o.ev_ready[b], cs);
+    if (e == cudaSuccess) e = cudaEventRecord(o.ev_copied[b], cs);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(st, o.ev_ready[b], 0);
+    if (e != cudaSuccess) return fail(cuda_fail(e, "frame upload"));
+    if (c0 == 0) o.last_gray = dg;
+    const size_t gf = (size_t)(f0 + c0);  // global index of the chunk's first frame
+    e = orb_run_detect(g, o.tab, F, dg, dm, mask_from_depth ? dd : nullptr, (uint8_t*)o.sh_cell_img.ptr + (size_t)g.cell_bytes * c0,
+                       (uint8_t*)o.cell_mask.ptr, (uint8_t*)o.score.ptr, (OrbCand*)o.sh_cand.ptr + (size_t)c0 * nc * kOrbCandCap,
+                       cnt_all + gf * nc, hist_all + gf * nc * 256, many_all + gf * nc, st, &launches);
+    if (e != cudaSuccess) return fail(cuda_fail(e, "orb detect kernels"));
+  }
+  // ---- the exchange that makes the frames independent: every rank gets every frame's score histograms, replays the
+  //      threshold recurrence of the whole sequence (feature_adjuster.cpp:131-150, 185-224) and keeps its own frames' thresholds
+  if (world > 1) {
+    ncclResult_t r = g_nccl.AllGather(hist_all + (size_t)rank * per * nc * 256, hist_all, (size_t)per * nc * 256 * 4, 0, cm->comm, st);
+    if (r == 0) r = g_nccl.AllGather(cnt_all + (size_t)rank * per * nc, cnt_all, (size_t)per * nc * 4, 0, cm->comm, st);
+    if (r == 0) r = g_nccl.AllGather(many_all + (size_t)rank * per * nc, many_all, (size_t)per * nc * 4, 0, cm->comm, st);
+    if (r != 0) return fail(nccl_fail(r, "ncclAllGather(histograms)"));
+  }
+  if ((rc = detector_to_device(det, st))) return fail(rc);
+  e = orb_run_adapt(g, total_frames, hist_all, cnt_all, many_all, (double*)det->d_state.ptr, thr_all, o.min_cell, o.max_cell,
+                    s.params.adjuster_max_iterations, (int*)o.err.ptr, st, &launches);
+  if (e != cudaSuccess) return fail(cuda_fail(e, "orb threshold kernel"));
+  det->host_valid = false;
+  // ---- pass B: Harris / keepStrongest / finalize / describe of the own frames, straight into the slab
+  for (int c0 = 0; c0 < own; c0 += chunk) {
+    const int F = std::min(chunk, own - c0);
+    const size_t gf = (size_t)(f0 + c0);
+    const uint8_t* dg = (const uint8_t*)o.sh_gray.ptr + px * c0;
+    const float* dd = (const float*)o.sh_depth.ptr + px * c0;
+    const uint8_t* cimg = (const uint8_t*)o.sh_cell_img.ptr + (size_t)g.cell_bytes * c0;
+    e = orb_run_select(g, F, 1, o.max_per_cell, s.params.max_keypoints, cimg, (const OrbCand*)o.sh_cand.ptr + (size_t)c0 * nc * kOrbCandCap,
+                       cnt_all + gf * nc, thr_all + gf * nc, (float*)o.resp.ptr, (unsigned long long*)o.cell_out.ptr,
+                       (int*)o.cell_out_count.ptr, dd, (float)s.params.depth_scaling_factor, Kinv, o.scratch.ptr, sl_kp + (size_t)c0 * K,
+                       sl_xyz + gf * K, (float2*)o.trig.ptr, sl_n + gf, K, st, &launches);
+    if (e != cudaSuccess) return fail(cuda_fail(e, "orb select kernels"));
+    e = orb_run_describe(g, o.tab, F, dg, (uint8_t*)o.pyr_raw.ptr, (uint8_t*)o.pyr_blur.ptr, sl_kp + (size_t)c0 * K, sl_n + gf, K, K,
+                         (const float2*)o.trig.ptr, sl_desc + gf * K * 32, st, &launches);
+    if (e != cudaSuccess) return fail(cuda_fail(e, "orb describe kernels"));
+  }
+  // ---- every rank gets every node's features (48 KB per 1000-keypoint frame over NVLink)
+  if (world > 1) {
+    ncclResult_t r = g_nccl.AllGather(sl_desc + (size_t)rank * per * K * 32, sl_desc, (size_t)per * K * 32, 0, cm->comm, st);
+    if (r == 0) r = g_nccl.AllGather((uint8_t*)(sl_xyz + (size_t)rank * per * K), sl_xyz, (size_t)per * K * 16, 0, cm->comm, st);
+    if (r == 0) r = g_nccl.AllGather((uint8_t*)(sl_n + (size_t)rank * per), sl_n, (size_t)per * 4, 0, cm->comm, st);
+    if (r != 0) return fail(nccl_fail(r, "ncclAllGather(features)"));
+  }
+  e = launch_expand_i8_strided(sl_desc, sl_i8, sl_n, total_frames, K, Kpad, st);
+  if (e != cudaSuccess) return fail(cuda_fail(e, "expand_i8 kernel"));
+  launches++;
+  std::vector<int> n(total_frames);
+  int flag = 0;
+  e = cudaMemcpyAsync(n.data(), sl_n, 4 * (size_t)total_frames, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&flag, o.err.ptr, 4, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(cs);
+  if (e != cudaSuccess) return fail(cuda_fail(e, "nodes_create_sharded finish"));
+  if ((rc = orb_check_err_flag(flag))) return fail(rc);
+  for (int f = 0; f < total_frames; f++) {
+    NodeDev* nd = new NodeDev();
+    nd->magic = NodeDev::kMagic;
+    nd->id = ids ? ids[f] : f;
+    nd->n = n[f];
+    nd->n_pad = Kpad;
+    nd->desc = sl_desc + (size_t)f * K * 32;
+    nd->xyz = sl_xyz + (size_t)f * K;
+    nd->kp = (f >= f0 && f < f1) ? sl_kp + (size_t)(f - f0) * K : nullptr;  // 2-D keypoints stay on the rank that built the node
     nd->desc_i8 = sl_i8 + (size_t)f * Kpad * 256;
     nd->slab = slab;
     slab->refs++;

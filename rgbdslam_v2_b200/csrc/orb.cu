@@ -277,9 +277,13 @@ __global__ void __launch_bounds__(256) k_fast_nms(const uint8_t* __restrict__ ce
   __syncthreads();
   {  // scores: thread = (quad of 4 columns, row), two row passes
     const int q = threadIdx.x & 15, r0 = threadIdx.x >> 4;
+    // rows below the last output row of this tile (+ 1 for the NMS) are never read: skipping them (a warp owns two
+    // adjacent rows per pass) removes most of the waste of partially covered tiles
+    const int sy_last = min(kFT_H, ph - kFastEdge - oy0) + 1;
 #pragma unroll
     for (int pass = 0; pass < 2; pass++) {
       const int sy = r0 + 16 * pass;  // score row (relative y = sy - 1) -> image row sy + 3
+      if (sy > sy_last) continue;
       const uint32_t s01 = fast_score_pair(simg, sy + 3, 4 * q + 4);
       const uint32_t s23 = fast_score_pair(simg, sy + 3, 4 * q + 6);
       // halves hold 0..254: pack the four scores into bytes

@@ -17,7 +17,10 @@
 #include <cuda_runtime.h>
 
 #include <cfloat>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -471,6 +474,7 @@ struct PgCtx {
   int64_t launches = 0;
   int cg_iters = 0;
   double pcg_residual = -1.0;  // LinearSolverPCG::_residual
+  double pcg_seconds = 0.0;    // wall time inside the PCG launches (RB200_PG_TIMING=1 prints the split)
 };
 
 static int pg_errors(PgCtx& c, const double* dx_poses, double* robust, double* plain, double* per_edge) {
@@ -543,11 +547,13 @@ static int pg_pcg(PgCtx& c, double lambda, double* scale, bool* ok) {
   a.tol = (c.pcg_residual > 0.0 && c.pcg_residual > 1e-6) ? c.pcg_residual : 1e-6;
   a.maxit = 6 * c.nv;
   void* args[] = {&a};
+  const auto t0 = std::chrono::steady_clock::now();
   PG_CUDA(cudaLaunchCooperativeKernel((void*)pg_pcg_kernel, dim3(c.pcg_grid), dim3(256), args, 0, c.st));
   c.launches++;
   double res[4];
   PG_CUDA(cudaMemcpyAsync(res, c.dev.result.ptr, sizeof(res), cudaMemcpyDeviceToHost, c.st));
   PG_CUDA(cudaStreamSynchronize(c.st));
+  c.pcg_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   c.cg_iters += (int)res[0];
   c.pcg_residual = 0.5 * res[1];
   *scale = res[2];
@@ -615,6 +621,7 @@ int posegraph_optimize(int nv, double* poses, const uint8_t* fixed, int ne, cons
                        const double* info, double stop, double huber_delta, double* chi2_out, int* iters_out,
                        int* cg_iters_out, double* per_edge_chi2, bool optimize) {
   State& s = g_state;
+  const auto t_begin = std::chrono::steady_clock::now();
   PgCtx c;
   c.nv = nv;
   c.ne = ne;
@@ -700,6 +707,10 @@ int posegraph_optimize(int nv, double* poses, const uint8_t* fixed, int ne, cons
   if (per_edge_chi2 && ne > 0)
     PG_CUDA(cudaMemcpyAsync(per_edge_chi2, d.per_edge.ptr, 8 * (size_t)ne, cudaMemcpyDeviceToHost, st));
   PG_CUDA(cudaStreamSynchronize(st));
+  if (getenv("RB200_PG_TIMING"))
+    fprintf(stderr, "[posegraph] nv %d ne %d optimize %d: total %.3f ms, pcg launches %.3f ms (%d pcg iterations, grid %d), lm %d\n", nv, ne,
+            (int)optimize, 1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count(), 1e3 * c.pcg_seconds,
+            c.cg_iters, c.pcg_grid, it);
   if (chi2_out) *chi2_out = chi2;
   if (iters_out) *iters_out = it;
   if (cg_iters_out) *cg_iters_out = c.cg_iters;

@@ -47,3 +47,9 @@ def allgather_edges_torch(local: np.ndarray, n_items: int, world: int) -> np.nda
     dist.all_gather(out, buf)
     allb = np.concatenate([o.numpy() for o in out]).view(local.dtype)
     return merge_gathered(allb, n_items, world)
+
+
+def frame_shard(total_frames: int, rank: int, world: int) -> range:
+    """Frames of a sequence owned by `rank` in rgbdslam_b200_nodes_create_sharded: blocks of ceil(total / world)."""
+    per = -(-total_frames // world)
+    return range(min(rank * per, total_frames), min((rank + 1) * per, total_frames))

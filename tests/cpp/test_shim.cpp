@@ -18,7 +18,6 @@ int main() {
     std::printf("init failed (expected without a GPU): %s\n", rgbdslam_b200_last_error());
     return 77;
   }
-  Node::max_matches() = p.max_matches;
   const int n = 500;
   std::vector<uint8_t> d_old(n * 32), d_new(n * 32);
   std::vector<Vector4f> x_old(n), x_new(n);

@@ -230,3 +230,30 @@ def test_nodes_create_without_mask_and_small_batches(fe, seq40):
     assert np.array_equal(k, b[1][0]) and np.array_equal(d, b[1][1])
     for h in [h1[1]] + h2:
         fe.node_destroy(h)
+
+
+def test_nodes_create_sharded_single_rank_equals_plain(fe, seq40):
+    """The two-pass frame-sharded constructor (histogram exchange, threshold replay over the whole sequence, feature
+    all-gather) on a 1-rank NCCL communicator == the plain constructor: nodes and final detector thresholds."""
+    from rgbdslam_v2_b200 import synth
+    gray, depth, mask = seq40
+    K4 = (synth.FX, synth.FY, synth.CX, synth.CY)
+    _reinit(fe, max_keypoints=600)
+    det = fe.detector_create()
+    h1, n1 = fe.nodes_create(det, gray, depth, mask, K4)
+    thr1 = fe.detector_thresholds(det).copy()
+    fe.detector_destroy(det)
+    comm = fe.comm_init(0, 1, fe.comm_unique_id())
+    det = fe.detector_create()
+    h2, n2 = fe.nodes_create_sharded(det, comm, 40, gray, depth, mask, K4)
+    thr2 = fe.detector_thresholds(det).copy()
+    fe.detector_destroy(det)
+    assert np.array_equal(n1, n2) and np.array_equal(thr1, thr2)
+    assert _same_nodes(_node_dump(fe, h1), _node_dump(fe, h2))
+    # matching works on the gathered nodes
+    res, _, _ = fe.match_node_pairs(h2[1:6], h2[0:5], seed=3, want_matches=False)
+    ref, _, _ = fe.match_node_pairs(h1[1:6], h1[0:5], seed=3, want_matches=False)
+    assert np.array_equal(res["n_inliers"], ref["n_inliers"]) and np.array_equal(res["ransac_trafo"], ref["ransac_trafo"])
+    fe.comm_destroy(comm)
+    for h in h1 + h2:
+        fe.node_destroy(h)

@@ -98,3 +98,9 @@ def test_build_graph_fast_equals_build_graph():
     for k in ("init", "fixed", "ij", "meas", "info"):
         assert np.array_equal(a[k], b[k]), k
     assert a["n_const_edges"] == b["n_const_edges"] and a["n_valid_edges"] == b["n_valid_edges"]
+    # the C-ABI host glue (rgbdslam_b200_graph_from_pairs; no GPU needed) builds the same graph
+    from rgbdslam_v2_b200._capi import graph_from_pairs
+    c = graph_from_pairs(np.array(pairs), res, n)
+    assert np.array_equal(a["ij"], c["ij"]) and np.array_equal(a["fixed"], c["fixed"]) and np.array_equal(a["info"], c["info"])
+    assert np.abs(a["meas"] - c["meas"]).max() < 1e-15 and np.abs(a["init"] - c["init"]).max() < 1e-13
+    assert a["n_const_edges"] == c["n_const_edges"] > 0

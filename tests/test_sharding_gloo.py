@@ -44,6 +44,17 @@ def test_shard_ranges_cover_and_balance():
             assert max(len(r) for r in rs) - min(len(r) for r in rs) <= 1
 
 
+def test_frame_shards_are_contiguous_blocks():
+    """rgbdslam_b200_nodes_create_sharded: rank r owns frames [r * per, min((r + 1) * per, total)), per = ceil(total / world)"""
+    from rgbdslam_v2_b200 import sharding
+    for n in (0, 1, 7, 250, 2000, 2001):
+        for w in (1, 2, 3, 4, 8):
+            rs = [sharding.frame_shard(n, r, w) for r in range(w)]
+            assert [i for r in rs for i in r] == list(range(n))
+            per = -(-n // w) if n else 0
+            assert all(len(r) <= per for r in rs) and all(r.start == min(k * per, n) for k, r in enumerate(rs))
+
+
 def test_pad_and_merge_roundtrip():
     from rgbdslam_v2_b200 import sharding
     from rgbdslam_v2_b200._capi import PAIR_RESULT_DTYPE
