@@ -40,6 +40,10 @@ SEED = 2026
 METRIC = "frame_pairs_per_sec_640x480_1k_orb"
 UNIT = "pairs/s"
 ALGO_BYTES_PER_PAIR = (N_KP + N_KP) * 32 + N_KP * 8  # 72 000 B
+# one string for both arms (the driver compares config.workload of `ours` and `reference`)
+WORKLOAD = (f"C2: {PAIRS_PER_GPU} frame pairs x {N_KP} ORB kp per GPU, Hamming BF match + 4-pt RANSAC "
+            "(200 hypotheses, max_matches 300), synthetic feature-level pairs (rgbdslam_v2_b200/synth.py make_batch)")
+MIN_TIMED_MS = 50.0  # the timed regions cover at least this much device time whatever --steps says
 
 
 def measured_peaks():
@@ -240,7 +244,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64 popcount + f32 fit + f64 Mahalanobis", "data": "synthetic",
-        "config": {"workload": f"C2: {PAIRS_PER_GPU} frame pairs x {N_KP} ORB kp, Hamming BF match + 4-pt RANSAC (200 it)",
+        "config": {"workload": WORKLOAD,
                    "note": "CPU port of the reference path (oracle/frontend_oracle.c); the reference itself is unbuildable here"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                          "cores_available": usable_cpus(), "pairs_per_s_by_thread_count": thread_scan},
@@ -314,6 +318,118 @@ def bench_posegraph(fe):
             "chi2": chi2, "ate_m": synth.ate_rmse(x[:, :3], g["gt"][:, :3]), "pcg_iter_per_s": cg / dt,
             "algorithmic_GBps": (cg * 18.9e6 + it * 45e6) / dt / 1e9,
             "sample_1000V_6000E": {"gpu_seconds": dts, "cpu_oracle_seconds": dto, "cpu_threads": 1}}
+
+
+C3_KP = 2000
+C3_PAIRS = 64
+
+
+def _c3_descriptors(rng, n, kind):
+    """SIFT-like 128-d rows.  'sift': non-negative, gamma-distributed magnitudes, values 0..255 (cv::SIFT statistics, fed through
+    RootSIFT); 'siftgpu': unit L2 norm, clipped at 0.2 and renormalised (what SiftGPU hands to its matcher)."""
+    if kind == "sift":
+        return np.minimum(rng.gamma(0.6, 30.0, size=(n, 128)), 255.0).astype(np.float32)
+    d = rng.gamma(0.6, 1.0, size=(n, 128)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d = np.minimum(d, 0.2)
+    return (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+
+
+def bench_c3(fe, local_rank, cpu=True):
+    """BASELINE config C3: SIFT 128-d float descriptors, 2000 keypoints per frame, the distance matrix as a bf16 tensor-core
+    GEMM (ratio / uniqueness matcher = the FLANN branch node.cpp:610-667 with an exact search) and the SiftGPU matcher (u8
+    dot products); pairs/s with resident nodes, the tensor roofline of the match kernel, end to end from host descriptors,
+    the fraction of exact nearest neighbours, and cv2's brute-force / FLANN matchers on the host cores."""
+    import torch
+    from rgbdslam_v2_b200 import synth
+    rng = np.random.default_rng(33)
+    out = {"workload": f"C3: {C3_PAIRS} frame pairs x {C3_KP} SIFT-128 descriptors per frame (synthetic SIFT-like rows, 50 % of the "
+                       "newer frame's features are noisy copies of the older frame's), exact 2-NN via bf16 tcgen05 GEMM + fp32 re-rank, "
+                       "ratio 0.95 / uniqueness, 4-pt RANSAC"}
+    peak_bf16 = 1701.0
+    try:
+        peak_bf16 = float(json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["bf16_tflops"])
+        out["peak_source"] = "MEASURED_PEAKS.json bf16_tflops (burst)"
+    except Exception:
+        out["peak_source"] = "fallback 1701 TF/s"
+    for kind, matcher in (("sift", 0), ("siftgpu", 1)):
+        fe.set_sift_matcher(matcher)
+        frames = []
+        older_d = _c3_descriptors(rng, C3_KP, kind)
+        b0 = synth.make_pair(9000, C3_KP, overlap=0.5)
+        xyz_prev = b0["xyz_older"]
+        hs = [fe.node_from_sift(0, older_d, xyz_prev)]
+        host = [(older_d, xyz_prev)]
+        for k in range(C3_PAIRS):
+            b = synth.make_pair(9001 + k, C3_KP, overlap=0.5)
+            d = _c3_descriptors(rng, C3_KP, kind)
+            sel = rng.permutation(C3_KP)[: C3_KP // 2]
+            noise = rng.normal(0, 5.0 if kind == "sift" else 0.01, (len(sel), 128)).astype(np.float32)
+            d[sel] = np.abs(host[-1][0][sel] + noise)
+            host.append((d, b["xyz_newer"]))
+            hs.append(fe.node_from_sift(k + 1, d, b["xyz_newer"]))
+        newer, older = hs[1:], hs[:-1]
+        for _ in range(3):
+            res, _, _ = fe.match_node_pairs(newer, older, seed=5, want_matches=False)
+        ts, kern = [], []
+        for _ in range(5):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            res, _, _ = fe.match_node_pairs(newer, older, seed=5, want_matches=False)
+            ts.append(time.perf_counter() - t0)
+            st = fe.stage_times(0)
+            kern.append((st["hamming"], st["total"]))
+        k_ms = statistics.median(k for k, _ in kern)
+        dev_ms = statistics.median(t for _, t in kern)
+        items = 2 if matcher == 1 else 1  # the SiftGPU matcher runs the row and the column pass (two GEMMs) in one launch
+        flops = 2.0 * C3_KP * C3_KP * 128 * C3_PAIRS * items
+        entry = {"pairs_per_s_resident": C3_PAIRS / (dev_ms * 1e-3), "device_ms_per_batch": dev_ms, "wall_ms_per_batch": 1e3 * statistics.median(ts),
+                 "match_kernel_ms": k_ms, "valid_pairs": int((res["id1"] >= 0).sum()),
+                 "roofline": {"bound": "tensor", "kernel": "tc_match256_kernel<%d>" % (1 if matcher == 0 else 2),
+                              "achieved": flops / (k_ms * 1e-3) / 1e12, "peak": peak_bf16 * (2.0 if matcher == 1 else 1.0),
+                              "unit": "TFLOP/s (bf16)" if matcher == 0 else "TOP/s (u8; peak = 2 x measured bf16)",
+                              "algorithmic_flops_per_launch": flops}}
+        entry["roofline"]["frac"] = entry["roofline"]["achieved"] / entry["roofline"]["peak"]
+        # end to end: host descriptors in (upload + RootSIFT / tile preparation inside), host results out
+        t0 = time.perf_counter()
+        hh = [fe.node_from_sift(1000 + i, d, x) for i, (d, x) in enumerate(host)]
+        fe.match_node_pairs(hh[1:], hh[:-1], seed=5, want_matches=False)
+        e2e = time.perf_counter() - t0
+        for h in hh:
+            fe.node_destroy(h)
+        entry["e2e"] = {"pairs_per_s": C3_PAIRS / e2e, "h2d_bytes": int(len(host) * C3_KP * (512 + 16)), "note": "node_from_sift per frame (synchronous uploads) + one batched match"}
+        if matcher == 0:
+            from oracle import sift_oracle  # checker: exact float64 2-NN
+            same = []
+            for k in range(4):
+                q, t = host[k + 1][0], host[k][0]
+                idx, _ = fe.knn2_l2(q, t)
+                oidx, _ = sift_oracle.knn2_exact(sift_oracle.root_sift(q), sift_oracle.root_sift(t))
+                same.append(float((idx[:, 0] == oidx[:, 0]).mean()))
+            entry["exact_nearest_neighbour_fraction"] = float(np.mean(same))
+            if cpu:
+                import cv2
+                cv2.setNumThreads(usable_cpus())
+                q = sift_oracle.root_sift(host[1][0]); t = sift_oracle.root_sift(host[0][0])
+                bf = cv2.BFMatcher(cv2.NORM_L2)
+                bf.knnMatch(q, t, k=2)
+                t0 = time.perf_counter()
+                for k in range(4):
+                    bf.knnMatch(sift_oracle.root_sift(host[k + 1][0]), sift_oracle.root_sift(host[k][0]), k=2)
+                t_bf = (time.perf_counter() - t0) / 4
+                fl = cv2.FlannBasedMatcher(dict(algorithm=1, trees=4), dict(checks=16))  # node.cpp:503-510, 1573-1581
+                t0 = time.perf_counter()
+                for k in range(4):
+                    fl.knnMatch(sift_oracle.root_sift(host[k + 1][0]), sift_oracle.root_sift(host[k][0]), k=2)
+                t_fl = (time.perf_counter() - t0) / 4
+                entry["cpu_baseline"] = {"cv2_bfmatcher_knn2_pairs_per_s": 1.0 / t_bf, "cv2_flann_kdtree4_checks16_pairs_per_s": 1.0 / t_fl,
+                                         "cores": usable_cpus(), "kind": "reference dependency (cv2 4.13) -- matching stage only, no RANSAC",
+                                         "sample": "4 pairs of the same workload"}
+        out["ratio_matcher" if matcher == 0 else "siftgpu_matcher"] = entry
+        for h in hs:
+            fe.node_destroy(h)
+    fe.set_sift_matcher(0)
+    return out
 
 
 C4_FRAMES = 2000
@@ -545,12 +661,22 @@ def run_ours(args, rank, local_rank, world):
         sampler.start()
 
     # ---- timed: device-resident inputs, pipelined over DEPTH slots ------------------------------------
+    # --steps K is timed as R back-to-back blocks of K steps so that the region covers >= MIN_TIMED_MS (20 steps of 0.15 ms
+    # are four pipeline turn-overs); per-step numbers divide by K * R.  R comes from a short probe, identical on every rank.
+    p0 = time.perf_counter()
+    run_steps(submit_resident, max(args.steps, DEPTH))
+    torch.cuda.synchronize()
+    probe = torch.tensor([(time.perf_counter() - p0) / max(args.steps, DEPTH)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(probe, op=dist.ReduceOp.MAX)
+    repeats = max(1, int(np.ceil(MIN_TIMED_MS * 1e-3 / (float(probe.item()) * args.steps))))
+    timed_steps = args.steps * repeats
     launches0 = fe.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     wall0 = time.perf_counter()
     ev0.record(stream)
-    run_steps(submit_resident, args.steps)
+    run_steps(submit_resident, timed_steps)
     torch.cuda.synchronize()
     ev1.record(stream)
     barrier()
@@ -569,7 +695,7 @@ def run_ours(args, rank, local_rank, world):
     # ---- timed: end to end through the host-buffer C ABI (pinned host buffers in, host results out) -----
     barrier()
     t0 = time.perf_counter()
-    run_steps(submit_e2e, args.steps)
+    run_steps(submit_e2e, timed_steps)
     torch.cuda.synchronize()
     e2e_wall = time.perf_counter() - t0
     barrier()
@@ -608,8 +734,8 @@ def run_ours(args, rank, local_rank, world):
             c4 = {"error": repr(ex), "trace": traceback.format_exc()[-800:]}
 
     if rank == 0:
-        value = world * PAIRS_PER_GPU * args.steps / (total_ms * 1e-3)
-        e2e_value = world * PAIRS_PER_GPU * args.steps / e2e_total
+        value = world * PAIRS_PER_GPU * timed_steps / (total_ms * 1e-3)
+        e2e_value = world * PAIRS_PER_GPU * timed_steps / e2e_total
         peak, peak_src = measured_peaks()
         ham = statistics.mean(sync_ham)  # the kernel alone (one step at a time); pipelined launches share SMs with RANSAC
         achieved = ALGO_BYTES_PER_PAIR * PAIRS_PER_GPU / (ham * 1e-3) / 1e9
@@ -618,17 +744,17 @@ def run_ours(args, rank, local_rank, world):
         d2h = int(out_res.numel() + out_all.numel() + out_inl.numel())
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": total_ms / timed_steps, "timed_steps": timed_steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8 descriptors (exact integer Hamming) + f32 fit + f64 Mahalanobis", "data": "synthetic",
-            "config": {"workload": f"C2: {PAIRS_PER_GPU} frame pairs x {N_KP} ORB kp per GPU, Hamming BF match + 4-pt RANSAC "
-                                   f"({prm.ransac_iterations} hypotheses, max_matches {prm.max_matches})",
+            "config": {"workload": WORKLOAD,
                        "l2": f"inputs larger than L2: {DEPTH} alternating batches = {DEPTH} x 156 MB resident node data (126 MB L2); "
                              "the synchronous reference point flushes L2 (a 256 MiB read) before every step",
                        "pipeline": f"{DEPTH} batches in flight on {DEPTH} library streams (rgbdslam_b200_match_pairs_submit / _wait)",
                        "pairs_per_gpu": PAIRS_PER_GPU,
                        "exchange": "none (1 GPU)" if world == 1 else f"ncclAllGather of {world}x{PAIRS_PER_GPU} edge records (120 B) per step, queued behind each batch on the communicator stream (rgbdslam_b200_allgather_slot_edges), inside the timed region",
                        "edges_gathered": None if all_edges is None else int((all_edges["id1"] >= 0).sum()),
-                       "valid_edges_rank0": n_valid, "wall_ms_per_step_incl_flush": 1e3 * wall_resident / args.steps},
+                       "valid_edges_rank0": n_valid, "wall_ms_per_step_incl_flush": 1e3 * wall_resident / timed_steps,
+                       "repeats": f"{repeats} x --steps {args.steps} timed back to back (>= {MIN_TIMED_MS:.0f} ms per timed region)"},
             "roofline": {"bound": "hbm", "kernel": "hamming_match", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "traffic_source": NCU_TRAFFIC_SOURCE, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PAIR * PAIRS_PER_GPU, "kernel_ms": ham,
@@ -637,7 +763,7 @@ def run_ours(args, rank, local_rank, world):
                          "tensor": tensor_roofline(ham),
                          "note": "binding resource is the integer/tensor pipe, not HBM (1e6 256-bit distance evals per 72 kB)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": 1e3 * e2e_total / args.steps},
+                    "ms_per_step": 1e3 * e2e_total / timed_steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "device_ms_per_step": statistics.mean(dev_ms),
@@ -645,6 +771,18 @@ def run_ours(args, rank, local_rank, world):
                             "device_ms_per_step": statistics.mean(sync_dev), "note": "one batch at a time, L2 flushed, rank 0"},
         }
         out["c4"] = c4
+        if c4 and "ate_vs_gt_m" in c4:  # the second half of BASELINE's metric: "...; ATE RMSE vs reference"
+            op = c4.get("oracle_prefix") or {}
+            out["ate"] = {"sequence": f"C4 ({c4.get('pairs')} pairs, {args.c4_frames} frames)", "ate_rmse_vs_ground_truth_m": c4["ate_vs_gt_m"],
+                          "ate_rmse_gpu_vs_cpu_reference_path_m": op.get("ate_gpu_vs_oracle_m"),
+                          "cpu_reference_path_ate_vs_ground_truth_m": op.get("ate_oracle_vs_gt_m"),
+                          "cpu_reference_path_frames": op.get("frames"), "target": "within 1 mm of the reference path"}
+        if world == 1 and not args.no_c3:
+            try:
+                out["c3"] = bench_c3(fe, local_rank, cpu=not args.no_cpu_baseline)
+            except Exception as ex:
+                import traceback
+                out["c3"] = {"error": repr(ex), "trace": traceback.format_exc()[-800:]}
         if world == 1 and not args.no_cpu_baseline:
             try:
                 out["node_create"] = bench_node_create(fe)
@@ -680,6 +818,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-c4", action="store_true", help="skip the 2000-frame sequence (config C4) sub-measurement")
     ap.add_argument("--c4-frames", type=int, default=C4_FRAMES)
+    ap.add_argument("--no-c3", action="store_true", help="skip the SIFT-128 (config C3) sub-measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <map>
 #include <set>
+#include <string>
 
 #include "node.hpp"
 
@@ -98,6 +99,9 @@ class GraphManager {
     int optimizer_skip_step = 1;
     double optimizer_iterations = 0.01, huber_delta = 1.0;
     bool valid_odometry = false;  // !odom_frame_name.empty()
+    // fixationOfVertices strategy (graph_manager.cpp:911-937, parameter_server.cpp:118): "first" (default), "previous",
+    // "largest_loop", "inaffected" (the reference's benchmark setting, test/test_settings.launch:94)
+    std::string pose_relative_to = "first";
   };
   Params params;
   uint64_t seed = 0;
@@ -112,6 +116,8 @@ class GraphManager {
   MatchingResult curr_best_result_;
   unsigned loop_closures_edges = 0, sequential_edges = 0;
   double last_chi2 = 0.0;
+  int earliest_loop_closure_node_ = 0;         // graph_manager.h:356
+  std::set<int> fixed_ids_;                    // vertices with setFixed(true) (persist between optimisations like g2o's flags)
 
   ~GraphManager() {
     for (auto& kv : graph_) delete kv.second;
@@ -131,9 +137,11 @@ class GraphManager {
 
   // ---- graph_manager.cpp:681-782
   bool addNode(Node* new_node) {
-    if ((int)new_node->feature_locations_2d_.size() < params.min_matches &&
-        (int)new_node->feature_locations_3d_.size() < params.min_matches)
-      return false;
+    // the reference gates on feature_locations_2d_ only (:687); nodes built from bare features (no 2-D keypoints) fall back
+    // to their 3-D feature count
+    const size_t nfeat = new_node->feature_locations_2d_.empty() ? new_node->feature_locations_3d_.size()
+                                                                 : new_node->feature_locations_2d_.size();
+    if ((int)nfeat < params.min_matches) return false;
     if (graph_.empty()) {
       firstNode(new_node);
       return true;
@@ -142,11 +150,29 @@ class GraphManager {
     const bool found_match = nodeComparisons(new_node, edge_to_last_keyframe_found);
     if (found_match) {
       graph_[new_node->id_] = new_node;
-      // earliest_loop_closure_node_ == new id unless pose_relative_to == "largest_loop" (:438)
-      if (!edge_to_last_keyframe_found && new_node->id_ > keyframe_ids_.back()) keyframe_ids_.push_back(new_node->id_ - 1);
+      if (!edge_to_last_keyframe_found && earliest_loop_closure_node_ > keyframe_ids_.back())  // :731
+        keyframe_ids_.push_back(new_node->id_ - 1);
       if (params.optimizer_skip_step > 0 && (int)estimates_.size() % params.optimizer_skip_step == 0) optimizeGraph();
+    } else if (graph_.size() == 1) {
+      // only one node so far and it has fewer features: the new node replaces it (:760-767)
+      Node* first = graph_.begin()->second;
+      const size_t nfirst = first->feature_locations_2d_.empty() ? first->feature_locations_3d_.size() : first->feature_locations_2d_.size();
+      if (nfeat > nfirst) {
+        resetGraph();
+        firstNode(new_node);
+        return true;
+      }
     }
     return found_match;
+  }
+
+  void resetGraph() {  // GraphManager::resetGraph as far as this shim keeps state
+    for (auto& kv : graph_) delete kv.second;
+    graph_.clear(); keyframe_ids_.clear(); edges_.clear(); meas_.clear(); info_.clear(); active_.clear(); estimates_.clear();
+    adj_.clear(); fixed_ids_.clear();
+    curr_best_result_ = MatchingResult();
+    loop_closures_edges = sequential_edges = 0;
+    earliest_loop_closure_node_ = 0;
   }
 
   // ---- graph_manager.cpp:204-324
@@ -166,6 +192,7 @@ class GraphManager {
       std::map<int, int> weights;
       int sum = 0;
       for (int vid : geodesicBall(predecessor_id, params.geodesic_depth)) {
+        if (vid == new_node->id_) continue;  // (the reference can pick the new node itself here: a self-edge)
         if (!graph_.at(vid)->matchable_) continue;
         if (vid < predecessor_id - sequential_targets || (vid > predecessor_id && vid <= gsize - 1)) {
           weights[vid] = std::abs(predecessor_id - vid);
@@ -203,6 +230,7 @@ class GraphManager {
 
   // ---- graph_manager.cpp:811-898
   bool addEdgeToG2O(const LoadedEdge3D& edge, Node* n1, Node* n2, bool largeEdge, bool set_estimate) {
+    if (edge.id1 == edge.id2) return false;
     const bool v1 = estimates_.count(n1->id_) != 0, v2 = estimates_.count(n2->id_) != 0;
     if ((!v1 || !v2) && !largeEdge) return false;
     if (!v1 && !v2) return false;
@@ -224,6 +252,7 @@ class GraphManager {
     adj_[edge.id2].insert(edge.id1);
     if (std::abs(edge.id1 - edge.id2) > params.predecessor_candidates) loop_closures_edges++;
     else sequential_edges++;
+    earliest_loop_closure_node_ = std::min(earliest_loop_closure_node_, std::min(edge.id1, edge.id2));  // :894-895
     return true;
   }
 
@@ -235,15 +264,41 @@ class GraphManager {
     std::vector<int32_t> ij;
     gather(ids, poses, fixed, ij, meas, info);
     if (ij.empty()) return 0.0;
-    const double stop = break_criterion < 0 ? params.optimizer_iterations : break_criterion;
+    fixationOfVertices(ids, fixed);
+    const double stop = break_criterion > 0.0 ? break_criterion : params.optimizer_iterations;  // :942
     double chi2 = 0;
     int it = 0, cg = 0;
     check(rgbdslam_b200_posegraph_optimize((int)ids.size(), poses.data(), fixed.data(), (int)ij.size() / 2, ij.data(), meas.data(),
                                            info.data(), stop, params.huber_delta, &chi2, &it, &cg),
           "posegraph_optimize");
     for (size_t k = 0; k < ids.size(); k++) std::memcpy(estimates_[ids[k]].v, &poses[7 * k], sizeof(double) * 7);
+    // after the optimisation (:1031-1037): "inaffected" leaves every camera vertex fixed -- only vertices added afterwards are
+    // free in the next run --, every other strategy un-fixes them all
+    fixed_ids_.clear();
+    if (params.pose_relative_to == "inaffected") fixed_ids_.insert(ids.begin(), ids.end());
     last_chi2 = chi2;
     return chi2;
+  }
+
+  // fixationOfVertices (graph_manager.cpp:911-937).  `fixed` comes in with the persistent flags (fixed_ids_ + the first node,
+  // which firstNode fixes at the origin, :381).  "inaffected" has no branch there: the flags stay as the previous
+  // optimisation left them; its Dijkstra-selected vertex subset (:969-977) is overridden by the second
+  // initializeOptimization(cam_cam_edges_) (:989-992), so all edges are always active.
+  void fixationOfVertices(const std::vector<int>& ids, std::vector<uint8_t>& fixed) const {
+    const std::string& strategy = params.pose_relative_to;
+    auto index_of = [&](int id) { return (int)(std::lower_bound(ids.begin(), ids.end(), id) - ids.begin()); };
+    if (strategy == "previous" && graph_.size() > 2) {
+      std::fill(fixed.begin(), fixed.end(), 0);
+      fixed[index_of(graph_.at((int)graph_.size() - 2)->id_)] = 1;
+    } else if (strategy == "largest_loop") {
+      for (size_t k = 0; k < ids.size(); k++) fixed[k] = ids[k] < earliest_loop_closure_node_ ? 1 : 0;
+    } else if (strategy == "first") {
+      std::fill(fixed.begin(), fixed.end(), 0);
+      fixed[index_of(graph_.at(0)->id_)] = 1;
+    }
+    // an optimisation without any fixed vertex has a gauge freedom; g2o then fixes nothing either, but its damped LM
+    // still runs -- the PCG here needs one anchor
+    if (std::find(fixed.begin(), fixed.end(), 1) == fixed.end() && !fixed.empty()) fixed[0] = 1;
   }
 
   // ---- graph_manager.cpp:1106-1246
@@ -350,6 +405,7 @@ class GraphManager {
     const int num_keypoints = (int)std::max(new_node->feature_locations_2d_.size(), new_node->feature_locations_3d_.size());
     if (num_keypoints < params.min_matches && !params.keep_all_nodes) return false;
     new_node->id_ = (int)graph_.size();
+    earliest_loop_closure_node_ = new_node->id_;  // :444
     const size_t num_edges_before = edges_.size();
     edge_to_keyframe = false;
     const int sequentially_previous_id = graph_.rbegin()->second->id_;
@@ -405,7 +461,9 @@ class GraphManager {
       std::memset(&odom_edge.transform, 0, sizeof(odom_edge.transform));
       std::memset(&odom_edge.informationMatrix, 0, sizeof(odom_edge.informationMatrix));
       for (int i = 0; i < 4; i++) odom_edge.transform.m[5 * i] = 1.0;
-      for (int i = 0; i < 6; i++) odom_edge.informationMatrix.m[7 * i] = 1.0 / time_delta_sec;
+      // information = I / time_delta_sec (:647); nodes without stamps (dt == 0) would get an infinite information matrix
+      // (NaN in the linearisation): the time delta is clamped to 1 ms
+      for (int i = 0; i < 6; i++) odom_edge.informationMatrix.m[7 * i] = 1.0 / std::max(time_delta_sec, 1e-3);
       addEdgeToG2O(odom_edge, graph_[sequentially_previous_id], new_node, true, true);
       graph_[new_node->id_] = new_node;
       new_node->valid_tf_estimate_ = false;
@@ -425,7 +483,9 @@ class GraphManager {
       poses.insert(poses.end(), kv.second.v, kv.second.v + 7);
     }
     fixed.assign(ids.size(), 0);
-    if (!fixed.empty()) fixed[0] = 1;  // pose_relative_to = first (:933-936)
+    if (!fixed.empty()) fixed[0] = 1;  // firstNode: reference_pose->setFixed(true) (:381)
+    for (size_t k = 0; k < ids.size(); k++)
+      if (fixed_ids_.count(ids[k])) fixed[k] = 1;
     for (size_t e = 0; e < edges_.size(); e++) {
       if (!active_[e]) continue;
       ij.push_back(index[edges_[e].first]);

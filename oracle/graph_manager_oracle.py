@@ -1,4 +1,8 @@
-"""Host-side mirror of the reference's ONLINE graph front: which old nodes a new
+"""TEST INFRASTRUCTURE (host-logic oracle): Python twin of the product's C++ shim include/rgbdslam_b200/graph_manager.hpp,
+used by tests/ to drive the online front with either backend (CUDA library or CPU oracle).  The product implementation of
+this logic is the C++ shim; nothing in rgbdslam_v2_b200/ imports this module.
+
+Host-side mirror of the reference's ONLINE graph front: which old nodes a new
 node is compared with, which MatchingResults become edges, keyframes, the constant-position fallback, and when the
 optimiser runs.  Pure host logic (numpy); every compute step is a backend call -- the CUDA library in the product
 (`pipeline.GpuBackend`: the <= 12 comparisons of one new node are ONE `rgbdslam_b200_match_pairs` batch, the
@@ -20,8 +24,8 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-from .pipeline import mat_to_pose7
-from .synth import pose_compose
+from rgbdslam_v2_b200.pipeline import mat_to_pose7
+from rgbdslam_v2_b200.synth import pose_compose
 
 _M64 = (1 << 64) - 1
 
@@ -286,7 +290,7 @@ class GraphManager:
         dt_prev = abs(node.stamp - self.nodes[seq_prev].stamp)
         if (not found_trafo and valid_odometry) or (not found_trafo and keep_anyway) or (not predecessor_matched and dt_prev < 0.1):
             # constant position assumption :636-655 (information I / dt)
-            self.add_edge(seq_prev, node.id, np.eye(4), np.eye(6) / dt_prev, True, True)
+            self.add_edge(seq_prev, node.id, np.eye(4), np.eye(6) / max(dt_prev, 1e-3), True, True)
             self.nodes[node.id] = node
             node.valid_tf_estimate = False
             self.curr_best = dict(id1=seq_prev, n_inliers=0)

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "kernels.h"
+#include "posegraph.h"
 #include "state.h"
 
 namespace rb200 {
@@ -611,6 +612,7 @@ int rgbdslam_b200_shutdown(void) {
   cudaSetDevice(s.device);
   cudaDeviceSynchronize();
   s.release_workspaces();
+  posegraph_release();
   for (int k = 0; k < kSlots; k++) {
     for (int i = 0; i < 8; i++) cudaEventDestroy(s.ws[k].ev[i]);
     cudaEventDestroy(s.ws[k].ev_gather);

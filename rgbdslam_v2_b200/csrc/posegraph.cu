@@ -7,8 +7,8 @@
 // Kernels (all deterministic: fixed-order reductions, no atomics):
 //   pg_linearize_kernel : per edge  e, Ji, Jj, Huber weight -> blocks A=Ji'WJi, B=Jj'WJj, C=Ji'WJj, gi, gj
 //   pg_assemble_kernel  : per vertex (CSR of incident edges) H_vv = sum A|B, b_v = -sum g ; max diag
-//   pg_pcg_kernel       : whole block-Jacobi PCG in ONE cooperative launch (grid.sync between the phases);
-//                         matrix-free SpMV: y_v = (H_vv + lambda I) d_v + sum_inc (C d_j | C' d_i)
+//   pg_pcg_kernel       : whole block-Jacobi PCG in ONE cooperative launch, two grid barriers per iteration;
+//                         matrix-free SpMV: y_v = (H_vv + lambda I) s_v + sum_inc (C s_j | C' s_i)
 //   pg_update_kernel    : X <- X * fromVectorMQT(delta)      (VertexSE3::oplusImpl)
 //   pg_chi2_kernel      : sum rho(e'We) and sum e'We          (activeRobustChi2 / chi2)
 // Host: OptimizationAlgorithmLevenberg::solve bookkeeping + the optimizeGraphImpl stop rule
@@ -227,6 +227,7 @@ struct PcgArgs {
   int nv, ne;
   const int* off;
   const int* inc;
+  const int* oth;      // per incidence: the vertex at the other end of the edge
   const int2* ij;
   const uint8_t* fixed;
   const double* blk;   // per-edge blocks (C at +72)
@@ -235,6 +236,7 @@ struct PcgArgs {
   double* Minv;        // nv x 36
   double* x;           // out: nv x 6
   double* r;
+  double* s;           // M^-1 r
   double* d;
   double* q;
   double* part;        // grid partial sums (2 x gridDim)
@@ -250,138 +252,194 @@ __device__ __forceinline__ double warp_sum_d(double v) {
   return v;
 }
 
-// deterministic grid-wide sum: block partial -> global -> grid.sync -> every block adds the partials in order
-__device__ double grid_sum(cg::grid_group& grid, double v, double* part, double* sm) {
+// ---- block-Jacobi PCG with TWO grid barriers per iteration -----------------------------------------------------------
+// The textbook iteration needs a barrier after each of: the SpMV q = A d (every vertex reads its neighbours' d), the dot d.q,
+// the dot r.s, the update of d -- at 5000 vertices each of them is pure latency (37 us per iteration measured).  Written with
+//     q_{k+1} = A d_{k+1} = A s_{k+1} + beta_k q_k        (d_{k+1} = s_{k+1} + beta_k d_k,  s = M^-1 r)
+// the SpMV runs on s, which is complete as soon as the dot r.s is, so one iteration is two phases, each ending in one barrier
+// that also carries that phase's dot product:
+//   phase 1 (vertex-local)   x += alpha d ; r -= alpha q ; s = M^-1 r ; partial r.s              -> barrier -> beta
+//   phase 2 (SpMV on s)      q = A s + beta q ; d = s + beta d ; partial d.q                     -> barrier -> alpha
+// Same recurrences as g2o's LinearSolverPCG in exact arithmetic (carried residual, absolute tolerance on r'M^-1 r), different
+// rounding of q only.  Deterministic: vertex v is always handled by the same warp, dot products are reduced in a fixed order.
+__device__ __forceinline__ double block_partial(double v, double* sm) {  // fixed-order CTA sum, result in every thread
   v = warp_sum_d(v);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();  // sm may still be read by the previous reduction
   if (lane == 0) sm[warp] = v;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    double s = 0;
-    for (int w = 0; w < (int)(blockDim.x >> 5); w++) s += sm[w];
-    part[blockIdx.x] = s;
-  }
-  grid.sync();
-  double tot = 0;
-  for (int i = 0; i < (int)gridDim.x; i++) tot += part[i];
-  return tot;
+  double s = 0;
+  for (int w = 0; w < (int)(blockDim.x >> 5); w++) s += sm[w];
+  return s;
+}
+// every CTA's partial is in part[0 .. gridDim.x): every warp adds them in the same fixed order (strided by lane, then a butterfly)
+__device__ __forceinline__ double grid_total(const double* part) {
+  const int lane = threadIdx.x & 31;
+  double t = 0;
+  for (int i = lane; i < (int)gridDim.x; i += 32) t += __ldcg(part + i);
+  return warp_sum_d(t);
 }
 
-// y_v = (H_vv + lambda I) d_v + sum over incident edges of the off-diagonal block times the other end.
-// One warp per vertex; lanes split the incident edges.
-__device__ void spmv_vertex(const PcgArgs& a, int v, int lane, const double* __restrict__ vec, double* __restrict__ out) {
-  double acc[6] = {0, 0, 0, 0, 0, 0};
-  if (!a.fixed[v]) {
-    for (int p = a.off[v] + lane; p < a.off[v + 1]; p += 32) {
-      const int code = a.inc[p];
-      const int e = code >> 1;
-      const int2 vv = a.ij[e];
-      if (vv.x == vv.y) continue;
-      const double* C = a.blk + (size_t)e * kEdgeBlk + 72;
-      if ((code & 1) == 0) {  // v == i: C * d_j
-        const double* o = vec + 6 * (size_t)vv.y;
+// off-diagonal part of row block v applied to `vec` (lanes split the incident edges), summed over the warp
+__device__ __forceinline__ void spmv_offdiag(const PcgArgs& a, int v, int lane, const double* __restrict__ vec, double (&acc)[6]) {
 #pragma unroll
-        for (int r = 0; r < 6; r++)
+  for (int r = 0; r < 6; r++) acc[r] = 0;
+  for (int p = a.off[v] + lane; p < a.off[v + 1]; p += 32) {
+    const int code = a.inc[p];
+    const int other = a.oth[p];
+    if (other == v) continue;  // self edge: no off-diagonal block
+    const double* C = a.blk + (size_t)(code >> 1) * kEdgeBlk + 72;
+    const double* o = vec + 6 * (size_t)other;
+    double ov[6];
 #pragma unroll
-          for (int c = 0; c < 6; c++) acc[r] += C[6 * r + c] * o[c];
-      } else {  // v == j: C' * d_i
-        const double* o = vec + 6 * (size_t)vv.x;
+    for (int c = 0; c < 6; c++) ov[c] = __ldcg(o + c);
+    if ((code & 1) == 0) {  // v == i: C * d_j
 #pragma unroll
-        for (int r = 0; r < 6; r++)
+      for (int r = 0; r < 6; r++)
 #pragma unroll
-          for (int c = 0; c < 6; c++) acc[c] += C[6 * r + c] * o[r];
-      }
+        for (int c = 0; c < 6; c++) acc[r] += C[6 * r + c] * ov[c];
+    } else {  // v == j: C' * d_i
+#pragma unroll
+      for (int r = 0; r < 6; r++)
+#pragma unroll
+        for (int c = 0; c < 6; c++) acc[c] += C[6 * r + c] * ov[r];
     }
   }
 #pragma unroll
   for (int r = 0; r < 6; r++) acc[r] = warp_sum_d(acc[r]);
-  if (lane < 6) {
-    double s = 0;
-    if (!a.fixed[v]) {
-      const double* H = a.Hd + 36 * (size_t)v + 6 * lane;
-      const double* dv = vec + 6 * (size_t)v;
-#pragma unroll
-      for (int c = 0; c < 6; c++) s += H[c] * dv[c];
-      s += a.lambda * dv[lane];
-      double t = 0;
-#pragma unroll
-      for (int r = 0; r < 6; r++) t = (r == lane) ? acc[r] : t;
-      s += t;
-    }
-    out[6 * (size_t)v + lane] = s;
-  }
 }
 
-// LinearSolverPCG: block-Jacobi preconditioned CG on (H + lambda I) x = b; stops when r' M^-1 r <= tol where
-// tol = max(1e-6, 0.5 * final value of the previous solve) (g2o's absolute-tolerance mode).
-__global__ void __launch_bounds__(256) pg_pcg_kernel(PcgArgs a) {
+// block-Jacobi preconditioner: M^-1 = (H_vv + lambda I)^-1 per free vertex (own kernel: the Gauss-Jordan working set would
+// otherwise set the register budget of the PCG loop)
+__global__ void __launch_bounds__(128) pg_precond_kernel(int nv, const double* __restrict__ Hd, const uint8_t* __restrict__ fixed,
+                                                         double lambda, double* __restrict__ Minv) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= nv) return;
+  double A[36], Ai[36];
+  for (int i = 0; i < 36; i++) A[i] = Hd[36 * (size_t)v + i];
+  for (int k = 0; k < 6; k++) A[7 * k] += lambda;
+  const bool ok = !fixed[v] && inv6(A, Ai);
+  for (int i = 0; i < 36; i++) Minv[36 * (size_t)v + i] = ok ? Ai[i] : 0.0;
+}
+
+__global__ void __launch_bounds__(512, 1) pg_pcg_kernel(PcgArgs a) {
   cg::grid_group grid = cg::this_grid();
-  __shared__ double sm[8];
+  __shared__ double sm[16];
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int nthreads = gridDim.x * blockDim.x;
   const int lane = threadIdx.x & 31;
   const int gwarp = tid >> 5, nwarps = nthreads >> 5;
-  const int n = 6 * a.nv;
+  double* part_a = a.part;               // partials of r.s
+  double* part_b = a.part + gridDim.x;   // partials of d.q (two arrays: a CTA may already write the next phase's partial
+                                         // while another one still reads this phase's)
 
-  // preconditioner, x = 0, r = b, d = M^-1 r
-  for (int v = tid; v < a.nv; v += nthreads) {
-    double A[36], Ai[36];
-    for (int i = 0; i < 36; i++) A[i] = a.Hd[36 * (size_t)v + i];
-    for (int k = 0; k < 6; k++) A[7 * k] += a.lambda;
-    const bool ok = !a.fixed[v] && inv6(A, Ai);
-    for (int i = 0; i < 36; i++) a.Minv[36 * (size_t)v + i] = ok ? Ai[i] : 0.0;
+  // (the preconditioner M^-1 = (H_vv + lambda I)^-1 was written by pg_precond_kernel, launched just before on the same stream)
+  // x = 0, r = b, s = M^-1 r (kept in a.d until phase 2 turns it into d), dn = r.s
+  double loc = 0;
+  for (int v = gwarp; v < a.nv; v += nwarps) {
+    double rr = 0, sv = 0;
+    if (lane < 6) rr = a.b[6 * (size_t)v + lane];
+    double rv[6];
+#pragma unroll
+    for (int c = 0; c < 6; c++) rv[c] = __shfl_sync(0xffffffffu, rr, c);
+    if (lane < 6) {
+#pragma unroll
+      for (int c = 0; c < 6; c++) sv += a.Minv[36 * (size_t)v + 6 * lane + c] * rv[c];
+      a.x[6 * (size_t)v + lane] = 0.0;
+      a.r[6 * (size_t)v + lane] = rr;
+      a.s[6 * (size_t)v + lane] = sv;
+      a.d[6 * (size_t)v + lane] = 0.0;
+      a.q[6 * (size_t)v + lane] = 0.0;
+      loc += rr * sv;
+    }
+  }
+  {
+    const double p = block_partial(loc, sm);
+    if (threadIdx.x == 0) part_a[blockIdx.x] = p;
   }
   grid.sync();
-  double loc = 0;
-  for (int i = tid; i < n; i += nthreads) {
-    const int v = i / 6, rr = i % 6;
-    a.x[i] = 0.0;
-    const double ri = a.b[i];
-    a.r[i] = ri;
-    double s = 0;
-#pragma unroll
-    for (int c = 0; c < 6; c++) s += a.Minv[36 * (size_t)v + 6 * rr + c] * a.b[6 * (size_t)v + c];
-    a.d[i] = s;
-    loc += ri * s;
-  }
-  double dn = grid_sum(grid, loc, a.part, sm);
+  double dn = grid_total(part_a);
+  double beta = 0.0;  // first phase 2: d = s, q = A s
   int it = 0;
   bool breakdown = false;
-  for (; it < a.maxit; it++) {
-    if (dn <= a.tol) break;
-    for (int v = gwarp; v < a.nv; v += nwarps) spmv_vertex(a, v, lane, a.d, a.q);
-    grid.sync();
+  for (;;) {
+    // ---- phase 2: q = A s + beta q ; d = s + beta d ; partial d.q
     loc = 0;
-    for (int i = tid; i < n; i += nthreads) loc += a.d[i] * a.q[i];
-    const double dq = grid_sum(grid, loc, a.part + gridDim.x, sm);
+    for (int v = gwarp; v < a.nv; v += nwarps) {
+      const bool fx = a.fixed[v] != 0;
+      double acc[6];
+      if (!fx) spmv_offdiag(a, v, lane, a.s, acc);
+      if (lane < 6) {
+        double qn = 0, dnw = 0;
+        if (!fx) {
+          const double* H = a.Hd + 36 * (size_t)v + 6 * lane;
+          const double* sv = a.s + 6 * (size_t)v;
+          double t = 0;
+#pragma unroll
+          for (int c = 0; c < 6; c++) t += H[c] * sv[c];
+          t += a.lambda * sv[lane];
+          double o = 0;
+#pragma unroll
+          for (int r = 0; r < 6; r++) o = (r == lane) ? acc[r] : o;
+          t += o;
+          qn = t + beta * a.q[6 * (size_t)v + lane];
+          dnw = sv[lane] + beta * a.d[6 * (size_t)v + lane];
+        }
+        a.q[6 * (size_t)v + lane] = qn;
+        a.d[6 * (size_t)v + lane] = dnw;
+        loc += dnw * qn;
+      }
+    }
+    {
+      const double p = block_partial(loc, sm);
+      if (threadIdx.x == 0) part_b[blockIdx.x] = p;
+    }
+    grid.sync();
+    if (it >= a.maxit || dn <= a.tol) break;  // (the extra SpMV of the last round is the price of the two-barrier form)
+    const double dq = grid_total(part_b);
     if (!(dq > 0)) { breakdown = true; break; }
     const double alpha = dn / dq;
-    for (int i = tid; i < n; i += nthreads) {
-      a.x[i] += alpha * a.d[i];
-      a.r[i] -= alpha * a.q[i];  // recursive residual (g2o never resets it)
-    }
-    grid.sync();
-    // s = M^-1 r (kept in q), dn_new = r.s
+    // ---- phase 1: x += alpha d ; r -= alpha q (recursive residual: g2o never resets it) ; s = M^-1 r ; partial r.s
     loc = 0;
-    for (int i = tid; i < n; i += nthreads) {
-      const int v = i / 6, rr = i % 6;
-      double s = 0;
+    for (int v = gwarp; v < a.nv; v += nwarps) {
+      double rr = 0;
+      if (lane < 6) {
+        const size_t i = 6 * (size_t)v + lane;
+        a.x[i] += alpha * a.d[i];
+        rr = a.r[i] - alpha * a.q[i];
+        a.r[i] = rr;
+      }
+      double rv[6];
 #pragma unroll
-      for (int c = 0; c < 6; c++) s += a.Minv[36 * (size_t)v + 6 * rr + c] * a.r[6 * (size_t)v + c];
-      a.q[i] = s;
-      loc += a.r[i] * s;
+      for (int c = 0; c < 6; c++) rv[c] = __shfl_sync(0xffffffffu, rr, c);
+      if (lane < 6) {
+        double sv = 0;
+#pragma unroll
+        for (int c = 0; c < 6; c++) sv += a.Minv[36 * (size_t)v + 6 * lane + c] * rv[c];
+        a.s[6 * (size_t)v + lane] = sv;
+        loc += rr * sv;
+      }
     }
-    const double dn_new = grid_sum(grid, loc, a.part, sm);
-    const double beta = dn_new / dn;
-    dn = dn_new;
-    for (int i = tid; i < n; i += nthreads) a.d[i] = a.q[i] + beta * a.d[i];
+    {
+      const double p = block_partial(loc, sm);
+      if (threadIdx.x == 0) part_a[blockIdx.x] = p;
+    }
     grid.sync();
+    const double dn_new = grid_total(part_a);
+    beta = dn_new / dn;
+    dn = dn_new;
+    it++;
   }
-  grid.sync();  // (uniform) make sure nobody is still summing partials of the last reduction
   // computeScale(): sum x_j (lambda x_j + b_j)
   loc = 0;
+  const int n = 6 * a.nv;
   for (int i = tid; i < n; i += nthreads) loc += a.x[i] * (a.lambda * a.x[i] + a.b[i]);
-  const double scale = grid_sum(grid, loc, a.part + gridDim.x, sm);
+  {
+    const double p = block_partial(loc, sm);
+    if (threadIdx.x == 0) part_a[blockIdx.x] = p;
+  }
+  grid.sync();
+  const double scale = grid_total(part_a);
   if (tid == 0) {
     a.result[0] = (double)it;
     a.result[1] = dn;
@@ -451,9 +509,9 @@ __global__ void __launch_bounds__(256) pg_chi2_kernel(int ne, const double* __re
 // Host driver
 
 struct PgDevice {
-  DevBuf x, xtrial, meas, info, ij, fixed, off, inc, blk, Hd, b, Minv, dx, r, d, q, part, result, chipart, maxpart, per_edge;
+  DevBuf x, xtrial, meas, info, ij, fixed, off, inc, oth, blk, Hd, b, Minv, dx, r, sv, d, q, part, result, chipart, maxpart, per_edge;
   ~PgDevice() {
-    DevBuf* all[] = {&x, &xtrial, &meas, &info, &ij, &fixed, &off, &inc, &blk, &Hd, &b, &Minv, &dx, &r, &d, &q,
+    DevBuf* all[] = {&x, &xtrial, &meas, &info, &ij, &fixed, &off, &inc, &oth, &blk, &Hd, &b, &Minv, &dx, &r, &sv, &d, &q,
                      &part, &result, &chipart, &maxpart, &per_edge};
     for (DevBuf* bb : all) bb->release();
   }
@@ -465,8 +523,18 @@ struct PgDevice {
     if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
   } while (0)
 
+// The solver's device buffers live for the lifetime of the library (grow-only): a cudaMalloc / cudaFree pair per buffer and call
+// costs far more than the solve itself once the process holds gigabytes of pinned memory (measured: ~200 ms of cudaFree per call
+// in the 2000-frame sequence run against 30 ms inside the PCG kernels).  Guarded by the state mutex like every entry point.
+static PgDevice* g_pg_dev = nullptr;
+void posegraph_release() {
+  delete g_pg_dev;
+  g_pg_dev = nullptr;
+}
+
 struct PgCtx {
-  PgDevice dev;
+  PgDevice& dev;
+  explicit PgCtx(PgDevice& d) : dev(d) {}
   int nv = 0, ne = 0;
   double delta = 1.0;
   cudaStream_t st = nullptr;
@@ -531,6 +599,7 @@ static int pg_pcg(PgCtx& c, double lambda, double* scale, bool* ok) {
   a.ne = c.ne;
   a.off = (const int*)c.dev.off.ptr;
   a.inc = (const int*)c.dev.inc.ptr;
+  a.oth = (const int*)c.dev.oth.ptr;
   a.ij = (const int2*)c.dev.ij.ptr;
   a.fixed = (const uint8_t*)c.dev.fixed.ptr;
   a.blk = (const double*)c.dev.blk.ptr;
@@ -541,6 +610,7 @@ static int pg_pcg(PgCtx& c, double lambda, double* scale, bool* ok) {
   a.r = (double*)c.dev.r.ptr;
   a.d = (double*)c.dev.d.ptr;
   a.q = (double*)c.dev.q.ptr;
+  a.s = (double*)c.dev.sv.ptr;
   a.part = (double*)c.dev.part.ptr;
   a.result = (double*)c.dev.result.ptr;
   a.lambda = lambda;
@@ -548,7 +618,10 @@ static int pg_pcg(PgCtx& c, double lambda, double* scale, bool* ok) {
   a.maxit = 6 * c.nv;
   void* args[] = {&a};
   const auto t0 = std::chrono::steady_clock::now();
-  PG_CUDA(cudaLaunchCooperativeKernel((void*)pg_pcg_kernel, dim3(c.pcg_grid), dim3(256), args, 0, c.st));
+  pg_precond_kernel<<<(c.nv + 127) / 128, 128, 0, c.st>>>(c.nv, a.Hd, a.fixed, lambda, a.Minv);
+  PG_CUDA(cudaGetLastError());
+  c.launches++;
+  PG_CUDA(cudaLaunchCooperativeKernel((void*)pg_pcg_kernel, dim3(c.pcg_grid), dim3(512), args, 0, c.st));
   c.launches++;
   double res[4];
   PG_CUDA(cudaMemcpyAsync(res, c.dev.result.ptr, sizeof(res), cudaMemcpyDeviceToHost, c.st));
@@ -622,13 +695,14 @@ int posegraph_optimize(int nv, double* poses, const uint8_t* fixed, int ne, cons
                        int* cg_iters_out, double* per_edge_chi2, bool optimize) {
   State& s = g_state;
   const auto t_begin = std::chrono::steady_clock::now();
-  PgCtx c;
+  if (!g_pg_dev) g_pg_dev = new PgDevice();
+  PgCtx c(*g_pg_dev);
   c.nv = nv;
   c.ne = ne;
   c.delta = huber_delta;
   c.st = s.stream;
   // CSR of incident edges (edge order => deterministic sums)
-  std::vector<int> off(nv + 1, 0), inc(2 * (size_t)ne);
+  std::vector<int> off(nv + 1, 0), inc(2 * (size_t)ne), oth(2 * (size_t)ne);
   for (int k = 0; k < ne; k++) {
     if (ij[2 * k] < 0 || ij[2 * k] >= nv || ij[2 * k + 1] < 0 || ij[2 * k + 1] >= nv) {
       set_error("posegraph: edge vertex index out of range");
@@ -641,7 +715,9 @@ int posegraph_optimize(int nv, double* poses, const uint8_t* fixed, int ne, cons
   {
     std::vector<int> cur(off.begin(), off.end() - 1);
     for (int k = 0; k < ne; k++) {
+      oth[cur[ij[2 * k]]] = ij[2 * k + 1];
       inc[cur[ij[2 * k]]++] = (k << 1) | 0;
+      oth[cur[ij[2 * k + 1]]] = ij[2 * k];
       inc[cur[ij[2 * k + 1]]++] = (k << 1) | 1;
     }
   }
@@ -654,17 +730,17 @@ int posegraph_optimize(int nv, double* poses, const uint8_t* fixed, int ne, cons
       (rc = d.off.ensure(4 * (nv_ + 1))) || (rc = d.inc.ensure(8 * ne_)) || (rc = d.blk.ensure(8 * kEdgeBlk * ne_)) ||
       (rc = d.Hd.ensure(288 * nv_)) || (rc = d.b.ensure(48 * nv_)) || (rc = d.Minv.ensure(288 * nv_)) ||
       (rc = d.dx.ensure(48 * nv_)) || (rc = d.r.ensure(48 * nv_)) || (rc = d.d.ensure(48 * nv_)) ||
-      (rc = d.q.ensure(48 * nv_)) || (rc = d.result.ensure(64)) || (rc = d.chipart.ensure(16 * (size_t)chi_blocks)) ||
+      (rc = d.q.ensure(48 * nv_)) || (rc = d.sv.ensure(48 * nv_)) || (rc = d.oth.ensure(8 * ne_)) || (rc = d.result.ensure(64)) || (rc = d.chipart.ensure(16 * (size_t)chi_blocks)) ||
       (rc = d.maxpart.ensure(8 * (size_t)max_blocks)) || (rc = d.per_edge.ensure(8 * ne_)))
     return rc;
   // cooperative grid: all co-resident blocks of the PCG kernel
   int per_sm = 0;
-  PG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pg_pcg_kernel, 256, 0));
+  PG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pg_pcg_kernel, 512, 0));
   if (per_sm < 1) {
     set_error("posegraph: PCG kernel cannot be made resident");
     return RGBDSLAM_B200_ERR_CUDA;
   }
-  c.pcg_grid = s.sm_count * (per_sm > 2 ? 2 : per_sm);
+  c.pcg_grid = s.sm_count;  // one 512-thread CTA per SM: the barrier cost grows with the CTA count, the work per iteration is tiny
   if ((rc = d.part.ensure(16 * (size_t)c.pcg_grid))) return rc;
   cudaStream_t st = c.st;
   PG_CUDA(cudaMemcpyAsync(d.x.ptr, poses, 56 * (size_t)nv, cudaMemcpyHostToDevice, st));
@@ -675,6 +751,7 @@ int posegraph_optimize(int nv, double* poses, const uint8_t* fixed, int ne, cons
     PG_CUDA(cudaMemcpyAsync(d.info.ptr, info, 288 * (size_t)ne, cudaMemcpyHostToDevice, st));
     PG_CUDA(cudaMemcpyAsync(d.ij.ptr, ij, 8 * (size_t)ne, cudaMemcpyHostToDevice, st));
     PG_CUDA(cudaMemcpyAsync(d.inc.ptr, inc.data(), 8 * (size_t)ne, cudaMemcpyHostToDevice, st));
+    PG_CUDA(cudaMemcpyAsync(d.oth.ptr, oth.data(), 8 * (size_t)ne, cudaMemcpyHostToDevice, st));
   }
   PG_CUDA(cudaStreamSynchronize(st));  // host vectors (off/inc) go out of scope safely
 

