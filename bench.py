@@ -324,17 +324,6 @@ C3_KP = 2000
 C3_PAIRS = 64
 
 
-def _c3_descriptors(rng, n, kind):
-    """SIFT-like 128-d rows.  'sift': non-negative, gamma-distributed magnitudes, values 0..255 (cv::SIFT statistics, fed through
-    RootSIFT); 'siftgpu': unit L2 norm, clipped at 0.2 and renormalised (what SiftGPU hands to its matcher)."""
-    if kind == "sift":
-        return np.minimum(rng.gamma(0.6, 30.0, size=(n, 128)), 255.0).astype(np.float32)
-    d = rng.gamma(0.6, 1.0, size=(n, 128)).astype(np.float32)
-    d /= np.linalg.norm(d, axis=1, keepdims=True)
-    d = np.minimum(d, 0.2)
-    return (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
-
-
 def bench_c3(fe, local_rank, cpu=True):
     """BASELINE config C3: SIFT 128-d float descriptors, 2000 keypoints per frame, the distance matrix as a bf16 tensor-core
     GEMM (ratio / uniqueness matcher = the FLANN branch node.cpp:610-667 with an exact search) and the SiftGPU matcher (u8
@@ -354,21 +343,9 @@ def bench_c3(fe, local_rank, cpu=True):
         out["peak_source"] = "fallback 1701 TF/s"
     for kind, matcher in (("sift", 0), ("siftgpu", 1)):
         fe.set_sift_matcher(matcher)
-        frames = []
-        older_d = _c3_descriptors(rng, C3_KP, kind)
-        b0 = synth.make_pair(9000, C3_KP, overlap=0.5)
-        xyz_prev = b0["xyz_older"]
-        hs = [fe.node_from_sift(0, older_d, xyz_prev)]
-        host = [(older_d, xyz_prev)]
-        for k in range(C3_PAIRS):
-            b = synth.make_pair(9001 + k, C3_KP, overlap=0.5)
-            d = _c3_descriptors(rng, C3_KP, kind)
-            sel = rng.permutation(C3_KP)[: C3_KP // 2]
-            noise = rng.normal(0, 5.0 if kind == "sift" else 0.01, (len(sel), 128)).astype(np.float32)
-            d[sel] = np.abs(host[-1][0][sel] + noise)
-            host.append((d, b["xyz_newer"]))
-            hs.append(fe.node_from_sift(k + 1, d, b["xyz_newer"]))
-        newer, older = hs[1:], hs[:-1]
+        pairs = [synth.make_pair_sift(9000 + k, C3_KP, overlap=0.5, kind=kind) for k in range(C3_PAIRS)]
+        newer = [fe.node_from_sift(2 * k + 1, q["desc_newer"], q["xyz_newer"]) for k, q in enumerate(pairs)]
+        older = [fe.node_from_sift(2 * k, q["desc_older"], q["xyz_older"]) for k, q in enumerate(pairs)]
         for _ in range(3):
             res, _, _ = fe.match_node_pairs(newer, older, seed=5, want_matches=False)
         ts, kern = [], []
@@ -391,18 +368,24 @@ def bench_c3(fe, local_rank, cpu=True):
                               "algorithmic_flops_per_launch": flops}}
         entry["roofline"]["frac"] = entry["roofline"]["achieved"] / entry["roofline"]["peak"]
         # end to end: host descriptors in (upload + RootSIFT / tile preparation inside), host results out
-        t0 = time.perf_counter()
-        hh = [fe.node_from_sift(1000 + i, d, x) for i, (d, x) in enumerate(host)]
-        fe.match_node_pairs(hh[1:], hh[:-1], seed=5, want_matches=False)
-        e2e = time.perf_counter() - t0
-        for h in hh:
-            fe.node_destroy(h)
-        entry["e2e"] = {"pairs_per_s": C3_PAIRS / e2e, "h2d_bytes": int(len(host) * C3_KP * (512 + 16)), "note": "node_from_sift per frame (synchronous uploads) + one batched match"}
+        def e2e_pass():
+            t0 = time.perf_counter()
+            hn = [fe.node_from_sift(5000 + 2 * k + 1, q["desc_newer"], q["xyz_newer"]) for k, q in enumerate(pairs)]
+            ho = [fe.node_from_sift(5000 + 2 * k, q["desc_older"], q["xyz_older"]) for k, q in enumerate(pairs)]
+            fe.match_node_pairs(hn, ho, seed=5, want_matches=False)
+            dt = time.perf_counter() - t0
+            for h in hn + ho:
+                fe.node_destroy(h)
+            return dt
+        e2e_pass()
+        e2e = min(e2e_pass() for _ in range(2))
+        entry["e2e"] = {"pairs_per_s": C3_PAIRS / e2e, "h2d_bytes": int(2 * C3_PAIRS * C3_KP * (512 + 16)),
+                        "note": "node_from_sift per frame (synchronous uploads, RootSIFT + tile preparation) + one batched match"}
         if matcher == 0:
             from oracle import sift_oracle  # checker: exact float64 2-NN
             same = []
             for k in range(4):
-                q, t = host[k + 1][0], host[k][0]
+                q, t = pairs[k]["desc_newer"], pairs[k]["desc_older"]
                 idx, _ = fe.knn2_l2(q, t)
                 oidx, _ = sift_oracle.knn2_exact(sift_oracle.root_sift(q), sift_oracle.root_sift(t))
                 same.append(float((idx[:, 0] == oidx[:, 0]).mean()))
@@ -410,23 +393,23 @@ def bench_c3(fe, local_rank, cpu=True):
             if cpu:
                 import cv2
                 cv2.setNumThreads(usable_cpus())
-                q = sift_oracle.root_sift(host[1][0]); t = sift_oracle.root_sift(host[0][0])
+                rs = [(sift_oracle.root_sift(q["desc_newer"]), sift_oracle.root_sift(q["desc_older"])) for q in pairs[:4]]
                 bf = cv2.BFMatcher(cv2.NORM_L2)
-                bf.knnMatch(q, t, k=2)
+                bf.knnMatch(rs[0][0], rs[0][1], k=2)
                 t0 = time.perf_counter()
-                for k in range(4):
-                    bf.knnMatch(sift_oracle.root_sift(host[k + 1][0]), sift_oracle.root_sift(host[k][0]), k=2)
+                for q, t in rs:
+                    bf.knnMatch(q, t, k=2)
                 t_bf = (time.perf_counter() - t0) / 4
                 fl = cv2.FlannBasedMatcher(dict(algorithm=1, trees=4), dict(checks=16))  # node.cpp:503-510, 1573-1581
                 t0 = time.perf_counter()
-                for k in range(4):
-                    fl.knnMatch(sift_oracle.root_sift(host[k + 1][0]), sift_oracle.root_sift(host[k][0]), k=2)
+                for q, t in rs:
+                    fl.knnMatch(q, t, k=2)
                 t_fl = (time.perf_counter() - t0) / 4
                 entry["cpu_baseline"] = {"cv2_bfmatcher_knn2_pairs_per_s": 1.0 / t_bf, "cv2_flann_kdtree4_checks16_pairs_per_s": 1.0 / t_fl,
                                          "cores": usable_cpus(), "kind": "reference dependency (cv2 4.13) -- matching stage only, no RANSAC",
                                          "sample": "4 pairs of the same workload"}
         out["ratio_matcher" if matcher == 0 else "siftgpu_matcher"] = entry
-        for h in hs:
+        for h in newer + older:
             fe.node_destroy(h)
     fe.set_sift_matcher(0)
     return out

@@ -534,37 +534,46 @@ __global__ void __launch_bounds__(kTc256Threads, 1) tc_match256_kernel(const Ham
           } else if (MODE == 2) {
             // SiftGPU RowMatch / ColMatch bookkeeping (ProgramCU.cu:1708-1736, 1463-1478, 1771-1777): strict >, only
             // positive dots register, the runner-up VALUE counts duplicates of the maximum.
+            // common case first: a dot product below the current best only feeds the runner-up value (one IMNMX); the 64-bit
+            // (dot, tie priority) key is built only for candidates that reach the best dot product
+            const int nvalid = item.nsearch - col0;  // columns j < nvalid exist
+            int best_dot = u8_best >= 0 ? (int)(u8_best >> 17) : 0;
 #pragma unroll
             for (int j = 0; j < 32; j++) {
-              const int col = col0 + j;
-              const int dv = (int)v[j];
-              if (col < item.nsearch && dv > 0) {
+              const int dv = j < nvalid ? (int)v[j] : 0;  // dot products are >= 0 (unsigned operands); 0 never registers
+              if (dv >= best_dot && dv > 0) {
+                const int col = col0 + j;
                 const int prio = item.pad_ ? col : (((col & 31) << 12) | (col >> 5));
                 const long long key = ((long long)dv << 17) | (long long)(0x1FFFF - prio);
                 if (key > u8_best) {
                   if (u8_best >= 0) u8_next = max(u8_next, (int)(u8_best >> 17));
                   u8_best = key;
+                  best_dot = dv;
                 } else {
                   u8_next = max(u8_next, dv);
                 }
+              } else {
+                u8_next = max(u8_next, dv);
               }
             }
           } else {
+            // |b|^2 of the chunk's 32 train rows: one coalesced load per lane, handed round by shuffles (a global load per
+            // element inside the branchy insertion made this epilogue 20 x slower than the MMAs it drains); columns past the
+            // last train row get +inf, i.e. a score of -inf that never enters the list
+            const float bn_l = (col0 + lane < item.nsearch) ? __ldg(item.bnorm + col0 + lane) : __int_as_float(0x7f800000);
 #pragma unroll
             for (int j = 0; j < 32; j++) {
-              const int col = col0 + j;
-              if (col < item.nsearch) {
-                const float sc = fmaf(2.f, __uint_as_float(v[j]), -__ldg(item.bnorm + col));
-                if (sc > s3) {
-                  if (sc > s2) {
-                    s3 = s2; i3 = i2;
-                    if (sc > s1) {
-                      s2 = s1; i2 = i1;
-                      if (sc > s0) { s1 = s0; i1 = i0; s0 = sc; i0 = col; }
-                      else { s1 = sc; i1 = col; }
-                    } else { s2 = sc; i2 = col; }
-                  } else { s3 = sc; i3 = col; }
-                }
+              const float sc = fmaf(2.f, __uint_as_float(v[j]), -__shfl_sync(0xffffffffu, bn_l, j));
+              if (sc > s3) {  // rare after the first tiles: insert (ties keep the earlier = lower index)
+                const int col = col0 + j;
+                if (sc > s2) {
+                  s3 = s2; i3 = i2;
+                  if (sc > s1) {
+                    s2 = s1; i2 = i1;
+                    if (sc > s0) { s1 = s0; i1 = i0; s0 = sc; i0 = col; }
+                    else { s1 = sc; i1 = col; }
+                  } else { s2 = sc; i2 = col; }
+                } else { s3 = sc; i3 = col; }
               }
             }
           }

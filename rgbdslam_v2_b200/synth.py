@@ -74,6 +74,39 @@ def make_pair(seed: int, n_kp: int = 1000, overlap: float | None = None, max_tra
                 xyz_older=to4(p_old), T_true=T, n_common=n_common)
 
 
+def sift_like(rng: np.random.Generator, n: int, kind: str = "sift") -> np.ndarray:
+    """128-d float descriptors with SIFT-like statistics.  'sift': non-negative, gamma-distributed magnitudes, values 0..255 (what
+    cv::SIFT emits; Node applies RootSIFT); 'siftgpu': unit L2 norm, clipped at 0.2 and renormalised (SiftGPU's output)."""
+    if kind == "sift":
+        return np.minimum(rng.gamma(0.6, 30.0, size=(n, 128)), 255.0).astype(np.float32)
+    d = rng.gamma(0.6, 1.0, size=(n, 128)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d = np.minimum(d, 0.2)
+    return (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+
+
+def make_pair_sift(seed: int, n_kp: int = 2000, overlap: float = 0.5, kind: str = "sift", **kw):
+    """make_pair with 128-d float descriptors (BASELINE config C3): same geometry / noise model, the common features of the
+    newer frame carry noisy copies of the older frame's descriptors."""
+    p = make_pair(seed, n_kp, overlap=overlap, **kw)
+    rng = np.random.default_rng(seed + 7919)
+    # correspondences of the binary generator: a common feature's descriptor is a few-bit-flip copy of its older twin
+    d_old = sift_like(rng, n_kp, kind)
+    d_new = sift_like(rng, n_kp, kind)
+    bits_o = np.unpackbits(p["desc_older"], axis=1)
+    bits_n = np.unpackbits(p["desc_newer"], axis=1)
+    # exact nearest older row for each newer row (256-bit Hamming, blockwise matmul on +-1 vectors)
+    so = bits_o.astype(np.float32) * 2 - 1
+    sn = bits_n.astype(np.float32) * 2 - 1
+    dots = sn @ so.T
+    nn = dots.argmax(1)
+    common = dots[np.arange(n_kp), nn] > 256 - 2 * 70  # hd < 70: flipped copies have hd ~ 256 * [0.02, 0.2]
+    noise = rng.normal(0, 5.0 if kind == "sift" else 0.01, (int(common.sum()), 128)).astype(np.float32)
+    d_new[common] = np.abs(d_old[nn[common]] + noise)
+    return dict(desc_newer=d_new, xyz_newer=p["xyz_newer"], desc_older=d_old, xyz_older=p["xyz_older"], T_true=p["T_true"],
+                n_common=int(common.sum()))
+
+
 def make_batch(npairs: int, n_kp: int = 1000, seed0: int = 0, **kw):
     """Concatenated host buffers for match_pairs_host / the oracle batch driver."""
     pairs = [make_pair(seed0 + i, n_kp, **kw) for i in range(npairs)]
