@@ -320,6 +320,102 @@ def bench_posegraph(fe):
             "sample_1000V_6000E": {"gpu_seconds": dts, "cpu_oracle_seconds": dto, "cpu_threads": 1}}
 
 
+def bench_c2_rendered(fe, local_rank, cpu=True):
+    """The C2 step on a harder, more realistic workload (SURVEY 8d specified C2 on the rendered-frame generator): nodes built by
+    rgbdslam_b200_nodes_create from rendered 640x480 frames (real, correlated ORB descriptors), 256 pairs per batch of which
+    HALF pair a frame with a frame of a DIFFERENT scene (no true correspondences: the reference's loop-closure candidate lists
+    are dominated by such pairs -- they run all 200 RANSAC iterations and fail), the other half with a frame 1-8 steps back."""
+    import ctypes as C
+    import torch
+    from rgbdslam_v2_b200 import synth
+    from rgbdslam_v2_b200._capi import PAIR_RESULT_DTYPE, default_params
+    dev = torch.device("cuda", local_rank)
+    K4 = (synth.FX, synth.FY, synth.CX, synth.CY)
+    prm = default_params(); prm.depth_cov_z0 = 2.0; prm.max_keypoints = N_KP
+    old = fe.params
+    fe.params = prm
+    fe._check(fe.lib.rgbdslam_b200_init(local_rank, C.byref(prm)))
+    out = {}
+    try:
+        nA, nB, NB = 300, 160, 5
+        poses = synth.trajectory(2000)
+        hs = []
+        for tex, n, off in ((7, nA, 0), (8, nB, 700)):
+            g_d, d_d = synth.render_frames_torch(poses[off:off + n], dev, first_index=off, tex_seed=tex)
+            det = fe.detector_create()
+            h, nf = fe.nodes_create(det, g_d.cpu().numpy(), d_d.cpu().numpy(), None, K4, mask_from_depth=True)
+            fe.detector_destroy(det)
+            hs.append((h, nf))
+        (hA, nfA), (hB, nfB) = hs
+        rng = np.random.default_rng(5)
+        batches = []
+        for b in range(NB):
+            newer, older = [], []
+            for i in range(PAIRS_PER_GPU):
+                k = int(rng.integers(10, nA))
+                newer.append(hA[k])
+                older.append(hB[int(rng.integers(0, nB))] if i % 2 else hA[k - int(rng.choice([1, 2, 3, 5, 8]))])
+            res = torch.zeros(PAIRS_PER_GPU * PAIR_RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+            batches.append((np.array(newer, np.uint64), np.array(older, np.uint64), res.numpy().view(PAIR_RESULT_DTYPE), res))
+
+        def run(K):
+            for k in range(K):
+                if k >= NB:
+                    fe.wait_slot(1 + (k - NB) % NB)
+                nw, ol, r, _ = batches[k % NB]
+                fe.submit_node_pairs(1 + k % NB, nw, ol, (r, None, None), seed=SEED, first_pair_index=(k % NB) * PAIRS_PER_GPU)
+            for k in range(max(0, K - NB), K):
+                fe.wait_slot(1 + k % NB)
+        run(2 * NB)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter(); run(20); torch.cuda.synchronize(); probe = (time.perf_counter() - t0) / 20
+        K = max(20, int(np.ceil(MIN_TIMED_MS * 1e-3 / probe)))
+        t0 = time.perf_counter(); run(K); torch.cuda.synchronize(); dt = time.perf_counter() - t0
+        sync_dev = []
+        for _ in range(5):
+            nw, ol, r, _ = batches[0]
+            fe.match_node_pairs(nw, ol, seed=SEED, first_pair_index=0, out=(r, None, None))
+            sync_dev.append(fe.last_timing(0))
+        r0 = batches[0][2]
+        out = {"workload": f"C2 on rendered frames: {PAIRS_PER_GPU} pairs x <= {N_KP} ORB kp per batch, nodes from rgbdslam_b200_nodes_create "
+                           f"(mean {float(np.mean(nfA)):.0f} features), 50 % of the pairs across two different scenes (no overlap), "
+                           f"{NB} batches in flight",
+               "value": PAIRS_PER_GPU * K / dt, "unit": UNIT, "ms_per_step": 1e3 * dt / K, "timed_steps": K,
+               "synchronous_device_ms_per_step": statistics.median(t for _, t in sync_dev),
+               "hamming_kernel_ms": statistics.median(h for h, _ in sync_dev),
+               "valid_fraction": float((r0["id1"] >= 0).mean()),
+               "valid_fraction_same_scene_pairs": float((r0["id1"][0::2] >= 0).mean()),
+               "valid_fraction_cross_scene_pairs": float((r0["id1"][1::2] >= 0).mean())}
+        if cpu:
+            from oracle import oracle  # CPU arm on the same features (the GPU-built nodes are bit-identical to the cv2 pipeline's)
+            feats = {}
+            nw, ol, _, _ = batches[0]
+            for h in set(nw.tolist()) | set(ol.tolist()):
+                feats[h] = fe.node_download(int(h))
+            cat = lambda hh, j: np.ascontiguousarray(np.concatenate([feats[int(x)][j] for x in hh]))
+            n_n = np.array([len(feats[int(x)][0]) for x in nw], np.int32); n_o = np.array([len(feats[int(x)][0]) for x in ol], np.int32)
+            dn, xn, do, xo = cat(nw, 0), cat(nw, 1), cat(ol, 0), cat(ol, 1)
+            oprm = oracle.make_params(depth_cov_z0=2.0)
+            cores = usable_cpus()
+            best = None
+            for _ in range(3):
+                t0 = time.perf_counter()
+                ores, _, _ = oracle.match_pairs(oprm, dn, xn, n_n, do, xo, n_o, np.arange(PAIRS_PER_GPU, dtype=np.int32) + 1,
+                                                np.arange(PAIRS_PER_GPU, dtype=np.int32), seed=SEED, first_pair_index=0, threads=cores,
+                                                want_matches=False)
+                t = time.perf_counter() - t0
+                best = t if best is None else min(best, t)
+            out["cpu_baseline"] = {"value": PAIRS_PER_GPU / best, "unit": UNIT, "cores": cores, "kind": "port",
+                                   "sample": "one 256-pair batch of the same workload, best of 3, OpenMP over pairs",
+                                   "valid_flag_agreement": float(((ores["id1"] >= 0) == (r0["id1"] >= 0)).mean())}
+        for h in hA + hB:
+            fe.node_destroy(h)
+    finally:
+        fe.params = old
+        fe._check(fe.lib.rgbdslam_b200_init(local_rank, C.byref(old)))
+    return out
+
+
 C3_KP = 2000
 C3_PAIRS = 64
 
@@ -463,7 +559,11 @@ def bench_sequence(fe, local_rank, rank, world, comm, n_frames=C4_FRAMES, with_o
                 handles, nfeat = fe.nodes_create(det, gray[:nf], depth[:nf], None, K4, ids=np.arange(nf, dtype=np.int32),
                                                  mask_from_depth=True)
             else:
-                handles, nfeat = fe.nodes_create_sharded(det, comm, nf, gray, depth, None, K4, mask_from_depth=True)
+                # this rank's block of the first nf frames (for nf < n_frames -- the warm-up -- the block is cut from the rank's
+                # own shard: wrong frames, right sizes)
+                from rgbdslam_v2_b200.sharding import frame_shard
+                own = len(frame_shard(nf, rank, world))
+                handles, nfeat = fe.nodes_create_sharded(det, comm, nf, gray[:own], depth[:own], None, K4, mask_from_depth=True)
             t["nodes"] = time.perf_counter() - t0
             pp = pairs[pairs[:, 0] < nf]
             per_p = -(-len(pp) // world)
@@ -761,6 +861,11 @@ def run_ours(args, rank, local_rank, world):
                           "cpu_reference_path_ate_vs_ground_truth_m": op.get("ate_oracle_vs_gt_m"),
                           "cpu_reference_path_frames": op.get("frames"), "target": "within 1 mm of the reference path"}
         if world == 1 and not args.no_c3:
+            try:
+                out["c2_rendered"] = bench_c2_rendered(fe, local_rank, cpu=not args.no_cpu_baseline)
+            except Exception as ex:
+                import traceback
+                out["c2_rendered"] = {"error": repr(ex), "trace": traceback.format_exc()[-800:]}
             try:
                 out["c3"] = bench_c3(fe, local_rank, cpu=not args.no_cpu_baseline)
             except Exception as ex:
