@@ -137,9 +137,10 @@ int rgbdslam_b200_set_stream(void* cuda_stream);
 /* Block until all work queued by the library has finished. */
 int rgbdslam_b200_synchronize(void);
 
-/* Which kernel computes the Hamming brute-force stage: 0 = SIMT popcount kernel; 1 / 2 / 3 = tcgen05 kind::i8 tensor-core
- * GEMM with arg-max epilogue over work items of 128x256 / 256x128 / 256x256 (queries x train rows per tile).  All are
- * exact and give identical results; the library default is the fastest one measured. */
+/* Which kernel computes the Hamming brute-force stage: 0 = SIMT popcount kernel (cross-check); 1 (default) = tcgen05 kind::i8
+ * tensor-core GEMM with arg-max epilogue, the 32-byte descriptors expanded to int8 operands inside the kernel; 2 = the same
+ * GEMM reading +-1 operand tiles the nodes keep resident (8 x the descriptor bytes).  All are exact and give identical
+ * results. */
 int rgbdslam_b200_set_hamming_path(int path);
 
 const char* rgbdslam_b200_last_error(void);

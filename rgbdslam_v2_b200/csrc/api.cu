@@ -187,28 +187,32 @@ static int stage_match_items(const PairDesc* h_pairs, int npairs, int stride, in
     if ((rc = s.W().d_top4.ensure(sizeof(int4) * (size_t)npairs * stride))) return rc;
     if ((rc = s.W().d_knn.ensure(sizeof(float4) * (size_t)npairs * stride))) return rc;
   }
-  // work-item shape (queries x train rows per tile): path 1 = 128 x 256 (tc_match_kernel), path 2 = 256 x 128
-  // (tc_match256_kernel; also every float-descriptor batch on paths 2 / 3 and the SiftGPU matcher), path 3 = 256 x 256
-  // (tc_match_wide_kernel, Hamming only)
-  const bool q256 = s.hamming_path >= 2 || kind == 2;
-  const int mblk = q256 ? 256 : 128, nblk = (kind == 0 && s.hamming_path == 3) || !q256 ? 256 : 128;
+  // work items: 256 queries of one pair against 128-row train tiles (every tensor-core kernel).  ORB path 1 (default) hands the
+  // kernel the 32-byte descriptors themselves (expanded to int8 operands inside the kernel); path 2 and the float-descriptor
+  // matchers read the operand tiles the nodes keep resident.
+  const bool raw = kind == 0 && s.hamming_path == 1;
+  const int mblk = 256, nblk = 128;
   std::vector<HamItem> items;
   items.reserve((size_t)npairs * 8);
   for (int p = 0; p < npairs; p++) {
     const PairDesc& pd = h_pairs[p];
-    if (pd.nq > 0 && (!pd.q_i8 || !pd.t_i8)) {
+    if (!raw && pd.nq > 0 && (!pd.q_i8 || !pd.t_i8)) {
       set_error("internal: tensor-core match path without tiled operands");
       return RGBDSLAM_B200_ERR_STATE;
     }
     for (int pass = 0; pass < (kind == 2 ? 2 : 1); pass++) {
       const int8_t* a = pass ? pd.t_i8 : pd.q_i8;
       const int8_t* b = pass ? pd.q_i8 : pd.t_i8;
+      if (raw) {
+        a = reinterpret_cast<const int8_t*>(pd.q_desc);
+        b = reinterpret_cast<const int8_t*>(pd.t_desc);
+      }
       const int na = pass ? pd.nt : pd.nq, nb = pass ? pd.nq : pd.nt;
       // bruteForceSearchORB never looks at the last train row (features.cpp:174); the float matchers search every row
       const int nsearch = sift ? nb : (nb - 1 > 0 ? nb - 1 : 0);
       for (int m0 = 0; m0 < na; m0 += mblk) {
         HamItem it;
-        it.a = a + (size_t)m0 * 256;
+        it.a = a + (size_t)m0 * (raw ? 32 : 256);
         it.b = b;
         if (!sift) it.out = reinterpret_cast<int2*>(s.W().d_best.ptr) + (size_t)p * stride + m0;
         else if (pass == 0) it.out = reinterpret_cast<int2*>(reinterpret_cast<int4*>(s.W().d_top4.ptr) + (size_t)p * stride + m0);
@@ -238,8 +242,7 @@ static int launch_sift_knn(const PairDesc* d_pairs, int npairs, int max_nq, int 
   State& s = g_state;
   cudaEventRecord(s.W().ev[3], st);
   if (n_items > 0) {
-    cudaError_t e = s.hamming_path >= 2 ? launch_l2_tc256((const HamItem*)s.W().d_items.ptr, n_items, s.sm_count, st)
-                                        : launch_l2_tc((const HamItem*)s.W().d_items.ptr, n_items, s.sm_count, st);
+    cudaError_t e = launch_l2_tc256((const HamItem*)s.W().d_items.ptr, n_items, s.sm_count, st);
     if (e != cudaSuccess) return cuda_fail(e, "l2 tensor-core kernel");
     s.launches += 1;
   }
@@ -258,9 +261,8 @@ static int launch_hamming(const PairDesc* d_pairs, int npairs, int max_nq, int2*
   if (s.hamming_path == 0) {
     e = launch_hamming_simt(d_pairs, npairs, max_nq, best, stride, st);
   } else if (n_items > 0) {
-    e = s.hamming_path == 3   ? launch_hamming_tc_wide((const HamItem*)s.W().d_items.ptr, n_items, s.sm_count, st)
-        : s.hamming_path == 2 ? launch_hamming_tc256((const HamItem*)s.W().d_items.ptr, n_items, s.sm_count, st)
-                              : launch_hamming_tc((const HamItem*)s.W().d_items.ptr, n_items, s.sm_count, st);
+    e = s.hamming_path == 2 ? launch_hamming_tc256((const HamItem*)s.W().d_items.ptr, n_items, s.sm_count, st)
+                            : launch_hamming_tc_expand((const HamItem*)s.W().d_items.ptr, n_items, s.sm_count, st);
   } else {
     cudaEventRecord(s.W().ev[1], st);
     return 0;
@@ -725,8 +727,8 @@ int rgbdslam_b200_set_sift_matcher(int matcher) {
 
 int rgbdslam_b200_set_hamming_path(int path) {
   std::lock_guard<std::mutex> lk(g_state.mu);
-  if (path < 0 || path > 3) {
-    set_error("set_hamming_path: 0 = SIMT popcount, 1 / 2 / 3 = tcgen05 int8 GEMM with 128x256 / 256x128 / 256x256 work items");
+  if (path < 0 || path > 2) {
+    set_error("set_hamming_path: 0 = SIMT popcount, 1 = tcgen05 int8 GEMM with in-kernel operand expansion, 2 = with resident operand tiles");
     return RGBDSLAM_B200_ERR_ARG;
   }
   g_state.hamming_path = path;

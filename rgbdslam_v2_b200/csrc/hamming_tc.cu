@@ -16,10 +16,8 @@
 // cp.async.bulk (TMA bulk copy, completes on an mbarrier).  No tensor map / swizzle is needed and the
 // MMA reads conflict-free 8x16 B core matrices.
 //
-// Warp roles (192 threads, 1 CTA / SM, persistent over work items = (pair, 128-query tile)):
-//   warp 0 lane 0 : bulk-copy producer (A tile per item, B tiles of 256 train rows, 2-stage rings)
-//   warp 1 lane 0 : tcgen05.mma issuer
-//   warps 2..5    : epilogue -- tcgen05.ld of the accumulator, running arg-max per query row, final store
+// Two kernels: tc_match256_kernel (operand tiles resident in HBM, staged by cp.async.bulk: the float-descriptor matchers and the
+// legacy ORB path) and tc_hamming_expand_kernel (the default ORB path: descriptors expanded inside the kernel).
 #include "kernels.h"
 
 namespace rb200 {
@@ -179,17 +177,8 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
          (1ull << 46);
 }
 
-constexpr uint32_t kTileA = 128 * 256;   // 32 KiB: 128 query rows x 256 int8
-constexpr uint32_t kTileB = 256 * 256;   // 64 KiB: 256 train rows x 256 int8
-constexpr uint32_t kSmemBars = 2 * kTileA + 2 * kTileB;
-constexpr uint32_t kTcSmemBytes = kSmemBars + 128;
-constexpr int kTcThreads = 192;
+constexpr uint32_t kTileA = 128 * 256;   // 32 KiB: 128 rows x 256 B of operand data
 constexpr int kNoBest = (int)0x80000000;
-// instruction descriptor: D=S32 (2<<4), A=INT8 (1<<7), B=INT8 (1<<10), both K-major, N=256, M=128
-constexpr uint32_t kIdescI8 = (2u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
-
-// instruction descriptor for the SIFT path: D=F32 (1<<4), A=BF16 (1<<7), B=BF16 (1<<10), K-major, N=256, M=128
-constexpr uint32_t kIdescBF16 = (1u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
 
 __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
   asm volatile(
@@ -200,159 +189,6 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t desc_a, ui
       "}\n" ::"r"(tmem_d),
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(acc)
       : "memory");
-}
-
-// MODE 0: Hamming (int8 +-1 operands, int32 accumulators, arg-max of the dot product).
-// MODE 1: SIFT L2 (bf16 operands, 128-d rows are also 256 B => identical tile geometry; fp32 accumulators; the
-//         epilogue keeps the 4 best candidates per query by score 2 a.b - |b|^2; exact fp32 re-ranking follows).
-template <int MODE>
-__global__ void __launch_bounds__(kTcThreads, 1) tc_match_kernel(const HamItem* __restrict__ items, int n_items) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  const uint32_t sA = smem_u32(smem);
-  const uint32_t sB = sA + 2 * kTileA;
-  const uint32_t bars = sA + kSmemBars;
-  // barrier slots (8 B each): full_a[2] 0,1 | empty_a[2] 2,3 | full_b[2] 4,5 | empty_b[2] 6,7 | tmem_full[2] 8,9 |
-  // tmem_empty[2] 10,11 ; tmem base pointer at slot 12
-  auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
-  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + kSmemBars + 96);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < 10; i++) mbar_init(bar(i), 1);
-    mbar_init(bar(10), 4);
-    mbar_init(bar(11), 4);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32((const void*)tmem_ptr_smem))
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_smem;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
-      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-        const HamItem item = items[it];
-        mbar_wait(bar(2 + sa), pa ^ 1);
-        mbar_expect_tx(bar(0 + sa), kTileA);
-        bulk_g2s(sA + sa * kTileA, item.a, kTileA, bar(0 + sa));
-        if (++sa == 2) { sa = 0; pa ^= 1; }
-        for (int nb = 0; nb < item.n_btiles; nb++) {
-          mbar_wait(bar(6 + sb), pb ^ 1);
-          mbar_expect_tx(bar(4 + sb), kTileB);
-          bulk_g2s(sB + sb * kTileB, item.b + (size_t)nb * kTileB, kTileB, bar(4 + sb));
-          if (++sb == 2) { sb = 0; pb ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 1) {  // warp-uniform walk, one elected lane issues (see tc_match256_kernel)
-    uint32_t sa = 0, pa = 0, sb = 0, pb = 0, acc = 0, pacc = 0;
-    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-      const int n_btiles = items[it].n_btiles;
-      mbar_wait(bar(0 + sa), pa);
-      tc_fence_after();
-      for (int nb = 0; nb < n_btiles; nb++) {
-        mbar_wait(bar(4 + sb), pb);
-        mbar_wait(bar(10 + acc), pacc ^ 1);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint64_t da = make_desc(sA + sa * kTileA), db = make_desc(sB + sb * kTileB);
-#pragma unroll
-          for (int k = 0; k < 8; k++) {
-            if (MODE == 0)
-              tc_mma_i8(tmem_base + acc * 256, da + (uint64_t)(k * 16), db + (uint64_t)(k * 16), kIdescI8, k > 0 ? 1u : 0u);
-            else
-              tc_mma_bf16(tmem_base + acc * 256, da + (uint64_t)(k * 16), db + (uint64_t)(k * 16), kIdescBF16, k > 0 ? 1u : 0u);
-          }
-          tc_commit(bar(6 + sb));    // B stage may be refilled once these MMAs retire
-          tc_commit(bar(8 + acc));   // accumulator ready for the epilogue
-        }
-        __syncwarp();
-        if (++sb == 2) { sb = 0; pb ^= 1; }
-        if (++acc == 2) { acc = 0; pacc ^= 1; }
-      }
-      if (elect_one()) tc_commit(bar(2 + sa));  // A stage free
-      __syncwarp();
-      if (++sa == 2) { sa = 0; pa ^= 1; }
-    }
-  } else {
-    const int wq = warp & 3;  // TMEM lane quadrant this warp may access
-    const int row = wq * 32 + lane;
-    uint32_t acc = 0, pacc = 0;
-    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-      const HamItem item = items[it];
-      int best = kNoBest;
-      float s0 = -3.0e38f, s1 = -3.0e38f, s2 = -3.0e38f, s3 = -3.0e38f;  // MODE 1: 4 best scores, descending
-      int i0 = -1, i1 = -1, i2 = -1, i3 = -1;
-      for (int nb = 0; nb < item.n_btiles; nb++) {
-        mbar_wait(bar(8 + acc), pacc);
-        tc_fence_after();
-        const uint32_t t0 = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * 256;
-#pragma unroll 1
-        for (int c = 0; c < 8; c++) {
-          uint32_t v[32];
-          tc_ld32(t0 + c * 32, v);
-          tc_wait_ld();
-          const int col0 = nb * 256 + c * 32;
-          if (MODE == 0) {
-            if (col0 + 32 <= item.nsearch) {
-#pragma unroll
-              for (int j = 0; j < 32; j++) best = max(best, (int)v[j] * 65536 + (65535 - (col0 + j)));
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; j++)
-                if (col0 + j < item.nsearch) best = max(best, (int)v[j] * 65536 + (65535 - (col0 + j)));
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; j++) {
-              const int col = col0 + j;
-              if (col < item.nsearch) {
-                const float sc = fmaf(2.f, __uint_as_float(v[j]), -__ldg(item.bnorm + col));
-                if (sc > s3) {  // insert (ties keep the earlier = lower index)
-                  if (sc > s2) {
-                    s3 = s2; i3 = i2;
-                    if (sc > s1) {
-                      s2 = s1; i2 = i1;
-                      if (sc > s0) { s1 = s0; i1 = i0; s0 = sc; i0 = col; }
-                      else { s1 = sc; i1 = col; }
-                    } else { s2 = sc; i2 = col; }
-                  } else { s3 = sc; i3 = col; }
-                }
-              }
-            }
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar(10 + acc));
-        if (++acc == 2) { acc = 0; pacc ^= 1; }
-      }
-      if (row < item.nq_valid) {
-        if (MODE == 0) {
-          int2 o = make_int2(257, -1);  // features.cpp:172-173
-          if (best != kNoBest) {
-            const int s = best >> 16;  // dot product = 256 - 2*hd
-            o.x = (256 - s) >> 1;
-            o.y = 65535 - (best & 0xFFFF);
-          }
-          item.out[row] = o;
-        } else {
-          reinterpret_cast<int4*>(item.out)[row] = make_int4(i0, i1, i2, i3);
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
-  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -557,13 +393,27 @@ __global__ void __launch_bounds__(kTc256Threads, 1) tc_match256_kernel(const Ham
               }
             }
           } else {
-            // |b|^2 of the chunk's 32 train rows: one coalesced load per lane, handed round by shuffles (a global load per
-            // element inside the branchy insertion made this epilogue 20 x slower than the MMAs it drains); columns past the
-            // last train row get +inf, i.e. a score of -inf that never enters the list
-            const float bn_l = (col0 + lane < item.nsearch) ? __ldg(item.bnorm + col0 + lane) : __int_as_float(0x7f800000);
+            // |b|^2 of the chunk's 32 train rows: eight 16-byte loads with a warp-uniform address (one transaction each, L1
+            // resident), issued before the comparisons.  (First version: one global load per element inside the branchy insertion,
+            // 20 x slower than the MMAs it drains; second: one load per lane + a shuffle per element -- the shuffle unit became
+            // the bottleneck, ncu: 50 % of the stall samples on the SHFL.)  Columns past the last train row get +inf = score -inf.
+            float bn[32];
+            {
+              const float4* np4 = reinterpret_cast<const float4*>(item.bnorm + col0);
+#pragma unroll
+              for (int i = 0; i < 8; i++) {
+                const float4 t = __ldg(np4 + i);
+                bn[4 * i] = t.x; bn[4 * i + 1] = t.y; bn[4 * i + 2] = t.z; bn[4 * i + 3] = t.w;
+              }
+            }
+            if (col0 + 32 > item.nsearch) {
+#pragma unroll
+              for (int j = 0; j < 32; j++)
+                if (col0 + j >= item.nsearch) bn[j] = __int_as_float(0x7f800000);
+            }
 #pragma unroll
             for (int j = 0; j < 32; j++) {
-              const float sc = fmaf(2.f, __uint_as_float(v[j]), -__shfl_sync(0xffffffffu, bn_l, j));
+              const float sc = fmaf(2.f, __uint_as_float(v[j]), -bn[j]);
               if (sc > s3) {  // rare after the first tiles: insert (ties keep the earlier = lower index)
                 const int col = col0 + j;
                 if (sc > s2) {
@@ -648,40 +498,100 @@ cudaError_t launch_siftgpu_tc256(const HamItem* d_items, int n_items, int sm_cou
 }
 
 // ---------------------------------------------------------------------------------------------
-// Path 3 (default): 256-query items against 256-row train tiles.
-// ncu on tc_match256_kernel: tensor pipe 65 % active, L2 21 %, HBM 31 % -- and each M128 x N128 x K32 MMA reads 8 KiB of
-// operands from shared memory for 68 cycles of math (120 B/clk of a 128 B/clk port, plus the bulk-copy writes): the
-// shared-memory operand bandwidth is the limiter.  N = 256 halves the A re-reads per MAC (12 KiB per 136 cycles = 88 B/clk).
-// TMEM then holds exactly two M128 x N256 accumulators, one per query half; they double-buffer EACH OTHER: while half 1
-// accumulates tile b, the epilogue drains half 0 of tile b.  A ring: 3 x 32 KiB (one query half per slot), B ring:
-// 2 x 64 KiB.  16 epilogue warps: (half, column half, lane quadrant); the two column halves of a row meet in shared memory.
-constexpr int kWideEpiWarps = 16;
-constexpr int kWideThreads = 64 + kWideEpiWarps * 32;
-constexpr int kWASlots = 3, kWBSlots = 2;
-constexpr uint32_t kWideBarsOff = kWASlots * kTileA + kWBSlots * kTileB;  // 224 KiB
-constexpr uint32_t kWideSmemBytes = kWideBarsOff + 256 + 1024;
-static_assert(kWideSmemBytes <= 232448, "tc_match_wide: shared memory over the 227 KiB per-CTA limit");
-constexpr int kWAFull = 0, kWAEmpty = kWASlots, kWBFull = 2 * kWASlots, kWBEmpty = kWBFull + kWBSlots, kWAccFull = kWBEmpty + kWBSlots,
-              kWAccEmpty = kWAccFull + 2;
-static_assert((kWAccEmpty + 2) * 8 <= 192, "barrier area");
+// Hamming match with IN-KERNEL operand expansion (the default ORB path, `set_hamming_path(1)`).
+//
+// The resident-tile kernel above reads a +-1 int8 expansion of every descriptor (256 B per 32-byte descriptor) that
+// the nodes keep in HBM: 7.6 x the algorithmic DRAM traffic of the stage and 8 x the node memory.  Here the producer warps read
+// the 32-byte descriptors themselves and expand them straight into the UMMA operand layout in shared memory.
+// Two more things ride on the expansion:
+//  * operands are +-64 instead of +-1, so the accumulator holds 4096 * dot;
+//  * a NINTH k-step multiplies two constant operand blocks, A_idx rows (64, 1, 0 ...) x B_idx row j (hi_j, lo_j, 0 ...) with
+//    64 hi_j + lo_j = 127 - j: the accumulator of column j of a train tile becomes  4096 * dot + (127 - j),  i.e. the
+//    (dot product, lowest-column-wins) key the arg-max needs is produced BY THE TENSOR CORE.  The epilogue no longer builds a
+//    key per element (IMAD + VIADDMNMX, two issue slots per element, half of the SM's issue bandwidth): it takes a plain
+//    three-input maximum (VIMNMX3: half a slot per element), adds the tile's column offset once per tile, and leaves the
+//    issue slots to the expansion.  One extra MMA in nine (+12.5 % tensor time) buys a 4 x cheaper epilogue.
+// Exactness: |4096 dot| <= 2^20, 127 - j in [0, 128), global key = acc + (3968 - 128 tile) = 4096 dot + (4095 - col) with
+// col <= 4095 -- all exact in int32; dot = key >> 12 (arithmetic), col = 4095 - (key & 4095).
+//
+// Work item = 256 queries of one pair (two 128-row halves) against all train rows, 128-row train tiles.
+//   warps 0-3  : producers -- thread t expands row t of a tile (2 x LDG.128 -> 64 words of +-64 -> 16 x STS.128, layout
+//                tile[row_group 16][k_chunk 16][row 8][16 B]); writes are published to the async proxy (fence.proxy.async)
+//                before the arrival on the tile's mbarrier
+//   warp 4     : MMA issuer (one elected lane): per train tile 2 halves x (8 + 1) tcgen05.mma.kind::i8 M128 N128 K32
+//   warps 5-12 : epilogue (TMEM lane quadrant = warp & 3, half = (warp - 5) >> 2)
+// Shared memory: A ring 3 x 32 KiB (one query half per slot: the next item's first half is expanded while the current item
+// runs), B ring 3 x 32 KiB, the two 4 KiB index blocks.  TMEM: 2 stages x 2 halves x 128 int32 columns.
+constexpr int kXProducerWarps = 4, kXEpiWarps = 8;
+constexpr int kXThreads = (kXProducerWarps + 1 + kXEpiWarps) * 32;  // 416
+constexpr int kXASlots = 3, kXBSlots = 3;
+constexpr uint32_t kXIdxOff = (kXASlots + kXBSlots) * kTileA;      // 192 KiB
+constexpr uint32_t kXBarsOff = kXIdxOff + 2 * 4096;
+constexpr uint32_t kXSmemBytes = kXBarsOff + 256;
+static_assert(kXSmemBytes <= 232448, "tc_hamming_expand: shared memory over the 227 KiB per-CTA limit");
+constexpr int kXAFull = 0, kXAEmpty = kXASlots, kXBFull = 2 * kXASlots, kXBEmpty = 2 * kXASlots + kXBSlots,
+              kXAccFull = 2 * kXASlots + 2 * kXBSlots, kXAccEmpty = kXAccFull + 2, kXBarCount = kXAccEmpty + 2;
+static_assert(kXBarCount * 8 <= 192, "barrier area");
 
-__global__ void __launch_bounds__(kWideThreads, 1) tc_match_wide_kernel(const HamItem* __restrict__ items, int n_items) {
+__device__ __forceinline__ uint64_t make_desc_lbo_sbo(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// 4 descriptor bits (bits 0-3 of x, x < 16) -> 4 int8: bit set -> +64, clear -> -64
+__device__ __forceinline__ uint32_t pm64_from_nibble(uint32_t x) {
+  const uint32_t s4 = (x * 0x00204081u) & 0x01010101u;  // bit i -> byte i (0 / 1)
+  return 0xC0C0C0C0u - s4 * 0x80u;                      // per byte 0xC0 (-64) or 0x40 (+64), no borrow between bytes
+}
+// One 256-bit descriptor (8 words) -> 256 int8 at tile_row_addr + k_chunk * 128 (k_chunk = 16 descriptor bits = 16 bytes)
+__device__ __forceinline__ void expand_row(uint32_t tile_row_addr, const uint4 lo, const uint4 hi) {
+  const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const uint32_t m0 = w[i] & 0x0F0F0F0Fu, m1 = (w[i] >> 4) & 0x0F0F0F0Fu;  // low / high nibble of every byte
+#pragma unroll
+    for (int hf = 0; hf < 2; hf++) {  // two 16-bit halves of the word = two k-chunks
+      const uint32_t n0 = __byte_perm(m0, 0, 0x4440 + 2 * hf), n1 = __byte_perm(m1, 0, 0x4440 + 2 * hf);
+      const uint32_t n2 = __byte_perm(m0, 0, 0x4441 + 2 * hf), n3 = __byte_perm(m1, 0, 0x4441 + 2 * hf);
+      sts128(tile_row_addr + (uint32_t)(2 * i + hf) * 128u, pm64_from_nibble(n0), pm64_from_nibble(n1), pm64_from_nibble(n2),
+             pm64_from_nibble(n3));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kXThreads, 1) tc_hamming_expand_kernel(const HamItem* __restrict__ items, int n_items) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sA = smem_u32(smem);
-  const uint32_t sB = sA + kWASlots * kTileA;
-  const uint32_t bars = sA + kWideBarsOff;
+  const uint32_t sB = sA + kXASlots * kTileA;
+  const uint32_t sIdxA = sA + kXIdxOff, sIdxB = sIdxA + 4096;
+  const uint32_t bars = sA + kXBarsOff;
   auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
-  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + kWideBarsOff + 192);
-  int* s_best = reinterpret_cast<int*>(smem + kWideBarsOff + 256);  // [half][128 rows]: partial arg-max of column half 1
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + kXBarsOff + 192);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kWAccEmpty; i++) mbar_init(bar(i), 1);
-    mbar_init(bar(kWAccEmpty), 8);  // one arrival per epilogue warp of the half
-    mbar_init(bar(kWAccEmpty + 1), 8);
+    for (int i = 0; i < kXASlots; i++) { mbar_init(bar(kXAFull + i), kXProducerWarps * 32); mbar_init(bar(kXAEmpty + i), 1); }
+    for (int i = 0; i < kXBSlots; i++) { mbar_init(bar(kXBFull + i), kXProducerWarps * 32); mbar_init(bar(kXBEmpty + i), 1); }
+    mbar_init(bar(kXAccFull), 1);
+    mbar_init(bar(kXAccFull + 1), 1);
+    mbar_init(bar(kXAccEmpty), kXEpiWarps);
+    mbar_init(bar(kXAccEmpty + 1), kXEpiWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 2) {
+  if (threadIdx.x < 128) {
+    // index blocks, K-major no-swizzle: [row_group 16][k_chunk 2][row 8][16 B]; only bytes 0 and 1 of a row are non-zero
+    const int r = threadIdx.x;
+    const uint32_t off = (uint32_t)(r >> 3) * 256u + (uint32_t)(r & 7) * 16u;
+    sts128(sIdxA + off, 0x00000140u, 0, 0, 0);  // (64, 1, 0, ...)
+    sts128(sIdxA + off + 128u, 0, 0, 0, 0);
+    const uint32_t rem = 127u - (uint32_t)r;    // 64 * hi + lo
+    sts128(sIdxB + off, (rem >> 6) | ((rem & 63u) << 8), 0, 0, 0);
+    sts128(sIdxB + off + 128u, 0, 0, 0, 0);
+    fence_proxy_async_smem();
+  }
+  if (warp == kXProducerWarps) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32((const void*)tmem_ptr_smem))
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -690,158 +600,218 @@ __global__ void __launch_bounds__(kWideThreads, 1) tc_match_wide_kernel(const Ha
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  const int my_items = blockIdx.x < n_items ? (n_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
-  if (warp == 0) {
-    if (lane == 0) {
-      uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
-      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-        const HamItem item = items[it];
-        const int n_halves = item.nq_valid > 128 ? 2 : 1;
-        for (int h = 0; h < n_halves; h++) {
-          mbar_wait(bar(kWAEmpty + sa), pa ^ 1);
-          mbar_expect_tx(bar(kWAFull + sa), kTileA);
-          bulk_g2s(sA + sa * kTileA, item.a + (size_t)h * kTileA, kTileA, bar(kWAFull + sa));
-          if (++sa == kWASlots) { sa = 0; pa ^= 1; }
+  if (warp < kXProducerWarps) {
+    // ---------------- producers: thread t <-> row t of whichever 128-row tile is being filled
+    // Order of production (the consumer needs, per item: half 0 + tile 0, then half 1, then the other tiles):
+    //   A(0,0) B(0,0) A(0,1) | B(k,1) A(k+1,0) B(k,2) ... B(k,n-1) B(k+1,0) A(k+1,1) | ...
+    // A(k+1,0) goes into the ring slot item k-1 has released, A(k+1,1) into item k's first slot, i.e. after item k is done --
+    // by then the consumer already has half 0 and tile 0 of item k+1 to work on.  The descriptor row of the NEXT operation is
+    // loaded before the current one is expanded, so the global-memory latency hides behind ~230 ALU instructions.
+    const int t = threadIdx.x;
+    const uint32_t row_off = (uint32_t)(t >> 3) * 2048u + (uint32_t)(t & 7) * 16u;
+    struct Op {
+      const uint4* src;  // this thread's descriptor row, nullptr = row does not exist (zeros)
+      uint32_t dst, full, empty, parity;
+    };
+    uint32_t a_seq = 0, b_seq = 0;  // A halves / B tiles scheduled so far (slot = seq % slots, phase = (seq / slots) & 1)
+    auto op_a = [&](const HamItem& it, int h) {
+      Op o;
+      const int row = h * 128 + t;
+      o.src = row < it.nq_valid ? reinterpret_cast<const uint4*>(it.a) + 2 * (size_t)row : nullptr;
+      const uint32_t slot = a_seq % kXASlots;
+      o.dst = sA + slot * kTileA + row_off;
+      o.full = bar(kXAFull + slot);
+      o.empty = bar(kXAEmpty + slot);
+      o.parity = ((a_seq / kXASlots) & 1u) ^ 1u;
+      a_seq++;
+      return o;
+    };
+    auto op_b = [&](const HamItem& it, int nb) {
+      Op o;
+      const int row = nb * 128 + t;
+      o.src = row < it.nsearch ? reinterpret_cast<const uint4*>(it.b) + 2 * (size_t)row : nullptr;
+      const uint32_t slot = b_seq % kXBSlots;
+      o.dst = sB + slot * kTileA + row_off;
+      o.full = bar(kXBFull + slot);
+      o.empty = bar(kXBEmpty + slot);
+      o.parity = ((b_seq / kXBSlots) & 1u) ^ 1u;
+      b_seq++;
+      return o;
+    };
+    if (my_items > 0) {
+      HamItem cur = items[blockIdx.x], nxt = cur;
+      int k = 0, nb = 1, st = 0;
+      bool more = my_items > 1;
+      if (more) nxt = items[blockIdx.x + gridDim.x];
+      // the schedule above as a resumable state machine: returns false when everything has been produced
+      auto next_op = [&](Op& o) -> bool {
+        for (;;) {
+          switch (st) {
+            case 0: o = op_a(cur, 0); st = 1; return true;
+            case 1: st = 2; if (cur.n_btiles > 0) { o = op_b(cur, 0); return true; } break;
+            case 2: o = op_a(cur, 1); st = 3; nb = 1; return true;
+            case 3:
+              if (nb < cur.n_btiles) {
+                o = op_b(cur, nb);
+                if (nb == 1 && more) st = 4;
+                nb++;
+                return true;
+              }
+              st = 5;
+              break;
+            case 4: o = op_a(nxt, 0); st = 3; return true;
+            case 5:
+              if (!more) return false;
+              st = 6;
+              if (cur.n_btiles <= 1) { o = op_a(nxt, 0); return true; }
+              break;
+            case 6: st = 7; if (nxt.n_btiles > 0) { o = op_b(nxt, 0); return true; } break;
+            default:  // 7
+              o = op_a(nxt, 1);
+              cur = nxt;
+              k++;
+              more = k + 1 < my_items;
+              if (more) nxt = items[blockIdx.x + (size_t)(k + 1) * gridDim.x];
+              nb = 1;
+              st = 3;
+              return true;
+          }
         }
-        for (int nb = 0; nb < item.n_btiles; nb++) {
-          mbar_wait(bar(kWBEmpty + sb), pb ^ 1);
-          mbar_expect_tx(bar(kWBFull + sb), kTileB);
-          bulk_g2s(sB + sb * kTileB, item.b + (size_t)nb * kTileB, kTileB, bar(kWBFull + sb));
-          if (++sb == kWBSlots) { sb = 0; pb ^= 1; }
-        }
+      };
+      Op op;
+      bool have = next_op(op);
+      uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
+      if (have && op.src) { lo = __ldg(op.src); hi = __ldg(op.src + 1); }
+      while (have) {
+        Op nx;
+        const bool have_nx = next_op(nx);
+        uint4 nlo = make_uint4(0, 0, 0, 0), nhi = nlo;
+        if (have_nx && nx.src) { nlo = __ldg(nx.src); nhi = __ldg(nx.src + 1); }  // in flight while this row is expanded
+        mbar_wait(op.empty, op.parity);
+        expand_row(op.dst, lo, hi);
+        fence_proxy_async_smem();
+        mbar_arrive(op.full);
+        op = nx; lo = nlo; hi = nhi; have = have_nx;
       }
     }
-  } else if (warp == 1) {  // warp-uniform walk, one elected lane issues (see tc_match256_kernel)
-    uint32_t sa = 0, pa = 0, sb = 0, pb = 0, pacc0 = 0, pacc1 = 0;
-    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-      const HamItem item = items[it];
-      const int n_halves = item.nq_valid > 128 ? 2 : 1;
-      uint32_t slot[2], phase[2];
-      for (int h = 0; h < n_halves; h++) {
-        slot[h] = sa;
-        phase[h] = pa;
-        if (++sa == kWASlots) { sa = 0; pa ^= 1; }
-      }
-      for (int nb = 0; nb < item.n_btiles; nb++) {
-        mbar_wait(bar(kWBFull + sb), pb);
-        for (int h = 0; h < n_halves; h++) {
-          if (nb == 0) mbar_wait(bar(kWAFull + slot[h]), phase[h]);
-          mbar_wait(bar(kWAccEmpty + h), (h ? pacc1 : pacc0) ^ 1);
-          tc_fence_after();
-          if (elect_one()) {
-            const uint64_t da = make_desc(sA + slot[h] * kTileA), db = make_desc(sB + sb * kTileB);
-            const uint32_t d = tmem_base + h * 256;
+  } else if (warp == kXProducerWarps) {
+    // ---------------- MMA issuer
+    uint32_t a_seq = 0, b_seq = 0, acc = 0, pacc = 0;
+    const uint64_t dia = make_desc_lbo_sbo(sIdxA, 128, 256), dib = make_desc_lbo_sbo(sIdxB, 128, 256);
+    for (int k = 0; k < my_items; k++) {
+      const int n_btiles = items[blockIdx.x + (size_t)k * gridDim.x].n_btiles;
+      const uint32_t slot0 = a_seq % kXASlots, ph0 = (a_seq / kXASlots) & 1u;
+      const uint32_t slot1 = (a_seq + 1) % kXASlots, ph1 = ((a_seq + 1) / kXASlots) & 1u;
+      a_seq += 2;
+      for (int nb = 0; nb < n_btiles; nb++) {
+        const uint32_t sb = b_seq % kXBSlots, pb = (b_seq / kXBSlots) & 1u;
+        b_seq++;
+        mbar_wait(bar(kXBFull + sb), pb);
+        if (nb == 0) mbar_wait(bar(kXAFull + slot0), ph0);
+        mbar_wait(bar(kXAccEmpty + acc), pacc ^ 1u);
+        tc_fence_after();
+        const uint64_t db = make_desc(sB + sb * kTileA);
+        if (elect_one()) {
+          const uint64_t da = make_desc(sA + slot0 * kTileA);
+          const uint32_t d = tmem_base + acc * 256;
 #pragma unroll
-            for (int k = 0; k < 8; k++) tc_mma_i8(d, da + (uint64_t)(k * 16), db + (uint64_t)(k * 16), kIdescI8, k > 0 ? 1u : 0u);
-            tc_commit(bar(kWAccFull + h));
-            if (h == n_halves - 1) tc_commit(bar(kWBEmpty + sb));
-          }
-          __syncwarp();
-          if (h) pacc1 ^= 1; else pacc0 ^= 1;
+          for (int ks = 0; ks < 8; ks++) tc_mma_i8(d, da + (uint64_t)((ks * 256) >> 4), db + (uint64_t)((ks * 256) >> 4), kIdescI8_N128, ks > 0 ? 1u : 0u);
+          tc_mma_i8(d, dia, dib, kIdescI8_N128, 1u);
         }
-        if (++sb == kWBSlots) { sb = 0; pb ^= 1; }
+        __syncwarp();
+        if (nb == 0) {
+          mbar_wait(bar(kXAFull + slot1), ph1);
+          tc_fence_after();
+        }
+        if (elect_one()) {
+          const uint64_t da = make_desc(sA + slot1 * kTileA);
+          const uint32_t d = tmem_base + acc * 256 + 128;
+#pragma unroll
+          for (int ks = 0; ks < 8; ks++) tc_mma_i8(d, da + (uint64_t)((ks * 256) >> 4), db + (uint64_t)((ks * 256) >> 4), kIdescI8_N128, ks > 0 ? 1u : 0u);
+          tc_mma_i8(d, dia, dib, kIdescI8_N128, 1u);
+          tc_commit(bar(kXBEmpty + sb));
+          tc_commit(bar(kXAccFull + acc));
+        }
+        __syncwarp();
+        if (++acc == 2) { acc = 0; pacc ^= 1u; }
       }
-      if (elect_one())
-        for (int h = 0; h < n_halves; h++) tc_commit(bar(kWAEmpty + slot[h]));
+      if (elect_one()) {  // both query halves of the item are free once every MMA issued so far has retired
+        tc_commit(bar(kXAEmpty + slot0));
+        tc_commit(bar(kXAEmpty + slot1));
+      }
       __syncwarp();
     }
   } else {
-    const int e = warp - 2;
-    const int h = e >> 3;         // query half whose accumulator this warp drains
-    const int c = (e >> 2) & 1;   // column half of the 256-column tile
-    const int wq = warp & 3;      // TMEM lane quadrant this warp may access
+    // ---------------- epilogue
+    const int e = warp - (kXProducerWarps + 1);
+    const int h = e >> 2;      // query half drained by this warp
+    const int wq = warp & 3;   // TMEM lane quadrant this warp may access
     const int row = h * 128 + wq * 32 + lane;
-    uint32_t pacc = 0;
-    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-      const HamItem item = items[it];
-      if (h == 1 && item.nq_valid <= 128) continue;  // the second half is never issued for short items
+    uint32_t acc = 0, pacc = 0;
+    for (int k = 0; k < my_items; k++) {
+      const HamItem item = items[blockIdx.x + (size_t)k * gridDim.x];
       int best = kNoBest;
       for (int nb = 0; nb < item.n_btiles; nb++) {
-        mbar_wait(bar(kWAccFull + h), pacc);
+        mbar_wait(bar(kXAccFull + acc), pacc);
         tc_fence_after();
-        const uint32_t t0 = tmem_base + ((uint32_t)(wq * 32) << 16) + h * 256 + c * 128;
+        const uint32_t t0 = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * 256 + h * 128;
+        const int nvalid = item.nsearch - nb * 128;  // train rows of this tile that exist (>= 128: all)
+        int m = kNoBest;
 #pragma unroll 1
-        for (int ch = 0; ch < 4; ch++) {
+        for (int c = 0; c < 4; c++) {
           uint32_t v[32];
-          tc_ld32(t0 + ch * 32, v);
+          tc_ld32(t0 + c * 32, v);
           tc_wait_ld();
-          const int col0 = nb * 256 + c * 128 + ch * 32;
-          if (col0 + 32 <= item.nsearch) {
+          if (c * 32 + 32 <= nvalid) {
+            int m0 = __vimax3_s32((int)v[0], (int)v[1], (int)v[2]), m1 = __vimax3_s32((int)v[3], (int)v[4], (int)v[5]);
 #pragma unroll
-            for (int j = 0; j < 32; j++) best = max(best, (int)v[j] * 65536 + (65535 - (col0 + j)));
+            for (int j = 6; j < 30; j += 4) {
+              m0 = __vimax3_s32(m0, (int)v[j], (int)v[j + 1]);
+              m1 = __vimax3_s32(m1, (int)v[j + 2], (int)v[j + 3]);
+            }
+            m = __vimax3_s32(m, __vimax3_s32(m0, (int)v[30], (int)v[31]), m1);
           } else {
 #pragma unroll
             for (int j = 0; j < 32; j++)
-              if (col0 + j < item.nsearch) best = max(best, (int)v[j] * 65536 + (65535 - (col0 + j)));
+              if (c * 32 + j < nvalid) m = max(m, (int)v[j]);
           }
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar(kWAccEmpty + h));
-        pacc ^= 1;
+        if (lane == 0) mbar_arrive(bar(kXAccEmpty + acc));
+        if (++acc == 2) { acc = 0; pacc ^= 1u; }
+        if (m != kNoBest) best = max(best, m + (3968 - 128 * nb));  // 4096 dot + (4095 - col)
       }
-      // the two column halves of a row meet here (8 warps = 256 threads per query half, named barriers 1 and 2)
-      if (c == 1) s_best[h * 128 + wq * 32 + lane] = best;
-      asm volatile("bar.sync %0, 256;" ::"r"(1 + h) : "memory");
-      if (c == 0) {
-        best = max(best, s_best[h * 128 + wq * 32 + lane]);
-        if (row < item.nq_valid) {
-          int2 o = make_int2(257, -1);
-          if (best != kNoBest) {
-            const int sdot = best >> 16;
-            o.x = (256 - sdot) >> 1;
-            o.y = 65535 - (best & 0xFFFF);
-          }
-          item.out[row] = o;
+      if (row < item.nq_valid) {
+        int2 o = make_int2(257, -1);  // features.cpp:172-173
+        if (best != kNoBest) {
+          const int dot = best >> 12;
+          o.x = (256 - dot) >> 1;
+          o.y = 4095 - (best & 4095);
         }
+        item.out[row] = o;
       }
-      asm volatile("bar.sync %0, 256;" ::"r"(1 + h) : "memory");
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == kXProducerWarps) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
   }
 }
 
-cudaError_t launch_hamming_tc_wide(const HamItem* d_items, int n_items, int sm_count, cudaStream_t stream) {
+cudaError_t launch_hamming_tc_expand(const HamItem* d_items, int n_items, int sm_count, cudaStream_t stream) {
   if (n_items <= 0) return cudaSuccess;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc_match_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWideSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(tc_hamming_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kXSmemBytes);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
   const int grid = n_items < sm_count ? n_items : sm_count;
-  tc_match_wide_kernel<<<grid, kWideThreads, kWideSmemBytes, stream>>>(d_items, n_items);
-  return cudaGetLastError();
-}
-
-cudaError_t launch_hamming_tc(const HamItem* d_items, int n_items, int sm_count, cudaStream_t stream) {
-  if (n_items <= 0) return cudaSuccess;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc_match_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
-  const int grid = n_items < sm_count ? n_items : sm_count;
-  tc_match_kernel<0><<<grid, kTcThreads, kTcSmemBytes, stream>>>(d_items, n_items);
-  return cudaGetLastError();
-}
-
-// SIFT L2: items carry bf16 operand tiles, bnorm (|b|^2 of the bf16-rounded train rows) and an int4 output per query.
-cudaError_t launch_l2_tc(const HamItem* d_items, int n_items, int sm_count, cudaStream_t stream) {
-  if (n_items <= 0) return cudaSuccess;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc_match_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
-  const int grid = n_items < sm_count ? n_items : sm_count;
-  tc_match_kernel<1><<<grid, kTcThreads, kTcSmemBytes, stream>>>(d_items, n_items);
+  tc_hamming_expand_kernel<<<grid, kXThreads, kXSmemBytes, stream>>>(d_items, n_items);
   return cudaGetLastError();
 }
 

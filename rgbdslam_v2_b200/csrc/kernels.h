@@ -16,10 +16,11 @@ cudaError_t launch_expand_i8(const ExpandJob* d_jobs, int njobs, int max_n_pad, 
 cudaError_t launch_expand_i8_strided(const uint8_t* desc, int8_t* out, const int* d_n, int nframes, int K, int n_pad,
                                      cudaStream_t stream);
 // Tensor-core (tcgen05 kind::i8) Hamming brute force over work items; same output as launch_hamming_simt.
-cudaError_t launch_hamming_tc(const HamItem* d_items, int n_items, int sm_count, cudaStream_t stream);
+// Hamming brute force on the tensor cores, 32-byte descriptors expanded to int8 operands inside the kernel (HamItem::a / b =
+// descriptor rows); same output as launch_hamming_simt.
+cudaError_t launch_hamming_tc_expand(const HamItem* d_items, int n_items, int sm_count, cudaStream_t stream);
 // 256-query work items (HamItem::n_btiles counts 128-row B tiles, nq_valid <= 256)
 cudaError_t launch_hamming_tc256(const HamItem* d_items, int n_items, int sm_count, cudaStream_t stream);
-cudaError_t launch_hamming_tc_wide(const HamItem* d_items, int n_items, int sm_count, cudaStream_t stream);
 cudaError_t launch_l2_tc256(const HamItem* d_items, int n_items, int sm_count, cudaStream_t stream);
 
 // SIFT-128 path (sift_l2.cu / hamming_tc.cu MODE 1)
@@ -38,7 +39,6 @@ cudaError_t launch_refine_g2o(const PairDesc* pairs, int npairs, int max_matches
 cudaError_t launch_siftgpu_tc256(const HamItem* d_items, int n_items, int sm_count, cudaStream_t stream);
 cudaError_t launch_select_siftgpu(const PairDesc* pairs, int npairs, const int4* rowres, const int4* colres, int stride, int maxM,
                                   rgbdslam_b200_dmatch* matches, float4* mfrom, float4* mto, int32_t* n_all, cudaStream_t stream);
-cudaError_t launch_l2_tc(const HamItem* d_items, int n_items, int sm_count, cudaStream_t stream);
 cudaError_t launch_l2_refine(const PairDesc* pairs, int npairs, int max_nq, const int4* top4, int stride, float4* knn,
                              cudaStream_t stream);
 cudaError_t launch_select_sift(const PairDesc* pairs, int npairs, const float4* knn, int stride, float nn_ratio, int maxM,

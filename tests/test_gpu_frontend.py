@@ -74,21 +74,52 @@ def test_hamming_tensor_core_path_equals_simt_path(fe, oracle_mod, nq, nt):
         q[0] = t[-1]; q[1] = t[0]; q[2] = ~t[3]; t[nt // 3] = t[1]; q[3] = t[1]
         q[4] = 0; q[5] = 255; t[2] = 0; t[5] = 255
     try:
-        fe.set_hamming_path(1)
+        fe.set_hamming_path(1)  # default: descriptors expanded to int8 operands inside the kernel, column index in the accumulator
         hd1, idx1 = fe.brute_force_search_orb(q, t)
-        fe.set_hamming_path(2)
+        fe.set_hamming_path(2)  # operand tiles resident in HBM
         hd2, idx2 = fe.brute_force_search_orb(q, t)
-        fe.set_hamming_path(3)
-        hd3, idx3 = fe.brute_force_search_orb(q, t)
         fe.set_hamming_path(0)
         hd0, idx0 = fe.brute_force_search_orb(q, t)
     finally:
-        fe.set_hamming_path(2)
+        fe.set_hamming_path(1)
     ohd, oidx = oracle_mod.brute_force_orb(q, t)
     assert np.array_equal(hd0, ohd) and np.array_equal(idx0, oidx)
     assert np.array_equal(hd1, ohd) and np.array_equal(idx1, oidx)
-    assert np.array_equal(hd2, ohd) and np.array_equal(idx2, oidx)  # 256-query work items
-    assert np.array_equal(hd3, ohd) and np.array_equal(idx3, oidx)  # 256 x 256 work items
+    assert np.array_equal(hd2, ohd) and np.array_equal(idx2, oidx)
+
+
+def test_hamming_expand_kernel_many_items_and_ragged_pairs(fe, oracle_mod):
+    """The in-kernel-expansion match kernel over a batch whose work items outnumber the SMs (several items per persistent CTA:
+    ring-slot reuse, the producer's look-ahead schedule) with ragged feature counts incl. single-tile and empty train sets."""
+    from rgbdslam_v2_b200 import synth
+    rng = np.random.default_rng(77)
+    sizes = [(1000, 1000), (257, 129), (5, 1), (130, 2), (3, 600), (1000, 128), (999, 1025), (1, 1), (64, 4096), (4096, 64)] * 17
+    newer, older, exp = [], [], []
+    for i, (nq, nt) in enumerate(sizes):
+        q = rng.integers(0, 256, (nq, 32), dtype=np.uint8)
+        t = rng.integers(0, 256, (nt, 32), dtype=np.uint8)
+        k = min(nq, nt) // 2
+        if k:
+            q[:k] = t[rng.permutation(nt)[:k]] ^ (1 << rng.integers(0, 8, (k, 32))).astype(np.uint8) * (rng.random((k, 32)) < 0.1)
+        xq = np.concatenate([rng.uniform(0.5, 3, (nq, 3)), np.ones((nq, 1))], 1).astype(np.float32)
+        xt = np.concatenate([rng.uniform(0.5, 3, (nt, 3)), np.ones((nt, 1))], 1).astype(np.float32)
+        newer.append(fe.node_from_features(2 * i + 1, q, xq)); older.append(fe.node_from_features(2 * i, t, xt))
+        exp.append((q, t))
+    out = {}
+    try:
+        for path in (1, 0):
+            fe.set_hamming_path(path)
+            res, allm, _ = fe.match_node_pairs(newer, older, seed=4)
+            out[path] = (res["n_all_matches"].copy(), allm.copy())
+    finally:
+        fe.set_hamming_path(1)
+    assert np.array_equal(out[1][0], out[0][0])
+    for i in range(len(sizes)):
+        n = int(out[1][0][i])
+        for f in ("queryIdx", "trainIdx", "distance"):
+            assert np.array_equal(out[1][1][i, :n][f], out[0][1][i, :n][f]), (i, sizes[i], f)
+    for h in newer + older:
+        fe.node_destroy(h)
 
 
 def _oracle_run(oracle_mod, b, seed, first=0, **kw):

@@ -33,7 +33,7 @@ fe.set_hamming_path(1)
 print("resident sync, 128-query tc kernel ms", t(lambda: fe.match_node_pairs(newer, older, seed=1, out=(r, None, None))), "device", fe.last_timing())
 fe.set_hamming_path(0)
 print("e2e sync SIMT hamming (no int8 expansion) ms", t(host((r, None, None))))
-fe.set_hamming_path(2)
+fe.set_hamming_path(1)
 # pipelined e2e, depth 3
 outs = []
 for j in range(3):

@@ -35,7 +35,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "--child":
             if k >= 3: fe.wait_slot(1 + j)
             fe.submit_node_pairs(1 + j, sets[j][0], sets[j][1], (sets[j][2], None, None), seed=1)
         for j in range(3): fe.wait_slot(1 + j)
-    fe.set_hamming_path(2)
+    fe.set_hamming_path(1)
     pipe(9); torch.cuda.synchronize(); t0 = time.perf_counter(); pipe(60); torch.cuda.synchronize()
     out["pipelined_us_per_step"] = round((time.perf_counter() - t0) / 60 * 1e6, 1)
     out["valid"] = int((r["id1"] >= 0).sum()); out["inl_sum"] = int(r["n_inliers"].sum()); out["rmse_sum"] = float(r["rmse"].sum())
