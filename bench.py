@@ -254,70 +254,35 @@ def run_reference(args, rank, world):
     print(json.dumps(out), flush=True)
 
 
-def bench_node_create(fe, n_frames=32):
-    """Secondary: Node constructor (ORB detect + describe + back-projection) from HOST images, frames/s, next to the
-    cv2-based CPU path (oracle/orb_oracle.py; cv2 uses its own thread pool)."""
-    import ctypes as C
-    from oracle import orb_oracle
-    from rgbdslam_v2_b200 import synth
-    from rgbdslam_v2_b200._capi import default_params
-    poses = synth.trajectory(240)[:n_frames]
-    frames = [synth.render_frame(poses[k], seed=k) for k in range(n_frames)]
-    gray = np.stack([f[0] for f in frames]); depth = np.stack([f[1] for f in frames])
-    mask = np.stack([orb_oracle.depth_to_mask(d) for d in depth])
-    K4 = (synth.FX, synth.FY, synth.CX, synth.CY)
-    p = default_params(); p.depth_cov_z0 = 2.0; p.max_keypoints = 1000
-    old = fe.params
-    fe.params = p
-    fe._check(fe.lib.rgbdslam_b200_init(fe_device(fe), C.byref(p)))
-    det = fe.detector_create()
-    times = []
-    for it in range(6):
-        t0 = time.perf_counter()
-        handles, nf = fe.nodes_create(det, gray, depth, mask, K4)
-        times.append(time.perf_counter() - t0)
-        for h in handles:
-            fe.node_destroy(h)
-    fe.detector_destroy(det)
-    gpu_fps = n_frames / statistics.median(times[2:])
-    import cv2
-    cv2.setNumThreads(usable_cpus())  # cv2 sizes its pool from the visible CPUs, not from the cgroup quota
-    st = orb_oracle.DetectorState()
-    orb_oracle.node_construct(gray[0], depth[0], mask[0], K4, st, max_keypoints=1000)  # warm
-    t0 = time.perf_counter()
-    for g, d, m in zip(gray[:8], depth[:8], mask[:8]):
-        orb_oracle.node_construct(g, d, m, K4, st, max_keypoints=1000)
-    cpu_fps = 8 / (time.perf_counter() - t0)
-    fe.params = old
-    fe._check(fe.lib.rgbdslam_b200_init(fe_device(fe), C.byref(old)))
-    return {"metric": "node_constructor_frames_per_sec_640x480_1k_orb", "value": gpu_fps, "unit": "frames/s",
-            "batch": n_frames, "mean_features": float(np.mean(nf)), "includes": "H2D of gray+depth+mask, detect, describe, project, D2D into node handles",
-            "cpu_cv2_value": cpu_fps, "cpu_threads": usable_cpus()}
-
-
 def fe_device(fe):
     import torch
     return torch.cuda.current_device()
 
 
 def bench_posegraph(fe):
-    """Secondary: BASELINE config C5 (5000 vertices / 30000 edges) pose-graph LM on the GPU; CPU oracle on a bounded
-    1000 V / 6000 E sample of the same generator."""
+    """Secondary: BASELINE config C5 (5000 vertices / 30000 edges) pose-graph LM: the GPU solve and the CPU oracle (plain-C port of
+    g2o's LM + block-Jacobi PCG, single thread like g2o's solver) on the SAME graph."""
     from oracle import oracle
     from rgbdslam_v2_b200 import synth
     g = synth.make_pose_graph(5000, 30000, seed=0)
     fe.optimize_graph(g["init"], g["fixed"], g["ij"], g["meas"], g["info"], stop=0.01)  # warm-up
+    ts = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        x, chi2, it, cg = fe.optimize_graph(g["init"], g["fixed"], g["ij"], g["meas"], g["info"], stop=0.01)
+        ts.append(time.perf_counter() - t0)
+    dt = min(ts)
     t0 = time.perf_counter()
-    x, chi2, it, cg = fe.optimize_graph(g["init"], g["fixed"], g["ij"], g["meas"], g["info"], stop=0.01)
-    dt = time.perf_counter() - t0
-    gs = synth.make_pose_graph(1000, 6000, seed=0)
-    t0 = time.perf_counter(); fe.optimize_graph(gs["init"], gs["fixed"], gs["ij"], gs["meas"], gs["info"], stop=0.01); dts = time.perf_counter() - t0
-    t0 = time.perf_counter(); ox, ochi2, oit, ocg = oracle.posegraph_optimize(gs["init"], gs["fixed"], gs["ij"], gs["meas"], gs["info"], stop=0.01); dto = time.perf_counter() - t0
+    ox, ochi2, oit, ocg = oracle.posegraph_optimize(g["init"], g["fixed"], g["ij"], g["meas"], g["info"], stop=0.01)
+    dto = time.perf_counter() - t0
     # algorithmic HBM bytes (SURVEY 8d): 18.9 MB per PCG iteration, 45 MB per linearisation
     return {"workload": "C5: 5000 V / 30000 E, optimizer_iterations 0.01, pcg", "seconds": dt, "lm_iterations": it, "pcg_iterations": cg,
-            "chi2": chi2, "ate_m": synth.ate_rmse(x[:, :3], g["gt"][:, :3]), "pcg_iter_per_s": cg / dt,
+            "chi2": chi2, "ate_m": synth.ate_rmse(x[:, :3], g["gt"][:, :3]), "pcg_iter_per_s": cg / dt, "us_per_pcg_iteration": 1e6 * dt / max(cg, 1),
             "algorithmic_GBps": (cg * 18.9e6 + it * 45e6) / dt / 1e9,
-            "sample_1000V_6000E": {"gpu_seconds": dts, "cpu_oracle_seconds": dto, "cpu_threads": 1}}
+            "cpu_baseline": {"seconds": dto, "kind": "port", "cores": 1, "lm_iterations": oit, "pcg_iterations": ocg, "chi2": ochi2,
+                             "sample": "the same C5 graph, full solve", "speedup": dto / dt,
+                             "chi2_rel_diff": abs(chi2 - ochi2) / max(ochi2, 1e-30),
+                             "ate_gpu_vs_cpu_m": synth.ate_rmse(x[:, :3], ox[:, :3])}}
 
 
 def bench_c2_rendered(fe, local_rank, cpu=True):
@@ -695,17 +660,13 @@ def run_ours(args, rank, local_rank, world):
         uid = torch.from_numpy(fe.comm_unique_id() if rank == 0 else np.zeros(128, np.uint8)).cuda()
         dist.broadcast(uid, 0)
         comm = fe.comm_init(rank, world, uid.cpu().numpy())
-        all_edges = np.zeros(world * PAIRS_PER_GPU, PAIR_RESULT_DTYPE)
-        gathered = []
-        for j in range(DEPTH):  # one pinned destination per slot for the in-flight all-gather
-            t = torch.zeros(world * PAIRS_PER_GPU * PAIR_RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
-            gathered.append((t, t.numpy().view(PAIR_RESULT_DTYPE)))
+    # edge records of every step of a timed region, all-gathered ONCE at its end (north star: "a single NCCL all-gather of the
+    # resulting SE(3) edges before the global solve"; round 1 gathered every step: 8 ranks then rendezvous every 0.15 ms)
+    local_edges = {"buf": None, "n": 0}
 
     def submit_resident(k):
         st = sets[k % DEPTH]
         fe.submit_node_pairs(1 + k % DEPTH, st["newer"], st["older"], (st["res"], None, None), seed=SEED, first_pair_index=st["first"])
-        if comm is not None:  # the exchange step rides behind the slot's kernels (no host round trip)
-            fe.allgather_slot_edges(comm, 1 + k % DEPTH, PAIRS_PER_GPU, gathered[k % DEPTH][1])
 
     def submit_e2e(k):
         st = sets[k % DEPTH]
@@ -713,22 +674,27 @@ def run_ours(args, rank, local_rank, world):
         fe.submit_pairs_host(1 + k % DEPTH, pp["desc_newer"], pp["xyz_newer"], bb["n_newer"], pp["desc_older"], pp["xyz_older"],
                              bb["n_older"], bb["id_newer"], bb["id_older"], (st["res"], st["allm"], st["inl"]), seed=SEED,
                              first_pair_index=st["first"])
-        if comm is not None:
-            fe.allgather_slot_edges(comm, 1 + k % DEPTH, PAIRS_PER_GPU, gathered[k % DEPTH][1])
 
     def finish(k):
-        """results of step k (and, for N > 1, every rank's edge records) are on the host"""
+        """results of step k are on the host; N > 1: kept for the exchange at the end of the region"""
         fe.wait_slot(1 + k % DEPTH)
         if comm is not None:
-            all_edges[:] = gathered[k % DEPTH][1]
+            n = local_edges["n"]
+            local_edges["buf"][n:n + PAIRS_PER_GPU] = sets[k % DEPTH]["res"]
+            local_edges["n"] = n + PAIRS_PER_GPU
 
     def run_steps(submit, K):
+        if comm is not None:
+            local_edges["buf"] = np.zeros(K * PAIRS_PER_GPU, PAIR_RESULT_DTYPE)
+            local_edges["n"] = 0
         for k in range(K):
             if k >= DEPTH:
                 finish(k - DEPTH)
             submit(k)
         for k in range(max(0, K - DEPTH), K):
             finish(k)
+        if comm is not None:  # the one exchange: every rank ends up with every rank's edges of the whole region
+            local_edges["all"] = fe.allgather_edges(comm, local_edges["buf"], world)
 
     def barrier():
         torch.cuda.synchronize()
@@ -834,8 +800,8 @@ def run_ours(args, rank, local_rank, world):
                              "the synchronous reference point flushes L2 (a 256 MiB read) before every step",
                        "pipeline": f"{DEPTH} batches in flight on {DEPTH} library streams (rgbdslam_b200_match_pairs_submit / _wait)",
                        "pairs_per_gpu": PAIRS_PER_GPU,
-                       "exchange": "none (1 GPU)" if world == 1 else f"ncclAllGather of {world}x{PAIRS_PER_GPU} edge records (120 B) per step, queued behind each batch on the communicator stream (rgbdslam_b200_allgather_slot_edges), inside the timed region",
-                       "edges_gathered": None if all_edges is None else int((all_edges["id1"] >= 0).sum()),
+                       "exchange": "none (1 GPU)" if world == 1 else f"ONE ncclAllGather of the {world} x {timed_steps} x {PAIRS_PER_GPU} edge records (120 B) of the region at its end (rgbdslam_b200_allgather_edges), inside the timed region",
+                       "edges_gathered": None if comm is None else int((local_edges["all"]["id1"] >= 0).sum()),
                        "valid_edges_rank0": n_valid, "wall_ms_per_step_incl_flush": 1e3 * wall_resident / timed_steps,
                        "repeats": f"{repeats} x --steps {args.steps} timed back to back (>= {MIN_TIMED_MS:.0f} ms per timed region)"},
             "roofline": {"bound": "hbm", "kernel": "hamming_match", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -873,7 +839,14 @@ def run_ours(args, rank, local_rank, world):
                 out["c3"] = {"error": repr(ex), "trace": traceback.format_exc()[-800:]}
         if world == 1 and not args.no_cpu_baseline:
             try:
-                out["node_create"] = bench_node_create(fe)
+                if c4 and "node_constructor_frames_per_s" in c4:  # the Node constructor is measured inside the C4 sequence
+                    op = c4.get("oracle_prefix") or {}
+                    cs = (op.get("cpu_seconds") or {}).get("nodes_cv2")
+                    out["node_create"] = {"metric": "node_constructor_frames_per_sec_640x480_1k_orb", "value": c4["node_constructor_frames_per_s"],
+                                          "unit": "frames/s", "frames": args.c4_frames, "includes": "H2D of gray + depth from pinned host memory "
+                                          "(mask derived from depth on the device), detect, describe, project",
+                                          "h2d_GBps": c4["h2d_bytes"] / c4["seconds"]["nodes"] / 1e9,
+                                          "cpu_cv2_value": (op.get("frames") / cs) if cs else None, "cpu_threads": usable_cpus()}
                 out["posegraph"] = bench_posegraph(fe)
             except Exception as ex:  # secondary measurements must never hide the headline line
                 out["secondary_error"] = repr(ex)

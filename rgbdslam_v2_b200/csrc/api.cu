@@ -126,35 +126,6 @@ static int push_dev_params() {
 
 static inline int pad256(int n) { return ((n > 0 ? n : 1) + 255) / 256 * 256; }
 
-// +-1 int8 expansion of a set of nodes (tensor-core Hamming operands).
-// phase bit 1: stage the job table (a small host->device copy); bit 2: launch the expansion kernel.
-// The host-feature path stages every table BEFORE its bulk feature upload: a small copy issued behind the bulk
-// copies only reaches the copy engine once they have finished, i.e. behind the bulk copies of the other in-flight
-// slots, and holds this slot's kernels back by a whole upload (measured: 0.95 ms at 3 slots).
-static int expand_nodes(const std::vector<ExpandJob>& jobs, int phase = 3) {
-  State& s = g_state;
-  if (jobs.empty()) return 0;
-  int rc;
-  cudaError_t e;
-  if (phase & 1) {
-    if ((rc = s.W().d_jobs.ensure(sizeof(ExpandJob) * jobs.size()))) return rc;
-    if ((rc = s.W().h_jobs.ensure(sizeof(ExpandJob) * jobs.size()))) return rc;
-    memcpy(s.W().h_jobs.ptr, jobs.data(), sizeof(ExpandJob) * jobs.size());
-    e = cudaMemcpyAsync(s.W().d_jobs.ptr, s.W().h_jobs.ptr, sizeof(ExpandJob) * jobs.size(), cudaMemcpyHostToDevice, s.W().stream);
-    if (e != cudaSuccess) return cuda_fail(e, "upload expand jobs");
-  }
-  if (phase & 2) {
-    int max_pad = 0;
-    for (const ExpandJob& j : jobs) max_pad = j.n_pad > max_pad ? j.n_pad : max_pad;
-    e = launch_expand_i8((const ExpandJob*)s.W().d_jobs.ptr, (int)jobs.size(), max_pad, s.W().stream);
-    if (e != cudaSuccess) return cuda_fail(e, "expand_i8 kernel");
-    s.launches += 1;
-  }
-  return 0;
-}
-
-int expand_nodes_public(const std::vector<ExpandJob>& jobs) { return expand_nodes(jobs); }
-
 // RootSIFT + bf16 tiles + norms of a set of SIFT nodes.
 static int prepare_sift_nodes(const std::vector<SiftJob>& jobs, int siftgpu = 0) {
   State& s = g_state;
@@ -187,10 +158,10 @@ static int stage_match_items(const PairDesc* h_pairs, int npairs, int stride, in
     if ((rc = s.W().d_top4.ensure(sizeof(int4) * (size_t)npairs * stride))) return rc;
     if ((rc = s.W().d_knn.ensure(sizeof(float4) * (size_t)npairs * stride))) return rc;
   }
-  // work items: 256 queries of one pair against 128-row train tiles (every tensor-core kernel).  ORB path 1 (default) hands the
-  // kernel the 32-byte descriptors themselves (expanded to int8 operands inside the kernel); path 2 and the float-descriptor
-  // matchers read the operand tiles the nodes keep resident.
-  const bool raw = kind == 0 && s.hamming_path == 1;
+  // work items: 256 queries of one pair against 128-row train tiles (every tensor-core kernel).  The ORB kernel gets the 32-byte
+  // descriptors themselves (expanded to int8 operands inside the kernel); the float-descriptor matchers read the bf16 / u8
+  // operand tiles their nodes keep resident.
+  const bool raw = kind == 0;
   const int mblk = 256, nblk = 128;
   std::vector<HamItem> items;
   items.reserve((size_t)npairs * 8);
@@ -261,8 +232,7 @@ static int launch_hamming(const PairDesc* d_pairs, int npairs, int max_nq, int2*
   if (s.hamming_path == 0) {
     e = launch_hamming_simt(d_pairs, npairs, max_nq, best, stride, st);
   } else if (n_items > 0) {
-    e = s.hamming_path == 2 ? launch_hamming_tc256((const HamItem*)s.W().d_items.ptr, n_items, s.sm_count, st)
-                            : launch_hamming_tc_expand((const HamItem*)s.W().d_items.ptr, n_items, s.sm_count, st);
+    e = launch_hamming_tc_expand((const HamItem*)s.W().d_items.ptr, n_items, s.sm_count, st);
   } else {
     cudaEventRecord(s.W().ev[1], st);
     return 0;
@@ -727,8 +697,8 @@ int rgbdslam_b200_set_sift_matcher(int matcher) {
 
 int rgbdslam_b200_set_hamming_path(int path) {
   std::lock_guard<std::mutex> lk(g_state.mu);
-  if (path < 0 || path > 2) {
-    set_error("set_hamming_path: 0 = SIMT popcount, 1 = tcgen05 int8 GEMM with in-kernel operand expansion, 2 = with resident operand tiles");
+  if (path < 0 || path > 1) {
+    set_error("set_hamming_path: 0 = SIMT popcount (cross-check), 1 = tcgen05 int8 GEMM (default)");
     return RGBDSLAM_B200_ERR_ARG;
   }
   g_state.hamming_path = path;
@@ -877,16 +847,6 @@ int rgbdslam_b200_brute_force_orb(const uint64_t* q, int nq, const uint64_t* t, 
   pd.q_kp = pd.t_kp = nullptr;
   pd.q_cloud = pd.t_cloud = nullptr;
   pd.q_cw = pd.q_ch = pd.t_cw = pd.t_ch = 0;
-  if (s.hamming_path != 0) {
-    if ((rc = s.W().d_i8_a.ensure(256 * (size_t)pad256(nq)))) return rc;
-    if ((rc = s.W().d_i8_b.ensure(256 * (size_t)pad256(nt)))) return rc;
-    std::vector<ExpandJob> jobs(2);
-    jobs[0] = {(const uint8_t*)s.W().d_feat_a.ptr, (int8_t*)s.W().d_i8_a.ptr, nq, pad256(nq)};
-    jobs[1] = {(const uint8_t*)s.W().d_feat_b.ptr, (int8_t*)s.W().d_i8_b.ptr, nt, pad256(nt)};
-    if ((rc = expand_nodes(jobs))) return rc;
-    pd.q_i8 = (const int8_t*)s.W().d_i8_a.ptr;
-    pd.t_i8 = (const int8_t*)s.W().d_i8_b.ptr;
-  }
   memcpy(s.W().h_pairs.ptr, &pd, sizeof(pd));
   e = cudaMemcpyAsync(s.W().d_pairs.ptr, s.W().h_pairs.ptr, sizeof(pd), cudaMemcpyHostToDevice, st);
   if (e != cudaSuccess) return cuda_fail(e, "brute_force_orb pair upload");
@@ -926,32 +886,16 @@ int rgbdslam_b200_node_create_from_features(int32_t id, const uint8_t* desc, con
     return cuda_fail(e, "cudaMalloc(node)");
   }
   nd->n_pad = pad256(n);
-  e = cudaMalloc(&nd->desc_i8, 256 * (size_t)nd->n_pad);
-  if (e != cudaSuccess) {
-    cudaFree(nd->desc);
-    cudaFree(nd->xyz);
-    delete nd;
-    return cuda_fail(e, "cudaMalloc(node int8 descriptors)");
-  }
-  {
+  if (n > 0) {
     cudaStream_t st = g_state.stream;
-    if (n > 0) {
-      e = cudaMemcpyAsync(nd->desc, desc, 32 * (size_t)n, cudaMemcpyHostToDevice, st);
-      if (e == cudaSuccess) e = cudaMemcpyAsync(nd->xyz, xyz1, 16 * (size_t)n, cudaMemcpyHostToDevice, st);
-    }
-    int rc2 = 0;
-    if (e == cudaSuccess) {
-      std::vector<ExpandJob> jobs(1);
-      jobs[0] = {nd->desc, nd->desc_i8, n, nd->n_pad};
-      rc2 = expand_nodes(jobs);
-    }
-    if (e == cudaSuccess && rc2 == 0) e = cudaStreamSynchronize(st);
-    if (e != cudaSuccess || rc2 != 0) {
+    e = cudaMemcpyAsync(nd->desc, desc, 32 * (size_t)n, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(nd->xyz, xyz1, 16 * (size_t)n, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
       cudaFree(nd->desc);
       cudaFree(nd->xyz);
-      cudaFree(nd->desc_i8);
       delete nd;
-      return rc2 ? rc2 : cuda_fail(e, "node upload");
+      return cuda_fail(e, "node upload");
     }
   }
   *node_handle = (uint64_t)(uintptr_t)nd;
@@ -1118,19 +1062,7 @@ static int match_pairs_host_impl(int slot, bool sync, const uint8_t* desc_newer,
   cudaEventRecord(s.W().ev[4], st);
   s.W().host_path = true;
   std::vector<PairDesc> pairs(npairs);
-  size_t on = 0, oo = 0, pn = 0, po = 0;
-  const bool tc = s.hamming_path != 0;
-  if (tc) {
-    size_t rows_n = 0, rows_o = 0;
-    for (int i = 0; i < npairs; i++) {
-      rows_n += pad256(n_newer[i]);
-      rows_o += pad256(n_older[i]);
-    }
-    if ((rc = s.W().d_i8_a.ensure(256 * rows_n))) return rc;
-    if ((rc = s.W().d_i8_b.ensure(256 * rows_o))) return rc;
-  }
-  std::vector<ExpandJob> jobs;
-  if (tc) jobs.reserve(2 * (size_t)npairs);
+  size_t on = 0, oo = 0;
   for (int i = 0; i < npairs; i++) {
     pairs[i].q_i8 = pairs[i].t_i8 = nullptr;
     pairs[i].q_f32 = pairs[i].t_f32 = pairs[i].t_norm = nullptr;
@@ -1138,14 +1070,6 @@ static int match_pairs_host_impl(int slot, bool sync, const uint8_t* desc_newer,
     pairs[i].q_kp = pairs[i].t_kp = nullptr;
     pairs[i].q_cloud = pairs[i].t_cloud = nullptr;
     pairs[i].q_cw = pairs[i].q_ch = pairs[i].t_cw = pairs[i].t_ch = 0;
-    if (tc) {
-      pairs[i].q_i8 = (const int8_t*)s.W().d_i8_a.ptr + 256 * pn;
-      pairs[i].t_i8 = (const int8_t*)s.W().d_i8_b.ptr + 256 * po;
-      jobs.push_back({(const uint8_t*)s.W().d_feat_a.ptr + 32 * on, (int8_t*)s.W().d_i8_a.ptr + 256 * pn, n_newer[i], pad256(n_newer[i])});
-      jobs.push_back({(const uint8_t*)s.W().d_feat_b.ptr + 32 * oo, (int8_t*)s.W().d_i8_b.ptr + 256 * po, n_older[i], pad256(n_older[i])});
-      pn += pad256(n_newer[i]);
-      po += pad256(n_older[i]);
-    }
     pairs[i].q_desc = (const uint32_t*)((const uint8_t*)s.W().d_feat_a.ptr + 32 * on);
     pairs[i].t_desc = (const uint32_t*)((const uint8_t*)s.W().d_feat_b.ptr + 32 * oo);
     pairs[i].q_xyz = (const float4*)s.W().d_xyz_a.ptr + on;
@@ -1157,7 +1081,6 @@ static int match_pairs_host_impl(int slot, bool sync, const uint8_t* desc_newer,
     on += n_newer[i];
     oo += n_older[i];
   }
-  if (tc && (rc = expand_nodes(jobs, 1))) return rc;
   auto bulk_uploads = [&]() -> int {
     cudaError_t e = cudaSuccess;
     if (tot_n) {
@@ -1170,7 +1093,7 @@ static int match_pairs_host_impl(int slot, bool sync, const uint8_t* desc_newer,
     }
     if (e != cudaSuccess) return cuda_fail(e, "match_pairs_host upload");
     cudaEventRecord(s.W().ev[5], st);
-    return tc ? expand_nodes(jobs, 2) : 0;
+    return 0;
   };
   return run_pairs(pairs, seed, first_pair_index, results, all_matches, inlier_matches, sync, bulk_uploads);
 }

@@ -488,12 +488,12 @@ int rgbdslam_b200_nodes_create_ex(uint64_t detector, int nframes, const uint8_t*
   cudaStream_t st = s.stream, cs = o.copy_stream;
   const int K = std::min(o.kp_stride, s.params.max_keypoints);  // features per node (finalize mode 1 emits <= max_keypoints)
   const int Kpad = ((K > 0 ? K : 1) + 255) / 256 * 256;
-  // slab: [desc F x K x 32][xyz F x K x 16][kp F x K x 28 (padded to 16)][i8 F x Kpad x 256][n F x 4]
+  // slab: [desc F x K x 32][xyz F x K x 16][kp F x K x 28][n F x 4]
   const size_t b_desc = ((size_t)nframes * K * 32 + 255) / 256 * 256, b_xyz = ((size_t)nframes * K * 16 + 255) / 256 * 256;
   const size_t b_kp = ((size_t)nframes * K * sizeof(rgbdslam_b200_keypoint) + 255) / 256 * 256;
-  const size_t b_i8 = (size_t)nframes * Kpad * 256, b_n = ((size_t)nframes * 4 + 255) / 256 * 256;
+  const size_t b_n = ((size_t)nframes * 4 + 255) / 256 * 256;
   NodeSlab* slab = new NodeSlab();
-  cudaError_t e = cudaMalloc(&slab->base, b_desc + b_xyz + b_kp + b_i8 + b_n);
+  cudaError_t e = cudaMalloc(&slab->base, b_desc + b_xyz + b_kp + b_n);
   if (e != cudaSuccess) {
     delete slab;
     return cuda_fail(e, "cudaMalloc(node slab)");
@@ -501,8 +501,7 @@ int rgbdslam_b200_nodes_create_ex(uint64_t detector, int nframes, const uint8_t*
   uint8_t* sl_desc = (uint8_t*)slab->base;
   float4* sl_xyz = (float4*)(sl_desc + b_desc);
   rgbdslam_b200_keypoint* sl_kp = (rgbdslam_b200_keypoint*)((uint8_t*)sl_xyz + b_xyz);
-  int8_t* sl_i8 = (int8_t*)((uint8_t*)sl_kp + b_kp);
-  int* sl_n = (int*)((uint8_t*)sl_i8 + b_i8);
+  int* sl_n = (int*)((uint8_t*)sl_kp + b_kp);
   auto fail = [&](int code) {
     cudaStreamSynchronize(cs);
     cudaStreamSynchronize(st);
@@ -560,11 +559,6 @@ int rgbdslam_b200_nodes_create_ex(uint64_t detector, int nframes, const uint8_t*
     e = orb_run_describe(o.g, o.tab, F, dg, (uint8_t*)o.pyr_raw.ptr, (uint8_t*)o.pyr_blur.ptr, sl_kp + (size_t)f0 * K, sl_n + f0, K, K,
                          (const float2*)o.trig.ptr, sl_desc + (size_t)f0 * K * 32, st, &launches);
     if (e != cudaSuccess) return fail(cuda_fail(e, "orb describe kernels"));
-    {
-      e = launch_expand_i8_strided(sl_desc + (size_t)f0 * K * 32, sl_i8 + (size_t)f0 * Kpad * 256, sl_n + f0, F, K, Kpad, st);
-      if (e != cudaSuccess) return fail(cuda_fail(e, "expand_i8 kernel"));
-      launches++;
-    }
     if (s.params.observability_threshold > 0.0) {  // Node::pc_col for the environment measurement model
       for (int f = 0; f < F; f++) {
         NodeDev* nd = new NodeDev();
@@ -597,7 +591,6 @@ int rgbdslam_b200_nodes_create_ex(uint64_t detector, int nframes, const uint8_t*
     nd->desc = sl_desc + (size_t)f * K * 32;
     nd->xyz = sl_xyz + (size_t)f * K;
     nd->kp = sl_kp + (size_t)f * K;
-    nd->desc_i8 = sl_i8 + (size_t)f * Kpad * 256;
     nd->slab = slab;
     slab->refs++;
     node_handles[f] = (uint64_t)(uintptr_t)nd;
@@ -652,12 +645,12 @@ int rgbdslam_b200_nodes_create_sharded(uint64_t detector, uint64_t comm_handle, 
   cudaStream_t st = s.stream, cs = o.copy_stream;
   const int K = std::min(o.kp_stride, s.params.max_keypoints);
   const int Kpad = ((K > 0 ? K : 1) + 255) / 256 * 256;
-  // slab: [desc Wp x K x 32][xyz Wp x K x 16][n Wp x 4][kp own x K x 28][i8 total x Kpad x 256]
+  // slab: [desc Wp x K x 32][xyz Wp x K x 16][n Wp x 4][kp own x K x 28]
   auto up = [](size_t v) { return (v + 255) / 256 * 256; };
   const size_t b_desc = up((size_t)Wp * K * 32), b_xyz = up((size_t)Wp * K * 16), b_n = up((size_t)Wp * 4);
-  const size_t b_kp = up(own_ * K * sizeof(rgbdslam_b200_keypoint)), b_i8 = (size_t)total_frames * Kpad * 256;
+  const size_t b_kp = up(own_ * K * sizeof(rgbdslam_b200_keypoint));
   NodeSlab* slab = new NodeSlab();
-  cudaError_t e = cudaMalloc(&slab->base, b_desc + b_xyz + b_n + b_kp + b_i8);
+  cudaError_t e = cudaMalloc(&slab->base, b_desc + b_xyz + b_n + b_kp);
   if (e != cudaSuccess) {
     delete slab;
     return cuda_fail(e, "cudaMalloc(node slab)");
@@ -666,7 +659,6 @@ int rgbdslam_b200_nodes_create_sharded(uint64_t detector, uint64_t comm_handle, 
   float4* sl_xyz = (float4*)(sl_desc + b_desc);
   int* sl_n = (int*)((uint8_t*)sl_xyz + b_xyz);
   rgbdslam_b200_keypoint* sl_kp = (rgbdslam_b200_keypoint*)((uint8_t*)sl_n + b_n);
-  int8_t* sl_i8 = (int8_t*)((uint8_t*)sl_kp + b_kp);
   auto fail = [&](int code) {
     cudaStreamSynchronize(cs);
     cudaStreamSynchronize(st);
@@ -761,9 +753,6 @@ int rgbdslam_b200_nodes_create_sharded(uint64_t detector, uint64_t comm_handle, 
     if (r == 0) r = g_nccl.AllGather((uint8_t*)(sl_n + (size_t)rank * per), sl_n, (size_t)per * 4, 0, cm->comm, st);
     if (r != 0) return fail(nccl_fail(r, "ncclAllGather(features)"));
   }
-  e = launch_expand_i8_strided(sl_desc, sl_i8, sl_n, total_frames, K, Kpad, st);
-  if (e != cudaSuccess) return fail(cuda_fail(e, "expand_i8 kernel"));
-  launches++;
   std::vector<int> n(total_frames);
   int flag = 0;
   e = cudaMemcpyAsync(n.data(), sl_n, 4 * (size_t)total_frames, cudaMemcpyDeviceToHost, st);
@@ -781,7 +770,6 @@ int rgbdslam_b200_nodes_create_sharded(uint64_t detector, uint64_t comm_handle, 
     nd->desc = sl_desc + (size_t)f * K * 32;
     nd->xyz = sl_xyz + (size_t)f * K;
     nd->kp = (f >= f0 && f < f1) ? sl_kp + (size_t)(f - f0) * K : nullptr;  // 2-D keypoints stay on the rank that built the node
-    nd->desc_i8 = sl_i8 + (size_t)f * Kpad * 256;
     nd->slab = slab;
     slab->refs++;
     node_handles[f] = (uint64_t)(uintptr_t)nd;

@@ -19,8 +19,8 @@ struct PairDesc {
   const float4* t_xyz;     // older node points
   int32_t nq, nt;
   int32_t id_q, id_t;  // node ids (newer, older)
-  const int8_t* q_i8;  // +-1 int8 expansion, tiled (hamming_tc.cu); nullptr if the SIMT path is used
-  const int8_t* t_i8;  // (SIFT nodes: the bf16 tiles)
+  const int8_t* q_i8;  // float-descriptor nodes: operand tiles (bf16 RootSIFT rows / u8 SiftGPU rows), else nullptr
+  const int8_t* t_i8;
   const float* q_f32;  // SIFT nodes only: fp32 (Root)SIFT rows and train-row norms
   const float* t_f32;
   const float* t_norm;
@@ -34,21 +34,14 @@ struct PairDesc {
   int32_t pad_;
 };
 
-// One unit of the +-1 int8 expansion (one node).
-struct ExpandJob {
-  const uint8_t* desc;  // n x 32 B
-  int8_t* out;          // n_pad x 256 B, tiled
-  int32_t n, n_pad;     // n_pad: multiple of 256
-};
-
-// One work item of the tensor-core Hamming kernel = (pair, 128-query tile).
+// One work item of the tensor-core match kernels = 256 queries of one pair against all train rows.
 struct HamItem {
-  const int8_t* a;     // query tile (32 KiB)
-  const int8_t* b;     // train matrix of the older node (n_btiles x 64 KiB)
-  int2* out;           // best[] slot of the tile's first query row
-  int32_t nq_valid;    // valid rows in this tile (1..128)
-  int32_t nsearch;     // nt - 1: only train rows [0, nt-2] are examined (features.cpp:174)
-  int32_t n_btiles;    // ceil(nsearch / 256)
+  const int8_t* a;     // query block: ORB -- 32-byte descriptor rows; float descriptors -- operand tiles (2 x 32 KiB)
+  const int8_t* b;     // train rows of the older node: ORB -- descriptor rows; float descriptors -- n_btiles x 32 KiB tiles
+  int2* out;           // best[] slot of the block's first query row
+  int32_t nq_valid;    // valid rows in this block (1..256)
+  int32_t nsearch;     // ORB: nt - 1, only train rows [0, nt-2] are examined (features.cpp:174); float descriptors: nt
+  int32_t n_btiles;    // ceil(nsearch / 128)
   int32_t pad_;        // SiftGPU pass: tie rule of the arg-max (0 = RowMatch_Kernel's thread-major order, 1 = lowest index)
   const float* bnorm;  // SIFT L2 only: |b|^2 of the train rows (bf16-rounded values); out then points to int4 records
 };

@@ -18,77 +18,11 @@
 //
 // Two kernels: tc_match256_kernel (operand tiles resident in HBM, staged by cp.async.bulk: the float-descriptor matchers and the
 // legacy ORB path) and tc_hamming_expand_kernel (the default ORB path: descriptors expanded inside the kernel).
+#include <cstdio>
+
 #include "kernels.h"
 
 namespace rb200 {
-
-// ---------------------------------------------------------------------------------------------
-// +-1 int8 expansion into the tiled layout described above.  One thread per 16-byte chunk.
-__global__ void __launch_bounds__(256) expand_i8_kernel(const ExpandJob* __restrict__ jobs) {
-  const ExpandJob job = jobs[blockIdx.y];
-  const int c = blockIdx.x * 256 + threadIdx.x;  // chunk index in output order
-  if (c >= job.n_pad * 16) return;
-  const int tile = c >> 11;          // 2048 chunks per 128-row tile
-  const int rg = (c >> 7) & 15;      // row group
-  const int kc = (c >> 3) & 15;      // 16-byte K chunk
-  const int rr = c & 7;              // row in group
-  const int row = tile * 128 + rg * 8 + rr;
-  uint4 out = make_uint4(0, 0, 0, 0);
-  if (row < job.n) {
-    const unsigned bits = (unsigned)job.desc[(size_t)row * 32 + kc * 2] | ((unsigned)job.desc[(size_t)row * 32 + kc * 2 + 1] << 8);
-    unsigned w[4];
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      unsigned v = 0;
-#pragma unroll
-      for (int b = 0; b < 4; b++) v |= (((bits >> (i * 4 + b)) & 1u) ? 0x01u : 0xFFu) << (8 * b);
-      w[i] = v;
-    }
-    out = make_uint4(w[0], w[1], w[2], w[3]);
-  }
-  reinterpret_cast<uint4*>(job.out)[c] = out;
-}
-
-// The same expansion for the nodes of one rgbdslam_b200_nodes_create chunk: node f has its descriptors at desc + f * K * 32,
-// its feature count in n[f] (device memory: no host round trip) and its tiles at out + f * n_pad * 256.
-__global__ void __launch_bounds__(256) expand_i8_strided_kernel(const uint8_t* __restrict__ desc, int8_t* __restrict__ out,
-                                                                const int* __restrict__ n, int K, int n_pad) {
-  const int f = blockIdx.y;
-  const int c = blockIdx.x * 256 + threadIdx.x;
-  if (c >= n_pad * 16) return;
-  const int tile = c >> 11, rg = (c >> 7) & 15, kc = (c >> 3) & 15, rr = c & 7;
-  const int row = tile * 128 + rg * 8 + rr;
-  uint4 o = make_uint4(0, 0, 0, 0);
-  if (row < n[f]) {
-    const uint8_t* d = desc + ((size_t)f * K + row) * 32 + kc * 2;
-    const unsigned bits = (unsigned)d[0] | ((unsigned)d[1] << 8);
-    unsigned w[4];
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      unsigned v = 0;
-#pragma unroll
-      for (int b = 0; b < 4; b++) v |= (((bits >> (i * 4 + b)) & 1u) ? 0x01u : 0xFFu) << (8 * b);
-      w[i] = v;
-    }
-    o = make_uint4(w[0], w[1], w[2], w[3]);
-  }
-  reinterpret_cast<uint4*>(out + (size_t)f * n_pad * 256)[c] = o;
-}
-
-cudaError_t launch_expand_i8_strided(const uint8_t* desc, int8_t* out, const int* d_n, int nframes, int K, int n_pad,
-                                     cudaStream_t stream) {
-  if (nframes <= 0 || n_pad <= 0) return cudaSuccess;
-  dim3 grid((n_pad * 16 + 255) / 256, nframes);
-  expand_i8_strided_kernel<<<grid, 256, 0, stream>>>(desc, out, d_n, K, n_pad);
-  return cudaGetLastError();
-}
-
-cudaError_t launch_expand_i8(const ExpandJob* d_jobs, int njobs, int max_n_pad, cudaStream_t stream) {
-  if (njobs <= 0 || max_n_pad <= 0) return cudaSuccess;
-  dim3 grid((max_n_pad * 16 + 255) / 256, njobs);
-  expand_i8_kernel<<<grid, 256, 0, stream>>>(d_jobs);
-  return cudaGetLastError();
-}
 
 // ---------------------------------------------------------------------------------------------
 // PTX helpers
@@ -116,6 +50,35 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+// mbarrier wait with a watchdog for the kernels under development (-DRB200_HANG_DEBUG): a wait that spins for ~1 s reports which
+// role was waiting on which barrier and traps, so that a pipeline bug surfaces as an error with a message instead of a hung GPU.
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+#ifdef RB200_HANG_DEBUG
+__device__ __noinline__ void mbar_wait_dbg(uint32_t bar, uint32_t parity, int tag, int a, int b) {
+  const long long t0 = clock64();
+  while (!mbar_try(bar, parity)) {
+    if (clock64() - t0 > 2000000000ll) {
+      printf("HANG block %d thread %d tag %d (%d, %d) bar %u parity %u\n", blockIdx.x, threadIdx.x, tag, a, b, bar, parity);
+      __trap();
+    }
+  }
+}
+#define RB200_WAIT(bar, parity, tag, a, b) mbar_wait_dbg(bar, parity, tag, a, b)
+#else
+#define RB200_WAIT(bar, parity, tag, a, b) mbar_wait(bar, parity)
+#endif
 __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
                "l"(src), "r"(bytes), "r"(bar)
@@ -487,9 +450,6 @@ static cudaError_t launch_tc256(const HamItem* d_items, int n_items, int sm_coun
   tc_match256_kernel<MODE><<<grid, kTc256Threads, kTc256SmemBytes, stream>>>(d_items, n_items);
   return cudaGetLastError();
 }
-cudaError_t launch_hamming_tc256(const HamItem* d_items, int n_items, int sm_count, cudaStream_t stream) {
-  return launch_tc256<0>(d_items, n_items, sm_count, stream);
-}
 cudaError_t launch_l2_tc256(const HamItem* d_items, int n_items, int sm_count, cudaStream_t stream) {
   return launch_tc256<1>(d_items, n_items, sm_count, stream);
 }
@@ -515,15 +475,16 @@ cudaError_t launch_siftgpu_tc256(const HamItem* d_items, int n_items, int sm_cou
 // col <= 4095 -- all exact in int32; dot = key >> 12 (arithmetic), col = 4095 - (key & 4095).
 //
 // Work item = 256 queries of one pair (two 128-row halves) against all train rows, 128-row train tiles.
-//   warps 0-3  : producers -- thread t expands row t of a tile (2 x LDG.128 -> 64 words of +-64 -> 16 x STS.128, layout
+//   warps 0-7  : producers, two groups of 128 threads filling alternate tiles -- thread t expands row t of a tile (2 x LDG.128 -> 64 words of +-64 -> 16 x STS.128, layout
 //                tile[row_group 16][k_chunk 16][row 8][16 B]); writes are published to the async proxy (fence.proxy.async)
 //                before the arrival on the tile's mbarrier
-//   warp 4     : MMA issuer (one elected lane): per train tile 2 halves x (8 + 1) tcgen05.mma.kind::i8 M128 N128 K32
-//   warps 5-12 : epilogue (TMEM lane quadrant = warp & 3, half = (warp - 5) >> 2)
+//   warp 8     : MMA issuer (one elected lane): per train tile 2 halves x (8 + 1) tcgen05.mma.kind::i8 M128 N128 K32
+//   warps 9-16 : epilogue (TMEM lane quadrant = warp & 3, half = (warp - 9) >> 2)
 // Shared memory: A ring 3 x 32 KiB (one query half per slot: the next item's first half is expanded while the current item
 // runs), B ring 3 x 32 KiB, the two 4 KiB index blocks.  TMEM: 2 stages x 2 halves x 128 int32 columns.
-constexpr int kXProducerWarps = 4, kXEpiWarps = 8;
-constexpr int kXThreads = (kXProducerWarps + 1 + kXEpiWarps) * 32;  // 416
+constexpr int kXProducerGroups = 2;                     // tiles are filled alternately by two groups of 128 threads
+constexpr int kXProducerWarps = 4 * kXProducerGroups, kXEpiWarps = 8;
+constexpr int kXThreads = (kXProducerWarps + 1 + kXEpiWarps) * 32;  // 544
 constexpr int kXASlots = 3, kXBSlots = 3;
 constexpr uint32_t kXIdxOff = (kXASlots + kXBSlots) * kTileA;      // 192 KiB
 constexpr uint32_t kXBarsOff = kXIdxOff + 2 * 4096;
@@ -572,8 +533,8 @@ __global__ void __launch_bounds__(kXThreads, 1) tc_hamming_expand_kernel(const H
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kXASlots; i++) { mbar_init(bar(kXAFull + i), kXProducerWarps * 32); mbar_init(bar(kXAEmpty + i), 1); }
-    for (int i = 0; i < kXBSlots; i++) { mbar_init(bar(kXBFull + i), kXProducerWarps * 32); mbar_init(bar(kXBEmpty + i), 1); }
+    for (int i = 0; i < kXASlots; i++) { mbar_init(bar(kXAFull + i), 128); mbar_init(bar(kXAEmpty + i), 1); }
+    for (int i = 0; i < kXBSlots; i++) { mbar_init(bar(kXBFull + i), 128); mbar_init(bar(kXBEmpty + i), 1); }
     mbar_init(bar(kXAccFull), 1);
     mbar_init(bar(kXAccFull + 1), 1);
     mbar_init(bar(kXAccEmpty), kXEpiWarps);
@@ -609,7 +570,8 @@ __global__ void __launch_bounds__(kXThreads, 1) tc_hamming_expand_kernel(const H
     // A(k+1,0) goes into the ring slot item k-1 has released, A(k+1,1) into item k's first slot, i.e. after item k is done --
     // by then the consumer already has half 0 and tile 0 of item k+1 to work on.  The descriptor row of the NEXT operation is
     // loaded before the current one is expanded, so the global-memory latency hides behind ~230 ALU instructions.
-    const int t = threadIdx.x;
+    const int t = threadIdx.x & 127, group = threadIdx.x >> 7;  // both groups walk the same schedule, group g executes every
+    int op_index = 0;                                           // kXProducerGroups-th operation of it
     const uint32_t row_off = (uint32_t)(t >> 3) * 2048u + (uint32_t)(t & 7) * 16u;
     struct Op {
       const uint4* src;  // this thread's descriptor row, nullptr = row does not exist (zeros)
@@ -680,16 +642,22 @@ __global__ void __launch_bounds__(kXThreads, 1) tc_hamming_expand_kernel(const H
           }
         }
       };
+      auto next_own = [&](Op& o) -> bool {
+        for (;;) {
+          if (!next_op(o)) return false;
+          if ((op_index++ % kXProducerGroups) == group) return true;
+        }
+      };
       Op op;
-      bool have = next_op(op);
+      bool have = next_own(op);
       uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
       if (have && op.src) { lo = __ldg(op.src); hi = __ldg(op.src + 1); }
       while (have) {
         Op nx;
-        const bool have_nx = next_op(nx);
+        const bool have_nx = next_own(nx);
         uint4 nlo = make_uint4(0, 0, 0, 0), nhi = nlo;
         if (have_nx && nx.src) { nlo = __ldg(nx.src); nhi = __ldg(nx.src + 1); }  // in flight while this row is expanded
-        mbar_wait(op.empty, op.parity);
+        RB200_WAIT(op.empty, op.parity, 1, (int)a_seq, (int)b_seq);
         expand_row(op.dst, lo, hi);
         fence_proxy_async_smem();
         mbar_arrive(op.full);
@@ -708,9 +676,9 @@ __global__ void __launch_bounds__(kXThreads, 1) tc_hamming_expand_kernel(const H
       for (int nb = 0; nb < n_btiles; nb++) {
         const uint32_t sb = b_seq % kXBSlots, pb = (b_seq / kXBSlots) & 1u;
         b_seq++;
-        mbar_wait(bar(kXBFull + sb), pb);
-        if (nb == 0) mbar_wait(bar(kXAFull + slot0), ph0);
-        mbar_wait(bar(kXAccEmpty + acc), pacc ^ 1u);
+        RB200_WAIT(bar(kXBFull + sb), pb, 2, k, nb);
+        if (nb == 0) RB200_WAIT(bar(kXAFull + slot0), ph0, 3, k, nb);
+        RB200_WAIT(bar(kXAccEmpty + acc), pacc ^ 1u, 4, k, nb);
         tc_fence_after();
         const uint64_t db = make_desc(sB + sb * kTileA);
         if (elect_one()) {
@@ -722,7 +690,7 @@ __global__ void __launch_bounds__(kXThreads, 1) tc_hamming_expand_kernel(const H
         }
         __syncwarp();
         if (nb == 0) {
-          mbar_wait(bar(kXAFull + slot1), ph1);
+          RB200_WAIT(bar(kXAFull + slot1), ph1, 5, k, nb);
           tc_fence_after();
         }
         if (elect_one()) {
@@ -736,6 +704,12 @@ __global__ void __launch_bounds__(kXThreads, 1) tc_hamming_expand_kernel(const H
         }
         __syncwarp();
         if (++acc == 2) { acc = 0; pacc ^= 1u; }
+      }
+      if (n_btiles == 0) {
+        // nothing to multiply (empty train set): the halves are still produced and must be consumed before they are released --
+        // releasing a slot the producer has not filled yet flips the barrier phase under its feet (deadlock)
+        RB200_WAIT(bar(kXAFull + slot0), ph0, 7, k, 0);
+        RB200_WAIT(bar(kXAFull + slot1), ph1, 8, k, 0);
       }
       if (elect_one()) {  // both query halves of the item are free once every MMA issued so far has retired
         tc_commit(bar(kXAEmpty + slot0));
@@ -754,7 +728,7 @@ __global__ void __launch_bounds__(kXThreads, 1) tc_hamming_expand_kernel(const H
       const HamItem item = items[blockIdx.x + (size_t)k * gridDim.x];
       int best = kNoBest;
       for (int nb = 0; nb < item.n_btiles; nb++) {
-        mbar_wait(bar(kXAccFull + acc), pacc);
+        RB200_WAIT(bar(kXAccFull + acc), pacc, 6, k, nb);
         tc_fence_after();
         const uint32_t t0 = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * 256 + h * 128;
         const int nvalid = item.nsearch - nb * 128;  // train rows of this tile that exist (>= 128: all)

@@ -11,16 +11,9 @@ cudaError_t set_dev_params(const DevParams& p, cudaStream_t stream);
 cudaError_t launch_hamming_simt(const PairDesc* pairs, int npairs, int max_nq, int2* best, int stride,
                                 cudaStream_t stream);
 
-// +-1 int8 expansion of the descriptors into the tiled UMMA operand layout (hamming_tc.cu).
-cudaError_t launch_expand_i8(const ExpandJob* d_jobs, int njobs, int max_n_pad, cudaStream_t stream);
-cudaError_t launch_expand_i8_strided(const uint8_t* desc, int8_t* out, const int* d_n, int nframes, int K, int n_pad,
-                                     cudaStream_t stream);
-// Tensor-core (tcgen05 kind::i8) Hamming brute force over work items; same output as launch_hamming_simt.
 // Hamming brute force on the tensor cores, 32-byte descriptors expanded to int8 operands inside the kernel (HamItem::a / b =
 // descriptor rows); same output as launch_hamming_simt.
 cudaError_t launch_hamming_tc_expand(const HamItem* d_items, int n_items, int sm_count, cudaStream_t stream);
-// 256-query work items (HamItem::n_btiles counts 128-row B tiles, nq_valid <= 256)
-cudaError_t launch_hamming_tc256(const HamItem* d_items, int n_items, int sm_count, cudaStream_t stream);
 cudaError_t launch_l2_tc256(const HamItem* d_items, int n_items, int sm_count, cudaStream_t stream);
 
 // SIFT-128 path (sift_l2.cu / hamming_tc.cu MODE 1)

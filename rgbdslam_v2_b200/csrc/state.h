@@ -41,13 +41,13 @@ struct NodeDev {
   rgbdslam_b200_keypoint* kp = nullptr;  // n x cv::KeyPoint (only for nodes built from images)
   float* desc_f32 = nullptr;  // SIFT nodes: n x 128 fp32 (Root)SIFT rows (desc == nullptr then)
   float* norms = nullptr;     // SIFT nodes: n_pad |b|^2 of the bf16-rounded rows
-  int8_t* desc_i8 = nullptr;  // n_pad x 256 B  +-1 expansion for the tensor-core Hamming path (lazily built)
+  int8_t* desc_i8 = nullptr;  // float-descriptor nodes only: n_pad x 256 B operand tiles (bf16 RootSIFT rows / u8 SiftGPU rows)
   int32_t n_pad = 0;
   float* cloud_z = nullptr;   // depth cloud z-plane (cw x ch) for the environment measurement model
   int32_t cw = 0, ch = 0;
   float K[4] = {0, 0, 0, 0};  // fx, fy, cx, cy of the full-resolution camera
   int32_t sift_kind = 0;      // SIFT nodes: 0 = RootSIFT rows + bf16 tiles, 1 = raw rows + u8 tiles (SiftGPU matcher)
-  NodeSlab* slab = nullptr;   // desc / xyz / kp / desc_i8 live inside this shared allocation (cloud_z is always separate)
+  NodeSlab* slab = nullptr;   // desc / xyz / kp live inside this shared allocation (cloud_z is always separate)
 };
 
 constexpr int kSlots = 8;  // independent in-flight match_pairs pipelines (stream + workspace each)
@@ -91,7 +91,7 @@ struct State {
   Workspace& W() { return *cur; }
   DevBuf d_f32_a, d_f32_b, d_root_a, d_root_b, d_norm_a, d_norm_b;  // SIFT staging of the synchronous calls
   int sift_matcher = 0;  // float-descriptor nodes created from now on: 0 = exact 2-NN ratio matcher (FLANN branch), 1 = SiftGPU matcher
-  int hamming_path = 1;  // 1 = tcgen05 int8 GEMM, operands expanded in the kernel (default); 2 = resident operand tiles; 0 = SIMT popcount
+  int hamming_path = 1;  // 1 = tcgen05 int8 GEMM, operands expanded inside the kernel (default); 0 = SIMT popcount (cross-check)
   void release_workspaces() {
     for (Workspace& w : ws) w.release();
     DevBuf* all[] = {&d_f32_a, &d_f32_b, &d_root_a, &d_root_b, &d_norm_a, &d_norm_b};
@@ -104,7 +104,6 @@ void set_error(const std::string& s);
 int cuda_fail(cudaError_t e, const char* what);
 int check_inited();
 int node_build_cloud(NodeDev* nd, const float* d_depth, int w, int h, const float K4[4], cudaStream_t st);
-int expand_nodes_public(const std::vector<ExpandJob>& jobs);  // +-1 int8 expansion (api.cu)
 void free_node(NodeDev* nd);  // frees everything a (possibly half-built) node owns (api.cu)
 
 }  // namespace rb200
