@@ -373,6 +373,22 @@ int rgbdslam_b200_graph_from_pairs(int n_frames, int n_pairs, const int32_t* pai
 int rgbdslam_b200_posegraph_chi2(int nv, const double* poses, int ne, const int32_t* ij, const double* meas,
                                  const double* info, double huber_delta, double* chi2, double* per_edge_chi2);
 
+/* Bundle adjustment over camera poses AND 3-D landmarks (the reference's DO_FEATURE_OPTIMIZATION build: src/landmark.cpp:97-187
+ * creates a VertexPointXYZ per landmark and an EdgeSE3PointXYZDepth per observation, optimizeGraphImpl includes them when
+ * optimize_landmarks is set, src/graph_manager.cpp:963-967).  Observation o: landmark obs_point[o] seen by camera obs_cam[o]
+ * at pixel (u, v) with depth d (obs_uvd, 3 doubles), information diag(obs_info3[o]) -- the reference uses
+ * point_information_matrix(d) = diag(1, 1, 1 / depth_covariance(d)) (misc2.h:37-47) -- pin-hole K4 = (fx, fy, cx, cy)
+ * (ParameterCamera, graph_manager.cpp:189-192).  Optional pose-pose edges (ij / meas7 / info36, as posegraph_optimize) share
+ * the Huber kernel of width huber_delta; projection edges have no robust kernel (landmark.cpp:176).  Runs `iterations`
+ * Levenberg-Marquardt iterations (optimizer_->optimize(n)); every step eliminates the landmarks by the Schur complement and
+ * solves the reduced camera system with a block-Jacobi PCG on the GPU.  poses7 (n_cams x 7: t, q) and points3 (n_points x 3,
+ * world frame) are updated in place; chi2_* include the robustified pose-edge terms. */
+int rgbdslam_b200_landmark_ba(int n_cams, double* poses7, const uint8_t* fixed, int n_points, double* points3, int n_obs,
+                              const int32_t* obs_cam, const int32_t* obs_point, const double* obs_uvd, const double* obs_info3,
+                              const double* K4, int n_edges, const int32_t* ij, const double* meas7, const double* info36,
+                              int iterations, double huber_delta, double* chi2_before, double* chi2_after, int* lm_iterations,
+                              int* pcg_iterations);
+
 #ifdef __cplusplus
 }
 #endif

@@ -149,6 +149,9 @@ def load_library(path: str | Path | None = None) -> C.CDLL:
                                                      C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.rgbdslam_b200_graph_from_pairs.argtypes = [C.c_int, C.c_int, vp, vp, C.c_double, vp, vp, vp, vp, vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.rgbdslam_b200_posegraph_chi2.argtypes = [C.c_int, vp, C.c_int, vp, vp, vp, C.c_double, C.POINTER(C.c_double), vp]
+    lib.rgbdslam_b200_landmark_ba.argtypes = [C.c_int, vp, vp, C.c_int, vp, C.c_int, vp, vp, vp, vp, vp, C.c_int, vp, vp, vp, C.c_int,
+                                              C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int),
+                                              C.POINTER(C.c_int)]
     lib.rgbdslam_b200_last_timing.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float)]
     lib.rgbdslam_b200_slot_stage_times.argtypes = [C.c_int, vp]
     lib.rgbdslam_b200_timeline_epoch.argtypes = []
@@ -510,6 +513,28 @@ class Frontend:
         self._check(self.lib.rgbdslam_b200_posegraph_optimize(len(x), _ptr(x), _ptr(fixed), len(ij), _ptr(ij), _ptr(meas),
                                                               _ptr(info), stop, huber_delta, C.byref(chi2), C.byref(it), C.byref(cg)))
         return x, chi2.value, it.value, cg.value
+
+    def landmark_ba(self, poses, fixed, points, obs_cam, obs_point, obs_uvd, obs_info3, K4, ij=None, meas=None, info=None,
+                    iterations: int = 10, huber_delta: float = 1.0):
+        """Camera + landmark bundle adjustment (the reference's DO_FEATURE_OPTIMIZATION graph, landmark.cpp:97-187).
+        Returns (poses, points, chi2_before, chi2_after, lm_iterations, pcg_iterations)."""
+        x = np.array(poses, np.float64, order="C")
+        pts = np.array(points, np.float64, order="C").reshape(-1, 3)
+        fixed = np.ascontiguousarray(fixed, np.uint8)
+        oc = np.ascontiguousarray(obs_cam, np.int32)
+        op = np.ascontiguousarray(obs_point, np.int32)
+        uvd = np.ascontiguousarray(obs_uvd, np.float64).reshape(-1, 3)
+        w3 = np.ascontiguousarray(obs_info3, np.float64).reshape(-1, 3)
+        K = np.ascontiguousarray(K4, np.float64)
+        ne = 0 if ij is None else len(ij)
+        ij_ = None if ne == 0 else np.ascontiguousarray(ij, np.int32)
+        meas_ = None if ne == 0 else np.ascontiguousarray(meas, np.float64)
+        info_ = None if ne == 0 else np.ascontiguousarray(info, np.float64)
+        c0, c1, it, cg = C.c_double(), C.c_double(), C.c_int(), C.c_int()
+        self._check(self.lib.rgbdslam_b200_landmark_ba(len(x), _ptr(x), _ptr(fixed), len(pts), _ptr(pts), len(oc), _ptr(oc), _ptr(op),
+                                                       _ptr(uvd), _ptr(w3), _ptr(K), ne, _ptr(ij_), _ptr(meas_), _ptr(info_), iterations,
+                                                       huber_delta, C.byref(c0), C.byref(c1), C.byref(it), C.byref(cg)))
+        return x, pts, c0.value, c1.value, it.value, cg.value
 
     def graph_chi2(self, poses, ij, meas, info, huber_delta: float = 1.0, per_edge: bool = False):
         x = np.ascontiguousarray(poses, np.float64)

@@ -585,6 +585,7 @@ int rgbdslam_b200_shutdown(void) {
   cudaDeviceSynchronize();
   s.release_workspaces();
   posegraph_release();
+  landmark_ba_release();
   for (int k = 0; k < kSlots; k++) {
     for (int i = 0; i < 8; i++) cudaEventDestroy(s.ws[k].ev[i]);
     cudaEventDestroy(s.ws[k].ev_gather);

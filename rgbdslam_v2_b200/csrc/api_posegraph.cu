@@ -42,6 +42,34 @@ int rgbdslam_b200_posegraph_chi2(int nv, const double* poses, int ne, const int3
                             nullptr, nullptr, per_edge_chi2, false);
 }
 
+int rgbdslam_b200_landmark_ba(int n_cams, double* poses7, const uint8_t* fixed, int n_points, double* points3, int n_obs,
+                              const int32_t* obs_cam, const int32_t* obs_point, const double* obs_uvd, const double* obs_info3,
+                              const double* K4, int n_edges, const int32_t* ij, const double* meas7, const double* info36,
+                              int iterations, double huber_delta, double* chi2_before, double* chi2_after, int* lm_iterations,
+                              int* pcg_iterations) {
+  std::lock_guard<std::mutex> lk(g_state.mu);
+  int rc = check_inited();
+  if (rc) return rc;
+  if (n_cams <= 0 || n_points < 0 || n_obs < 0 || n_edges < 0 || iterations < 0 || !poses7 || !fixed || !K4 ||
+      (n_points > 0 && !points3) || (n_obs > 0 && (!obs_cam || !obs_point || !obs_uvd || !obs_info3)) ||
+      (n_edges > 0 && (!ij || !meas7 || !info36)) || !(huber_delta > 0)) {
+    set_error("landmark_ba: bad arguments");
+    return RGBDSLAM_B200_ERR_ARG;
+  }
+  for (size_t k = 0; k < (size_t)n_obs * 3; k++)
+    if (!std::isfinite(obs_info3[k]) || !std::isfinite(obs_uvd[k])) {
+      set_error("landmark_ba: non-finite observation or information entry");
+      return RGBDSLAM_B200_ERR_ARG;
+    }
+  for (size_t k = 0; k < (size_t)n_edges * 36; k++)
+    if (!std::isfinite(info36[k])) {
+      set_error("landmark_ba: non-finite entry in an information matrix");
+      return RGBDSLAM_B200_ERR_ARG;
+    }
+  return landmark_ba(n_cams, poses7, fixed, n_points, points3, n_obs, obs_cam, obs_point, obs_uvd, obs_info3, K4, n_edges, ij, meas7,
+                     info36, iterations, huber_delta, chi2_before, chi2_after, lm_iterations, pcg_iterations);
+}
+
 // ---- host glue: MatchingResults of an offline candidate list -> vertices and edges --------------------------------
 namespace {
 inline void qmul(const double* a, const double* b, double* o) {  // (x y z w)

@@ -502,23 +502,26 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 // 4 descriptor bits (bits 0-3 of x, x < 16) -> 4 int8: bit set -> +64, clear -> -64
-__device__ __forceinline__ uint32_t pm64_from_nibble(uint32_t x) {
-  const uint32_t s4 = (x * 0x00204081u) & 0x01010101u;  // bit i -> byte i (0 / 1)
-  return 0xC0C0C0C0u - s4 * 0x80u;                      // per byte 0xC0 (-64) or 0x40 (+64), no borrow between bytes
+// (x & 0x80808080) ^ 0xC0C0C0C0 in ONE LOP3 (immLut (a & b) ^ c = (0xF0 & 0xCC) ^ 0xAA = 0x6A): bit 7 of every byte of x selects
+// 0x40 (+64, bit set) or 0xC0 (-64, bit clear)
+__device__ __forceinline__ uint32_t pm64_from_bit7(uint32_t x) {
+  uint32_t r;
+  asm("lop3.b32 %0, %1, %2, %3, 0x6A;" : "=r"(r) : "r"(x), "r"(0x80808080u), "r"(0xC0C0C0C0u));
+  return r;
 }
-// One 256-bit descriptor (8 words) -> 256 int8 at tile_row_addr + k_chunk * 128 (k_chunk = 16 descriptor bits = 16 bytes)
+// One 256-bit descriptor (8 words) -> 256 int8 (+-64) at tile_row_addr + k_chunk * 128 (k_chunk = 16 operand bytes).
+// The order of the 256 k positions inside a row is free as long as both operands use the same one (a dot product is a sum),
+// so no bit is ever moved to a "natural" place: output word s of input word w is the four bits 7-s, 15-s, 23-s, 31-s, brought
+// to bit 7 of their byte by one left shift (an IMAD on the FMA pipe) and turned into +-64 by one LOP3 -- one ALU-pipe
+// instruction per 4 operand bytes.
 __device__ __forceinline__ void expand_row(uint32_t tile_row_addr, const uint4 lo, const uint4 hi) {
   const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
 #pragma unroll
   for (int i = 0; i < 8; i++) {
-    const uint32_t m0 = w[i] & 0x0F0F0F0Fu, m1 = (w[i] >> 4) & 0x0F0F0F0Fu;  // low / high nibble of every byte
 #pragma unroll
-    for (int hf = 0; hf < 2; hf++) {  // two 16-bit halves of the word = two k-chunks
-      const uint32_t n0 = __byte_perm(m0, 0, 0x4440 + 2 * hf), n1 = __byte_perm(m1, 0, 0x4440 + 2 * hf);
-      const uint32_t n2 = __byte_perm(m0, 0, 0x4441 + 2 * hf), n3 = __byte_perm(m1, 0, 0x4441 + 2 * hf);
-      sts128(tile_row_addr + (uint32_t)(2 * i + hf) * 128u, pm64_from_nibble(n0), pm64_from_nibble(n1), pm64_from_nibble(n2),
-             pm64_from_nibble(n3));
-    }
+    for (int hf = 0; hf < 2; hf++)
+      sts128(tile_row_addr + (uint32_t)(2 * i + hf) * 128u, pm64_from_bit7(w[i] << (4 * hf)), pm64_from_bit7(w[i] << (4 * hf + 1)),
+             pm64_from_bit7(w[i] << (4 * hf + 2)), pm64_from_bit7(w[i] << (4 * hf + 3)));
   }
 }
 

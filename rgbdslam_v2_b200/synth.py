@@ -385,3 +385,79 @@ def make_refine_scene(rng, n, noise_px=0.3, noise_z=0.002, angle=0.08, trans=(0.
     return X1, kp_n, xyz_n, kp_e, xyz_e
 
 
+
+
+# ------------------------------------------------------------------------------------------------
+# landmark bundle adjustment problems (landmark.cpp:97-187: cameras, 3-D landmarks, (u, v, depth) observations)
+def landmark_information(depths: np.ndarray, sigma_depth: float = 0.01, static_first: bool = False) -> np.ndarray:
+    """point_information_matrix (misc2.h:37-47) per observation: diag(1, 1, 1 / depth_covariance(d)), depth_covariance =
+    (sigma_depth d^2)^2 (misc2.h:20-35).  static_first=True reproduces the reference's function-local statics: the covariance
+    of the FIRST depth ever passed is reused for every later call."""
+    d = np.asarray(depths, np.float64)
+    ref = np.full_like(d, d.flat[0]) if (static_first and d.size) else d
+    w = np.ones((d.size, 3))
+    w[:, 2] = 1.0 / (sigma_depth * ref.reshape(-1) ** 2) ** 2
+    return w
+
+
+def make_ba_problem(n_cams: int = 6, n_points: int = 60, seed: int = 0, pix_noise: float = 0.3, depth_sigma: float = 0.002,
+                    pose_noise: float = 0.03, rot_noise_deg: float = 1.5, K4=(525.0, 525.0, 319.5, 239.5), with_edges: bool = True,
+                    edge_noise: float = 0.01):
+    """Cameras on a short arc looking at a point cloud; every point is observed by every camera that sees it inside 640x480.
+    Returns a dict with ground truth, perturbed initial poses, landmarks initialised from their FIRST observation through the
+    initial pose of that camera (updateLandmarkInGraph, landmark.cpp:100-121), observations and odometry-like pose edges."""
+    rng = np.random.default_rng(seed)
+    fx, fy, cx, cy = K4
+    gt = np.zeros((n_cams, 7))
+    step_ang, step_x = min(0.08, 0.6 / n_cams), min(0.15, 1.2 / n_cams)  # the whole arc keeps the cloud in view
+    for c in range(n_cams):
+        ang = step_ang * c
+        q = np.array([0.0, np.sin(ang / 2), 0.0, np.cos(ang / 2)])
+        gt[c, :3] = [step_x * c, 0.02 * np.sin(c), 0.2 * step_x * c]
+        gt[c, 3:] = q
+    pts = np.stack([rng.uniform(-1.2, 1.8, n_points), rng.uniform(-0.9, 0.9, n_points), rng.uniform(1.5, 4.0, n_points)], 1)
+    oc, op, uvd = [], [], []
+    for c in range(n_cams):
+        R = _quat_to_rot(gt[c, 3:])
+        pc = (pts - gt[c, :3]) @ R  # R^T (p - t)
+        u = fx * pc[:, 0] / pc[:, 2] + cx
+        v = fy * pc[:, 1] / pc[:, 2] + cy
+        ok = (pc[:, 2] > 0.4) & (u > 0) & (u < 639) & (v > 0) & (v < 479)
+        for p in np.nonzero(ok)[0]:
+            oc.append(c); op.append(p)
+            uvd.append([u[p] + rng.normal(0, pix_noise), v[p] + rng.normal(0, pix_noise), pc[p, 2] + rng.normal(0, depth_sigma)])
+    oc, op, uvd = np.array(oc, np.int32), np.array(op, np.int32), np.array(uvd)
+    seen = np.zeros(n_points, bool); seen[op] = True
+    remap = -np.ones(n_points, np.int64); remap[seen] = np.arange(seen.sum())
+    pts = pts[seen]; op = remap[op].astype(np.int32)
+    init = gt.copy()
+    for c in range(1, n_cams):
+        d = np.concatenate([rng.normal(0, pose_noise, 3), np.deg2rad(rot_noise_deg) / 2 * rng.normal(0, 1, 3)])
+        init[c] = pose_compose(gt[c], np.concatenate([d[:3], d[3:], [np.sqrt(max(0.0, 1 - d[3:] @ d[3:]))]]))
+    p0 = np.zeros_like(pts)
+    first = {}
+    for o in range(len(oc)):
+        first.setdefault(int(op[o]), o)
+    for p, o in first.items():
+        c = oc[o]
+        x = (uvd[o, 0] - cx) / fx * uvd[o, 2]; y = (uvd[o, 1] - cy) / fy * uvd[o, 2]
+        p0[p] = init[c, :3] + _quat_to_rot(init[c, 3:]) @ np.array([x, y, uvd[o, 2]])
+    fixed = np.zeros(n_cams, np.uint8); fixed[0] = 1
+    out = dict(gt_poses=gt, gt_points=pts, poses=init, points=p0, fixed=fixed, obs_cam=oc, obs_point=op, obs_uvd=uvd,
+               obs_info3=landmark_information(uvd[:, 2], sigma_depth=max(depth_sigma, 0.002) / 4.0), K4=np.array(K4, np.float64))
+    if with_edges:
+        ij, meas, info = [], [], []
+        for c in range(n_cams - 1):
+            rel = pose_compose(pose_inverse(gt[c]), gt[c + 1])
+            d = np.concatenate([rng.normal(0, edge_noise, 3), rng.normal(0, edge_noise / 2, 3)])
+            rel = pose_compose(rel, np.concatenate([d, [np.sqrt(1 - d[3:] @ d[3:])]]))
+            ij.append([c, c + 1]); meas.append(rel); info.append((np.eye(6) * 400.0).reshape(-1))
+        out.update(ij=np.array(ij, np.int32), meas=np.array(meas), info=np.array(info))
+    return out
+
+
+def _quat_to_rot(q):
+    x, y, z, w = q / np.linalg.norm(q)
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
