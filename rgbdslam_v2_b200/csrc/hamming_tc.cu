@@ -475,23 +475,26 @@ cudaError_t launch_siftgpu_tc256(const HamItem* d_items, int n_items, int sm_cou
 // col <= 4095 -- all exact in int32; dot = key >> 12 (arithmetic), col = 4095 - (key & 4095).
 //
 // Work item = 256 queries of one pair (two 128-row halves) against all train rows, 128-row train tiles.
-//   warps 0-7  : producers, two groups of 128 threads filling alternate tiles -- thread t expands row t of a tile (2 x LDG.128 -> 64 words of +-64 -> 16 x STS.128, layout
+//   warps 0-7  : producers, two groups of 128 threads filling alternate tiles, one thread per tile row (2 x LDG.128 -> 64 words of +-64 -> 16 x STS.128, layout
 //                tile[row_group 16][k_chunk 16][row 8][16 B]); writes are published to the async proxy (fence.proxy.async)
 //                before the arrival on the tile's mbarrier
-//   warp 8     : MMA issuer (one elected lane): per train tile 2 halves x (8 + 1) tcgen05.mma.kind::i8 M128 N128 K32
-//   warps 9-16 : epilogue (TMEM lane quadrant = warp & 3, half = (warp - 9) >> 2)
+//   warps 8-9  : MMA issuers, one per query half (one elected lane each): per train tile (8 + 1) tcgen05.mma.kind::i8 M128 N128 K32
+//   warps 10-17: epilogue (TMEM lane quadrant = warp & 3, half = (warp - 10) >> 2)
 // Shared memory: A ring 3 x 32 KiB (one query half per slot: the next item's first half is expanded while the current item
 // runs), B ring 3 x 32 KiB, the two 4 KiB index blocks.  TMEM: 2 stages x 2 halves x 128 int32 columns.
+#ifndef RB200_X_EPI_PAIR
+#define RB200_X_EPI_PAIR 1
+#endif
 constexpr int kXProducerGroups = 2;                     // tiles are filled alternately by two groups of 128 threads
-constexpr int kXProducerWarps = 4 * kXProducerGroups, kXEpiWarps = 8;
-constexpr int kXThreads = (kXProducerWarps + 1 + kXEpiWarps) * 32;  // 544
+constexpr int kXProducerWarps = 4 * kXProducerGroups, kXIssuerWarps = 2, kXEpiWarps = 8;
+constexpr int kXThreads = (kXProducerWarps + kXIssuerWarps + kXEpiWarps) * 32;  // 576
 constexpr int kXASlots = 3, kXBSlots = 3;
 constexpr uint32_t kXIdxOff = (kXASlots + kXBSlots) * kTileA;      // 192 KiB
 constexpr uint32_t kXBarsOff = kXIdxOff + 2 * 4096;
 constexpr uint32_t kXSmemBytes = kXBarsOff + 256;
 static_assert(kXSmemBytes <= 232448, "tc_hamming_expand: shared memory over the 227 KiB per-CTA limit");
 constexpr int kXAFull = 0, kXAEmpty = kXASlots, kXBFull = 2 * kXASlots, kXBEmpty = 2 * kXASlots + kXBSlots,
-              kXAccFull = 2 * kXASlots + 2 * kXBSlots, kXAccEmpty = kXAccFull + 2, kXBarCount = kXAccEmpty + 2;
+              kXAccFull = 2 * kXASlots + 2 * kXBSlots, kXAccEmpty = kXAccFull + 4, kXBarCount = kXAccEmpty + 4;  // [stage][half]
 static_assert(kXBarCount * 8 <= 192, "barrier area");
 
 __device__ __forceinline__ uint64_t make_desc_lbo_sbo(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -509,22 +512,22 @@ __device__ __forceinline__ uint32_t pm64_from_bit7(uint32_t x) {
   asm("lop3.b32 %0, %1, %2, %3, 0x6A;" : "=r"(r) : "r"(x), "r"(0x80808080u), "r"(0xC0C0C0C0u));
   return r;
 }
-// One 256-bit descriptor (8 words) -> 256 int8 (+-64) at tile_row_addr + k_chunk * 128 (k_chunk = 16 operand bytes).
+// A 256-bit descriptor (8 words) becomes 256 int8 (+-64) at tile_row_addr + k_chunk * 128 (k_chunk = 16 operand bytes).
 // The order of the 256 k positions inside a row is free as long as both operands use the same one (a dot product is a sum),
 // so no bit is ever moved to a "natural" place: output word s of input word w is the four bits 7-s, 15-s, 23-s, 31-s, brought
 // to bit 7 of their byte by one left shift (an IMAD on the FMA pipe) and turned into +-64 by one LOP3 -- one ALU-pipe
 // instruction per 4 operand bytes.
-__device__ __forceinline__ void expand_row(uint32_t tile_row_addr, const uint4 lo, const uint4 hi) {
-  const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+// half a descriptor (4 words) -> 128 int8 in 8 consecutive k-chunks starting at addr (the caller adds 1024 B for the upper half)
+__device__ __forceinline__ void expand_half_row(uint32_t addr, const uint4 v) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-  for (int i = 0; i < 8; i++) {
+  for (int i = 0; i < 4; i++) {
 #pragma unroll
     for (int hf = 0; hf < 2; hf++)
-      sts128(tile_row_addr + (uint32_t)(2 * i + hf) * 128u, pm64_from_bit7(w[i] << (4 * hf)), pm64_from_bit7(w[i] << (4 * hf + 1)),
+      sts128(addr + (uint32_t)(2 * i + hf) * 128u, pm64_from_bit7(w[i] << (4 * hf)), pm64_from_bit7(w[i] << (4 * hf + 1)),
              pm64_from_bit7(w[i] << (4 * hf + 2)), pm64_from_bit7(w[i] << (4 * hf + 3)));
   }
 }
-
 __global__ void __launch_bounds__(kXThreads, 1) tc_hamming_expand_kernel(const HamItem* __restrict__ items, int n_items) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sA = smem_u32(smem);
@@ -534,14 +537,15 @@ __global__ void __launch_bounds__(kXThreads, 1) tc_hamming_expand_kernel(const H
   auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + kXBarsOff + 192);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef RB200_PROFILE_TC
+  unsigned long long gt_entry;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_entry));
+#endif
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kXASlots; i++) { mbar_init(bar(kXAFull + i), 128); mbar_init(bar(kXAEmpty + i), 1); }
-    for (int i = 0; i < kXBSlots; i++) { mbar_init(bar(kXBFull + i), 128); mbar_init(bar(kXBEmpty + i), 1); }
-    mbar_init(bar(kXAccFull), 1);
-    mbar_init(bar(kXAccFull + 1), 1);
-    mbar_init(bar(kXAccEmpty), kXEpiWarps);
-    mbar_init(bar(kXAccEmpty + 1), kXEpiWarps);
+    for (int i = 0; i < kXBSlots; i++) { mbar_init(bar(kXBFull + i), 128); mbar_init(bar(kXBEmpty + i), kXIssuerWarps); }
+    for (int i = 0; i < 4; i++) { mbar_init(bar(kXAccFull + i), 1); mbar_init(bar(kXAccEmpty + i), kXEpiWarps / 2); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (threadIdx.x < 128) {
@@ -565,164 +569,146 @@ __global__ void __launch_bounds__(kXThreads, 1) tc_hamming_expand_kernel(const H
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   const int my_items = blockIdx.x < n_items ? (n_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+#ifdef RB200_PROFILE_TC
+  // cycles this warp spends in each kind of wait (role 0 producers: [0] slot empty; role 1 issuer: [0] A full, [1] B full,
+  // [2] accumulator empty; role 2 epilogue: [2] accumulator full), [3] = lifetime, [4] = warps, [5] = cycles inside expand_row /
+  // the drain of a tile
+  long long pf_a = 0, pf_b = 0, pf_acc = 0, pf_work = 0;
+  const long long pf_t0 = clock64();
+  unsigned long long pf_gt_start;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(pf_gt_start));
+#define XWAIT(ACC, BAR, PAR, TAG, I, J) { const long long c0_ = clock64(); mbar_wait(BAR, PAR); ACC += clock64() - c0_; }
+#else
+#define XWAIT(ACC, BAR, PAR, TAG, I, J) RB200_WAIT(BAR, PAR, TAG, I, J)
+#endif
 
   if (warp < kXProducerWarps) {
-    // ---------------- producers: thread t <-> row t of whichever 128-row tile is being filled
-    // Order of production (the consumer needs, per item: half 0 + tile 0, then half 1, then the other tiles):
+    // ---------------- producers: two groups of 128 threads filling ALTERNATE tiles, thread t & 127 <-> row of the tile.
+    // (One fence.proxy.async per thread and tile costs a few hundred cycles in which the warp issues nothing: with all 256
+    // threads on every tile, two per row, the match kernel was 4 us slower than with the other group expanding meanwhile.)
+    // Order of production (the consumers need, per item: half 0 + tile 0, then half 1, then the other tiles):
     //   A(0,0) B(0,0) A(0,1) | B(k,1) A(k+1,0) B(k,2) ... B(k,n-1) B(k+1,0) A(k+1,1) | ...
     // A(k+1,0) goes into the ring slot item k-1 has released, A(k+1,1) into item k's first slot, i.e. after item k is done --
-    // by then the consumer already has half 0 and tile 0 of item k+1 to work on.  The descriptor row of the NEXT operation is
-    // loaded before the current one is expanded, so the global-memory latency hides behind ~230 ALU instructions.
-    const int t = threadIdx.x & 127, group = threadIdx.x >> 7;  // both groups walk the same schedule, group g executes every
-    int op_index = 0;                                           // kXProducerGroups-th operation of it
-    const uint32_t row_off = (uint32_t)(t >> 3) * 2048u + (uint32_t)(t & 7) * 16u;
-    struct Op {
-      const uint4* src;  // this thread's descriptor row, nullptr = row does not exist (zeros)
-      uint32_t dst, full, empty, parity;
-    };
+    // by then the consumers already have half 0 and tile 0 of item k+1 to work on.  The schedule is written out as plain loops
+    // (an earlier resumable state machine cost the producer warps 2.8 x the cycles of the expansion itself -- ncu source
+    // view); one operation is kept in flight: produce() first issues the loads of the NEW operation, then waits for the ring
+    // slot of the PREVIOUS one and expands it, so the load latency hides behind the expansion.
+    const int prow = threadIdx.x & 127, group = threadIdx.x >> 7;
+    int op_index = 0;
+    const uint32_t row_off = (uint32_t)(prow >> 3) * 2048u + (uint32_t)(prow & 7) * 16u;
     uint32_t a_seq = 0, b_seq = 0;  // A halves / B tiles scheduled so far (slot = seq % slots, phase = (seq / slots) & 1)
-    auto op_a = [&](const HamItem& it, int h) {
-      Op o;
-      const int row = h * 128 + t;
-      o.src = row < it.nq_valid ? reinterpret_cast<const uint4*>(it.a) + 2 * (size_t)row : nullptr;
-      const uint32_t slot = a_seq % kXASlots;
-      o.dst = sA + slot * kTileA + row_off;
-      o.full = bar(kXAFull + slot);
-      o.empty = bar(kXAEmpty + slot);
-      o.parity = ((a_seq / kXASlots) & 1u) ^ 1u;
-      a_seq++;
-      return o;
+    uint32_t p_dst = 0, p_full = 0, p_empty = 0, p_parity = 0;  // the operation in flight
+    uint4 p_lo = make_uint4(0, 0, 0, 0), p_hi = p_lo;
+    bool pending = false;
+    auto finish = [&]() {
+      if (!pending) return;
+      XWAIT(pf_a, p_empty, p_parity, 1, (int)a_seq, (int)b_seq);
+#ifdef RB200_PROFILE_TC
+      const long long w0_ = clock64();
+#endif
+      expand_half_row(p_dst, p_lo);
+      expand_half_row(p_dst + 1024u, p_hi);
+#ifdef RB200_PROFILE_TC
+      pf_work += clock64() - w0_;
+#endif
+#ifndef RB200_X_NO_PROXY_FENCE  // timing experiment only: without the fence the MMA may read stale operand bytes
+      fence_proxy_async_smem();
+#endif
+      mbar_arrive(p_full);
+      pending = false;
     };
-    auto op_b = [&](const HamItem& it, int nb) {
-      Op o;
-      const int row = nb * 128 + t;
-      o.src = row < it.nsearch ? reinterpret_cast<const uint4*>(it.b) + 2 * (size_t)row : nullptr;
+    auto produce = [&](const int8_t* rows, int row, int n_rows, uint32_t tile, uint32_t full, uint32_t empty, uint32_t seq, uint32_t slots) {
+      if ((op_index++ & 1) != group) return;  // the other group's tile
+      uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
+      if (row < n_rows) {  // rows that do not exist: zeros
+        lo = __ldg(reinterpret_cast<const uint4*>(rows) + 2 * (size_t)row);
+        hi = __ldg(reinterpret_cast<const uint4*>(rows) + 2 * (size_t)row + 1);
+      }
+      finish();
+      p_lo = lo;
+      p_hi = hi;
+      p_dst = tile + row_off;
+      p_full = full;
+      p_empty = empty;
+      p_parity = ((seq / slots) & 1u) ^ 1u;
+      pending = true;
+    };
+    auto produce_a = [&](const HamItem& it, int h) {
+      const uint32_t slot = a_seq % kXASlots;
+      produce(it.a, h * 128 + prow, it.nq_valid, sA + slot * kTileA, bar(kXAFull + slot), bar(kXAEmpty + slot), a_seq, kXASlots);
+      a_seq++;
+    };
+    auto produce_b = [&](const HamItem& it, int nb) {
       const uint32_t slot = b_seq % kXBSlots;
-      o.dst = sB + slot * kTileA + row_off;
-      o.full = bar(kXBFull + slot);
-      o.empty = bar(kXBEmpty + slot);
-      o.parity = ((b_seq / kXBSlots) & 1u) ^ 1u;
+      produce(it.b, nb * 128 + prow, it.nsearch, sB + slot * kTileA, bar(kXBFull + slot), bar(kXBEmpty + slot), b_seq, kXBSlots);
       b_seq++;
-      return o;
     };
     if (my_items > 0) {
-      HamItem cur = items[blockIdx.x], nxt = cur;
-      int k = 0, nb = 1, st = 0;
-      bool more = my_items > 1;
-      if (more) nxt = items[blockIdx.x + gridDim.x];
-      // the schedule above as a resumable state machine: returns false when everything has been produced
-      auto next_op = [&](Op& o) -> bool {
-        for (;;) {
-          switch (st) {
-            case 0: o = op_a(cur, 0); st = 1; return true;
-            case 1: st = 2; if (cur.n_btiles > 0) { o = op_b(cur, 0); return true; } break;
-            case 2: o = op_a(cur, 1); st = 3; nb = 1; return true;
-            case 3:
-              if (nb < cur.n_btiles) {
-                o = op_b(cur, nb);
-                if (nb == 1 && more) st = 4;
-                nb++;
-                return true;
-              }
-              st = 5;
-              break;
-            case 4: o = op_a(nxt, 0); st = 3; return true;
-            case 5:
-              if (!more) return false;
-              st = 6;
-              if (cur.n_btiles <= 1) { o = op_a(nxt, 0); return true; }
-              break;
-            case 6: st = 7; if (nxt.n_btiles > 0) { o = op_b(nxt, 0); return true; } break;
-            default:  // 7
-              o = op_a(nxt, 1);
-              cur = nxt;
-              k++;
-              more = k + 1 < my_items;
-              if (more) nxt = items[blockIdx.x + (size_t)(k + 1) * gridDim.x];
-              nb = 1;
-              st = 3;
-              return true;
-          }
+      HamItem cur = items[blockIdx.x];
+      produce_a(cur, 0);
+      if (cur.n_btiles > 0) produce_b(cur, 0);
+      produce_a(cur, 1);
+      for (int k = 0; k < my_items; k++) {
+        const bool more = k + 1 < my_items;
+        HamItem nxt = cur;
+        if (more) nxt = items[blockIdx.x + (size_t)(k + 1) * gridDim.x];
+        for (int nb = 1; nb < cur.n_btiles; nb++) {
+          produce_b(cur, nb);
+          if (nb == 1 && more) produce_a(nxt, 0);
         }
-      };
-      auto next_own = [&](Op& o) -> bool {
-        for (;;) {
-          if (!next_op(o)) return false;
-          if ((op_index++ % kXProducerGroups) == group) return true;
+        if (more) {
+          if (cur.n_btiles <= 1) produce_a(nxt, 0);
+          if (nxt.n_btiles > 0) produce_b(nxt, 0);
+          produce_a(nxt, 1);
         }
-      };
-      Op op;
-      bool have = next_own(op);
-      uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
-      if (have && op.src) { lo = __ldg(op.src); hi = __ldg(op.src + 1); }
-      while (have) {
-        Op nx;
-        const bool have_nx = next_own(nx);
-        uint4 nlo = make_uint4(0, 0, 0, 0), nhi = nlo;
-        if (have_nx && nx.src) { nlo = __ldg(nx.src); nhi = __ldg(nx.src + 1); }  // in flight while this row is expanded
-        RB200_WAIT(op.empty, op.parity, 1, (int)a_seq, (int)b_seq);
-        expand_row(op.dst, lo, hi);
-        fence_proxy_async_smem();
-        mbar_arrive(op.full);
-        op = nx; lo = nlo; hi = nhi; have = have_nx;
+        cur = nxt;
       }
+      finish();
     }
-  } else if (warp == kXProducerWarps) {
-    // ---------------- MMA issuer
-    uint32_t a_seq = 0, b_seq = 0, acc = 0, pacc = 0;
+  } else if (warp < kXProducerWarps + kXIssuerWarps) {
+    // ---------------- MMA issuers: warp 8 owns query half 0, warp 9 half 1 (one elected lane each).
+    // Measured (tools/microbench/tc_ts_probe.cu, "issue_queue"): the issuing thread can run only ~2 MMAs (128 cycles) ahead of
+    // the tensor pipe, so every cycle beyond that which it spends between two bursts -- barrier checks, descriptor set-up,
+    // ~50 single-lane instructions per burst -- is a cycle the pipe idles (one issuer: tensor pipe 65 % busy).  With one issuer
+    // per accumulator half, one of them is setting up its next burst while the other one's nine MMAs execute.
+    const int h = warp - kXProducerWarps;
+    uint32_t a_seq = (uint32_t)h, b_seq = 0, acc = 0, pacc = 0;
     const uint64_t dia = make_desc_lbo_sbo(sIdxA, 128, 256), dib = make_desc_lbo_sbo(sIdxB, 128, 256);
     for (int k = 0; k < my_items; k++) {
       const int n_btiles = items[blockIdx.x + (size_t)k * gridDim.x].n_btiles;
-      const uint32_t slot0 = a_seq % kXASlots, ph0 = (a_seq / kXASlots) & 1u;
-      const uint32_t slot1 = (a_seq + 1) % kXASlots, ph1 = ((a_seq + 1) / kXASlots) & 1u;
+      const uint32_t slot = a_seq % kXASlots, ph = (a_seq / kXASlots) & 1u;
       a_seq += 2;
+      const uint64_t da = make_desc(sA + slot * kTileA);
       for (int nb = 0; nb < n_btiles; nb++) {
         const uint32_t sb = b_seq % kXBSlots, pb = (b_seq / kXBSlots) & 1u;
         b_seq++;
-        RB200_WAIT(bar(kXBFull + sb), pb, 2, k, nb);
-        if (nb == 0) RB200_WAIT(bar(kXAFull + slot0), ph0, 3, k, nb);
-        RB200_WAIT(bar(kXAccEmpty + acc), pacc ^ 1u, 4, k, nb);
-        tc_fence_after();
         const uint64_t db = make_desc(sB + sb * kTileA);
+        const uint32_t d = tmem_base + acc * 256 + h * 128;
+        XWAIT(pf_b, bar(kXBFull + sb), pb, 2, k, nb);
+        if (nb == 0) XWAIT(pf_a, bar(kXAFull + slot), ph, 3, k, nb);
+        XWAIT(pf_acc, bar(kXAccEmpty + 2 * acc + h), pacc ^ 1u, 4, k, nb);
+        tc_fence_after();
         if (elect_one()) {
-          const uint64_t da = make_desc(sA + slot0 * kTileA);
-          const uint32_t d = tmem_base + acc * 256;
 #pragma unroll
           for (int ks = 0; ks < 8; ks++) tc_mma_i8(d, da + (uint64_t)((ks * 256) >> 4), db + (uint64_t)((ks * 256) >> 4), kIdescI8_N128, ks > 0 ? 1u : 0u);
           tc_mma_i8(d, dia, dib, kIdescI8_N128, 1u);
-        }
-        __syncwarp();
-        if (nb == 0) {
-          RB200_WAIT(bar(kXAFull + slot1), ph1, 5, k, nb);
-          tc_fence_after();
-        }
-        if (elect_one()) {
-          const uint64_t da = make_desc(sA + slot1 * kTileA);
-          const uint32_t d = tmem_base + acc * 256 + 128;
-#pragma unroll
-          for (int ks = 0; ks < 8; ks++) tc_mma_i8(d, da + (uint64_t)((ks * 256) >> 4), db + (uint64_t)((ks * 256) >> 4), kIdescI8_N128, ks > 0 ? 1u : 0u);
-          tc_mma_i8(d, dia, dib, kIdescI8_N128, 1u);
-          tc_commit(bar(kXBEmpty + sb));
-          tc_commit(bar(kXAccFull + acc));
+          tc_commit(bar(kXBEmpty + sb));            // the tile is free once BOTH issuers' MMAs on it have retired (count 2)
+          tc_commit(bar(kXAccFull + 2 * acc + h));
         }
         __syncwarp();
         if (++acc == 2) { acc = 0; pacc ^= 1u; }
       }
       if (n_btiles == 0) {
-        // nothing to multiply (empty train set): the halves are still produced and must be consumed before they are released --
+        // nothing to multiply (empty train set): the half is still produced and must be consumed before it is released --
         // releasing a slot the producer has not filled yet flips the barrier phase under its feet (deadlock)
-        RB200_WAIT(bar(kXAFull + slot0), ph0, 7, k, 0);
-        RB200_WAIT(bar(kXAFull + slot1), ph1, 8, k, 0);
+        XWAIT(pf_a, bar(kXAFull + slot), ph, 7, k, 0);
       }
-      if (elect_one()) {  // both query halves of the item are free once every MMA issued so far has retired
-        tc_commit(bar(kXAEmpty + slot0));
-        tc_commit(bar(kXAEmpty + slot1));
-      }
+      if (elect_one()) tc_commit(bar(kXAEmpty + slot));  // free once every MMA this thread has issued so far has retired
       __syncwarp();
     }
   } else {
     // ---------------- epilogue
-    const int e = warp - (kXProducerWarps + 1);
+    const int e = warp - (kXProducerWarps + kXIssuerWarps);
     const int h = e >> 2;      // query half drained by this warp
     const int wq = warp & 3;   // TMEM lane quadrant this warp may access
     const int row = h * 128 + wq * 32 + lane;
@@ -731,16 +717,16 @@ __global__ void __launch_bounds__(kXThreads, 1) tc_hamming_expand_kernel(const H
       const HamItem item = items[blockIdx.x + (size_t)k * gridDim.x];
       int best = kNoBest;
       for (int nb = 0; nb < item.n_btiles; nb++) {
-        RB200_WAIT(bar(kXAccFull + acc), pacc, 6, k, nb);
+        XWAIT(pf_acc, bar(kXAccFull + 2 * acc + h), pacc, 6, k, nb);
         tc_fence_after();
+#ifdef RB200_PROFILE_TC
+        const long long w0_ = clock64();
+#endif
         const uint32_t t0 = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * 256 + h * 128;
         const int nvalid = item.nsearch - nb * 128;  // train rows of this tile that exist (>= 128: all)
         int m = kNoBest;
-#pragma unroll 1
-        for (int c = 0; c < 4; c++) {
-          uint32_t v[32];
-          tc_ld32(t0 + c * 32, v);
-          tc_wait_ld();
+        // maximum of one 32-column chunk (columns at or beyond nvalid do not exist)
+        auto chunk_max = [&](const uint32_t (&v)[32], int c) {
           if (c * 32 + 32 <= nvalid) {
             int m0 = __vimax3_s32((int)v[0], (int)v[1], (int)v[2]), m1 = __vimax3_s32((int)v[3], (int)v[4], (int)v[5]);
 #pragma unroll
@@ -754,10 +740,32 @@ __global__ void __launch_bounds__(kXThreads, 1) tc_hamming_expand_kernel(const H
             for (int j = 0; j < 32; j++)
               if (c * 32 + j < nvalid) m = max(m, (int)v[j]);
           }
+        };
+#if RB200_X_EPI_PAIR
+#pragma unroll 1
+        for (int c = 0; c < 4; c += 2) {  // two chunk loads in flight per wait: two TMEM round trips per tile instead of four
+          uint32_t v[32], u[32];
+          tc_ld32(t0 + c * 32, v);
+          tc_ld32(t0 + c * 32 + 32, u);
+          tc_wait_ld();
+          chunk_max(v, c);
+          chunk_max(u, c + 1);
         }
+#else
+#pragma unroll 1
+        for (int c = 0; c < 4; c++) {
+          uint32_t v[32];
+          tc_ld32(t0 + c * 32, v);
+          tc_wait_ld();
+          chunk_max(v, c);
+        }
+#endif
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar(kXAccEmpty + acc));
+        if (lane == 0) mbar_arrive(bar(kXAccEmpty + 2 * acc + h));
+#ifdef RB200_PROFILE_TC
+        pf_work += clock64() - w0_;
+#endif
         if (++acc == 2) { acc = 0; pacc ^= 1u; }
         if (m != kNoBest) best = max(best, m + (3968 - 128 * nb));  // 4096 dot + (4095 - col)
       }
@@ -772,6 +780,26 @@ __global__ void __launch_bounds__(kXThreads, 1) tc_hamming_expand_kernel(const H
       }
     }
   }
+#ifdef RB200_PROFILE_TC
+  if (lane == 0) {
+    const int role = warp < kXProducerWarps ? 0 : (warp < kXProducerWarps + kXIssuerWarps ? 1 : 2);
+    atomicAdd(&g_tc_prof[role][0], (unsigned long long)pf_a);
+    atomicAdd(&g_tc_prof[role][1], (unsigned long long)pf_b);
+    atomicAdd(&g_tc_prof[role][2], (unsigned long long)pf_acc);
+    atomicAdd(&g_tc_prof[role][3], (unsigned long long)(clock64() - pf_t0));
+    atomicAdd(&g_tc_prof[role][4], 1ull);
+    atomicAdd(&g_tc_prof[role][5], (unsigned long long)pf_work);
+    // wall clock (ns): [0][6] = ~(earliest CTA entry), [0][7] = latest warp exit, [1][6] = longest entry -> pipeline start,
+    // [2][6] = ~(earliest pipeline start)
+    unsigned long long gt_now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_now));
+    atomicMax(&g_tc_prof[0][6], ~gt_entry);
+    atomicMax(&g_tc_prof[0][7], gt_now);
+    atomicMax(&g_tc_prof[1][6], pf_gt_start - gt_entry);
+    atomicMax(&g_tc_prof[2][6], ~pf_gt_start);
+  }
+#endif
+#undef XWAIT
   tc_fence_before();
   __syncthreads();
   if (warp == kXProducerWarps) {
