@@ -147,11 +147,15 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE tc_match256_kernel<0> launch on this workload, from the committed
-# `ncu --set full` capture: 134.29 MB + 4.98 MB.  7.6 x the algorithmic 18.4 MB because the kernel reads the +-1 int8 operand
-# expansion (256 B per 256-bit descriptor) the nodes keep resident; the descriptors themselves are read once, by expand_i8.
-NCU_DRAM_BYTES_PER_LAUNCH = 139277312
-NCU_TRAFFIC_SOURCE = "profiles/r1_v8_tc_match256_ncu_full.txt (ncu --set full, 1 launch, C2 batch)"
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE tc_hamming_expand_kernel launch on this workload, from the committed
+# `ncu --set full` capture: 16.46 MB read + 0 written (the 2 MB of results stay in L2 for the selection kernel) against 18.4 MB
+# algorithmic -- the kernel expands the 32-byte descriptors to MMA operands in shared memory itself.  (Round 1 read a resident
+# +-1 int8 expansion instead: 139.3 MB per launch, 7.6 x the algorithmic bytes.)
+NCU_DRAM_BYTES_PER_LAUNCH = 16464640
+NCU_TRAFFIC_SOURCE = "profiles/r2_v10_hamming_expand_ncu_full.txt (ncu --set full, 1 launch, C2 batch)"
+# tcgen05.mma.kind::i8 M128 N128 K32 issued back to back on all 148 SMs, no epilogue (tools/microbench/tc_peaks.cu on this pool's
+# B200s, profiles/r2_v7_tc_peaks.json): 64.0 cycles per MMA = 4514.7 TOP/s at the 1.86 GHz the SMs hold under that load
+INT8_MMA_MEASURED_TOPS = 4514.7
 
 
 def tensor_roofline(kernel_ms: float) -> dict:
@@ -167,7 +171,10 @@ def tensor_roofline(kernel_ms: float) -> dict:
             src = "2 x MEASURED_PEAKS.json bf16_tflops (int8 dense = 2 x bf16 dense on sm_100)"
     except Exception:
         pass
-    return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TOP/s (int8)", "frac": achieved / peak, "peak_source": src}
+    return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TOP/s (int8)", "frac": achieved / peak, "peak_source": src,
+            "ops_counted": "algorithmic 2 * Nq * Nt * 256 per pair (the ninth, column-index k-step and the padding to 128-row tiles are overhead)",
+            "int8_mma_issue_peak": INT8_MMA_MEASURED_TOPS, "frac_of_int8_mma_issue_peak": achieved / INT8_MMA_MEASURED_TOPS,
+            "int8_mma_issue_peak_source": "tools/microbench/tc_peaks.cu (profiles/r2_v7_tc_peaks.json): tcgen05.mma.kind::i8 alone, 64.0 cycles per M128 N128 K32"}
 
 
 def make_workload(rank: int):
@@ -251,7 +258,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 def fe_device(fe):
@@ -862,12 +869,21 @@ def run_ours(args, rank, local_rank, world):
                                    "single_thread_value": 32 / dt1}
             agree = int(((ores["id1"] >= 0) == (res_np["id1"] >= 0)).sum())
             out["config"]["oracle_agreement_valid_flags"] = f"{agree}/{PAIRS_PER_GPU}"
-        print(json.dumps(out), flush=True)
+        emit(out)
     if comm is not None:
         fe.comm_destroy(comm)
     fe.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+_JSON_OUT = None
+
+
+def emit(out: dict):
+    f = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    f.write(json.dumps(out) + "\n")
+    f.flush()
 
 
 def main():
@@ -885,6 +901,12 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # stdout carries the ONE JSON line and nothing else: libraries that write to file descriptor 1 on their own (NCCL prints its
+    # version banner there at the first communicator) are sent to stderr; the line is written to the saved descriptor
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args, rank, world)
     else:

@@ -16,6 +16,7 @@
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cfloat>
 #include <chrono>
 #include <cmath>
@@ -389,6 +390,284 @@ __global__ void __launch_bounds__(512, 1) pg_pcg_kernel(PcgArgs a) {
   }
 }
 
+// ---- the same iteration for graphs that fit the chip: everything a vertex owns stays ON the SM ------------------------------
+// Up to 80 vertices per CTA (16 warps x 5 groups of 6 lanes: lane = one of the 6 rows of one vertex).  A lane keeps its row of
+// x, r, d, q, s, b, M^-1 and H_vv + lambda I in REGISTERS for the whole solve; the CTA stages the off-diagonal 6x6 blocks of
+// its vertices' incident edges (already oriented for the owner: C or C', written once per linearisation by pg_orient_kernel,
+// contiguous per CTA because the CSR is vertex-major) and the neighbour indices in SHARED memory.  The only global traffic of
+// an iteration is the publication of s (48 B per vertex) and the gather of the neighbours' s; the SpMV of a row is a
+// sequential sum over its incidences in one lane -- no warp reduction, no atomics, fixed order.  Two grid barriers per
+// iteration as in pg_pcg_kernel, but a barrier that carries the dot product itself (pg_tree_barrier).
+// C5 (5000 V / 30 000 E, 7814 PCG iterations): 25.5 -> 10.9 us per iteration, 0.20 -> 0.085 s for the whole solve.  Where the
+// remaining time goes (clock64 profile, -DRB200_PG_PROFILE): the two barriers 2 x 3.4 us (three fences and two global
+// store -> poll hops each), gather + SpMV 2.4 us, block sums 0.9 us.
+// Incidences beyond the shared-memory capacity of a CTA (hub vertices) are read from the global copy.
+constexpr int kPgResGroups = 5, kPgResWarps = 16, kPgResSlots = kPgResGroups * kPgResWarps;
+
+__global__ void __launch_bounds__(128) pg_orient_kernel(int nv, const int* __restrict__ off, const int* __restrict__ inc,
+                                                        const int* __restrict__ oth, const double* __restrict__ blk,
+                                                        double* __restrict__ incblk) {
+  const int v = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (v >= nv) return;
+  for (int p = off[v]; p < off[v + 1]; p++) {
+    const int code = inc[p];
+    const bool self = oth[p] == v;  // self edge: no off-diagonal block
+    const double* C = blk + (size_t)(code >> 1) * kEdgeBlk + 72;
+    for (int e = lane; e < 36; e += 32) {
+      const int r = e / 6, c = e - 6 * r;
+      incblk[36 * (size_t)p + e] = self ? 0.0 : ((code & 1) == 0 ? C[6 * r + c] : C[6 * c + r]);
+    }
+  }
+}
+
+// Grid barrier that CARRIES the dot product (resident solver), two levels so that no cache line is polled by more than one
+// warp per CTA and no CTA reads more than one line per level:
+//   level 1: a CTA publishes its partial sum in slot[bid]; the first CTA of every group of kPgGroup consecutive CTAs polls
+//            the group's slots (one 128-byte line), adds them in slot order and publishes the group sum in gslot[group];
+//   level 2: every CTA polls the <= 32 group sums (one or two lines) and adds them in order.
+// A published double carries the parity of the barrier's use count in its lowest mantissa bit (st.relaxed after a
+// __threadfence; polled with relaxed loads, one __threadfence after the last poll): value and flag travel in one word, one
+// global round trip per level.  The flag bit is part of the value every reader sees, so the sum is identical in every CTA and
+// from run to run.  Two slot sets used alternately (a CTA can only reach the next use of a set after every CTA has consumed
+// the previous one: the barrier in between needs all of them).  Measured: 3.4 us per barrier; cooperative-groups grid.sync()
+// followed by every warp loading the 148 partials cost the same iteration 4.5 us, a one-level version in which every CTA
+// polls all 148 slots 5 us (148 warps hammering the same ten cache lines).  Needs all CTAs co-resident (cooperative launch);
+// the host presets all slots to all-ones (parity 1; the first use expects 0).
+constexpr int kPgGroup = 12;  // 12 x 8 B = 96 B: the slots of a group share one 128-byte line (slots are 128-byte aligned per group)
+__device__ __forceinline__ unsigned long long pg_flagged(double v, unsigned parity) {
+  return ((unsigned long long)__double_as_longlong(v) & ~1ull) | (unsigned long long)parity;
+}
+__device__ __forceinline__ void pg_st_relaxed(double* p, unsigned long long u) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(u) : "memory");
+}
+__device__ __forceinline__ unsigned long long pg_ld_relaxed(const double* p) {
+  unsigned long long u;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(u) : "l"(p) : "memory");
+  return u;
+}
+// slots: [group][16] doubles (12 used), gslots: [32] doubles, both per set.  Returns the grid total in every thread.
+// fence.acq_rel is all the barrier needs (release before a publication, acquire after the last poll); __threadfence() is the
+// sequentially consistent fence
+__device__ __forceinline__ void pg_fence() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ double pg_tree_barrier(double block_sum, double* slots, double* gslots, unsigned parity, double* sm) {
+  const int bid = blockIdx.x, grp = bid / kPgGroup, idx = bid - grp * kPgGroup;
+  const int n_groups = ((int)gridDim.x + kPgGroup - 1) / kPgGroup;
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    if (lane == 0) {
+      pg_fence();  // the CTA's s rows (ordered before this thread by the __syncthreads of block_partial) become visible first
+      pg_st_relaxed(slots + 16 * grp + idx, pg_flagged(block_sum, parity));
+    }
+    if (idx == 0) {  // group leader
+      const int members = min(kPgGroup, (int)gridDim.x - grp * kPgGroup);
+      unsigned long long u;
+      bool ok;
+      do {
+        u = lane < members ? pg_ld_relaxed(slots + 16 * grp + lane) : (unsigned long long)parity;
+        ok = __all_sync(0xffffffffu, (u & 1ull) == (unsigned long long)parity);
+      } while (!ok);
+      const double t = warp_sum_d(lane < members ? __longlong_as_double((long long)u) : 0.0);
+      if (lane == 0) {
+        pg_fence();
+        pg_st_relaxed(gslots + grp, pg_flagged(t, parity));
+      }
+    }
+    unsigned long long u;
+    bool ok;
+    do {
+      u = lane < n_groups ? pg_ld_relaxed(gslots + lane) : (unsigned long long)parity;
+      ok = __all_sync(0xffffffffu, (u & 1ull) == (unsigned long long)parity);
+    } while (!ok);
+    const double t = warp_sum_d(lane < n_groups ? __longlong_as_double((long long)u) : 0.0);
+    pg_fence();
+    if (lane == 0) sm[0] = t;
+  }
+  __syncthreads();
+  const double r = sm[0];
+  return r;  // (the next block_partial starts with a __syncthreads before it reuses sm)
+}
+constexpr int kPgBarrierDoubles = 2 * (16 * 32 + 32);  // two sets of (<= 32 groups x 16 slots) + 32 group sums: grids up to 384 CTAs
+
+__global__ void __launch_bounds__(kPgResWarps * 32, 1) pg_pcg_resident_kernel(PcgArgs a, const double* __restrict__ incblk, int vpc, int cap) {
+  extern __shared__ __align__(16) unsigned char pg_dsm[];
+  double* sm = reinterpret_cast<double*>(pg_dsm);  // 16 doubles of block_partial
+  double* blk_s = sm + 16;                         // cap x 36
+  double* sg_s = blk_s + 36 * (size_t)cap;         // cap x 6: the neighbours' s rows of the current iteration
+  int* src_s = reinterpret_cast<int*>(sg_s + 6 * (size_t)cap);  // cap x 6: where element i of sg_s comes from (index into s)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane / 6, row = lane - 6 * g;
+  const int v0 = blockIdx.x * vpc, v1 = min(a.nv, v0 + vpc);
+  const int p0 = v0 < a.nv ? a.off[v0] : 0, p1 = v0 < a.nv ? a.off[v1] : 0;
+  const int n_s = min(p1 - p0, cap);
+  for (int i = threadIdx.x; i < 36 * n_s; i += blockDim.x) blk_s[i] = incblk[36 * (size_t)p0 + i];
+  for (int i = threadIdx.x; i < 6 * n_s; i += blockDim.x) {
+    const int li = i / 6;
+    src_s[i] = 6 * a.oth[p0 + li] + (i - 6 * li);
+  }
+  const int slot = warp * kPgResGroups + g;
+  const int v = v0 + slot;
+  const bool act = g < kPgResGroups && slot < vpc && v < v1;
+  const int gbase = 6 * g;
+  double* slots_a = a.part;                 // set A (r.s and the final scale), set B (d.q)
+  double* gslots_a = a.part + 16 * 32;
+  double* slots_b = a.part + 16 * 32 + 32;
+  double* gslots_b = slots_b + 16 * 32;
+
+  double Mrow[6], Hrow[6], xb = 0, rr = 0, dd = 0, qq = 0, sv = 0, bb = 0;
+  bool fx = true;
+  int pb = 0, pe = 0;
+#pragma unroll
+  for (int c = 0; c < 6; c++) { Mrow[c] = 0; Hrow[c] = 0; }
+  if (act) {
+    fx = a.fixed[v] != 0;
+#pragma unroll
+    for (int c = 0; c < 6; c++) {
+      Mrow[c] = a.Minv[36 * (size_t)v + 6 * row + c];
+      Hrow[c] = a.Hd[36 * (size_t)v + 6 * row + c] + (c == row ? a.lambda : 0.0);
+    }
+    bb = a.b[6 * (size_t)v + row];
+    pb = a.off[v];
+    pe = a.off[v + 1];
+  }
+  __syncthreads();
+  // x = 0, r = b, s = M^-1 r, dn = r.s
+  rr = bb;
+  {
+    double t = 0;
+#pragma unroll
+    for (int c = 0; c < 6; c++) t += Mrow[c] * __shfl_sync(0xffffffffu, rr, (gbase + c) & 31);
+    sv = t;
+  }
+  if (act) a.s[6 * (size_t)v + row] = sv;
+  unsigned ea = 0, eb = 0;  // use counts of the two slot sets
+  double bsum;
+  {
+    bsum = block_partial(act ? rr * sv : 0.0, sm);
+  }
+  double dn = pg_tree_barrier(bsum, slots_a, gslots_a, ea & 1u, sm);
+  ea++;
+  double beta = 0.0;
+  int it = 0;
+  bool breakdown = false;
+#ifdef RB200_PG_PROFILE
+  long long pf[6] = {0, 0, 0, 0, 0, 0}, pc0 = clock64(), pc1;
+#define PG_LAP(k) { pc1 = clock64(); pf[k] += pc1 - pc0; pc0 = pc1; }
+#else
+#define PG_LAP(k)
+#endif
+  for (;;) {
+    // ---- phase 2: q = A s + beta q ; d = s + beta d ; partial d.q
+    // the s rows of all neighbours of this CTA's vertices, fetched by the whole CTA in ONE round trip (one double per thread
+    // and step, all independent) into shared memory; a lane then sums its row over its incidences out of shared memory only --
+    // the time of the phase no longer depends on the largest vertex degree in the grid
+    for (int base = 0; base < 6 * n_s; base += 8 * (int)blockDim.x) {
+      double tmp[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) {  // eight independent loads in flight per thread
+        const int i = base + u * (int)blockDim.x + (int)threadIdx.x;
+        tmp[u] = i < 6 * n_s ? __ldcg(a.s + src_s[i]) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int i = base + u * (int)blockDim.x + (int)threadIdx.x;
+        if (i < 6 * n_s) sg_s[i] = tmp[u];
+      }
+    }
+    __syncthreads();
+    double acc = 0;
+    if (act && !fx) {
+      // six independent accumulators (one per column) and two incidences per step: a single running sum would serialise
+      // degree x 6 dependent FP64 FMAs (their latency, not their number, was the cost of the phase)
+      double ac0[6] = {0, 0, 0, 0, 0, 0}, ac1[6] = {0, 0, 0, 0, 0, 0};
+      const int pe_s = min(pe, p0 + n_s);
+      int p = pb;
+      for (; p + 1 < pe_s; p += 2) {
+        const int li = p - p0;
+        const double* C0 = blk_s + 36 * li + 6 * row;
+        const double* o0 = sg_s + 6 * li;
+#pragma unroll
+        for (int c = 0; c < 6; c++) {
+          ac0[c] += C0[c] * o0[c];
+          ac1[c] += C0[36 + c] * o0[6 + c];
+        }
+      }
+      if (p < pe_s) {
+        const int li = p - p0;
+        const double* C0 = blk_s + 36 * li + 6 * row;
+        const double* o0 = sg_s + 6 * li;
+#pragma unroll
+        for (int c = 0; c < 6; c++) ac0[c] += C0[c] * o0[c];
+        p++;
+      }
+      for (; p < pe; p++) {  // beyond the shared-memory capacity of the CTA (hub vertices): straight from global memory
+        const double* C = incblk + 36 * (size_t)p + 6 * row;
+        const double* o = a.s + 6 * (size_t)a.oth[p];
+#pragma unroll
+        for (int c = 0; c < 6; c++) ac1[c] += C[c] * __ldcg(o + c);
+      }
+      acc = ((ac0[0] + ac1[0]) + (ac0[1] + ac1[1])) + ((ac0[2] + ac1[2]) + (ac0[3] + ac1[3])) + ((ac0[4] + ac1[4]) + (ac0[5] + ac1[5]));
+    }
+    double qn = 0, dnw = 0;
+    {
+      double t = 0;
+#pragma unroll
+      for (int c = 0; c < 6; c++) t += Hrow[c] * __shfl_sync(0xffffffffu, sv, (gbase + c) & 31);
+      if (act && !fx) {
+        qn = t + acc + beta * qq;
+        dnw = sv + beta * dd;
+      }
+    }
+    qq = qn;
+    dd = dnw;
+    PG_LAP(0)
+    {
+      bsum = block_partial(act ? dnw * qn : 0.0, sm);
+      PG_LAP(1)
+    }
+    const double dq = pg_tree_barrier(bsum, slots_b, gslots_b, eb & 1u, sm);
+    PG_LAP(3)
+    eb++;
+    if (it >= a.maxit || dn <= a.tol) break;
+    if (!(dq > 0)) { breakdown = true; break; }
+    const double alpha = dn / dq;
+    // ---- phase 1: x += alpha d ; r -= alpha q ; s = M^-1 r ; partial r.s
+    xb += alpha * dd;
+    rr -= alpha * qq;
+    {
+      double t = 0;
+#pragma unroll
+      for (int c = 0; c < 6; c++) t += Mrow[c] * __shfl_sync(0xffffffffu, rr, (gbase + c) & 31);
+      sv = t;
+    }
+    if (act) a.s[6 * (size_t)v + row] = sv;
+    PG_LAP(4)
+    {
+      bsum = block_partial(act ? rr * sv : 0.0, sm);
+      PG_LAP(1)
+    }
+    const double dn_new = pg_tree_barrier(bsum, slots_a, gslots_a, ea & 1u, sm);
+    PG_LAP(5)
+    ea++;
+    beta = dn_new / dn;
+    dn = dn_new;
+    it++;
+  }
+  if (act) a.x[6 * (size_t)v + row] = xb;
+  {
+    bsum = block_partial(act ? xb * (a.lambda * xb + bb) : 0.0, sm);
+  }
+  const double scale = pg_tree_barrier(bsum, slots_a, gslots_a, ea & 1u, sm);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    a.result[0] = (double)it;
+    a.result[1] = dn;
+    a.result[2] = scale;
+    a.result[3] = breakdown ? 1.0 : 0.0;
+#ifdef RB200_PG_PROFILE
+    for (int k = 0; k < 6; k++) a.result[4 + k] = (double)pf[k];  // cycles of thread 0: spmv, block sum, fence+store, wait d.q, phase 1, wait r.s
+#endif
+  }
+}
+
 __global__ void __launch_bounds__(128) pg_update_kernel(int nv, const double* __restrict__ xin, const double* __restrict__ dlt,
                                                         const uint8_t* __restrict__ fixed, double* __restrict__ xout) {
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
@@ -468,10 +747,10 @@ cudaError_t pg_launch_chi2(int ne, const double* x, const int32_t* ij, const dou
 // Host driver
 
 struct PgDevice {
-  DevBuf x, xtrial, meas, info, ij, fixed, off, inc, oth, blk, Hd, b, Minv, dx, r, sv, d, q, part, result, chipart, maxpart, per_edge;
+  DevBuf x, xtrial, meas, info, ij, fixed, off, inc, oth, blk, Hd, b, Minv, dx, r, sv, d, q, part, result, chipart, maxpart, per_edge, incblk;
   ~PgDevice() {
     DevBuf* all[] = {&x, &xtrial, &meas, &info, &ij, &fixed, &off, &inc, &oth, &blk, &Hd, &b, &Minv, &dx, &r, &sv, &d, &q,
-                     &part, &result, &chipart, &maxpart, &per_edge};
+                     &part, &result, &chipart, &maxpart, &per_edge, &incblk};
     for (DevBuf* bb : all) bb->release();
   }
 };
@@ -502,6 +781,8 @@ struct PgCtx {
   int cg_iters = 0;
   double pcg_residual = -1.0;  // LinearSolverPCG::_residual
   double pcg_seconds = 0.0;    // wall time inside the PCG launches (RB200_PG_TIMING=1 prints the split)
+  // resident solver (pg_pcg_resident_kernel): vertices per CTA, shared-memory capacity in incidences, dynamic bytes; vpc == 0: off
+  int res_vpc = 0, res_cap = 0, res_smem = 0;
 };
 
 static int pg_errors(PgCtx& c, const double* dx_poses, double* robust, double* plain, double* per_edge) {
@@ -541,6 +822,13 @@ static int pg_build(PgCtx& c, double* maxdiag) {
                                            (double*)c.dev.Hd.ptr, (double*)c.dev.b.ptr, (double*)c.dev.maxpart.ptr);
   PG_CUDA(cudaGetLastError());
   c.launches++;
+  if (c.res_vpc > 0 && c.ne > 0) {
+    pg_orient_kernel<<<(c.nv + 3) / 4, 128, 0, c.st>>>(c.nv, (const int*)c.dev.off.ptr, (const int*)c.dev.inc.ptr,
+                                                       (const int*)c.dev.oth.ptr, (const double*)c.dev.blk.ptr,
+                                                       (double*)c.dev.incblk.ptr);
+    PG_CUDA(cudaGetLastError());
+    c.launches++;
+  }
   if (maxdiag) {
     std::vector<double> part(nb);
     PG_CUDA(cudaMemcpyAsync(part.data(), c.dev.maxpart.ptr, sizeof(double) * nb, cudaMemcpyDeviceToHost, c.st));
@@ -580,11 +868,24 @@ static int pg_pcg(PgCtx& c, double lambda, double* scale, bool* ok) {
   pg_precond_kernel<<<(c.nv + 127) / 128, 128, 0, c.st>>>(c.nv, a.Hd, a.fixed, lambda, a.Minv);
   PG_CUDA(cudaGetLastError());
   c.launches++;
-  PG_CUDA(cudaLaunchCooperativeKernel((void*)pg_pcg_kernel, dim3(c.pcg_grid), dim3(512), args, 0, c.st));
+  if (c.res_vpc > 0) {
+    PG_CUDA(cudaMemsetAsync(c.dev.part.ptr, 0xFF, 8 * (size_t)kPgBarrierDoubles, c.st));  // barrier slots: parity 1
+    const double* incblk = (const double*)c.dev.incblk.ptr;
+    void* rargs[] = {&a, &incblk, &c.res_vpc, &c.res_cap};
+    PG_CUDA(cudaLaunchCooperativeKernel((void*)pg_pcg_resident_kernel, dim3(c.pcg_grid), dim3(kPgResWarps * 32), rargs,
+                                        (size_t)c.res_smem, c.st));
+  } else {
+    PG_CUDA(cudaLaunchCooperativeKernel((void*)pg_pcg_kernel, dim3(c.pcg_grid), dim3(512), args, 0, c.st));
+  }
   c.launches++;
-  double res[4];
+  double res[10];
   PG_CUDA(cudaMemcpyAsync(res, c.dev.result.ptr, sizeof(res), cudaMemcpyDeviceToHost, c.st));
   PG_CUDA(cudaStreamSynchronize(c.st));
+#ifdef RB200_PG_PROFILE
+  if (c.res_vpc > 0 && res[0] > 0)
+    fprintf(stderr, "[pcg profile] %d iterations, cycles per iteration: spmv %.0f, block sums %.0f, fence+store %.0f, wait d.q %.0f, phase 1 %.0f, wait r.s %.0f\n",
+            (int)res[0], res[4] / res[0], res[5] / res[0], res[6] / res[0], res[7] / res[0], res[8] / res[0], res[9] / res[0]);
+#endif
   c.pcg_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   c.cg_iters += (int)res[0];
   c.pcg_residual = 0.5 * res[1];
@@ -689,7 +990,7 @@ int posegraph_optimize(int nv, double* poses, const uint8_t* fixed, int ne, cons
       (rc = d.off.ensure(4 * (nv_ + 1))) || (rc = d.inc.ensure(8 * ne_)) || (rc = d.blk.ensure(8 * kEdgeBlk * ne_)) ||
       (rc = d.Hd.ensure(288 * nv_)) || (rc = d.b.ensure(48 * nv_)) || (rc = d.Minv.ensure(288 * nv_)) ||
       (rc = d.dx.ensure(48 * nv_)) || (rc = d.r.ensure(48 * nv_)) || (rc = d.d.ensure(48 * nv_)) ||
-      (rc = d.q.ensure(48 * nv_)) || (rc = d.sv.ensure(48 * nv_)) || (rc = d.oth.ensure(8 * ne_)) || (rc = d.result.ensure(64)) || (rc = d.chipart.ensure(16 * (size_t)chi_blocks)) ||
+      (rc = d.q.ensure(48 * nv_)) || (rc = d.sv.ensure(48 * nv_)) || (rc = d.oth.ensure(8 * ne_)) || (rc = d.result.ensure(128)) || (rc = d.chipart.ensure(16 * (size_t)chi_blocks)) ||
       (rc = d.maxpart.ensure(8 * (size_t)max_blocks)) || (rc = d.per_edge.ensure(8 * ne_)))
     return rc;
   // cooperative grid: all co-resident blocks of the PCG kernel
@@ -700,7 +1001,34 @@ int posegraph_optimize(int nv, double* poses, const uint8_t* fixed, int ne, cons
     return RGBDSLAM_B200_ERR_CUDA;
   }
   c.pcg_grid = s.sm_count;  // one 512-thread CTA per SM: the barrier cost grows with the CTA count, the work per iteration is tiny
-  if ((rc = d.part.ensure(16 * (size_t)c.pcg_grid))) return rc;
+  if ((rc = d.part.ensure(16 * (size_t)c.pcg_grid + 8 * (size_t)kPgBarrierDoubles))) return rc;
+  {
+    // resident solver when every vertex gets its own 6-lane group (RB200_PG_RESIDENT=0 forces the general kernel)
+    const char* env = std::getenv("RB200_PG_RESIDENT");
+    const int vpc = (nv + c.pcg_grid - 1) / c.pcg_grid;
+    if (!(env && env[0] == '0') && nv > 0 && vpc <= kPgResSlots && c.pcg_grid <= 32 * kPgGroup) {
+      int max_inc = 0;
+      for (int v0 = 0; v0 < nv; v0 += vpc) {
+        const int v1 = v0 + vpc < nv ? v0 + vpc : nv;
+        max_inc = std::max(max_inc, off[v1] - off[v0]);
+      }
+      const int cap_max = (200 * 1024 - 128) / 360;  // 36 + 6 doubles + 6 source indices per incidence
+      c.res_cap = max_inc < cap_max ? max_inc : cap_max;
+      c.res_smem = 128 + 360 * c.res_cap;
+      c.res_smem = (c.res_smem + 15) & ~15;
+      static int attr_bytes = 0;
+      if (c.res_smem > attr_bytes) {
+        PG_CUDA(cudaFuncSetAttribute(pg_pcg_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 16));
+        attr_bytes = 200 * 1024 + 16;
+      }
+      int per_sm_res = 0;
+      PG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_res, pg_pcg_resident_kernel, kPgResWarps * 32, (size_t)c.res_smem));
+      if (per_sm_res >= 1) {
+        c.res_vpc = vpc;
+        if ((rc = d.incblk.ensure(288 * 2 * ne_))) return rc;
+      }
+    }
+  }
   cudaStream_t st = c.st;
   PG_CUDA(cudaMemcpyAsync(d.x.ptr, poses, 56 * (size_t)nv, cudaMemcpyHostToDevice, st));
   PG_CUDA(cudaMemcpyAsync(d.fixed.ptr, fixed, (size_t)nv, cudaMemcpyHostToDevice, st));

@@ -8,7 +8,7 @@ sys.path.insert(0, str(ROOT))
 from rgbdslam_v2_b200.build import CSRC, _nvcc, sources
 OUT = ROOT / "build_variants"; OBJ = OUT / "obj"; OBJ.mkdir(parents=True, exist_ok=True)
 FL = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-ccbin", shutil.which("g++")]
-TUNED = {"frontend_kernels.cu", "hamming_tc.cu"}
+TUNED = {"frontend_kernels.cu", "hamming_tc.cu", "posegraph.cu"}
 def cc(src, obj, extra=()):
     subprocess.run([_nvcc(), *FL, *extra, "-c", str(src), "-o", str(obj)], check=True)
 common = []
