@@ -564,6 +564,7 @@ def bench_sequence(fe, local_rank, rank, world, comm, n_frames=C4_FRAMES, with_o
                 fe.node_destroy(h)
             return traj, t, info, res
 
+        fe.posegraph_reserve(n_frames, 12 * n_frames)  # solver buffers sized for the session, like the pinned image buffers
         run(min(n_frames, 96 * world))  # warm-up (allocations, first launches)
         traj, t, info, _ = run(n_frames)
         tt = torch.tensor([t[k] for k in ("nodes", "match", "gather", "graph_host", "solve", "total")], dtype=torch.float64, device=dev)

@@ -358,6 +358,10 @@ int rgbdslam_b200_allgather_slot_edges(uint64_t comm, int slot, int n_per_rank, 
 int rgbdslam_b200_posegraph_optimize(int nv, double* poses, const uint8_t* fixed, int ne, const int32_t* ij,
                                      const double* meas, const double* info, double stop, double huber_delta,
                                      double* chi2, int* iters, int* cg_iters);
+/* Pre-size the solver's cached device buffers for graphs of up to nv vertices / ne edges (they only ever grow).  The reference
+ * lets g2o allocate as the graph grows (graph_manager.cpp:811-898); a caller that knows the size of its session takes the
+ * allocations out of its first large solve. */
+int rgbdslam_b200_posegraph_reserve(int nv, int ne);
 /* Host glue (no device work): what GraphManager::nodeComparisons + addEdgeToG2O (graph_manager.cpp:550-583, 636-655,
  * 811-898) do with the MatchingResults of a new node, for an OFFLINE candidate list (no Dijkstra feedback).
  * pairs: n_pairs x (newer, older) frame indices grouped by ascending newer frame, results aligned with them.  Per new frame:

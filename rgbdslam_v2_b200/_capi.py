@@ -147,6 +147,7 @@ def load_library(path: str | Path | None = None) -> C.CDLL:
     lib.rgbdslam_b200_allgather_slot_edges.argtypes = [u64, C.c_int, C.c_int, vp]
     lib.rgbdslam_b200_posegraph_optimize.argtypes = [C.c_int, vp, vp, C.c_int, vp, vp, vp, C.c_double, C.c_double,
                                                      C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.rgbdslam_b200_posegraph_reserve.argtypes = [C.c_int, C.c_int]
     lib.rgbdslam_b200_graph_from_pairs.argtypes = [C.c_int, C.c_int, vp, vp, C.c_double, vp, vp, vp, vp, vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.rgbdslam_b200_posegraph_chi2.argtypes = [C.c_int, vp, C.c_int, vp, vp, vp, C.c_double, C.POINTER(C.c_double), vp]
     lib.rgbdslam_b200_landmark_ba.argtypes = [C.c_int, vp, vp, C.c_int, vp, C.c_int, vp, vp, vp, vp, vp, C.c_int, vp, vp, vp, C.c_int,
@@ -535,6 +536,9 @@ class Frontend:
                                                        _ptr(uvd), _ptr(w3), _ptr(K), ne, _ptr(ij_), _ptr(meas_), _ptr(info_), iterations,
                                                        huber_delta, C.byref(c0), C.byref(c1), C.byref(it), C.byref(cg)))
         return x, pts, c0.value, c1.value, it.value, cg.value
+
+    def posegraph_reserve(self, nv: int, ne: int):
+        self._check(self.lib.rgbdslam_b200_posegraph_reserve(nv, ne))
 
     def graph_chi2(self, poses, ij, meas, info, huber_delta: float = 1.0, per_edge: bool = False):
         x = np.ascontiguousarray(poses, np.float64)

@@ -28,6 +28,17 @@ int rgbdslam_b200_posegraph_optimize(int nv, double* poses, const uint8_t* fixed
   return posegraph_optimize(nv, poses, fixed, ne, ij, meas, info, stop, huber_delta, chi2, iters, cg_iters, nullptr, true);
 }
 
+int rgbdslam_b200_posegraph_reserve(int nv, int ne) {
+  std::lock_guard<std::mutex> lk(g_state.mu);
+  int rc = check_inited();
+  if (rc) return rc;
+  if (nv < 0 || ne < 0) {
+    set_error("posegraph_reserve: negative size");
+    return RGBDSLAM_B200_ERR_ARG;
+  }
+  return posegraph_reserve(nv, ne);
+}
+
 int rgbdslam_b200_posegraph_chi2(int nv, const double* poses, int ne, const int32_t* ij, const double* meas,
                                  const double* info, double huber_delta, double* chi2, double* per_edge_chi2) {
   std::lock_guard<std::mutex> lk(g_state.mu);

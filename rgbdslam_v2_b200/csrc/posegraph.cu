@@ -950,6 +950,28 @@ static int pg_optimize(PgCtx& c, int iterations, int* done) {  // SparseOptimize
   return 0;
 }
 
+// grow-only device buffers of a solve with nv vertices and ne edges (rgbdslam_b200_posegraph_reserve: a caller that knows how
+// large its graph will get takes the allocations out of its first solve)
+static int pg_ensure(PgDevice& d, int nv, int ne) {
+  int rc;
+  const size_t nv_ = (size_t)(nv > 0 ? nv : 1), ne_ = (size_t)(ne > 0 ? ne : 1);
+  const int chi_blocks = (ne + 255) / 256 + 1, max_blocks = (nv + 2) / 3 + 1;
+  if ((rc = d.x.ensure(56 * nv_)) || (rc = d.xtrial.ensure(56 * nv_)) || (rc = d.meas.ensure(56 * ne_)) ||
+      (rc = d.info.ensure(288 * ne_)) || (rc = d.ij.ensure(8 * ne_)) || (rc = d.fixed.ensure(nv_)) ||
+      (rc = d.off.ensure(4 * (nv_ + 1))) || (rc = d.inc.ensure(8 * ne_)) || (rc = d.blk.ensure(8 * kEdgeBlk * ne_)) ||
+      (rc = d.Hd.ensure(288 * nv_)) || (rc = d.b.ensure(48 * nv_)) || (rc = d.Minv.ensure(288 * nv_)) ||
+      (rc = d.dx.ensure(48 * nv_)) || (rc = d.r.ensure(48 * nv_)) || (rc = d.d.ensure(48 * nv_)) ||
+      (rc = d.q.ensure(48 * nv_)) || (rc = d.sv.ensure(48 * nv_)) || (rc = d.oth.ensure(8 * ne_)) || (rc = d.result.ensure(128)) ||
+      (rc = d.chipart.ensure(16 * (size_t)chi_blocks)) || (rc = d.maxpart.ensure(8 * (size_t)max_blocks)) ||
+      (rc = d.per_edge.ensure(8 * ne_)) || (rc = d.incblk.ensure(288 * 2 * ne_)))
+    return rc;
+  return 0;
+}
+int posegraph_reserve(int nv, int ne) {
+  if (!g_pg_dev) g_pg_dev = new PgDevice();
+  return pg_ensure(*g_pg_dev, nv, ne);
+}
+
 int posegraph_optimize(int nv, double* poses, const uint8_t* fixed, int ne, const int32_t* ij, const double* meas,
                        const double* info, double stop, double huber_delta, double* chi2_out, int* iters_out,
                        int* cg_iters_out, double* per_edge_chi2, bool optimize) {
@@ -983,16 +1005,7 @@ int posegraph_optimize(int nv, double* poses, const uint8_t* fixed, int ne, cons
   }
   int rc;
   PgDevice& d = c.dev;
-  const size_t nv_ = (size_t)(nv > 0 ? nv : 1), ne_ = (size_t)(ne > 0 ? ne : 1);
-  const int chi_blocks = (ne + 255) / 256 + 1, max_blocks = (nv + 2) / 3 + 1;
-  if ((rc = d.x.ensure(56 * nv_)) || (rc = d.xtrial.ensure(56 * nv_)) || (rc = d.meas.ensure(56 * ne_)) ||
-      (rc = d.info.ensure(288 * ne_)) || (rc = d.ij.ensure(8 * ne_)) || (rc = d.fixed.ensure(nv_)) ||
-      (rc = d.off.ensure(4 * (nv_ + 1))) || (rc = d.inc.ensure(8 * ne_)) || (rc = d.blk.ensure(8 * kEdgeBlk * ne_)) ||
-      (rc = d.Hd.ensure(288 * nv_)) || (rc = d.b.ensure(48 * nv_)) || (rc = d.Minv.ensure(288 * nv_)) ||
-      (rc = d.dx.ensure(48 * nv_)) || (rc = d.r.ensure(48 * nv_)) || (rc = d.d.ensure(48 * nv_)) ||
-      (rc = d.q.ensure(48 * nv_)) || (rc = d.sv.ensure(48 * nv_)) || (rc = d.oth.ensure(8 * ne_)) || (rc = d.result.ensure(128)) || (rc = d.chipart.ensure(16 * (size_t)chi_blocks)) ||
-      (rc = d.maxpart.ensure(8 * (size_t)max_blocks)) || (rc = d.per_edge.ensure(8 * ne_)))
-    return rc;
+  if ((rc = pg_ensure(d, nv, ne))) return rc;
   // cooperative grid: all co-resident blocks of the PCG kernel
   int per_sm = 0;
   PG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pg_pcg_kernel, 512, 0));
@@ -1025,7 +1038,6 @@ int posegraph_optimize(int nv, double* poses, const uint8_t* fixed, int ne, cons
       PG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_res, pg_pcg_resident_kernel, kPgResWarps * 32, (size_t)c.res_smem));
       if (per_sm_res >= 1) {
         c.res_vpc = vpc;
-        if ((rc = d.incblk.ensure(288 * 2 * ne_))) return rc;
       }
     }
   }

@@ -9,6 +9,7 @@ int posegraph_optimize(int nv, double* poses, const uint8_t* fixed, int ne, cons
                        const double* info, double stop, double huber_delta, double* chi2_out, int* iters_out,
                        int* cg_iters_out, double* per_edge_chi2, bool optimize);
 void posegraph_release();
+int posegraph_reserve(int nv, int ne);  // pre-size the cached device buffers
 // pose-pose constraints for other solvers (landmark_ba.cu): per-edge normal-equation blocks [A 36 | B 36 | C 36 | gi 6 | gj 6]
 // (A = Ji'WJi, B = Jj'WJj, C = Ji'WJj, g = J'We, all scaled by the Huber weight), pose update X <- X * fromVectorMQT(d),
 // per-block partial sums of (robust, plain) chi2 (2 doubles per 256 edges)

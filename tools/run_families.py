@@ -1,7 +1,7 @@
 """One pass over every kernel family that has a SURVEY section-8 row (ORB node constructor, SIFT matchers, pose graph,
-EMM, pairwise refinement) -- the target of the ncu launch list / `--set full` captures under profiles/.
+landmark bundle adjustment, EMM, pairwise refinement) -- the target of the ncu launch list / `--set full` captures under profiles/.
 
-  python tools/run_families.py [orb] [sift] [posegraph] [emm] [refine]      (default: all)
+  python tools/run_families.py [orb] [sift] [posegraph] [landmark] [emm] [refine]      (default: all)
 Prints CUDA-event / wall times per family as one JSON line (NOT a bench value when run under ncu)."""
 import json
 import sys
@@ -14,7 +14,7 @@ import numpy as np
 from rgbdslam_v2_b200 import Frontend, synth
 from rgbdslam_v2_b200._capi import default_params
 
-which = set(sys.argv[1:]) or {"orb", "sift", "posegraph", "emm", "refine"}
+which = set(sys.argv[1:]) or {"orb", "sift", "posegraph", "landmark", "emm", "refine"}
 out = {}
 K4 = (synth.FX, synth.FY, synth.CX, synth.CY)
 
@@ -87,6 +87,20 @@ if "posegraph" in which:
         x, chi2, lm, cg = fe.optimize_graph(g["init"], g["fixed"], g["ij"], g["meas"], g["info"], stop=0.01)
         dt = time.perf_counter() - t0
     out["posegraph"] = {"seconds": dt, "lm": lm, "pcg": cg, "chi2": chi2}
+    fe.close()
+
+if "landmark" in which:
+    p = default_params(); p.depth_cov_z0 = 2.0
+    fe = Frontend(0, p)
+    d = synth.make_ba_problem(n_cams=60, n_points=6000, seed=11, edge_noise=0.02)
+    for it in range(2):
+        t0 = time.perf_counter()
+        x, pts, c0, c1, lm, cg = fe.landmark_ba(d["poses"], d["fixed"], d["points"], d["obs_cam"], d["obs_point"], d["obs_uvd"], d["obs_info3"],
+                                                d["K4"], ij=d["ij"], meas=d["meas"], info=d["info"], iterations=6)
+        dt = time.perf_counter() - t0
+    err = float(np.linalg.norm(x[:, :3] - d["gt_poses"][:, :3], axis=1).max())
+    out["landmark_ba"] = {"cams": len(x), "points": len(pts), "observations": int(len(d["obs_cam"])), "seconds": dt, "lm": lm, "pcg": cg,
+                          "chi2_before": c0, "chi2_after": c1, "max_cam_error_m": err}
     fe.close()
 
 if "emm" in which or "refine" in which:
