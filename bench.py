@@ -670,7 +670,22 @@ def run_ours(args, rank, local_rank, world):
         comm = fe.comm_init(rank, world, uid.cpu().numpy())
     # edge records of every step of a timed region, all-gathered ONCE at its end (north star: "a single NCCL all-gather of the
     # resulting SE(3) edges before the global solve"; round 1 gathered every step: 8 ranks then rendezvous every 0.15 ms)
-    local_edges = {"buf": None, "n": 0}
+    local_edges = {"buf": None, "n": 0, "pin_buf": None, "pin_all": None}
+
+    def pinned_records(n):
+        t = torch.empty(n * PAIR_RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+        return t, t.numpy().view(PAIR_RESULT_DTYPE)
+
+    def reserve_exchange(K):
+        """pinned host buffers for the region's edge records and their gathered union, and the communicator's device buffers at
+        their final size -- allocated once, outside the timed regions (a fresh 30 MB pageable array per region cost the 8-GPU
+        run a quarter of its timed region in page faults and a pageable device-to-host copy)"""
+        if comm is None:
+            return
+        local_edges["pin_buf"] = pinned_records(K * PAIRS_PER_GPU)
+        local_edges["pin_all"] = pinned_records(world * K * PAIRS_PER_GPU)
+        local_edges["pin_buf"][1][:] = np.zeros(1, PAIR_RESULT_DTYPE)
+        fe.allgather_edges(comm, local_edges["pin_buf"][1], world, out=local_edges["pin_all"][1])
 
     def submit_resident(k):
         st = sets[k % DEPTH]
@@ -693,7 +708,9 @@ def run_ours(args, rank, local_rank, world):
 
     def run_steps(submit, K):
         if comm is not None:
-            local_edges["buf"] = np.zeros(K * PAIRS_PER_GPU, PAIR_RESULT_DTYPE)
+            pin = local_edges["pin_buf"]
+            local_edges["buf"] = pin[1][:K * PAIRS_PER_GPU] if pin is not None and len(pin[1]) >= K * PAIRS_PER_GPU else \
+                np.zeros(K * PAIRS_PER_GPU, PAIR_RESULT_DTYPE)
             local_edges["n"] = 0
         for k in range(K):
             if k >= DEPTH:
@@ -702,7 +719,9 @@ def run_ours(args, rank, local_rank, world):
         for k in range(max(0, K - DEPTH), K):
             finish(k)
         if comm is not None:  # the one exchange: every rank ends up with every rank's edges of the whole region
-            local_edges["all"] = fe.allgather_edges(comm, local_edges["buf"], world)
+            pin = local_edges["pin_all"]
+            out = pin[1][:world * K * PAIRS_PER_GPU] if pin is not None and len(pin[1]) >= world * K * PAIRS_PER_GPU else None
+            local_edges["all"] = fe.allgather_edges(comm, local_edges["buf"], world, out=out)
 
     def barrier():
         torch.cuda.synchronize()
@@ -728,6 +747,7 @@ def run_ours(args, rank, local_rank, world):
         dist.all_reduce(probe, op=dist.ReduceOp.MAX)
     repeats = max(1, int(np.ceil(MIN_TIMED_MS * 1e-3 / (float(probe.item()) * args.steps))))
     timed_steps = args.steps * repeats
+    reserve_exchange(timed_steps)
     launches0 = fe.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
