@@ -86,3 +86,50 @@ def test_c5_size_properties(fe, oracle_mod):
     # idempotence: optimising the optimum again changes nothing measurable
     x2, chi2b, _, _ = fe.optimize_graph(x, g["fixed"], g["ij"], g["meas"], g["info"], stop=0.01)
     assert chi2b <= chi2 * (1 + 1e-9) and np.abs(x2[:, :3] - x[:, :3]).max() < 1e-4
+
+
+def _hub_graph(nv, seed):
+    """a chain with one hub vertex connected to every other vertex (degree nv - 1: more incidences than one CTA of the resident
+    solver can keep in shared memory) plus a few random loop closures"""
+    from rgbdslam_v2_b200 import synth
+    g = synth.make_pose_graph(nv, nv - 1, seed=seed)  # odometry chain only
+    rng = np.random.default_rng(seed)
+    gt = g["gt"]
+    hub = 3
+    ij, meas = [list(e) for e in g["ij"]], [m for m in g["meas"]]
+    others = [v for v in range(nv) if v != hub and abs(v - hub) > 1]
+    pairs = [(hub, v) if k % 2 == 0 else (v, hub) for k, v in enumerate(others)]  # the hub in both roles of an edge
+    pairs += [tuple(rng.choice(nv, 2, replace=False)) for _ in range(nv // 2)]
+    for i, j in pairs:
+        rel = synth.pose_compose(synth.pose_inverse(gt[i]), gt[j])
+        d = np.concatenate([rng.normal(0, 0.005, 3), rng.normal(0, 0.002, 3)])
+        rel = synth.pose_compose(rel, np.concatenate([d, [np.sqrt(1 - d[3:] @ d[3:])]]))
+        ij.append([int(i), int(j)]); meas.append(rel)
+    ne = len(ij)
+    info = np.tile((np.eye(6) * 200.0).reshape(1, 36), (ne, 1))
+    return dict(init=g["init"], fixed=g["fixed"], ij=np.array(ij, np.int32), meas=np.array(meas), info=info, gt=gt)
+
+
+def test_resident_solver_matches_general_kernel_on_hub_graph(fe, monkeypatch):
+    """700 vertices on 148 CTAs = 5 per CTA; the hub's 699 incidences exceed the 568 a CTA stages in shared memory, so the
+    resident kernel takes its global-memory path for the tail -- same solution as the general kernel (RB200_PG_RESIDENT=0)"""
+    g = _hub_graph(700, seed=5)
+    monkeypatch.setenv("RB200_PG_RESIDENT", "1")
+    x1, c1, it1, cg1 = fe.optimize_graph(g["init"], g["fixed"], g["ij"], g["meas"], g["info"], stop=0.01)
+    monkeypatch.setenv("RB200_PG_RESIDENT", "0")
+    x0, c0, it0, cg0 = fe.optimize_graph(g["init"], g["fixed"], g["ij"], g["meas"], g["info"], stop=0.01)
+    assert c1 == pytest.approx(c0, rel=1e-7)
+    assert abs(it1 - it0) <= 2
+    assert np.abs(x1[:, :3] - x0[:, :3]).max() < 1e-6
+    sgn = np.sign((x1[:, 3:] * x0[:, 3:]).sum(1))[:, None]
+    assert np.abs(x1[:, 3:] - sgn * x0[:, 3:]).max() < 1e-6
+    from rgbdslam_v2_b200 import synth
+    assert synth.ate_rmse(x1[:, :3], g["gt"][:, :3]) < 0.02
+
+
+def test_reserve_then_solve(fe):
+    from rgbdslam_v2_b200 import synth
+    fe.posegraph_reserve(3000, 40000)
+    g = synth.make_pose_graph(150, 600, seed=3)
+    x, chi2, it, cg = fe.optimize_graph(g["init"], g["fixed"], g["ij"], g["meas"], g["info"], stop=0.01)
+    assert np.isfinite(chi2) and it >= 1
