@@ -1,23 +1,18 @@
-// hamming_tc.cu -- Hamming N x M brute-force match on the 5th-gen tensor cores (tcgen05, sm_100a).
+// hamming_tc.cu -- brute-force descriptor matching on the 5th-gen tensor cores (tcgen05, sm_100a).
 //
 // bruteForceSearchORB (features.cpp:168-182) for all query rows of all pairs, exact:
-//   256-bit descriptors are expanded once per node to +-1 int8 vectors (bit set -> +1, clear -> -1).
-//   For two descriptors a, b:  a . b = 256 - 2 * hamming(a, b)   (exact in int32)
+//   for two 256-bit descriptors a, b read as +-1 vectors:  a . b = 256 - 2 * hamming(a, b)   (exact in int32)
 //   => argmin_j hd(q_i, t_j)  ==  argmax_j (Q T^T)_ij, ties -> lowest j  (features.cpp:176 strict <).
-// The N x M distance matrix is therefore an int8 GEMM with a row-arg-max epilogue:
-//   tcgen05.mma.kind::i8  M=128 (queries -> TMEM lanes)  N=256 (train rows -> TMEM columns)  K=32 x 8 steps,
-//   int32 accumulators in TMEM, double buffered (2 x 256 columns) so the epilogue of tile n overlaps the
-//   MMAs of tile n+1.
+// The N x M distance matrix is therefore an int8 GEMM with a row-arg-max epilogue: tcgen05.mma.kind::i8, M = 128 (queries ->
+// TMEM lanes), N = 128 (train rows -> TMEM columns), K = 32 per instruction, int32 accumulators in TMEM, double buffered so the
+// epilogue of tile n overlaps the MMAs of tile n+1.  Operand tiles use the UMMA canonical K-major no-swizzle shared-memory
+// layout in 128-row tiles of 32 KiB:  tile[row_group 16][k_chunk 16][row_in_group 8][16 B]  (conflict-free 8 x 16 B core matrices).
 //
-// Data movement: the expansion kernel writes each node's int8 matrix already in the UMMA canonical
-// K-major no-swizzle shared-memory layout, in 128-row tiles of 32 KiB:
-//     tile[row_group 16][k_chunk 16][row_in_group 8][16 B]
-// so a whole operand tile is ONE contiguous global block and is staged with a single
-// cp.async.bulk (TMA bulk copy, completes on an mbarrier).  No tensor map / swizzle is needed and the
-// MMA reads conflict-free 8x16 B core matrices.
-//
-// Two kernels: tc_match256_kernel (operand tiles resident in HBM, staged by cp.async.bulk: the float-descriptor matchers and the
-// legacy ORB path) and tc_hamming_expand_kernel (the default ORB path: descriptors expanded inside the kernel).
+// Two kernels:
+//  * tc_hamming_expand_kernel -- the ORB path: producer warps expand the 32-byte descriptors to +-64 operands straight into
+//    shared memory, a ninth k-step carries the column index, two MMA-issuing warps, VIMNMX3 epilogue (see its own header below);
+//  * tc_match256_kernel<1|2>  -- the float-descriptor matchers (bf16 RootSIFT scores / SiftGPU's u8 dot products): operand
+//    tiles resident in HBM in the layout above, each staged by ONE cp.async.bulk completing on an mbarrier.
 #include <cstdio>
 
 #include "kernels.h"
