@@ -148,11 +148,11 @@ class ClockSampler:
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE tc_hamming_expand_kernel launch on this workload, from the committed
-# `ncu --set full` capture: 16.46 MB read + 0 written (the 2 MB of results stay in L2 for the selection kernel) against 18.4 MB
+# `ncu --set full` capture: 16.48 MB read + 0 written (the 2 MB of results stay in L2 for the selection kernel) against 18.4 MB
 # algorithmic -- the kernel expands the 32-byte descriptors to MMA operands in shared memory itself.  (Round 1 read a resident
 # +-1 int8 expansion instead: 139.3 MB per launch, 7.6 x the algorithmic bytes.)
-NCU_DRAM_BYTES_PER_LAUNCH = 16464640
-NCU_TRAFFIC_SOURCE = "profiles/r2_v10_hamming_expand_ncu_full.txt (ncu --set full, 1 launch, C2 batch)"
+NCU_DRAM_BYTES_PER_LAUNCH = 16479744
+NCU_TRAFFIC_SOURCE = "profiles/r2_final_c2_kernels_ncu_full.txt (ncu --set full, 1 launch, C2 batch)"
 # tcgen05.mma.kind::i8 M128 N128 K32 issued back to back on all 148 SMs, no epilogue (tools/microbench/tc_peaks.cu on this pool's
 # B200s, profiles/r2_v7_tc_peaks.json): 64.0 cycles per MMA = 4514.7 TOP/s at the 1.86 GHz the SMs hold under that load
 INT8_MMA_MEASURED_TOPS = 4514.7
