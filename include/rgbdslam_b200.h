@@ -138,9 +138,8 @@ int rgbdslam_b200_set_stream(void* cuda_stream);
 int rgbdslam_b200_synchronize(void);
 
 /* Which kernel computes the Hamming brute-force stage: 0 = SIMT popcount kernel (cross-check); 1 (default) = tcgen05 kind::i8
- * tensor-core GEMM with arg-max epilogue, the 32-byte descriptors expanded to int8 operands inside the kernel; 2 = the same
- * GEMM reading +-1 operand tiles the nodes keep resident (8 x the descriptor bytes).  All are exact and give identical
- * results. */
+ * tensor-core GEMM with arg-max epilogue, the 32-byte descriptors expanded to int8 operands inside the kernel.  Both are exact
+ * and give identical results; other values are rejected. */
 int rgbdslam_b200_set_hamming_path(int path);
 
 const char* rgbdslam_b200_last_error(void);
@@ -249,8 +248,8 @@ int rgbdslam_b200_match_pairs_wait(int slot);
  * and of the whole device part of the last match_pairs* call. */
 int rgbdslam_b200_last_timing(float* hamming_ms, float* total_device_ms);
 int rgbdslam_b200_last_timing_slot(int slot, float* hamming_ms, float* total_device_ms);
-/* CUDA-event stage times (ms) of the last finished call on a slot: [0] host->device copies, [1] int8 expansion,
- * [2] Hamming kernel, [3] match selection + RANSAC, [4] device->host copies, [5] whole call on the stream. */
+/* CUDA-event stage times (ms) of the last finished call on a slot: [0] host->device copies, [1] float-descriptor operand
+ * preparation (0 for ORB: descriptors are expanded inside the match kernel), [2] Hamming kernel, [3] match selection + RANSAC, [4] device->host copies, [5] whole call on the stream. */
 int rgbdslam_b200_slot_stage_times(int slot, float* ms6);
 /* Pipeline diagnostics: timeline_epoch() marks t = 0 on the device; slot_timeline() returns, for the last finished
  * call on a slot, the device time (ms since the epoch) of [0] submit, [1] uploads done, [2] operand expansion done,
