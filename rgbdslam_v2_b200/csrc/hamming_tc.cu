@@ -254,12 +254,13 @@ __global__ void __launch_bounds__(kTc256Threads, 1) tc_match256_kernel(const Ham
       }
     }
   } else if (warp == 1) {
-    // The whole warp walks the pipeline and one elected lane issues the tcgen05 instructions.  Issuing from inside an
-    // `if (lane == 0)` region made the compiler wrap every UTCIMMA in an ELECT / BRA.U.ANY retry loop and rebuild both
-    // descriptors from the shared-memory address: ~13 dependent instructions = 82 cycles per MMA that needs 68 cycles of
-    // tensor time (in-kernel clock64 profile: the issuer waited on barriers only 15 % of the time, i.e. it WAS the bottleneck).
+    // The whole warp walks the pipeline and one elected lane issues the tcgen05 instructions (issuing from inside an
+    // `if (lane == 0)` region makes the compiler wrap every UTCIMMA in an ELECT / BRA.U.ANY retry loop: ~13 dependent
+    // instructions per MMA).  ONE issuer for both accumulator halves: the issuing thread runs only ~2 MMAs ahead of the tensor
+    // pipe (tc_hamming_expand_kernel uses one issuer per half for that reason); here the top-4 / runner-up epilogue, not the
+    // tensor pipe, bounds the kernel (10 % of the bf16 peak), so the simpler form stays.
     uint32_t sa = 0, pa = 0, sb = 0, pb = 0, acc = 0, pacc = 0;
-    constexpr uint32_t kIdesc = MODE == 0 ? kIdescI8_N128 : (MODE == 2 ? kIdescU8_N128 : kIdescBF16_N128);
+    constexpr uint32_t kIdesc = MODE == 2 ? kIdescU8_N128 : kIdescBF16_N128;
     for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
       const int n_btiles = items[it].n_btiles;
       RB200_TIMED_WAIT(pf_a, bar(kBarAFull + sa), pa)
@@ -298,7 +299,6 @@ __global__ void __launch_bounds__(kTc256Threads, 1) tc_match256_kernel(const Ham
     uint32_t acc = 0, pacc = 0;
     for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
       const HamItem item = items[it];
-      int best = kNoBest;
       float s0 = -3.0e38f, s1 = -3.0e38f, s2 = -3.0e38f, s3 = -3.0e38f;
       int i0 = -1, i1 = -1, i2 = -1, i3 = -1;
       long long u8_best = -1;  // MODE 2: (dot << 17) | (0x1FFFF - tie priority); -1 = no positive dot yet
@@ -313,19 +313,7 @@ __global__ void __launch_bounds__(kTc256Threads, 1) tc_match256_kernel(const Ham
           tc_ld32(t0 + c * 32, v);
           tc_wait_ld();
           const int col0 = nb * 128 + c * 32;
-          if (MODE == 0) {
-            // (a software-pipelined drain with the next tcgen05.ld in flight and 4 independent arg-max accumulators was
-            //  measured SLOWER: 63.5 vs 55.7 us -- the epilogue is not the critical path, the shared-memory operand
-            //  bandwidth of the M128 x N128 MMAs is; see tc_match_wide_kernel)
-            if (col0 + 32 <= item.nsearch) {
-#pragma unroll
-              for (int j = 0; j < 32; j++) best = max(best, (int)v[j] * 65536 + (65535 - (col0 + j)));
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; j++)
-                if (col0 + j < item.nsearch) best = max(best, (int)v[j] * 65536 + (65535 - (col0 + j)));
-            }
-          } else if (MODE == 2) {
+          if (MODE == 2) {
             // SiftGPU RowMatch / ColMatch bookkeeping (ProgramCU.cu:1708-1736, 1463-1478, 1771-1777): strict >, only
             // positive dots register, the runner-up VALUE counts duplicates of the maximum.
             // common case first: a dot product below the current best only feeds the runner-up value (one IMNMX); the 64-bit
@@ -392,15 +380,7 @@ __global__ void __launch_bounds__(kTc256Threads, 1) tc_match256_kernel(const Ham
         if (++acc == 2) { acc = 0; pacc ^= 1; }
       }
       if (row < item.nq_valid) {
-        if (MODE == 0) {
-          int2 o = make_int2(257, -1);
-          if (best != kNoBest) {
-            const int s = best >> 16;
-            o.x = (256 - s) >> 1;
-            o.y = 65535 - (best & 0xFFFF);
-          }
-          item.out[row] = o;
-        } else if (MODE == 2) {
+        if (MODE == 2) {
           int4 o = make_int4(0, -1, u8_next, 0);
           if (u8_best >= 0) {
             const int prio = 0x1FFFF - (int)(u8_best & 0x1FFFF);
@@ -415,7 +395,7 @@ __global__ void __launch_bounds__(kTc256Threads, 1) tc_match256_kernel(const Ham
     }
   }
 #ifdef RB200_PROFILE_TC
-  if (lane == 0 && MODE == 0) {
+  if (lane == 0 && MODE == 1) {
     const int role = warp == 0 ? 0 : (warp == 1 ? 1 : 2);
     atomicAdd(&g_tc_prof[role][0], (unsigned long long)pf_a);
     atomicAdd(&g_tc_prof[role][1], (unsigned long long)pf_b);
